@@ -1,0 +1,394 @@
+"""Inference API — host-side mirror of ``src/inference_engine.jl`` and ``src/dependencies.jl``.
+
+Same names, argument meaning and error behaviour as the reference; the work is done behind the
+C ABI (``include/cortex_b200.h``): graph ingestion through the 7 backend generics, dependency
+resolution, ``request_inference_for`` / ``scan_inference_request`` / ``update_marginals!``.
+Rules are *registered kernels keyed by factor type* (``RuleProcessor``) instead of Julia methods.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import time
+from dataclasses import dataclass, field
+from typing import Any, Dict, List, Optional, Sequence, Tuple
+
+import numpy as np
+
+from . import _capi as capi
+from .inference_signal import (IndividualMarginal, JointMarginal, MessageToFactor, MessageToVariable, NoRuleError,
+                               ProductOfMessages, Signal, SignalStore, get_value, get_variant, _ids)
+from .model_engine import (Connection, Factor, Variable, backend_get_connected_factor_ids,
+                           backend_get_connected_variable_ids, backend_get_connection, backend_get_factor,
+                           backend_get_factor_ids, backend_get_variable, backend_get_variable_ids,
+                           throw_if_engine_unsupported)
+
+
+# ---- dependency resolvers: src/dependencies.jl:1-3 -------------------------------------------------
+class AbstractDependencyResolver:
+    resolver_kind = capi.RESOLVER_NONE
+
+
+class DefaultDependencyResolver(AbstractDependencyResolver):
+    """Sum-product BP wiring incl. the >5-neighbour segment tree, src/dependencies.jl:17-173."""
+    resolver_kind = capi.RESOLVER_DEFAULT_BP
+
+
+class MeanFieldResolver(AbstractDependencyResolver):
+    """The weak-dependency resolver of test/inference_engine_tests.jl:597-621."""
+    resolver_kind = capi.RESOLVER_MEAN_FIELD
+
+
+# ---- request processors: src/inference_engine.jl:331 -----------------------------------------------
+class AbstractInferenceRequestProcessor:
+    value_dim = 1
+    family = capi.FAMILY_SUM
+    rules: Dict[Any, Tuple[int, Sequence[float]]] = {}
+
+
+class InferenceRequestScanner(AbstractInferenceRequestProcessor):
+    """Default processor of the reference constructor (src/inference_engine.jl:528-537): collects only."""
+
+
+class RuleProcessor(AbstractInferenceRequestProcessor):
+    """Rules registered by factor type (``Factor.functional_form``): ``{form: (CXB_RULE_*, params)}``.
+
+    Replaces user methods of compute_message_to_variable! (per factor type) and the
+    compute_message_to_factor! / compute_product_of_messages! / compute_individual_marginal!
+    family (``family`` = how values of this model multiply, CXB_FAMILY_*).
+    """
+
+    def __init__(self, rules: Dict[Any, Tuple[int, Sequence[float]]], family: int, value_dim: int):
+        self.rules = dict(rules)
+        self.family = family
+        self.value_dim = value_dim
+
+
+class CallbackProcessor(AbstractInferenceRequestProcessor):
+    """User-defined Python rules (oracle backend only: the device engine runs registered kernels).
+
+    Subclasses override the five compute_* methods with the reference signature
+    ``(engine, variant, signal, dependencies) -> value``.
+    """
+
+    def __init__(self, value_dim: int = 1):
+        self.value_dim = value_dim
+        self.family = capi.FAMILY_SUM
+
+    def _missing(self, name):
+        raise NoRuleError(f"The function `{name}` is not implemented for the processor of type {type(self).__name__}")
+
+    def compute_message_to_variable(self, engine, variant, signal, dependencies):
+        self._missing("compute_message_to_variable!")
+
+    def compute_message_to_factor(self, engine, variant, signal, dependencies):
+        self._missing("compute_message_to_factor!")
+
+    def compute_individual_marginal(self, engine, variant, signal, dependencies):
+        self._missing("compute_individual_marginal!")
+
+    def compute_product_of_messages(self, engine, variant, signal, dependencies):
+        self._missing("compute_product_of_messages!")
+
+    def compute_joint_marginal(self, engine, variant, signal, dependencies):
+        self._missing("compute_joint_marginal!")
+
+
+@dataclass
+class InferenceEngineWarning:  # src/inference_engine.jl:11-14
+    description: str
+    context: Any
+
+
+# ---- tracing: src/inference_engine.jl:650-754 ---------------------------------------------------------
+@dataclass
+class TracedInferenceExecution:
+    engine: Any
+    variable_id: Any
+    signal: Signal
+    total_time_in_ns: int
+    value_before_execution: Any
+    value_after_execution: Any
+
+
+@dataclass
+class TracedInferenceRound:
+    engine: Any
+    total_time_in_ns: int
+    executions: List[TracedInferenceExecution]
+
+
+@dataclass
+class TracedInferenceRequest:
+    engine: Any
+    total_time_in_ns: int
+    request: Any
+    rounds: List[TracedInferenceRound]
+
+
+@dataclass
+class InferenceEngineTracer:
+    inference_requests: List[TracedInferenceRequest] = field(default_factory=list)
+
+
+@dataclass
+class InferenceRequest:  # src/inference_engine.jl:265-270
+    engine: Any
+    variable_ids: Tuple[int, ...]
+    marginals: List[Signal]
+
+
+class InferenceEngine:
+    """InferenceEngine(; model_engine, dependency_resolver, inference_request_processor,
+    prepare_signals_metadata, resolve_dependencies, trace), src/inference_engine.jl:53-90."""
+
+    def __init__(self, *, model_engine, dependency_resolver=None, inference_request_processor=None,
+                 prepare_signals_metadata: bool = True, resolve_dependencies: bool = True, trace: bool = False,
+                 dtype: int = capi.F64, device: int = 0, api: Optional[capi.CApi] = None):
+        self.model_engine = throw_if_engine_unsupported(model_engine)
+        resolver = DefaultDependencyResolver() if dependency_resolver is None else dependency_resolver
+        processor = InferenceRequestScanner() if inference_request_processor is None else inference_request_processor
+        if not isinstance(resolver, AbstractDependencyResolver):  # convert(...) has no methods, :69
+            raise TypeError("dependency_resolver must be an AbstractDependencyResolver")
+        if not isinstance(processor, AbstractInferenceRequestProcessor):  # :70
+            raise TypeError("inference_request_processor must be an AbstractInferenceRequestProcessor")
+        self.dependency_resolver = resolver
+        self.inference_request_processor = processor
+        self.tracer = InferenceEngineTracer() if trace else None
+        self.warnings: List[InferenceEngineWarning] = []
+        self.api = api if api is not None else capi.default_api()
+        self.store = SignalStore(self.api, processor.value_dim, processor.family, dtype, device)
+        self._ingest()
+        self._register_rules()
+        if isinstance(processor, CallbackProcessor):
+            self._install_callback(processor)
+        if trace:
+            self.store.check(self.api.trace_enable(self.store.h, 1))
+        if resolve_dependencies:
+            self.store.check(self.api.resolve_dependencies(self.store.h, resolver.resolver_kind))
+            n = self.api.get_warnings(self.store.h, None, 0)
+            if n > 0:
+                buf = np.zeros(n, dtype=np.int64)
+                self.api.get_warnings(self.store.h, buf.ctypes.data_as(capi.i64p), n)
+                for v in buf:  # src/dependencies.jl:40-43
+                    self.warnings.append(InferenceEngineWarning("Variable has no connected factors", int(v)))
+
+    # -- graph ingestion through the 7 generics (src/model_engine.jl:329-391) ---------------------------
+    def _ingest(self):
+        me = self.model_engine
+        vids = [int(v) for v in backend_get_variable_ids(me)]
+        fids = [int(f) for f in backend_get_factor_ids(me)]
+        n_ids = (max(vids + fids) + 1) if (vids or fids) else 0
+        is_factor = np.zeros(max(n_ids, 1), dtype=np.uint8)
+        ftype = np.zeros(max(n_ids, 1), dtype=np.int32)
+        self._type_of_form: Dict[Any, int] = {}
+        for f in fids:
+            is_factor[f] = 1
+            form = backend_get_factor(me, f).functional_form
+            ftype[f] = self._type_of_form.setdefault(form, len(self._type_of_form))
+        edges = me.edges() if hasattr(me, "edges") else [
+            (int(v), f) for f in fids for v in backend_get_connected_variable_ids(me, f)]
+        ev = np.ascontiguousarray([e[0] for e in edges], dtype=np.int64)
+        ef = np.ascontiguousarray([e[1] for e in edges], dtype=np.int64)
+        st = self.store
+        st.check(self.api.graph_build(st.h, n_ids, is_factor.ctypes.data_as(capi.u8p),
+                                      ftype.ctypes.data_as(capi.i32p), len(edges),
+                                      ev.ctypes.data_as(capi.i64p), ef.ctypes.data_as(capi.i64p)))
+        self._variable_ids, self._factor_ids = vids, fids
+        for v in vids:  # bind the signal references (set_signals_variants!, :228-247, is done by graph_build)
+            var = backend_get_variable(me, v)
+            var.marginal = Signal(st, self.api.signal_id(st.h, capi.KIND_MARGINAL, v, -1))
+            var._engine, var._id = self, v
+            st._neighbours[v] = tuple(backend_get_connected_factor_ids(me, v))
+        for (v, f) in edges:
+            c = backend_get_connection(me, v, f)
+            c.message_to_variable = Signal(st, self.api.signal_id(st.h, capi.KIND_M2V, v, f))
+            c.message_to_factor = Signal(st, self.api.signal_id(st.h, capi.KIND_M2F, v, f))
+
+    def _register_rules(self):
+        st = self.store
+        for form, (kind, params) in getattr(self.inference_request_processor, "rules", {}).items():
+            if form not in self._type_of_form:
+                continue
+            p = np.ascontiguousarray(np.asarray(params, dtype=np.float64).ravel())
+            st.check(self.api.register_rule(st.h, self._type_of_form[form], int(kind),
+                                            p.ctypes.data_as(capi.f64p) if p.size else None, p.size))
+
+    def _install_callback(self, processor: CallbackProcessor):
+        if not hasattr(self.api, "set_rule_callback"):
+            raise NoRuleError("Python rule callbacks are not available on the device engine: register rule kernels "
+                              "by factor type (RuleProcessor)")
+        engine, st, dim = self, self.store, self.store.value_dim
+
+        def cb(_user, sid, kind, var, fac, ndeps, dep_ids, dep_values, out):
+            try:
+                signal = Signal(st, sid)
+                deps = [Signal(st, dep_ids[i]) for i in range(ndeps)]
+                variant = get_variant(signal)
+                fn = {capi.KIND_M2V: processor.compute_message_to_variable,
+                      capi.KIND_M2F: processor.compute_message_to_factor,
+                      capi.KIND_MARGINAL: processor.compute_individual_marginal,
+                      capi.KIND_PRODUCT: processor.compute_product_of_messages,
+                      capi.KIND_JOINT: processor.compute_joint_marginal}.get(kind)
+                if fn is None:
+                    raise NoRuleError(f"Unprocessed signal variant: {variant}")  # :506
+                val = np.atleast_1d(np.asarray(fn(engine, variant, signal, deps), dtype=np.float64)).ravel()
+                for k in range(dim):
+                    out[k] = val[k] if k < val.size else 0.0
+                return capi.OK
+            except NoRuleError as e:
+                self._callback_error = e
+                return capi.ERR_NO_RULE
+            except Exception as e:  # noqa: BLE001 - surfaced to the caller of update_marginals
+                self._callback_error = e
+                return capi.ERR_NO_RULE
+
+        self._callback_error = None
+        self._cb = capi.RULE_CB(cb)  # keep alive
+        st.check(self.api.set_rule_callback(st.h, self._cb, None))
+
+    def __repr__(self):  # src/inference_engine.jl:92-100
+        return f"InferenceEngine(trace = {'true' if self.tracer is not None else 'false'})"
+
+
+# ---- accessors, src/inference_engine.jl:119-205 ---------------------------------------------------------
+def get_model_engine(engine: InferenceEngine):
+    return engine.model_engine
+
+
+def get_inference_request_processor(engine: InferenceEngine):
+    return engine.inference_request_processor
+
+
+def get_trace(engine: InferenceEngine):
+    return engine.tracer
+
+
+def get_warnings(engine: InferenceEngine):
+    return engine.warnings
+
+
+def get_variable(engine: InferenceEngine, variable_id: int) -> Variable:
+    return backend_get_variable(engine.model_engine, variable_id)
+
+
+def get_variable_ids(engine: InferenceEngine):
+    return backend_get_variable_ids(engine.model_engine)
+
+
+def get_factor(engine: InferenceEngine, factor_id: int) -> Factor:
+    return backend_get_factor(engine.model_engine, factor_id)
+
+
+def get_factor_ids(engine: InferenceEngine):
+    return backend_get_factor_ids(engine.model_engine)
+
+
+def get_connection(engine: InferenceEngine, variable_id: int, factor_id: int) -> Connection:
+    return backend_get_connection(engine.model_engine, variable_id, factor_id)
+
+
+def get_connection_message_to_variable(engine_or_connection, variable_id=None, factor_id=None) -> Signal:
+    if isinstance(engine_or_connection, Connection):
+        return engine_or_connection.message_to_variable
+    return get_connection(engine_or_connection, variable_id, factor_id).message_to_variable
+
+
+def get_connection_message_to_factor(engine_or_connection, variable_id=None, factor_id=None) -> Signal:
+    if isinstance(engine_or_connection, Connection):
+        return engine_or_connection.message_to_factor
+    return get_connection(engine_or_connection, variable_id, factor_id).message_to_factor
+
+
+def get_connected_variable_ids(engine: InferenceEngine, factor_id: int):
+    return backend_get_connected_variable_ids(engine.model_engine, factor_id)
+
+
+def get_connected_factor_ids(engine: InferenceEngine, variable_id: int):
+    return backend_get_connected_factor_ids(engine.model_engine, variable_id)
+
+
+def link_signal_to_variable(variable: Variable, signal: Signal) -> None:
+    """link_signal_to_variable!(variable, signal), src/model_engine.jl:80-83."""
+    variable.linked_signals.append(signal)
+    eng = getattr(variable, "_engine", None)
+    if eng is None:
+        raise RuntimeError("link_signal_to_variable!: the variable is not bound to an InferenceEngine yet")
+    eng.store.check(eng.api.link_signal(eng.store.h, variable._id, signal.sid))
+
+
+def _as_ids(variable_id_or_ids) -> Tuple[int, ...]:
+    if isinstance(variable_id_or_ids, (list, tuple, np.ndarray)):
+        return tuple(int(v) for v in variable_id_or_ids)
+    return (int(variable_id_or_ids),)
+
+
+def request_inference_for(engine: InferenceEngine, variable_id_or_ids) -> InferenceRequest:
+    """request_inference_for(engine, ids), src/inference_engine.jl:294-323."""
+    ids = _as_ids(variable_id_or_ids)
+    arr, p = _ids(ids)
+    engine.store.check(engine.api.request_inference(engine.store.h, len(ids), p))
+    return InferenceRequest(engine, ids, [get_variable(engine, v).marginal for v in ids])
+
+
+def scan_inference_request(request: InferenceRequest, order: str = "id") -> List[Signal]:
+    """scan_inference_request(request), src/inference_engine.jl:540-546.
+
+    ``order="id"``: pending signals in ascending signal id, de-duplicated (device and oracle);
+    ``order="dfs"``: the reference's literal DFS visit order (oracle only).
+    """
+    eng = request.engine
+    fn = eng.api.scan if order == "id" else eng.api.scan_dfs
+    n = fn(eng.store.h, None, 0)
+    if n < 0:
+        eng.store.check(capi.ERR_STATE)
+    buf = np.zeros(max(n, 1), dtype=np.int64)
+    # scanning is idempotent (is_pending only caches), so the sizing call above is harmless
+    n = fn(eng.store.h, buf.ctypes.data_as(capi.i64p), n)
+    return [Signal(eng.store, s) for s in buf[:n]]
+
+
+def update_marginals(engine: InferenceEngine, variable_id_or_ids, schedule: str = "lvl") -> capi.UpdateStats:
+    """update_marginals!(engine, ids), src/inference_engine.jl:553-632.
+
+    ``schedule="lvl"``: the level-synchronous schedule the device runs;
+    ``schedule="seq"``: the reference's sequential in-place schedule (oracle backend only).
+    Returns the per-call statistics (the reference returns ``nothing``).
+    """
+    ids = _as_ids(variable_id_or_ids)
+    arr, p = _ids(ids)
+    stats = capi.UpdateStats()
+    fn = engine.api.update_marginals if schedule == "lvl" else engine.api.update_marginals_seq
+    engine._callback_error = None
+    t0 = time.perf_counter_ns()
+    status = fn(engine.store.h, len(ids), p, C.byref(stats))
+    t1 = time.perf_counter_ns()
+    if status != capi.OK and getattr(engine, "_callback_error", None) is not None:
+        raise engine._callback_error
+    engine.store.check(status)
+    if engine.tracer is not None:
+        engine.tracer.inference_requests.append(_collect_trace(engine, ids, t1 - t0))
+    return stats
+
+
+def _collect_trace(engine: InferenceEngine, ids, total_ns: int) -> TracedInferenceRequest:
+    n = engine.api.trace_get(engine.store.h, None, None, 0)
+    lv = np.zeros(max(n, 1), dtype=np.int64)
+    sg = np.zeros(max(n, 1), dtype=np.int64)
+    engine.api.trace_get(engine.store.h, lv.ctypes.data_as(capi.i64p), sg.ctypes.data_as(capi.i64p), n)
+    var = None
+    if hasattr(engine.api, "trace_get_variables"):
+        var = np.zeros(max(n, 1), dtype=np.int64)
+        engine.api.trace_get_variables(engine.store.h, var.ctypes.data_as(capi.i64p), n)
+    rounds: List[TracedInferenceRound] = []
+    cur_key, cur = None, None
+    for k in range(n):
+        key = int(lv[k]) if lv[k] >= 0 else -1  # the final phase (marginals, then linked signals) is ONE round, :610-628
+        if key != cur_key:
+            cur = TracedInferenceRound(engine, max(total_ns // max(n, 1), 1), [])
+            rounds.append(cur)  # only rounds with >= 1 execution are recorded, :818
+            cur_key = key
+        s = Signal(engine.store, int(sg[k]))
+        variant = get_variant(s)
+        vid = int(var[k]) if var is not None else getattr(variant, "variable_id", None)
+        cur.executions.append(TracedInferenceExecution(engine, vid, s, max(total_ns // max(n, 1), 1), None, get_value(s)))
+    return TracedInferenceRequest(engine, max(total_ns, 1), InferenceRequest(engine, tuple(ids), []), rounds)

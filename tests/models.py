@@ -1,0 +1,203 @@
+"""Model builders shared by the tests, bench.py's CPU leg and smoke(): the reference's own test models
+(test/inference_engine_tests.jl) and the benchmark graph families of BASELINE.json at reduced size."""
+from __future__ import annotations
+
+import numpy as np
+
+from tests._pkg import pkg
+
+C = pkg
+cap = pkg.capi
+
+
+def make_ssm_model(n, api, *, form="canon", dtype=cap.F64, q=1.0, r=1.0, resolver=None, processor=None, trace=False):
+    """test/inference_engine_tests.jl:436-462: x_i, y_i, likelihood_i (y_i, x_i), transition_i (x_i, x_{i+1})."""
+    g = C.BipartiteFactorGraph()
+    x = [g.add_variable(C.Variable(name="x", index=(i,))) for i in range(n)]
+    y = [g.add_variable(C.Variable(name="y", index=(i,))) for i in range(n)]
+    lik = [g.add_factor(C.Factor(functional_form="likelihood")) for _ in range(n)]
+    tr = [g.add_factor(C.Factor(functional_form="transition")) for _ in range(n - 1)]
+    for i in range(n):
+        g.add_edge(y[i], lik[i], C.Connection(label="out"))
+        g.add_edge(x[i], lik[i], C.Connection(label="out"))
+    for i in range(n - 1):
+        g.add_edge(x[i], tr[i], C.Connection(label="out"))
+        g.add_edge(x[i + 1], tr[i], C.Connection(label="in"))
+    if processor is None:
+        if form == "canon":
+            processor = C.RuleProcessor({"likelihood": (cap.RULE_GAUSS_OBS, [r]), "transition": (cap.RULE_GAUSS_RW, [q])},
+                                        family=cap.FAMILY_GAUSS_CANON, value_dim=2)
+        else:  # the reference fixture's own moment form
+            processor = C.RuleProcessor({"likelihood": (cap.RULE_GAUSS_MV_OBS, [r]), "transition": (cap.RULE_GAUSS_MV_RW, [q])},
+                                        family=cap.FAMILY_GAUSS_MV, value_dim=2)
+    engine = C.InferenceEngine(model_engine=g, dependency_resolver=resolver or C.DefaultDependencyResolver(),
+                               inference_request_processor=processor, dtype=dtype, api=api, trace=trace)
+    return engine, x, y, lik, tr
+
+
+def ssm_set_data(engine, y, lik, data):
+    sigs = [C.get_connection_message_to_factor(engine, y[i], lik[i]) for i in range(len(y))]
+    C.set_values(sigs, np.asarray(data, dtype=np.float64).reshape(-1, 1))
+
+
+def make_beta_bernoulli_model(n, api, dtype=cap.F64):
+    """test/inference_engine_tests.jl:316-341."""
+    g = C.BipartiteFactorGraph()
+    p = g.add_variable(C.Variable(name="p"))
+    o, f = [], []
+    for i in range(n):
+        oi = g.add_variable(C.Variable(name="o", index=(i,)))
+        fi = g.add_factor(C.Factor(functional_form="bernoulli"))
+        o.append(oi)
+        f.append(fi)
+        g.add_edge(p, fi, C.Connection(label="out"))
+        g.add_edge(oi, fi, C.Connection(label="out"))
+    proc = C.RuleProcessor({"bernoulli": (cap.RULE_BETA_BERNOULLI, [])}, family=cap.FAMILY_BETA, value_dim=2)
+    engine = C.InferenceEngine(model_engine=g, dependency_resolver=C.DefaultDependencyResolver(),
+                               inference_request_processor=proc, dtype=dtype, api=api)
+    return engine, p, o, f
+
+
+def potts_table(K, beta):
+    return np.exp(beta * np.eye(K))
+
+
+def make_grid_model(H, W, K, beta, api, dtype=cap.F64, rule="potts", link=True):
+    """BASELINE config 4 at reduced size: pixels row-major, one unary leaf factor per pixel, pairwise factors
+    on the 4-neighbourhood (horizontal edges then vertical, ascending ids), protocol B linked signals."""
+    g = C.BipartiteFactorGraph()
+    pix = [[g.add_variable(C.Variable(name="s", index=(i, j))) for j in range(W)] for i in range(H)]
+    un = [[g.add_factor(C.Factor(functional_form="unary")) for j in range(W)] for i in range(H)]
+    for i in range(H):
+        for j in range(W):
+            g.add_edge(pix[i][j], un[i][j], C.Connection(label="out"))
+    pair = []
+    for i in range(H):
+        for j in range(W):
+            if j + 1 < W:
+                f = g.add_factor(C.Factor(functional_form="pair"))
+                g.add_edge(pix[i][j], f, C.Connection(label="a"))
+                g.add_edge(pix[i][j + 1], f, C.Connection(label="b"))
+                pair.append((f, pix[i][j], pix[i][j + 1]))
+            if i + 1 < H:
+                f = g.add_factor(C.Factor(functional_form="pair"))
+                g.add_edge(pix[i][j], f, C.Connection(label="a"))
+                g.add_edge(pix[i + 1][j], f, C.Connection(label="b"))
+                pair.append((f, pix[i][j], pix[i + 1][j]))
+    if rule == "potts":
+        rules = {"pair": (cap.RULE_POTTS, [beta])}
+    else:
+        rules = {"pair": (cap.RULE_CAT_TABLE, potts_table(K, beta).ravel())}
+    proc = C.RuleProcessor(rules, family=cap.FAMILY_CATEGORICAL, value_dim=K)
+    engine = C.InferenceEngine(model_engine=g, dependency_resolver=C.DefaultDependencyResolver(),
+                               inference_request_processor=proc, dtype=dtype, api=api)
+    if link:
+        protocol_b_link(engine, [v for row in pix for v in row])
+    return engine, pix, un, pair
+
+
+def protocol_b_link(engine, variable_ids):
+    """link every non-leaf m2f(v,f) to its variable."""
+    for v in variable_ids:
+        var = C.get_variable(engine, v)
+        for f in C.get_connected_factor_ids(engine, v):
+            if len(C.get_connected_variable_ids(engine, f)) > 1:
+                C.link_signal_to_variable(var, C.get_connection_message_to_factor(engine, v, f))
+
+
+def protocol_b_init(engine, variable_ids, K):
+    sigs = []
+    for v in variable_ids:
+        for f in C.get_connected_factor_ids(engine, v):
+            if len(C.get_connected_variable_ids(engine, f)) > 1:
+                sigs.append(C.get_connection_message_to_factor(engine, v, f))
+    C.set_values(sigs, np.full((len(sigs), K), 1.0 / K))
+
+
+def protocol_b_sweep(engine, variable_ids, unary_signals, unary_values, schedule="lvl"):
+    """Re-assert the evidence, then one update_marginals!(engine, all) (Appendix B step 2)."""
+    C.set_values(unary_signals, unary_values)
+    return C.update_marginals(engine, variable_ids, schedule=schedule)
+
+
+def chung_lu_edges(n, m, alpha=2.5, seed=1234):
+    """BASELINE config 5 generator: weights w_i ∝ (i+10)^(-1/(alpha-1)); m distinct pairs, no self loops,
+    returned sorted so that factor ids ascend with (u, v)."""
+    rng = np.random.Generator(np.random.PCG64(seed))
+    w = (np.arange(n) + 10.0) ** (-1.0 / (alpha - 1.0))
+    p = w / w.sum()
+    pairs = set()
+    while len(pairs) < m:
+        need = m - len(pairs)
+        a = rng.choice(n, size=2 * need + 16, p=p)
+        b = rng.choice(n, size=2 * need + 16, p=p)
+        for u, v in zip(a, b):
+            if u != v:
+                pairs.add((min(u, v), max(u, v)))
+                if len(pairs) == m:
+                    break
+    return sorted((int(u), int(v)) for u, v in pairs)
+
+
+def make_powerlaw_model(n, m, K, api, dtype=cap.F64, n_tables=16, seed=1234, link=True):
+    rng = np.random.Generator(np.random.PCG64(seed + 1))
+    edges = chung_lu_edges(n, m, seed=seed)
+    tables = np.exp(rng.standard_normal((n_tables, K, K)))
+    ttype = rng.integers(0, n_tables, size=len(edges))
+    g = C.BipartiteFactorGraph()
+    vs = [g.add_variable(C.Variable(name="v", index=(i,))) for i in range(n)]
+    un = [g.add_factor(C.Factor(functional_form="unary")) for _ in range(n)]
+    for i in range(n):
+        g.add_edge(vs[i], un[i], C.Connection(label="out"))
+    pair = []
+    for (u, v), t in zip(edges, ttype):
+        f = g.add_factor(C.Factor(functional_form=f"pair{int(t)}"))
+        g.add_edge(vs[u], f, C.Connection(label="a"))
+        g.add_edge(vs[v], f, C.Connection(label="b"))
+        pair.append((f, vs[u], vs[v]))
+    rules = {f"pair{t}": (cap.RULE_CAT_TABLE, tables[t].ravel()) for t in range(n_tables)}
+    proc = C.RuleProcessor(rules, family=cap.FAMILY_CATEGORICAL, value_dim=K)
+    engine = C.InferenceEngine(model_engine=g, dependency_resolver=C.DefaultDependencyResolver(),
+                               inference_request_processor=proc, dtype=dtype, api=api)
+    if link:
+        protocol_b_link(engine, vs)
+    unary = rng.dirichlet(np.ones(K), size=n)
+    return engine, vs, un, pair, unary, tables, ttype
+
+
+def engine_state(engine):
+    """Observable state of every signal: (is_computed, is_pending, nibbles, value) — for seq-vs-lvl and
+    oracle-vs-device comparisons. NOTE: evaluates is_pending (lazy cache) on every signal."""
+    st = engine.store
+    out = []
+    for s in range(st.n_signals()):
+        sig = C.Signal(st, s)
+        out.append((C.is_computed(sig), C.is_pending(sig), tuple(C.get_dependency_props(sig))))
+    ids = [C.Signal(st, s) for s in range(st.n_signals())]
+    vals = C.get_values(ids) if ids else np.zeros((0, st.value_dim))
+    return out, vals
+
+
+def canon_to_mv(v):
+    v = np.asarray(v, dtype=np.float64)
+    return np.stack([v[..., 1] / v[..., 0], 1.0 / v[..., 0]], axis=-1)
+
+
+def rts_smoother(y, q, r):
+    """Independent numpy Kalman filter + RTS smoother for the random-walk model with a flat prior on x_1
+    (returns means, variances) — cross-check that does not share code with the oracle."""
+    T = len(y)
+    mf, Pf = np.zeros(T), np.zeros(T)
+    mf[0], Pf[0] = y[0], r
+    for t in range(1, T):
+        mp, Pp = mf[t - 1], Pf[t - 1] + q
+        k = Pp / (Pp + r)
+        mf[t] = mp + k * (y[t] - mp)
+        Pf[t] = (1 - k) * Pp
+    ms, Ps = mf.copy(), Pf.copy()
+    for t in range(T - 2, -1, -1):
+        Pp = Pf[t] + q
+        g = Pf[t] / Pp
+        ms[t] = mf[t] + g * (ms[t + 1] - mf[t])
+        Ps[t] = Pf[t] + g * g * (Ps[t + 1] - Pp)
+    return ms, Ps

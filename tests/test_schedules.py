@@ -1,0 +1,154 @@
+"""The level-synchronous schedule (what the device runs) must equal the reference's
+sequential in-place schedule (src/inference_engine.jl:559-632) on every benchmark graph family:
+same executed multiset, bit-identical values, same observable end state."""
+from collections import Counter
+
+import numpy as np
+import pytest
+
+from tests._pkg import pkg
+from tests import models
+
+C = pkg
+cap = pkg.capi
+
+
+def _trace(engine):
+    n = engine.api.trace_get(engine.store.h, None, None, 0)
+    lv = np.zeros(max(n, 1), dtype=np.int64)
+    sg = np.zeros(max(n, 1), dtype=np.int64)
+    engine.api.trace_get(engine.store.h, lv.ctypes.data_as(cap.i64p), sg.ctypes.data_as(cap.i64p), n)
+    return lv[:n], sg[:n]
+
+
+def _same_state(e1, e2):
+    s1, v1 = models.engine_state(e1)
+    s2, v2 = models.engine_state(e2)
+    assert s1 == s2
+    assert np.array_equal(v1, v2)
+
+
+def test_chain_seq_equals_lvl(oracle_api):
+    T = 200
+    data = np.cumsum(np.random.Generator(np.random.PCG64(1234)).standard_normal(T))
+    engines = []
+    for sched in ("seq", "lvl"):
+        e, x, y, lik, tr = models.make_ssm_model(T, oracle_api, form="canon", q=0.7, r=1.3)
+        models.ssm_set_data(e, y, lik, data)
+        st = C.update_marginals(e, x, schedule=sched)
+        assert st.updates == 6 * T - 4
+        engines.append((e, st, _trace(e)))
+    (e1, st1, (lv1, sg1)), (e2, st2, (lv2, sg2)) = engines
+    assert Counter(sg1.tolist()) == Counter(sg2.tolist())
+    assert st1.levels == 2  # two productive rounds
+    assert st2.levels == 2 * T - 1
+    widths = Counter(lv2[lv2 >= 0].tolist())
+    assert widths[0] == T and all(widths[k] == 2 for k in range(1, 2 * T - 1))
+    _same_state(e1, e2)
+    # a second request on the already-updated model does nothing in either schedule
+    for e, *_ in engines:
+        pass
+    assert C.update_marginals(e1, list(range(T)), schedule="seq").updates == 0
+    assert C.update_marginals(e2, list(range(T)), schedule="lvl").updates == 0
+
+
+def _sync_bp_reference(H, W, K, unary, psi, sweeps):
+    """Independent dense numpy flooding BP on a grid (no shared code with the oracle)."""
+    # messages m[(i,j) -> (k,l)] initialised uniform
+    nbrs = lambda i, j: [(a, b) for a, b in ((i - 1, j), (i + 1, j), (i, j - 1), (i, j + 1)) if 0 <= a < H and 0 <= b < W]
+    v2f = {((i, j), n): np.full(K, 1.0 / K) for i in range(H) for j in range(W) for n in nbrs(i, j)}
+    marg = np.zeros((H, W, K))
+    for _ in range(sweeps):
+        f2v = {}
+        for (src, dst), m in v2f.items():  # factor (src,dst) sends to dst
+            out = psi.T @ m if src < dst else psi @ m
+            f2v[(src, dst)] = out / out.sum()
+        new = {}
+        for i in range(H):
+            for j in range(W):
+                inc = {n: f2v[(n, (i, j))] for n in nbrs(i, j)}
+                b = unary[i, j].copy()
+                for n in sorted(inc):
+                    b = b * inc[n]
+                marg[i, j] = b / b.sum()
+                for n in inc:
+                    o = unary[i, j].copy()
+                    for n2 in sorted(inc):
+                        if n2 != n:
+                            o = o * inc[n2]
+                    new[((i, j), n)] = o / o.sum()
+        v2f = new
+    return marg
+
+
+@pytest.mark.parametrize("rule", ["potts", "table"])
+def test_grid_protocol_b_seq_equals_lvl_equals_flooding(oracle_api, rule):
+    H, W, K, beta, sweeps = 4, 5, 3, 0.7, 5
+    rng = np.random.Generator(np.random.PCG64(1234))
+    unary = rng.dirichlet(np.ones(K), size=(H, W))
+    res = []
+    for sched in ("seq", "lvl"):
+        e, pix, un, pair = models.make_grid_model(H, W, K, beta, oracle_api, rule=rule)
+        vids = [v for row in pix for v in row]
+        models.protocol_b_init(e, vids, K)
+        usig = [C.get_connection_message_to_variable(e, pix[i][j], un[i][j]) for i in range(H) for j in range(W)]
+        for s in range(sweeps):
+            st = models.protocol_b_sweep(e, vids, usig, unary.reshape(-1, K), schedule=sched)
+            n_pair_conn = 2 * len(pair)
+            assert st.updates == 2 * n_pair_conn + H * W  # m2v + m2f + marginals, every sweep (Appendix B)
+            assert st.final_marginals == H * W and st.final_linked == n_pair_conn
+            if sched == "lvl":
+                assert st.levels == 1
+        res.append(e)
+    _same_state(res[0], res[1])
+    got = C.get_values([C.get_variable_marginal(C.get_variable(res[1], v)) for v in vids]).reshape(H, W, K)
+    want = _sync_bp_reference(H, W, K, unary, models.potts_table(K, beta), sweeps)
+    np.testing.assert_allclose(got, want, rtol=1e-12, atol=0)
+
+
+def test_powerlaw_with_segment_trees_seq_equals_lvl(oracle_api):
+    n, m, K, sweeps = 60, 150, 4, 4
+    res, stats = [], []
+    for sched in ("seq", "lvl"):
+        e, vs, un, pair, unary, tables, ttype = models.make_powerlaw_model(n, m, K, oracle_api)
+        models.protocol_b_init(e, vs, K)
+        usig = [C.get_connection_message_to_variable(e, vs[i], un[i]) for i in range(n)]
+        for s in range(sweeps):
+            st = models.protocol_b_sweep(e, vs, usig, unary, schedule=sched)
+        res.append(e)
+        stats.append((st, _trace(e)))
+    degs = [len(C.get_connected_factor_ids(res[0], v)) for v in vs]
+    assert max(degs) > 5  # hubs use the segment tree
+    n_prod = sum(d - 2 for d in degs if d > 5)
+    (st1, (lv1, sg1)), (st2, (lv2, sg2)) = stats
+    assert st1.updates == st2.updates == 4 * m + n + n_prod
+    assert Counter(sg1.tolist()) == Counter(sg2.tolist())
+    assert max(Counter(sg2.tolist()).values()) == 1  # every signal executed exactly once per sweep
+    assert st2.levels > 1  # one level per product-tree height
+    _same_state(res[0], res[1])
+
+
+def test_naive_loopy_protocol_is_out_of_contract_or_equal(oracle_api):
+    """Appendix B 'naive protocol': call 2 is Gauss-Seidel in the reference. The level-synchronous
+    schedule must either reproduce it exactly or refuse (CXB_ERR_OUT_OF_CONTRACT) — never silently differ."""
+    H, W, K = 3, 3, 3
+    rng = np.random.Generator(np.random.PCG64(5))
+    unary = rng.dirichlet(np.ones(K), size=(H, W))
+    engines = []
+    for sched in ("seq", "lvl"):
+        e, pix, un, pair = models.make_grid_model(H, W, K, 0.5, oracle_api, link=False)
+        vids = [v for row in pix for v in row]
+        models.protocol_b_init(e, vids, K)
+        usig = [C.get_connection_message_to_variable(e, pix[i][j], un[i][j]) for i in range(H) for j in range(W)]
+        C.set_values(usig, unary.reshape(-1, K))
+        C.update_marginals(e, vids, schedule=sched)
+        engines.append((e, vids))
+    _same_state(engines[0][0], engines[1][0])  # call 1 is synchronous in both
+    e_seq, vids = engines[0]
+    e_lvl, _ = engines[1]
+    C.update_marginals(e_seq, vids, schedule="seq")
+    try:
+        C.update_marginals(e_lvl, vids, schedule="lvl")
+    except C.OutOfContractError:
+        return
+    _same_state(e_seq, e_lvl)
