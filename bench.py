@@ -1,0 +1,600 @@
+#!/usr/bin/env python
+"""bench.py — message-updates/sec of the update_marginals! hot path on B200 (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload gauss_chains|potts_grid|hmm64|powerlaw|chain1k]
+    python bench.py --impl reference ...     # the CPU oracle port of the reference, on the host cores
+
+One "step" = one pass of the hot path over one batch of synthetic input:
+  gauss_chains (default, BASELINE configs[1]): update_marginals! over 65,536 chains x T=1,024 (fp32);
+  potts_grid  (configs[3]): one synchronous sweep of the 8192^2, K=16 grid, row-sharded over N GPUs;
+  hmm64       (configs[2], K=64): scaled forward-backward of 1,024 HMMs x T (see --hmm-steps);
+  powerlaw    (configs[4]): one protocol-B sweep of the generic CSR engine on a Chung-Lu graph;
+  chain1k     (configs[0]): update_marginals! on one T=1,000 chain through the generic engine (latency).
+Prints ONE JSON line (rank 0). Nothing here reads /root/reference.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+import __graft_entry__ as entry  # noqa: E402
+
+METRIC, UNIT = "message_updates_per_sec", "updates/s"
+
+
+def measured_peaks():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        d = json.loads(p.read_text())
+        return float(d.get("hbm_gbs", 6650.0)), "measured (MEASURED_PEAKS.json)", d
+    return 6650.0, "fallback (B200_PROFILING.md)", {}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device_index):
+        self.idx, self.rows, self.proc = device_index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.idx)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1]))
+                mx = float(r[2])
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                pass
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ---------------------------------------------------------------------------------------------------------------
+def dist_setup(n_gpus):
+    import torch
+    import torch.distributed as dist
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    return rank, world, local
+
+
+def barrier(world):
+    import torch
+    import torch.distributed as dist
+
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+
+
+def max_over_ranks(x, world, local):
+    import torch
+    import torch.distributed as dist
+
+    if world == 1:
+        return x
+    t = torch.tensor([x], dtype=torch.float64, device=f"cuda:{local}")
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def sum_over_ranks(x, world, local):
+    import torch
+    import torch.distributed as dist
+
+    if world == 1:
+        return x
+    t = torch.tensor([x], dtype=torch.float64, device=f"cuda:{local}")
+    dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    return float(t.item())
+
+
+class DevArr:
+    def __init__(self, ptr, n, typestr="<f4"):
+        self.__cuda_array_interface__ = {"shape": (n,), "typestr": typestr, "data": (int(ptr), False), "version": 2}
+
+
+def timed(stream_ptr, fn, steps, warmup, world, local):
+    """W warm-up + K timed steps on the library's stream; returns (elapsed_ms max over ranks)."""
+    import torch
+
+    ext = torch.cuda.ExternalStream(stream_ptr, device=local)
+    for _ in range(warmup):
+        fn()
+    ext.synchronize()
+    barrier(world)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(ext)
+    for _ in range(steps):
+        fn()
+    e1.record(ext)
+    e1.synchronize()
+    barrier(world)
+    return max_over_ranks(e0.elapsed_time(e1), world, local)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+def cpu_baseline_chain(T=1024, budget_s=12.0):
+    """The reference CPU path = oracle port (explicit Signal graph, sequential update_marginals!), 1 core."""
+    from tests import models
+    from tests._pkg import ORACLE_LIB, pkg
+
+    api = pkg.CApi(ORACLE_LIB, "cxo_")
+    rng = np.random.Generator(np.random.PCG64(1234))
+    e, x, y, lik, tr = models.make_ssm_model(T, api, form="canon", q=1.0, r=1.0)
+    data = np.cumsum(rng.standard_normal(T)) + rng.standard_normal(T)
+    sig = [pkg.get_connection_message_to_factor(e, y[i], lik[i]) for i in range(T)]
+    ids = np.ascontiguousarray([s.sid for s in sig], dtype=np.int64)
+    vals = np.zeros((T, 2))
+    vals[:, 0] = data
+    xs = np.ascontiguousarray(x, dtype=np.int64)
+    cap = pkg.capi
+
+    def one():
+        api.set_values(e.store.h, T, ids.ctypes.data_as(cap.i64p), vals.ctypes.data_as(cap.f64p), 2)
+        st = cap.UpdateStats()
+        import ctypes
+
+        api.update_marginals_seq(e.store.h, T, xs.ctypes.data_as(cap.i64p), ctypes.byref(st))
+        return st.updates
+
+    one()
+    t0, n, reps = time.perf_counter(), 0, 0
+    while time.perf_counter() - t0 < budget_s:
+        n += one()
+        reps += 1
+    dt = time.perf_counter() - t0
+    return n / dt, f"1 chain x T={T} explicit Signal graph, sequential update_marginals!, {reps} repetitions in {dt:.1f} s"
+
+
+def _ref_worker(args):
+    T, budget = args
+    v, _ = cpu_baseline_chain(T, budget)
+    return v
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU implementation of the path (= the oracle port; Julia is absent from the
+    image) on the host cores. The reference is single-threaded, so 'all host threads' = independent replicas."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import multiprocessing as mp
+
+    subprocess.run(["make", "-C", str(ROOT / "oracle")], check=True, stdout=subprocess.DEVNULL)
+    cores = os.cpu_count() or 1
+    T = 1000 if args.workload == "chain1k" else 1024
+    per_step_budget = max(1.0, min(10.0, 60.0 / max(1, args.steps + args.warmup)))
+    vals = []
+    with mp.get_context("spawn").Pool(cores) as pool:
+        for s in range(args.warmup + args.steps):
+            t0 = time.perf_counter()
+            v = sum(pool.map(_ref_worker, [(T, per_step_budget)] * cores))
+            if s >= args.warmup:
+                vals.append((v, time.perf_counter() - t0))
+    value = statistics.mean(v for v, _ in vals)
+    sample = (f"{cores} independent replicas (one per core; the reference is single-threaded), each: 1 chain x T={T} explicit "
+              f"Signal graph, sequential update_marginals!, ~{per_step_budget:.1f} s per step")
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * statistics.mean(t for _, t in vals), "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": workload_config(args, 1),
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+def workload_config(args, world):
+    if args.workload == "gauss_chains":
+        return {"workload": f"batch of {args.chains} independent linear-Gaussian chains per GPU, T={args.chain_steps}, "
+                            f"canonical-form forward-backward (BASELINE configs[1])", "chains_per_gpu": args.chains,
+                "T": args.chain_steps, "l2": "inputs exceed L2 (4.3 GB touched per step)", "parallelism": f"batch-shard x{world}"}
+    if args.workload == "potts_grid":
+        return {"workload": f"2D Potts grid {args.grid}x{args.grid}, K=16, synchronous sweeps (protocol B), row-sharded "
+                            f"(BASELINE configs[3])", "grid": args.grid, "K": 16, "l2": "inputs exceed L2",
+                "parallelism": f"row-shard x{world} + halo exchange"}
+    if args.workload == "hmm64":
+        return {"workload": f"{args.hmm_chains} HMMs per GPU, K=64, M=32, T={args.hmm_steps} (BASELINE configs[2] K=64)",
+                "l2": "inputs exceed L2", "parallelism": f"batch-shard x{world}"}
+    if args.workload == "powerlaw":
+        return {"workload": f"Chung-Lu power-law graph, {args.pl_vars} variables, {2 * args.pl_vars} pairwise factors, K=8, "
+                            f"protocol-B sweeps on the generic CSR engine (BASELINE configs[4])", "l2": "inputs exceed L2 at full size",
+                "parallelism": "replicas only"}
+    return {"workload": "1-D Gaussian random-walk chain T=1000 through the generic engine (BASELINE configs[0])",
+            "l2": "fits L2 (latency config)", "parallelism": "replicas only"}
+
+
+# ---------------------------------------------------------------------------------------------------------------
+def bench_gauss_chains(args, pkg, rank, world, local):
+    import torch
+
+    cap = pkg.capi
+    dtype = cap.F32 if args.dtype == "f32" else cap.F64
+    B, T = args.chains, args.chain_steps
+    npdt = np.float32 if dtype == cap.F32 else np.float64
+    rng = np.random.Generator(np.random.PCG64(1234 + rank))
+    q, r = rng.uniform(0.5, 2.0, B), rng.uniform(0.5, 2.0, B)
+    y_host = torch.empty((T, B), dtype=torch.float32 if dtype == cap.F32 else torch.float64).pin_memory()
+    ynp = y_host.numpy()
+    x = np.zeros(B)
+    for t in range(T):  # fp64 master data cast to the engine dtype
+        x = x + rng.standard_normal(B) * np.sqrt(q)
+        ynp[t] = (x + rng.standard_normal(B) * np.sqrt(r)).astype(npdt)
+    out_host = torch.empty((T, B, 2), dtype=y_host.dtype).pin_memory()
+    ch = pkg.GaussianChainBatch(B, T, dtype=dtype, device=local)
+    ch.set_noise(q, r)
+    ch.set_observations(ynp)
+    n_upd = ch.n_updates
+    kernel_ms = []
+
+    def step():
+        ch.update_marginals()
+
+    launches0 = pkg.default_api().kernel_launches()
+    # device-resident timing (value)
+    for _ in range(args.warmup):
+        step()
+    ch.sync()
+    sampler = ClockSampler(local)
+    sampler.start()
+    ms = timed(ch.stream, step, args.steps, 0, world, local)
+    launches = pkg.default_api().kernel_launches() - launches0 - args.warmup
+    # per-launch kernel duration from the library's own CUDA events (same stream)
+    for _ in range(min(args.steps, 10)):
+        step()
+        kernel_ms.append(ch.last_kernel_ms())
+    # end to end: pinned host observations -> device -> update -> marginals back to pinned host memory
+    def e2e_step():
+        ch.infer_host(y_host.data_ptr(), out_host.data_ptr())
+
+    e2e_ms = timed(ch.stream, e2e_step, max(2, min(args.steps, 5)), 1, world, local)
+    e2e_steps = max(2, min(args.steps, 5))
+    clocks = sampler.stop()
+    esz = 4 if dtype == cap.F32 else 8
+    alg_bytes = B * T * (16 * esz)  # 64 B (fp32) / 128 B (fp64) per variable: SURVEY §8d config 2
+    return {"ms": ms, "updates_per_step": n_upd, "kernel_ms": statistics.mean(kernel_ms), "alg_bytes": alg_bytes,
+            "e2e_ms": e2e_ms, "e2e_steps": e2e_steps, "h2d": B * T * esz, "d2h": B * T * 2 * esz, "launches": launches,
+            "clocks": clocks, "dtype": args.dtype, "kernel": "k_chains_fwd_bwd", "scaling": "weak"}
+
+
+def bench_potts_grid(args, pkg, rank, world, local):
+    import torch
+    import torch.distributed as dist
+
+    cap = pkg.capi
+    N, K, beta = args.grid, 16, 0.7
+    rows = N // world
+    row0 = rank * rows
+    if rank == world - 1:
+        rows = N - row0
+    gr = pkg.PottsGrid(rows, N, K, beta, dtype=cap.F32, device=local, has_upper=rank > 0, has_lower=rank < world - 1)
+    rng = np.random.Generator(np.random.PCG64(1234 + rank))
+    unary_host = torch.empty((rows, N, K), dtype=torch.float32).pin_memory()
+    un = unary_host.numpy()
+    blk = 256
+    for i in range(0, rows, blk):  # Dirichlet(1) rows = normalised exponentials
+        e = rng.standard_exponential((min(blk, rows - i), N, K), dtype=np.float32)
+        un[i:i + blk] = e / e.sum(axis=-1, keepdims=True)
+    gr.set_unary(un)
+    gr.reset_messages()
+    ext = torch.cuda.ExternalStream(gr.stream, device=local)
+    n = gr.halo_elems
+    cache = {}
+
+    def tens(ptr):
+        if ptr not in cache:
+            cache[ptr] = torch.as_tensor(DevArr(ptr, n), device=f"cuda:{local}")
+        return cache[ptr]
+
+    upd = [0]
+
+    def step():
+        upd[0] = gr.sweep()
+        if world > 1:
+            ops = []
+            with torch.cuda.stream(ext):
+                if rank > 0:
+                    ops.append(dist.P2POp(dist.isend, tens(gr.halo_send_ptr(0)), rank - 1))
+                    ops.append(dist.P2POp(dist.irecv, tens(gr.halo_recv_ptr(0)), rank - 1))
+                if rank < world - 1:
+                    ops.append(dist.P2POp(dist.isend, tens(gr.halo_send_ptr(1)), rank + 1))
+                    ops.append(dist.P2POp(dist.irecv, tens(gr.halo_recv_ptr(1)), rank + 1))
+                for w in dist.batch_isend_irecv(ops):
+                    w.wait()
+
+    launches0 = pkg.default_api().kernel_launches()
+    for _ in range(args.warmup):
+        step()
+    gr.sync()
+    sampler = ClockSampler(local)
+    sampler.start()
+    ms = timed(gr.stream, step, args.steps, 0, world, local)
+    launches = pkg.default_api().kernel_launches() - launches0 - args.warmup
+    kernel_ms = []
+    for _ in range(min(args.steps, 10)):
+        step()
+        kernel_ms.append(gr.last_kernel_ms())
+    # end to end: evidence from pinned host memory, one sweep, marginals back
+    marg_host = torch.empty((rows, N, K), dtype=torch.float32).pin_memory()
+
+    def e2e_step():
+        gr.set_unary(un)
+        step()
+        gr.api.grid_get_marginals(gr.h, marg_host.data_ptr())
+
+    e2e_steps = 2
+    e2e_ms = timed(gr.stream, e2e_step, e2e_steps, 1, world, local)
+    clocks = sampler.stop()
+    total_updates = sum_over_ranks(upd[0], world, local)
+    pix = rows * N
+    # 64 B x [(4 m2f + unary) reads + (4 m2v + 4 m2f + marginal) writes] for interior pixels; exact count from the updates
+    m2v_local = (upd[0] - pix) // 2
+    alg_bytes = 64 * ((m2v_local + pix) + (2 * m2v_local + pix))
+    return {"ms": ms, "updates_per_step": total_updates, "kernel_ms": statistics.mean(kernel_ms), "alg_bytes": alg_bytes,
+            "e2e_ms": e2e_ms, "e2e_steps": e2e_steps, "h2d": pix * K * 4, "d2h": pix * K * 4, "launches": launches,
+            "clocks": clocks, "dtype": "f32", "kernel": "k_potts_sweep", "scaling": "strong", "already_global": True}
+
+
+def bench_hmm64(args, pkg, rank, world, local):
+    import torch
+
+    cap = pkg.capi
+    B, T, K, M = args.hmm_chains, args.hmm_steps, 64, 32
+    rng = np.random.Generator(np.random.PCG64(1234 + rank))
+    A = rng.dirichlet(np.ones(K), size=K)
+    E = rng.dirichlet(np.ones(K), size=M).T * K
+    obs_host = torch.empty((T, B), dtype=torch.uint8).pin_memory()
+    obs_host.numpy()[:] = rng.integers(0, M, size=(T, B), dtype=np.uint8)
+    hm = pkg.HmmBatch(B, T, K, M, dtype=cap.F32, device=local)
+    hm.set_tables(A, E)
+    hm.set_observations(obs_host.numpy())
+
+    def step():
+        hm.update_marginals()
+
+    launches0 = pkg.default_api().kernel_launches()
+    for _ in range(args.warmup):
+        step()
+    hm.sync()
+    sampler = ClockSampler(local)
+    sampler.start()
+    ms = timed(hm.stream, step, args.steps, 0, world, local)
+    launches = pkg.default_api().kernel_launches() - launches0 - args.warmup
+    kernel_ms = []
+    for _ in range(min(args.steps, 3)):
+        step()
+        kernel_ms.append(hm.last_kernel_ms())
+    tail = min(T, 256)
+    out_host = torch.empty((tail, B, K), dtype=torch.float32).pin_memory()
+
+    def e2e_step():
+        hm.set_observations(obs_host.numpy())
+        step()
+        hm.api.hmm_get_marginals(hm.h, T - tail, T, out_host.data_ptr())
+
+    e2e_steps = 2
+    e2e_ms = timed(hm.stream, e2e_step, e2e_steps, 1, world, local)
+    clocks = sampler.stop()
+    alg_bytes = B * T * (12 * K + 2)  # forward message + marginal contract
+    return {"ms": ms, "updates_per_step": hm.n_updates, "kernel_ms": statistics.mean(kernel_ms), "alg_bytes": alg_bytes,
+            "e2e_ms": e2e_ms, "e2e_steps": e2e_steps, "h2d": B * T, "d2h": tail * B * K * 4, "launches": launches,
+            "clocks": clocks, "dtype": "f32", "kernel": "k_hmm_pass (fwd + bwd launches)", "scaling": "weak"}
+
+
+def bench_engine_graph(args, pkg, rank, world, local, which):
+    """Generic CSR engine: chain1k (one update_marginals!) or powerlaw (protocol-B sweeps)."""
+    import ctypes
+
+    import torch
+
+    cap = pkg.capi
+    api = pkg.default_api()
+    if which == "chain1k":
+        T = 1000
+        rng = np.random.Generator(np.random.PCG64(1234))
+        n_ids = 4 * T - 1
+        is_factor = np.zeros(n_ids, dtype=np.uint8)
+        is_factor[2 * T:] = 1
+        ftype = np.zeros(n_ids, dtype=np.int32)
+        ftype[3 * T:] = 1
+        ev, ef = [], []
+        for i in range(T):
+            ev += [T + i, i]
+            ef += [2 * T + i, 2 * T + i]
+        for i in range(T - 1):
+            ev += [i, i + 1]
+            ef += [3 * T + i, 3 * T + i]
+        store = pkg.SignalStore(api, 2, cap.FAMILY_GAUSS_CANON, cap.F64, local)
+        ev, ef = np.ascontiguousarray(ev, dtype=np.int64), np.ascontiguousarray(ef, dtype=np.int64)
+        store.check(api.graph_build(store.h, n_ids, is_factor.ctypes.data_as(cap.u8p), ftype.ctypes.data_as(cap.i32p), len(ev),
+                                    ev.ctypes.data_as(cap.i64p), ef.ctypes.data_as(cap.i64p)))
+        one = np.array([1.0])
+        store.check(api.register_rule(store.h, 0, cap.RULE_GAUSS_OBS, one.ctypes.data_as(cap.f64p), 1))
+        store.check(api.register_rule(store.h, 1, cap.RULE_GAUSS_RW, one.ctypes.data_as(cap.f64p), 1))
+        store.check(api.resolve_dependencies(store.h, cap.RESOLVER_DEFAULT_BP))
+        obs_sig = np.ascontiguousarray([api.signal_id(store.h, cap.KIND_M2F, T + i, 2 * T + i) for i in range(T)], dtype=np.int64)
+        vals = np.zeros((T, 2))
+        vals[:, 0] = np.cumsum(rng.standard_normal(T)) + rng.standard_normal(T)
+        xs = np.arange(T, dtype=np.int64)
+        stats = cap.UpdateStats()
+
+        def step():
+            store.check(api.set_values(store.h, T, obs_sig.ctypes.data_as(cap.i64p), vals.ctypes.data_as(cap.f64p), 2))
+            store.check(api.update_marginals(store.h, T, xs.ctypes.data_as(cap.i64p), ctypes.byref(stats)))
+
+        step()
+        upd = 6 * T - 4
+        assert stats.updates == upd, stats.updates
+        alg_bytes, dtype = 0, "f64"
+    else:
+        from tests import models  # graph generator only (numpy); no oracle code is executed
+
+        n = args.pl_vars
+        m, K = 2 * n, 8
+        rng = np.random.Generator(np.random.PCG64(1235))
+        edges = np.asarray(models.chung_lu_edges(n, m), dtype=np.int64)
+        ttype = rng.integers(0, 16, size=m)
+        tables = np.exp(rng.standard_normal((16, K, K)))
+        n_ids = 2 * n + m
+        is_factor = np.zeros(n_ids, dtype=np.uint8)
+        is_factor[n:] = 1
+        ftype = np.zeros(n_ids, dtype=np.int32)
+        ftype[n:2 * n] = 16  # unary
+        ftype[2 * n:] = ttype
+        ev = np.concatenate([np.arange(n), edges.ravel()]).astype(np.int64)
+        ef = np.concatenate([n + np.arange(n), np.repeat(2 * n + np.arange(m), 2)]).astype(np.int64)
+        store = pkg.SignalStore(api, K, cap.FAMILY_CATEGORICAL, cap.F32, local)
+        store.check(api.graph_build(store.h, n_ids, is_factor.ctypes.data_as(cap.u8p), ftype.ctypes.data_as(cap.i32p), len(ev),
+                                    ev.ctypes.data_as(cap.i64p), ef.ctypes.data_as(cap.i64p)))
+        for t in range(16):
+            tb = np.ascontiguousarray(tables[t].ravel())
+            store.check(api.register_rule(store.h, t, cap.RULE_CAT_TABLE, tb.ctypes.data_as(cap.f64p), tb.size))
+        store.check(api.resolve_dependencies(store.h, cap.RESOLVER_DEFAULT_BP))
+        # protocol B: link + initialise every pairwise m2f, evidence = unary m2v
+        pair_m2f = n + 2 * (n + np.arange(2 * m)) + 1  # sid of m2f(connection c) = n_var + 2c + 1, pair connections c >= n
+        for c, s in zip(range(n, n + 2 * m), pair_m2f):
+            store.check(api.link_signal(store.h, int(ev[c]), int(s)))
+        init = np.full((2 * m, K), 1.0 / K)
+        pm = np.ascontiguousarray(pair_m2f, dtype=np.int64)
+        store.check(api.set_values(store.h, 2 * m, pm.ctypes.data_as(cap.i64p), init.ctypes.data_as(cap.f64p), K))
+        unary_sig = np.ascontiguousarray(n + 2 * np.arange(n), dtype=np.int64)
+        unary = rng.dirichlet(np.ones(K), size=n)
+        xs = np.arange(n, dtype=np.int64)
+        stats = cap.UpdateStats()
+
+        def step():
+            store.check(api.set_values(store.h, n, unary_sig.ctypes.data_as(cap.i64p), unary.ctypes.data_as(cap.f64p), K))
+            store.check(api.update_marginals(store.h, n, xs.ctypes.data_as(cap.i64p), ctypes.byref(stats)))
+
+        step()
+        upd = int(stats.updates)
+        deg = np.bincount(edges.ravel(), minlength=n)
+        n_prod = int(np.sum(np.where(deg + 1 > 5, deg - 1, 0)))
+        alg_bytes = 32 * (int(np.sum((deg + 1) + (2 * deg + 1))) + 3 * n_prod)
+        dtype = "f32"
+    launches0 = api.kernel_launches()
+    for _ in range(args.warmup):
+        step()
+    torch.cuda.synchronize()
+    sampler = ClockSampler(local)
+    sampler.start()
+    barrier(world)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+    torch.cuda.synchronize()
+    ms = max_over_ranks(1e3 * (time.perf_counter() - t0), world, local)
+    clocks = sampler.stop()
+    launches = api.kernel_launches() - launches0 - 0
+    return {"ms": ms, "updates_per_step": upd, "kernel_ms": ms / args.steps, "alg_bytes": alg_bytes, "e2e_ms": ms,
+            "e2e_steps": args.steps, "h2d": int(vals.nbytes) if which == "chain1k" else int(unary.nbytes), "d2h": 0,
+            "launches": launches, "clocks": clocks, "dtype": dtype,
+            "kernel": "generic engine (k_bfs / k_ms_* / k_rule_* / k_apply)", "scaling": "weak",
+            "timer": "host wall clock around synchronous ABI calls (each call ends with a stream sync)"}
+
+
+# ---------------------------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="gauss_chains", choices=["gauss_chains", "potts_grid", "hmm64", "powerlaw", "chain1k"])
+    ap.add_argument("--dtype", default="f32", choices=["f32", "f64"])
+    ap.add_argument("--chains", type=int, default=65536)
+    ap.add_argument("--chain-steps", type=int, default=1024)
+    ap.add_argument("--grid", type=int, default=8192)
+    ap.add_argument("--hmm-chains", type=int, default=1024)
+    ap.add_argument("--hmm-steps", type=int, default=100000)
+    ap.add_argument("--pl-vars", type=int, default=1000000)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.impl == "reference":
+        run_reference(args)
+        return
+
+    pkg = entry.load_package()
+    rank, world, local = dist_setup(args.gpus)
+    fn = {"gauss_chains": bench_gauss_chains, "potts_grid": bench_potts_grid, "hmm64": bench_hmm64,
+          "powerlaw": lambda *a: bench_engine_graph(*a, "powerlaw"), "chain1k": lambda *a: bench_engine_graph(*a, "chain1k")}[args.workload]
+    r = fn(args, pkg, rank, world, local)
+    peak, peak_src, _ = measured_peaks()
+    ms_per_step = r["ms"] / args.steps
+    total_updates = r["updates_per_step"] if r.get("already_global") else r["updates_per_step"] * world
+    value = total_updates / (ms_per_step * 1e-3)
+    e2e_value = total_updates / (r["e2e_ms"] / r["e2e_steps"] * 1e-3)
+    achieved = r["alg_bytes"] / (r["kernel_ms"] * 1e-3) / 1e9 if r["alg_bytes"] else None
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": r["scaling"], "vs_baseline": None,
+            "dtype": r["dtype"], "data": "synthetic", "config": workload_config(args, world),
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": r["h2d"], "d2h_bytes_per_step": r["d2h"]},
+            "gpu_launches": int(r["launches"]), "clocks": r["clocks"],
+            "roofline": {"bound": "hbm", "kernel": r["kernel"], "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": (achieved / peak) if achieved else None, "traffic": None, "peak_source": peak_src,
+                         "kernel_ms": r["kernel_ms"], "algorithmic_bytes_per_launch": r["alg_bytes"]}}
+    if "timer" in r:
+        line["timer"] = r["timer"]
+    traffic_file = ROOT / "profiles" / f"traffic_{args.workload}.json"
+    if traffic_file.exists():
+        try:
+            line["roofline"]["traffic"] = json.loads(traffic_file.read_text()).get("dram_bytes_per_launch")
+        except Exception:
+            pass
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        subprocess.run(["make", "-C", str(ROOT / "oracle")], check=True, stdout=subprocess.DEVNULL)
+        v, sample = cpu_baseline_chain(1000 if args.workload == "chain1k" else 1024)
+        line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": 1, "kind": "port", "sample": sample,
+                                "host_cores_available": os.cpu_count()}
+    if rank == 0:
+        print(json.dumps(line))
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -5,8 +5,7 @@ Only what the `update_marginals!` hot path needs lives here:
   _capi.py            ctypes binding of that ABI
   inference_signal.py / model_engine.py / inference_engine.py
                       host-side mirror of the reference interface (same names and semantics)
-  chains.py / grid.py / hmm.py
-                      structured model engines (closed-form plans of the fixed-stencil graphs)
+  structured.py       structured model engines (closed-form plans of the fixed-stencil graphs)
   julia/CortexB200.jl the `ccall` glue a Cortex.jl maintainer adds (cannot run in this image)
 
 The directory name contains a dot, so import it through `__graft_entry__.load_package()`
@@ -20,5 +19,6 @@ from .inference_signal import (CortexError, NoRuleError, NotPendingError, OutOfC
 from .model_engine import *  # noqa: F401,F403
 from .inference_engine import *  # noqa: F401,F403
 from .inference_engine import _as_ids  # noqa: F401
+from .structured import GaussianChainBatch, HmmBatch, PottsGrid  # noqa: F401
 
 __version__ = "0.1.0"

@@ -70,6 +70,7 @@ _COMMON = {
 # structured engines, cxb_ only
 _STRUCTURED = {
     "version": (C.c_char_p, []),
+    "kernel_launches": (C.c_uint64, []),
     "chains_create": (i32, [i32, i32, i64, i64, C.POINTER(vp)]),
     "chains_destroy": (None, [vp]),
     "chains_last_error": (C.c_char_p, [vp]),

@@ -1,0 +1,343 @@
+// chains.cu — structured engine for a batch of independent linear-Gaussian random-walk chains
+// (BASELINE configs 1-2).  One call = update_marginals!(engine, x[1:T]) of every chain of the graph
+// of test/inference_engine_tests.jl:436-462 under the DefaultDependencyResolver: the forward round
+// computes m2v(x_t,lik_t), m2v(x_t,tr_{t-1}), m2f(x_t,tr_t); the reverse round m2v(x_t,tr_t),
+// m2f(x_t,tr_{t-1}); the final phase the marginals — 6T-4 message updates per chain,
+// every one of them materialised in HBM ("materialise-all").
+//
+// Rules (canonical form (precision L, precision-mean h)):
+//   observation factor, variance r :  (1/r, y/r)
+//   random-walk factor, variance q :  (L, h) -> (L/(1+qL), h/(1+qL))
+//   m2f / marginal                 :  component-wise sum of the dependencies, left to right
+//
+// Data layout: time-major [T][B] so that the 32 chains of a warp touch one contiguous 128 B (y) /
+// 256 B (float2 message) / 512 B (double2) segment per step. One thread owns one chain; the loads of
+// a whole time tile are issued before the sequential recursion consumes them (the recursion itself
+// is a ~40-cycle dependent chain per step, hidden by ~14 resident warps per SM). Stores are
+// streaming (st.global.cs): nothing written is re-read before ~2 GB of other traffic.
+// HBM-bound: 64 B (fp32) / 128 B (fp64) of algorithmic traffic per variable.
+#include <cmath>
+
+#include "common.cuh"
+
+namespace cxb {
+
+template <class T>
+struct Vec2;
+template <>
+struct Vec2<float> {
+    using type = float2;
+};
+template <>
+struct Vec2<double> {
+    using type = double2;
+};
+
+template <class T>
+__device__ __forceinline__ typename Vec2<T>::type mk2(T a, T b) {
+    typename Vec2<T>::type v;
+    v.x = a;
+    v.y = b;
+    return v;
+}
+
+constexpr int CH_TILE = 8;  // time steps whose loads are in flight together
+
+// msg: [6][T][B] of (L,h) pairs. Classes: 0 m2v(x_t,lik_t)  1 m2v(x_t,tr_{t-1})  2 m2f(x_t,tr_t)
+//                                          3 m2v(x_t,tr_t)   4 m2f(x_t,tr_{t-1})  5 marginal(x_t)
+template <class T>
+__global__ void __launch_bounds__(128)
+k_chains_fwd_bwd(const T* __restrict__ y, const T* __restrict__ qv, const T* __restrict__ rv,
+                 typename Vec2<T>::type* __restrict__ msg, long long B, long long Tn) {
+    using V = typename Vec2<T>::type;
+    const long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    const T q = qv[b], r = rv[b];
+    const T inv_r = T(1) / r;
+    const size_t plane = (size_t)Tn * (size_t)B;
+    V* __restrict__ m_obs = msg;
+    V* __restrict__ m_pred = msg + plane;
+    V* __restrict__ m_fwd = msg + 2 * plane;
+    V* __restrict__ m_bwd = msg + 3 * plane;
+    V* __restrict__ m_back = msg + 4 * plane;
+    V* __restrict__ m_marg = msg + 5 * plane;
+
+    // ---- forward round: t = 0 .. T-1 -------------------------------------------------------------------
+    T L = 0, h = 0;  // m2f(x_{t-1}, tr_{t-1}) carried in registers
+    for (long long t0 = 0; t0 < Tn; t0 += CH_TILE) {
+        T yy[CH_TILE];
+#pragma unroll
+        for (int k = 0; k < CH_TILE; ++k) {
+            long long t = t0 + k;
+            yy[k] = t < Tn ? __ldcs(&y[(size_t)t * B + b]) : T(0);
+        }
+#pragma unroll
+        for (int k = 0; k < CH_TILE; ++k) {
+            long long t = t0 + k;
+            if (t < Tn) {
+                size_t idx = (size_t)t * B + b;
+                T oL = inv_r, oh = yy[k] * inv_r;  // m2v(x_t, lik_t) = (1/r, y/r)
+                T pL = 0, ph = 0;
+                if (t > 0) {  // m2v(x_t, tr_{t-1}) = RW(m2f(x_{t-1}, tr_{t-1}))
+                    T den = T(1) + q * L;
+                    pL = L / den;
+                    ph = h / den;
+                    L = oL + pL;  // m2f(x_t, tr_t) = lik (+) tr_{t-1}, dependency order
+                    h = oh + ph;
+                } else {
+                    L = oL;
+                    h = oh;
+                }
+                __stcs(&m_obs[idx], mk2<T>(oL, oh));
+                __stcs(&m_pred[idx], mk2<T>(pL, ph));
+                __stcs(&m_fwd[idx], mk2<T>(L, h));
+            }
+        }
+    }
+    // ---- reverse round + final phase: t = T-1 .. 0 --------------------------------------------------------
+    L = 0;
+    h = 0;  // m2f(x_{t+1}, tr_t)
+    for (long long t1 = Tn - 1; t1 >= 0; t1 -= CH_TILE) {
+        T yy[CH_TILE];
+        V pr[CH_TILE];
+#pragma unroll
+        for (int k = 0; k < CH_TILE; ++k) {
+            long long t = t1 - k;
+            if (t >= 0) {
+                yy[k] = __ldcs(&y[(size_t)t * B + b]);
+                pr[k] = __ldcs(&m_pred[(size_t)t * B + b]);
+            } else {
+                yy[k] = T(0);
+                pr[k] = mk2<T>(T(0), T(0));
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < CH_TILE; ++k) {
+            long long t = t1 - k;
+            if (t >= 0) {
+                size_t idx = (size_t)t * B + b;
+                T oL = inv_r, oh = yy[k] * inv_r;
+                T bL = 0, bh = 0;
+                if (t < Tn - 1) {  // m2v(x_t, tr_t) = RW(m2f(x_{t+1}, tr_t))
+                    T den = T(1) + q * L;
+                    bL = L / den;
+                    bh = h / den;
+                    L = oL + bL;  // m2f(x_t, tr_{t-1}) = lik (+) tr_t
+                    h = oh + bh;
+                } else {
+                    L = oL;
+                    h = oh;
+                }
+                // marginal(x_t) = lik (+) tr_{t-1} (+) tr_t, left to right
+                T gL = oL, gh = oh;
+                if (t > 0) {
+                    gL = gL + pr[k].x;
+                    gh = gh + pr[k].y;
+                }
+                if (t < Tn - 1) {
+                    gL = gL + bL;
+                    gh = gh + bh;
+                }
+                __stcs(&m_bwd[idx], mk2<T>(bL, bh));
+                __stcs(&m_back[idx], mk2<T>(L, h));
+                __stcs(&m_marg[idx], mk2<T>(gL, gh));
+            }
+        }
+    }
+}
+
+struct Chains {
+    int device = 0, dtype = CXB_F32;
+    long long B = 0, T = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    std::string err;
+    DBuf<unsigned char> y, q, r, msg;
+    bool have_noise = false, have_obs = false, ran = false;
+    size_t esz() const { return dtype == CXB_F32 ? 4 : 8; }
+    size_t plane_bytes() const { return (size_t)T * B * 2 * esz(); }
+    ~Chains() {
+        if (ev0) cudaEventDestroy(ev0);
+        if (ev1) cudaEventDestroy(ev1);
+        if (stream) cudaStreamDestroy(stream);
+    }
+    int32_t init() {
+        int count = 0;
+        if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0) {
+            err = "no CUDA device available (cortex_b200 has no CPU fallback)";
+            return CXB_ERR_CUDA;
+        }
+        if (device < 0 || device >= count || B <= 0 || T <= 0) {
+            err = "bad device / shape";
+            return CXB_ERR_BAD_ARG;
+        }
+        CXB_CUDA(cudaSetDevice(device));
+        CXB_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+        CXB_CUDA(cudaEventCreate(&ev0));
+        CXB_CUDA(cudaEventCreate(&ev1));
+        CXB_CUDA(y.reserve((size_t)T * B * esz()));
+        CXB_CUDA(q.reserve((size_t)B * esz()));
+        CXB_CUDA(r.reserve((size_t)B * esz()));
+        CXB_CUDA(msg.reserve(6 * plane_bytes()));
+        return CXB_OK;
+    }
+    int32_t set_noise(const double* qh, const double* rh) {
+        CXB_CUDA(cudaSetDevice(device));
+        std::vector<unsigned char> a((size_t)B * esz()), c((size_t)B * esz());
+        for (long long i = 0; i < B; ++i) {
+            if (!(qh[i] >= 0) || !(rh[i] > 0)) {
+                err = "noise variances must satisfy q >= 0, r > 0";
+                return CXB_ERR_BAD_ARG;
+            }
+            if (dtype == CXB_F32) {
+                ((float*)a.data())[i] = (float)qh[i];
+                ((float*)c.data())[i] = (float)rh[i];
+            } else {
+                ((double*)a.data())[i] = qh[i];
+                ((double*)c.data())[i] = rh[i];
+            }
+        }
+        CXB_CUDA(cudaMemcpyAsync(q.p, a.data(), a.size(), cudaMemcpyHostToDevice, stream));
+        CXB_CUDA(cudaMemcpyAsync(r.p, c.data(), c.size(), cudaMemcpyHostToDevice, stream));
+        CXB_CUDA(cudaStreamSynchronize(stream));
+        have_noise = true;
+        return CXB_OK;
+    }
+    int32_t launch() {
+        if (!have_noise || !have_obs) {
+            err = "set the noise variances and the observations first";
+            return CXB_ERR_STATE;
+        }
+        CXB_CUDA(cudaSetDevice(device));
+        unsigned grid = cdiv((size_t)B, 128);
+        CXB_CUDA(cudaEventRecord(ev0, stream));
+        if (dtype == CXB_F32)
+            CXB_LAUNCH(k_chains_fwd_bwd<float>, grid, 128, 0, stream, (const float*)y.p, (const float*)q.p, (const float*)r.p,
+                       (float2*)msg.p, B, T);
+        else
+            CXB_LAUNCH(k_chains_fwd_bwd<double>, grid, 128, 0, stream, (const double*)y.p, (const double*)q.p,
+                       (const double*)r.p, (double2*)msg.p, B, T);
+        CXB_CUDA(cudaEventRecord(ev1, stream));
+        CXB_CUDA(cudaGetLastError());
+        ran = true;
+        return CXB_OK;
+    }
+};
+
+}  // namespace cxb
+
+using cxb::Chains;
+static inline Chains* CH(cxb_chains* c) { return reinterpret_cast<Chains*>(c); }
+
+extern "C" {
+
+int32_t cxb_chains_create(int32_t device, int32_t dtype, int64_t n_chains, int64_t n_steps, cxb_chains** out) {
+    if (!out || (dtype != CXB_F32 && dtype != CXB_F64)) return CXB_ERR_BAD_ARG;
+    *out = nullptr;
+    Chains* c = new Chains();
+    c->device = device;
+    c->dtype = dtype;
+    c->B = n_chains;
+    c->T = n_steps;
+    int32_t st = c->init();
+    if (st) {
+        fprintf(stderr, "cxb_chains_create: %s\n", c->err.c_str());
+        delete c;
+        return st;
+    }
+    *out = reinterpret_cast<cxb_chains*>(c);
+    return CXB_OK;
+}
+void cxb_chains_destroy(cxb_chains* c) {
+    if (c) {
+        cudaSetDevice(CH(c)->device);
+        delete CH(c);
+    }
+}
+const char* cxb_chains_last_error(cxb_chains* c) { return c ? CH(c)->err.c_str() : "null handle"; }
+int32_t cxb_chains_set_noise(cxb_chains* c, const double* q, const double* r) { return CH(c)->set_noise(q, r); }
+
+#define CH_CUDA(c, expr)                                        \
+    do {                                                        \
+        cudaError_t e__ = (expr);                               \
+        if (e__ != cudaSuccess) {                               \
+            CH(c)->err = ::cxb::cuda_msg(e__, #expr);           \
+            return CXB_ERR_CUDA;                                \
+        }                                                       \
+    } while (0)
+
+int32_t cxb_chains_set_observations(cxb_chains* c, const void* y_host) {
+    Chains* h = CH(c);
+    CH_CUDA(c, cudaSetDevice(h->device));
+    CH_CUDA(c, cudaMemcpyAsync(h->y.p, y_host, (size_t)h->T * h->B * h->esz(), cudaMemcpyHostToDevice, h->stream));
+    CH_CUDA(c, cudaStreamSynchronize(h->stream));
+    h->have_obs = true;
+    return CXB_OK;
+}
+int32_t cxb_chains_set_observations_device(cxb_chains* c, const void* y_dev) {
+    Chains* h = CH(c);
+    CH_CUDA(c, cudaSetDevice(h->device));
+    if (y_dev != h->y.p)
+        CH_CUDA(c, cudaMemcpyAsync(h->y.p, y_dev, (size_t)h->T * h->B * h->esz(), cudaMemcpyDeviceToDevice, h->stream));
+    h->have_obs = true;
+    return CXB_OK;
+}
+int32_t cxb_chains_update_marginals(cxb_chains* c, int64_t* n_updates_out) {
+    Chains* h = CH(c);
+    int32_t st = h->launch();
+    if (st) return st;
+    if (n_updates_out) *n_updates_out = h->B * (6 * h->T - 4);
+    return CXB_OK;
+}
+int32_t cxb_chains_get_messages(cxb_chains* c, int32_t m, void* out_host) {
+    Chains* h = CH(c);
+    if (m < 0 || m > 5) {
+        h->err = "message class must be 0..5";
+        return CXB_ERR_BAD_ARG;
+    }
+    if (!h->ran) {
+        h->err = "no update has run yet";
+        return CXB_ERR_STATE;
+    }
+    CH_CUDA(c, cudaSetDevice(h->device));
+    CH_CUDA(c, cudaMemcpyAsync(out_host, h->msg.p + (size_t)m * h->plane_bytes(), h->plane_bytes(), cudaMemcpyDeviceToHost,
+                               h->stream));
+    CH_CUDA(c, cudaStreamSynchronize(h->stream));
+    return CXB_OK;
+}
+int32_t cxb_chains_get_marginals(cxb_chains* c, void* out_host) { return cxb_chains_get_messages(c, 5, out_host); }
+void* cxb_chains_device_ptr(cxb_chains* c, int32_t which) {
+    Chains* h = CH(c);
+    if (which >= 0 && which <= 5) return h->msg.p + (size_t)which * h->plane_bytes();
+    if (which == 6) return h->y.p;
+    return nullptr;
+}
+int32_t cxb_chains_infer_host(cxb_chains* c, const void* y_host, void* marg_out, int64_t* n_updates_out) {
+    Chains* h = CH(c);
+    CH_CUDA(c, cudaSetDevice(h->device));
+    CH_CUDA(c, cudaMemcpyAsync(h->y.p, y_host, (size_t)h->T * h->B * h->esz(), cudaMemcpyHostToDevice, h->stream));
+    h->have_obs = true;
+    int32_t st = h->launch();
+    if (st) return st;
+    CH_CUDA(c, cudaMemcpyAsync(marg_out, h->msg.p + 5 * h->plane_bytes(), h->plane_bytes(), cudaMemcpyDeviceToHost, h->stream));
+    CH_CUDA(c, cudaStreamSynchronize(h->stream));
+    if (n_updates_out) *n_updates_out = h->B * (6 * h->T - 4);
+    return CXB_OK;
+}
+void* cxb_chains_stream(cxb_chains* c) { return (void*)CH(c)->stream; }
+int32_t cxb_chains_last_kernel_ms(cxb_chains* c, float* ms_out) {
+    Chains* h = CH(c);
+    if (!h->ran) {
+        h->err = "no update has run yet";
+        return CXB_ERR_STATE;
+    }
+    CH_CUDA(c, cudaEventSynchronize(h->ev1));
+    CH_CUDA(c, cudaEventElapsedTime(ms_out, h->ev0, h->ev1));
+    return CXB_OK;
+}
+int32_t cxb_chains_sync(cxb_chains* c) {
+    CH_CUDA(c, cudaStreamSynchronize(CH(c)->stream));
+    return CXB_OK;
+}
+
+}  // extern "C"

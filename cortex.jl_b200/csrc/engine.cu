@@ -1,0 +1,1416 @@
+// engine.cu — the generic device engine: Cortex.jl's Signal DAG + update_marginals! as a
+// device-resident CSR with a level-synchronous frontier.
+//
+// What replaces what (reference paths relative to Cortex.jl v0.3.0):
+//   Signal.props / SignalDependenciesProps (src/signal.jl:36-51)   -> props[N] bytes + packed 64-bit nibble chunks
+//   is_pending / is_meeting_pending_criteria (:141-154, :668-730)  -> pending_eval() (same lazy two-flag protocol)
+//   set_value! + notify_listener! (:232-253, :339-356)             -> k_apply (listener CSR with precomputed first slot)
+//   process_dependencies! DFS (:466-490)                           -> k_bfs level-synchronous reachability
+//   process! rule dispatch (src/inference_engine.jl:479-509)       -> frontier multisplit by rule key + one batched
+//                                                                     kernel per (signal kind, factor type)
+//   update_marginals! (:559-632)                                   -> DeviceEngine::update()
+// No CPU fallback: every compute entry point needs the CUDA device.
+#include <algorithm>
+#include <cstring>
+#include <map>
+#include <unordered_set>
+
+#include "common.cuh"
+#include "host_graph.hpp"
+
+namespace cxb {
+
+unsigned long long g_kernel_launches = 0;
+
+constexpr uint64_t ALL_W = 0x2222222222222222ull, ALL_C = 0x4444444444444444ull, ALL_F = 0x8888888888888888ull,
+                   PASS = 0x1111111111111111ull;
+constexpr int ERR_INDEPENDENCE = 1, ERR_LISTENER_DONE = 2, ERR_RULE_ARG = 4;
+constexpr int KEY_COMBINE = 0;  // dense rule keys: 0 = family reduce, 1..n_types = m2v of a factor type, n_types+1 = no rule
+constexpr int MS_THREADS = 256, MS_ITEMS = 16, MS_TILE = MS_THREADS * MS_ITEMS;
+
+// device view of the engine state (plain pointers, passed by value to kernels)
+struct View {
+    uint32_t n_sig;
+    int dim;
+    const uint32_t *dep_off, *dep_ids, *nib_off;
+    uint64_t* nib;
+    const uint32_t *lis_off, *lis_ids, *lis_slot;
+    const uint8_t* lis_listen;
+    uint8_t* props;
+    const uint8_t *kind, *rkey;
+    const int32_t *svar, *sfac;
+    uint32_t *done_epoch, *visit_epoch;
+    uint8_t* front_flag;
+    int* err_flag;
+    unsigned long long* kind_count;  // [6]
+};
+
+// ---- is_meeting_pending_criteria, src/signal.jl:668-730 (same chunk arithmetic) -------------------------
+__device__ __forceinline__ bool criteria(const View& e, uint32_t s) {
+    uint32_t nd = e.dep_off[s + 1] - e.dep_off[s];
+    if (nd == 0) return false;
+    uint32_t noff = e.nib_off[s], nch = e.nib_off[s + 1] - noff;
+    for (uint32_t i = 0; i + 1 < nch; ++i) {
+        uint64_t c = e.nib[noff + i];
+        uint64_t W = (c & ALL_W) >> 1, C = (c & ALL_C) >> 2, F = (c & ALL_F) >> 3;
+        if ((C & (W | F)) != PASS) return false;
+    }
+    uint32_t last = nd - 1;
+    int shift = (int)((last & 15) << 2) + 4;
+    uint64_t pad = shift >= 64 ? 0ull : (~0ull << shift);
+    uint64_t c = e.nib[noff + (last >> 4)] | pad;
+    uint64_t W = (c & ALL_W) >> 1, C = (c & ALL_C) >> 2, F = (c & ALL_F) >> 3;
+    return (C & (W | F)) == PASS;
+}
+// is_pending, src/signal.jl:141-154. Concurrent evaluations of one signal are idempotent inside a level
+// (no set_value! happens between them), so racing threads write the same byte.
+__device__ __forceinline__ bool pending_eval(const View& e, uint32_t s) {
+    uint8_t p = e.props[s];
+    if (p & P_P) return true;
+    if (p & P_PP) {
+        bool r = criteria(e, s);
+        e.props[s] = (uint8_t)((p & P_COMPUTED) | (r ? P_P : 0));
+        return r;
+    }
+    return false;
+}
+
+// request_inference_for, src/inference_engine.jl:305-318: flag the direct dependencies of every requested
+// marginal and its linked signals (is_potentially_pending = true, is_pending = false)
+__global__ void k_request(View e, const uint32_t* req_marg, const uint32_t* link_off, const uint32_t* link_ids, uint32_t n) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint32_t m = req_marg[i];
+    for (uint32_t k = e.dep_off[m]; k < e.dep_off[m + 1]; ++k) {
+        uint32_t d = e.dep_ids[k];
+        e.props[d] = (uint8_t)((e.props[d] & P_COMPUTED) | P_PP);
+    }
+    for (uint32_t k = link_off[i]; k < link_off[i + 1]; ++k) {
+        uint32_t d = link_ids[k];
+        e.props[d] = (uint8_t)((e.props[d] & P_COMPUTED) | P_PP);
+    }
+}
+
+// seeds of one level: marginals of the requested variables that are not ready yet (:585)
+__global__ void k_seeds(const uint32_t* req_marg, const uint8_t* ready, uint32_t n, uint32_t* out, uint32_t* n_out) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    bool take = i < n && !ready[i];
+    unsigned m = __ballot_sync(0xffffffffu, take);
+    if (!m) return;
+    int lane = threadIdx.x & 31;
+    uint32_t base = 0;
+    if (lane == __ffs(m) - 1) base = atomicAdd(n_out, (uint32_t)__popc(m));
+    base = __shfl_sync(0xffffffffu, base, __ffs(m) - 1);
+    if (take) out[base + __popc(m & ((1u << lane) - 1))] = req_marg[i];
+}
+
+// One breadth-first step of process_dependencies! (src/signal.jl:466-490) over a list of signals:
+// visit every dependency (f(dep) = is_pending), flag the pending ones, descend through non-pending
+// *intermediate* ones. `done` signals are neither reported nor descended through (A.5).
+__global__ void k_bfs(View e, const uint32_t* in, uint32_t n_in, uint32_t* out, uint32_t* n_out, uint32_t lvl_epoch,
+                      uint32_t req_epoch, int use_done) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_in) return;
+    uint32_t s = in[i];
+    uint32_t off = e.dep_off[s], nd = e.dep_off[s + 1] - off, noff = e.nib_off[s];
+    for (uint32_t k = 0; k < nd; ++k) {
+        uint32_t d = e.dep_ids[off + k];
+        if (use_done && e.done_epoch[d] == req_epoch) continue;
+        if (pending_eval(e, d)) {
+            e.front_flag[d] = 1;
+        } else {
+            uint32_t nibble = (uint32_t)(e.nib[noff + (k >> 4)] >> ((k & 15) << 2)) & 0xF;
+            if ((nibble & CXB_NIB_INTERMEDIATE) && atomicExch(&e.visit_epoch[d], lvl_epoch) != lvl_epoch)
+                out[atomicAdd(n_out, 1u)] = d;
+        }
+    }
+}
+
+// final phase candidates (:610-628): mode 0 = requested marginals, mode 1 = their linked signals
+__global__ void k_final_flags(View e, const uint32_t* req_marg, const uint32_t* link_off, const uint32_t* link_ids,
+                              uint32_t n, int mode) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    if (mode == 0) {
+        uint32_t m = req_marg[i];
+        if (pending_eval(e, m)) e.front_flag[m] = 1;
+    } else {
+        for (uint32_t k = link_off[i]; k < link_off[i + 1]; ++k) {
+            uint32_t d = link_ids[k];
+            if (pending_eval(e, d)) e.front_flag[d] = 1;
+        }
+    }
+}
+
+// readiness, :593-595
+__global__ void k_ready(View e, const uint32_t* req_marg, uint8_t* ready, uint32_t n) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n || ready[i]) return;
+    if (pending_eval(e, req_marg[i])) ready[i] = 1;
+}
+
+// ---- ordered multisplit of the flagged signals by rule key (warp-ballot / match ranking) ---------------
+// pass 1: per-tile histogram of keys
+__global__ void k_ms_hist(const uint8_t* flag, const uint8_t* rkey, uint32_t n, uint32_t* tile_hist, uint32_t n_tiles,
+                          int n_keys, int use_keys) {
+    extern __shared__ uint32_t sh[];
+    for (int k = threadIdx.x; k < n_keys; k += blockDim.x) sh[k] = 0;
+    __syncthreads();
+    uint32_t base = blockIdx.x * MS_TILE;
+#pragma unroll
+    for (int it = 0; it < MS_ITEMS; ++it) {
+        uint32_t i = base + it * MS_THREADS + threadIdx.x;
+        if (i < n && flag[i]) atomicAdd(&sh[use_keys ? rkey[i] : 0], 1u);
+    }
+    __syncthreads();
+    for (int k = threadIdx.x; k < n_keys; k += blockDim.x) tile_hist[(size_t)k * n_tiles + blockIdx.x] = sh[k];
+}
+// pass 2: exclusive scan of the key-major histogram (single block), writes per-key totals
+__global__ void k_ms_scan(uint32_t* tile_hist, uint32_t n_tiles, int n_keys, uint32_t* key_count) {
+    __shared__ uint32_t warp_sum[32];
+    __shared__ uint32_t carry;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    size_t total = (size_t)n_keys * n_tiles;
+    int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    for (size_t base = 0; base < total; base += blockDim.x) {
+        size_t i = base + threadIdx.x;
+        uint32_t v = i < total ? tile_hist[i] : 0, x = v;
+        for (int o = 1; o < 32; o <<= 1) {
+            uint32_t y = __shfl_up_sync(0xffffffffu, x, o);
+            if (lane >= o) x += y;
+        }
+        if (lane == 31) warp_sum[wid] = x;
+        __syncthreads();
+        if (wid == 0) {
+            uint32_t w = lane < nw ? warp_sum[lane] : 0, ws = w;
+            for (int o = 1; o < 32; o <<= 1) {
+                uint32_t y = __shfl_up_sync(0xffffffffu, ws, o);
+                if (lane >= o) ws += y;
+            }
+            warp_sum[lane] = ws - w;  // exclusive
+        }
+        __syncthreads();
+        uint32_t excl = carry + warp_sum[wid] + x - v;
+        if (i < total) tile_hist[i] = excl;
+        __syncthreads();
+        if (threadIdx.x == blockDim.x - 1) carry = excl + v;
+        __syncthreads();
+    }
+    // key totals: start of key k+1 minus start of key k
+    for (int k = threadIdx.x; k < n_keys; k += blockDim.x) {
+        uint32_t start = tile_hist[(size_t)k * n_tiles];
+        uint32_t end = (k + 1 < n_keys) ? tile_hist[(size_t)(k + 1) * n_tiles] : carry;
+        key_count[k] = end - start;
+        key_count[n_keys + k] = start;  // offsets
+    }
+}
+// pass 3: stable scatter (ascending signal id inside each key), clears the flags
+__global__ void k_ms_scatter(uint8_t* flag, const uint8_t* rkey, uint32_t n, const uint32_t* tile_hist, uint32_t n_tiles,
+                             int n_keys, int use_keys, uint32_t* out) {
+    extern __shared__ uint32_t sh[];  // [n_keys] running base + [8][n_keys] per-warp counts
+    uint32_t* run = sh;
+    uint32_t* wcnt = sh + n_keys;
+    int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int nw = MS_THREADS / 32;
+    for (int k = threadIdx.x; k < n_keys; k += blockDim.x) run[k] = tile_hist[(size_t)k * n_tiles + blockIdx.x];
+    uint32_t base = blockIdx.x * MS_TILE;
+    for (int it = 0; it < MS_ITEMS; ++it) {
+        for (int k = threadIdx.x; k < n_keys * nw; k += blockDim.x) wcnt[k] = 0;
+        __syncthreads();
+        uint32_t i = base + it * MS_THREADS + threadIdx.x;
+        bool f = i < n && flag[i];
+        int key = f ? (use_keys ? rkey[i] : 0) : -1;
+        unsigned same = __match_any_sync(0xffffffffu, key);
+        int rank = __popc(same & ((1u << lane) - 1));
+        if (f && rank == 0) wcnt[wid * n_keys + key] = __popc(same);
+        __syncthreads();
+        uint32_t pos = 0;
+        if (f) {
+            pos = run[key] + rank;
+            for (int w = 0; w < wid; ++w) pos += wcnt[w * n_keys + key];
+            out[pos] = i;
+            flag[i] = 0;
+        }
+        __syncthreads();
+        for (int k = threadIdx.x; k < n_keys; k += blockDim.x) {
+            uint32_t add = 0;
+            for (int w = 0; w < nw; ++w) add += wcnt[w * n_keys + k];
+            run[k] += add;
+        }
+        __syncthreads();
+    }
+}
+
+// ---- set_value! side effects for a list of signals, src/signal.jl:232-253 + 339-356 ---------------------
+// (values are already written). check_mode: 0 none (user set_value!), 1 loop phase (independence + done-listener
+// contract), 2 final phase (independence only).
+__global__ void k_apply(View e, const uint32_t* list, uint32_t n, uint32_t req_epoch, int check_mode) {
+    __shared__ unsigned int kc[6];
+    if (threadIdx.x < 6) kc[threadIdx.x] = 0;
+    __syncthreads();
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) {
+        uint32_t s = list[i];
+        for (uint32_t c = e.nib_off[s]; c < e.nib_off[s + 1]; ++c) e.nib[c] &= ~ALL_F;  // unset_all_dependencies_fresh!
+        e.props[s] = P_COMPUTED;                                                         // (pp, p) = (false, false)
+        if (check_mode) e.done_epoch[s] = req_epoch;
+        atomicAdd(&kc[e.kind[s]], 1u);
+        for (uint32_t k = e.lis_off[s]; k < e.lis_off[s + 1]; ++k) {
+            uint32_t L = e.lis_ids[k], slot = e.lis_slot[k];
+            if (e.lis_listen[k]) e.props[L] = (uint8_t)((e.props[L] & P_COMPUTED) | P_PP);
+            atomicOr((unsigned long long*)&e.nib[e.nib_off[L] + (slot >> 4)],
+                     (unsigned long long)(CXB_NIB_COMPUTED | CXB_NIB_FRESH) << ((slot & 15) << 2));
+            if (check_mode == 1 && e.done_epoch[L] == req_epoch) atomicOr(e.err_flag, ERR_LISTENER_DONE);
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x < 6 && kc[threadIdx.x]) atomicAdd(&e.kind_count[threadIdx.x], (unsigned long long)kc[threadIdx.x]);
+}
+// independence of a level (A.5): no member may depend on another member. Runs BEFORE the rules, while the
+// members are still marked by `mark_epoch` in visit-independent scratch (`done_epoch` is not yet written).
+__global__ void k_mark(uint32_t* mark, const uint32_t* list, uint32_t n, uint32_t tag) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) mark[list[i]] = tag;
+}
+__global__ void k_check_independent(View e, const uint32_t* mark, const uint32_t* list, uint32_t n, uint32_t tag) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint32_t s = list[i];
+    for (uint32_t k = e.dep_off[s]; k < e.dep_off[s + 1]; ++k)
+        if (mark[e.dep_ids[k]] == tag) atomicOr(e.err_flag, ERR_INDEPENDENCE);
+}
+
+// ---- values ------------------------------------------------------------------------------------------------
+template <class T>
+__global__ void k_write_values(T* val, int dim, const uint32_t* list, const T* src, uint32_t n) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (size_t)n * dim) return;
+    val[(size_t)list[i / dim] * dim + (i % dim)] = src[i];
+}
+template <class T>
+__global__ void k_gather_values(const T* val, int dim, const uint32_t* list, T* dst, uint32_t n) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (size_t)n * dim) return;
+    dst[i] = val[(size_t)list[i / dim] * dim + (i % dim)];
+}
+__global__ void k_pending_single(View e, uint32_t s, int* out) { *out = pending_eval(e, s) ? 1 : 0; }
+
+// ---- rule kernels ----------------------------------------------------------------------------------------------
+// Small fixed-size values (dim <= 4): one thread per signal. Families GAUSS_CANON / GAUSS_MV / BETA / SUM and
+// the scalar m2v rules. rule < 0 => family reduce (m2f / ProductOfMessages / marginal), left-to-right
+// (test/inference_engine_tests.jl:385-413).
+template <class T>
+__global__ void k_rule_small(View e, T* __restrict__ val, const uint32_t* list, uint32_t n, int family, int rule,
+                             const T* __restrict__ fparam, T default_param) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint32_t s = list[i];
+    const int dim = e.dim;
+    uint32_t off = e.dep_off[s], nd = e.dep_off[s + 1] - off;
+    T acc[4] = {0, 0, 0, 0};
+    if (nd == 0) {
+        atomicOr(e.err_flag, ERR_RULE_ARG);
+        return;
+    }
+    {
+        const T* a = val + (size_t)e.dep_ids[off] * dim;
+        for (int k = 0; k < dim; ++k) acc[k] = a[k];
+    }
+    if (rule < 0) {
+        for (uint32_t j = 1; j < nd; ++j) {
+            const T* b = val + (size_t)e.dep_ids[off + j] * dim;
+            if (family == CXB_FAMILY_GAUSS_CANON || family == CXB_FAMILY_SUM) {
+                for (int k = 0; k < dim; ++k) acc[k] = acc[k] + b[k];
+            } else if (family == CXB_FAMILY_GAUSS_MV) {  // test/runtests.jl:40-46
+                T xi = acc[0] / acc[1] + b[0] / b[1];
+                T w = T(1) / acc[1] + T(1) / b[1];
+                T variance = T(1) / w;
+                acc[0] = variance * xi;
+                acc[1] = variance;
+            } else if (family == CXB_FAMILY_BETA) {  // test/inference_engine_tests.jl:273-278
+                acc[0] = acc[0] + b[0] - T(1);
+                acc[1] = acc[1] + b[1] - T(1);
+            }
+        }
+    } else {
+        T p = default_param;
+        if (fparam) {
+            T fp = fparam[e.sfac[s]];
+            if (fp == fp) p = fp;  // NaN = "not set": use the rule default
+        }
+        switch (rule) {
+            case CXB_RULE_GAUSS_OBS: {
+                T y = acc[0];
+                acc[0] = T(1) / p;
+                acc[1] = y / p;
+                break;
+            }
+            case CXB_RULE_GAUSS_RW: {
+                T den = T(1) + p * acc[0];
+                acc[0] = acc[0] / den;
+                acc[1] = acc[1] / den;
+                break;
+            }
+            case CXB_RULE_GAUSS_MV_OBS:
+                acc[1] = p;
+                break;
+            case CXB_RULE_GAUSS_MV_RW:
+                acc[1] = acc[1] + p;
+                break;
+            case CXB_RULE_BETA_BERNOULLI: {
+                T r = acc[0];
+                acc[0] = T(1) + r;
+                acc[1] = T(2) - r;
+                break;
+            }
+            case CXB_RULE_SCALE2:
+                for (int k = 0; k < dim; ++k) acc[k] = T(2) * acc[k];
+                break;
+            default:
+                atomicOr(e.err_flag, ERR_RULE_ARG);
+                return;
+        }
+    }
+    T* o = val + (size_t)s * dim;
+    for (int k = 0; k < dim; ++k) o[k] = acc[k];
+}
+
+// Categorical values (dim = K states): G lanes cooperate on one signal (G = min(32, pow2 >= K)), lane l owns
+// components l, l+G, ... . rule < 0: element-wise product of the dependencies, normalised (App. C);
+// CAT_TABLE: out[a] = sum_b psi(a,b) in[b] with the table staged in shared memory; POTTS: closed form;
+// HMM_EMIT: column of the emission table.  Normalisation by warp-shuffle reduction.
+template <class T, int G, int MAXC>
+__global__ void k_rule_cat(View e, T* __restrict__ val, const uint32_t* list, uint32_t n, int rule,
+                           const T* __restrict__ table, const T* __restrict__ table_t, int n_sym, T potts_w) {
+    extern __shared__ unsigned char smem_raw[];
+    T* sh = reinterpret_cast<T*>(smem_raw);
+    const int K = e.dim;
+    const int groups_per_block = blockDim.x / G;
+    T* sh_table = sh;                                   // K*K (both orientations) when CAT_TABLE
+    T* sh_in = sh + (rule == CXB_RULE_CAT_TABLE ? 2 * (size_t)K * K : 0);  // per group K staging
+    if (rule == CXB_RULE_CAT_TABLE) {
+        for (int t = threadIdx.x; t < K * K; t += blockDim.x) {
+            sh_table[t] = table[t];            // [x_lo][x_hi]
+            sh_table[K * K + t] = table_t[t];  // [x_hi][x_lo]
+        }
+    }
+    __syncthreads();
+    const int g = threadIdx.x / G, lane = threadIdx.x % G;
+    const unsigned gmask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << ((threadIdx.x & 31) / G * G));
+    uint32_t i = blockIdx.x * groups_per_block + g;
+    const bool active = i < n;
+    uint32_t s = active ? list[i] : 0;
+    uint32_t off = active ? e.dep_off[s] : 0, nd = active ? e.dep_off[s + 1] - off : 0;
+    T acc[MAXC];
+#pragma unroll
+    for (int c = 0; c < MAXC; ++c) acc[c] = T(0);
+    if (active && nd == 0) atomicOr(e.err_flag, ERR_RULE_ARG);
+    if (active && nd > 0) {
+        const T* a = val + (size_t)e.dep_ids[off] * K;
+#pragma unroll
+        for (int c = 0; c < MAXC; ++c) {
+            int k = lane + c * G;
+            if (k < K) acc[c] = a[k];
+        }
+    }
+    if (rule < 0) {
+        for (uint32_t j = 1; j < nd; ++j) {
+            const T* b = val + (size_t)e.dep_ids[off + j] * K;
+#pragma unroll
+            for (int c = 0; c < MAXC; ++c) {
+                int k = lane + c * G;
+                if (k < K) acc[c] = acc[c] * b[k];
+            }
+        }
+    } else if (rule == CXB_RULE_POTTS) {
+        T part = T(0);
+#pragma unroll
+        for (int c = 0; c < MAXC; ++c) part += acc[c];
+        for (int o = G / 2; o > 0; o >>= 1) part += __shfl_xor_sync(gmask, part, o, G);
+#pragma unroll
+        for (int c = 0; c < MAXC; ++c) acc[c] = part + potts_w * acc[c];  // sum_b in[b] + (e^beta - 1) in[a]
+    } else if (rule == CXB_RULE_CAT_TABLE) {
+        // stage the incoming message, then every lane contracts its own output components
+        T* my_in = sh_in + (size_t)g * K;
+#pragma unroll
+        for (int c = 0; c < MAXC; ++c) {
+            int k = lane + c * G;
+            if (k < K) my_in[k] = acc[c];
+        }
+        __syncwarp(gmask);
+        bool u_is_low = false;
+        if (active && nd > 0) u_is_low = e.svar[e.dep_ids[off]] < e.svar[s];
+        // u low : out[a] = sum_b psi[b][a] in[b] -> table  [b*K + a];  u high: out[a] = sum_b psi[a][b] in[b] -> table_t[b*K + a]
+        const T* tb = sh_table + (u_is_low ? 0 : (size_t)K * K);
+#pragma unroll
+        for (int c = 0; c < MAXC; ++c) {
+            int a = lane + c * G;
+            T sum = T(0);
+            if (a < K)
+                for (int b = 0; b < K; ++b) sum += tb[b * K + a] * my_in[b];
+            acc[c] = sum;
+        }
+        __syncwarp(gmask);
+    } else if (rule == CXB_RULE_HMM_EMIT) {
+        int o = 0;
+        if (active && nd > 0) {
+            o = (int)val[(size_t)e.dep_ids[off] * K];
+            if (o < 0 || o >= n_sym) {
+                atomicOr(e.err_flag, ERR_RULE_ARG);
+                o = 0;
+            }
+        }
+#pragma unroll
+        for (int c = 0; c < MAXC; ++c) {
+            int a = lane + c * G;
+            acc[c] = (a < K) ? table[(size_t)a * n_sym + o] : T(0);
+        }
+    }
+    // normalise to sum 1
+    T part = T(0);
+#pragma unroll
+    for (int c = 0; c < MAXC; ++c) part += acc[c];
+    for (int o = G / 2; o > 0; o >>= 1) part += __shfl_xor_sync(gmask, part, o, G);
+    if (active && nd > 0) {
+        T* o = val + (size_t)s * K;
+#pragma unroll
+        for (int c = 0; c < MAXC; ++c) {
+            int k = lane + c * G;
+            if (k < K) o[k] = acc[c] / part;
+        }
+    }
+}
+
+// =================================================================================================================
+struct RuleDef {
+    int kind = CXB_RULE_NONE;
+    std::vector<double> params;
+};
+
+struct DeviceEngine {
+    int device = 0, dtype = CXB_F64, dim = 1, family = 0;
+    cudaStream_t stream = nullptr;
+    std::string err;
+    HostGraph g;
+    Csr csr;
+    bool structure_dirty = true, device_live = false, rules_dirty = true, trace_on = false;
+    bool host_state_valid = true;            // host mirrors (props, C/F nibbles, values) equal the device state
+    std::vector<unsigned char> host_vals;    // value mirror, valid with host_state_valid
+    std::vector<uint32_t> lnk_off, lnk_ids;  // linked signals per variable id (CSR), rebuilt when links change
+    bool links_dirty = true;
+    std::map<int32_t, RuleDef> rules;     // by factor type
+    std::vector<int32_t> key_ftype;       // key-1 -> factor type
+    std::vector<double> fparam;           // per id, NaN = unset
+    uint32_t req_epoch = 0, lvl_epoch = 0, mark_tag = 0;
+    size_t n_uploaded = 0;
+
+    // device state
+    DBuf<uint32_t> d_dep_off, d_dep_ids, d_nib_off, d_lis_off, d_lis_ids, d_lis_slot, d_done, d_visit, d_mark;
+    DBuf<uint64_t> d_nib;
+    DBuf<uint8_t> d_lis_listen, d_props, d_kind, d_rkey, d_front_flag;
+    DBuf<int32_t> d_svar, d_sfac;
+    DBuf<unsigned char> d_val, d_fparam, d_tables, d_stage_val;
+    DBuf<uint32_t> d_list_a, d_list_b, d_front, d_tile_hist, d_key_count, d_req_marg, d_link_off, d_link_ids, d_stage_ids;
+    DBuf<uint8_t> d_ready;
+    DBuf<int> d_flags;  // [0] err flag, [1] scratch int
+    DBuf<uint32_t> d_counters;
+    DBuf<unsigned long long> d_kind_count;
+    HBuf<uint32_t> h_counts;
+    HBuf<unsigned char> h_stage;
+    HBuf<int> h_flags;
+    HBuf<unsigned long long> h_kind_count;
+    std::map<int32_t, std::pair<size_t, size_t>> table_off;  // factor type -> (offset, count) in d_tables (elements)
+
+    // request
+    std::vector<int64_t> req_ids;
+    std::vector<uint32_t> h_req_marg, h_link_off, h_link_ids;
+    bool req_uploaded = false;
+    uint32_t n_req = 0;
+
+    // trace of the last update
+    std::vector<int64_t> tr_level, tr_sid;
+    cxb_update_stats stats{};
+
+    size_t esz() const { return dtype == CXB_F32 ? 4 : 8; }
+
+    ~DeviceEngine() {
+        if (stream) cudaStreamDestroy(stream);
+    }
+
+    int32_t init() {
+        int count = 0;
+        cudaError_t e0 = cudaGetDeviceCount(&count);
+        if (e0 != cudaSuccess || count == 0) {
+            err = "no CUDA device available (cortex_b200 has no CPU fallback)";
+            return CXB_ERR_CUDA;
+        }
+        if (device < 0 || device >= count) {
+            err = "bad device index";
+            return CXB_ERR_BAD_ARG;
+        }
+        CXB_CUDA(cudaSetDevice(device));
+        CXB_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+        CXB_CUDA(d_flags.reserve(4));
+        CXB_CUDA(d_counters.reserve(8));
+        CXB_CUDA(d_kind_count.reserve(8));
+        CXB_CUDA(h_counts.reserve(1024));
+        CXB_CUDA(h_flags.reserve(4));
+        CXB_CUDA(h_kind_count.reserve(8));
+        CXB_CUDA(cudaMemsetAsync(d_flags.p, 0, 4 * sizeof(int), stream));
+        CXB_CUDA(cudaMemsetAsync(d_kind_count.p, 0, 8 * sizeof(unsigned long long), stream));
+        return CXB_OK;
+    }
+
+    View view() {
+        View v;
+        v.n_sig = (uint32_t)g.n_sig();
+        v.dim = dim;
+        v.dep_off = d_dep_off.p;
+        v.dep_ids = d_dep_ids.p;
+        v.nib_off = d_nib_off.p;
+        v.nib = d_nib.p;
+        v.lis_off = d_lis_off.p;
+        v.lis_ids = d_lis_ids.p;
+        v.lis_slot = d_lis_slot.p;
+        v.lis_listen = d_lis_listen.p;
+        v.props = d_props.p;
+        v.kind = d_kind.p;
+        v.rkey = d_rkey.p;
+        v.svar = d_svar.p;
+        v.sfac = d_sfac.p;
+        v.done_epoch = d_done.p;
+        v.visit_epoch = d_visit.p;
+        v.front_flag = d_front_flag.p;
+        v.err_flag = d_flags.p;
+        v.kind_count = d_kind_count.p;
+        return v;
+    }
+
+    template <class T>
+    int32_t up(DBuf<T>& d, const T* src, size_t n) {
+        CXB_CUDA(d.reserve(n));
+        if (n) CXB_CUDA(cudaMemcpyAsync(d.p, src, n * sizeof(T), cudaMemcpyHostToDevice, stream));
+        return CXB_OK;
+    }
+
+    // bring the dynamic state back to the host mirrors before a structural change
+    int32_t sync_host() {
+        if (!device_live || host_state_valid) return CXB_OK;
+        CXB_CUDA(cudaSetDevice(device));
+        int32_t st = download_state(host_vals);
+        if (st) return st;
+        host_state_valid = true;
+        return CXB_OK;
+    }
+    int32_t download_state(std::vector<unsigned char>& values_out) {
+        size_t N = n_uploaded;
+        CXB_CUDA(cudaMemcpyAsync(g.props.data(), d_props.p, N, cudaMemcpyDeviceToHost, stream));
+        CXB_CUDA(cudaMemcpyAsync(csr.nib.data(), d_nib.p, csr.nib.size() * sizeof(uint64_t), cudaMemcpyDeviceToHost, stream));
+        values_out.resize(N * dim * esz());
+        if (N) CXB_CUDA(cudaMemcpyAsync(values_out.data(), d_val.p, values_out.size(), cudaMemcpyDeviceToHost, stream));
+        CXB_CUDA(cudaStreamSynchronize(stream));
+        // csr still describes the uploaded structure: only the first E_old log entries existed then
+        HostGraph& gg = g;
+        size_t E_old = csr.edge_pos.size();
+        for (size_t e = 0; e < E_old; ++e) {
+            uint32_t s = (uint32_t)gg.e_sig[e];
+            uint32_t slot = csr.edge_pos[e] - csr.dep_off[s];
+            uint64_t nibble = (csr.nib[csr.nib_off[s] + (slot >> 4)] >> ((slot & 15) << 2)) & 0xF;
+            gg.e_nib[e] = (uint8_t)(nibble & 0xC);
+        }
+        return CXB_OK;
+    }
+
+    int32_t build_keys() {
+        // rule key per signal: 0 = family reduce, 1.. = m2v of factor type, 255 = no rule (Unspecified / Joint)
+        std::map<int32_t, int> key_of;
+        key_ftype.clear();
+        for (int64_t f : g.factors)
+            if (!key_of.count(g.ftype[f])) {
+                key_of[g.ftype[f]] = (int)key_ftype.size() + 1;
+                key_ftype.push_back(g.ftype[f]);
+            }
+        if (key_ftype.size() > 250) {
+            err = "more than 250 distinct factor types";
+            return CXB_ERR_BAD_ARG;
+        }
+        size_t N = (size_t)g.n_sig();
+        std::vector<uint8_t> rkey(N);
+        std::vector<int32_t> svar(N), sfac(N);
+        for (size_t s = 0; s < N; ++s) {
+            uint8_t k = g.kind[s];
+            svar[s] = (int32_t)g.svar[s];
+            sfac[s] = (int32_t)g.sfac[s];
+            if (k == CXB_KIND_M2F || k == CXB_KIND_PRODUCT || k == CXB_KIND_MARGINAL)
+                rkey[s] = KEY_COMBINE;
+            else if (k == CXB_KIND_M2V)
+                rkey[s] = (uint8_t)key_of[g.ftype[g.sfac[s]]];
+            else
+                rkey[s] = (uint8_t)key_no_rule();
+        }
+        int32_t st;
+        if ((st = up(d_rkey, rkey.data(), N))) return st;
+        if ((st = up(d_svar, svar.data(), N))) return st;
+        if ((st = up(d_sfac, sfac.data(), N))) return st;
+        if ((st = up(d_kind, g.kind.data(), N))) return st;
+        CXB_CUDA(cudaStreamSynchronize(stream));
+        return CXB_OK;
+    }
+
+    int32_t upload_rules() {
+        // tables: CAT_TABLE psi and its transpose, HMM emission; per-factor params
+        std::vector<double> all;
+        table_off.clear();
+        for (auto& kv : rules) {
+            const RuleDef& r = kv.second;
+            if (r.kind == CXB_RULE_CAT_TABLE) {
+                if ((int64_t)r.params.size() != (int64_t)dim * dim) {
+                    err = "CAT_TABLE needs value_dim*value_dim parameters";
+                    return CXB_ERR_BAD_ARG;
+                }
+                table_off[kv.first] = {all.size(), r.params.size()};
+                all.insert(all.end(), r.params.begin(), r.params.end());
+                for (int a = 0; a < dim; ++a)
+                    for (int b = 0; b < dim; ++b) all.push_back(r.params[(size_t)b * dim + a]);  // transpose
+            } else if (r.kind == CXB_RULE_HMM_EMIT) {
+                if (r.params.empty() || (int64_t)r.params.size() != 1 + (int64_t)dim * (int64_t)r.params[0]) {
+                    err = "HMM_EMIT needs {M, E[K][M]} parameters";
+                    return CXB_ERR_BAD_ARG;
+                }
+                table_off[kv.first] = {all.size(), r.params.size() - 1};
+                all.insert(all.end(), r.params.begin() + 1, r.params.end());
+            }
+        }
+        size_t n = all.size();
+        std::vector<unsigned char> raw(std::max<size_t>(n, 1) * esz());
+        for (size_t i = 0; i < n; ++i) {
+            if (dtype == CXB_F32)
+                ((float*)raw.data())[i] = (float)all[i];
+            else
+                ((double*)raw.data())[i] = all[i];
+        }
+        int32_t st;
+        if ((st = up(d_tables, raw.data(), raw.size()))) return st;
+        std::vector<unsigned char> fp((size_t)std::max<int64_t>(g.n_ids, 1) * esz());
+        for (int64_t i = 0; i < g.n_ids; ++i) {
+            double v = (i < (int64_t)fparam.size()) ? fparam[i] : NAN;
+            if (dtype == CXB_F32)
+                ((float*)fp.data())[i] = (float)v;
+            else
+                ((double*)fp.data())[i] = v;
+        }
+        if ((st = up(d_fparam, fp.data(), fp.size()))) return st;
+        CXB_CUDA(cudaStreamSynchronize(stream));
+        rules_dirty = false;
+        return CXB_OK;
+    }
+
+    // (re)build the CSR and upload everything; keeps the dynamic state across structural changes
+    int32_t ensure_device() {
+        if (!stream) {
+            err = "engine not initialised";
+            return CXB_ERR_STATE;
+        }
+        CXB_CUDA(cudaSetDevice(device));
+        int32_t st;
+        if (structure_dirty) {
+            size_t N_old = 0;
+            if (device_live) {
+                if ((st = sync_host())) return st;
+                N_old = n_uploaded;
+            }
+            std::vector<unsigned char>& old_vals = host_vals;
+            build_csr(g, csr);
+            size_t N = (size_t)g.n_sig(), E = csr.dep_ids.size();
+            if ((st = up(d_dep_off, csr.dep_off.data(), N + 1))) return st;
+            if ((st = up(d_dep_ids, csr.dep_ids.data(), E))) return st;
+            if ((st = up(d_nib_off, csr.nib_off.data(), N + 1))) return st;
+            if ((st = up(d_nib, csr.nib.data(), csr.nib.size()))) return st;
+            if ((st = up(d_lis_off, csr.lis_off.data(), N + 1))) return st;
+            if ((st = up(d_lis_ids, csr.lis_ids.data(), E))) return st;
+            if ((st = up(d_lis_slot, csr.lis_slot.data(), E))) return st;
+            if ((st = up(d_lis_listen, csr.lis_listen.data(), E))) return st;
+            if ((st = up(d_props, g.props.data(), N))) return st;
+            // values: keep the old ones, zero the new signals
+            {
+                std::vector<unsigned char> vals(std::max<size_t>(N, 1) * dim * esz(), 0);
+                if (N_old) std::memcpy(vals.data(), old_vals.data(), std::min(old_vals.size(), vals.size()));
+                if ((st = up(d_val, vals.data(), vals.size()))) return st;
+                CXB_CUDA(cudaStreamSynchronize(stream));
+            }
+            size_t Np = std::max<size_t>(N, 1);
+            CXB_CUDA(d_done.reserve(Np));
+            CXB_CUDA(d_visit.reserve(Np));
+            CXB_CUDA(d_mark.reserve(Np));
+            CXB_CUDA(d_front_flag.reserve(Np));
+            CXB_CUDA(d_list_a.reserve(Np));
+            CXB_CUDA(d_list_b.reserve(Np));
+            CXB_CUDA(d_front.reserve(Np));
+            CXB_CUDA(cudaMemsetAsync(d_done.p, 0, Np * 4, stream));
+            CXB_CUDA(cudaMemsetAsync(d_visit.p, 0, Np * 4, stream));
+            CXB_CUDA(cudaMemsetAsync(d_mark.p, 0, Np * 4, stream));
+            CXB_CUDA(cudaMemsetAsync(d_front_flag.p, 0, Np, stream));
+            req_epoch = lvl_epoch = mark_tag = 0;
+            if ((st = build_keys())) return st;
+            size_t n_tiles = cdiv(Np, MS_TILE);
+            CXB_CUDA(d_tile_hist.reserve(n_tiles * (size_t)n_keys() + 1));
+            CXB_CUDA(d_key_count.reserve(512));
+            CXB_CUDA(cudaStreamSynchronize(stream));
+            n_uploaded = N;
+            structure_dirty = false;
+            device_live = true;
+            rules_dirty = true;
+            req_uploaded = false;
+        }
+        if (rules_dirty && (st = upload_rules())) return st;
+        host_state_valid = false;  // whatever runs next may mutate the device state
+        return CXB_OK;
+    }
+
+    int n_keys() const { return (int)key_ftype.size() + 2; }
+    int key_no_rule() const { return (int)key_ftype.size() + 1; }
+
+    // ordered compaction of the flagged signals, grouped by rule key; counts/offsets land in h_counts[0..2*nk)
+    int32_t compact(bool use_keys, uint32_t& total) {
+        uint32_t N = (uint32_t)g.n_sig();
+        int nk = use_keys ? n_keys() : 1;
+        uint32_t n_tiles = cdiv(std::max<uint32_t>(N, 1), MS_TILE);
+        View v = view();
+        CXB_LAUNCH(k_ms_hist, n_tiles, MS_THREADS, nk * sizeof(uint32_t), stream, v.front_flag, v.rkey, N, d_tile_hist.p,
+                   n_tiles, nk, use_keys ? 1 : 0);
+        CXB_LAUNCH(k_ms_scan, 1, 1024, 0, stream, d_tile_hist.p, n_tiles, nk, d_key_count.p);
+        CXB_LAUNCH(k_ms_scatter, n_tiles, MS_THREADS, (size_t)nk * (1 + MS_THREADS / 32) * sizeof(uint32_t), stream,
+                   v.front_flag, v.rkey, N, d_tile_hist.p, n_tiles, nk, use_keys ? 1 : 0, d_front.p);
+        CXB_CUDA(cudaMemcpyAsync(h_counts.p, d_key_count.p, 2 * nk * sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
+        CXB_CUDA(cudaMemcpyAsync(h_flags.p, d_flags.p, sizeof(int), cudaMemcpyDeviceToHost, stream));
+        CXB_CUDA(cudaStreamSynchronize(stream));
+        total = 0;
+        for (int k = 0; k < nk; ++k) total += h_counts.p[k];
+        return CXB_OK;
+    }
+
+    // breadth-first reachability from `seeds` (already in d_list_a, count in n_seed): flags pending signals
+    int32_t bfs(uint32_t n_seed, bool use_done) {
+        ++lvl_epoch;
+        uint32_t n_in = n_seed;
+        uint32_t *in = d_list_a.p, *out = d_list_b.p;
+        View v = view();
+        while (n_in > 0) {
+            CXB_CUDA(cudaMemsetAsync(d_counters.p, 0, sizeof(uint32_t), stream));
+            CXB_LAUNCH(k_bfs, cdiv(n_in, 256), 256, 0, stream, v, in, n_in, out, d_counters.p, lvl_epoch, req_epoch,
+                       use_done ? 1 : 0);
+            CXB_CUDA(cudaMemcpyAsync(h_counts.p + 600, d_counters.p, sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
+            CXB_CUDA(cudaStreamSynchronize(stream));
+            n_in = h_counts.p[600];
+            std::swap(in, out);
+        }
+        return CXB_OK;
+    }
+
+    template <class T>
+    int32_t launch_rules_t(uint32_t total) {
+        View v = view();
+        T* val = (T*)d_val.p;
+        const int nk = n_keys();
+        bool categorical = family == CXB_FAMILY_CATEGORICAL;
+        if (!categorical && dim > 4) {
+            err = "value_dim > 4 is only supported for the categorical family";
+            return CXB_ERR_BAD_ARG;
+        }
+        for (int k = 0; k < nk; ++k) {
+            uint32_t cnt = h_counts.p[k], off = h_counts.p[nk + k];
+            if (!cnt) continue;
+            if (k == key_no_rule()) {
+                err = "Unprocessed signal variant (no rule for an Unspecified / JointMarginal signal)";
+                return CXB_ERR_NO_RULE;
+            }
+            int rule = -1;
+            const RuleDef* rd = nullptr;
+            if (k != KEY_COMBINE) {
+                auto it = rules.find(key_ftype[k - 1]);
+                if (it == rules.end() || it->second.kind == CXB_RULE_NONE) {
+                    err = "The function `compute_message_to_variable!` is not implemented for factor type " +
+                          std::to_string(key_ftype[k - 1]);
+                    return CXB_ERR_NO_RULE;
+                }
+                rd = &it->second;
+                rule = rd->kind;
+            }
+            const uint32_t* list = d_front.p + off;
+            bool cat_rule = rule == CXB_RULE_CAT_TABLE || rule == CXB_RULE_POTTS || rule == CXB_RULE_HMM_EMIT;
+            if (categorical && (rule < 0 || cat_rule)) {
+                const T* tb = nullptr;
+                const T* tbt = nullptr;
+                int n_sym = 0;
+                T w = T(0);
+                if (rule == CXB_RULE_CAT_TABLE) {
+                    tb = (const T*)d_tables.p + table_off[key_ftype[k - 1]].first;
+                    tbt = tb + (size_t)dim * dim;
+                } else if (rule == CXB_RULE_HMM_EMIT) {
+                    tb = (const T*)d_tables.p + table_off[key_ftype[k - 1]].first;
+                    n_sym = (int)rd->params[0];
+                } else if (rule == CXB_RULE_POTTS) {
+                    w = (T)(std::exp(rd->params.empty() ? 0.0 : rd->params[0]) - 1.0);
+                }
+                int G = 1;
+                while (G < dim && G < 32) G <<= 1;
+                int maxc = (dim + G - 1) / G;
+                const int threads = 256;
+                int gpb = threads / G;
+                size_t smem = ((rule == CXB_RULE_CAT_TABLE ? 2 * (size_t)dim * dim : 0) + (size_t)gpb * dim) * sizeof(T);
+                if (smem > 200 * 1024 || maxc > 16) {
+                    err = "categorical value_dim too large for the generic engine (use the structured HMM engine)";
+                    return CXB_ERR_BAD_ARG;
+                }
+                unsigned grid = cdiv(cnt, gpb);
+#define CAT_LAUNCH(GG, MC)                                                                                        \
+    do {                                                                                                          \
+        if (smem > 48 * 1024)                                                                                     \
+            cudaFuncSetAttribute(k_rule_cat<T, GG, MC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);   \
+        CXB_LAUNCH((k_rule_cat<T, GG, MC>), grid, threads, smem, stream, v, val, list, cnt, rule, tb, tbt, n_sym, w); \
+    } while (0)
+                if (G == 1) CAT_LAUNCH(1, 1);
+                else if (G == 2) CAT_LAUNCH(2, 1);
+                else if (G == 4) CAT_LAUNCH(4, 1);
+                else if (G == 8) CAT_LAUNCH(8, 1);
+                else if (G == 16) CAT_LAUNCH(16, 1);
+                else if (maxc == 1) CAT_LAUNCH(32, 1);
+                else if (maxc == 2) CAT_LAUNCH(32, 2);
+                else if (maxc <= 4) CAT_LAUNCH(32, 4);
+                else if (maxc <= 8) CAT_LAUNCH(32, 8);
+                else CAT_LAUNCH(32, 16);
+#undef CAT_LAUNCH
+            } else if (!categorical && !cat_rule) {
+                T defp = (T)((rd && !rd->params.empty()) ? rd->params[0] : 1.0);
+                CXB_LAUNCH(k_rule_small<T>, cdiv(cnt, 256), 256, 0, stream, v, val, list, cnt, family, rule,
+                           (const T*)d_fparam.p, defp);
+            } else {
+                err = "rule kind does not match the engine's value family";
+                return CXB_ERR_BAD_ARG;
+            }
+        }
+        (void)total;
+        return CXB_OK;
+    }
+    int32_t launch_rules(uint32_t total) {
+        return dtype == CXB_F32 ? launch_rules_t<float>(total) : launch_rules_t<double>(total);
+    }
+
+    int32_t check_flags() {
+        CXB_CUDA(cudaMemcpyAsync(h_flags.p, d_flags.p, sizeof(int), cudaMemcpyDeviceToHost, stream));
+        CXB_CUDA(cudaStreamSynchronize(stream));
+        int f = h_flags.p[0];
+        if (!f) return CXB_OK;
+        cudaMemsetAsync(d_flags.p, 0, sizeof(int), stream);
+        if (f & ERR_RULE_ARG) {
+            err = "rule kernel rejected its arguments (no dependencies, symbol out of range or unknown rule kind)";
+            return CXB_ERR_NO_RULE;
+        }
+        if (f & ERR_INDEPENDENCE)
+            err = "level-synchronous schedule out of contract: frontier member depends on another member";
+        else
+            err = "level-synchronous schedule out of contract: a dependency is recomputed after its listener within one "
+                  "request (order-dependent in the reference)";
+        return CXB_ERR_OUT_OF_CONTRACT;
+    }
+
+    // evaluate + apply one compacted level (the frontier is in d_front, counts in h_counts)
+    int32_t run_level(uint32_t total, int check_mode, int64_t level_tag) {
+        if (!total) return CXB_OK;
+        View v = view();
+        int32_t st;
+        ++mark_tag;
+        CXB_LAUNCH(k_mark, cdiv(total, 256), 256, 0, stream, d_mark.p, d_front.p, total, mark_tag);
+        CXB_LAUNCH(k_check_independent, cdiv(total, 256), 256, 0, stream, v, d_mark.p, d_front.p, total, mark_tag);
+        if ((st = check_flags())) return st;
+        if ((st = launch_rules(total))) return st;
+        CXB_LAUNCH(k_apply, cdiv(total, 256), 256, 0, stream, v, d_front.p, total, req_epoch, check_mode);
+        if ((st = check_flags())) return st;
+        stats.updates += total;
+        if (trace_on) {
+            std::vector<uint32_t> ids(total);
+            CXB_CUDA(cudaMemcpyAsync(ids.data(), d_front.p, total * sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
+            CXB_CUDA(cudaStreamSynchronize(stream));
+            std::sort(ids.begin(), ids.end());
+            for (uint32_t s : ids) {
+                tr_level.push_back(level_tag);
+                tr_sid.push_back(s);
+            }
+        }
+        return CXB_OK;
+    }
+
+    int32_t request(int64_t n, const int64_t* ids) {
+        int32_t st = ensure_device();
+        if (st) return st;
+        bool same = req_uploaded && (int64_t)req_ids.size() == n && (n == 0 || !std::memcmp(req_ids.data(), ids, n * 8));
+        if (!same) {
+            req_ids.assign(ids, ids + n);
+            h_req_marg.resize(n);
+            h_link_off.assign(n + 1, 0);
+            h_link_ids.clear();
+            // linked signals per variable, in link order (src/model_engine.jl:80-83)
+            if (links_dirty) {
+                lnk_off.assign((size_t)g.n_ids + 1, 0);
+                for (auto& l : g.links) ++lnk_off[(size_t)l.first + 1];
+                for (int64_t i = 0; i < g.n_ids; ++i) lnk_off[i + 1] += lnk_off[i];
+                lnk_ids.resize(g.links.size());
+                std::vector<uint32_t> cur(lnk_off.begin(), lnk_off.end() - 1);
+                for (auto& l : g.links) lnk_ids[cur[(size_t)l.first]++] = (uint32_t)l.second;
+                links_dirty = false;
+            }
+            for (int64_t i = 0; i < n; ++i) {
+                int64_t v = ids[i];
+                if (v < 0 || v >= g.n_ids || g.is_factor[v] || g.marg_of[v] < 0) {
+                    err = "request_inference_for: not a variable id";
+                    return CXB_ERR_BAD_ARG;
+                }
+                h_req_marg[i] = (uint32_t)g.marg_of[v];
+                for (uint32_t k = lnk_off[v]; k < lnk_off[v + 1]; ++k) h_link_ids.push_back(lnk_ids[k]);
+                h_link_off[i + 1] = (uint32_t)h_link_ids.size();
+            }
+            if ((st = up(d_req_marg, h_req_marg.data(), (size_t)n))) return st;
+            if ((st = up(d_link_off, h_link_off.data(), (size_t)n + 1))) return st;
+            if ((st = up(d_link_ids, h_link_ids.data(), h_link_ids.size()))) return st;
+            CXB_CUDA(d_ready.reserve(std::max<size_t>(n, 1)));
+            CXB_CUDA(cudaStreamSynchronize(stream));
+            req_uploaded = true;
+        }
+        n_req = (uint32_t)n;
+        ++req_epoch;
+        CXB_CUDA(cudaMemsetAsync(d_ready.p, 0, std::max<size_t>(n, 1), stream));
+        if (n) CXB_LAUNCH(k_request, cdiv(n, 256), 256, 0, stream, view(), d_req_marg.p, d_link_off.p, d_link_ids.p, n_req);
+        return CXB_OK;
+    }
+
+    int32_t seeds(uint32_t& n_seed) {
+        CXB_CUDA(cudaMemsetAsync(d_counters.p + 1, 0, sizeof(uint32_t), stream));
+        if (n_req)
+            CXB_LAUNCH(k_seeds, cdiv(n_req, 256), 256, 0, stream, d_req_marg.p, d_ready.p, n_req, d_list_a.p, d_counters.p + 1);
+        CXB_CUDA(cudaMemcpyAsync(h_counts.p + 601, d_counters.p + 1, sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
+        CXB_CUDA(cudaStreamSynchronize(stream));
+        n_seed = h_counts.p[601];
+        return CXB_OK;
+    }
+
+    int32_t scan(std::vector<int64_t>& out) {
+        if (!req_uploaded) {
+            err = "scan_inference_request: no request";
+            return CXB_ERR_STATE;
+        }
+        int32_t st;
+        uint32_t n_seed = 0, total = 0;
+        if ((st = seeds(n_seed))) return st;
+        if ((st = bfs(n_seed, false))) return st;
+        if ((st = compact(false, total))) return st;
+        std::vector<uint32_t> ids(total);
+        if (total) CXB_CUDA(cudaMemcpy(ids.data(), d_front.p, total * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+        out.assign(ids.begin(), ids.end());
+        return CXB_OK;
+    }
+
+    int32_t update(int64_t n, const int64_t* ids) {
+        unsigned long long launches0 = g_kernel_launches;
+        stats = cxb_update_stats{};
+        tr_level.clear();
+        tr_sid.clear();
+        int32_t st = request(n, ids);
+        if (st) return st;
+        CXB_CUDA(cudaMemsetAsync(d_kind_count.p, 0, 8 * sizeof(unsigned long long), stream));
+        int64_t level = 0;
+        for (;;) {
+            uint32_t n_seed = 0, total = 0;
+            if ((st = seeds(n_seed))) return st;
+            if (!n_seed) break;
+            if ((st = bfs(n_seed, true))) return st;
+            if ((st = compact(true, total))) return st;
+            if (!total) break;
+            if ((st = run_level(total, 1, level))) return st;
+            CXB_LAUNCH(k_ready, cdiv(n_req, 256), 256, 0, stream, view(), d_req_marg.p, d_ready.p, n_req);
+            ++stats.levels;
+            ++level;
+        }
+        for (int mode = 0; mode < 2 && n_req; ++mode) {  // final phase: marginals, then linked signals
+            uint32_t total = 0;
+            CXB_LAUNCH(k_final_flags, cdiv(n_req, 256), 256, 0, stream, view(), d_req_marg.p, d_link_off.p, d_link_ids.p, n_req,
+                       mode);
+            if ((st = compact(true, total))) return st;
+            if ((st = run_level(total, 2, mode == 0 ? -1 : -2))) return st;
+            (mode == 0 ? stats.final_marginals : stats.final_linked) = total;
+        }
+        CXB_CUDA(cudaMemcpyAsync(h_kind_count.p, d_kind_count.p, 6 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, stream));
+        CXB_CUDA(cudaStreamSynchronize(stream));
+        for (int k = 0; k < 6; ++k) stats.updates_by_kind[k] = (int64_t)h_kind_count.p[k];
+        stats.kernel_launches = (int64_t)(g_kernel_launches - launches0);
+        return CXB_OK;
+    }
+
+    // bulk set_value!: sequential semantics; members that depend on each other are applied one by one
+    int32_t set_values(int64_t n, const int64_t* sids, const double* values, int64_t stride) {
+        int32_t st = ensure_device();
+        if (st) return st;
+        if (n == 0) return CXB_OK;
+        int64_t N = g.n_sig();
+        for (int64_t i = 0; i < n; ++i)
+            if (sids[i] < 0 || sids[i] >= N) {
+                err = "set_values: bad signal id";
+                return CXB_ERR_BAD_ARG;
+            }
+        bool independent = true;
+        if (n > 1) {
+            std::unordered_set<int64_t> members(sids, sids + n);
+            if ((int64_t)members.size() != n) independent = false;
+            for (int64_t i = 0; i < n && independent; ++i) {
+                uint32_t s = (uint32_t)sids[i];
+                for (uint32_t k = csr.dep_off[s]; k < csr.dep_off[s + 1]; ++k)
+                    if (members.count(csr.dep_ids[k])) {
+                        independent = false;
+                        break;
+                    }
+            }
+        }
+        if (!independent) {
+            for (int64_t i = 0; i < n; ++i)
+                if ((st = set_values_batch(1, sids + i, values + i * stride, stride))) return st;
+            return CXB_OK;
+        }
+        return set_values_batch(n, sids, values, stride);
+    }
+    int32_t set_values_batch(int64_t n, const int64_t* sids, const double* values, int64_t stride) {
+        size_t bytes = (size_t)n * dim * esz();
+        CXB_CUDA(h_stage.reserve(bytes + (size_t)n * 4));
+        uint32_t* hid = (uint32_t*)(h_stage.p);
+        unsigned char* hv = h_stage.p + (size_t)n * 4;
+        for (int64_t i = 0; i < n; ++i) {
+            hid[i] = (uint32_t)sids[i];
+            for (int k = 0; k < dim; ++k) {
+                double v = values[i * stride + k];
+                if (dtype == CXB_F32)
+                    ((float*)hv)[i * dim + k] = (float)v;
+                else
+                    ((double*)hv)[i * dim + k] = v;
+            }
+        }
+        CXB_CUDA(d_stage_ids.reserve((size_t)n));
+        CXB_CUDA(d_stage_val.reserve(bytes));
+        CXB_CUDA(cudaMemcpyAsync(d_stage_ids.p, hid, (size_t)n * 4, cudaMemcpyHostToDevice, stream));
+        CXB_CUDA(cudaMemcpyAsync(d_stage_val.p, hv, bytes, cudaMemcpyHostToDevice, stream));
+        unsigned grid = cdiv((size_t)n * dim, 256);
+        if (dtype == CXB_F32)
+            CXB_LAUNCH(k_write_values<float>, grid, 256, 0, stream, (float*)d_val.p, dim, d_stage_ids.p, (const float*)d_stage_val.p,
+                       (uint32_t)n);
+        else
+            CXB_LAUNCH(k_write_values<double>, grid, 256, 0, stream, (double*)d_val.p, dim, d_stage_ids.p,
+                       (const double*)d_stage_val.p, (uint32_t)n);
+        CXB_LAUNCH(k_apply, cdiv(n, 256), 256, 0, stream, view(), d_stage_ids.p, (uint32_t)n, req_epoch, 0);
+        CXB_CUDA(cudaStreamSynchronize(stream));  // the pinned staging buffer is reused by the next call
+        return CXB_OK;
+    }
+    int32_t get_values(int64_t n, const int64_t* sids, double* out, int64_t stride) {
+        int32_t st = ensure_device();
+        if (st) return st;
+        if (n == 0) return CXB_OK;
+        int64_t N = g.n_sig();
+        size_t bytes = (size_t)n * dim * esz();
+        CXB_CUDA(h_stage.reserve(bytes + (size_t)n * 4));
+        uint32_t* hid = (uint32_t*)(h_stage.p);
+        unsigned char* hv = h_stage.p + (size_t)n * 4;
+        for (int64_t i = 0; i < n; ++i) {
+            if (sids[i] < 0 || sids[i] >= N) {
+                err = "get_values: bad signal id";
+                return CXB_ERR_BAD_ARG;
+            }
+            hid[i] = (uint32_t)sids[i];
+        }
+        CXB_CUDA(d_stage_ids.reserve((size_t)n));
+        CXB_CUDA(d_stage_val.reserve(bytes));
+        CXB_CUDA(cudaMemcpyAsync(d_stage_ids.p, hid, (size_t)n * 4, cudaMemcpyHostToDevice, stream));
+        unsigned grid = cdiv((size_t)n * dim, 256);
+        if (dtype == CXB_F32)
+            CXB_LAUNCH(k_gather_values<float>, grid, 256, 0, stream, (const float*)d_val.p, dim, d_stage_ids.p, (float*)d_stage_val.p,
+                       (uint32_t)n);
+        else
+            CXB_LAUNCH(k_gather_values<double>, grid, 256, 0, stream, (const double*)d_val.p, dim, d_stage_ids.p,
+                       (double*)d_stage_val.p, (uint32_t)n);
+        CXB_CUDA(cudaMemcpyAsync(hv, d_stage_val.p, bytes, cudaMemcpyDeviceToHost, stream));
+        CXB_CUDA(cudaStreamSynchronize(stream));
+        for (int64_t i = 0; i < n; ++i)
+            for (int k = 0; k < dim; ++k)
+                out[i * stride + k] = dtype == CXB_F32 ? (double)((float*)hv)[i * dim + k] : ((double*)hv)[i * dim + k];
+        return CXB_OK;
+    }
+    int32_t is_pending(int64_t s, int& out) {
+        int32_t st = ensure_device();
+        if (st) return st;
+        CXB_LAUNCH(k_pending_single, 1, 1, 0, stream, view(), (uint32_t)s, d_flags.p + 1);
+        CXB_CUDA(cudaMemcpyAsync(h_flags.p + 1, d_flags.p + 1, sizeof(int), cudaMemcpyDeviceToHost, stream));
+        CXB_CUDA(cudaStreamSynchronize(stream));
+        out = h_flags.p[1];
+        return CXB_OK;
+    }
+    int32_t is_computed(int64_t s, int& out) {
+        int32_t st = ensure_device();
+        if (st) return st;
+        uint8_t p = 0;
+        CXB_CUDA(cudaMemcpyAsync(&p, d_props.p + s, 1, cudaMemcpyDeviceToHost, stream));
+        CXB_CUDA(cudaStreamSynchronize(stream));
+        out = (p & P_COMPUTED) ? 1 : 0;
+        return CXB_OK;
+    }
+    // compute!(strategy = registered rule / family reduce, signal; force, skip_if_no_listeners), src/signal.jl:392-410
+    int32_t compute(int64_t s, bool force, bool skip) {
+        int32_t st = ensure_device();
+        if (st) return st;
+        if (skip && g.lis_count[s] == 0) return CXB_OK;
+        int pend = 0;
+        if ((st = is_pending(s, pend))) return st;
+        if (!force && !pend) {
+            err = "Signal is not pending. Cannot compute a non-pending signal. Use `force=true` to force computation.";
+            return CXB_ERR_NOT_PENDING;
+        }
+        if (g.dep_count[s] == 0) {
+            err = "compute!: the signal has no dependencies to reduce";
+            return CXB_ERR_NO_RULE;
+        }
+        uint32_t id = (uint32_t)s;
+        CXB_CUDA(cudaMemcpyAsync(d_front.p, &id, 4, cudaMemcpyHostToDevice, stream));
+        CXB_CUDA(cudaStreamSynchronize(stream));
+        // a bare compute! on an Unspecified signal uses the family reduce as strategy
+        int key = g.kind[s] == CXB_KIND_M2V ? -2 : KEY_COMBINE;
+        for (int k = 0; k < 2 * n_keys(); ++k) h_counts.p[k] = 0;
+        if (key == -2) {
+            for (size_t k = 0; k < key_ftype.size(); ++k)
+                if (key_ftype[k] == g.ftype[g.sfac[s]]) key = (int)k + 1;
+        }
+        h_counts.p[key] = 1;
+        if ((st = launch_rules(1))) return st;
+        CXB_LAUNCH(k_apply, 1, 32, 0, stream, view(), d_front.p, 1u, req_epoch, 0);
+        return check_flags();
+    }
+};
+
+}  // namespace cxb
+
+// =================================================================================================================
+// C ABI (include/cortex_b200.h) — generic engine part
+// =================================================================================================================
+using cxb::DeviceEngine;
+static inline DeviceEngine* E(cxb_engine* h) { return reinterpret_cast<DeviceEngine*>(h); }
+#define CHECK_SIG(h, s)                                             \
+    if ((s) < 0 || (s) >= (int64_t)E(h)->g.n_sig()) {               \
+        E(h)->err = "bad signal id";                                \
+        return CXB_ERR_BAD_ARG;                                     \
+    }
+
+extern "C" {
+
+const char* cxb_version(void) { return "cortex_b200 0.1.0 (sm_100a)"; }
+uint64_t cxb_kernel_launches(void) { return (uint64_t)cxb::g_kernel_launches; }
+
+int32_t cxb_create(int32_t device, int32_t dtype, int32_t value_dim, int32_t family, cxb_engine** out) {
+    if (!out || value_dim < 1 || (dtype != CXB_F32 && dtype != CXB_F64)) return CXB_ERR_BAD_ARG;
+    *out = nullptr;
+    DeviceEngine* e = new DeviceEngine();
+    e->device = device;
+    e->dtype = dtype;
+    e->dim = value_dim;
+    e->family = family;
+    int32_t st = e->init();
+    if (st) {
+        fprintf(stderr, "cxb_create: %s\n", e->err.c_str());
+        delete e;
+        return st;
+    }
+    *out = reinterpret_cast<cxb_engine*>(e);
+    return CXB_OK;
+}
+void cxb_destroy(cxb_engine* h) {
+    if (h) {
+        cudaSetDevice(E(h)->device);
+        delete E(h);
+    }
+}
+const char* cxb_last_error(cxb_engine* h) { return h ? E(h)->err.c_str() : "null handle"; }
+
+int32_t cxb_graph_build(cxb_engine* h, int64_t n_ids, const uint8_t* is_factor, const int32_t* factor_type, int64_t n_edges,
+                        const int64_t* edge_var, const int64_t* edge_fac) {
+    DeviceEngine* e = E(h);
+    int32_t st = e->g.build(n_ids, is_factor, factor_type, n_edges, edge_var, edge_fac, e->err);
+    e->fparam.assign((size_t)n_ids, NAN);
+    e->structure_dirty = true;
+    return st;
+}
+int32_t cxb_register_rule(cxb_engine* h, int32_t factor_type, int32_t rule_kind, const double* params, int64_t n_params) {
+    cxb::RuleDef r;
+    r.kind = rule_kind;
+    if (params && n_params > 0) r.params.assign(params, params + n_params);
+    E(h)->rules[factor_type] = r;
+    E(h)->rules_dirty = true;
+    return CXB_OK;
+}
+int32_t cxb_set_factor_params(cxb_engine* h, int64_t n, const int64_t* factor_ids, const double* values) {
+    DeviceEngine* e = E(h);
+    for (int64_t i = 0; i < n; ++i) {
+        int64_t f = factor_ids[i];
+        if (f < 0 || f >= e->g.n_ids || !e->g.is_factor[f]) {
+            e->err = "set_factor_params: not a factor id";
+            return CXB_ERR_BAD_ARG;
+        }
+        e->fparam[f] = values[i];
+    }
+    e->rules_dirty = true;
+    return CXB_OK;
+}
+int64_t cxb_create_signal(cxb_engine* h) {
+    DeviceEngine* e = E(h);
+    if (e->sync_host()) return -1;  // pull the dynamic state before growing the structure
+    e->structure_dirty = true;
+    return e->g.new_signal();
+}
+int32_t cxb_add_dependency(cxb_engine* h, int64_t s, int64_t d, int32_t flags) {
+    DeviceEngine* e = E(h);
+    CHECK_SIG(h, s);
+    CHECK_SIG(h, d);
+    {
+        int32_t st = e->sync_host();
+        if (st) return st;
+    }
+    e->g.add_dependency((int32_t)s, (int32_t)d, flags & CXB_DEP_WEAK, !(flags & CXB_DEP_NO_LISTEN),
+                        !(flags & CXB_DEP_NO_CHECK_COMPUTED), flags & CXB_DEP_INTERMEDIATE);
+    e->structure_dirty = true;
+    return CXB_OK;
+}
+int32_t cxb_resolve_dependencies(cxb_engine* h, int32_t resolver) {
+    DeviceEngine* e = E(h);
+    {
+        int32_t st = e->sync_host();
+        if (st) return st;
+    }
+    e->structure_dirty = true;
+    return e->g.resolve(resolver, e->err);
+}
+int32_t cxb_link_signal(cxb_engine* h, int64_t v, int64_t s) {
+    DeviceEngine* e = E(h);
+    CHECK_SIG(h, s);
+    if (v < 0 || v >= e->g.n_ids || e->g.is_factor[v]) {
+        e->err = "link_signal: not a variable id";
+        return CXB_ERR_BAD_ARG;
+    }
+    e->g.links.emplace_back(v, (int32_t)s);
+    e->req_uploaded = false;
+    e->links_dirty = true;
+    return CXB_OK;
+}
+int64_t cxb_n_signals(cxb_engine* h) { return E(h)->g.n_sig(); }
+int64_t cxb_signal_id(cxb_engine* h, int32_t kind, int64_t v, int64_t f) {
+    DeviceEngine* e = E(h);
+    if (v < 0 || v >= e->g.n_ids || e->g.is_factor[v]) return -1;
+    if (kind == CXB_KIND_MARGINAL) return e->g.marg_of[v];
+    if (f < 0 || f >= e->g.n_ids || !e->g.is_factor[f]) return -1;
+    int32_t c = e->g.conn_of(v, f);
+    if (c < 0) return -1;
+    if (kind == CXB_KIND_M2V) return e->g.m2v_of_conn(c);
+    if (kind == CXB_KIND_M2F) return e->g.m2f_of_conn(c);
+    return -1;
+}
+int32_t cxb_signal_info(cxb_engine* h, int64_t s, int64_t out[5]) {
+    CHECK_SIG(h, s);
+    const cxb::HostGraph& g = E(h)->g;
+    out[0] = g.kind[s];
+    out[1] = g.svar[s];
+    out[2] = g.sfac[s];
+    out[3] = g.r0[s];
+    out[4] = g.r1[s];
+    return CXB_OK;
+}
+// dependency lists with the live 4-bit props: the structure comes from the log, the C/F bits from the device
+int64_t cxb_get_dependencies(cxb_engine* h, int64_t s, int64_t* out_ids, uint8_t* out_nib, int64_t cap) {
+    DeviceEngine* e = E(h);
+    if (s < 0 || s >= (int64_t)e->g.n_sig()) return -1;
+    int64_t nd = e->g.dep_count[s];
+    if (cap <= 0 || nd == 0) return nd;
+    if (e->ensure_device()) return -1;
+    uint32_t off = e->csr.dep_off[s], noff = e->csr.nib_off[s], nch = e->csr.nib_off[s + 1] - noff;
+    std::vector<uint64_t> ch(nch);
+    if (cudaMemcpy(ch.data(), e->d_nib.p + noff, nch * sizeof(uint64_t), cudaMemcpyDeviceToHost) != cudaSuccess) return -1;
+    for (int64_t i = 0; i < nd && i < cap; ++i) {
+        if (out_ids) out_ids[i] = e->csr.dep_ids[off + i];
+        if (out_nib) out_nib[i] = (uint8_t)((ch[i >> 4] >> ((i & 15) << 2)) & 0xF);
+    }
+    return nd;
+}
+int64_t cxb_get_listeners(cxb_engine* h, int64_t s, int64_t* out_ids, uint8_t* out_listen, int64_t cap) {
+    DeviceEngine* e = E(h);
+    if (s < 0 || s >= (int64_t)e->g.n_sig()) return -1;
+    int64_t nl = e->g.lis_count[s];
+    if (cap <= 0 || nl == 0) return nl;
+    if (e->structure_dirty) {  // structure only: rebuild the CSR on the host, nothing needs the device
+        if (e->ensure_device()) return -1;
+    }
+    uint32_t off = e->csr.lis_off[s];
+    for (int64_t i = 0; i < nl && i < cap; ++i) {
+        if (out_ids) out_ids[i] = e->csr.lis_ids[off + i];
+        if (out_listen) out_listen[i] = e->csr.lis_listen[off + i];
+    }
+    return nl;
+}
+int64_t cxb_get_warnings(cxb_engine* h, int64_t* out, int64_t cap) {
+    const auto& w = E(h)->g.warnings;
+    for (int64_t i = 0; i < (int64_t)w.size() && i < cap; ++i) out[i] = w[i];
+    return (int64_t)w.size();
+}
+int32_t cxb_set_values(cxb_engine* h, int64_t n, const int64_t* sids, const double* values, int64_t stride) {
+    return E(h)->set_values(n, sids, values, stride);
+}
+int32_t cxb_get_values(cxb_engine* h, int64_t n, const int64_t* sids, double* out, int64_t stride) {
+    return E(h)->get_values(n, sids, out, stride);
+}
+int32_t cxb_is_pending(cxb_engine* h, int64_t s) {
+    if (s < 0 || s >= (int64_t)E(h)->g.n_sig()) return -1;
+    int r = 0;
+    if (E(h)->is_pending(s, r)) return -1;
+    return r;
+}
+int32_t cxb_is_computed(cxb_engine* h, int64_t s) {
+    if (s < 0 || s >= (int64_t)E(h)->g.n_sig()) return -1;
+    int r = 0;
+    if (E(h)->is_computed(s, r)) return -1;
+    return r;
+}
+int32_t cxb_compute(cxb_engine* h, int64_t s, int32_t force, int32_t skip) {
+    CHECK_SIG(h, s);
+    return E(h)->compute(s, force != 0, skip != 0);
+}
+int32_t cxb_request_inference(cxb_engine* h, int64_t n, const int64_t* ids) {
+    DeviceEngine* e = E(h);
+    int32_t st = e->request(n, ids);
+    if (st) return st;
+    if (cudaStreamSynchronize(e->stream) != cudaSuccess) return CXB_ERR_CUDA;
+    return CXB_OK;
+}
+int64_t cxb_scan(cxb_engine* h, int64_t* out, int64_t cap) {
+    std::vector<int64_t> v;
+    if (E(h)->scan(v)) return -1;
+    for (int64_t i = 0; i < (int64_t)v.size() && i < cap; ++i) out[i] = v[i];
+    return (int64_t)v.size();
+}
+int32_t cxb_update_marginals(cxb_engine* h, int64_t n, const int64_t* ids, cxb_update_stats* stats) {
+    int32_t st = E(h)->update(n, ids);
+    if (stats) *stats = E(h)->stats;
+    return st;
+}
+int32_t cxb_trace_enable(cxb_engine* h, int32_t on) {
+    E(h)->trace_on = on != 0;
+    return CXB_OK;
+}
+int64_t cxb_trace_get(cxb_engine* h, int64_t* out_level, int64_t* out_sid, int64_t cap) {
+    DeviceEngine* e = E(h);
+    for (int64_t i = 0; i < (int64_t)e->tr_sid.size() && i < cap; ++i) {
+        if (out_level) out_level[i] = e->tr_level[i];
+        if (out_sid) out_sid[i] = e->tr_sid[i];
+    }
+    return (int64_t)e->tr_sid.size();
+}
+
+}  // extern "C"

@@ -1,0 +1,370 @@
+// hmm.cu — structured engine for a batch of discrete HMMs (BASELINE config 3).
+//
+// Graph per chain: hidden z_t, observed y_t, emission factor (z_t, y_t), transition factor
+// (z_t, z_{t+1}), uniform prior leaf on z_1; data enter as set_value!(m2f(y_t, em_t), o_t).  One call =
+// update_marginals!(engine, z[1:T]) of every chain = 6T-4 message updates per chain (categorical sum-product,
+// every message normalised to sum 1).  Materialised in HBM: the forward message m2f(z_t, tr_t) and the marginal
+// ("forward message + marginal" contract of SURVEY §8d: 12K+2 bytes per (chain, step)).
+//
+// Kernel shape: the recursion over t is strictly sequential, the batch is small (1,024 chains), so the unit of
+// parallelism is ONE WARP PER CHAIN with lane l owning states l, l+32, ...:
+//   out[j] = sum_i Tbl[i][j] * v[i]        (Tbl = A forward, A^T backward)
+// For K <= 64 (fp32) the lane's columns of Tbl live in REGISTERS (2 x 64 values), v is staged in a per-warp
+// shared-memory line and read back with broadcast 128-bit loads, so a step is K*K/32 FFMAs + K/4 LDS per warp
+// and no block-level barrier.  Larger K stream Tbl through shared memory in row tiles shared by the 8 chains of
+// the CTA.  (The tcgen05 path for K = 512 named by the north star is future work: see DESIGN.md.)
+#include <cmath>
+
+#include "common.cuh"
+
+namespace cxb {
+
+constexpr int HMM_WARPS = 8;  // chains per CTA
+
+template <class T>
+__device__ __forceinline__ T warp_sum(T v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// One pass over time. FWD: t ascending, writes fwd[t] = m2f(z_t, tr_t) = normalise(em_t * pred_t).
+// BWD: t descending, reads fwd[t], writes marg[t] = normalise(fwd[t] * bwd_t), carries
+// m2f(z_t, tr_{t-1}) = normalise(em_t * bwd_t).  tbl is A (FWD) or A^T (BWD), row-major [K][K];
+// emis_n is the column-normalised emission table transposed to [M][K] (m2v(z_t, em_t) = emis_n[o_t]).
+template <class T, int K, bool REGA, bool FWD>
+__global__ void __launch_bounds__(HMM_WARPS * 32)
+k_hmm_pass(const T* __restrict__ tbl, const T* __restrict__ emis_n, const uint8_t* __restrict__ obs, T* __restrict__ fwd,
+           T* __restrict__ marg, long long B, long long Tn, int Kdyn, int n_sym, int tile_rows) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int Kk = REGA ? K : Kdyn;
+    constexpr int CPL_MAX = REGA ? K / 32 : 32;  // states per lane (<= 1024 states in the streamed path)
+    const int cpl = (Kk + 31) / 32;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const long long b = (long long)blockIdx.x * HMM_WARPS + warp;
+    const bool live = b < B;
+    T* sh_v = reinterpret_cast<T*>(smem_raw) + (size_t)warp * Kk;       // per-warp staging of v
+    T* sh_tbl = reinterpret_cast<T*>(smem_raw) + (size_t)HMM_WARPS * Kk;  // streamed path: row tile of tbl
+
+    T areg[REGA ? K : 1][REGA ? K / 32 : 1];
+    if (REGA) {
+#pragma unroll
+        for (int i = 0; i < K; ++i)
+#pragma unroll
+            for (int c = 0; c < K / 32; ++c) areg[i][c] = tbl[(size_t)i * K + lane + 32 * c];
+    }
+    const bool whole_table = !REGA && tile_rows >= Kk;
+    if (whole_table) {
+        for (int x = threadIdx.x; x < Kk * Kk; x += blockDim.x) sh_tbl[x] = tbl[x];
+        __syncthreads();
+    }
+
+    T v[CPL_MAX];  // carried message (lane's states)
+#pragma unroll
+    for (int c = 0; c < CPL_MAX; ++c) v[c] = T(0);
+
+    for (long long step = 0; step < Tn; ++step) {
+        const long long t = FWD ? step : Tn - 1 - step;
+        T out[CPL_MAX];
+#pragma unroll
+        for (int c = 0; c < CPL_MAX; ++c) out[c] = T(0);
+        const bool has_prev = step > 0;
+        if (has_prev) {
+            // stage v, then out[j] = sum_i tbl[i][j] v[i]
+            __syncwarp();
+#pragma unroll
+            for (int c = 0; c < CPL_MAX; ++c)
+                if (c < cpl && lane + 32 * c < Kk) sh_v[lane + 32 * c] = v[c];
+            __syncwarp();
+            if (REGA) {
+#pragma unroll
+                for (int i = 0; i < K; i += 4) {
+                    T vi[4];
+                    if (sizeof(T) == 4) {
+                        float4 q = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(sh_v) + i);
+                        vi[0] = q.x; vi[1] = q.y; vi[2] = q.z; vi[3] = q.w;
+                    } else {
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) vi[u] = sh_v[i + u];
+                    }
+#pragma unroll
+                    for (int u = 0; u < 4; ++u)
+#pragma unroll
+                        for (int c = 0; c < K / 32; ++c) out[c] = fma(areg[i + u][c], vi[u], out[c]);
+                }
+            } else if (whole_table) {
+                for (int i = 0; i < Kk; ++i) {
+                    T vi = sh_v[i];
+#pragma unroll 4
+                    for (int c = 0; c < cpl; ++c) {
+                        int j = lane + 32 * c;
+                        if (j < Kk) out[c] = fma(sh_tbl[(size_t)i * Kk + j], vi, out[c]);
+                    }
+                }
+            } else {
+                for (int r0 = 0; r0 < Kk; r0 += tile_rows) {
+                    int nr = min(tile_rows, Kk - r0);
+                    __syncthreads();
+                    for (int x = threadIdx.x; x < nr * Kk; x += blockDim.x) sh_tbl[x] = tbl[(size_t)r0 * Kk + x];
+                    __syncthreads();
+                    for (int i = 0; i < nr; ++i) {
+                        T vi = sh_v[r0 + i];
+#pragma unroll 4
+                        for (int c = 0; c < cpl; ++c) {
+                            int j = lane + 32 * c;
+                            if (j < Kk) out[c] = fma(sh_tbl[(size_t)i * Kk + j], vi, out[c]);
+                        }
+                    }
+                }
+            }
+        }
+        // emission message of this step
+        int o = live ? (int)obs[(size_t)t * B + b] : 0;
+        if (o >= n_sym) o = n_sym - 1;
+        T em[CPL_MAX];
+#pragma unroll
+        for (int c = 0; c < CPL_MAX; ++c) {
+            int j = lane + 32 * c;
+            em[c] = (c < cpl && j < Kk) ? emis_n[(size_t)o * Kk + j] : T(0);
+        }
+        const size_t base = ((size_t)t * B + (live ? b : 0)) * Kk;
+        if (FWD) {
+            // m2f(z_t, tr_t) = normalise(em * pred); at t = 0 the uniform prior leaves normalise(em)
+            T part = T(0);
+#pragma unroll
+            for (int c = 0; c < CPL_MAX; ++c) {
+                v[c] = has_prev ? em[c] * out[c] : em[c];
+                part += v[c];
+            }
+            T tot = warp_sum(part);
+#pragma unroll
+            for (int c = 0; c < CPL_MAX; ++c) {
+                v[c] = v[c] / tot;
+                int j = lane + 32 * c;
+                if (live && c < cpl && j < Kk) __stcs(&fwd[base + j], v[c]);
+            }
+        } else {
+            T a[CPL_MAX];
+            T part = T(0), part2 = T(0);
+#pragma unroll
+            for (int c = 0; c < CPL_MAX; ++c) {
+                int j = lane + 32 * c;
+                a[c] = (live && c < cpl && j < Kk) ? __ldcs(&fwd[base + j]) : T(0);
+                T g = has_prev ? a[c] * out[c] : a[c];  // marginal = fwd * bwd
+                T m = has_prev ? em[c] * out[c] : em[c];  // m2f(z_t, tr_{t-1}) = em * bwd
+                a[c] = g;
+                v[c] = m;
+                part += g;
+                part2 += m;
+            }
+            T tot = warp_sum(part), tot2 = warp_sum(part2);
+#pragma unroll
+            for (int c = 0; c < CPL_MAX; ++c) {
+                int j = lane + 32 * c;
+                v[c] = v[c] / tot2;
+                if (live && c < cpl && j < Kk) __stcs(&marg[base + j], a[c] / tot);
+            }
+        }
+    }
+}
+
+struct Hmm {
+    int device = 0, dtype = CXB_F32, K = 0, M = 0;
+    long long B = 0, T = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    std::string err;
+    DBuf<unsigned char> A, At, En, fwd, marg;
+    DBuf<uint8_t> obs;
+    bool have_tables = false, have_obs = false, ran = false;
+    size_t esz() const { return dtype == CXB_F32 ? 4 : 8; }
+    ~Hmm() {
+        if (ev0) cudaEventDestroy(ev0);
+        if (ev1) cudaEventDestroy(ev1);
+        if (stream) cudaStreamDestroy(stream);
+    }
+    int32_t init() {
+        int count = 0;
+        if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0) {
+            err = "no CUDA device available (cortex_b200 has no CPU fallback)";
+            return CXB_ERR_CUDA;
+        }
+        if (device < 0 || device >= count || B <= 0 || T <= 0 || K < 2 || K > 1024 || M < 1 || M > 256) {
+            err = "bad device / shape (2 <= states <= 1024, 1 <= symbols <= 256)";
+            return CXB_ERR_BAD_ARG;
+        }
+        CXB_CUDA(cudaSetDevice(device));
+        CXB_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+        CXB_CUDA(cudaEventCreate(&ev0));
+        CXB_CUDA(cudaEventCreate(&ev1));
+        CXB_CUDA(A.reserve((size_t)K * K * esz()));
+        CXB_CUDA(At.reserve((size_t)K * K * esz()));
+        CXB_CUDA(En.reserve((size_t)M * K * esz()));
+        CXB_CUDA(obs.reserve((size_t)T * B));
+        CXB_CUDA(fwd.reserve((size_t)T * B * K * esz()));
+        CXB_CUDA(marg.reserve((size_t)T * B * K * esz()));
+        return CXB_OK;
+    }
+    void put(std::vector<unsigned char>& raw, size_t i, double v) {
+        if (dtype == CXB_F32)
+            ((float*)raw.data())[i] = (float)v;
+        else
+            ((double*)raw.data())[i] = v;
+    }
+    int32_t set_tables(const double* trans, const double* emis) {
+        CXB_CUDA(cudaSetDevice(device));
+        std::vector<unsigned char> a((size_t)K * K * esz()), at((size_t)K * K * esz()), en((size_t)M * K * esz());
+        for (int i = 0; i < K; ++i)
+            for (int j = 0; j < K; ++j) {
+                put(a, (size_t)i * K + j, trans[(size_t)i * K + j]);
+                put(at, (size_t)j * K + i, trans[(size_t)i * K + j]);
+            }
+        for (int o = 0; o < M; ++o) {  // m2v(z, em) = normalise(E[:, o]) (HMM_EMIT rule)
+            double s = 0;
+            for (int j = 0; j < K; ++j) s += emis[(size_t)j * M + o];
+            if (!(s > 0)) {
+                err = "emission column sums must be positive";
+                return CXB_ERR_BAD_ARG;
+            }
+            for (int j = 0; j < K; ++j) put(en, (size_t)o * K + j, emis[(size_t)j * M + o] / s);
+        }
+        CXB_CUDA(cudaMemcpyAsync(A.p, a.data(), a.size(), cudaMemcpyHostToDevice, stream));
+        CXB_CUDA(cudaMemcpyAsync(At.p, at.data(), at.size(), cudaMemcpyHostToDevice, stream));
+        CXB_CUDA(cudaMemcpyAsync(En.p, en.data(), en.size(), cudaMemcpyHostToDevice, stream));
+        CXB_CUDA(cudaStreamSynchronize(stream));
+        have_tables = true;
+        return CXB_OK;
+    }
+    template <class T, int KK, bool REGA>
+    int32_t launch_pair(int tile_rows, size_t smem) {
+        unsigned grid = cdiv((size_t)B, HMM_WARPS);
+        if (smem > 48 * 1024) {
+            CXB_CUDA(cudaFuncSetAttribute(k_hmm_pass<T, KK, REGA, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            CXB_CUDA(cudaFuncSetAttribute(k_hmm_pass<T, KK, REGA, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        }
+        CXB_LAUNCH((k_hmm_pass<T, KK, REGA, true>), grid, HMM_WARPS * 32, smem, stream, (const T*)A.p, (const T*)En.p, obs.p,
+                   (T*)fwd.p, (T*)marg.p, B, this->T, K, M, tile_rows);
+        CXB_LAUNCH((k_hmm_pass<T, KK, REGA, false>), grid, HMM_WARPS * 32, smem, stream, (const T*)At.p, (const T*)En.p, obs.p,
+                   (T*)fwd.p, (T*)marg.p, B, this->T, K, M, tile_rows);
+        return CXB_OK;
+    }
+    template <class T>
+    int32_t launch_t() {
+        size_t stage = (size_t)HMM_WARPS * K * sizeof(T);
+        if (sizeof(T) == 4 && K == 64) return launch_pair<T, 64, true>(0, stage);
+        if (K == 32) return launch_pair<T, 32, true>(0, stage);
+        size_t budget = 200 * 1024 - stage;
+        int tile_rows = (int)std::min<size_t>((size_t)K, budget / ((size_t)K * sizeof(T)));
+        if (tile_rows < 1) {
+            err = "state count too large";
+            return CXB_ERR_BAD_ARG;
+        }
+        return launch_pair<T, 0, false>(tile_rows, stage + (size_t)tile_rows * K * sizeof(T));
+    }
+    int32_t launch() {
+        if (!have_tables || !have_obs) {
+            err = "set the tables and the observations first";
+            return CXB_ERR_STATE;
+        }
+        CXB_CUDA(cudaSetDevice(device));
+        CXB_CUDA(cudaEventRecord(ev0, stream));
+        int32_t st = dtype == CXB_F32 ? launch_t<float>() : launch_t<double>();
+        if (st) return st;
+        CXB_CUDA(cudaEventRecord(ev1, stream));
+        CXB_CUDA(cudaGetLastError());
+        ran = true;
+        return CXB_OK;
+    }
+};
+
+}  // namespace cxb
+
+using cxb::Hmm;
+static inline Hmm* HM(cxb_hmm* m) { return reinterpret_cast<Hmm*>(m); }
+#define HM_CUDA(m, expr)                                        \
+    do {                                                        \
+        cudaError_t e__ = (expr);                               \
+        if (e__ != cudaSuccess) {                               \
+            HM(m)->err = ::cxb::cuda_msg(e__, #expr);           \
+            return CXB_ERR_CUDA;                                \
+        }                                                       \
+    } while (0)
+
+extern "C" {
+
+int32_t cxb_hmm_create(int32_t device, int32_t dtype, int64_t n_chains, int64_t n_steps, int32_t n_states, int32_t n_symbols,
+                       cxb_hmm** out) {
+    if (!out || (dtype != CXB_F32 && dtype != CXB_F64)) return CXB_ERR_BAD_ARG;
+    *out = nullptr;
+    Hmm* m = new Hmm();
+    m->device = device;
+    m->dtype = dtype;
+    m->B = n_chains;
+    m->T = n_steps;
+    m->K = n_states;
+    m->M = n_symbols;
+    int32_t st = m->init();
+    if (st) {
+        fprintf(stderr, "cxb_hmm_create: %s\n", m->err.c_str());
+        delete m;
+        return st;
+    }
+    *out = reinterpret_cast<cxb_hmm*>(m);
+    return CXB_OK;
+}
+void cxb_hmm_destroy(cxb_hmm* m) {
+    if (m) {
+        cudaSetDevice(HM(m)->device);
+        delete HM(m);
+    }
+}
+const char* cxb_hmm_last_error(cxb_hmm* m) { return m ? HM(m)->err.c_str() : "null handle"; }
+int32_t cxb_hmm_set_tables(cxb_hmm* m, const double* transition, const double* emission) {
+    return HM(m)->set_tables(transition, emission);
+}
+int32_t cxb_hmm_set_observations(cxb_hmm* m, const uint8_t* obs_host) {
+    Hmm* h = HM(m);
+    HM_CUDA(m, cudaSetDevice(h->device));
+    HM_CUDA(m, cudaMemcpyAsync(h->obs.p, obs_host, (size_t)h->T * h->B, cudaMemcpyHostToDevice, h->stream));
+    HM_CUDA(m, cudaStreamSynchronize(h->stream));
+    h->have_obs = true;
+    return CXB_OK;
+}
+int32_t cxb_hmm_update_marginals(cxb_hmm* m, int64_t* n_updates_out) {
+    Hmm* h = HM(m);
+    int32_t st = h->launch();
+    if (st) return st;
+    if (n_updates_out) *n_updates_out = h->B * (6 * h->T - 4);
+    return CXB_OK;
+}
+static int32_t hmm_get(cxb_hmm* m, const unsigned char* src, int64_t t0, int64_t t1, void* out_host) {
+    Hmm* h = HM(m);
+    if (!h->ran || t0 < 0 || t1 > h->T || t0 >= t1) {
+        h->err = "bad time slice or no update has run yet";
+        return CXB_ERR_BAD_ARG;
+    }
+    size_t step = (size_t)h->B * h->K * h->esz();
+    HM_CUDA(m, cudaSetDevice(h->device));
+    HM_CUDA(m, cudaMemcpyAsync(out_host, src + (size_t)t0 * step, (size_t)(t1 - t0) * step, cudaMemcpyDeviceToHost, h->stream));
+    HM_CUDA(m, cudaStreamSynchronize(h->stream));
+    return CXB_OK;
+}
+int32_t cxb_hmm_get_marginals(cxb_hmm* m, int64_t t0, int64_t t1, void* out_host) { return hmm_get(m, HM(m)->marg.p, t0, t1, out_host); }
+int32_t cxb_hmm_get_forward(cxb_hmm* m, int64_t t0, int64_t t1, void* out_host) { return hmm_get(m, HM(m)->fwd.p, t0, t1, out_host); }
+void* cxb_hmm_stream(cxb_hmm* m) { return (void*)HM(m)->stream; }
+int32_t cxb_hmm_last_kernel_ms(cxb_hmm* m, float* ms_out) {
+    Hmm* h = HM(m);
+    if (!h->ran) {
+        h->err = "no update has run yet";
+        return CXB_ERR_STATE;
+    }
+    HM_CUDA(m, cudaEventSynchronize(h->ev1));
+    HM_CUDA(m, cudaEventElapsedTime(ms_out, h->ev0, h->ev1));
+    return CXB_OK;
+}
+int32_t cxb_hmm_sync(cxb_hmm* m) {
+    HM_CUDA(m, cudaStreamSynchronize(HM(m)->stream));
+    return CXB_OK;
+}
+
+}  // extern "C"

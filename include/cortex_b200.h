@@ -122,6 +122,8 @@ int32_t cxb_create(int32_t device, int32_t dtype, int32_t value_dim, int32_t fam
 void cxb_destroy(cxb_engine* h);
 const char* cxb_last_error(cxb_engine* h);
 const char* cxb_version(void);
+/* number of CUDA kernels this library has launched in this process (bench.py reports the delta as gpu_launches) */
+uint64_t cxb_kernel_launches(void);
 
 /* Graph ingestion. Replaces the 7 backend generics get_variable / get_factor / get_variable_ids /
  * get_factor_ids / get_connection / get_connected_variable_ids / get_connected_factor_ids

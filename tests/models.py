@@ -201,3 +201,46 @@ def rts_smoother(y, q, r):
         ms[t] = mf[t] + g * (ms[t + 1] - mf[t])
         Ps[t] = Pf[t] + g * g * (Ps[t + 1] - Pp)
     return ms, Ps
+
+
+def make_hmm_model(T, K, M, A, E, api, dtype=cap.F64):
+    """SURVEY Appendix C HMM graph for one chain: z_t, y_t, prior leaf on z_1, emission (y_t,z_t), transition (z_t,z_{t+1})."""
+    g = C.BipartiteFactorGraph()
+    z = [g.add_variable(C.Variable(name="z", index=(t,))) for t in range(T)]
+    y = [g.add_variable(C.Variable(name="y", index=(t,))) for t in range(T)]
+    prior = g.add_factor(C.Factor(functional_form="prior"))
+    em = [g.add_factor(C.Factor(functional_form="emission")) for _ in range(T)]
+    tr = [g.add_factor(C.Factor(functional_form="transition")) for _ in range(T - 1)]
+    g.add_edge(z[0], prior, C.Connection(label="out"))
+    for t in range(T):
+        g.add_edge(y[t], em[t], C.Connection(label="out"))
+        g.add_edge(z[t], em[t], C.Connection(label="in"))
+    for t in range(T - 1):
+        g.add_edge(z[t], tr[t], C.Connection(label="in"))
+        g.add_edge(z[t + 1], tr[t], C.Connection(label="out"))
+    rules = {"emission": (cap.RULE_HMM_EMIT, np.concatenate([[float(M)], np.asarray(E, dtype=np.float64).ravel()])),
+             "transition": (cap.RULE_CAT_TABLE, np.asarray(A, dtype=np.float64).ravel())}
+    proc = C.RuleProcessor(rules, family=cap.FAMILY_CATEGORICAL, value_dim=K)
+    engine = C.InferenceEngine(model_engine=g, dependency_resolver=C.DefaultDependencyResolver(),
+                               inference_request_processor=proc, dtype=dtype, api=api)
+    return engine, z, y, prior, em, tr
+
+
+def hmm_set_data(engine, z, y, prior, em, obs, K):
+    sig = [C.get_connection_message_to_factor(engine, y[t], em[t]) for t in range(len(y))]
+    vals = np.zeros((len(y), K))
+    vals[:, 0] = obs
+    C.set_values(sig, vals)
+    C.set_value(C.get_connection_message_to_variable(engine, z[0], prior), np.full(K, 1.0 / K))
+
+
+def level_trace(engine):
+    """{level: sorted signal ids} of the last update_marginals (levels >= 0 loop phase, -1 marginals, -2 linked)."""
+    n = engine.api.trace_get(engine.store.h, None, None, 0)
+    lv = np.zeros(max(n, 1), dtype=np.int64)
+    sg = np.zeros(max(n, 1), dtype=np.int64)
+    engine.api.trace_get(engine.store.h, lv.ctypes.data_as(cap.i64p), sg.ctypes.data_as(cap.i64p), n)
+    out = {}
+    for l, s in zip(lv[:n].tolist(), sg[:n].tolist()):
+        out.setdefault(l, []).append(s)
+    return {l: sorted(v) for l, v in out.items()}

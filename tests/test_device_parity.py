@@ -1,0 +1,281 @@
+"""GPU parity tests proper: the CUDA path (through the C ABI) against the CPU oracle on the same seeded
+inputs. Bar (BASELINE.json north_star): bit-exact frontier / wiring / pending state; values within
+rel 1e-12 (fp64) and 1e-5 (fp32) of the oracle."""
+import numpy as np
+import pytest
+
+from tests._pkg import pkg
+from tests import models
+
+C = pkg
+cap = pkg.capi
+pytestmark = pytest.mark.gpu
+TOL = {cap.F64: 1e-12, cap.F32: 1e-5}
+
+
+def _wiring(engine):
+    st = engine.store
+    out = []
+    for s in range(st.n_signals()):
+        sig = C.Signal(st, s)
+        out.append((C.get_variant(sig), [d.sid for d in C.get_dependencies(sig)], C.get_dependency_props(sig),
+                    [l.sid for l in C.get_listeners(sig)], C.get_listenmask(sig)))
+    return out
+
+
+def _compare(e_dev, e_ora, dtype):
+    so, vo = models.engine_state(e_ora)
+    sd, vd = models.engine_state(e_dev)
+    assert so == sd  # is_computed / is_pending / nibbles of every signal: bit-exact
+    np.testing.assert_allclose(vd, vo, rtol=TOL[dtype], atol=TOL[dtype] * 1e-3)
+
+
+@pytest.mark.parametrize("dtype", [cap.F64, cap.F32])
+def test_chain_engine_parity(oracle_api, device_api, dtype):
+    T = 64
+    data = np.cumsum(np.random.Generator(np.random.PCG64(1234)).standard_normal(T))
+    eng = {}
+    for name, api in (("o", oracle_api), ("d", device_api)):
+        e, x, y, lik, tr = models.make_ssm_model(T, api, form="canon", q=0.7, r=1.3, dtype=dtype, trace=True)
+        models.ssm_set_data(e, y, lik, data)
+        eng[name] = (e, x)
+    assert _wiring(eng["o"][0]) == _wiring(eng["d"][0])  # dependency resolution: bit-exact
+    # frontier of the fresh request (scan_inference_request)
+    so = C.scan_inference_request(C.request_inference_for(eng["o"][0], eng["o"][1]))
+    sd = C.scan_inference_request(C.request_inference_for(eng["d"][0], eng["d"][1]))
+    assert [s.sid for s in so] == [s.sid for s in sd] and len(so) == T
+    sto = C.update_marginals(eng["o"][0], eng["o"][1])
+    std = C.update_marginals(eng["d"][0], eng["d"][1])
+    assert (sto.updates, sto.levels, list(sto.updates_by_kind)) == (std.updates, std.levels, list(std.updates_by_kind))
+    assert std.updates == 6 * T - 4 and std.levels == 2 * T - 1 and std.kernel_launches > 0
+    assert models.level_trace(eng["o"][0]) == models.level_trace(eng["d"][0])  # per-level frontier lists: bit-exact
+    _compare(eng["d"][0], eng["o"][0], dtype)
+    assert C.update_marginals(eng["d"][0], eng["d"][1]).updates == 0
+
+
+@pytest.mark.parametrize("dtype", [cap.F64, cap.F32])
+@pytest.mark.parametrize("rule", ["potts", "table"])
+def test_grid_protocol_b_engine_parity(oracle_api, device_api, dtype, rule):
+    H, W, K, beta, sweeps = 5, 6, 4, 0.7, 4
+    unary = np.random.Generator(np.random.PCG64(1234)).dirichlet(np.ones(K), size=(H, W))
+    eng = {}
+    for name, api in (("o", oracle_api), ("d", device_api)):
+        e, pix, un, pair = models.make_grid_model(H, W, K, beta, api, dtype=dtype, rule=rule)
+        e.store.check(e.api.trace_enable(e.store.h, 1))
+        vids = [v for row in pix for v in row]
+        models.protocol_b_init(e, vids, K)
+        usig = [C.get_connection_message_to_variable(e, pix[i][j], un[i][j]) for i in range(H) for j in range(W)]
+        eng[name] = (e, vids, usig)
+    assert _wiring(eng["o"][0]) == _wiring(eng["d"][0])
+    for s in range(sweeps):
+        st = {}
+        for name in ("o", "d"):
+            e, vids, usig = eng[name]
+            st[name] = models.protocol_b_sweep(e, vids, usig, unary.reshape(-1, K))
+        assert st["o"].updates == st["d"].updates and st["o"].levels == st["d"].levels == 1
+        assert (st["o"].final_marginals, st["o"].final_linked) == (st["d"].final_marginals, st["d"].final_linked)
+        assert models.level_trace(eng["o"][0]) == models.level_trace(eng["d"][0])
+    _compare(eng["d"][0], eng["o"][0], dtype)
+
+
+@pytest.mark.parametrize("dtype", [cap.F64, cap.F32])
+def test_powerlaw_segment_tree_engine_parity(oracle_api, device_api, dtype):
+    n, m, K, sweeps = 80, 220, 8, 3
+    eng = {}
+    for name, api in (("o", oracle_api), ("d", device_api)):
+        e, vs, un, pair, unary, tables, ttype = models.make_powerlaw_model(n, m, K, api, dtype=dtype)
+        e.store.check(e.api.trace_enable(e.store.h, 1))
+        models.protocol_b_init(e, vs, K)
+        usig = [C.get_connection_message_to_variable(e, vs[i], un[i]) for i in range(n)]
+        eng[name] = (e, vs, usig, unary)
+    assert _wiring(eng["o"][0]) == _wiring(eng["d"][0])
+    assert max(len(C.get_connected_factor_ids(eng["d"][0], v)) for v in eng["d"][1]) > 5
+    for s in range(sweeps):
+        st = {}
+        for name in ("o", "d"):
+            e, vs, usig, unary = eng[name]
+            st[name] = models.protocol_b_sweep(e, vs, usig, unary)
+        assert st["o"].updates == st["d"].updates and st["o"].levels == st["d"].levels > 1
+        assert list(st["o"].updates_by_kind) == list(st["d"].updates_by_kind)
+        assert models.level_trace(eng["o"][0]) == models.level_trace(eng["d"][0])
+    _compare(eng["d"][0], eng["o"][0], dtype)
+
+
+def test_out_of_contract_is_refused_not_silently_different(device_api):
+    H, W, K = 3, 3, 4
+    unary = np.random.Generator(np.random.PCG64(5)).dirichlet(np.ones(K), size=(H, W))
+    e, pix, un, pair = models.make_grid_model(H, W, K, 0.5, device_api, link=False)
+    vids = [v for row in pix for v in row]
+    models.protocol_b_init(e, vids, K)
+    usig = [C.get_connection_message_to_variable(e, pix[i][j], un[i][j]) for i in range(H) for j in range(W)]
+    C.set_values(usig, unary.reshape(-1, K))
+    C.update_marginals(e, vids)
+    with pytest.raises(C.OutOfContractError):  # Appendix B naive protocol, call 2: Gauss-Seidel in the reference
+        C.update_marginals(e, vids)
+
+
+@pytest.mark.parametrize("dtype", [cap.F64, cap.F32])
+def test_hmm_engine_parity(oracle_api, device_api, dtype):
+    T, K, M = 12, 8, 5
+    rng = np.random.Generator(np.random.PCG64(1234))
+    A = rng.dirichlet(np.ones(K), size=K)
+    E = rng.dirichlet(np.ones(K), size=M).T * K
+    obs = rng.integers(0, M, size=T)
+    eng = {}
+    for name, api in (("o", oracle_api), ("d", device_api)):
+        e, z, y, prior, em, tr = models.make_hmm_model(T, K, M, A, E, api, dtype=dtype)
+        models.hmm_set_data(e, z, y, prior, em, obs, K)
+        st = C.update_marginals(e, z)
+        assert st.updates == 6 * T - 4
+        eng[name] = e
+    _compare(eng["d"], eng["o"], dtype)
+
+
+# ---- structured engines against the oracle -------------------------------------------------------------------------
+@pytest.mark.parametrize("dtype", [cap.F64, cap.F32])
+@pytest.mark.parametrize("shape", [(1, 1), (3, 2), (70, 37), (300, 129)])
+def test_chain_batch_kernel_vs_oracle(oracle_api, dtype, shape):
+    B, T = shape
+    rng = np.random.Generator(np.random.PCG64(1234))
+    q, r = rng.uniform(0.5, 2.0, B), rng.uniform(0.5, 2.0, B)
+    x = np.cumsum(rng.standard_normal((T, B)) * np.sqrt(q), axis=0)
+    y = x + rng.standard_normal((T, B)) * np.sqrt(r)
+    ch = C.GaussianChainBatch(B, T, dtype=dtype)
+    ch.set_noise(q, r)
+    ch.set_observations(y)
+    assert ch.update_marginals() == B * (6 * T - 4)
+    y_used = y.astype(ch.np_dtype).astype(np.float64)  # the oracle sees the same (rounded) observations
+    ref = np.zeros((6, T, B, 2))
+    oracle_api.chains_reference(B, T, q.ctypes.data_as(cap.f64p), r.ctypes.data_as(cap.f64p),
+                                np.ascontiguousarray(y_used).ctypes.data_as(cap.f64p), ref.ctypes.data_as(cap.f64p))
+    for m in range(6):
+        got = ch.get_messages(m).astype(np.float64)
+        np.testing.assert_allclose(got, ref[m], rtol=TOL[dtype] if dtype == cap.F64 else 2e-5, atol=1e-30,
+                                   err_msg=C.GaussianChainBatch.MESSAGE_CLASSES[m])
+    assert ch.last_kernel_ms() > 0
+
+
+def test_chain_batch_kernel_vs_explicit_graph_engine(oracle_api):
+    """The structured plan is the same graph/wiring/schedule as the explicit BipartiteFactorGraph + DEFAULT_BP."""
+    B, T = 3, 17
+    rng = np.random.Generator(np.random.PCG64(99))
+    q, r = rng.uniform(0.5, 2.0, B), rng.uniform(0.5, 2.0, B)
+    y = rng.standard_normal((T, B)) * 3
+    ch = C.GaussianChainBatch(B, T, dtype=cap.F64)
+    ch.set_noise(q, r)
+    ch.set_observations(y)
+    ch.update_marginals()
+    for b in range(B):
+        e, x, yv, lik, tr = models.make_ssm_model(T, oracle_api, form="canon", q=q[b], r=r[b])
+        models.ssm_set_data(e, yv, lik, y[:, b])
+        C.update_marginals(e, x, schedule="seq")
+        want = {0: [C.get_connection_message_to_variable(e, x[t], lik[t]) for t in range(T)],
+                1: [None] + [C.get_connection_message_to_variable(e, x[t], tr[t - 1]) for t in range(1, T)],
+                2: [C.get_connection_message_to_factor(e, x[t], tr[t]) for t in range(T - 1)] + [None],
+                3: [C.get_connection_message_to_variable(e, x[t], tr[t]) for t in range(T - 1)] + [None],
+                4: [None] + [C.get_connection_message_to_factor(e, x[t], tr[t - 1]) for t in range(1, T)],
+                5: [C.get_variable_marginal(C.get_variable(e, x[t])) for t in range(T)]}
+        for m, sigs in want.items():
+            got = ch.get_messages(m)[:, b, :]
+            for t, s in enumerate(sigs):
+                if s is not None:
+                    np.testing.assert_allclose(got[t], C.get_value(s), rtol=1e-12)
+
+
+@pytest.mark.parametrize("dtype", [cap.F64, cap.F32])
+@pytest.mark.parametrize("shape", [(1, 1, 4), (1, 7, 4), (6, 1, 4), (5, 7, 8), (9, 33, 16)])
+def test_potts_grid_kernel_vs_oracle(oracle_api, dtype, shape):
+    H, W, K = shape
+    beta, sweeps = 0.7, 3
+    unary = np.random.Generator(np.random.PCG64(1234)).dirichlet(np.ones(K), size=(H, W))
+    gr = C.PottsGrid(H, W, K, beta, dtype=dtype)
+    gr.set_unary(unary)
+    gr.reset_messages()
+    e, pix, un, pair = models.make_grid_model(H, W, K, beta, oracle_api)
+    vids = [v for row in pix for v in row]
+    models.protocol_b_init(e, vids, K)
+    usig = [C.get_connection_message_to_variable(e, pix[i][j], un[i][j]) for i in range(H) for j in range(W)]
+    unary_used = unary.astype(gr.np_dtype).astype(np.float64)
+    for s in range(sweeps):
+        st = models.protocol_b_sweep(e, vids, usig, unary_used.reshape(-1, K))
+        assert gr.sweep() == st.updates
+    tol = TOL[dtype] if dtype == cap.F64 else 2e-5
+    want = C.get_values([C.get_variable_marginal(C.get_variable(e, v)) for v in vids]).reshape(H, W, K)
+    np.testing.assert_allclose(gr.get_marginals(), want, rtol=tol, atol=tol * 1e-3)
+    # every message plane: m2v from / m2f towards the (up, left, right, down) factor
+    nb = {0: (-1, 0), 1: (0, -1), 2: (0, 1), 3: (1, 0)}
+    fac = {}
+    for f, a, b in pair:
+        fac[(a, b)] = f
+        fac[(b, a)] = f
+    for d, (di, dj) in nb.items():
+        got_v, got_f = gr.get_messages(d), gr.get_messages(4 + d)
+        for i in range(H):
+            for j in range(W):
+                if 0 <= i + di < H and 0 <= j + dj < W:
+                    f = fac[(pix[i][j], pix[i + di][j + dj])]
+                    np.testing.assert_allclose(got_v[i, j], C.get_value(C.get_connection_message_to_variable(e, pix[i][j], f)),
+                                               rtol=tol, atol=tol * 1e-3)
+                    np.testing.assert_allclose(got_f[i, j], C.get_value(C.get_connection_message_to_factor(e, pix[i][j], f)),
+                                               rtol=tol, atol=tol * 1e-3)
+
+
+def test_potts_grid_row_sharding_is_bit_identical():
+    """Two shards exchanging halo rows give exactly the single-shard result."""
+    H, W, K, beta, sweeps = 10, 12, 16, 0.7, 4
+    unary = np.random.Generator(np.random.PCG64(3)).dirichlet(np.ones(K), size=(H, W)).astype(np.float32)
+    full = C.PottsGrid(H, W, K, beta)
+    full.set_unary(unary)
+    full.reset_messages()
+    top = C.PottsGrid(4, W, K, beta, has_lower=True)
+    bot = C.PottsGrid(6, W, K, beta, has_upper=True)
+    top.set_unary(unary[:4])
+    bot.set_unary(unary[4:])
+    top.reset_messages()
+    bot.reset_messages()
+    nbytes = top.halo_elems * 4
+    for s in range(sweeps):
+        full.sweep()
+        top.sweep()
+        bot.sweep()
+        top.sync()
+        bot.sync()
+        # top sends its `down` row to bot's upper halo; bot sends its `up` row to top's lower halo
+        _d2d(bot.halo_recv_ptr(0), top.halo_send_ptr(1), nbytes)
+        _d2d(top.halo_recv_ptr(1), bot.halo_send_ptr(0), nbytes)
+    got = np.concatenate([top.get_marginals(), bot.get_marginals()], axis=0)
+    assert np.array_equal(got, full.get_marginals())
+    assert top.sweep() + bot.sweep() == full.sweep()  # same number of message updates
+
+
+def _d2d(dst, src, nbytes):
+    """raw device-to-device copy (plumbing only)"""
+    import ctypes
+
+    rt = ctypes.CDLL("libcudart.so.12")
+    rt.cudaMemcpy.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int]
+    assert rt.cudaMemcpy(dst, src, nbytes, 3) == 0  # 3 = cudaMemcpyDeviceToDevice
+
+
+@pytest.mark.parametrize("dtype,K", [(cap.F32, 64), (cap.F64, 64), (cap.F32, 32), (cap.F32, 8), (cap.F32, 96)])
+def test_hmm_kernel_vs_oracle(oracle_api, dtype, K):
+    B, T, M = 11, 40, 7
+    rng = np.random.Generator(np.random.PCG64(1234))
+    A = rng.dirichlet(np.ones(K), size=K)
+    E = rng.dirichlet(np.ones(K), size=M).T * K
+    obs = rng.integers(0, M, size=(T, B)).astype(np.uint8)
+    hm = C.HmmBatch(B, T, K, M, dtype=dtype)
+    hm.set_tables(A, E)
+    hm.set_observations(obs)
+    assert hm.update_marginals() == B * (6 * T - 4)
+    got_m, got_f = hm.get_marginals(), hm.get_forward()
+    A_used = A.astype(hm.np_dtype).astype(np.float64)
+    tol = 1e-11 if dtype == cap.F64 else 3e-5
+    for b in (0, B - 1):
+        e, z, y, prior, em, tr = models.make_hmm_model(T, K, M, A_used, E, oracle_api)
+        models.hmm_set_data(e, z, y, prior, em, obs[:, b], K)
+        C.update_marginals(e, z, schedule="seq")
+        want_m = C.get_values([C.get_variable_marginal(C.get_variable(e, v)) for v in z])
+        np.testing.assert_allclose(got_m[:, b, :], want_m, rtol=tol, atol=tol * 1e-3)
+        want_f = C.get_values([C.get_connection_message_to_factor(e, z[t], tr[t]) for t in range(T - 1)])
+        np.testing.assert_allclose(got_f[:-1, b, :], want_f, rtol=tol, atol=tol * 1e-3)
