@@ -304,11 +304,8 @@ def bench_potts_grid(args, pkg, rank, world, local):
 
     cap = pkg.capi
     N, K, beta = args.grid, 16, 0.7
-    rows = N // world
-    row0 = rank * rows
-    if rank == world - 1:
-        rows = N - row0
-    gr = pkg.PottsGrid(rows, N, K, beta, dtype=cap.F32, device=local, has_upper=rank > 0, has_lower=rank < world - 1)
+    row0, rows, has_up, has_down = pkg.row_shard(N, world, rank)
+    gr = pkg.PottsGrid(rows, N, K, beta, dtype=cap.F32, device=local, has_upper=has_up, has_lower=has_down)
     rng = np.random.Generator(np.random.PCG64(1234 + rank))
     unary_host = torch.empty((rows, N, K), dtype=torch.float32).pin_memory()
     un = unary_host.numpy()
@@ -324,24 +321,18 @@ def bench_potts_grid(args, pkg, rank, world, local):
 
     def tens(ptr):
         if ptr not in cache:
-            cache[ptr] = torch.as_tensor(DevArr(ptr, n), device=f"cuda:{local}")
+            cache[ptr] = pkg.device_tensor(ptr, n, local)
         return cache[ptr]
 
+    halo = pkg.HaloExchanger(dist, rank, world)
     upd = [0]
 
     def step():
         upd[0] = gr.sweep()
         if world > 1:
-            ops = []
-            with torch.cuda.stream(ext):
-                if rank > 0:
-                    ops.append(dist.P2POp(dist.isend, tens(gr.halo_send_ptr(0)), rank - 1))
-                    ops.append(dist.P2POp(dist.irecv, tens(gr.halo_recv_ptr(0)), rank - 1))
-                if rank < world - 1:
-                    ops.append(dist.P2POp(dist.isend, tens(gr.halo_send_ptr(1)), rank + 1))
-                    ops.append(dist.P2POp(dist.irecv, tens(gr.halo_recv_ptr(1)), rank + 1))
-                for w in dist.batch_isend_irecv(ops):
-                    w.wait()
+            with torch.cuda.stream(ext):  # NCCL orders itself after the sweep on the library's stream
+                halo.exchange(tens(gr.halo_send_ptr(0)) if has_up else None, tens(gr.halo_send_ptr(1)) if has_down else None,
+                              tens(gr.halo_recv_ptr(0)) if has_up else None, tens(gr.halo_recv_ptr(1)) if has_down else None)
 
     launches0 = pkg.default_api().kernel_launches()
     for _ in range(args.warmup):

@@ -13,7 +13,6 @@
 #include <algorithm>
 #include <cstring>
 #include <map>
-#include <unordered_set>
 
 #include "common.cuh"
 #include "host_graph.hpp"
@@ -499,6 +498,8 @@ struct DeviceEngine {
     std::vector<unsigned char> host_vals;    // value mirror, valid with host_state_valid
     std::vector<uint32_t> lnk_off, lnk_ids;  // linked signals per variable id (CSR), rebuilt when links change
     bool links_dirty = true;
+    std::vector<uint32_t> host_mark;  // epoch-stamped scratch for the set_values independence check
+    uint32_t host_mark_tag = 0;
     std::map<int32_t, RuleDef> rules;     // by factor type
     std::vector<int32_t> key_ftype;       // key-1 -> factor type
     std::vector<double> fparam;           // per id, NaN = unset
@@ -1057,14 +1058,22 @@ struct DeviceEngine {
                 err = "set_values: bad signal id";
                 return CXB_ERR_BAD_ARG;
             }
+        // members that depend on each other (or repeat) must be applied one by one, in order (sequential set_value!)
         bool independent = true;
         if (n > 1) {
-            std::unordered_set<int64_t> members(sids, sids + n);
-            if ((int64_t)members.size() != n) independent = false;
+            if (host_mark.size() < (size_t)N) host_mark.assign((size_t)N, 0);
+            if (++host_mark_tag == 0) {
+                std::fill(host_mark.begin(), host_mark.end(), 0u);
+                host_mark_tag = 1;
+            }
+            for (int64_t i = 0; i < n && independent; ++i) {
+                if (host_mark[sids[i]] == host_mark_tag) independent = false;
+                host_mark[sids[i]] = host_mark_tag;
+            }
             for (int64_t i = 0; i < n && independent; ++i) {
                 uint32_t s = (uint32_t)sids[i];
                 for (uint32_t k = csr.dep_off[s]; k < csr.dep_off[s + 1]; ++k)
-                    if (members.count(csr.dep_ids[k])) {
+                    if (host_mark[csr.dep_ids[k]] == host_mark_tag) {
                         independent = false;
                         break;
                     }

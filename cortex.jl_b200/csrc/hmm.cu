@@ -31,7 +31,10 @@ __device__ __forceinline__ T warp_sum(T v) {
 // One pass over time. FWD: t ascending, writes fwd[t] = m2f(z_t, tr_t) = normalise(em_t * pred_t).
 // BWD: t descending, reads fwd[t], writes marg[t] = normalise(fwd[t] * bwd_t), carries
 // m2f(z_t, tr_{t-1}) = normalise(em_t * bwd_t).  tbl is A (FWD) or A^T (BWD), row-major [K][K];
-// emis_n is the column-normalised emission table transposed to [M][K] (m2v(z_t, em_t) = emis_n[o_t]).
+// emis_n is the column-normalised emission table transposed to [M][K] (m2v(z_t, em_t) = emis_n[o_t]), staged in
+// shared memory.  Nothing on the per-step critical path waits on global memory: observations are fetched 32 steps at a
+// time (one per lane, broadcast by shuffle, double buffered), the forward message of the next step is already in
+// registers and the one 8 steps ahead is being pulled into L2 (prefetch.global.L2).
 template <class T, int K, bool REGA, bool FWD>
 __global__ void __launch_bounds__(HMM_WARPS * 32)
 k_hmm_pass(const T* __restrict__ tbl, const T* __restrict__ emis_n, const uint8_t* __restrict__ obs, T* __restrict__ fwd,
@@ -43,8 +46,10 @@ k_hmm_pass(const T* __restrict__ tbl, const T* __restrict__ emis_n, const uint8_
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const long long b = (long long)blockIdx.x * HMM_WARPS + warp;
     const bool live = b < B;
-    T* sh_v = reinterpret_cast<T*>(smem_raw) + (size_t)warp * Kk;       // per-warp staging of v
-    T* sh_tbl = reinterpret_cast<T*>(smem_raw) + (size_t)HMM_WARPS * Kk;  // streamed path: row tile of tbl
+    const long long bb = live ? b : 0;
+    T* sh_v = reinterpret_cast<T*>(smem_raw) + (size_t)warp * Kk;            // per-warp staging of v
+    T* sh_em = reinterpret_cast<T*>(smem_raw) + (size_t)HMM_WARPS * Kk;        // [M][K] emission messages
+    T* sh_tbl = sh_em + (size_t)n_sym * Kk;                                    // streamed path: row tile of tbl
 
     T areg[REGA ? K : 1][REGA ? K / 32 : 1];
     if (REGA) {
@@ -53,18 +58,54 @@ k_hmm_pass(const T* __restrict__ tbl, const T* __restrict__ emis_n, const uint8_
 #pragma unroll
             for (int c = 0; c < K / 32; ++c) areg[i][c] = tbl[(size_t)i * K + lane + 32 * c];
     }
+    for (int x = threadIdx.x; x < n_sym * Kk; x += blockDim.x) sh_em[x] = emis_n[x];
     const bool whole_table = !REGA && tile_rows >= Kk;
-    if (whole_table) {
+    if (whole_table)
         for (int x = threadIdx.x; x < Kk * Kk; x += blockDim.x) sh_tbl[x] = tbl[x];
-        __syncthreads();
-    }
+    __syncthreads();
+
+    auto time_of = [&](long long step) { return FWD ? step : Tn - 1 - step; };
+    auto load_obs_block = [&](long long step0) -> int {  // lane l fetches the symbol of step0 + l
+        long long st = step0 + lane;
+        return (st < Tn) ? (int)obs[(size_t)time_of(st) * B + bb] : 0;
+    };
+    int obs_cur = 0, obs_next = load_obs_block(0);
 
     T v[CPL_MAX];  // carried message (lane's states)
 #pragma unroll
     for (int c = 0; c < CPL_MAX; ++c) v[c] = T(0);
+    T a_next[CPL_MAX];  // BWD: forward message of the upcoming step
+#pragma unroll
+    for (int c = 0; c < CPL_MAX; ++c) {
+        int j = lane + 32 * c;
+        a_next[c] = (!FWD && c < cpl && j < Kk) ? __ldcs(&fwd[((size_t)time_of(0) * B + bb) * Kk + j]) : T(0);
+    }
 
     for (long long step = 0; step < Tn; ++step) {
-        const long long t = FWD ? step : Tn - 1 - step;
+        const long long t = time_of(step);
+        if ((step & 31) == 0) {
+            obs_cur = obs_next;
+            obs_next = load_obs_block(step + 32);
+        }
+        int o = __shfl_sync(0xffffffffu, obs_cur, (int)(step & 31));
+        if (o >= n_sym) o = n_sym - 1;
+        T a[CPL_MAX];
+        if (!FWD) {
+#pragma unroll
+            for (int c = 0; c < CPL_MAX; ++c) a[c] = a_next[c];
+            if (step + 1 < Tn) {
+                const T* nx = &fwd[((size_t)time_of(step + 1) * B + bb) * Kk];
+#pragma unroll
+                for (int c = 0; c < CPL_MAX; ++c) {
+                    int j = lane + 32 * c;
+                    if (c < cpl && j < Kk) a_next[c] = __ldcs(nx + j);
+                }
+            }
+            if (step + 8 < Tn) {
+                const T* far = &fwd[((size_t)time_of(step + 8) * B + bb) * Kk];
+                if (lane * 32 < Kk * (int)sizeof(T)) asm volatile("prefetch.global.L2 [%0];" ::"l"(far + lane * (32 / sizeof(T))));
+            }
+        }
         T out[CPL_MAX];
 #pragma unroll
         for (int c = 0; c < CPL_MAX; ++c) out[c] = T(0);
@@ -77,6 +118,11 @@ k_hmm_pass(const T* __restrict__ tbl, const T* __restrict__ emis_n, const uint8_
                 if (c < cpl && lane + 32 * c < Kk) sh_v[lane + 32 * c] = v[c];
             __syncwarp();
             if (REGA) {
+                T acc[REGA ? K / 32 : 1][4];  // 4 independent FMA chains per column
+#pragma unroll
+                for (int c = 0; c < K / 32; ++c)
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) acc[c][u] = T(0);
 #pragma unroll
                 for (int i = 0; i < K; i += 4) {
                     T vi[4];
@@ -90,8 +136,10 @@ k_hmm_pass(const T* __restrict__ tbl, const T* __restrict__ emis_n, const uint8_
 #pragma unroll
                     for (int u = 0; u < 4; ++u)
 #pragma unroll
-                        for (int c = 0; c < K / 32; ++c) out[c] = fma(areg[i + u][c], vi[u], out[c]);
+                        for (int c = 0; c < K / 32; ++c) acc[c][u] = fma(areg[i + u][c], vi[u], acc[c][u]);
                 }
+#pragma unroll
+                for (int c = 0; c < K / 32; ++c) out[c] = (acc[c][0] + acc[c][1]) + (acc[c][2] + acc[c][3]);
             } else if (whole_table) {
                 for (int i = 0; i < Kk; ++i) {
                     T vi = sh_v[i];
@@ -118,16 +166,14 @@ k_hmm_pass(const T* __restrict__ tbl, const T* __restrict__ emis_n, const uint8_
                 }
             }
         }
-        // emission message of this step
-        int o = live ? (int)obs[(size_t)t * B + b] : 0;
-        if (o >= n_sym) o = n_sym - 1;
+        // emission message of this step (shared memory)
         T em[CPL_MAX];
 #pragma unroll
         for (int c = 0; c < CPL_MAX; ++c) {
             int j = lane + 32 * c;
-            em[c] = (c < cpl && j < Kk) ? emis_n[(size_t)o * Kk + j] : T(0);
+            em[c] = (c < cpl && j < Kk) ? sh_em[(size_t)o * Kk + j] : T(0);
         }
-        const size_t base = ((size_t)t * B + (live ? b : 0)) * Kk;
+        const size_t base = ((size_t)t * B + bb) * Kk;
         if (FWD) {
             // m2f(z_t, tr_t) = normalise(em * pred); at t = 0 the uniform prior leaves normalise(em)
             T part = T(0);
@@ -144,13 +190,10 @@ k_hmm_pass(const T* __restrict__ tbl, const T* __restrict__ emis_n, const uint8_
                 if (live && c < cpl && j < Kk) __stcs(&fwd[base + j], v[c]);
             }
         } else {
-            T a[CPL_MAX];
             T part = T(0), part2 = T(0);
 #pragma unroll
             for (int c = 0; c < CPL_MAX; ++c) {
-                int j = lane + 32 * c;
-                a[c] = (live && c < cpl && j < Kk) ? __ldcs(&fwd[base + j]) : T(0);
-                T g = has_prev ? a[c] * out[c] : a[c];  // marginal = fwd * bwd
+                T g = has_prev ? a[c] * out[c] : a[c];    // marginal = fwd * bwd
                 T m = has_prev ? em[c] * out[c] : em[c];  // m2f(z_t, tr_{t-1}) = em * bwd
                 a[c] = g;
                 v[c] = m;
@@ -250,7 +293,7 @@ struct Hmm {
     }
     template <class T>
     int32_t launch_t() {
-        size_t stage = (size_t)HMM_WARPS * K * sizeof(T);
+        size_t stage = ((size_t)HMM_WARPS * K + (size_t)M * K) * sizeof(T);  // per-warp staging + emission messages
         if (sizeof(T) == 4 && K == 64) return launch_pair<T, 64, true>(0, stage);
         if (K == 32) return launch_pair<T, 32, true>(0, stage);
         size_t budget = 200 * 1024 - stage;

@@ -1,0 +1,48 @@
+#!/usr/bin/env python
+"""Summarise an ncu report into the few counters the roofline argument needs.
+usage: python profiles/extract_ncu.py gpurun_out/prof.ncu-rep [kernel-substring] > profiles/rNN_<kernel>.json"""
+import csv
+import json
+import subprocess
+import sys
+
+WANT = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum",
+        "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "sm__throughput.avg.pct_of_peak_sustained_elapsed",
+        "sm__warps_active.avg.pct_of_peak_sustained_active", "launch__registers_per_thread", "launch__grid_size",
+        "launch__block_size", "launch__occupancy_limit_registers", "launch__occupancy_limit_shared_mem",
+        "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active", "smsp__inst_executed.sum",
+        "l1tex__t_sectors_pipe_lsu_mem_global_op_ld.sum", "l1tex__t_requests_pipe_lsu_mem_global_op_ld.sum",
+        "l1tex__t_sectors_pipe_lsu_mem_global_op_st.sum", "l1tex__t_requests_pipe_lsu_mem_global_op_st.sum",
+        "smsp__average_warp_latency_issue_stalled_long_scoreboard.ratio", "smsp__issue_active.avg.pct_of_peak_sustained_active",
+        "lts__t_sector_hit_rate.pct"]
+TO_BYTES = {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}
+
+
+def main():
+    rep, sub = sys.argv[1], (sys.argv[2] if len(sys.argv) > 2 else "")
+    out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(out.splitlines()))
+    hdr, units = rows[0], rows[1]
+    idx = {h: i for i, h in enumerate(hdr)}
+    res = []
+    for r in rows[2:]:
+        name = r[idx["Kernel Name"]]
+        if sub and sub not in name:
+            continue
+        d = {"kernel": name}
+        for k in WANT:
+            if k in idx:
+                try:
+                    d[k] = float(r[idx[k]].replace(",", ""))
+                    d[k + ".unit"] = units[idx[k]]
+                except ValueError:
+                    pass
+        rd = d.get("dram__bytes_read.sum", 0) * TO_BYTES.get(d.get("dram__bytes_read.sum.unit", "byte"), 1)
+        wr = d.get("dram__bytes_write.sum", 0) * TO_BYTES.get(d.get("dram__bytes_write.sum.unit", "byte"), 1)
+        d["dram_bytes_per_launch"] = rd + wr
+        res.append(d)
+    json.dump(res, sys.stdout, indent=1)
+
+
+if __name__ == "__main__":
+    main()

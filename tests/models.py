@@ -62,24 +62,31 @@ def potts_table(K, beta):
     return np.exp(beta * np.eye(K))
 
 
-def make_grid_model(H, W, K, beta, api, dtype=cap.F64, rule="potts", link=True):
+def make_grid_model(H, W, K, beta, api, dtype=cap.F64, rule="potts", link=True, ghost_top=False, ghost_bottom=False):
     """BASELINE config 4 at reduced size: pixels row-major, one unary leaf factor per pixel, pairwise factors
-    on the 4-neighbourhood (horizontal edges then vertical, ascending ids), protocol B linked signals."""
+    on the 4-neighbourhood (horizontal edges then vertical, ascending ids), protocol B linked signals.
+
+    ghost_top / ghost_bottom (row sharding): an extra row of *ghost* pixels stands for the neighbour
+    shard's boundary row. A ghost has exactly one factor (the cut edge), so its m2f is a plain data signal that the
+    halo exchange sets every sweep; `pix` then has H + ghosts rows and only rows `real` are requested."""
     g = C.BipartiteFactorGraph()
-    pix = [[g.add_variable(C.Variable(name="s", index=(i, j))) for j in range(W)] for i in range(H)]
-    un = [[g.add_factor(C.Factor(functional_form="unary")) for j in range(W)] for i in range(H)]
-    for i in range(H):
+    R = H + int(ghost_top) + int(ghost_bottom)
+    is_ghost = [ghost_top and i == 0 or ghost_bottom and i == R - 1 for i in range(R)]
+    pix = [[g.add_variable(C.Variable(name="s", index=(i, j))) for j in range(W)] for i in range(R)]
+    un = [[None if is_ghost[i] else g.add_factor(C.Factor(functional_form="unary")) for j in range(W)] for i in range(R)]
+    for i in range(R):
         for j in range(W):
-            g.add_edge(pix[i][j], un[i][j], C.Connection(label="out"))
+            if not is_ghost[i]:
+                g.add_edge(pix[i][j], un[i][j], C.Connection(label="out"))
     pair = []
-    for i in range(H):
+    for i in range(R):
         for j in range(W):
-            if j + 1 < W:
+            if j + 1 < W and not is_ghost[i]:
                 f = g.add_factor(C.Factor(functional_form="pair"))
                 g.add_edge(pix[i][j], f, C.Connection(label="a"))
                 g.add_edge(pix[i][j + 1], f, C.Connection(label="b"))
                 pair.append((f, pix[i][j], pix[i][j + 1]))
-            if i + 1 < H:
+            if i + 1 < R:
                 f = g.add_factor(C.Factor(functional_form="pair"))
                 g.add_edge(pix[i][j], f, C.Connection(label="a"))
                 g.add_edge(pix[i + 1][j], f, C.Connection(label="b"))
@@ -92,7 +99,7 @@ def make_grid_model(H, W, K, beta, api, dtype=cap.F64, rule="potts", link=True):
     engine = C.InferenceEngine(model_engine=g, dependency_resolver=C.DefaultDependencyResolver(),
                                inference_request_processor=proc, dtype=dtype, api=api)
     if link:
-        protocol_b_link(engine, [v for row in pix for v in row])
+        protocol_b_link(engine, [v for i, row in enumerate(pix) if not is_ghost[i] for v in row])
     return engine, pix, un, pair
 
 
