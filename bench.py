@@ -484,8 +484,9 @@ def bench_engine_graph(args, pkg, rank, world, local, which):
         store.check(api.resolve_dependencies(store.h, cap.RESOLVER_DEFAULT_BP))
         # protocol B: link + initialise every pairwise m2f, evidence = unary m2v
         pair_m2f = n + 2 * (n + np.arange(2 * m)) + 1  # sid of m2f(connection c) = n_var + 2c + 1, pair connections c >= n
-        for c, s in zip(range(n, n + 2 * m), pair_m2f):
-            store.check(api.link_signal(store.h, int(ev[c]), int(s)))
+        lv = np.ascontiguousarray(ev[n:n + 2 * m], dtype=np.int64)
+        ls = np.ascontiguousarray(pair_m2f, dtype=np.int64)
+        store.check(api.link_signals(store.h, 2 * m, lv.ctypes.data_as(cap.i64p), ls.ctypes.data_as(cap.i64p)))
         init = np.full((2 * m, K), 1.0 / K)
         pm = np.ascontiguousarray(pair_m2f, dtype=np.int64)
         store.check(api.set_values(store.h, 2 * m, pm.ctypes.data_as(cap.i64p), init.ctypes.data_as(cap.f64p), K))

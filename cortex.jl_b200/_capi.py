@@ -49,6 +49,7 @@ _COMMON = {
     "add_dependency": (i32, [vp, i64, i64, i32]),
     "resolve_dependencies": (i32, [vp, i32]),
     "link_signal": (i32, [vp, i64, i64]),
+    "link_signals": (i32, [vp, i64, i64p, i64p]),
     "n_signals": (i64, [vp]),
     "signal_id": (i64, [vp, i32, i64, i64]),
     "signal_info": (i32, [vp, i64, i64p]),

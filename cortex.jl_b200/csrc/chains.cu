@@ -46,12 +46,11 @@ constexpr int CH_BLOCK = 64;  // 65,536 chains -> 1,024 CTAs = 6.9 per SM: <1.2%
 
 // msg: [6][T][B] of (L,h) pairs. Classes: 0 m2v(x_t,lik_t)  1 m2v(x_t,tr_{t-1})  2 m2f(x_t,tr_t)
 //                                          3 m2v(x_t,tr_t)   4 m2f(x_t,tr_{t-1})  5 marginal(x_t)
-template <class T>
-__global__ void __launch_bounds__(CH_BLOCK, 8)
+template <class T, int TILE, int BLOCK>
+__global__ void __launch_bounds__(BLOCK, 512 / BLOCK)
 k_chains_fwd_bwd(const T* __restrict__ y, const T* __restrict__ qv, const T* __restrict__ rv,
                  typename Vec2<T>::type* __restrict__ msg, long long B, long long Tn) {
     using V = typename Vec2<T>::type;
-    constexpr int TILE = sizeof(T) == 4 ? CH_TILE : CH_TILE / 2;  // same bytes in flight for fp32 and fp64
     const long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= B) return;
     const T q = qv[b], r = rv[b];
@@ -229,20 +228,34 @@ struct Chains {
         have_noise = true;
         return CXB_OK;
     }
+    template <class T, int TILE, int BLOCK>
+    int32_t launch_variant() {
+        CXB_LAUNCH((k_chains_fwd_bwd<T, TILE, BLOCK>), cdiv((size_t)B, BLOCK), BLOCK, 0, stream, (const T*)y.p, (const T*)q.p,
+                   (const T*)r.p, (typename Vec2<T>::type*)msg.p, B, this->T);
+        return CXB_OK;
+    }
+    // tile = time steps in flight per thread (double buffered), block = chains per CTA. Defaults are the measured
+    // best on B200 (profiles/); CXB_CHAINS_TILE / CXB_CHAINS_BLOCK override them for tuning runs.
+    template <class T>
+    int32_t dispatch() {
+        int tile = sizeof(T) == 4 ? CH_TILE : CH_TILE / 2, block = CH_BLOCK;
+        if (const char* e = getenv("CXB_CHAINS_TILE")) tile = atoi(e);
+        if (const char* e = getenv("CXB_CHAINS_BLOCK")) block = atoi(e);
+#define V_(TL, BL) if (tile == TL && block == BL) return launch_variant<T, TL, BL>();
+        V_(2, 64) V_(4, 64) V_(8, 64) V_(16, 64) V_(2, 128) V_(4, 128) V_(8, 128) V_(16, 128) V_(4, 256) V_(8, 256) V_(4, 32) V_(8, 32)
+#undef V_
+        err = "unsupported CXB_CHAINS_TILE / CXB_CHAINS_BLOCK combination";
+        return CXB_ERR_BAD_ARG;
+    }
     int32_t launch() {
         if (!have_noise || !have_obs) {
             err = "set the noise variances and the observations first";
             return CXB_ERR_STATE;
         }
         CXB_CUDA(cudaSetDevice(device));
-        unsigned grid = cdiv((size_t)B, CH_BLOCK);
         CXB_CUDA(cudaEventRecord(ev0, stream));
-        if (dtype == CXB_F32)
-            CXB_LAUNCH(k_chains_fwd_bwd<float>, grid, CH_BLOCK, 0, stream, (const float*)y.p, (const float*)q.p, (const float*)r.p,
-                       (float2*)msg.p, B, T);
-        else
-            CXB_LAUNCH(k_chains_fwd_bwd<double>, grid, CH_BLOCK, 0, stream, (const double*)y.p, (const double*)q.p,
-                       (const double*)r.p, (double2*)msg.p, B, T);
+        int32_t st = dtype == CXB_F32 ? dispatch<float>() : dispatch<double>();
+        if (st) return st;
         CXB_CUDA(cudaEventRecord(ev1, stream));
         CXB_CUDA(cudaGetLastError());
         ran = true;

@@ -25,7 +25,7 @@ constexpr uint64_t ALL_W = 0x2222222222222222ull, ALL_C = 0x4444444444444444ull,
                    PASS = 0x1111111111111111ull;
 constexpr int ERR_INDEPENDENCE = 1, ERR_LISTENER_DONE = 2, ERR_RULE_ARG = 4;
 constexpr int KEY_COMBINE = 0;  // dense rule keys: 0 = family reduce, 1..n_types = m2v of a factor type, n_types+1 = no rule
-constexpr int MS_THREADS = 256, MS_ITEMS = 16, MS_TILE = MS_THREADS * MS_ITEMS;
+
 
 // device view of the engine state (plain pointers, passed by value to kernels)
 struct View {
@@ -39,7 +39,11 @@ struct View {
     const uint8_t *kind, *rkey;
     const int32_t *svar, *sfac;
     uint32_t *done_epoch, *visit_epoch;
-    uint8_t* front_flag;
+    uint32_t* front_epoch;            // == lvl_epoch: member of the current level's frontier
+    uint32_t* front;                  // frontier buffer, partitioned by rule key
+    const uint32_t* key_base;         // [n_keys] start of each key's partition
+    uint32_t* key_cnt;                // [n_keys] cursors
+    int use_keys;
     int* err_flag;
     unsigned long long* kind_count;  // [6]
 };
@@ -75,17 +79,18 @@ __device__ __forceinline__ bool pending_eval(const View& e, uint32_t s) {
 }
 
 // request_inference_for, src/inference_engine.jl:305-318: flag the direct dependencies of every requested
-// marginal and its linked signals (is_potentially_pending = true, is_pending = false)
-__global__ void k_request(View e, const uint32_t* req_marg, const uint32_t* link_off, const uint32_t* link_ids, uint32_t n) {
+// marginal and its linked signals (is_potentially_pending = true, is_pending = false). One thread per requested
+// marginal, then one thread per linked-signal entry (flat: hub variables link thousands of signals).
+__global__ void k_request(View e, const uint32_t* req_marg, const uint32_t* link_ids, uint32_t n, uint32_t n_links) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    uint32_t m = req_marg[i];
-    for (uint32_t k = e.dep_off[m]; k < e.dep_off[m + 1]; ++k) {
-        uint32_t d = e.dep_ids[k];
-        e.props[d] = (uint8_t)((e.props[d] & P_COMPUTED) | P_PP);
-    }
-    for (uint32_t k = link_off[i]; k < link_off[i + 1]; ++k) {
-        uint32_t d = link_ids[k];
+    if (i < n) {
+        uint32_t m = req_marg[i];
+        for (uint32_t k = e.dep_off[m]; k < e.dep_off[m + 1]; ++k) {
+            uint32_t d = e.dep_ids[k];
+            e.props[d] = (uint8_t)((e.props[d] & P_COMPUTED) | P_PP);
+        }
+    } else if (i < n + n_links) {
+        uint32_t d = link_ids[i - n];
         e.props[d] = (uint8_t)((e.props[d] & P_COMPUTED) | P_PP);
     }
 }
@@ -103,41 +108,53 @@ __global__ void k_seeds(const uint32_t* req_marg, const uint8_t* ready, uint32_t
     if (take) out[base + __popc(m & ((1u << lane) - 1))] = req_marg[i];
 }
 
+// Append a pending signal to the frontier of this level, grouped by rule key: the frontier buffer is partitioned
+// statically by key (key_base[k] = number of signals with a smaller key), the per-key cursors are bumped with
+// warp-aggregated atomics (one atomic per distinct key per warp: __match_any over the active lanes).
+__device__ __forceinline__ void frontier_push(const View& e, uint32_t d, uint32_t lvl_epoch) {
+    if (atomicExch(&e.front_epoch[d], lvl_epoch) == lvl_epoch) return;  // already in this level's frontier
+    int key = e.use_keys ? e.rkey[d] : 0;
+    unsigned act = __activemask();
+    unsigned same = __match_any_sync(act, key);
+    int lane = threadIdx.x & 31, leader = __ffs(same) - 1;
+    uint32_t base = 0;
+    if (lane == leader) base = atomicAdd(&e.key_cnt[key], (uint32_t)__popc(same));
+    base = __shfl_sync(same, base, leader);
+    e.front[e.key_base[key] + base + __popc(same & ((1u << lane) - 1))] = d;
+}
+
 // One breadth-first step of process_dependencies! (src/signal.jl:466-490) over a list of signals:
-// visit every dependency (f(dep) = is_pending), flag the pending ones, descend through non-pending
-// *intermediate* ones. `done` signals are neither reported nor descended through (A.5).
-__global__ void k_bfs(View e, const uint32_t* in, uint32_t n_in, uint32_t* out, uint32_t* n_out, uint32_t lvl_epoch,
+// visit every dependency (f(dep) = is_pending), push the pending ones to the frontier, descend through non-pending
+// *intermediate* ones. `done` signals are neither reported nor descended through (A.5). The list length lives on
+// the device (written by the previous step), so consecutive steps need no host round trip.
+__global__ void k_bfs(View e, const uint32_t* in, const uint32_t* n_in_ptr, uint32_t* out, uint32_t* n_out, uint32_t lvl_epoch,
                       uint32_t req_epoch, int use_done) {
-    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n_in) return;
-    uint32_t s = in[i];
-    uint32_t off = e.dep_off[s], nd = e.dep_off[s + 1] - off, noff = e.nib_off[s];
-    for (uint32_t k = 0; k < nd; ++k) {
-        uint32_t d = e.dep_ids[off + k];
-        if (use_done && e.done_epoch[d] == req_epoch) continue;
-        if (pending_eval(e, d)) {
-            e.front_flag[d] = 1;
-        } else {
-            uint32_t nibble = (uint32_t)(e.nib[noff + (k >> 4)] >> ((k & 15) << 2)) & 0xF;
-            if ((nibble & CXB_NIB_INTERMEDIATE) && atomicExch(&e.visit_epoch[d], lvl_epoch) != lvl_epoch)
-                out[atomicAdd(n_out, 1u)] = d;
+    const uint32_t n_in = *n_in_ptr;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_in; i += gridDim.x * blockDim.x) {
+        uint32_t s = in[i];
+        uint32_t off = e.dep_off[s], nd = e.dep_off[s + 1] - off, noff = e.nib_off[s];
+        for (uint32_t k = 0; k < nd; ++k) {
+            uint32_t d = e.dep_ids[off + k];
+            if (use_done && e.done_epoch[d] == req_epoch) continue;
+            if (pending_eval(e, d)) {
+                frontier_push(e, d, lvl_epoch);
+            } else {
+                uint32_t nibble = (uint32_t)(e.nib[noff + (k >> 4)] >> ((k & 15) << 2)) & 0xF;
+                if ((nibble & CXB_NIB_INTERMEDIATE) && atomicExch(&e.visit_epoch[d], lvl_epoch) != lvl_epoch)
+                    out[atomicAdd(n_out, 1u)] = d;
+            }
         }
     }
 }
 
-// final phase candidates (:610-628): mode 0 = requested marginals, mode 1 = their linked signals
-__global__ void k_final_flags(View e, const uint32_t* req_marg, const uint32_t* link_off, const uint32_t* link_ids,
-                              uint32_t n, int mode) {
+// final phase candidates (:610-628): the requested marginals (i < n), their linked signals (flat entries after)
+__global__ void k_final_flags(View e, const uint32_t* req_marg, const uint32_t* link_ids, uint32_t n, uint32_t n_links, int mode,
+                              uint32_t lvl_epoch) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
     if (mode == 0) {
-        uint32_t m = req_marg[i];
-        if (pending_eval(e, m)) e.front_flag[m] = 1;
+        if (i < n && pending_eval(e, req_marg[i])) frontier_push(e, req_marg[i], lvl_epoch);
     } else {
-        for (uint32_t k = link_off[i]; k < link_off[i + 1]; ++k) {
-            uint32_t d = link_ids[k];
-            if (pending_eval(e, d)) e.front_flag[d] = 1;
-        }
+        if (i < n_links && pending_eval(e, link_ids[i])) frontier_push(e, link_ids[i], lvl_epoch);
     }
 }
 
@@ -148,136 +165,76 @@ __global__ void k_ready(View e, const uint32_t* req_marg, uint8_t* ready, uint32
     if (pending_eval(e, req_marg[i])) ready[i] = 1;
 }
 
-// ---- ordered multisplit of the flagged signals by rule key (warp-ballot / match ranking) ---------------
-// pass 1: per-tile histogram of keys
-__global__ void k_ms_hist(const uint8_t* flag, const uint8_t* rkey, uint32_t n, uint32_t* tile_hist, uint32_t n_tiles,
-                          int n_keys, int use_keys) {
-    extern __shared__ uint32_t sh[];
-    for (int k = threadIdx.x; k < n_keys; k += blockDim.x) sh[k] = 0;
-    __syncthreads();
-    uint32_t base = blockIdx.x * MS_TILE;
-#pragma unroll
-    for (int it = 0; it < MS_ITEMS; ++it) {
-        uint32_t i = base + it * MS_THREADS + threadIdx.x;
-        if (i < n && flag[i]) atomicAdd(&sh[use_keys ? rkey[i] : 0], 1u);
-    }
-    __syncthreads();
-    for (int k = threadIdx.x; k < n_keys; k += blockDim.x) tile_hist[(size_t)k * n_tiles + blockIdx.x] = sh[k];
-}
-// pass 2: exclusive scan of the key-major histogram (single block), writes per-key totals
-__global__ void k_ms_scan(uint32_t* tile_hist, uint32_t n_tiles, int n_keys, uint32_t* key_count) {
-    __shared__ uint32_t warp_sum[32];
-    __shared__ uint32_t carry;
-    if (threadIdx.x == 0) carry = 0;
-    __syncthreads();
-    size_t total = (size_t)n_keys * n_tiles;
-    int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = blockDim.x >> 5;
-    for (size_t base = 0; base < total; base += blockDim.x) {
-        size_t i = base + threadIdx.x;
-        uint32_t v = i < total ? tile_hist[i] : 0, x = v;
-        for (int o = 1; o < 32; o <<= 1) {
-            uint32_t y = __shfl_up_sync(0xffffffffu, x, o);
-            if (lane >= o) x += y;
-        }
-        if (lane == 31) warp_sum[wid] = x;
-        __syncthreads();
-        if (wid == 0) {
-            uint32_t w = lane < nw ? warp_sum[lane] : 0, ws = w;
-            for (int o = 1; o < 32; o <<= 1) {
-                uint32_t y = __shfl_up_sync(0xffffffffu, ws, o);
-                if (lane >= o) ws += y;
-            }
-            warp_sum[lane] = ws - w;  // exclusive
-        }
-        __syncthreads();
-        uint32_t excl = carry + warp_sum[wid] + x - v;
-        if (i < total) tile_hist[i] = excl;
-        __syncthreads();
-        if (threadIdx.x == blockDim.x - 1) carry = excl + v;
-        __syncthreads();
-    }
-    // key totals: start of key k+1 minus start of key k
-    for (int k = threadIdx.x; k < n_keys; k += blockDim.x) {
-        uint32_t start = tile_hist[(size_t)k * n_tiles];
-        uint32_t end = (k + 1 < n_keys) ? tile_hist[(size_t)(k + 1) * n_tiles] : carry;
-        key_count[k] = end - start;
-        key_count[n_keys + k] = start;  // offsets
-    }
-}
-// pass 3: stable scatter (ascending signal id inside each key), clears the flags
-__global__ void k_ms_scatter(uint8_t* flag, const uint8_t* rkey, uint32_t n, const uint32_t* tile_hist, uint32_t n_tiles,
-                             int n_keys, int use_keys, uint32_t* out) {
-    extern __shared__ uint32_t sh[];  // [n_keys] running base + [8][n_keys] per-warp counts
-    uint32_t* run = sh;
-    uint32_t* wcnt = sh + n_keys;
-    int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    const int nw = MS_THREADS / 32;
-    for (int k = threadIdx.x; k < n_keys; k += blockDim.x) run[k] = tile_hist[(size_t)k * n_tiles + blockIdx.x];
-    uint32_t base = blockIdx.x * MS_TILE;
-    for (int it = 0; it < MS_ITEMS; ++it) {
-        for (int k = threadIdx.x; k < n_keys * nw; k += blockDim.x) wcnt[k] = 0;
-        __syncthreads();
-        uint32_t i = base + it * MS_THREADS + threadIdx.x;
-        bool f = i < n && flag[i];
-        int key = f ? (use_keys ? rkey[i] : 0) : -1;
-        unsigned same = __match_any_sync(0xffffffffu, key);
-        int rank = __popc(same & ((1u << lane) - 1));
-        if (f && rank == 0) wcnt[wid * n_keys + key] = __popc(same);
-        __syncthreads();
-        uint32_t pos = 0;
-        if (f) {
-            pos = run[key] + rank;
-            for (int w = 0; w < wid; ++w) pos += wcnt[w * n_keys + key];
-            out[pos] = i;
-            flag[i] = 0;
-        }
-        __syncthreads();
-        for (int k = threadIdx.x; k < n_keys; k += blockDim.x) {
-            uint32_t add = 0;
-            for (int w = 0; w < nw; ++w) add += wcnt[w * n_keys + k];
-            run[k] += add;
-        }
-        __syncthreads();
-    }
+// the frontier of a level = up to 32 per-key segments of the frontier buffer
+struct Segs {
+    int n;
+    uint32_t total;
+    uint32_t base[32], cnt[32];
+};
+__device__ __forceinline__ uint32_t seg_member(const Segs& sg, const uint32_t* front, uint32_t i) {
+    int k = 0;
+    while (k < sg.n - 1 && i >= sg.cnt[k]) i -= sg.cnt[k++];
+    return front[sg.base[k] + i];
 }
 
-// ---- set_value! side effects for a list of signals, src/signal.jl:232-253 + 339-356 ---------------------
-// (values are already written). check_mode: 0 none (user set_value!), 1 loop phase (independence + done-listener
-// contract), 2 final phase (independence only).
-__global__ void k_apply(View e, const uint32_t* list, uint32_t n, uint32_t req_epoch, int check_mode) {
+// ---- set_value! side effects for the members of a level, src/signal.jl:232-253 + 339-356 -------------------
+// (values are already written). check_mode: 0 none (user set_value!), 1 loop phase (done-listener contract),
+// 2 final phase.  Listener lists of hubs are long (a top ProductOfMessages node of a degree-d variable is a
+// dependency of d/2 m2f signals): members with more than 8 listeners are handled by the whole warp.
+__device__ __forceinline__ void notify(const View& e, uint32_t k, uint32_t req_epoch, int check_mode) {
+    uint32_t L = e.lis_ids[k], slot = e.lis_slot[k];
+    if (e.lis_listen[k]) e.props[L] = (uint8_t)((e.props[L] & P_COMPUTED) | P_PP);
+    atomicOr((unsigned long long*)&e.nib[e.nib_off[L] + (slot >> 4)],
+             (unsigned long long)(CXB_NIB_COMPUTED | CXB_NIB_FRESH) << ((slot & 15) << 2));
+    if (check_mode == 1 && e.done_epoch[L] == req_epoch) atomicOr(e.err_flag, ERR_LISTENER_DONE);
+}
+__global__ void k_apply(View e, Segs sg, uint32_t req_epoch, int check_mode) {
     __shared__ unsigned int kc[6];
     if (threadIdx.x < 6) kc[threadIdx.x] = 0;
     __syncthreads();
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) {
-        uint32_t s = list[i];
+    const bool active = i < sg.total;
+    uint32_t lo = 0, hi = 0;
+    if (active) {
+        uint32_t s = seg_member(sg, e.front, i);
         for (uint32_t c = e.nib_off[s]; c < e.nib_off[s + 1]; ++c) e.nib[c] &= ~ALL_F;  // unset_all_dependencies_fresh!
         e.props[s] = P_COMPUTED;                                                         // (pp, p) = (false, false)
         if (check_mode) e.done_epoch[s] = req_epoch;
         atomicAdd(&kc[e.kind[s]], 1u);
-        for (uint32_t k = e.lis_off[s]; k < e.lis_off[s + 1]; ++k) {
-            uint32_t L = e.lis_ids[k], slot = e.lis_slot[k];
-            if (e.lis_listen[k]) e.props[L] = (uint8_t)((e.props[L] & P_COMPUTED) | P_PP);
-            atomicOr((unsigned long long*)&e.nib[e.nib_off[L] + (slot >> 4)],
-                     (unsigned long long)(CXB_NIB_COMPUTED | CXB_NIB_FRESH) << ((slot & 15) << 2));
-            if (check_mode == 1 && e.done_epoch[L] == req_epoch) atomicOr(e.err_flag, ERR_LISTENER_DONE);
-        }
+        lo = e.lis_off[s];
+        hi = e.lis_off[s + 1];
+    }
+    const bool heavy_me = hi - lo > 8;
+    if (!heavy_me)
+        for (uint32_t k = lo; k < hi; ++k) notify(e, k, req_epoch, check_mode);
+    unsigned heavy = __ballot_sync(0xffffffffu, heavy_me);
+    const int lane = threadIdx.x & 31;
+    while (heavy) {
+        int src = __ffs(heavy) - 1;
+        heavy &= heavy - 1;
+        uint32_t hlo = __shfl_sync(0xffffffffu, lo, src), hhi = __shfl_sync(0xffffffffu, hi, src);
+        for (uint32_t k = hlo + lane; k < hhi; k += 32) notify(e, k, req_epoch, check_mode);
     }
     __syncthreads();
     if (threadIdx.x < 6 && kc[threadIdx.x]) atomicAdd(&e.kind_count[threadIdx.x], (unsigned long long)kc[threadIdx.x]);
 }
-// independence of a level (A.5): no member may depend on another member. Runs BEFORE the rules, while the
-// members are still marked by `mark_epoch` in visit-independent scratch (`done_epoch` is not yet written).
-__global__ void k_mark(uint32_t* mark, const uint32_t* list, uint32_t n, uint32_t tag) {
-    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) mark[list[i]] = tag;
-}
-__global__ void k_check_independent(View e, const uint32_t* mark, const uint32_t* list, uint32_t n, uint32_t tag) {
+// set_value! side effects for an explicit list (user set_value! / compute!)
+__global__ void k_apply_list(View e, const uint32_t* list, uint32_t n, uint32_t req_epoch) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     uint32_t s = list[i];
+    for (uint32_t c = e.nib_off[s]; c < e.nib_off[s + 1]; ++c) e.nib[c] &= ~ALL_F;
+    e.props[s] = P_COMPUTED;
+    for (uint32_t k = e.lis_off[s]; k < e.lis_off[s + 1]; ++k) notify(e, k, req_epoch, 0);
+}
+// independence of a level (A.5): no member may depend on another member. Members are recognisable by
+// front_epoch == lvl_epoch (set when they were pushed); runs BEFORE the rules.
+__global__ void k_check_independent(View e, Segs sg, uint32_t lvl_epoch) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= sg.total) return;
+    uint32_t s = seg_member(sg, e.front, i);
     for (uint32_t k = e.dep_off[s]; k < e.dep_off[s + 1]; ++k)
-        if (mark[e.dep_ids[k]] == tag) atomicOr(e.err_flag, ERR_INDEPENDENCE);
+        if (e.front_epoch[e.dep_ids[k]] == lvl_epoch) atomicOr(e.err_flag, ERR_INDEPENDENCE);
 }
 
 // ---- values ------------------------------------------------------------------------------------------------
@@ -503,16 +460,21 @@ struct DeviceEngine {
     std::map<int32_t, RuleDef> rules;     // by factor type
     std::vector<int32_t> key_ftype;       // key-1 -> factor type
     std::vector<double> fparam;           // per id, NaN = unset
-    uint32_t req_epoch = 0, lvl_epoch = 0, mark_tag = 0;
+    uint32_t req_epoch = 0, lvl_epoch = 0;
     size_t n_uploaded = 0;
 
     // device state
-    DBuf<uint32_t> d_dep_off, d_dep_ids, d_nib_off, d_lis_off, d_lis_ids, d_lis_slot, d_done, d_visit, d_mark;
+    DBuf<uint32_t> d_dep_off, d_dep_ids, d_nib_off, d_lis_off, d_lis_ids, d_lis_slot, d_done, d_visit;
     DBuf<uint64_t> d_nib;
-    DBuf<uint8_t> d_lis_listen, d_props, d_kind, d_rkey, d_front_flag;
+    DBuf<uint8_t> d_lis_listen, d_props, d_kind, d_rkey;
+    DBuf<uint32_t> d_front_epoch, d_key_base;
+    std::vector<uint32_t> key_base;  // per rule key: start of its partition of the frontier buffer
+    bool cur_use_keys = true;
+    uint32_t cur_total = 0, n_links = 0;
+    int bfs_guess = 2;               // BFS steps launched before the host looks (adapts to the graph)
     DBuf<int32_t> d_svar, d_sfac;
     DBuf<unsigned char> d_val, d_fparam, d_tables, d_stage_val;
-    DBuf<uint32_t> d_list_a, d_list_b, d_front, d_tile_hist, d_key_count, d_req_marg, d_link_off, d_link_ids, d_stage_ids;
+    DBuf<uint32_t> d_list_a, d_list_b, d_front, d_key_count, d_req_marg, d_link_ids, d_stage_ids;
     DBuf<uint8_t> d_ready;
     DBuf<int> d_flags;  // [0] err flag, [1] scratch int
     DBuf<uint32_t> d_counters;
@@ -582,7 +544,11 @@ struct DeviceEngine {
         v.sfac = d_sfac.p;
         v.done_epoch = d_done.p;
         v.visit_epoch = d_visit.p;
-        v.front_flag = d_front_flag.p;
+        v.front_epoch = d_front_epoch.p;
+        v.front = d_front.p;
+        v.key_base = d_key_base.p;
+        v.key_cnt = d_key_count.p;
+        v.use_keys = cur_use_keys ? 1 : 0;
         v.err_flag = d_flags.p;
         v.kind_count = d_kind_count.p;
         return v;
@@ -650,7 +616,11 @@ struct DeviceEngine {
             else
                 rkey[s] = (uint8_t)key_no_rule();
         }
+        key_base.assign((size_t)n_keys() + 1, 0);
+        for (size_t s2 = 0; s2 < N; ++s2) ++key_base[(size_t)rkey[s2] + 1];
+        for (int k = 0; k < n_keys(); ++k) key_base[k + 1] += key_base[k];
         int32_t st;
+        if ((st = up(d_key_base, key_base.data(), key_base.size()))) return st;
         if ((st = up(d_rkey, rkey.data(), N))) return st;
         if ((st = up(d_svar, svar.data(), N))) return st;
         if ((st = up(d_sfac, sfac.data(), N))) return st;
@@ -743,19 +713,15 @@ struct DeviceEngine {
             size_t Np = std::max<size_t>(N, 1);
             CXB_CUDA(d_done.reserve(Np));
             CXB_CUDA(d_visit.reserve(Np));
-            CXB_CUDA(d_mark.reserve(Np));
-            CXB_CUDA(d_front_flag.reserve(Np));
+            CXB_CUDA(d_front_epoch.reserve(Np));
             CXB_CUDA(d_list_a.reserve(Np));
             CXB_CUDA(d_list_b.reserve(Np));
             CXB_CUDA(d_front.reserve(Np));
             CXB_CUDA(cudaMemsetAsync(d_done.p, 0, Np * 4, stream));
             CXB_CUDA(cudaMemsetAsync(d_visit.p, 0, Np * 4, stream));
-            CXB_CUDA(cudaMemsetAsync(d_mark.p, 0, Np * 4, stream));
-            CXB_CUDA(cudaMemsetAsync(d_front_flag.p, 0, Np, stream));
-            req_epoch = lvl_epoch = mark_tag = 0;
+            CXB_CUDA(cudaMemsetAsync(d_front_epoch.p, 0, Np * 4, stream));
+            req_epoch = lvl_epoch = 0;
             if ((st = build_keys())) return st;
-            size_t n_tiles = cdiv(Np, MS_TILE);
-            CXB_CUDA(d_tile_hist.reserve(n_tiles * (size_t)n_keys() + 1));
             CXB_CUDA(d_key_count.reserve(512));
             CXB_CUDA(cudaStreamSynchronize(stream));
             n_uploaded = N;
@@ -771,43 +737,6 @@ struct DeviceEngine {
 
     int n_keys() const { return (int)key_ftype.size() + 2; }
     int key_no_rule() const { return (int)key_ftype.size() + 1; }
-
-    // ordered compaction of the flagged signals, grouped by rule key; counts/offsets land in h_counts[0..2*nk)
-    int32_t compact(bool use_keys, uint32_t& total) {
-        uint32_t N = (uint32_t)g.n_sig();
-        int nk = use_keys ? n_keys() : 1;
-        uint32_t n_tiles = cdiv(std::max<uint32_t>(N, 1), MS_TILE);
-        View v = view();
-        CXB_LAUNCH(k_ms_hist, n_tiles, MS_THREADS, nk * sizeof(uint32_t), stream, v.front_flag, v.rkey, N, d_tile_hist.p,
-                   n_tiles, nk, use_keys ? 1 : 0);
-        CXB_LAUNCH(k_ms_scan, 1, 1024, 0, stream, d_tile_hist.p, n_tiles, nk, d_key_count.p);
-        CXB_LAUNCH(k_ms_scatter, n_tiles, MS_THREADS, (size_t)nk * (1 + MS_THREADS / 32) * sizeof(uint32_t), stream,
-                   v.front_flag, v.rkey, N, d_tile_hist.p, n_tiles, nk, use_keys ? 1 : 0, d_front.p);
-        CXB_CUDA(cudaMemcpyAsync(h_counts.p, d_key_count.p, 2 * nk * sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
-        CXB_CUDA(cudaMemcpyAsync(h_flags.p, d_flags.p, sizeof(int), cudaMemcpyDeviceToHost, stream));
-        CXB_CUDA(cudaStreamSynchronize(stream));
-        total = 0;
-        for (int k = 0; k < nk; ++k) total += h_counts.p[k];
-        return CXB_OK;
-    }
-
-    // breadth-first reachability from `seeds` (already in d_list_a, count in n_seed): flags pending signals
-    int32_t bfs(uint32_t n_seed, bool use_done) {
-        ++lvl_epoch;
-        uint32_t n_in = n_seed;
-        uint32_t *in = d_list_a.p, *out = d_list_b.p;
-        View v = view();
-        while (n_in > 0) {
-            CXB_CUDA(cudaMemsetAsync(d_counters.p, 0, sizeof(uint32_t), stream));
-            CXB_LAUNCH(k_bfs, cdiv(n_in, 256), 256, 0, stream, v, in, n_in, out, d_counters.p, lvl_epoch, req_epoch,
-                       use_done ? 1 : 0);
-            CXB_CUDA(cudaMemcpyAsync(h_counts.p + 600, d_counters.p, sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
-            CXB_CUDA(cudaStreamSynchronize(stream));
-            n_in = h_counts.p[600];
-            std::swap(in, out);
-        }
-        return CXB_OK;
-    }
 
     template <class T>
     int32_t launch_rules_t(uint32_t total) {
@@ -894,14 +823,55 @@ struct DeviceEngine {
         (void)total;
         return CXB_OK;
     }
-    int32_t launch_rules(uint32_t total) {
-        return dtype == CXB_F32 ? launch_rules_t<float>(total) : launch_rules_t<double>(total);
+    // ---- frontier plumbing ------------------------------------------------------------------------------------
+    // device counters: [0],[1] = ping-pong BFS list lengths; key cursors live in d_key_count[0..nk)
+    int32_t begin_level(bool use_keys) {
+        ++lvl_epoch;
+        cur_use_keys = use_keys;
+        CXB_CUDA(cudaMemsetAsync(d_key_count.p, 0, (size_t)n_keys() * sizeof(uint32_t), stream));
+        CXB_CUDA(cudaMemsetAsync(d_counters.p, 0, 2 * sizeof(uint32_t), stream));
+        return CXB_OK;
     }
+    unsigned stride_grid(size_t n_max) const { return std::max(1u, std::min(cdiv(std::max<size_t>(n_max, 1), 256), 148u * 16u)); }
 
-    int32_t check_flags() {
+    // breadth-first reachability from the seeds in d_list_a (length in d_counters[0]): pushes pending signals to the
+    // frontier. `bfs_guess` steps are launched back to back; the host only looks at the result afterwards.
+    int32_t bfs(bool use_done) {
+        View v = view();
+        uint32_t N = (uint32_t)g.n_sig();
+        int which = 0;  // list holding the current input
+        for (;;) {
+            for (int it = 0; it < bfs_guess; ++it) {
+                uint32_t* in = which ? d_list_b.p : d_list_a.p;
+                uint32_t* out = which ? d_list_a.p : d_list_b.p;
+                CXB_CUDA(cudaMemsetAsync(d_counters.p + (which ^ 1), 0, sizeof(uint32_t), stream));
+                CXB_LAUNCH(k_bfs, stride_grid(N), 256, 0, stream, v, in, d_counters.p + which, out, d_counters.p + (which ^ 1),
+                           lvl_epoch, req_epoch, use_done ? 1 : 0);
+                which ^= 1;
+            }
+            // one round trip: remaining BFS work + per-key frontier sizes + error flag
+            CXB_CUDA(cudaMemcpyAsync(h_counts.p + 600, d_counters.p + which, sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
+            int32_t st = fetch_frontier();
+            if (st) return st;
+            if (h_counts.p[600] == 0) break;
+            ++bfs_guess;  // deeper than expected: keep going and remember
+        }
+        return CXB_OK;
+    }
+    // per-key frontier sizes (+ error flag) to the host; fills h_counts[0..nk) = counts, [nk..2nk) = segment bases
+    int32_t fetch_frontier() {
+        int nk = n_keys();
+        CXB_CUDA(cudaMemcpyAsync(h_counts.p, d_key_count.p, nk * sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
         CXB_CUDA(cudaMemcpyAsync(h_flags.p, d_flags.p, sizeof(int), cudaMemcpyDeviceToHost, stream));
         CXB_CUDA(cudaStreamSynchronize(stream));
-        int f = h_flags.p[0];
+        cur_total = 0;
+        for (int k = 0; k < nk; ++k) {
+            h_counts.p[nk + k] = cur_use_keys ? key_base[k] : 0;
+            cur_total += h_counts.p[k];
+        }
+        return flags_to_status(h_flags.p[0]);
+    }
+    int32_t flags_to_status(int f) {
         if (!f) return CXB_OK;
         cudaMemsetAsync(d_flags.p, 0, sizeof(int), stream);
         if (f & ERR_RULE_ARG) {
@@ -915,23 +885,52 @@ struct DeviceEngine {
                   "request (order-dependent in the reference)";
         return CXB_ERR_OUT_OF_CONTRACT;
     }
+    int32_t check_flags() {
+        CXB_CUDA(cudaMemcpyAsync(h_flags.p, d_flags.p, sizeof(int), cudaMemcpyDeviceToHost, stream));
+        CXB_CUDA(cudaStreamSynchronize(stream));
+        return flags_to_status(h_flags.p[0]);
+    }
 
-    // evaluate + apply one compacted level (the frontier is in d_front, counts in h_counts)
-    int32_t run_level(uint32_t total, int check_mode, int64_t level_tag) {
+    int32_t launch_rules(uint32_t total) {
+        return dtype == CXB_F32 ? launch_rules_t<float>(total) : launch_rules_t<double>(total);
+    }
+
+    // evaluate + apply the fetched level (segments described by h_counts). Errors raised by the kernels of this
+    // level surface at the next fetch_frontier / check_flags.
+    int32_t run_level(int check_mode, int64_t level_tag) {
+        uint32_t total = cur_total;
         if (!total) return CXB_OK;
         View v = view();
         int32_t st;
-        ++mark_tag;
-        CXB_LAUNCH(k_mark, cdiv(total, 256), 256, 0, stream, d_mark.p, d_front.p, total, mark_tag);
-        CXB_LAUNCH(k_check_independent, cdiv(total, 256), 256, 0, stream, v, d_mark.p, d_front.p, total, mark_tag);
-        if ((st = check_flags())) return st;
+        int nk = n_keys();
+        std::vector<Segs> chunks;
+        Segs sg{};
+        for (int k = 0; k < nk; ++k) {
+            if (!h_counts.p[k]) continue;
+            if (sg.n == 32) {
+                chunks.push_back(sg);
+                sg = Segs{};
+            }
+            sg.base[sg.n] = h_counts.p[nk + k];
+            sg.cnt[sg.n] = h_counts.p[k];
+            sg.total += h_counts.p[k];
+            ++sg.n;
+        }
+        if (sg.n) chunks.push_back(sg);
+        for (auto& c : chunks) CXB_LAUNCH(k_check_independent, cdiv(c.total, 256), 256, 0, stream, v, c, lvl_epoch);
         if ((st = launch_rules(total))) return st;
-        CXB_LAUNCH(k_apply, cdiv(total, 256), 256, 0, stream, v, d_front.p, total, req_epoch, check_mode);
-        if ((st = check_flags())) return st;
+        for (auto& c : chunks) CXB_LAUNCH(k_apply, cdiv(c.total, 256), 256, 0, stream, v, c, req_epoch, check_mode);
         stats.updates += total;
         if (trace_on) {
-            std::vector<uint32_t> ids(total);
-            CXB_CUDA(cudaMemcpyAsync(ids.data(), d_front.p, total * sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
+            std::vector<uint32_t> ids;
+            for (int k = 0; k < nk; ++k) {
+                uint32_t cnt = h_counts.p[k];
+                if (!cnt) continue;
+                size_t o = ids.size();
+                ids.resize(o + cnt);
+                CXB_CUDA(cudaMemcpyAsync(ids.data() + o, d_front.p + h_counts.p[nk + k], cnt * sizeof(uint32_t), cudaMemcpyDeviceToHost,
+                                         stream));
+            }
             CXB_CUDA(cudaStreamSynchronize(stream));
             std::sort(ids.begin(), ids.end());
             for (uint32_t s : ids) {
@@ -949,7 +948,6 @@ struct DeviceEngine {
         if (!same) {
             req_ids.assign(ids, ids + n);
             h_req_marg.resize(n);
-            h_link_off.assign(n + 1, 0);
             h_link_ids.clear();
             // linked signals per variable, in link order (src/model_engine.jl:80-83)
             if (links_dirty) {
@@ -969,30 +967,28 @@ struct DeviceEngine {
                 }
                 h_req_marg[i] = (uint32_t)g.marg_of[v];
                 for (uint32_t k = lnk_off[v]; k < lnk_off[v + 1]; ++k) h_link_ids.push_back(lnk_ids[k]);
-                h_link_off[i + 1] = (uint32_t)h_link_ids.size();
             }
             if ((st = up(d_req_marg, h_req_marg.data(), (size_t)n))) return st;
-            if ((st = up(d_link_off, h_link_off.data(), (size_t)n + 1))) return st;
             if ((st = up(d_link_ids, h_link_ids.data(), h_link_ids.size()))) return st;
             CXB_CUDA(d_ready.reserve(std::max<size_t>(n, 1)));
             CXB_CUDA(cudaStreamSynchronize(stream));
             req_uploaded = true;
         }
         n_req = (uint32_t)n;
+        n_links = (uint32_t)h_link_ids.size();
         ++req_epoch;
         CXB_CUDA(cudaMemsetAsync(d_ready.p, 0, std::max<size_t>(n, 1), stream));
-        if (n) CXB_LAUNCH(k_request, cdiv(n, 256), 256, 0, stream, view(), d_req_marg.p, d_link_off.p, d_link_ids.p, n_req);
+        if (n_req + n_links)
+            CXB_LAUNCH(k_request, cdiv((size_t)n_req + n_links, 256), 256, 0, stream, view(), d_req_marg.p, d_link_ids.p, n_req, n_links);
         return CXB_OK;
     }
 
-    int32_t seeds(uint32_t& n_seed) {
-        CXB_CUDA(cudaMemsetAsync(d_counters.p + 1, 0, sizeof(uint32_t), stream));
-        if (n_req)
-            CXB_LAUNCH(k_seeds, cdiv(n_req, 256), 256, 0, stream, d_req_marg.p, d_ready.p, n_req, d_list_a.p, d_counters.p + 1);
-        CXB_CUDA(cudaMemcpyAsync(h_counts.p + 601, d_counters.p + 1, sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
-        CXB_CUDA(cudaStreamSynchronize(stream));
-        n_seed = h_counts.p[601];
-        return CXB_OK;
+    // one level of the frontier: seeds -> BFS -> per-key segments on the host
+    int32_t find_frontier(bool use_done, bool use_keys) {
+        int32_t st = begin_level(use_keys);
+        if (st) return st;
+        if (n_req) CXB_LAUNCH(k_seeds, cdiv(n_req, 256), 256, 0, stream, d_req_marg.p, d_ready.p, n_req, d_list_a.p, d_counters.p);
+        return bfs(use_done);
     }
 
     int32_t scan(std::vector<int64_t>& out) {
@@ -1000,13 +996,11 @@ struct DeviceEngine {
             err = "scan_inference_request: no request";
             return CXB_ERR_STATE;
         }
-        int32_t st;
-        uint32_t n_seed = 0, total = 0;
-        if ((st = seeds(n_seed))) return st;
-        if ((st = bfs(n_seed, false))) return st;
-        if ((st = compact(false, total))) return st;
-        std::vector<uint32_t> ids(total);
-        if (total) CXB_CUDA(cudaMemcpy(ids.data(), d_front.p, total * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+        int32_t st = find_frontier(false, false);
+        if (st) return st;
+        std::vector<uint32_t> ids(cur_total);
+        if (cur_total) CXB_CUDA(cudaMemcpy(ids.data(), d_front.p, cur_total * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+        std::sort(ids.begin(), ids.end());  // reported in ascending signal id
         out.assign(ids.begin(), ids.end());
         return CXB_OK;
     }
@@ -1020,28 +1014,25 @@ struct DeviceEngine {
         if (st) return st;
         CXB_CUDA(cudaMemsetAsync(d_kind_count.p, 0, 8 * sizeof(unsigned long long), stream));
         int64_t level = 0;
-        for (;;) {
-            uint32_t n_seed = 0, total = 0;
-            if ((st = seeds(n_seed))) return st;
-            if (!n_seed) break;
-            if ((st = bfs(n_seed, true))) return st;
-            if ((st = compact(true, total))) return st;
-            if (!total) break;
-            if ((st = run_level(total, 1, level))) return st;
+        while (n_req) {
+            if ((st = find_frontier(true, true))) return st;
+            if (!cur_total) break;
+            if ((st = run_level(1, level))) return st;
             CXB_LAUNCH(k_ready, cdiv(n_req, 256), 256, 0, stream, view(), d_req_marg.p, d_ready.p, n_req);
             ++stats.levels;
             ++level;
         }
         for (int mode = 0; mode < 2 && n_req; ++mode) {  // final phase: marginals, then linked signals
-            uint32_t total = 0;
-            CXB_LAUNCH(k_final_flags, cdiv(n_req, 256), 256, 0, stream, view(), d_req_marg.p, d_link_off.p, d_link_ids.p, n_req,
-                       mode);
-            if ((st = compact(true, total))) return st;
-            if ((st = run_level(total, 2, mode == 0 ? -1 : -2))) return st;
-            (mode == 0 ? stats.final_marginals : stats.final_linked) = total;
+            uint32_t cnt = mode == 0 ? n_req : n_links;
+            if ((st = begin_level(true))) return st;
+            if (cnt)
+                CXB_LAUNCH(k_final_flags, cdiv(cnt, 256), 256, 0, stream, view(), d_req_marg.p, d_link_ids.p, n_req, n_links, mode, lvl_epoch);
+            if ((st = fetch_frontier())) return st;
+            (mode == 0 ? stats.final_marginals : stats.final_linked) = cur_total;
+            if ((st = run_level(2, mode == 0 ? -1 : -2))) return st;
         }
         CXB_CUDA(cudaMemcpyAsync(h_kind_count.p, d_kind_count.p, 6 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, stream));
-        CXB_CUDA(cudaStreamSynchronize(stream));
+        if ((st = check_flags())) return st;
         for (int k = 0; k < 6; ++k) stats.updates_by_kind[k] = (int64_t)h_kind_count.p[k];
         stats.kernel_launches = (int64_t)(g_kernel_launches - launches0);
         return CXB_OK;
@@ -1112,7 +1103,7 @@ struct DeviceEngine {
         else
             CXB_LAUNCH(k_write_values<double>, grid, 256, 0, stream, (double*)d_val.p, dim, d_stage_ids.p,
                        (const double*)d_stage_val.p, (uint32_t)n);
-        CXB_LAUNCH(k_apply, cdiv(n, 256), 256, 0, stream, view(), d_stage_ids.p, (uint32_t)n, req_epoch, 0);
+        CXB_LAUNCH(k_apply_list, cdiv(n, 256), 256, 0, stream, view(), d_stage_ids.p, (uint32_t)n, req_epoch);
         CXB_CUDA(cudaStreamSynchronize(stream));  // the pinned staging buffer is reused by the next call
         return CXB_OK;
     }
@@ -1194,7 +1185,7 @@ struct DeviceEngine {
         }
         h_counts.p[key] = 1;
         if ((st = launch_rules(1))) return st;
-        CXB_LAUNCH(k_apply, 1, 32, 0, stream, view(), d_front.p, 1u, req_epoch, 0);
+        CXB_LAUNCH(k_apply_list, 1, 32, 0, stream, view(), d_front.p, 1u, req_epoch);
         return check_flags();
     }
 };
@@ -1309,6 +1300,13 @@ int32_t cxb_link_signal(cxb_engine* h, int64_t v, int64_t s) {
     e->g.links.emplace_back(v, (int32_t)s);
     e->req_uploaded = false;
     e->links_dirty = true;
+    return CXB_OK;
+}
+int32_t cxb_link_signals(cxb_engine* h, int64_t n, const int64_t* vs, const int64_t* ss) {
+    for (int64_t i = 0; i < n; ++i) {
+        int32_t st = cxb_link_signal(h, vs[i], ss[i]);
+        if (st) return st;
+    }
     return CXB_OK;
 }
 int64_t cxb_n_signals(cxb_engine* h) { return E(h)->g.n_sig(); }

@@ -147,6 +147,8 @@ int32_t cxb_add_dependency(cxb_engine* h, int64_t signal, int64_t dependency, in
 int32_t cxb_resolve_dependencies(cxb_engine* h, int32_t resolver);
 /* link_signal_to_variable!(variable, signal), src/model_engine.jl:80-83 */
 int32_t cxb_link_signal(cxb_engine* h, int64_t variable_id, int64_t signal);
+/* bulk form of the above (protocol B links every pairwise m2f: 4e7 signals at config-5 size) */
+int32_t cxb_link_signals(cxb_engine* h, int64_t n, const int64_t* variable_ids, const int64_t* signals);
 
 /* ---- introspection (bit-exact parity of the wiring) ---------------------------------------- */
 int64_t cxb_n_signals(cxb_engine* h);

@@ -800,6 +800,13 @@ int32_t cxo_link_signal(void* h, int64_t v, int64_t s) {
     o->linked[v].push_back(s);
     return CXB_OK;
 }
+int32_t cxo_link_signals(void* h, int64_t n, const int64_t* vs, const int64_t* ss) {
+    for (int64_t i = 0; i < n; ++i) {
+        int32_t st = cxo_link_signal(h, vs[i], ss[i]);
+        if (st) return st;
+    }
+    return CXB_OK;
+}
 int64_t cxo_n_signals(void* h) { return (int64_t)O(h)->sig.size(); }
 int64_t cxo_signal_id(void* h, int32_t kind, int64_t v, int64_t f) {
     Oracle* o = O(h);
