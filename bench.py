@@ -237,9 +237,10 @@ def workload_config(args, world):
     if args.workload == "hmm64":
         return {"workload": f"{args.hmm_chains} HMMs per GPU, K=64, M=32, T={args.hmm_steps} (BASELINE configs[2] K=64)",
                 "l2": "inputs exceed L2", "parallelism": f"batch-shard x{world}"}
-    if args.workload == "powerlaw":
+    if args.workload in ("powerlaw", "powerlaw_engine"):
+        eng = "fused CSR sweep engine" if args.workload == "powerlaw" else "generic reactive engine"
         return {"workload": f"Chung-Lu power-law graph, {args.pl_vars} variables, {2 * args.pl_vars} pairwise factors, K=8, "
-                            f"protocol-B sweeps on the generic CSR engine (BASELINE configs[4])", "l2": "inputs exceed L2 at full size",
+                            f"protocol-B sweeps on the {eng} (BASELINE configs[4])", "l2": "inputs exceed L2 at full size",
                 "parallelism": "replicas only"}
     return {"workload": "1-D Gaussian random-walk chain T=1000 through the generic engine (BASELINE configs[0])",
             "l2": "fits L2 (latency config)", "parallelism": "replicas only"}
@@ -413,6 +414,56 @@ def bench_hmm64(args, pkg, rank, world, local):
             "clocks": clocks, "dtype": "f32", "kernel": "k_hmm_pass (fwd + bwd launches)", "scaling": "weak"}
 
 
+def bench_powerlaw(args, pkg, rank, world, local):
+    """BASELINE configs[4] on the fused CSR sweep engine (cxb_pairwise_*): replicas only."""
+    import torch
+    from tests import models  # graph generator only (numpy); no oracle code is executed
+
+    cap = pkg.capi
+    n = args.pl_vars
+    m, K = 2 * n, 8
+    rng = np.random.Generator(np.random.PCG64(1235 + rank))
+    edges = np.asarray(models.chung_lu_edges_fast(n, m), dtype=np.int64)
+    ttype = rng.integers(0, 16, size=m).astype(np.int32)
+    tables = np.exp(rng.standard_normal((16, K, K)))
+    pw = pkg.PairwiseGraph(n, edges[:, 0], edges[:, 1], ttype, tables, dtype=cap.F32, device=local)
+    unary_host = torch.empty((n, K), dtype=torch.float32).pin_memory()
+    e = rng.standard_exponential((n, K), dtype=np.float32)
+    unary_host.numpy()[:] = e / e.sum(axis=-1, keepdims=True)
+    pw.set_unary(unary_host.numpy())
+    pw.reset_messages()
+    upd = [0]
+
+    def step():
+        upd[0] = pw.sweep()
+
+    launches0 = pkg.default_api().kernel_launches()
+    for _ in range(args.warmup):
+        step()
+    pw.sync()
+    sampler = ClockSampler(local)
+    sampler.start()
+    ms = timed(pw.stream, step, args.steps, 0, world, local)
+    launches = pkg.default_api().kernel_launches() - launches0 - 3 * args.warmup
+    kernel_ms = []
+    for _ in range(min(args.steps, 10)):
+        step()
+        kernel_ms.append(pw.last_kernel_ms())
+    marg_host = torch.empty((n, K), dtype=torch.float32).pin_memory()
+
+    def e2e_step():
+        pw.api.pairwise_set_unary(pw.h, unary_host.data_ptr())
+        step()
+        pw.api.pairwise_get_marginals(pw.h, marg_host.data_ptr())
+
+    e2e_steps = max(2, min(args.steps, 5))
+    e2e_ms = timed(pw.stream, e2e_step, e2e_steps, 1, world, local)
+    clocks = sampler.stop()
+    return {"ms": ms, "updates_per_step": upd[0], "kernel_ms": statistics.mean(kernel_ms), "alg_bytes": pw.algorithmic_bytes,
+            "e2e_ms": e2e_ms, "e2e_steps": e2e_steps, "h2d": n * K * 4, "d2h": n * K * 4, "launches": launches,
+            "clocks": clocks, "dtype": "f32", "kernel": "k_pw_small + k_pw_hub (one sweep)", "scaling": "weak"}
+
+
 def bench_engine_graph(args, pkg, rank, world, local, which):
     """Generic CSR engine: chain1k (one update_marginals!) or powerlaw (protocol-B sweeps)."""
     import ctypes
@@ -464,7 +515,7 @@ def bench_engine_graph(args, pkg, rank, world, local, which):
         n = args.pl_vars
         m, K = 2 * n, 8
         rng = np.random.Generator(np.random.PCG64(1235))
-        edges = np.asarray(models.chung_lu_edges(n, m), dtype=np.int64)
+        edges = np.asarray(models.chung_lu_edges_fast(n, m), dtype=np.int64)
         ttype = rng.integers(0, 16, size=m)
         tables = np.exp(rng.standard_normal((16, K, K)))
         n_ids = 2 * n + m
@@ -533,14 +584,14 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="gauss_chains", choices=["gauss_chains", "potts_grid", "hmm64", "powerlaw", "chain1k"])
+    ap.add_argument("--workload", default="gauss_chains", choices=["gauss_chains", "potts_grid", "hmm64", "powerlaw", "powerlaw_engine", "chain1k"])
     ap.add_argument("--dtype", default="f32", choices=["f32", "f64"])
     ap.add_argument("--chains", type=int, default=65536)
     ap.add_argument("--chain-steps", type=int, default=1024)
     ap.add_argument("--grid", type=int, default=8192)
     ap.add_argument("--hmm-chains", type=int, default=1024)
     ap.add_argument("--hmm-steps", type=int, default=100000)
-    ap.add_argument("--pl-vars", type=int, default=1000000)
+    ap.add_argument("--pl-vars", type=int, default=10000000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
@@ -551,7 +602,7 @@ def main():
     pkg = entry.load_package()
     rank, world, local = dist_setup(args.gpus)
     fn = {"gauss_chains": bench_gauss_chains, "potts_grid": bench_potts_grid, "hmm64": bench_hmm64,
-          "powerlaw": lambda *a: bench_engine_graph(*a, "powerlaw"), "chain1k": lambda *a: bench_engine_graph(*a, "chain1k")}[args.workload]
+          "powerlaw": bench_powerlaw, "powerlaw_engine": lambda *a: bench_engine_graph(*a, "powerlaw"), "chain1k": lambda *a: bench_engine_graph(*a, "chain1k")}[args.workload]
     r = fn(args, pkg, rank, world, local)
     peak, peak_src, _ = measured_peaks()
     ms_per_step = r["ms"] / args.steps

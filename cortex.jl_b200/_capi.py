@@ -111,6 +111,20 @@ _STRUCTURED = {
     "hmm_stream": (vp, [vp]),
     "hmm_last_kernel_ms": (i32, [vp, C.POINTER(C.c_float)]),
     "hmm_sync": (i32, [vp]),
+    "pairwise_create": (i32, [i32, i32, i64, i64, i32, i32, C.POINTER(vp)]),
+    "pairwise_destroy": (None, [vp]),
+    "pairwise_last_error": (C.c_char_p, [vp]),
+    "pairwise_set_graph": (i32, [vp, i64p, i64p, i32p]),
+    "pairwise_set_tables": (i32, [vp, f64p]),
+    "pairwise_set_unary": (i32, [vp, vp]),
+    "pairwise_reset_messages": (i32, [vp]),
+    "pairwise_sweep": (i32, [vp, i64p]),
+    "pairwise_get_marginals": (i32, [vp, vp]),
+    "pairwise_get_messages": (i32, [vp, i32, vp]),
+    "pairwise_algorithmic_bytes": (i64, [vp]),
+    "pairwise_stream": (vp, [vp]),
+    "pairwise_last_kernel_ms": (i32, [vp, C.POINTER(C.c_float)]),
+    "pairwise_sync": (i32, [vp]),
 }
 
 # oracle-only extras (bound when present)

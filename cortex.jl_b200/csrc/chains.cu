@@ -171,6 +171,106 @@ k_chains_fwd_bwd(const T* __restrict__ y, const T* __restrict__ qv, const T* __r
     }
 }
 
+// Variant without the explicit double buffer: the loads of a time tile are issued together at the top of the tile and
+// the recursion then consumes them (latency is hidden by the other resident warps only). Kept because it measured
+// FASTER for fp32 on B200 (0.739 ms vs 0.79 ms, profiles/r01_sweep_chains.txt): CXB_CHAINS_PIPE=0 selects it.
+template <class T, int TILE, int BLOCK>
+__global__ void __launch_bounds__(BLOCK)
+k_chains_fwd_bwd_np(const T* __restrict__ y, const T* __restrict__ qv, const T* __restrict__ rv,
+                    typename Vec2<T>::type* __restrict__ msg, long long B, long long Tn) {
+    using V = typename Vec2<T>::type;
+    const long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    const T q = qv[b], r = rv[b];
+    const T inv_r = T(1) / r;
+    const size_t plane = (size_t)Tn * (size_t)B;
+    V* __restrict__ m_obs = msg;
+    V* __restrict__ m_pred = msg + plane;
+    V* __restrict__ m_fwd = msg + 2 * plane;
+    V* __restrict__ m_bwd = msg + 3 * plane;
+    V* __restrict__ m_back = msg + 4 * plane;
+    V* __restrict__ m_marg = msg + 5 * plane;
+    T L = 0, h = 0;
+    for (long long t0 = 0; t0 < Tn; t0 += TILE) {
+        T yy[TILE];
+#pragma unroll
+        for (int k = 0; k < TILE; ++k) {
+            long long t = t0 + k;
+            yy[k] = t < Tn ? __ldcs(&y[(size_t)t * B + b]) : T(0);
+        }
+#pragma unroll
+        for (int k = 0; k < TILE; ++k) {
+            long long t = t0 + k;
+            if (t < Tn) {
+                size_t idx = (size_t)t * B + b;
+                T oL = inv_r, oh = yy[k] * inv_r;
+                T pL = 0, ph = 0;
+                if (t > 0) {
+                    T den = T(1) + q * L;
+                    pL = L / den;
+                    ph = h / den;
+                    L = oL + pL;
+                    h = oh + ph;
+                } else {
+                    L = oL;
+                    h = oh;
+                }
+                __stcs(&m_obs[idx], mk2<T>(oL, oh));
+                __stcs(&m_pred[idx], mk2<T>(pL, ph));
+                __stcs(&m_fwd[idx], mk2<T>(L, h));
+            }
+        }
+    }
+    L = 0;
+    h = 0;
+    for (long long t1 = Tn - 1; t1 >= 0; t1 -= TILE) {
+        T yy[TILE];
+        V pr[TILE];
+#pragma unroll
+        for (int k = 0; k < TILE; ++k) {
+            long long t = t1 - k;
+            if (t >= 0) {
+                yy[k] = __ldcs(&y[(size_t)t * B + b]);
+                pr[k] = __ldcs(&m_pred[(size_t)t * B + b]);
+            } else {
+                yy[k] = T(0);
+                pr[k] = mk2<T>(T(0), T(0));
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < TILE; ++k) {
+            long long t = t1 - k;
+            if (t >= 0) {
+                size_t idx = (size_t)t * B + b;
+                T oL = inv_r, oh = yy[k] * inv_r;
+                T bL = 0, bh = 0;
+                if (t < Tn - 1) {
+                    T den = T(1) + q * L;
+                    bL = L / den;
+                    bh = h / den;
+                    L = oL + bL;
+                    h = oh + bh;
+                } else {
+                    L = oL;
+                    h = oh;
+                }
+                T gL = oL, gh = oh;
+                if (t > 0) {
+                    gL = gL + pr[k].x;
+                    gh = gh + pr[k].y;
+                }
+                if (t < Tn - 1) {
+                    gL = gL + bL;
+                    gh = gh + bh;
+                }
+                __stcs(&m_bwd[idx], mk2<T>(bL, bh));
+                __stcs(&m_back[idx], mk2<T>(L, h));
+                __stcs(&m_marg[idx], mk2<T>(gL, gh));
+            }
+        }
+    }
+}
+
 struct Chains {
     int device = 0, dtype = CXB_F32;
     long long B = 0, T = 0;
@@ -236,13 +336,25 @@ struct Chains {
     }
     // tile = time steps in flight per thread (double buffered), block = chains per CTA. Defaults are the measured
     // best on B200 (profiles/); CXB_CHAINS_TILE / CXB_CHAINS_BLOCK override them for tuning runs.
+    template <class T, int TILE, int BLOCK>
+    int32_t launch_variant_np() {
+        CXB_LAUNCH((k_chains_fwd_bwd_np<T, TILE, BLOCK>), cdiv((size_t)B, BLOCK), BLOCK, 0, stream, (const T*)y.p, (const T*)q.p,
+                   (const T*)r.p, (typename Vec2<T>::type*)msg.p, B, this->T);
+        return CXB_OK;
+    }
     template <class T>
     int32_t dispatch() {
-        int tile = sizeof(T) == 4 ? CH_TILE : CH_TILE / 2, block = CH_BLOCK;
+        // measured best on B200 (profiles/r01_sweep_chains.txt): fp32 -> tile 8, 128-thread CTAs, no explicit double
+        // buffer; fp64 -> tile 2, 64-thread CTAs, double buffered
+        int tile = sizeof(T) == 4 ? 8 : 2, block = sizeof(T) == 4 ? 128 : 64, pipe = sizeof(T) == 4 ? 0 : 1;
         if (const char* e = getenv("CXB_CHAINS_TILE")) tile = atoi(e);
         if (const char* e = getenv("CXB_CHAINS_BLOCK")) block = atoi(e);
-#define V_(TL, BL) if (tile == TL && block == BL) return launch_variant<T, TL, BL>();
+        if (const char* e = getenv("CXB_CHAINS_PIPE")) pipe = atoi(e);
+#define V_(TL, BL) if (pipe && tile == TL && block == BL) return launch_variant<T, TL, BL>();
         V_(2, 64) V_(4, 64) V_(8, 64) V_(16, 64) V_(2, 128) V_(4, 128) V_(8, 128) V_(16, 128) V_(4, 256) V_(8, 256) V_(4, 32) V_(8, 32)
+#undef V_
+#define V_(TL, BL) if (!pipe && tile == TL && block == BL) return launch_variant_np<T, TL, BL>();
+        V_(4, 64) V_(8, 64) V_(16, 64) V_(4, 128) V_(8, 128) V_(16, 128) V_(8, 256) V_(16, 256)
 #undef V_
         err = "unsupported CXB_CHAINS_TILE / CXB_CHAINS_BLOCK combination";
         return CXB_ERR_BAD_ARG;

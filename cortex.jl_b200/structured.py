@@ -201,3 +201,53 @@ class HmmBatch(_Handle):
         out = np.empty((t1 - t0, self.B, self.K), dtype=self.np_dtype)
         self.check(self.api.hmm_get_forward(self.h, t0, t1, out.ctypes.data))
         return out
+
+
+class PairwiseGraph(_Handle):
+    """Arbitrary pairwise categorical graph (one unary leaf factor per variable + pairwise table factors), synchronous
+    sweeps = protocol B. `factors` = (u, v, table) with u < v in ascending factor id."""
+    _prefix = "pairwise"
+
+    def __init__(self, n_variables, fac_u, fac_v, fac_table, tables, dtype=capi.F32, device=0, api=None):
+        self.api = api or capi.default_api()
+        tables = np.ascontiguousarray(tables, dtype=np.float64)
+        self.n, self.m, self.K, self.n_tables, self.dtype = int(n_variables), len(fac_u), tables.shape[-1], tables.shape[0], dtype
+        self.np_dtype = _np_dtype(dtype)
+        h = C.c_void_p()
+        st = self.api.pairwise_create(device, dtype, self.n, self.m, self.K, self.n_tables, C.byref(h))
+        if st != capi.OK or not h:
+            raise CortexError(st, "cxb_pairwise_create failed (CUDA device required; there is no CPU fallback)")
+        self.h = h
+        fu = np.ascontiguousarray(fac_u, dtype=np.int64)
+        fv = np.ascontiguousarray(fac_v, dtype=np.int64)
+        ft = np.ascontiguousarray(fac_table, dtype=np.int32)
+        self.check(self.api.pairwise_set_graph(self.h, fu.ctypes.data_as(capi.i64p), fv.ctypes.data_as(capi.i64p),
+                                               ft.ctypes.data_as(capi.i32p)))
+        self.check(self.api.pairwise_set_tables(self.h, tables.ctypes.data_as(capi.f64p)))
+
+    def set_unary(self, unary):
+        u = np.ascontiguousarray(unary, dtype=self.np_dtype)
+        assert u.shape == (self.n, self.K)
+        self.check(self.api.pairwise_set_unary(self.h, u.ctypes.data))
+
+    def reset_messages(self):
+        self.check(self.api.pairwise_reset_messages(self.h))
+
+    def sweep(self) -> int:
+        n = C.c_int64()
+        self.check(self.api.pairwise_sweep(self.h, C.byref(n)))
+        return int(n.value)
+
+    def get_marginals(self):
+        out = np.empty((self.n, self.K), dtype=self.np_dtype)
+        self.check(self.api.pairwise_get_marginals(self.h, out.ctypes.data))
+        return out
+
+    def get_messages(self, which: int):
+        out = np.empty((self.m, 2, self.K), dtype=self.np_dtype)
+        self.check(self.api.pairwise_get_messages(self.h, which, out.ctypes.data))
+        return out
+
+    @property
+    def algorithmic_bytes(self) -> int:
+        return int(self.api.pairwise_algorithmic_bytes(self.h))

@@ -280,6 +280,31 @@ void* cxb_hmm_stream(cxb_hmm* m);
 int32_t cxb_hmm_last_kernel_ms(cxb_hmm* m, float* ms_out);
 int32_t cxb_hmm_sync(cxb_hmm* m);
 
+/* ---- arbitrary pairwise categorical graph, loopy BP by synchronous sweeps (BASELINE config 5) -------------------
+ * variables 0..n-1, one unary (leaf) factor per variable, pairwise factor f = (u_f < v_f) with table
+ * psi_{t_f}[x_u][x_v]; K states. Same graph, wiring and protocol B sweep as cxb_graph_build + DEFAULT_BP +
+ * linked m2f on tests/models.py:make_powerlaw_model; a sweep stands for 4m + n + (#ProductOfMessages) updates. */
+typedef struct cxb_pairwise cxb_pairwise;
+int32_t cxb_pairwise_create(int32_t device, int32_t dtype, int64_t n_variables, int64_t n_factors, int32_t n_states,
+                            int32_t n_tables, cxb_pairwise** out);
+void cxb_pairwise_destroy(cxb_pairwise* g);
+const char* cxb_pairwise_last_error(cxb_pairwise* g);
+/* factor endpoints (u < v) and table index per factor, in ascending factor id */
+int32_t cxb_pairwise_set_graph(cxb_pairwise* g, const int64_t* fac_u, const int64_t* fac_v, const int32_t* fac_table);
+/* tables [n_tables][K][K] float64, indexed [x_lower][x_higher] (CXB_RULE_CAT_TABLE convention) */
+int32_t cxb_pairwise_set_tables(cxb_pairwise* g, const double* tables);
+/* set_value!(m2v(v, unary_v), u_v): host [n][K] engine dtype */
+int32_t cxb_pairwise_set_unary(cxb_pairwise* g, const void* unary_host);
+int32_t cxb_pairwise_reset_messages(cxb_pairwise* g);
+int32_t cxb_pairwise_sweep(cxb_pairwise* g, int64_t* n_updates_out);
+int32_t cxb_pairwise_get_marginals(cxb_pairwise* g, void* out_host);
+/* which = 0: m2v, 1: m2f; out[(2f + side)][K], side 0 = endpoint u, 1 = endpoint v; engine dtype */
+int32_t cxb_pairwise_get_messages(cxb_pairwise* g, int32_t which, void* out_host);
+int64_t cxb_pairwise_algorithmic_bytes(cxb_pairwise* g);
+void* cxb_pairwise_stream(cxb_pairwise* g);
+int32_t cxb_pairwise_last_kernel_ms(cxb_pairwise* g, float* ms_out);
+int32_t cxb_pairwise_sync(cxb_pairwise* g);
+
 #ifdef __cplusplus
 }
 #endif

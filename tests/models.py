@@ -251,3 +251,23 @@ def level_trace(engine):
     for l, s in zip(lv[:n].tolist(), sg[:n].tolist()):
         out.setdefault(l, []).append(s)
     return {l: sorted(v) for l, v in out.items()}
+
+
+def chung_lu_edges_fast(n, m, alpha=2.5, seed=1234):
+    """Vectorised Chung-Lu generator for benchmark-sized graphs (same weights as chung_lu_edges): m distinct pairs
+    (u < v), sorted, as an (m, 2) int64 array."""
+    rng = np.random.Generator(np.random.PCG64(seed))
+    w = (np.arange(n) + 10.0) ** (-1.0 / (alpha - 1.0))
+    cdf = np.cumsum(w)
+    cdf /= cdf[-1]
+    have = np.zeros(0, dtype=np.int64)
+    while have.size < m:
+        need = int((m - have.size) * 1.15) + 1024
+        a = np.searchsorted(cdf, rng.random(need))
+        b = np.searchsorted(cdf, rng.random(need))
+        keep = a != b
+        lo, hi = np.minimum(a[keep], b[keep]), np.maximum(a[keep], b[keep])
+        have = np.unique(np.concatenate([have, lo.astype(np.int64) * n + hi]))
+    if have.size > m:
+        have = np.sort(rng.choice(have, size=m, replace=False))
+    return np.stack([have // n, have % n], axis=1)

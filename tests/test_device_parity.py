@@ -285,3 +285,69 @@ def test_hmm_kernel_vs_oracle(oracle_api, dtype, K):
         assert_close(got_m[:, b, :], want_m, dtype)
         want_f = C.get_values([C.get_connection_message_to_factor(e, z[t], tr[t]) for t in range(T - 1)])
         assert_close(got_f[:-1, b, :], want_f, dtype)
+
+
+def _pairwise_vs_oracle(oracle_api, dtype, n, edges, K, sweeps, seed=7):
+    rng = np.random.Generator(np.random.PCG64(seed))
+    n_tables = 5
+    tables = np.exp(rng.standard_normal((n_tables, K, K)))
+    ttype = rng.integers(0, n_tables, size=len(edges))
+    unary = rng.dirichlet(np.ones(K), size=n)
+    pw = C.PairwiseGraph(n, [e[0] for e in edges], [e[1] for e in edges], ttype, tables, dtype=dtype)
+    pw.set_unary(unary)
+    pw.reset_messages()
+    # the same model as an explicit graph on the oracle (tests/models.py conventions: unary factors first)
+    g = C.BipartiteFactorGraph()
+    vs = [g.add_variable(C.Variable(name="v", index=(i,))) for i in range(n)]
+    un = [g.add_factor(C.Factor(functional_form="unary")) for _ in range(n)]
+    for i in range(n):
+        g.add_edge(vs[i], un[i], C.Connection(label="out"))
+    fac = []
+    for (u, v), t in zip(edges, ttype):
+        f = g.add_factor(C.Factor(functional_form=f"pair{int(t)}"))
+        g.add_edge(vs[u], f, C.Connection(label="a"))
+        g.add_edge(vs[v], f, C.Connection(label="b"))
+        fac.append(f)
+    tables_used = tables.astype(pw.np_dtype).astype(np.float64)
+    proc = C.RuleProcessor({f"pair{t}": (cap.RULE_CAT_TABLE, tables_used[t].ravel()) for t in range(n_tables)},
+                           family=cap.FAMILY_CATEGORICAL, value_dim=K)
+    e = C.InferenceEngine(model_engine=g, dependency_resolver=C.DefaultDependencyResolver(), inference_request_processor=proc,
+                          api=oracle_api)
+    models.protocol_b_link(e, vs)
+    models.protocol_b_init(e, vs, K)
+    usig = [C.get_connection_message_to_variable(e, vs[i], un[i]) for i in range(n)]
+    unary_used = unary.astype(pw.np_dtype).astype(np.float64)
+    for _ in range(sweeps):
+        st = models.protocol_b_sweep(e, vs, usig, unary_used, schedule="lvl")
+        assert pw.sweep() == st.updates  # same number of reference signal updates (incl. ProductOfMessages nodes)
+    want = C.get_values([C.get_variable_marginal(C.get_variable(e, v)) for v in vs])
+    assert_close(pw.get_marginals(), want, dtype)
+    got_v, got_f = pw.get_messages(0), pw.get_messages(1)
+    want_v = np.zeros((len(edges), 2, K))
+    want_f = np.zeros((len(edges), 2, K))
+    for k, ((u, v), f) in enumerate(zip(edges, fac)):
+        for side, x in enumerate((u, v)):
+            want_v[k, side] = C.get_value(C.get_connection_message_to_variable(e, vs[x], f))
+            want_f[k, side] = C.get_value(C.get_connection_message_to_factor(e, vs[x], f))
+    assert_close(got_v, want_v, dtype)
+    assert_close(got_f, want_f, dtype)
+
+
+@pytest.mark.parametrize("dtype", [cap.F64, cap.F32])
+@pytest.mark.parametrize("K", [8, 4])
+def test_pairwise_kernel_powerlaw_vs_oracle(oracle_api, dtype, K):
+    n, m = 120, 330
+    edges = models.chung_lu_edges(n, m, seed=11)
+    deg = np.bincount(np.asarray(edges).ravel(), minlength=n)
+    assert deg.max() > 4 and deg.min() == 0 or deg.max() > 4  # small path + hub path both exercised
+    _pairwise_vs_oracle(oracle_api, dtype, n, edges, K, sweeps=3)
+
+
+def test_pairwise_kernel_big_hub_and_isolated_variables(oracle_api):
+    """A star with 1,100 leaves (block-per-hub path), a medium hub, a chain and two isolated variables."""
+    n = 1150
+    edges = [(0, i) for i in range(1, 1101)]                 # big hub: degree 1100 >= 1024
+    edges += [(1101, i) for i in range(1102, 1122)]          # medium hub: degree 20
+    edges += [(i, i + 1) for i in range(1122, 1147)]         # chain
+    edges = sorted(edges)
+    _pairwise_vs_oracle(oracle_api, cap.F32, n, edges, 8, sweeps=2)
