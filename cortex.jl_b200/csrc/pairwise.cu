@@ -74,9 +74,12 @@ __device__ __forceinline__ T slot_m2v(const PwView& g, const T* sh_tables, uint3
     return x / gsum<T, K>(x, gm);
 }
 
-// ---- variables with <= PW_SMALL_MAX pairwise factors: one group of K lanes per variable, all in registers ---------
-template <class T, int K>
-__global__ void __launch_bounds__(256) k_pw_small(PwView g, const uint32_t* __restrict__ vars, uint32_t n_vars) {
+// ---- variables with <= DMAX pairwise factors: one group of K lanes per variable, all messages in registers ---------
+// DMAX = 4  : the reference's n <= 5 path (src/dependencies.jl:60-88): products left to right over "all others";
+// DMAX > 4  : the reference uses the segment tree; here exclusive products by a renormalised prefix/suffix scan.
+// Groups name only their own lanes in the shuffle masks, so each group runs exactly its own degree.
+template <class T, int K, int DMAX>
+__global__ void __launch_bounds__(256) k_pw_reg(PwView g, const uint32_t* __restrict__ vars, uint32_t n_vars) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     T* sh_tables = reinterpret_cast<T*>(smem_raw);
     for (int x = threadIdx.x; x < g.n_tables * 2 * K * K; x += blockDim.x) sh_tables[x] = ((const T*)g.tables)[x];
@@ -84,40 +87,75 @@ __global__ void __launch_bounds__(256) k_pw_small(PwView g, const uint32_t* __re
     const uint32_t gid = (blockIdx.x * blockDim.x + threadIdx.x) / K;
     const int a = threadIdx.x % K;
     const unsigned gm = group_mask<K>();
-    const bool valid = gid < n_vars;
-    const uint32_t v = vars[valid ? gid : n_vars - 1];
+    if (gid >= n_vars) return;  // whole groups leave together
+    const uint32_t v = vars[gid];
     const uint32_t p0 = g.adj_off[v], d = g.adj_off[v + 1] - p0;
     const T un = __ldg((const T*)g.unary + (size_t)v * K + a);
-    T x[PW_SMALL_MAX];
+    // gather: indices first, then the messages (independent loads in flight together)
+    uint32_t op[DMAX];
+    int sel[DMAX];
+    T x[DMAX];
 #pragma unroll
-    for (int k = 0; k < PW_SMALL_MAX; ++k) {
-        const bool ex = (uint32_t)k < d;
-        T m = slot_m2v<T, K>(g, sh_tables, p0 + k, a, gm, ex);
-        x[k] = ex ? m : T(1);
-        if (valid && ex) __stcs((T*)g.m2v + (size_t)(p0 + k) * K + a, m);
-    }
-    // marginal = unary * x0 * x1 * ... (ascending factor id, left to right), normalised
-    {
+    for (int k = 0; k < DMAX; ++k)
+        if ((uint32_t)k < d) {
+            op[k] = __ldg(g.opp + p0 + k);
+            sel[k] = __ldg(g.tsel + p0 + k);
+        }
+#pragma unroll
+    for (int k = 0; k < DMAX; ++k)
+        if ((uint32_t)k < d) x[k] = __ldg((const T*)g.m2f_cur + (size_t)op[k] * K + a);
+#pragma unroll
+    for (int k = 0; k < DMAX; ++k)
+        if ((uint32_t)k < d) {
+            const T* tb = sh_tables + ((size_t)(sel[k] >> 1) * 2 + ((sel[k] & 1) ? 0 : 1)) * K * K;
+            T m = contract<T, K>(tb, x[k], a, gm);
+            m = m / gsum<T, K>(m, gm);
+            x[k] = m;
+            __stcs((T*)g.m2v + (size_t)(p0 + k) * K + a, m);
+        }
+    if (DMAX <= PW_SMALL_MAX) {
         T acc = un;
 #pragma unroll
-        for (int k = 0; k < PW_SMALL_MAX; ++k)
+        for (int k = 0; k < DMAX; ++k)
             if ((uint32_t)k < d) acc = acc * x[k];
-        T tot = gsum<T, K>(acc, gm);
-        if (valid) __stcs((T*)g.marg + (size_t)v * K + a, acc / tot);
-    }
+        __stcs((T*)g.marg + (size_t)v * K + a, acc / gsum<T, K>(acc, gm));
 #pragma unroll
-    for (int k = 0; k < PW_SMALL_MAX; ++k) {
-        T acc = un;
+        for (int k = 0; k < DMAX; ++k)
+            if ((uint32_t)k < d) {
+                T o = un;
 #pragma unroll
-        for (int j = 0; j < PW_SMALL_MAX; ++j)
-            if (j != k && (uint32_t)j < d) acc = acc * x[j];
-        T tot = gsum<T, K>(acc, gm);
-        if (valid && (uint32_t)k < d) __stcs((T*)g.m2f_nxt + (size_t)(p0 + k) * K + a, acc / tot);
+                for (int j = 0; j < DMAX; ++j)
+                    if (j != k && (uint32_t)j < d) o = o * x[j];
+                __stcs((T*)g.m2f_nxt + (size_t)(p0 + k) * K + a, o / gsum<T, K>(o, gm));
+            }
+    } else {
+        T pre[DMAX];  // pre[k] = normalise(unary * x_0 * ... * x_{k-1})
+        pre[0] = un;
+#pragma unroll
+        for (int k = 1; k < DMAX; ++k)
+            if ((uint32_t)k < d) {
+                T t = pre[k - 1] * x[k - 1];
+                pre[k] = t / gsum<T, K>(t, gm);
+            }
+        T suf = T(1);
+#pragma unroll
+        for (int k = DMAX - 1; k >= 0; --k)
+            if ((uint32_t)k < d) {
+                if ((uint32_t)k == d - 1) {
+                    T mg = pre[k] * x[k];
+                    __stcs((T*)g.marg + (size_t)v * K + a, mg / gsum<T, K>(mg, gm));
+                }
+                T o = pre[k] * suf;
+                __stcs((T*)g.m2f_nxt + (size_t)(p0 + k) * K + a, o / gsum<T, K>(o, gm));
+                suf = suf * x[k];
+                suf = suf / gsum<T, K>(suf, gm);
+            }
     }
 }
 
 // ---- hubs: one CTA per variable, NG groups of K lanes ----------------------------------------------------------------
-// pass 1: every group walks its contiguous segment of the adjacency: m2v per slot (stored) and the segment product;
+// pass 1: every group walks its contiguous segment of the adjacency, 4 slots at a time (4 gathers in flight): m2v per
+//         slot (stored) and the segment product;
 // pass 2: exclusive prefix (unary * earlier segments) / suffix (later segments) per group through shared memory;
 // pass 3: forward over the segment stores the running exclusive prefix in m2f_nxt (scratch), backward combines it with
 //         the running suffix into the final m2f. Products are renormalised at every step (as every BP message is).
@@ -130,6 +168,7 @@ __global__ void __launch_bounds__(NG * K) k_pw_hub(PwView g, const uint32_t* __r
     __syncthreads();
     const int grp = threadIdx.x / K, a = threadIdx.x % K;
     const unsigned gm = group_mask<K>();
+    constexpr int U = 4;
     for (uint32_t hv = blockIdx.x; hv < n_vars; hv += gridDim.x) {
         const uint32_t v = vars[hv];
         const uint32_t p0 = g.adj_off[v], d = g.adj_off[v + 1] - p0;
@@ -138,11 +177,29 @@ __global__ void __launch_bounds__(NG * K) k_pw_hub(PwView g, const uint32_t* __r
         const T un = __ldg((const T*)g.unary + (size_t)v * K + a);
         // pass 1
         T prod = T(1);
-        for (uint32_t k = lo; k < hi; ++k) {
-            T m = slot_m2v<T, K>(g, sh_tables, p0 + k, a, gm);
-            ((T*)g.m2v)[(size_t)(p0 + k) * K + a] = m;
-            prod = prod * m;
-            prod = prod / gsum<T, K>(prod, gm);
+        for (uint32_t k0 = lo; k0 < hi; k0 += U) {
+            uint32_t op[U];
+            int sel[U];
+            T in[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u)
+                if (k0 + u < hi) {
+                    op[u] = __ldg(g.opp + p0 + k0 + u);
+                    sel[u] = __ldg(g.tsel + p0 + k0 + u);
+                }
+#pragma unroll
+            for (int u = 0; u < U; ++u)
+                if (k0 + u < hi) in[u] = __ldg((const T*)g.m2f_cur + (size_t)op[u] * K + a);
+#pragma unroll
+            for (int u = 0; u < U; ++u)
+                if (k0 + u < hi) {
+                    const T* tb = sh_tables + ((size_t)(sel[u] >> 1) * 2 + ((sel[u] & 1) ? 0 : 1)) * K * K;
+                    T m = contract<T, K>(tb, in[u], a, gm);
+                    m = m / gsum<T, K>(m, gm);
+                    ((T*)g.m2v)[(size_t)(p0 + k0 + u) * K + a] = m;
+                    prod = prod * m;
+                    prod = prod / gsum<T, K>(prod, gm);
+                }
         }
         sh_part[grp * K + a] = prod;
         __syncthreads();
@@ -198,10 +255,10 @@ struct Pairwise {
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     std::string err;
-    DBuf<uint32_t> adj_off, opp, small_vars, mid_vars, big_vars, slot_of_edge;
+    DBuf<uint32_t> adj_off, opp, small_vars, r8_vars, r16_vars, mid_vars, big_vars, slot_of_edge;
     DBuf<uint8_t> tsel;
     DBuf<unsigned char> tables, unary, m2f[2], m2v, marg, scratch;
-    uint32_t n_small = 0, n_mid = 0, n_big = 0;
+    uint32_t n_small = 0, n_r8 = 0, n_r16 = 0, n_mid = 0, n_big = 0;
     long long n_products = 0;
     bool have_graph = false, have_tables = false, have_unary = false, have_msgs = false, ran = false;
     size_t esz() const { return dtype == CXB_F32 ? 4 : 8; }
@@ -251,18 +308,30 @@ struct Pairwise {
             sel[pu] = (uint8_t)(ft[f] * 2 + 0);  // u is the lower endpoint
             sel[pv] = (uint8_t)(ft[f] * 2 + 1);
         }
-        std::vector<uint32_t> sm, md, bg;
+        // degree bins: <= 4 register path (reference n<=5 order), 5..8 and 9..16 register prefix/suffix,
+        // 17..255 one warp-sized CTA per variable, >= 256 one 256-thread CTA per variable (largest first)
+        std::vector<uint32_t> sm, r8, r16, md, bg;
         n_products = 0;
         for (long long v = 0; v < n; ++v) {
             uint32_t d = off[v + 1] - off[v];
-            if (d <= PW_SMALL_MAX)
+            if (d <= PW_SMALL_MAX) {
                 sm.push_back((uint32_t)v);
-            else {
-                (d < 1024 ? md : bg).push_back((uint32_t)v);
-                n_products += (long long)d - 1;  // (d+1) factors incl. the unary -> d-1 ProductOfMessages nodes in the reference
+                continue;
             }
+            n_products += (long long)d - 1;  // (d+1) factors incl. the unary -> d-1 ProductOfMessages nodes in the reference
+            if (d <= 8)
+                r8.push_back((uint32_t)v);
+            else if (d <= 16)
+                r16.push_back((uint32_t)v);
+            else
+                (d < 256 ? md : bg).push_back((uint32_t)v);
         }
+        auto by_degree_desc = [&](uint32_t x, uint32_t y) { return off[x + 1] - off[x] > off[y + 1] - off[y]; };
+        std::stable_sort(md.begin(), md.end(), by_degree_desc);
+        std::stable_sort(bg.begin(), bg.end(), by_degree_desc);
         n_small = (uint32_t)sm.size();
+        n_r8 = (uint32_t)r8.size();
+        n_r16 = (uint32_t)r16.size();
         n_mid = (uint32_t)md.size();
         n_big = (uint32_t)bg.size();
         auto up = [&](auto& dbuf, const auto& vec) -> cudaError_t {
@@ -276,6 +345,8 @@ struct Pairwise {
         CXB_CUDA(up(tsel, sel));
         CXB_CUDA(up(slot_of_edge, slot));
         CXB_CUDA(up(small_vars, sm));
+        CXB_CUDA(up(r8_vars, r8));
+        CXB_CUDA(up(r16_vars, r16));
         CXB_CUDA(up(mid_vars, md));
         CXB_CUDA(up(big_vars, bg));
         size_t pb = std::max<size_t>(P, 1) * K * esz(), nb = (size_t)n * K * esz();
@@ -347,8 +418,16 @@ struct Pairwise {
             if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         };
         if (n_small) {
-            attr(k_pw_small<T, KK>, tb);
-            CXB_LAUNCH((k_pw_small<T, KK>), cdiv((size_t)n_small * KK, 256), 256, tb, stream, g, small_vars.p, n_small);
+            attr(k_pw_reg<T, KK, PW_SMALL_MAX>, tb);
+            CXB_LAUNCH((k_pw_reg<T, KK, PW_SMALL_MAX>), cdiv((size_t)n_small * KK, 256), 256, tb, stream, g, small_vars.p, n_small);
+        }
+        if (n_r8) {
+            attr(k_pw_reg<T, KK, 8>, tb);
+            CXB_LAUNCH((k_pw_reg<T, KK, 8>), cdiv((size_t)n_r8 * KK, 256), 256, tb, stream, g, r8_vars.p, n_r8);
+        }
+        if (n_r16) {
+            attr(k_pw_reg<T, KK, 16>, tb);
+            CXB_LAUNCH((k_pw_reg<T, KK, 16>), cdiv((size_t)n_r16 * KK, 256), 256, tb, stream, g, r16_vars.p, n_r16);
         }
         if (n_mid) {  // one warp-sized CTA per medium hub
             constexpr int NG = 32 / KK > 0 ? 32 / KK : 1;
