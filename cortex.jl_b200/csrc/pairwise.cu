@@ -21,6 +21,7 @@
 // HBM-bound: (d+1)*K*4 B read + (2d+1)*K*4 B written per variable of degree d.
 #include <algorithm>
 #include <cmath>
+#include <type_traits>
 
 #include "common.cuh"
 
@@ -53,25 +54,71 @@ __device__ __forceinline__ T gsum(T v, unsigned gm) {
     for (int o = K / 2; o > 0; o >>= 1) v += __shfl_xor_sync(gm, v, o, K);
     return v;
 }
-// out[a] = sum_b tb[b][a] * in[b] where lane a holds in[a]; tb points at the [K][K] block to use (shared memory)
+// ---- building blocks (K lanes per variable, lane a owns state a) -------------------------------------------------------
+// The incoming message is loaded WHOLE by every lane of the group (K*sizeof(T) bytes, the same sector(s) for the
+// K lanes: one DRAM/L2 access, no shuffles), the lane's table row [a][0..K) is read with 128-bit shared loads.
 template <class T, int K>
-__device__ __forceinline__ T contract(const T* tb, T in, int a, unsigned gm) {
-    T acc = T(0);
+__device__ __forceinline__ void load_msg(const T* p, T (&m)[K]) {
+    constexpr int V = 16 / sizeof(T);
+    using VT = typename std::conditional<sizeof(T) == 4, float4, double2>::type;
+    if (K % V == 0) {
 #pragma unroll
-    for (int b = 0; b < K; ++b) acc = fma(tb[b * K + a], __shfl_sync(gm, in, b, K), acc);
-    return acc;
+        for (int i = 0; i < K / V; ++i) {
+            VT q = __ldg(reinterpret_cast<const VT*>(p) + i);
+            const T* s = reinterpret_cast<const T*>(&q);
+#pragma unroll
+            for (int j = 0; j < V; ++j) m[i * V + j] = s[j];
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < K; ++i) m[i] = __ldg(p + i);
+    }
 }
-// m2v(v, f) for slot p: gather the neighbour's m2f, contract with the table in the right orientation, normalise.
-// `live` = false (padding iteration of a group): no memory is touched, the result is discarded by the caller.
+// out[a] = sum_b psi(b -> a) in[b]; row = the lane's table row: row[b] = weight of in[b]
 template <class T, int K>
-__device__ __forceinline__ T slot_m2v(const PwView& g, const T* sh_tables, uint32_t p, int a, unsigned gm, bool live = true) {
-    const T in = live ? __ldg((const T*)g.m2f_cur + (size_t)g.opp[p] * K + a) : T(1);
-    const int sel = live ? g.tsel[p] : 0;
-    // this variable is the higher endpoint -> out[x_hi] = sum_{x_lo} psi[x_lo][x_hi] in[x_lo] -> block 0 ([b][a] = psi[b][a])
-    // this variable is the lower endpoint  -> out[x_lo] = sum_{x_hi} psi[x_lo][x_hi] in[x_hi] -> block 1 (transpose)
-    const T* tb = sh_tables + ((size_t)(sel >> 1) * 2 + ((sel & 1) ? 0 : 1)) * K * K;
-    T x = contract<T, K>(tb, in, a, gm);
-    return x / gsum<T, K>(x, gm);
+__device__ __forceinline__ T contract_row(const T* row, const T (&in)[K]) {
+    constexpr int V = 16 / sizeof(T);
+    using VT = typename std::conditional<sizeof(T) == 4, float4, double2>::type;
+    T acc0 = T(0), acc1 = T(0);
+    if (K % V == 0) {
+#pragma unroll
+        for (int i = 0; i < K / V; ++i) {
+            VT q = *(reinterpret_cast<const VT*>(row) + i);
+            const T* s = reinterpret_cast<const T*>(&q);
+#pragma unroll
+            for (int j = 0; j < V; ++j) {
+                if ((j & 1) == 0)
+                    acc0 = fma(s[j], in[i * V + j], acc0);
+                else
+                    acc1 = fma(s[j], in[i * V + j], acc1);
+            }
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < K; ++i) acc0 = fma(row[i], in[i], acc0);
+    }
+    return acc0 + acc1;
+}
+template <class T>
+__device__ __forceinline__ T recip(T x);
+template <>
+__device__ __forceinline__ float recip<float>(float x) {
+    return __frcp_rn(x);
+}
+template <>
+__device__ __forceinline__ double recip<double>(double x) {
+    return 1.0 / x;
+}
+// normalise the K-vector spread over the group's lanes to sum 1 (one reciprocal, one multiply per lane)
+template <class T, int K>
+__device__ __forceinline__ T gnorm(T v, unsigned gm) {
+    return v * recip<T>(gsum<T, K>(v, gm));
+}
+// the lane's table row for slot selector `sel`: this variable higher endpoint -> out[a=x_hi] needs psi[b=x_lo][a] =
+// transpose block row a; lower endpoint -> out[a=x_lo] needs psi[a][b] = plain block row a
+template <class T, int K>
+__device__ __forceinline__ const T* table_row(const T* sh_tables, int sel, int a) {
+    return sh_tables + (((size_t)(sel >> 1) * 2 + ((sel & 1) ? 1 : 0)) * K + a) * K;
 }
 
 // ---- variables with <= DMAX pairwise factors: one group of K lanes per variable, all messages in registers ---------
@@ -91,7 +138,6 @@ __global__ void __launch_bounds__(256) k_pw_reg(PwView g, const uint32_t* __rest
     const uint32_t v = vars[gid];
     const uint32_t p0 = g.adj_off[v], d = g.adj_off[v + 1] - p0;
     const T un = __ldg((const T*)g.unary + (size_t)v * K + a);
-    // gather: indices first, then the messages (independent loads in flight together)
     uint32_t op[DMAX];
     int sel[DMAX];
     T x[DMAX];
@@ -103,13 +149,10 @@ __global__ void __launch_bounds__(256) k_pw_reg(PwView g, const uint32_t* __rest
         }
 #pragma unroll
     for (int k = 0; k < DMAX; ++k)
-        if ((uint32_t)k < d) x[k] = __ldg((const T*)g.m2f_cur + (size_t)op[k] * K + a);
-#pragma unroll
-    for (int k = 0; k < DMAX; ++k)
         if ((uint32_t)k < d) {
-            const T* tb = sh_tables + ((size_t)(sel[k] >> 1) * 2 + ((sel[k] & 1) ? 0 : 1)) * K * K;
-            T m = contract<T, K>(tb, x[k], a, gm);
-            m = m / gsum<T, K>(m, gm);
+            T in[K];
+            load_msg<T, K>((const T*)g.m2f_cur + (size_t)op[k] * K, in);
+            T m = gnorm<T, K>(contract_row<T, K>(table_row<T, K>(sh_tables, sel[k], a), in), gm);
             x[k] = m;
             __stcs((T*)g.m2v + (size_t)(p0 + k) * K + a, m);
         }
@@ -118,7 +161,7 @@ __global__ void __launch_bounds__(256) k_pw_reg(PwView g, const uint32_t* __rest
 #pragma unroll
         for (int k = 0; k < DMAX; ++k)
             if ((uint32_t)k < d) acc = acc * x[k];
-        __stcs((T*)g.marg + (size_t)v * K + a, acc / gsum<T, K>(acc, gm));
+        __stcs((T*)g.marg + (size_t)v * K + a, gnorm<T, K>(acc, gm));
 #pragma unroll
         for (int k = 0; k < DMAX; ++k)
             if ((uint32_t)k < d) {
@@ -126,34 +169,86 @@ __global__ void __launch_bounds__(256) k_pw_reg(PwView g, const uint32_t* __rest
 #pragma unroll
                 for (int j = 0; j < DMAX; ++j)
                     if (j != k && (uint32_t)j < d) o = o * x[j];
-                __stcs((T*)g.m2f_nxt + (size_t)(p0 + k) * K + a, o / gsum<T, K>(o, gm));
+                __stcs((T*)g.m2f_nxt + (size_t)(p0 + k) * K + a, gnorm<T, K>(o, gm));
             }
     } else {
         T pre[DMAX];  // pre[k] = normalise(unary * x_0 * ... * x_{k-1})
         pre[0] = un;
 #pragma unroll
         for (int k = 1; k < DMAX; ++k)
-            if ((uint32_t)k < d) {
-                T t = pre[k - 1] * x[k - 1];
-                pre[k] = t / gsum<T, K>(t, gm);
-            }
+            if ((uint32_t)k < d) pre[k] = gnorm<T, K>(pre[k - 1] * x[k - 1], gm);
         T suf = T(1);
 #pragma unroll
         for (int k = DMAX - 1; k >= 0; --k)
             if ((uint32_t)k < d) {
-                if ((uint32_t)k == d - 1) {
-                    T mg = pre[k] * x[k];
-                    __stcs((T*)g.marg + (size_t)v * K + a, mg / gsum<T, K>(mg, gm));
-                }
-                T o = pre[k] * suf;
-                __stcs((T*)g.m2f_nxt + (size_t)(p0 + k) * K + a, o / gsum<T, K>(o, gm));
-                suf = suf * x[k];
-                suf = suf / gsum<T, K>(suf, gm);
+                if ((uint32_t)k == d - 1) __stcs((T*)g.marg + (size_t)v * K + a, gnorm<T, K>(pre[k] * x[k], gm));
+                __stcs((T*)g.m2f_nxt + (size_t)(p0 + k) * K + a, gnorm<T, K>(pre[k] * suf, gm));
+                suf = gnorm<T, K>(suf * x[k], gm);
             }
     }
 }
 
-// ---- hubs: one CTA per variable, NG groups of K lanes ----------------------------------------------------------------
+// ---- medium hubs (17 .. 16*NG pairwise factors): one CTA per variable, NG groups, each group keeps its segment of
+// <= 16 messages in registers (same code shape as k_pw_reg) and the segments are combined through shared memory.
+template <class T, int K, int NG>
+__global__ void __launch_bounds__(NG * K) k_pw_hub16(PwView g, const uint32_t* __restrict__ vars, uint32_t n_vars) {
+    constexpr int S = 16;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    T* sh_tables = reinterpret_cast<T*>(smem_raw);
+    T* sh_part = sh_tables + (size_t)g.n_tables * 2 * K * K;  // [NG][K] segment products
+    for (int x = threadIdx.x; x < g.n_tables * 2 * K * K; x += blockDim.x) sh_tables[x] = ((const T*)g.tables)[x];
+    __syncthreads();
+    const int grp = threadIdx.x / K, a = threadIdx.x % K;
+    const unsigned gm = group_mask<K>();
+    for (uint32_t hv = blockIdx.x; hv < n_vars; hv += gridDim.x) {
+        const uint32_t v = vars[hv];
+        const uint32_t p0 = g.adj_off[v], d = g.adj_off[v + 1] - p0;
+        const uint32_t seg = (d + NG - 1) / NG;  // <= S by construction of the bin
+        const uint32_t lo = min(d, grp * seg), n_loc = min(d, lo + seg) - lo;
+        const uint32_t pb = p0 + lo;
+        const T un = __ldg((const T*)g.unary + (size_t)v * K + a);
+        uint32_t op[S];
+        int sel[S];
+        T x[S];
+#pragma unroll
+        for (int k = 0; k < S; ++k)
+            if ((uint32_t)k < n_loc) {
+                op[k] = __ldg(g.opp + pb + k);
+                sel[k] = __ldg(g.tsel + pb + k);
+            }
+        T prod = T(1);
+#pragma unroll
+        for (int k = 0; k < S; ++k)
+            if ((uint32_t)k < n_loc) {
+                T in[K];
+                load_msg<T, K>((const T*)g.m2f_cur + (size_t)op[k] * K, in);
+                T m = gnorm<T, K>(contract_row<T, K>(table_row<T, K>(sh_tables, sel[k], a), in), gm);
+                x[k] = m;
+                __stcs((T*)g.m2v + (size_t)(pb + k) * K + a, m);
+                prod = gnorm<T, K>(prod * m, gm);
+            }
+        sh_part[grp * K + a] = prod;
+        __syncthreads();
+        T pre0 = un, suf = T(1);
+        for (int h = 0; h < grp; ++h) pre0 = gnorm<T, K>(pre0 * sh_part[h * K + a], gm);
+        for (int h = NG - 1; h > grp; --h) suf = gnorm<T, K>(suf * sh_part[h * K + a], gm);
+        if (grp == NG - 1) __stcs((T*)g.marg + (size_t)v * K + a, gnorm<T, K>(pre0 * prod, gm));
+        T pre[S];
+        pre[0] = pre0;
+#pragma unroll
+        for (int k = 1; k < S; ++k)
+            if ((uint32_t)k < n_loc) pre[k] = gnorm<T, K>(pre[k - 1] * x[k - 1], gm);
+#pragma unroll
+        for (int k = S - 1; k >= 0; --k)
+            if ((uint32_t)k < n_loc) {
+                __stcs((T*)g.m2f_nxt + (size_t)(pb + k) * K + a, gnorm<T, K>(pre[k] * suf, gm));
+                suf = gnorm<T, K>(suf * x[k], gm);
+            }
+        __syncthreads();  // sh_part is reused by the next hub
+    }
+}
+
+// ---- big hubs: one CTA per variable, NG groups of K lanes, segments of any length ----------------------------------------
 // pass 1: every group walks its contiguous segment of the adjacency, 4 slots at a time (4 gathers in flight): m2v per
 //         slot (stored) and the segment product;
 // pass 2: exclusive prefix (unary * earlier segments) / suffix (later segments) per group through shared memory;
@@ -180,7 +275,6 @@ __global__ void __launch_bounds__(NG * K) k_pw_hub(PwView g, const uint32_t* __r
         for (uint32_t k0 = lo; k0 < hi; k0 += U) {
             uint32_t op[U];
             int sel[U];
-            T in[U];
 #pragma unroll
             for (int u = 0; u < U; ++u)
                 if (k0 + u < hi) {
@@ -189,49 +283,33 @@ __global__ void __launch_bounds__(NG * K) k_pw_hub(PwView g, const uint32_t* __r
                 }
 #pragma unroll
             for (int u = 0; u < U; ++u)
-                if (k0 + u < hi) in[u] = __ldg((const T*)g.m2f_cur + (size_t)op[u] * K + a);
-#pragma unroll
-            for (int u = 0; u < U; ++u)
                 if (k0 + u < hi) {
-                    const T* tb = sh_tables + ((size_t)(sel[u] >> 1) * 2 + ((sel[u] & 1) ? 0 : 1)) * K * K;
-                    T m = contract<T, K>(tb, in[u], a, gm);
-                    m = m / gsum<T, K>(m, gm);
+                    T in[K];
+                    load_msg<T, K>((const T*)g.m2f_cur + (size_t)op[u] * K, in);
+                    T m = gnorm<T, K>(contract_row<T, K>(table_row<T, K>(sh_tables, sel[u], a), in), gm);
                     ((T*)g.m2v)[(size_t)(p0 + k0 + u) * K + a] = m;
-                    prod = prod * m;
-                    prod = prod / gsum<T, K>(prod, gm);
+                    prod = gnorm<T, K>(prod * m, gm);
                 }
         }
         sh_part[grp * K + a] = prod;
         __syncthreads();
         // pass 2
         T pre = un, suf = T(1);
-        for (int h = 0; h < grp; ++h) {
-            pre = pre * sh_part[h * K + a];
-            pre = pre / gsum<T, K>(pre, gm);
-        }
-        for (int h = NG - 1; h > grp; --h) {
-            suf = suf * sh_part[h * K + a];
-            suf = suf / gsum<T, K>(suf, gm);
-        }
-        if (grp == NG - 1) {  // marginal = (unary * everything before the last segment) * last segment
-            T acc = pre * prod;
-            ((T*)g.marg)[(size_t)v * K + a] = acc / gsum<T, K>(acc, gm);
-        }
+        for (int h = 0; h < grp; ++h) pre = gnorm<T, K>(pre * sh_part[h * K + a], gm);
+        for (int h = NG - 1; h > grp; --h) suf = gnorm<T, K>(suf * sh_part[h * K + a], gm);
+        if (grp == NG - 1) ((T*)g.marg)[(size_t)v * K + a] = gnorm<T, K>(pre * prod, gm);
         // pass 3 forward: exclusive prefixes into the scratch
         T run = pre;
         for (uint32_t k = lo; k < hi; ++k) {
             ((T*)g.m2f_nxt)[(size_t)(p0 + k) * K + a] = run;
-            run = run * ((const T*)g.m2v)[(size_t)(p0 + k) * K + a];
-            run = run / gsum<T, K>(run, gm);
+            run = gnorm<T, K>(run * ((const T*)g.m2v)[(size_t)(p0 + k) * K + a], gm);
         }
         // pass 3 backward: m2f = prefix * suffix
         run = suf;
         for (uint32_t k = hi; k > lo; --k) {
             const size_t o = (size_t)(p0 + k - 1) * K + a;
-            T acc = ((const T*)g.m2f_nxt)[o] * run;
-            ((T*)g.m2f_nxt)[o] = acc / gsum<T, K>(acc, gm);
-            run = run * ((const T*)g.m2v)[o];
-            run = run / gsum<T, K>(run, gm);
+            ((T*)g.m2f_nxt)[o] = gnorm<T, K>(((const T*)g.m2f_nxt)[o] * run, gm);
+            run = gnorm<T, K>(run * ((const T*)g.m2v)[o], gm);
         }
         __syncthreads();  // sh_part is reused by the next hub
     }
@@ -255,10 +333,10 @@ struct Pairwise {
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     std::string err;
-    DBuf<uint32_t> adj_off, opp, small_vars, r8_vars, r16_vars, mid_vars, big_vars, slot_of_edge;
+    DBuf<uint32_t> adj_off, opp, small_vars, r8_vars, r16_vars, mid_vars, mid2_vars, big_vars, slot_of_edge;
     DBuf<uint8_t> tsel;
     DBuf<unsigned char> tables, unary, m2f[2], m2v, marg, scratch;
-    uint32_t n_small = 0, n_r8 = 0, n_r16 = 0, n_mid = 0, n_big = 0;
+    uint32_t n_small = 0, n_r8 = 0, n_r16 = 0, n_mid = 0, n_mid2 = 0, n_big = 0;
     long long n_products = 0;
     bool have_graph = false, have_tables = false, have_unary = false, have_msgs = false, ran = false;
     size_t esz() const { return dtype == CXB_F32 ? 4 : 8; }
@@ -309,8 +387,9 @@ struct Pairwise {
             sel[pv] = (uint8_t)(ft[f] * 2 + 1);
         }
         // degree bins: <= 4 register path (reference n<=5 order), 5..8 and 9..16 register prefix/suffix,
-        // 17..255 one warp-sized CTA per variable, >= 256 one 256-thread CTA per variable (largest first)
-        std::vector<uint32_t> sm, r8, r16, md, bg;
+        // <= 16*(32/K) one warp-sized CTA, <= 16*(256/K) one 256-thread CTA (segments in registers), larger: streamed
+        std::vector<uint32_t> sm, r8, r16, md, md2, bg;
+        const uint32_t mid_max = 16u * (uint32_t)std::max(1, 32 / K), mid2_max = 16u * (uint32_t)(256 / K);
         n_products = 0;
         for (long long v = 0; v < n; ++v) {
             uint32_t d = off[v + 1] - off[v];
@@ -324,15 +403,17 @@ struct Pairwise {
             else if (d <= 16)
                 r16.push_back((uint32_t)v);
             else
-                (d < 256 ? md : bg).push_back((uint32_t)v);
+                (d <= mid_max ? md : d <= mid2_max ? md2 : bg).push_back((uint32_t)v);
         }
         auto by_degree_desc = [&](uint32_t x, uint32_t y) { return off[x + 1] - off[x] > off[y + 1] - off[y]; };
         std::stable_sort(md.begin(), md.end(), by_degree_desc);
+        std::stable_sort(md2.begin(), md2.end(), by_degree_desc);
         std::stable_sort(bg.begin(), bg.end(), by_degree_desc);
         n_small = (uint32_t)sm.size();
         n_r8 = (uint32_t)r8.size();
         n_r16 = (uint32_t)r16.size();
         n_mid = (uint32_t)md.size();
+        n_mid2 = (uint32_t)md2.size();
         n_big = (uint32_t)bg.size();
         auto up = [&](auto& dbuf, const auto& vec) -> cudaError_t {
             cudaError_t e = dbuf.reserve(vec.size());
@@ -348,6 +429,7 @@ struct Pairwise {
         CXB_CUDA(up(r8_vars, r8));
         CXB_CUDA(up(r16_vars, r16));
         CXB_CUDA(up(mid_vars, md));
+        CXB_CUDA(up(mid2_vars, md2));
         CXB_CUDA(up(big_vars, bg));
         size_t pb = std::max<size_t>(P, 1) * K * esz(), nb = (size_t)n * K * esz();
         CXB_CUDA(m2f[0].reserve(pb));
@@ -429,13 +511,19 @@ struct Pairwise {
             attr(k_pw_reg<T, KK, 16>, tb);
             CXB_LAUNCH((k_pw_reg<T, KK, 16>), cdiv((size_t)n_r16 * KK, 256), 256, tb, stream, g, r16_vars.p, n_r16);
         }
-        if (n_mid) {  // one warp-sized CTA per medium hub
+        if (n_mid) {  // 17 .. 16*NG1 factors: one warp-sized CTA per variable, segments in registers
             constexpr int NG = 32 / KK > 0 ? 32 / KK : 1;
             size_t smem = tb + (size_t)NG * KK * sizeof(T);
-            attr(k_pw_hub<T, KK, NG>, smem);
-            CXB_LAUNCH((k_pw_hub<T, KK, NG>), std::min<uint32_t>(n_mid, 148u * 64u), NG * KK, smem, stream, g, mid_vars.p, n_mid);
+            attr(k_pw_hub16<T, KK, NG>, smem);
+            CXB_LAUNCH((k_pw_hub16<T, KK, NG>), std::min<uint32_t>(n_mid, 148u * 64u), NG * KK, smem, stream, g, mid_vars.p, n_mid);
         }
-        if (n_big) {  // 256-thread CTA per big hub
+        if (n_mid2) {  // up to 16*(256/K) factors: 256-thread CTA, segments in registers
+            constexpr int NG = 256 / KK;
+            size_t smem = tb + (size_t)NG * KK * sizeof(T);
+            attr(k_pw_hub16<T, KK, NG>, smem);
+            CXB_LAUNCH((k_pw_hub16<T, KK, NG>), std::min<uint32_t>(n_mid2, 148u * 8u), NG * KK, smem, stream, g, mid2_vars.p, n_mid2);
+        }
+        if (n_big) {  // anything larger: 256-thread CTA, segments streamed
             constexpr int NG = 256 / KK;
             size_t smem = tb + (size_t)NG * KK * sizeof(T);
             attr(k_pw_hub<T, KK, NG>, smem);
