@@ -16,6 +16,7 @@
 // is a ~40-cycle dependent chain per step, hidden by ~14 resident warps per SM). Stores are
 // streaming (st.global.cs): nothing written is re-read before ~2 GB of other traffic.
 // HBM-bound: 64 B (fp32) / 128 B (fp64) of algorithmic traffic per variable.
+#include <algorithm>
 #include <cmath>
 
 #include "common.cuh"
@@ -49,10 +50,10 @@ constexpr int CH_BLOCK = 64;  // 65,536 chains -> 1,024 CTAs = 6.9 per SM: <1.2%
 template <class T, int TILE, int BLOCK>
 __global__ void __launch_bounds__(BLOCK, 512 / BLOCK)
 k_chains_fwd_bwd(const T* __restrict__ y, const T* __restrict__ qv, const T* __restrict__ rv,
-                 typename Vec2<T>::type* __restrict__ msg, long long B, long long Tn) {
+                 typename Vec2<T>::type* __restrict__ msg, long long B, long long Tn, long long b0, long long b1) {
     using V = typename Vec2<T>::type;
-    const long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (b >= B) return;
+    const long long b = b0 + (long long)blockIdx.x * blockDim.x + threadIdx.x;  // chains [b0, b1) of the batch
+    if (b >= b1) return;
     const T q = qv[b], r = rv[b];
     const T inv_r = T(1) / r;
     const size_t plane = (size_t)Tn * (size_t)B;
@@ -177,10 +178,10 @@ k_chains_fwd_bwd(const T* __restrict__ y, const T* __restrict__ qv, const T* __r
 template <class T, int TILE, int BLOCK>
 __global__ void __launch_bounds__(BLOCK)
 k_chains_fwd_bwd_np(const T* __restrict__ y, const T* __restrict__ qv, const T* __restrict__ rv,
-                    typename Vec2<T>::type* __restrict__ msg, long long B, long long Tn) {
+                    typename Vec2<T>::type* __restrict__ msg, long long B, long long Tn, long long b0, long long b1) {
     using V = typename Vec2<T>::type;
-    const long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (b >= B) return;
+    const long long b = b0 + (long long)blockIdx.x * blockDim.x + threadIdx.x;  // chains [b0, b1) of the batch
+    if (b >= b1) return;
     const T q = qv[b], r = rv[b];
     const T inv_r = T(1) / r;
     const size_t plane = (size_t)Tn * (size_t)B;
@@ -275,6 +276,10 @@ struct Chains {
     int device = 0, dtype = CXB_F32;
     long long B = 0, T = 0;
     cudaStream_t stream = nullptr;
+    cudaStream_t s_in = nullptr, s_out = nullptr;  // copy streams of the chunk-pipelined host entry point
+    static constexpr int MAX_CHUNKS = 32;
+    cudaEvent_t ev_in[MAX_CHUNKS] = {}, ev_k[MAX_CHUNKS] = {}, ev_done = nullptr;
+    long long rb0 = 0, rb1 = 0;  // chain range of the next launch
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     std::string err;
     DBuf<unsigned char> y, q, r, msg;
@@ -284,6 +289,13 @@ struct Chains {
     ~Chains() {
         if (ev0) cudaEventDestroy(ev0);
         if (ev1) cudaEventDestroy(ev1);
+        for (int i = 0; i < MAX_CHUNKS; ++i) {
+            if (ev_in[i]) cudaEventDestroy(ev_in[i]);
+            if (ev_k[i]) cudaEventDestroy(ev_k[i]);
+        }
+        if (ev_done) cudaEventDestroy(ev_done);
+        if (s_in) cudaStreamDestroy(s_in);
+        if (s_out) cudaStreamDestroy(s_out);
         if (stream) cudaStreamDestroy(stream);
     }
     int32_t init() {
@@ -300,6 +312,15 @@ struct Chains {
         CXB_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
         CXB_CUDA(cudaEventCreate(&ev0));
         CXB_CUDA(cudaEventCreate(&ev1));
+        CXB_CUDA(cudaStreamCreateWithFlags(&s_in, cudaStreamNonBlocking));
+        CXB_CUDA(cudaStreamCreateWithFlags(&s_out, cudaStreamNonBlocking));
+        for (int i = 0; i < MAX_CHUNKS; ++i) {
+            CXB_CUDA(cudaEventCreateWithFlags(&ev_in[i], cudaEventDisableTiming));
+            CXB_CUDA(cudaEventCreateWithFlags(&ev_k[i], cudaEventDisableTiming));
+        }
+        CXB_CUDA(cudaEventCreateWithFlags(&ev_done, cudaEventDisableTiming));
+        rb0 = 0;
+        rb1 = B;
         CXB_CUDA(y.reserve((size_t)T * B * esz()));
         CXB_CUDA(q.reserve((size_t)B * esz()));
         CXB_CUDA(r.reserve((size_t)B * esz()));
@@ -330,16 +351,16 @@ struct Chains {
     }
     template <class T, int TILE, int BLOCK>
     int32_t launch_variant() {
-        CXB_LAUNCH((k_chains_fwd_bwd<T, TILE, BLOCK>), cdiv((size_t)B, BLOCK), BLOCK, 0, stream, (const T*)y.p, (const T*)q.p,
-                   (const T*)r.p, (typename Vec2<T>::type*)msg.p, B, this->T);
+        CXB_LAUNCH((k_chains_fwd_bwd<T, TILE, BLOCK>), cdiv((size_t)(rb1 - rb0), BLOCK), BLOCK, 0, stream, (const T*)y.p,
+                   (const T*)q.p, (const T*)r.p, (typename Vec2<T>::type*)msg.p, B, this->T, rb0, rb1);
         return CXB_OK;
     }
     // tile = time steps in flight per thread (double buffered), block = chains per CTA. Defaults are the measured
     // best on B200 (profiles/); CXB_CHAINS_TILE / CXB_CHAINS_BLOCK override them for tuning runs.
     template <class T, int TILE, int BLOCK>
     int32_t launch_variant_np() {
-        CXB_LAUNCH((k_chains_fwd_bwd_np<T, TILE, BLOCK>), cdiv((size_t)B, BLOCK), BLOCK, 0, stream, (const T*)y.p, (const T*)q.p,
-                   (const T*)r.p, (typename Vec2<T>::type*)msg.p, B, this->T);
+        CXB_LAUNCH((k_chains_fwd_bwd_np<T, TILE, BLOCK>), cdiv((size_t)(rb1 - rb0), BLOCK), BLOCK, 0, stream, (const T*)y.p,
+                   (const T*)q.p, (const T*)r.p, (typename Vec2<T>::type*)msg.p, B, this->T, rb0, rb1);
         return CXB_OK;
     }
     template <class T>
@@ -366,12 +387,60 @@ struct Chains {
             return CXB_ERR_STATE;
         }
         CXB_CUDA(cudaSetDevice(device));
+        rb0 = 0;
+        rb1 = B;
         CXB_CUDA(cudaEventRecord(ev0, stream));
         int32_t st = dtype == CXB_F32 ? dispatch<float>() : dispatch<double>();
         if (st) return st;
         CXB_CUDA(cudaEventRecord(ev1, stream));
         CXB_CUDA(cudaGetLastError());
         ran = true;
+        return CXB_OK;
+    }
+    // Host entry point: observations from (pinned) host memory, marginals back to host memory. The batch is cut into
+    // chunks of chains; chunk c's observations travel host->device on s_in while chunk c-1 is computed on `stream` and
+    // chunk c-2's marginals travel device->host on s_out, so that the PCIe link is busy in both directions at once.
+    int32_t infer_host(const void* y_host, void* marg_out) {
+        if (!have_noise) {
+            err = "set the noise variances first";
+            return CXB_ERR_STATE;
+        }
+        CXB_CUDA(cudaSetDevice(device));
+        int n_chunks = 8;
+        if (const char* e = getenv("CXB_CHAINS_HOST_CHUNKS")) n_chunks = atoi(e);
+        n_chunks = std::max(1, std::min<int>(n_chunks, MAX_CHUNKS));
+        long long per = ((B + n_chunks - 1) / n_chunks + 63) / 64 * 64;  // whole CTAs per chunk
+        n_chunks = (int)((B + per - 1) / per);
+        const size_t e1 = esz(), e2 = 2 * esz();
+        unsigned char* marg_dev = msg.p + 5 * plane_bytes();
+        // the previous call may still be using the buffers on the other streams
+        CXB_CUDA(cudaEventRecord(ev_done, stream));
+        CXB_CUDA(cudaStreamWaitEvent(s_in, ev_done, 0));
+        CXB_CUDA(cudaEventRecord(ev0, stream));
+        for (int c = 0; c < n_chunks; ++c) {
+            const long long c0 = c * per, c1 = std::min(B, c0 + per);
+            CXB_CUDA(cudaMemcpy2DAsync(y.p + c0 * e1, (size_t)B * e1, (const unsigned char*)y_host + c0 * e1, (size_t)B * e1,
+                                       (size_t)(c1 - c0) * e1, (size_t)T, cudaMemcpyHostToDevice, s_in));
+            CXB_CUDA(cudaEventRecord(ev_in[c], s_in));
+            CXB_CUDA(cudaStreamWaitEvent(stream, ev_in[c], 0));
+            rb0 = c0;
+            rb1 = c1;
+            int32_t st = dtype == CXB_F32 ? dispatch<float>() : dispatch<double>();
+            if (st) return st;
+            CXB_CUDA(cudaEventRecord(ev_k[c], stream));
+            CXB_CUDA(cudaStreamWaitEvent(s_out, ev_k[c], 0));
+            CXB_CUDA(cudaMemcpy2DAsync((unsigned char*)marg_out + c0 * e2, (size_t)B * e2, marg_dev + c0 * e2, (size_t)B * e2,
+                                       (size_t)(c1 - c0) * e2, (size_t)T, cudaMemcpyDeviceToHost, s_out));
+        }
+        rb0 = 0;
+        rb1 = B;
+        CXB_CUDA(cudaEventRecord(ev1, stream));
+        CXB_CUDA(cudaEventRecord(ev_done, s_out));
+        CXB_CUDA(cudaStreamWaitEvent(stream, ev_done, 0));  // later work on `stream` is ordered after the copies
+        CXB_CUDA(cudaGetLastError());
+        have_obs = true;
+        ran = true;
+        CXB_CUDA(cudaStreamSynchronize(stream));
         return CXB_OK;
     }
 };
@@ -466,13 +535,8 @@ void* cxb_chains_device_ptr(cxb_chains* c, int32_t which) {
 }
 int32_t cxb_chains_infer_host(cxb_chains* c, const void* y_host, void* marg_out, int64_t* n_updates_out) {
     Chains* h = CH(c);
-    CH_CUDA(c, cudaSetDevice(h->device));
-    CH_CUDA(c, cudaMemcpyAsync(h->y.p, y_host, (size_t)h->T * h->B * h->esz(), cudaMemcpyHostToDevice, h->stream));
-    h->have_obs = true;
-    int32_t st = h->launch();
+    int32_t st = h->infer_host(y_host, marg_out);
     if (st) return st;
-    CH_CUDA(c, cudaMemcpyAsync(marg_out, h->msg.p + 5 * h->plane_bytes(), h->plane_bytes(), cudaMemcpyDeviceToHost, h->stream));
-    CH_CUDA(c, cudaStreamSynchronize(h->stream));
     if (n_updates_out) *n_updates_out = h->B * (6 * h->T - 4);
     return CXB_OK;
 }

@@ -13,7 +13,9 @@
 // shared-memory line and read back with broadcast 128-bit loads, so a step is K*K/32 FFMAs + K/4 LDS per warp
 // and no block-level barrier.  Larger K stream Tbl through shared memory in row tiles shared by the 8 chains of
 // the CTA.  (The tcgen05 path for K = 512 named by the north star is future work: see DESIGN.md.)
+#include <algorithm>
 #include <cmath>
+#include <type_traits>
 
 #include "common.cuh"
 
@@ -211,6 +213,175 @@ k_hmm_pass(const T* __restrict__ tbl, const T* __restrict__ emis_n, const uint8_
     }
 }
 
+// ---- K = 64, fp32: one warp per chain, one warp per CTA (1,024 CTAs = 6.9 per SM for config 3) ------------------------------
+// The 64 x 64 table lives in registers: lane (jg = lane / 2, ig = lane % 2) owns the 4 x 32 tile
+// tbl[32 ig .. 32 ig + 31][4 jg .. 4 jg + 3] as 64 packed pairs and does 64 FFMA2 (fma.rn.f32x2) per step; the carried
+// message is read back with eight conflict-free 128-bit shared loads; the two i-halves are combined by a 2-shuffle
+// transpose-reduce that leaves output states (2 lane, 2 lane + 1) in the lane, so messages move as one float2 per lane
+// (256 contiguous bytes per warp).  Nothing but the matvec is on the per-step critical path: the carried message is NOT
+// normalised exactly, it is scaled by the power of two 2^-floor(log2 sum(u_{s-1})) (exact, keeps sum(u_s) within
+// [n_s, 2 n_s), n_s = the true normaliser), and the exactly normalised message / marginal of step s-1
+// (u_{s-1} / sum(u_{s-1})) is written one step late, while the matvec of step s is in flight.
+__device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
+    unsigned long long ra = *reinterpret_cast<unsigned long long*>(&a), rb = *reinterpret_cast<unsigned long long*>(&b),
+                       rc = *reinterpret_cast<unsigned long long*>(&c), rd;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(rd) : "l"(ra), "l"(rb), "l"(rc));
+    return *reinterpret_cast<float2*>(&rd);
+}
+// branch-free reciprocal (MUFU.RCP + one Newton step, <= 1 ulp for the normal, positive sums it is used on): __frcp_rn
+// carries a slow-path call that would split the step into basic blocks and serialise the shuffle chain with the matvec
+__device__ __forceinline__ float hmm_rcp(float x) {
+    float q;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(q) : "f"(x));
+    return fmaf(q, fmaf(-x, q, 1.0f), q);
+}
+__device__ __forceinline__ float hmm_pow2_inv(float s) {
+    unsigned e = (__float_as_uint(s) >> 23) & 0xffu;
+    return __uint_as_float((254u - e) << 23);
+}
+template <bool FWD, bool EM_SMEM>
+__global__ void __launch_bounds__(256)
+k_hmm64_pass(const float* __restrict__ tbl, const float* __restrict__ emis_n, const uint8_t* __restrict__ obs,
+             float* __restrict__ fwd, float* __restrict__ marg, long long B, long long Tn, int n_sym) {
+    constexpr int K = 64, LOOK = 4, VS = 72;  // VS: the second half of the message is shifted by 4 banks
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int warp = threadIdx.x >> 5, n_warps = blockDim.x >> 5;
+    float* sh_v = reinterpret_cast<float*>(smem_raw) + warp * 2 * VS;  // [2][VS] carried message, double buffered
+    float* sh_em = reinterpret_cast<float*>(smem_raw) + n_warps * 2 * VS;  // [M][64] emission messages (if they fit)
+    const int lane = threadIdx.x & 31, jg = lane >> 1, ig = lane & 1;
+    const long long b = (long long)blockIdx.x * n_warps + warp;
+    float2 a2[4][16];  // a2[jj][ip] = (tbl[32 ig + 2 ip][4 jg + jj], tbl[32 ig + 2 ip + 1][4 jg + jj])
+#pragma unroll
+    for (int jj = 0; jj < 4; ++jj)
+#pragma unroll
+        for (int ip = 0; ip < 16; ++ip) {
+            const int j = 4 * jg + jj, i = 32 * ig + 2 * ip;
+            a2[jj][ip] = make_float2(tbl[(size_t)i * K + j], tbl[(size_t)(i + 1) * K + j]);
+        }
+    if (EM_SMEM) {
+        for (int x = threadIdx.x; x < n_sym * K; x += blockDim.x) sh_em[x] = emis_n[x];
+        __syncthreads();
+    }
+    if (b >= B) return;  // whole warps leave; nothing below synchronises across warps
+    const int my_slot = 2 * lane + 4 * (lane >> 4);  // where states (2 lane, 2 lane + 1) live in sh_v
+
+    auto time_of = [&](long long step) { return FWD ? step : Tn - 1 - step; };
+    auto load_obs_block = [&](long long step0) -> int {  // lane l fetches the symbol of step0 + l
+        long long st = step0 + lane;
+        return (st < Tn) ? (int)obs[(size_t)time_of(st) * B + b] : 0;
+    };
+    auto fwd_at = [&](long long step) -> float2 {  // BWD: forward message of `step` for this lane's two states
+        return (step < Tn) ? __ldcs(reinterpret_cast<const float2*>(&fwd[((size_t)time_of(step) * B + b) * K]) + lane)
+                           : make_float2(0.0f, 0.0f);
+    };
+    int obs_cur = 0, obs_next = load_obs_block(0);
+    float2 a_cur[LOOK], a_nxt[LOOK];
+#pragma unroll
+    for (int u = 0; u < LOOK; ++u) {
+        a_cur[u] = make_float2(0.0f, 0.0f);
+        a_nxt[u] = FWD ? make_float2(0.0f, 0.0f) : fwd_at(u);
+    }
+    float2 u1 = make_float2(0.0f, 0.0f);  // carried message of the previous step (scaled, not normalised)
+    float2 ring[LOOK];                      // what steps s-1 .. s-4 leave behind (FWD: the message, BWD: fwd * bwd)
+#pragma unroll
+    for (int u = 0; u < LOOK; ++u) ring[u] = make_float2(0.0f, 0.0f);
+    float p1 = 0.0f, p2 = 0.0f, p3 = 0.0f;  // butterfly partial sums in flight (one level per step)
+
+    // One step. GEN = false is the steady state (4 <= s < Tn): straight-line code.
+    //  * scale: r = 2^-floor(log2 max(u_{s-1})) from ONE warp-wide redux.sync.max.f32 (exact scaling, bounded range);
+    //  * exact sums for the write-out are a software-pipelined butterfly: every step issues the five shuffles of five
+    //    different ages (no dependent shuffle chain inside a step), so the value of step s-4 leaves, exactly
+    //    normalised, during step s.
+    auto step = [&](auto gen_tag, long long s, int slot, float2 a_now) {
+        constexpr bool GEN = decltype(gen_tag)::value;
+        int o = __shfl_sync(0xffffffffu, obs_cur, (int)(s & 31));
+        if (o >= n_sym) o = n_sym - 1;
+        const float2 em = EM_SMEM ? *reinterpret_cast<const float2*>(sh_em + o * K + 2 * lane)
+                                  : __ldg(reinterpret_cast<const float2*>(emis_n + (size_t)o * K) + lane);
+        float mx;
+        {
+            const float lm = fmaxf(u1.x, u1.y);
+            asm("redux.sync.max.f32 %0, %1, 0xffffffff;" : "=f"(mx) : "f"(lm));
+        }
+        const float r = hmm_pow2_inv(mx);
+        {   // pipelined butterfly: ring[(s-1)&3] entered at level 1, ring[s&3] (step s-4) completes now
+            const float2 x1 = ring[(slot + LOOK - 1) % LOOK];
+            const float q1 = x1.x + x1.y;
+            const float n1 = q1 + __shfl_xor_sync(0xffffffffu, q1, 16);
+            const float n2 = p1 + __shfl_xor_sync(0xffffffffu, p1, 8);
+            const float n3 = p2 + __shfl_xor_sync(0xffffffffu, p2, 4);
+            const float m4 = p3 + __shfl_xor_sync(0xffffffffu, p3, 2);
+            const float tot = m4 + __shfl_xor_sync(0xffffffffu, m4, 1);
+            p1 = n1;
+            p2 = n2;
+            p3 = n3;
+            if (!GEN || (s >= LOOK && s - LOOK < Tn)) {
+                const float q = hmm_rcp(tot);
+                const float2 x4 = ring[slot];
+                float* dst = FWD ? fwd : marg;
+                __stcs(reinterpret_cast<float2*>(&dst[((size_t)time_of(s - LOOK) * B + b) * K]) + lane,
+                       make_float2(x4.x * q, x4.y * q));
+            }
+        }
+        if (!GEN || s < Tn) {
+            float2 val = make_float2(1.0f, 1.0f);
+            if (!GEN || s > 0) {
+                const float4* vp = reinterpret_cast<const float4*>(sh_v + (s & 1) * VS + 36 * ig);
+                float4 v4[8];  // the whole half-message first: 8 independent 128-bit shared loads in flight
+#pragma unroll
+                for (int q = 0; q < 8; ++q) v4[q] = vp[q];
+                float2 c[4], e[4];  // 8 independent FFMA2 chains
+#pragma unroll
+                for (int jj = 0; jj < 4; ++jj) c[jj] = e[jj] = make_float2(0.0f, 0.0f);
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                    const float2 lo = make_float2(v4[q].x, v4[q].y), hi = make_float2(v4[q].z, v4[q].w);
+#pragma unroll
+                    for (int jj = 0; jj < 4; ++jj) c[jj] = ffma2(a2[jj][2 * q], lo, c[jj]);
+#pragma unroll
+                    for (int jj = 0; jj < 4; ++jj) e[jj] = ffma2(a2[jj][2 * q + 1], hi, e[jj]);
+                }
+#pragma unroll
+                for (int jj = 0; jj < 4; ++jj) c[jj] = make_float2(c[jj].x + e[jj].x, c[jj].y + e[jj].y);
+                // transpose-reduce over the two i-halves: lane ig keeps states 2 ig, 2 ig + 1 of its j-group
+                const float acc0 = c[0].x + c[0].y, acc1 = c[1].x + c[1].y, acc2 = c[2].x + c[2].y, acc3 = c[3].x + c[3].y;
+                const float keep0 = ig ? acc2 : acc0, keep1 = ig ? acc3 : acc1;
+                const float send0 = ig ? acc0 : acc2, send1 = ig ? acc1 : acc3;
+                val.x = keep0 + __shfl_xor_sync(0xffffffffu, send0, 1);
+                val.y = keep1 + __shfl_xor_sync(0xffffffffu, send1, 1);
+            }
+            const float2 unew = (!GEN || s > 0) ? make_float2(em.x * val.x * r, em.y * val.y * r) : em;
+            ring[slot] = FWD ? unew : make_float2(a_now.x * val.x, a_now.y * val.y);
+            *reinterpret_cast<float2*>(sh_v + ((s + 1) & 1) * VS + my_slot) = unew;
+            u1 = unew;
+            __syncwarp();
+        }
+    };
+
+    for (long long s0 = 0; s0 < Tn + LOOK; s0 += LOOK) {
+        if ((s0 & 31) == 0) {
+            obs_cur = obs_next;
+            obs_next = load_obs_block(s0 + 32);
+        }
+        if (!FWD) {
+#pragma unroll
+            for (int u = 0; u < LOOK; ++u) {
+                a_cur[u] = a_nxt[u];
+                a_nxt[u] = fwd_at(s0 + LOOK + u);
+            }
+            if (s0 + 16 < Tn && lane < 2)
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(&fwd[((size_t)time_of(s0 + 16) * B + b) * K + 32 * lane]));
+        }
+        if (s0 >= LOOK && s0 + LOOK <= Tn) {
+#pragma unroll
+            for (int uu = 0; uu < LOOK; ++uu) step(std::false_type{}, s0 + uu, uu, a_cur[uu]);
+        } else {
+#pragma unroll
+            for (int uu = 0; uu < LOOK; ++uu) step(std::true_type{}, s0 + uu, uu, a_cur[uu]);
+        }
+    }
+}
+
 struct Hmm {
     int device = 0, dtype = CXB_F32, K = 0, M = 0;
     long long B = 0, T = 0;
@@ -291,10 +462,30 @@ struct Hmm {
                    (T*)fwd.p, (T*)marg.p, B, this->T, K, M, tile_rows);
         return CXB_OK;
     }
+    int32_t launch_k64() {
+        // one warp per chain; warps per CTA chosen so that one CTA per SM holds the whole batch when it can (its warps
+        // then spread evenly over the 4 schedulers): 1,024 chains -> 147 CTAs of 7 warps
+        int n_sm = 148;
+        cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, device);
+        int wpc = (int)std::min<long long>(8, std::max<long long>(1, (B + n_sm - 1) / n_sm));
+        if (const char* e = getenv("CXB_HMM_WARPS")) wpc = std::max(1, std::min(8, atoi(e)));
+        const unsigned grid = (unsigned)((B + wpc - 1) / wpc), threads = 32u * (unsigned)wpc;
+        const bool em_smem = M <= 128;
+        size_t smem = (size_t)wpc * 2 * 72 * sizeof(float) + (em_smem ? (size_t)M * 64 * sizeof(float) : 0);
+        const float *a = (const float*)A.p, *at = (const float*)At.p, *en = (const float*)En.p;
+        if (em_smem) {
+            CXB_LAUNCH((k_hmm64_pass<true, true>), grid, threads, smem, stream, a, en, obs.p, (float*)fwd.p, (float*)marg.p, B, this->T, M);
+            CXB_LAUNCH((k_hmm64_pass<false, true>), grid, threads, smem, stream, at, en, obs.p, (float*)fwd.p, (float*)marg.p, B, this->T, M);
+        } else {
+            CXB_LAUNCH((k_hmm64_pass<true, false>), grid, threads, smem, stream, a, en, obs.p, (float*)fwd.p, (float*)marg.p, B, this->T, M);
+            CXB_LAUNCH((k_hmm64_pass<false, false>), grid, threads, smem, stream, at, en, obs.p, (float*)fwd.p, (float*)marg.p, B, this->T, M);
+        }
+        return CXB_OK;
+    }
     template <class T>
     int32_t launch_t() {
         size_t stage = ((size_t)HMM_WARPS * K + (size_t)M * K) * sizeof(T);  // per-warp staging + emission messages
-        if (sizeof(T) == 4 && K == 64) return launch_pair<T, 64, true>(0, stage);
+        if (sizeof(T) == 4 && K == 64) return launch_k64();
         if (K == 32) return launch_pair<T, 32, true>(0, stage);
         size_t budget = 200 * 1024 - stage;
         int tile_rows = (int)std::min<size_t>((size_t)K, budget / ((size_t)K * sizeof(T)));

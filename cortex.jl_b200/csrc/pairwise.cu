@@ -27,11 +27,11 @@
 
 namespace cxb {
 
-constexpr int PW_SMALL_MAX = 4;  // pairwise factors per variable handled by the register path (unary + 4 = 5 = n<=5 path)
+constexpr int PW_EXACT_MAX = 4;  // pairwise factors per variable on the reference's n <= 5 path (unary + 4)
+constexpr int PW_SEG = 8;        // slots one lane group keeps in registers
 
 struct PwView {
     int n_tables;
-    const uint32_t* adj_off;   // [n+1] slots of variable v
     const uint32_t* opp;       // [P] slot of the opposite directed edge (the neighbour's message towards the same factor)
     const uint8_t* tsel;       // [P] table id * 2 + (1 if this variable is the HIGHER endpoint of the factor)
     const void* tables;        // [n_tables][2][K][K]: [0] = psi[x_lo][x_hi], [1] = its transpose
@@ -40,64 +40,96 @@ struct PwView {
     void* m2f_nxt;             // [P][K]
     void* m2v;                 // [P][K]
     void* marg;                // [n][K]
+    void* chunk_prod;          // [n_chunks][K] hub chunks: product of the chunk's m2v
+    void* chunk_pre;           // [n_chunks][K] unary * product of the earlier chunks
+    void* chunk_suf;           // [n_chunks][K] product of the later chunks
+};
+// work records in processing order (degree-sorted inside a bin so that the lanes of a warp run the same trip counts)
+struct PwBin {
+    const uint32_t* v;   // variable
+    const uint32_t* p0;  // first slot (of the variable, or of the hub chunk)
+    const uint32_t* d;   // number of slots
+    uint32_t n;
 };
 
-// Group helpers: the K lanes of a group name only themselves in the shuffle masks, so groups of one warp may
-// run different trip counts (segments of different length) without deadlocking each other.
+// Lane geometry: a message of K states is spread over L = K / S adjacent lanes, S = min(K, 4) states (one 16-byte
+// vector at fp32) per lane.  All shuffles are full-mask: every lane of a warp runs every shuffle (absent slots carry
+// the neutral message), the loops are skipped warp-uniformly.
 template <int K>
-__device__ __forceinline__ unsigned group_mask() {
-    return K == 32 ? 0xffffffffu : (((1u << (K & 31)) - 1u) << ((threadIdx.x & 31) / K * K));
-}
-template <class T, int K>
-__device__ __forceinline__ T gsum(T v, unsigned gm) {
+struct PwGeo {
+    static constexpr int S = K < 4 ? K : 4;
+    static constexpr int L = K / S;
+};
+constexpr unsigned PW_FULL_MASK = 0xffffffffu;
+
+template <class T, int N>
+__device__ __forceinline__ void ld_vec(const T* p, T (&r)[N]) {  // read-only path, 16-byte (or 8-byte) vectors
+    constexpr int BYTES = N * (int)sizeof(T);
+    if constexpr (BYTES % 16 == 0) {
 #pragma unroll
-    for (int o = K / 2; o > 0; o >>= 1) v += __shfl_xor_sync(gm, v, o, K);
+        for (int i = 0; i < BYTES / 16; ++i) {
+            uint4 q = __ldg(reinterpret_cast<const uint4*>(p) + i);
+            const T* s = reinterpret_cast<const T*>(&q);
+#pragma unroll
+            for (int j = 0; j < 16 / (int)sizeof(T); ++j) r[i * (16 / (int)sizeof(T)) + j] = s[j];
+        }
+    } else {
+        static_assert(BYTES == 8, "vector of 8 or a multiple of 16 bytes");
+        uint2 q = __ldg(reinterpret_cast<const uint2*>(p));
+        const T* s = reinterpret_cast<const T*>(&q);
+#pragma unroll
+        for (int j = 0; j < N; ++j) r[j] = s[j];
+    }
+}
+template <class T, int N>
+__device__ __forceinline__ void ld_vec_plain(const T* p, T (&r)[N]) {  // coherent load (data written by an earlier kernel)
+    constexpr int BYTES = N * (int)sizeof(T);
+    if constexpr (BYTES % 16 == 0) {
+#pragma unroll
+        for (int i = 0; i < BYTES / 16; ++i) {
+            uint4 q = *(reinterpret_cast<const uint4*>(p) + i);
+            const T* s = reinterpret_cast<const T*>(&q);
+#pragma unroll
+            for (int j = 0; j < 16 / (int)sizeof(T); ++j) r[i * (16 / (int)sizeof(T)) + j] = s[j];
+        }
+    } else {
+        uint2 q = *reinterpret_cast<const uint2*>(p);
+        const T* s = reinterpret_cast<const T*>(&q);
+#pragma unroll
+        for (int j = 0; j < N; ++j) r[j] = s[j];
+    }
+}
+template <bool STREAM, class T, int N>
+__device__ __forceinline__ void st_vec(T* p, const T (&r)[N]) {
+    constexpr int BYTES = N * (int)sizeof(T);
+    if constexpr (BYTES % 16 == 0) {
+#pragma unroll
+        for (int i = 0; i < BYTES / 16; ++i) {
+            uint4 q;
+            T* s = reinterpret_cast<T*>(&q);
+#pragma unroll
+            for (int j = 0; j < 16 / (int)sizeof(T); ++j) s[j] = r[i * (16 / (int)sizeof(T)) + j];
+            if (STREAM)
+                __stcs(reinterpret_cast<uint4*>(p) + i, q);
+            else
+                *(reinterpret_cast<uint4*>(p) + i) = q;
+        }
+    } else {
+        uint2 q;
+        T* s = reinterpret_cast<T*>(&q);
+#pragma unroll
+        for (int j = 0; j < N; ++j) s[j] = r[j];
+        if (STREAM)
+            __stcs(reinterpret_cast<uint2*>(p), q);
+        else
+            *reinterpret_cast<uint2*>(p) = q;
+    }
+}
+template <class T, int L>
+__device__ __forceinline__ T gsum(T v) {  // sum over the L lanes of a group (groups are aligned, L a power of two)
+#pragma unroll
+    for (int o = L / 2; o > 0; o >>= 1) v += __shfl_xor_sync(PW_FULL_MASK, v, o);
     return v;
-}
-// ---- building blocks (K lanes per variable, lane a owns state a) -------------------------------------------------------
-// The incoming message is loaded WHOLE by every lane of the group (K*sizeof(T) bytes, the same sector(s) for the
-// K lanes: one DRAM/L2 access, no shuffles), the lane's table row [a][0..K) is read with 128-bit shared loads.
-template <class T, int K>
-__device__ __forceinline__ void load_msg(const T* p, T (&m)[K]) {
-    constexpr int V = 16 / sizeof(T);
-    using VT = typename std::conditional<sizeof(T) == 4, float4, double2>::type;
-    if (K % V == 0) {
-#pragma unroll
-        for (int i = 0; i < K / V; ++i) {
-            VT q = __ldg(reinterpret_cast<const VT*>(p) + i);
-            const T* s = reinterpret_cast<const T*>(&q);
-#pragma unroll
-            for (int j = 0; j < V; ++j) m[i * V + j] = s[j];
-        }
-    } else {
-#pragma unroll
-        for (int i = 0; i < K; ++i) m[i] = __ldg(p + i);
-    }
-}
-// out[a] = sum_b psi(b -> a) in[b]; row = the lane's table row: row[b] = weight of in[b]
-template <class T, int K>
-__device__ __forceinline__ T contract_row(const T* row, const T (&in)[K]) {
-    constexpr int V = 16 / sizeof(T);
-    using VT = typename std::conditional<sizeof(T) == 4, float4, double2>::type;
-    T acc0 = T(0), acc1 = T(0);
-    if (K % V == 0) {
-#pragma unroll
-        for (int i = 0; i < K / V; ++i) {
-            VT q = *(reinterpret_cast<const VT*>(row) + i);
-            const T* s = reinterpret_cast<const T*>(&q);
-#pragma unroll
-            for (int j = 0; j < V; ++j) {
-                if ((j & 1) == 0)
-                    acc0 = fma(s[j], in[i * V + j], acc0);
-                else
-                    acc1 = fma(s[j], in[i * V + j], acc1);
-            }
-        }
-    } else {
-#pragma unroll
-        for (int i = 0; i < K; ++i) acc0 = fma(row[i], in[i], acc0);
-    }
-    return acc0 + acc1;
 }
 template <class T>
 __device__ __forceinline__ T recip(T x);
@@ -109,209 +141,360 @@ template <>
 __device__ __forceinline__ double recip<double>(double x) {
     return 1.0 / x;
 }
-// normalise the K-vector spread over the group's lanes to sum 1 (one reciprocal, one multiply per lane)
-template <class T, int K>
-__device__ __forceinline__ T gnorm(T v, unsigned gm) {
-    return v * recip<T>(gsum<T, K>(v, gm));
+// 2^-floor(log2 s): multiplying by it is exact, so intermediate products keep every bit of the unscaled product
+__device__ __forceinline__ float pow2_inv(float s) {
+    unsigned e = (__float_as_uint(s) >> 23) & 0xffu;
+    return __uint_as_float((254u - e) << 23);
 }
-// the lane's table row for slot selector `sel`: this variable higher endpoint -> out[a=x_hi] needs psi[b=x_lo][a] =
-// transpose block row a; lower endpoint -> out[a=x_lo] needs psi[a][b] = plain block row a
+__device__ __forceinline__ double pow2_inv(double s) {
+    unsigned e = ((unsigned)__double2hiint(s) >> 20) & 0x7ffu;
+    return __hiloint2double((int)((2046u - e) << 20), 0);
+}
 template <class T, int K>
-__device__ __forceinline__ const T* table_row(const T* sh_tables, int sel, int a) {
-    return sh_tables + (((size_t)(sel >> 1) * 2 + ((sel & 1) ? 1 : 0)) * K + a) * K;
+__device__ __forceinline__ void norm1(T (&v)[PwGeo<K>::S]) {  // normalise the group's K-vector to sum 1
+    T s = v[0];
+#pragma unroll
+    for (int i = 1; i < PwGeo<K>::S; ++i) s += v[i];
+    T r = recip<T>(gsum<T, PwGeo<K>::L>(s));
+#pragma unroll
+    for (int i = 0; i < PwGeo<K>::S; ++i) v[i] *= r;
+}
+template <class T, int K>
+__device__ __forceinline__ void rescale(T (&v)[PwGeo<K>::S]) {  // keep a running product in range (exact power-of-two scaling)
+    T s = v[0];
+#pragma unroll
+    for (int i = 1; i < PwGeo<K>::S; ++i) s += v[i];
+    T r = pow2_inv(gsum<T, PwGeo<K>::L>(s));
+#pragma unroll
+    for (int i = 0; i < PwGeo<K>::S; ++i) v[i] *= r;
+}
+template <class T, int S>
+__device__ __forceinline__ void vmul(T (&a)[S], const T (&b)[S]) {
+#pragma unroll
+    for (int i = 0; i < S; ++i) a[i] *= b[i];
+}
+template <class T, int S>
+__device__ __forceinline__ void vset(T (&a)[S], T x) {
+#pragma unroll
+    for (int i = 0; i < S; ++i) a[i] = x;
+}
+template <class T, int S>
+__device__ __forceinline__ void vcopy(T (&a)[S], const T (&b)[S]) {
+#pragma unroll
+    for (int i = 0; i < S; ++i) a[i] = b[i];
+}
+// out[r] = sum_b psi(b -> a0 + r) in[b]; rows = the lane's S table rows in shared memory (row a0 of the selected block:
+// this variable higher endpoint -> transpose block, lower endpoint -> plain block)
+template <class T, int K>
+__device__ __forceinline__ void contract(const T* rows, const T (&in)[K], T (&out)[PwGeo<K>::S]) {
+    constexpr int S = PwGeo<K>::S;
+    constexpr int V = (K * (int)sizeof(T)) % 16 == 0 ? 16 / (int)sizeof(T) : 1;
+#pragma unroll
+    for (int r = 0; r < S; ++r) {
+        T acc0 = T(0), acc1 = T(0);
+        if constexpr (V > 1) {
+#pragma unroll
+            for (int i = 0; i < K / V; ++i) {
+                uint4 q = *(reinterpret_cast<const uint4*>(rows + r * K) + i);
+                const T* s = reinterpret_cast<const T*>(&q);
+#pragma unroll
+                for (int j = 0; j < V; ++j) {
+                    if ((j & 1) == 0)
+                        acc0 = fma(s[j], in[i * V + j], acc0);
+                    else
+                        acc1 = fma(s[j], in[i * V + j], acc1);
+                }
+            }
+        } else {
+#pragma unroll
+            for (int i = 0; i < K; ++i) acc0 = fma(rows[r * K + i], in[i], acc0);
+        }
+        out[r] = acc0 + acc1;
+    }
+}
+template <class T>
+__device__ __forceinline__ void stage_tables(T* sh, const PwView& g, int K) {
+    for (int x = threadIdx.x; x < g.n_tables * 2 * K * K; x += blockDim.x) sh[x] = ((const T*)g.tables)[x];
+    __syncthreads();
 }
 
-// ---- variables with <= DMAX pairwise factors: one group of K lanes per variable, all messages in registers ---------
-// DMAX = 4  : the reference's n <= 5 path (src/dependencies.jl:60-88): products left to right over "all others";
-// DMAX > 4  : the reference uses the segment tree; here exclusive products by a renormalised prefix/suffix scan.
-// Groups name only their own lanes in the shuffle masks, so each group runs exactly its own degree.
-template <class T, int K, int DMAX>
-__global__ void __launch_bounds__(256) k_pw_reg(PwView g, const uint32_t* __restrict__ vars, uint32_t n_vars) {
+// ---- variables with <= 4 pairwise factors: one lane group per variable, the reference's n <= 5 path -----------------------
+// (src/dependencies.jl:60-88): marginal = unary * x_0 * x_1 ..., m2f(v, f_k) = unary * prod_{j != k} x_j, left to right.
+template <class T, int K>
+__global__ void __launch_bounds__(256) k_pw_exact(PwView g, PwBin bin) {
+    constexpr int S = PwGeo<K>::S, L = PwGeo<K>::L, D = PW_EXACT_MAX;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     T* sh_tables = reinterpret_cast<T*>(smem_raw);
-    for (int x = threadIdx.x; x < g.n_tables * 2 * K * K; x += blockDim.x) sh_tables[x] = ((const T*)g.tables)[x];
-    __syncthreads();
-    const uint32_t gid = (blockIdx.x * blockDim.x + threadIdx.x) / K;
-    const int a = threadIdx.x % K;
-    const unsigned gm = group_mask<K>();
-    if (gid >= n_vars) return;  // whole groups leave together
-    const uint32_t v = vars[gid];
-    const uint32_t p0 = g.adj_off[v], d = g.adj_off[v + 1] - p0;
-    const T un = __ldg((const T*)g.unary + (size_t)v * K + a);
-    uint32_t op[DMAX];
-    int sel[DMAX];
-    T x[DMAX];
+    stage_tables<T>(sh_tables, g, K);
+    const uint32_t gid = (blockIdx.x * blockDim.x + threadIdx.x) / L;
+    const int a0 = (threadIdx.x % L) * S;
+    const bool live = gid < bin.n;
+    uint32_t v = 0, p0 = 0, d = 0;
+    if (live) {
+        v = __ldg(bin.v + gid);
+        p0 = __ldg(bin.p0 + gid);
+        d = __ldg(bin.d + gid);
+    }
+    T un[S];
+    vset<T, S>(un, T(1));
+    if (live) ld_vec<T, S>((const T*)g.unary + (size_t)v * K + a0, un);
+    uint32_t op[D];
+    int sel[D];
 #pragma unroll
-    for (int k = 0; k < DMAX; ++k)
+    for (int k = 0; k < D; ++k) {
+        op[k] = 0;
+        sel[k] = 0;
         if ((uint32_t)k < d) {
             op[k] = __ldg(g.opp + p0 + k);
             sel[k] = __ldg(g.tsel + p0 + k);
         }
+    }
+    T x[D][S];
 #pragma unroll
-    for (int k = 0; k < DMAX; ++k)
-        if ((uint32_t)k < d) {
-            T in[K];
-            load_msg<T, K>((const T*)g.m2f_cur + (size_t)op[k] * K, in);
-            T m = gnorm<T, K>(contract_row<T, K>(table_row<T, K>(sh_tables, sel[k], a), in), gm);
-            x[k] = m;
-            __stcs((T*)g.m2v + (size_t)(p0 + k) * K + a, m);
+    for (int k = 0; k < D; ++k) {
+        vset<T, S>(x[k], T(1));
+        const bool have = (uint32_t)k < d;
+        if (!__any_sync(PW_FULL_MASK, have)) continue;
+        T in[K];
+#pragma unroll
+        for (int i = 0; i < K; ++i) in[i] = T(1);
+        if (have) ld_vec<T, K>((const T*)g.m2f_cur + (size_t)op[k] * K, in);
+        T m[S];
+        contract<T, K>(sh_tables + ((size_t)sel[k] * K + a0) * K, in, m);
+        norm1<T, K>(m);
+        if (have) {
+            st_vec<true, T, S>((T*)g.m2v + (size_t)(p0 + k) * K + a0, m);
+            vcopy<T, S>(x[k], m);
         }
-    if (DMAX <= PW_SMALL_MAX) {
-        T acc = un;
+    }
+    {
+        T acc[S];
+        vcopy<T, S>(acc, un);
 #pragma unroll
-        for (int k = 0; k < DMAX; ++k)
-            if ((uint32_t)k < d) acc = acc * x[k];
-        __stcs((T*)g.marg + (size_t)v * K + a, gnorm<T, K>(acc, gm));
+        for (int k = 0; k < D; ++k) vmul<T, S>(acc, x[k]);
+        norm1<T, K>(acc);
+        if (live) st_vec<true, T, S>((T*)g.marg + (size_t)v * K + a0, acc);
+    }
 #pragma unroll
-        for (int k = 0; k < DMAX; ++k)
-            if ((uint32_t)k < d) {
-                T o = un;
+    for (int k = 0; k < D; ++k) {
+        const bool have = (uint32_t)k < d;
+        if (!__any_sync(PW_FULL_MASK, have)) continue;
+        T o[S];
+        vcopy<T, S>(o, un);
 #pragma unroll
-                for (int j = 0; j < DMAX; ++j)
-                    if (j != k && (uint32_t)j < d) o = o * x[j];
-                __stcs((T*)g.m2f_nxt + (size_t)(p0 + k) * K + a, gnorm<T, K>(o, gm));
-            }
-    } else {
-        T pre[DMAX];  // pre[k] = normalise(unary * x_0 * ... * x_{k-1})
-        pre[0] = un;
-#pragma unroll
-        for (int k = 1; k < DMAX; ++k)
-            if ((uint32_t)k < d) pre[k] = gnorm<T, K>(pre[k - 1] * x[k - 1], gm);
-        T suf = T(1);
-#pragma unroll
-        for (int k = DMAX - 1; k >= 0; --k)
-            if ((uint32_t)k < d) {
-                if ((uint32_t)k == d - 1) __stcs((T*)g.marg + (size_t)v * K + a, gnorm<T, K>(pre[k] * x[k], gm));
-                __stcs((T*)g.m2f_nxt + (size_t)(p0 + k) * K + a, gnorm<T, K>(pre[k] * suf, gm));
-                suf = gnorm<T, K>(suf * x[k], gm);
-            }
+        for (int j = 0; j < D; ++j)
+            if (j != k) vmul<T, S>(o, x[j]);
+        norm1<T, K>(o);
+        if (have) st_vec<true, T, S>((T*)g.m2f_nxt + (size_t)(p0 + k) * K + a0, o);
     }
 }
 
-// ---- medium hubs (17 .. 16*NG pairwise factors): one CTA per variable, NG groups, each group keeps its segment of
-// <= 16 messages in registers (same code shape as k_pw_reg) and the segments are combined through shared memory.
-template <class T, int K, int NG>
-__global__ void __launch_bounds__(NG * K) k_pw_hub16(PwView g, const uint32_t* __restrict__ vars, uint32_t n_vars) {
-    constexpr int S = 16;
+// ---- teams: G lane groups cooperate on one variable (FULL) or on one 8G-slot chunk of a hub (H1 / H3) -------------------
+// Each group keeps its segment of <= 8 messages in registers; segment products are combined by a shuffle scan over the
+// groups of the team; exclusive products inside the segment by a prefix / suffix pass (the reference uses the segment
+// tree of src/dependencies.jl:90-173 there: same values up to rounding, no tree nodes materialised).
+//   FULL : m2v from the gathered m2f, marginal, m2f               (variables with 5 .. 8G factors)
+//   H1   : m2v from the gathered m2f, chunk product -> chunk_prod  (hub chunks, pass 1)
+//   H3   : m2v re-read, chunk_pre / chunk_suf from k_pw_hub_scan, m2f (hub chunks, pass 3)
+enum { PW_MODE_FULL = 0, PW_MODE_H1 = 1, PW_MODE_H3 = 2 };
+template <class T, int K, int G, int MODE>
+__global__ void __launch_bounds__(256) k_pw_team(PwView g, PwBin bin) {
+    constexpr int S = PwGeo<K>::S, L = PwGeo<K>::L, TL = G * L, SEG = PW_SEG;
+    static_assert(TL <= 32, "a team lives inside one warp");
     extern __shared__ __align__(16) unsigned char smem_raw[];
     T* sh_tables = reinterpret_cast<T*>(smem_raw);
-    T* sh_part = sh_tables + (size_t)g.n_tables * 2 * K * K;  // [NG][K] segment products
-    for (int x = threadIdx.x; x < g.n_tables * 2 * K * K; x += blockDim.x) sh_tables[x] = ((const T*)g.tables)[x];
-    __syncthreads();
-    const int grp = threadIdx.x / K, a = threadIdx.x % K;
-    const unsigned gm = group_mask<K>();
-    for (uint32_t hv = blockIdx.x; hv < n_vars; hv += gridDim.x) {
-        const uint32_t v = vars[hv];
-        const uint32_t p0 = g.adj_off[v], d = g.adj_off[v + 1] - p0;
-        const uint32_t seg = (d + NG - 1) / NG;  // <= S by construction of the bin
-        const uint32_t lo = min(d, grp * seg), n_loc = min(d, lo + seg) - lo;
-        const uint32_t pb = p0 + lo;
-        const T un = __ldg((const T*)g.unary + (size_t)v * K + a);
-        uint32_t op[S];
-        int sel[S];
-        T x[S];
+    if (MODE != PW_MODE_H3) stage_tables<T>(sh_tables, g, K);
+    const uint32_t team = (blockIdx.x * blockDim.x + threadIdx.x) / TL;
+    const int tl = threadIdx.x % TL, grp = tl / L, a0 = (tl % L) * S;
+    const bool live = team < bin.n;
+    uint32_t v = 0, p0 = 0, d = 0;
+    if (live) {
+        v = __ldg(bin.v + team);
+        p0 = __ldg(bin.p0 + team);
+        d = __ldg(bin.d + team);
+    }
+    const uint32_t seg = (d + G - 1) / G;  // <= SEG by construction of the bins
+    const uint32_t lo = min(d, (uint32_t)grp * seg), n_loc = min(d, lo + seg) - lo;
+    const uint32_t pb = p0 + lo;
+    T x[SEG][S];
+    if (MODE != PW_MODE_H3) {
+        uint32_t op[SEG];
+        int sel[SEG];
 #pragma unroll
-        for (int k = 0; k < S; ++k)
+        for (int k = 0; k < SEG; ++k) {
+            op[k] = 0;
+            sel[k] = 0;
             if ((uint32_t)k < n_loc) {
                 op[k] = __ldg(g.opp + pb + k);
                 sel[k] = __ldg(g.tsel + pb + k);
             }
-        T prod = T(1);
+        }
 #pragma unroll
-        for (int k = 0; k < S; ++k)
-            if ((uint32_t)k < n_loc) {
-                T in[K];
-                load_msg<T, K>((const T*)g.m2f_cur + (size_t)op[k] * K, in);
-                T m = gnorm<T, K>(contract_row<T, K>(table_row<T, K>(sh_tables, sel[k], a), in), gm);
-                x[k] = m;
-                __stcs((T*)g.m2v + (size_t)(pb + k) * K + a, m);
-                prod = gnorm<T, K>(prod * m, gm);
+        for (int k = 0; k < SEG; ++k) {
+            vset<T, S>(x[k], T(1));
+            const bool have = (uint32_t)k < n_loc;
+            if (!__any_sync(PW_FULL_MASK, have)) continue;
+            T in[K];
+#pragma unroll
+            for (int i = 0; i < K; ++i) in[i] = T(1);
+            if (have) ld_vec<T, K>((const T*)g.m2f_cur + (size_t)op[k] * K, in);
+            T m[S];
+            contract<T, K>(sh_tables + ((size_t)sel[k] * K + a0) * K, in, m);
+            norm1<T, K>(m);
+            if (have) {
+                st_vec<MODE == PW_MODE_FULL, T, S>((T*)g.m2v + (size_t)(pb + k) * K + a0, m);
+                vcopy<T, S>(x[k], m);
             }
-        sh_part[grp * K + a] = prod;
-        __syncthreads();
-        T pre0 = un, suf = T(1);
-        for (int h = 0; h < grp; ++h) pre0 = gnorm<T, K>(pre0 * sh_part[h * K + a], gm);
-        for (int h = NG - 1; h > grp; --h) suf = gnorm<T, K>(suf * sh_part[h * K + a], gm);
-        if (grp == NG - 1) __stcs((T*)g.marg + (size_t)v * K + a, gnorm<T, K>(pre0 * prod, gm));
-        T pre[S];
-        pre[0] = pre0;
+        }
+    } else {
 #pragma unroll
-        for (int k = 1; k < S; ++k)
-            if ((uint32_t)k < n_loc) pre[k] = gnorm<T, K>(pre[k - 1] * x[k - 1], gm);
+        for (int k = 0; k < SEG; ++k) {
+            vset<T, S>(x[k], T(1));
+            if ((uint32_t)k < n_loc) ld_vec_plain<T, S>((const T*)g.m2v + (size_t)(pb + k) * K + a0, x[k]);
+        }
+    }
+    // segment product
+    T P[S];
+    vcopy<T, S>(P, x[0]);
 #pragma unroll
-        for (int k = S - 1; k >= 0; --k)
-            if ((uint32_t)k < n_loc) {
-                __stcs((T*)g.m2f_nxt + (size_t)(pb + k) * K + a, gnorm<T, K>(pre[k] * suf, gm));
-                suf = gnorm<T, K>(suf * x[k], gm);
-            }
-        __syncthreads();  // sh_part is reused by the next hub
+    for (int k = 1; k < SEG; ++k) {
+        vmul<T, S>(P, x[k]);
+        if (k & 1) rescale<T, K>(P);
+    }
+    // inclusive prefix over the groups of the team, exclusive = the previous group's inclusive
+    T inc[S], exc[S];
+    vcopy<T, S>(inc, P);
+#pragma unroll
+    for (int off = 1; off < G; off <<= 1) {
+        T y[S];
+#pragma unroll
+        for (int i = 0; i < S; ++i) y[i] = __shfl_up_sync(PW_FULL_MASK, inc[i], off * L, TL);
+        if (grp >= off) vmul<T, S>(inc, y);
+        rescale<T, K>(inc);
+    }
+#pragma unroll
+    for (int i = 0; i < S; ++i) {
+        T y = __shfl_up_sync(PW_FULL_MASK, inc[i], L, TL);
+        exc[i] = (G > 1 && grp > 0) ? y : T(1);
+    }
+    if (MODE == PW_MODE_H1) {
+        if (live && grp == G - 1) st_vec<false, T, S>((T*)g.chunk_prod + (size_t)team * K + a0, inc);
+        return;
+    }
+    // exclusive suffix over the groups
+    T sinc[S], sexc[S];
+    vcopy<T, S>(sinc, P);
+#pragma unroll
+    for (int off = 1; off < G; off <<= 1) {
+        T y[S];
+#pragma unroll
+        for (int i = 0; i < S; ++i) y[i] = __shfl_down_sync(PW_FULL_MASK, sinc[i], off * L, TL);
+        if (grp + off < G) vmul<T, S>(sinc, y);
+        rescale<T, K>(sinc);
+    }
+#pragma unroll
+    for (int i = 0; i < S; ++i) {
+        T y = __shfl_down_sync(PW_FULL_MASK, sinc[i], L, TL);
+        sexc[i] = (G > 1 && grp < G - 1) ? y : T(1);
+    }
+    T ext_pre[S], ext_suf[S];  // what lies outside the team: unary (FULL) or the other chunks of the hub (H3)
+    vset<T, S>(ext_pre, T(1));
+    vset<T, S>(ext_suf, T(1));
+    if (live) {
+        if (MODE == PW_MODE_FULL) {
+            ld_vec<T, S>((const T*)g.unary + (size_t)v * K + a0, ext_pre);
+        } else {
+            ld_vec_plain<T, S>((const T*)g.chunk_pre + (size_t)team * K + a0, ext_pre);
+            ld_vec_plain<T, S>((const T*)g.chunk_suf + (size_t)team * K + a0, ext_suf);
+        }
+    }
+    if (MODE == PW_MODE_FULL) {  // marginal = unary * every segment product (held by the last group)
+        T mg[S];
+        vcopy<T, S>(mg, ext_pre);
+        vmul<T, S>(mg, inc);
+        norm1<T, K>(mg);
+        if (live && grp == G - 1) st_vec<true, T, S>((T*)g.marg + (size_t)v * K + a0, mg);
+    }
+    T run[S], suf[S];
+    vcopy<T, S>(run, ext_pre);
+    vmul<T, S>(run, exc);
+    rescale<T, K>(run);
+    vcopy<T, S>(suf, ext_suf);
+    vmul<T, S>(suf, sexc);
+    rescale<T, K>(suf);
+    T pre[SEG][S];
+#pragma unroll
+    for (int k = 0; k < SEG; ++k) {
+        vcopy<T, S>(pre[k], run);
+        vmul<T, S>(run, x[k]);
+        if (k & 1) rescale<T, K>(run);
+    }
+#pragma unroll
+    for (int k = SEG - 1; k >= 0; --k) {
+        const bool have = (uint32_t)k < n_loc;
+        if (!__any_sync(PW_FULL_MASK, have)) continue;
+        T o[S];
+        vcopy<T, S>(o, pre[k]);
+        vmul<T, S>(o, suf);
+        norm1<T, K>(o);
+        if (have) st_vec<true, T, S>((T*)g.m2f_nxt + (size_t)(pb + k) * K + a0, o);
+        vmul<T, S>(suf, x[k]);
+        if (k & 1) rescale<T, K>(suf);
     }
 }
 
-// ---- big hubs: one CTA per variable, NG groups of K lanes, segments of any length ----------------------------------------
-// pass 1: every group walks its contiguous segment of the adjacency, 4 slots at a time (4 gathers in flight): m2v per
-//         slot (stored) and the segment product;
-// pass 2: exclusive prefix (unary * earlier segments) / suffix (later segments) per group through shared memory;
-// pass 3: forward over the segment stores the running exclusive prefix in m2f_nxt (scratch), backward combines it with
-//         the running suffix into the final m2f. Products are renormalised at every step (as every BP message is).
-template <class T, int K, int NG>
-__global__ void __launch_bounds__(NG * K) k_pw_hub(PwView g, const uint32_t* __restrict__ vars, uint32_t n_vars) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    T* sh_tables = reinterpret_cast<T*>(smem_raw);
-    T* sh_part = sh_tables + (size_t)g.n_tables * 2 * K * K;  // [NG][K] segment products
-    for (int x = threadIdx.x; x < g.n_tables * 2 * K * K; x += blockDim.x) sh_tables[x] = ((const T*)g.tables)[x];
-    __syncthreads();
-    const int grp = threadIdx.x / K, a = threadIdx.x % K;
-    const unsigned gm = group_mask<K>();
-    constexpr int U = 4;
-    for (uint32_t hv = blockIdx.x; hv < n_vars; hv += gridDim.x) {
-        const uint32_t v = vars[hv];
-        const uint32_t p0 = g.adj_off[v], d = g.adj_off[v + 1] - p0;
-        const uint32_t seg = (d + NG - 1) / NG;
-        const uint32_t lo = min(d, grp * seg), hi = min(d, lo + seg);
-        const T un = __ldg((const T*)g.unary + (size_t)v * K + a);
-        // pass 1
-        T prod = T(1);
-        for (uint32_t k0 = lo; k0 < hi; k0 += U) {
-            uint32_t op[U];
-            int sel[U];
+// ---- hub pass 2: one lane group per hub scans the products of its chunks (prefix includes the unary), writes the marginal
+template <class T, int K>
+__global__ void __launch_bounds__(128) k_pw_hub_scan(PwView g, PwBin hubs /* v, first chunk, number of chunks */) {
+    constexpr int S = PwGeo<K>::S, L = PwGeo<K>::L, U = 8;
+    const uint32_t gid = (blockIdx.x * blockDim.x + threadIdx.x) / L;
+    const int a0 = (threadIdx.x % L) * S;
+    const bool live = gid < hubs.n;
+    uint32_t v = 0, c0 = 0, nc = 0;
+    if (live) {
+        v = __ldg(hubs.v + gid);
+        c0 = __ldg(hubs.p0 + gid);
+        nc = __ldg(hubs.d + gid);
+    }
+    uint32_t ncmax = nc;
 #pragma unroll
-            for (int u = 0; u < U; ++u)
-                if (k0 + u < hi) {
-                    op[u] = __ldg(g.opp + p0 + k0 + u);
-                    sel[u] = __ldg(g.tsel + p0 + k0 + u);
-                }
+    for (int o = 16; o > 0; o >>= 1) ncmax = max(ncmax, __shfl_xor_sync(PW_FULL_MASK, ncmax, o));
+    T run[S];
+    vset<T, S>(run, T(1));
+    if (live) ld_vec<T, S>((const T*)g.unary + (size_t)v * K + a0, run);
+    for (uint32_t cb = 0; cb < ncmax; cb += U) {  // U independent loads in flight, then the dependent product chain
+        T cp[U][S];
 #pragma unroll
-            for (int u = 0; u < U; ++u)
-                if (k0 + u < hi) {
-                    T in[K];
-                    load_msg<T, K>((const T*)g.m2f_cur + (size_t)op[u] * K, in);
-                    T m = gnorm<T, K>(contract_row<T, K>(table_row<T, K>(sh_tables, sel[u], a), in), gm);
-                    ((T*)g.m2v)[(size_t)(p0 + k0 + u) * K + a] = m;
-                    prod = gnorm<T, K>(prod * m, gm);
-                }
+        for (int u = 0; u < U; ++u) {
+            vset<T, S>(cp[u], T(1));
+            if (cb + u < nc) ld_vec_plain<T, S>((const T*)g.chunk_prod + (size_t)(c0 + cb + u) * K + a0, cp[u]);
         }
-        sh_part[grp * K + a] = prod;
-        __syncthreads();
-        // pass 2
-        T pre = un, suf = T(1);
-        for (int h = 0; h < grp; ++h) pre = gnorm<T, K>(pre * sh_part[h * K + a], gm);
-        for (int h = NG - 1; h > grp; --h) suf = gnorm<T, K>(suf * sh_part[h * K + a], gm);
-        if (grp == NG - 1) ((T*)g.marg)[(size_t)v * K + a] = gnorm<T, K>(pre * prod, gm);
-        // pass 3 forward: exclusive prefixes into the scratch
-        T run = pre;
-        for (uint32_t k = lo; k < hi; ++k) {
-            ((T*)g.m2f_nxt)[(size_t)(p0 + k) * K + a] = run;
-            run = gnorm<T, K>(run * ((const T*)g.m2v)[(size_t)(p0 + k) * K + a], gm);
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            if (cb + u < nc) st_vec<false, T, S>((T*)g.chunk_pre + (size_t)(c0 + cb + u) * K + a0, run);
+            vmul<T, S>(run, cp[u]);
+            rescale<T, K>(run);
         }
-        // pass 3 backward: m2f = prefix * suffix
-        run = suf;
-        for (uint32_t k = hi; k > lo; --k) {
-            const size_t o = (size_t)(p0 + k - 1) * K + a;
-            ((T*)g.m2f_nxt)[o] = gnorm<T, K>(((const T*)g.m2f_nxt)[o] * run, gm);
-            run = gnorm<T, K>(run * ((const T*)g.m2v)[o], gm);
+    }
+    norm1<T, K>(run);
+    if (live) st_vec<true, T, S>((T*)g.marg + (size_t)v * K + a0, run);
+    T suf[S];
+    vset<T, S>(suf, T(1));
+    const uint32_t nb = (ncmax + U - 1) / U;
+    for (uint32_t b = nb; b > 0; --b) {
+        const uint32_t cb = (b - 1) * U;
+        T cp[U][S];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            vset<T, S>(cp[u], T(1));
+            if (cb + u < nc) ld_vec_plain<T, S>((const T*)g.chunk_prod + (size_t)(c0 + cb + u) * K + a0, cp[u]);
         }
-        __syncthreads();  // sh_part is reused by the next hub
+#pragma unroll
+        for (int u = U - 1; u >= 0; --u) {
+            if (cb + u < nc) st_vec<false, T, S>((T*)g.chunk_suf + (size_t)(c0 + cb + u) * K + a0, suf);
+            vmul<T, S>(suf, cp[u]);
+            rescale<T, K>(suf);
+        }
     }
 }
 
@@ -333,10 +516,18 @@ struct Pairwise {
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     std::string err;
-    DBuf<uint32_t> adj_off, opp, small_vars, r8_vars, r16_vars, mid_vars, mid2_vars, big_vars, slot_of_edge;
+    // work bins: 0 = exact path (<= 4 factors), 1 + log2(G) = teams of G groups, then hub chunks and hubs
+    static constexpr int N_TEAM_BINS = 5;  // G = 1, 2, 4, 8, 16
+    struct Bin {
+        DBuf<uint32_t> v, p0, d;
+        uint32_t n = 0;
+        PwBin view() const { return PwBin{v.p, p0.p, d.p, n}; }
+    };
+    Bin exact_bin, team_bin[N_TEAM_BINS], chunk_bin, hub_bin;
+    DBuf<uint32_t> opp, slot_of_edge;
     DBuf<uint8_t> tsel;
-    DBuf<unsigned char> tables, unary, m2f[2], m2v, marg, scratch;
-    uint32_t n_small = 0, n_r8 = 0, n_r16 = 0, n_mid = 0, n_mid2 = 0, n_big = 0;
+    DBuf<unsigned char> tables, unary, m2f[2], m2v, marg, scratch, chunk_prod, chunk_pre, chunk_suf;
+    int g_max = 16;  // largest team (groups) that fits one warp at this K
     long long n_products = 0;
     bool have_graph = false, have_tables = false, have_unary = false, have_msgs = false, ran = false;
     size_t esz() const { return dtype == CXB_F32 ? 4 : 8; }
@@ -386,51 +577,78 @@ struct Pairwise {
             sel[pu] = (uint8_t)(ft[f] * 2 + 0);  // u is the lower endpoint
             sel[pv] = (uint8_t)(ft[f] * 2 + 1);
         }
-        // degree bins: <= 4 register path (reference n<=5 order), 5..8 and 9..16 register prefix/suffix,
-        // <= 16*(32/K) one warp-sized CTA, <= 16*(256/K) one 256-thread CTA (segments in registers), larger: streamed
-        std::vector<uint32_t> sm, r8, r16, md, md2, bg;
-        const uint32_t mid_max = 16u * (uint32_t)std::max(1, 32 / K), mid2_max = 16u * (uint32_t)(256 / K);
+        // degree bins (records sorted by degree inside a bin, ascending id inside a degree: the lanes of a warp then run
+        // the same trip counts and neighbouring records still gather from neighbouring slots of the same hubs):
+        //   <= 4 factors: exact path; <= 8G: team of G groups, G = 1 .. g_max; larger: hub, cut into chunks of 8 g_max slots
+        const int lanes = K / std::min(K, 4);
+        g_max = std::min(16, 32 / lanes);
+        const uint32_t chunk_slots = (uint32_t)PW_SEG * (uint32_t)g_max;
+        struct Rec {
+            uint32_t v, p0, d;
+        };
+        std::vector<Rec> ex, tm[N_TEAM_BINS], hubs, chunks;
         n_products = 0;
         for (long long v = 0; v < n; ++v) {
             uint32_t d = off[v + 1] - off[v];
-            if (d <= PW_SMALL_MAX) {
-                sm.push_back((uint32_t)v);
+            Rec r{(uint32_t)v, off[v], d};
+            if (d <= (uint32_t)PW_EXACT_MAX) {
+                ex.push_back(r);
                 continue;
             }
             n_products += (long long)d - 1;  // (d+1) factors incl. the unary -> d-1 ProductOfMessages nodes in the reference
-            if (d <= 8)
-                r8.push_back((uint32_t)v);
-            else if (d <= 16)
-                r16.push_back((uint32_t)v);
-            else
-                (d <= mid_max ? md : d <= mid2_max ? md2 : bg).push_back((uint32_t)v);
+            if (d > chunk_slots) {
+                hubs.push_back(r);
+                continue;
+            }
+            int b = 0;
+            while ((uint32_t)PW_SEG << b < d) ++b;
+            tm[b].push_back(r);
         }
-        auto by_degree_desc = [&](uint32_t x, uint32_t y) { return off[x + 1] - off[x] > off[y + 1] - off[y]; };
-        std::stable_sort(md.begin(), md.end(), by_degree_desc);
-        std::stable_sort(md2.begin(), md2.end(), by_degree_desc);
-        std::stable_sort(bg.begin(), bg.end(), by_degree_desc);
-        n_small = (uint32_t)sm.size();
-        n_r8 = (uint32_t)r8.size();
-        n_r16 = (uint32_t)r16.size();
-        n_mid = (uint32_t)md.size();
-        n_mid2 = (uint32_t)md2.size();
-        n_big = (uint32_t)bg.size();
+        auto by_degree_desc = [](const Rec& x, const Rec& y) { return x.d > y.d; };
+        std::stable_sort(ex.begin(), ex.end(), by_degree_desc);
+        for (auto& t : tm) std::stable_sort(t.begin(), t.end(), by_degree_desc);
+        std::stable_sort(hubs.begin(), hubs.end(), by_degree_desc);
+        std::vector<Rec> hub_recs;  // v, first chunk, number of chunks
+        for (const Rec& h : hubs) {
+            uint32_t nc = (h.d + chunk_slots - 1) / chunk_slots;
+            hub_recs.push_back(Rec{h.v, (uint32_t)chunks.size(), nc});
+            for (uint32_t c = 0; c < nc; ++c)
+                chunks.push_back(Rec{h.v, h.p0 + c * chunk_slots, std::min(chunk_slots, h.d - c * chunk_slots)});
+        }
         auto up = [&](auto& dbuf, const auto& vec) -> cudaError_t {
             cudaError_t e = dbuf.reserve(vec.size());
             if (e != cudaSuccess) return e;
             return vec.empty() ? cudaSuccess
                                : cudaMemcpyAsync(dbuf.p, vec.data(), vec.size() * sizeof(vec[0]), cudaMemcpyHostToDevice, stream);
         };
-        CXB_CUDA(up(adj_off, off));
+        std::vector<uint32_t> tmp_v, tmp_p, tmp_d;
+        auto up_bin = [&](Bin& bin, const std::vector<Rec>& recs) -> cudaError_t {
+            tmp_v.resize(recs.size());
+            tmp_p.resize(recs.size());
+            tmp_d.resize(recs.size());
+            for (size_t i = 0; i < recs.size(); ++i) {
+                tmp_v[i] = recs[i].v;
+                tmp_p[i] = recs[i].p0;
+                tmp_d[i] = recs[i].d;
+            }
+            bin.n = (uint32_t)recs.size();
+            cudaError_t e = up(bin.v, tmp_v);
+            if (e == cudaSuccess) e = up(bin.p0, tmp_p);
+            if (e == cudaSuccess) e = up(bin.d, tmp_d);
+            if (e == cudaSuccess) e = cudaStreamSynchronize(stream);  // tmp_* are reused
+            return e;
+        };
+        CXB_CUDA(up_bin(exact_bin, ex));
+        for (int b = 0; b < N_TEAM_BINS; ++b) CXB_CUDA(up_bin(team_bin[b], tm[b]));
+        CXB_CUDA(up_bin(chunk_bin, chunks));
+        CXB_CUDA(up_bin(hub_bin, hub_recs));
         CXB_CUDA(up(opp, oppv));
         CXB_CUDA(up(tsel, sel));
         CXB_CUDA(up(slot_of_edge, slot));
-        CXB_CUDA(up(small_vars, sm));
-        CXB_CUDA(up(r8_vars, r8));
-        CXB_CUDA(up(r16_vars, r16));
-        CXB_CUDA(up(mid_vars, md));
-        CXB_CUDA(up(mid2_vars, md2));
-        CXB_CUDA(up(big_vars, bg));
+        size_t cb = std::max<size_t>(chunks.size(), 1) * K * esz();
+        CXB_CUDA(chunk_prod.reserve(cb));
+        CXB_CUDA(chunk_pre.reserve(cb));
+        CXB_CUDA(chunk_suf.reserve(cb));
         size_t pb = std::max<size_t>(P, 1) * K * esz(), nb = (size_t)n * K * esz();
         CXB_CUDA(m2f[0].reserve(pb));
         CXB_CUDA(m2f[1].reserve(pb));
@@ -489,45 +707,48 @@ struct Pairwise {
         have_msgs = true;
         return CXB_OK;
     }
+    template <class T, int KK, int G>
+    void launch_team(const PwView& g, size_t tb) {
+        constexpr int TL = G * PwGeo<KK>::L;
+        if constexpr (TL <= 32) {
+            const Bin& bin = team_bin[G == 1 ? 0 : G == 2 ? 1 : G == 4 ? 2 : G == 8 ? 3 : 4];
+            if (!bin.n) return;
+            if (tb > 48 * 1024)
+                cudaFuncSetAttribute(k_pw_team<T, KK, G, PW_MODE_FULL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tb);
+            CXB_LAUNCH((k_pw_team<T, KK, G, PW_MODE_FULL>), cdiv((size_t)bin.n * TL, 256), 256, tb, stream, g, bin.view());
+        }
+    }
+    template <class T, int KK, int G>
+    void launch_hubs(const PwView& g, size_t tb) {
+        constexpr int L = PwGeo<KK>::L, TL = G * L;
+        if constexpr (TL <= 32) {
+            if (G != g_max || !chunk_bin.n) return;
+            if (tb > 48 * 1024)
+                cudaFuncSetAttribute(k_pw_team<T, KK, G, PW_MODE_H1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tb);
+            CXB_LAUNCH((k_pw_team<T, KK, G, PW_MODE_H1>), cdiv((size_t)chunk_bin.n * TL, 256), 256, tb, stream, g, chunk_bin.view());
+            CXB_LAUNCH((k_pw_hub_scan<T, KK>), cdiv((size_t)hub_bin.n * L, 128), 128, 0, stream, g, hub_bin.view());
+            CXB_LAUNCH((k_pw_team<T, KK, G, PW_MODE_H3>), cdiv((size_t)chunk_bin.n * TL, 256), 256, 0, stream, g, chunk_bin.view());
+        }
+    }
     template <class T, int KK>
     int32_t launch_k(const PwView& g) {
         size_t tb = (size_t)n_tables * 2 * KK * KK * sizeof(T);
-        if (tb + 64 * KK * sizeof(T) > 200 * 1024) {
+        if (tb > 200 * 1024) {
             err = "tables do not fit in shared memory";
             return CXB_ERR_BAD_ARG;
         }
-        auto attr = [&](auto kern, size_t smem) {
-            if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        };
-        if (n_small) {
-            attr(k_pw_reg<T, KK, PW_SMALL_MAX>, tb);
-            CXB_LAUNCH((k_pw_reg<T, KK, PW_SMALL_MAX>), cdiv((size_t)n_small * KK, 256), 256, tb, stream, g, small_vars.p, n_small);
-        }
-        if (n_r8) {
-            attr(k_pw_reg<T, KK, 8>, tb);
-            CXB_LAUNCH((k_pw_reg<T, KK, 8>), cdiv((size_t)n_r8 * KK, 256), 256, tb, stream, g, r8_vars.p, n_r8);
-        }
-        if (n_r16) {
-            attr(k_pw_reg<T, KK, 16>, tb);
-            CXB_LAUNCH((k_pw_reg<T, KK, 16>), cdiv((size_t)n_r16 * KK, 256), 256, tb, stream, g, r16_vars.p, n_r16);
-        }
-        if (n_mid) {  // 17 .. 16*NG1 factors: one warp-sized CTA per variable, segments in registers
-            constexpr int NG = 32 / KK > 0 ? 32 / KK : 1;
-            size_t smem = tb + (size_t)NG * KK * sizeof(T);
-            attr(k_pw_hub16<T, KK, NG>, smem);
-            CXB_LAUNCH((k_pw_hub16<T, KK, NG>), std::min<uint32_t>(n_mid, 148u * 64u), NG * KK, smem, stream, g, mid_vars.p, n_mid);
-        }
-        if (n_mid2) {  // up to 16*(256/K) factors: 256-thread CTA, segments in registers
-            constexpr int NG = 256 / KK;
-            size_t smem = tb + (size_t)NG * KK * sizeof(T);
-            attr(k_pw_hub16<T, KK, NG>, smem);
-            CXB_LAUNCH((k_pw_hub16<T, KK, NG>), std::min<uint32_t>(n_mid2, 148u * 8u), NG * KK, smem, stream, g, mid2_vars.p, n_mid2);
-        }
-        if (n_big) {  // anything larger: 256-thread CTA, segments streamed
-            constexpr int NG = 256 / KK;
-            size_t smem = tb + (size_t)NG * KK * sizeof(T);
-            attr(k_pw_hub<T, KK, NG>, smem);
-            CXB_LAUNCH((k_pw_hub<T, KK, NG>), std::min<uint32_t>(n_big, 148u * 8u), NG * KK, smem, stream, g, big_vars.p, n_big);
+        // hubs first (their three dependent launches are the long pole), then the bins from heavy to light
+        launch_hubs<T, KK, 16>(g, tb);
+        launch_hubs<T, KK, 8>(g, tb);
+        launch_hubs<T, KK, 4>(g, tb);
+        launch_team<T, KK, 16>(g, tb);
+        launch_team<T, KK, 8>(g, tb);
+        launch_team<T, KK, 4>(g, tb);
+        launch_team<T, KK, 2>(g, tb);
+        launch_team<T, KK, 1>(g, tb);
+        if (exact_bin.n) {
+            if (tb > 48 * 1024) cudaFuncSetAttribute(k_pw_exact<T, KK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tb);
+            CXB_LAUNCH((k_pw_exact<T, KK>), cdiv((size_t)exact_bin.n * PwGeo<KK>::L, 256), 256, tb, stream, g, exact_bin.view());
         }
         return CXB_OK;
     }
@@ -549,7 +770,6 @@ struct Pairwise {
         CXB_CUDA(cudaSetDevice(device));
         PwView g;
         g.n_tables = n_tables;
-        g.adj_off = adj_off.p;
         g.opp = opp.p;
         g.tsel = tsel.p;
         g.tables = tables.p;
@@ -558,6 +778,9 @@ struct Pairwise {
         g.m2f_nxt = m2f[cur ^ 1].p;
         g.m2v = m2v.p;
         g.marg = marg.p;
+        g.chunk_prod = chunk_prod.p;
+        g.chunk_pre = chunk_pre.p;
+        g.chunk_suf = chunk_suf.p;
         CXB_CUDA(cudaEventRecord(ev0, stream));
         int32_t st = dtype == CXB_F32 ? launch_t<float>(g) : launch_t<double>(g);
         if (st) return st;

@@ -264,6 +264,30 @@ def _d2d(dst, src, nbytes):
     assert rt.cudaMemcpy(dst, src, nbytes, 3) == 0  # 3 = cudaMemcpyDeviceToDevice
 
 
+@pytest.mark.parametrize("dtype", [cap.F64, cap.F32])
+@pytest.mark.parametrize("B,T,chunks", [(1, 3, 8), (70, 9, 8), (1000, 33, 8), (1000, 33, 1), (4099, 17, 32)])
+def test_chain_batch_host_entry_point_is_bit_identical(dtype, B, T, chunks, monkeypatch):
+    """cxb_chains_infer_host (chunk-pipelined host->device / compute / device->host) == set_observations +
+    update_marginals + get_marginals, bit for bit, for ragged chunkings; repeated calls reuse the buffers safely."""
+    import torch
+
+    monkeypatch.setenv("CXB_CHAINS_HOST_CHUNKS", str(chunks))
+    rng = np.random.Generator(np.random.PCG64(99))
+    ch = C.GaussianChainBatch(B, T, dtype=dtype)
+    ch.set_noise(rng.uniform(0.5, 2.0, B), rng.uniform(0.5, 2.0, B))
+    tdt = torch.float32 if dtype == cap.F32 else torch.float64
+    for rep in range(2):
+        y = rng.standard_normal((T, B)).astype(ch.np_dtype)
+        ch.set_observations(y)
+        ch.update_marginals()
+        want = ch.get_messages(5).copy()
+        ch.set_observations(np.zeros_like(y))  # make sure the host path really uploads
+        y_host = torch.from_numpy(y.copy()).pin_memory()
+        out_host = torch.zeros((T, B, 2), dtype=tdt).pin_memory()
+        assert ch.infer_host(y_host.data_ptr(), out_host.data_ptr()) == B * (6 * T - 4)
+        np.testing.assert_array_equal(out_host.numpy(), want.reshape(T, B, 2))
+
+
 @pytest.mark.parametrize("dtype,K", [(cap.F32, 64), (cap.F64, 64), (cap.F32, 32), (cap.F32, 8), (cap.F32, 96)])
 def test_hmm_kernel_vs_oracle(oracle_api, dtype, K):
     B, T, M = 11, 40, 7
@@ -285,6 +309,53 @@ def test_hmm_kernel_vs_oracle(oracle_api, dtype, K):
         assert_close(got_m[:, b, :], want_m, dtype)
         want_f = C.get_values([C.get_connection_message_to_factor(e, z[t], tr[t]) for t in range(T - 1)])
         assert_close(got_f[:-1, b, :], want_f, dtype)
+
+
+def _hmm_numpy(A, E, obs):
+    """Independent dense fp64 scaled forward-backward: forward messages m2f(z_t, tr_t) and marginals, all normalised."""
+    T = len(obs)
+    K = A.shape[0]
+    En = E / E.sum(axis=0, keepdims=True)
+    fwd = np.zeros((T, K))
+    v = En[:, obs[0]].copy()
+    fwd[0] = v / v.sum()
+    for t in range(1, T):
+        v = En[:, obs[t]] * (fwd[t - 1] @ A)
+        fwd[t] = v / v.sum()
+    marg = np.zeros((T, K))
+    marg[T - 1] = fwd[T - 1]
+    w = En[:, obs[T - 1]].copy()
+    w /= w.sum()
+    for t in range(T - 2, -1, -1):
+        back = A @ w
+        g = fwd[t] * back
+        marg[t] = g / g.sum()
+        w = En[:, obs[t]] * back
+        w /= w.sum()
+    return fwd, marg
+
+
+@pytest.mark.parametrize("T,M", [(1, 3), (2, 3), (3, 3), (4, 5), (5, 5), (9, 32), (70, 100), (3000, 32)])
+def test_hmm64_kernel_lengths_and_long_chain_vs_numpy(T, M):
+    """K = 64 fp32 register kernel: the two-step-late write-out (T around the pipeline depth), emission tables in shared
+    memory (M <= 64) and in global memory, and the drift-free power-of-two scaling over a long chain."""
+    B, K = 5, 64
+    rng = np.random.Generator(np.random.PCG64(77))
+    A = rng.dirichlet(np.ones(K) * 0.3, size=K)
+    E = rng.dirichlet(np.ones(K) * 0.5, size=M).T * K
+    obs = rng.integers(0, M, size=(T, B)).astype(np.uint8)
+    hm = C.HmmBatch(B, T, K, M, dtype=cap.F32)
+    hm.set_tables(A, E)
+    hm.set_observations(obs)
+    assert hm.update_marginals() == B * (6 * T - 4)
+    got_m, got_f = hm.get_marginals(), hm.get_forward()
+    A_used = A.astype(np.float32).astype(np.float64)
+    for b in (0, B - 1):
+        want_f, want_m = _hmm_numpy(A_used, E, obs[:, b])
+        assert_close(got_f[:, b, :], want_f, cap.F32)
+        assert_close(got_m[:, b, :], want_m, cap.F32)
+        np.testing.assert_allclose(got_f[:, b, :].sum(axis=-1), 1.0, rtol=0, atol=2e-6)
+        np.testing.assert_allclose(got_m[:, b, :].sum(axis=-1), 1.0, rtol=0, atol=2e-6)
 
 
 def _pairwise_vs_oracle(oracle_api, dtype, n, edges, K, sweeps, seed=7):
@@ -341,6 +412,22 @@ def test_pairwise_kernel_powerlaw_vs_oracle(oracle_api, dtype, K):
     deg = np.bincount(np.asarray(edges).ravel(), minlength=n)
     assert deg.max() > 4 and deg.min() == 0 or deg.max() > 4  # small path + hub path both exercised
     _pairwise_vs_oracle(oracle_api, dtype, n, edges, K, sweeps=3)
+
+
+@pytest.mark.parametrize("K,dtype", [(8, cap.F32), (16, cap.F32), (32, cap.F32), (2, cap.F32), (4, cap.F64), (16, cap.F64)])
+def test_pairwise_kernel_every_degree_bin(oracle_api, K, dtype):
+    """Hubs whose degrees sit on both sides of every bin boundary of pairwise.cu (exact <= 4, teams of 1..16 groups of 8
+    slots, chunked hubs), all sharing one pool of leaves so that leaves have mixed small degrees."""
+    hub_degrees = [1, 3, 4, 5, 7, 8, 9, 15, 16, 17, 31, 32, 33, 63, 64, 65, 127, 128, 129, 200, 257, 300]
+    n_hubs, n_leaves = len(hub_degrees), 300
+    rng = np.random.Generator(np.random.PCG64(5))
+    edges = []
+    for h, d in enumerate(hub_degrees):
+        for leaf in sorted(rng.choice(n_leaves, size=d, replace=False)):
+            edges.append((h, n_hubs + int(leaf)))
+    edges += [(0, 1), (1, 2), (5, 9)]  # hub-hub factors
+    edges = sorted(set(edges))
+    _pairwise_vs_oracle(oracle_api, dtype, n_hubs + n_leaves + 2, edges, K, sweeps=2)
 
 
 def test_pairwise_kernel_big_hub_and_isolated_variables(oracle_api):
