@@ -12,9 +12,12 @@
 // go through the segment tree of src/dependencies.jl:90-173; here their exclusive products are computed by a
 // renormalised prefix/suffix scan — same values up to rounding, no tree nodes materialised).
 //
-// Layout: messages live in per-variable CSR order ("slot" p = position of (v,f) in v's adjacency), so everything a
-// variable WRITES (its m2v, m2f and marginal) is contiguous; the only irregular access is the gather of the
-// neighbour's previous m2f (one K*4-byte message = one 32-byte sector at K=8 fp32).  m2f is double buffered.
+// Layout: messages live in per-variable CSR order ("slot" p = position of (v,f) in v's adjacency).  m2f is stored in
+// the RECEIVER's order ("inbox": inbox[p] = the message the other endpoint of slot p's factor sends to that factor), so
+// everything a variable READS (inbox, unary, opp, tsel) and its m2v / marginal writes are contiguous streams; the only
+// irregular access is the scatter of the outgoing m2f into the neighbours' inboxes: one K*4-byte message = one full
+// 32-byte sector at K=8 fp32, fire-and-forget, nothing waits on it (a gather would cost 64 B of DRAM fetch per 32 B
+// and sit on the latency chain).  The inbox is double buffered.
 // Load balance by degree: variables with <= 4 pairwise factors are handled by a group of K lanes entirely in
 // registers (lane a owns state a, contractions by group shuffles); larger ones get one CTA each (NG groups scan
 // segments of the adjacency, partial products are combined through shared memory).
@@ -34,7 +37,11 @@ struct PwView {
     int n_tables;
     const uint32_t* opp;       // [P] slot of the opposite directed edge (the neighbour's message towards the same factor)
     const uint8_t* tsel;       // [P] table id * 2 + (1 if this variable is the HIGHER endpoint of the factor)
-    const void* tables;        // [n_tables][2][K][K]: [0] = psi[x_lo][x_hi], [1] = its transpose
+    const void* tables;        // bank-conflict-free shared-memory image of the tables (see Pairwise::set_tables)
+    int tab_elems;             // elements in the image
+    int tab_block;             // elements between the blocks of consecutive lanes (lane % 8 selects the block)
+    int tab_blocks;            // 8 (one block per lane of a 128-bit shared-load phase) or L (one block per lane of a group)
+    int tab_sel;               // elements between consecutive (table, orientation) selections inside a block
     const void* unary;         // [n][K]
     const void* m2f_cur;       // [P][K]
     void* m2f_nxt;             // [P][K]
@@ -214,8 +221,37 @@ __device__ __forceinline__ void contract(const T* rows, const T (&in)[K], T (&ou
 }
 template <class T>
 __device__ __forceinline__ void stage_tables(T* sh, const PwView& g, int K) {
-    for (int x = threadIdx.x; x < g.n_tables * 2 * K * K; x += blockDim.x) sh[x] = ((const T*)g.tables)[x];
+    for (int x = threadIdx.x; x < g.tab_elems; x += blockDim.x) sh[x] = ((const T*)g.tables)[x];
     __syncthreads();
+}
+// The lane's private view of the table image: block (lane % 8) % tab_blocks holds, for every selection, the S rows this
+// lane's states need; consecutive blocks start 16 bytes (4 banks) further round the 32 banks, so the 8 lanes of a
+// 128-bit load phase always hit 8 different bank groups whatever tables their slots use.
+template <class T>
+__device__ __forceinline__ const T* lane_tables(const T* sh, const PwView& g) {
+    return sh + (size_t)(((threadIdx.x & 7) % g.tab_blocks) * g.tab_block);
+}
+
+// ---- software pipeline of the persistent loops: the records of iteration i+2 are fetched into registers, the data of
+// iteration i+1 (whose records are already here) is pulled into L2, iteration i computes on L2 hits ---------------------------
+struct PwRec {
+    uint32_t v, p0, d;
+    bool live;
+};
+__device__ __forceinline__ PwRec load_rec(const PwBin& bin, uint32_t idx) {
+    PwRec r{0u, 0u, 0u, idx < bin.n};
+    if (r.live) {
+        r.v = __ldg(bin.v + idx);
+        r.p0 = __ldg(bin.p0 + idx);
+        r.d = __ldg(bin.d + idx);
+    }
+    return r;
+}
+__device__ __forceinline__ void prefetch_l2(const void* p, size_t bytes) {  // every 128-byte line of [p, p + bytes)
+    if (bytes == 0) return;
+    const char* c = reinterpret_cast<const char*>(p);
+    for (size_t o = 0; o < bytes; o += 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(c + o));
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(c + bytes - 1));
 }
 
 // ---- variables with <= 4 pairwise factors: one lane group per variable, the reference's n <= 5 path -----------------------
@@ -226,15 +262,30 @@ __global__ void __launch_bounds__(256) k_pw_exact(PwView g, PwBin bin) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     T* sh_tables = reinterpret_cast<T*>(smem_raw);
     stage_tables<T>(sh_tables, g, K);
-    const uint32_t gid = (blockIdx.x * blockDim.x + threadIdx.x) / L;
+    const T* my_tab = lane_tables<T>(sh_tables, g);
+    const int tab_sel = g.tab_sel;
     const int a0 = (threadIdx.x % L) * S;
-    const bool live = gid < bin.n;
-    uint32_t v = 0, p0 = 0, d = 0;
-    if (live) {
-        v = __ldg(bin.v + gid);
-        p0 = __ldg(bin.p0 + gid);
-        d = __ldg(bin.d + gid);
+    // persistent CTAs: the tables are staged once, then the CTA walks the bin with a grid stride (all CTAs work on
+    // neighbouring records at the same time, so the streamed arrays stay hot in L2)
+    const uint32_t per_cta = blockDim.x / L, stride = gridDim.x * per_cta, li = threadIdx.x % L;
+    const uint32_t first = blockIdx.x * per_cta + threadIdx.x / L;
+    PwRec cur = load_rec(bin, first), nxt = load_rec(bin, first + stride);
+    for (uint32_t base = blockIdx.x * per_cta; base < bin.n; base += stride) {
+    const PwRec nn = load_rec(bin, first + (base - blockIdx.x * per_cta) + 2 * stride);
+    if (nxt.live) {  // pull the next iteration's streams into L2 (lane 0 of the group: messages, last lane: indices)
+        if (li == 0) {
+            prefetch_l2((const T*)g.unary + (size_t)nxt.v * K, K * sizeof(T));
+            prefetch_l2((const T*)g.m2f_cur + (size_t)nxt.p0 * K, (size_t)nxt.d * K * sizeof(T));
+        }
+        if (li == L - 1) {
+            prefetch_l2(g.opp + nxt.p0, (size_t)nxt.d * sizeof(uint32_t));
+            prefetch_l2(g.tsel + nxt.p0, (size_t)nxt.d);
+        }
     }
+    const bool live = cur.live;
+    const uint32_t v = cur.v, p0 = cur.p0, d = cur.d;
+    cur = nxt;
+    nxt = nn;
     T un[S];
     vset<T, S>(un, T(1));
     if (live) ld_vec<T, S>((const T*)g.unary + (size_t)v * K + a0, un);
@@ -250,17 +301,20 @@ __global__ void __launch_bounds__(256) k_pw_exact(PwView g, PwBin bin) {
         }
     }
     T x[D][S];
+    T in[D][K];  // every incoming message is requested before the first one is used (one round trip, not D)
+#pragma unroll
+    for (int k = 0; k < D; ++k) {
+#pragma unroll
+        for (int i = 0; i < K; ++i) in[k][i] = T(1);
+        if ((uint32_t)k < d) ld_vec<T, K>((const T*)g.m2f_cur + (size_t)(p0 + k) * K, in[k]);
+    }
 #pragma unroll
     for (int k = 0; k < D; ++k) {
         vset<T, S>(x[k], T(1));
         const bool have = (uint32_t)k < d;
         if (!__any_sync(PW_FULL_MASK, have)) continue;
-        T in[K];
-#pragma unroll
-        for (int i = 0; i < K; ++i) in[i] = T(1);
-        if (have) ld_vec<T, K>((const T*)g.m2f_cur + (size_t)op[k] * K, in);
         T m[S];
-        contract<T, K>(sh_tables + ((size_t)sel[k] * K + a0) * K, in, m);
+        contract<T, K>(my_tab + sel[k] * tab_sel, in[k], m);
         norm1<T, K>(m);
         if (have) {
             st_vec<true, T, S>((T*)g.m2v + (size_t)(p0 + k) * K + a0, m);
@@ -285,8 +339,9 @@ __global__ void __launch_bounds__(256) k_pw_exact(PwView g, PwBin bin) {
         for (int j = 0; j < D; ++j)
             if (j != k) vmul<T, S>(o, x[j]);
         norm1<T, K>(o);
-        if (have) st_vec<true, T, S>((T*)g.m2f_nxt + (size_t)(p0 + k) * K + a0, o);
+        if (have) st_vec<true, T, S>((T*)g.m2f_nxt + (size_t)op[k] * K + a0, o);  // into the receiver's inbox
     }
+    }  // grid-stride loop
 }
 
 // ---- teams: G lane groups cooperate on one variable (FULL) or on one 8G-slot chunk of a hub (H1 / H3) -------------------
@@ -304,46 +359,75 @@ __global__ void __launch_bounds__(256) k_pw_team(PwView g, PwBin bin) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     T* sh_tables = reinterpret_cast<T*>(smem_raw);
     if (MODE != PW_MODE_H3) stage_tables<T>(sh_tables, g, K);
-    const uint32_t team = (blockIdx.x * blockDim.x + threadIdx.x) / TL;
+    const T* my_tab = lane_tables<T>(sh_tables, g);
+    const int tab_sel = g.tab_sel;
     const int tl = threadIdx.x % TL, grp = tl / L, a0 = (tl % L) * S;
-    const bool live = team < bin.n;
-    uint32_t v = 0, p0 = 0, d = 0;
-    if (live) {
-        v = __ldg(bin.v + team);
-        p0 = __ldg(bin.p0 + team);
-        d = __ldg(bin.d + team);
+    const uint32_t per_cta = blockDim.x / TL, stride = gridDim.x * per_cta, li = tl % L;
+    const uint32_t first = blockIdx.x * per_cta + threadIdx.x / TL;
+    PwRec cur = load_rec(bin, first), nxt = load_rec(bin, first + stride);
+    for (uint32_t base = blockIdx.x * per_cta; base < bin.n; base += stride) {
+    const uint32_t team = first + (base - blockIdx.x * per_cta);
+    const PwRec nn = load_rec(bin, team + 2 * stride);
+    if (nxt.live) {  // pull the next iteration's streams into L2 (lane 0 of the group: messages, last lane: indices)
+        const uint32_t nseg = (nxt.d + G - 1) / G, nlo = min(nxt.d, (uint32_t)grp * nseg), nn_loc = min(nxt.d, nlo + nseg) - nlo;
+        const uint32_t npb = nxt.p0 + nlo;
+        if (li == 0) {
+            if (MODE == PW_MODE_FULL && grp == 0) prefetch_l2((const T*)g.unary + (size_t)nxt.v * K, K * sizeof(T));
+            if (MODE != PW_MODE_H3)
+                prefetch_l2((const T*)g.m2f_cur + (size_t)npb * K, (size_t)nn_loc * K * sizeof(T));
+            else
+                prefetch_l2((const T*)g.m2v + (size_t)npb * K, (size_t)nn_loc * K * sizeof(T));
+        }
+        if (li == L - 1) {
+            if (MODE != PW_MODE_H1) prefetch_l2(g.opp + npb, (size_t)nn_loc * sizeof(uint32_t));
+            if (MODE != PW_MODE_H3) prefetch_l2(g.tsel + npb, (size_t)nn_loc);
+        }
     }
+    const bool live = cur.live;
+    const uint32_t v = cur.v, p0 = cur.p0, d = cur.d;
+    cur = nxt;
+    nxt = nn;
     const uint32_t seg = (d + G - 1) / G;  // <= SEG by construction of the bins
     const uint32_t lo = min(d, (uint32_t)grp * seg), n_loc = min(d, lo + seg) - lo;
     const uint32_t pb = p0 + lo;
     T x[SEG][S];
+    uint32_t op[SEG];  // the receiver's slot of each outgoing m2f (not needed by H1)
+#pragma unroll
+    for (int k = 0; k < SEG; ++k) {
+        op[k] = 0;
+        if (MODE != PW_MODE_H1 && (uint32_t)k < n_loc) op[k] = __ldg(g.opp + pb + k);
+    }
     if (MODE != PW_MODE_H3) {
-        uint32_t op[SEG];
         int sel[SEG];
 #pragma unroll
         for (int k = 0; k < SEG; ++k) {
-            op[k] = 0;
             sel[k] = 0;
-            if ((uint32_t)k < n_loc) {
-                op[k] = __ldg(g.opp + pb + k);
-                sel[k] = __ldg(g.tsel + pb + k);
-            }
+            if ((uint32_t)k < n_loc) sel[k] = __ldg(g.tsel + pb + k);
         }
 #pragma unroll
-        for (int k = 0; k < SEG; ++k) {
-            vset<T, S>(x[k], T(1));
-            const bool have = (uint32_t)k < n_loc;
-            if (!__any_sync(PW_FULL_MASK, have)) continue;
-            T in[K];
+        for (int k = 0; k < SEG; ++k) vset<T, S>(x[k], T(1));
+        constexpr int HB = 4;  // incoming messages requested together (one round trip per batch)
 #pragma unroll
-            for (int i = 0; i < K; ++i) in[i] = T(1);
-            if (have) ld_vec<T, K>((const T*)g.m2f_cur + (size_t)op[k] * K, in);
-            T m[S];
-            contract<T, K>(sh_tables + ((size_t)sel[k] * K + a0) * K, in, m);
-            norm1<T, K>(m);
-            if (have) {
-                st_vec<MODE == PW_MODE_FULL, T, S>((T*)g.m2v + (size_t)(pb + k) * K + a0, m);
-                vcopy<T, S>(x[k], m);
+        for (int h = 0; h < SEG; h += HB) {
+            if (!__any_sync(PW_FULL_MASK, (uint32_t)h < n_loc)) continue;
+            T in[HB][K];
+#pragma unroll
+            for (int kk = 0; kk < HB; ++kk) {
+#pragma unroll
+                for (int i = 0; i < K; ++i) in[kk][i] = T(1);
+                if ((uint32_t)(h + kk) < n_loc) ld_vec<T, K>((const T*)g.m2f_cur + (size_t)(pb + h + kk) * K, in[kk]);
+            }
+#pragma unroll
+            for (int kk = 0; kk < HB; ++kk) {
+                const int k = h + kk;
+                const bool have = (uint32_t)k < n_loc;
+                T m[S];
+                contract<T, K>(my_tab + sel[k] * tab_sel, in[kk], m);
+                norm1<T, K>(m);
+                if (have) {
+                    st_vec<MODE == PW_MODE_FULL, T, S>((T*)g.m2v + (size_t)(pb + k) * K + a0, m);
+                    vcopy<T, S>(x[k], m);
+                }
             }
         }
     } else {
@@ -379,7 +463,7 @@ __global__ void __launch_bounds__(256) k_pw_team(PwView g, PwBin bin) {
     }
     if (MODE == PW_MODE_H1) {
         if (live && grp == G - 1) st_vec<false, T, S>((T*)g.chunk_prod + (size_t)team * K + a0, inc);
-        return;
+        continue;
     }
     // exclusive suffix over the groups
     T sinc[S], sexc[S];
@@ -437,10 +521,11 @@ __global__ void __launch_bounds__(256) k_pw_team(PwView g, PwBin bin) {
         vcopy<T, S>(o, pre[k]);
         vmul<T, S>(o, suf);
         norm1<T, K>(o);
-        if (have) st_vec<true, T, S>((T*)g.m2f_nxt + (size_t)(pb + k) * K + a0, o);
+        if (have) st_vec<true, T, S>((T*)g.m2f_nxt + (size_t)op[k] * K + a0, o);  // into the receiver's inbox
         vmul<T, S>(suf, x[k]);
         if (k & 1) rescale<T, K>(suf);
     }
+    }  // grid-stride loop
 }
 
 // ---- hub pass 2: one lane group per hub scans the products of its chunks (prefix includes the unary), writes the marginal
@@ -505,9 +590,9 @@ __global__ void k_pw_fill(T* p, size_t n, T v) {
 }
 // gather per-slot planes into factor order: out[2f + side] = plane[slot_of_edge[2f + side]]
 template <class T>
-__global__ void k_pw_gather(const T* plane, const uint32_t* slot_of_edge, T* out, size_t n_edges, int K) {
+__global__ void k_pw_gather(const T* plane, const uint32_t* slot_of_edge, T* out, size_t n_edges, int K, int flip) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n_edges * K) out[i] = plane[(size_t)slot_of_edge[i / K] * K + (i % K)];
+    if (i < n_edges * K) out[i] = plane[(size_t)slot_of_edge[(i / K) ^ (size_t)flip] * K + (i % K)];
 }
 
 struct Pairwise {
@@ -528,6 +613,7 @@ struct Pairwise {
     DBuf<uint8_t> tsel;
     DBuf<unsigned char> tables, unary, m2f[2], m2v, marg, scratch, chunk_prod, chunk_pre, chunk_suf;
     int g_max = 16;  // largest team (groups) that fits one warp at this K
+    int n_sm = 148;
     long long n_products = 0;
     bool have_graph = false, have_tables = false, have_unary = false, have_msgs = false, ran = false;
     size_t esz() const { return dtype == CXB_F32 ? 4 : 8; }
@@ -548,9 +634,17 @@ struct Pairwise {
             return CXB_ERR_BAD_ARG;
         }
         CXB_CUDA(cudaSetDevice(device));
+        if (const char* e = getenv("CXB_L2_FETCH")) {  // tuning knob: L2 -> DRAM fetch granularity hint (32 / 64 / 128 bytes)
+            size_t before = 0, after = 0;
+            cudaDeviceGetLimit(&before, cudaLimitMaxL2FetchGranularity);
+            cudaError_t le = cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)atoi(e));
+            cudaDeviceGetLimit(&after, cudaLimitMaxL2FetchGranularity);
+            fprintf(stderr, "cxb_pairwise: L2 fetch granularity %zu -> %zu (%s)\n", before, after, cudaGetErrorString(le));
+        }
         CXB_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
         CXB_CUDA(cudaEventCreate(&ev0));
         CXB_CUDA(cudaEventCreate(&ev1));
+        CXB_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, device));
         return CXB_OK;
     }
     int32_t set_graph(const int64_t* fu, const int64_t* fv, const int32_t* ft) {
@@ -577,8 +671,8 @@ struct Pairwise {
             sel[pu] = (uint8_t)(ft[f] * 2 + 0);  // u is the lower endpoint
             sel[pv] = (uint8_t)(ft[f] * 2 + 1);
         }
-        // degree bins (records sorted by degree inside a bin, ascending id inside a degree: the lanes of a warp then run
-        // the same trip counts and neighbouring records still gather from neighbouring slots of the same hubs):
+        // degree bins (records in ascending variable id inside a bin, so that the per-variable arrays — unary, opp, tsel, the
+        // inbox and everything written — stream; sorting by degree made warps uniform but cost 2x the DRAM reads):
         //   <= 4 factors: exact path; <= 8G: team of G groups, G = 1 .. g_max; larger: hub, cut into chunks of 8 g_max slots
         const int lanes = K / std::min(K, 4);
         g_max = std::min(16, 32 / lanes);
@@ -605,8 +699,16 @@ struct Pairwise {
             tm[b].push_back(r);
         }
         auto by_degree_desc = [](const Rec& x, const Rec& y) { return x.d > y.d; };
-        std::stable_sort(ex.begin(), ex.end(), by_degree_desc);
-        for (auto& t : tm) std::stable_sort(t.begin(), t.end(), by_degree_desc);
+        // ...but inside windows of 4,096 records the records ARE sorted by degree: the lanes of a warp then run the same
+        // trip counts, and a window's lines are all consumed while they are still in L2
+        size_t window = 4096;
+        if (const char* e = getenv("CXB_PW_WINDOW")) window = (size_t)std::max(1, atoi(e));
+        auto window_sort = [&](std::vector<Rec>& recs) {
+            for (size_t i = 0; i < recs.size(); i += window)
+                std::stable_sort(recs.begin() + i, recs.begin() + std::min(recs.size(), i + window), by_degree_desc);
+        };
+        window_sort(ex);
+        for (auto& t : tm) window_sort(t);
         std::stable_sort(hubs.begin(), hubs.end(), by_degree_desc);
         std::vector<Rec> hub_recs;  // v, first chunk, number of chunks
         for (const Rec& h : hubs) {
@@ -656,34 +758,47 @@ struct Pairwise {
         CXB_CUDA(scratch.reserve(pb));
         CXB_CUDA(marg.reserve(nb));
         CXB_CUDA(unary.reserve(nb));
-        CXB_CUDA(tables.reserve((size_t)n_tables * 2 * K * K * esz()));
         CXB_CUDA(cudaMemsetAsync(m2v.p, 0, pb, stream));
         CXB_CUDA(cudaMemsetAsync(marg.p, 0, nb, stream));
         CXB_CUDA(cudaStreamSynchronize(stream));
         have_graph = true;
         return CXB_OK;
     }
+    // Shared-memory image of the tables. Selection sel = 2 * table + side: side 0 (this variable is the lower endpoint of
+    // the factor) needs rows of psi, side 1 rows of its transpose: row a of selection sel, column b = weight of in[b] for
+    // output state a. A lane owns S = min(K, 4) consecutive states, the L = K / S lanes of a group own different rows.
+    // Block j (j = lane % 8) holds rows [(j % L) S, (j % L) S + S) of every selection, selections tab_sel elements apart
+    // (a multiple of 128 bytes); blocks are tab_block = plane + 16 bytes apart, so block j starts 4 j banks round.
+    int tab_elems = 0, tab_block = 0, tab_blocks = 0, tab_sel = 0;
     int32_t set_tables(const double* tb) {
         if (!have_graph) {
             err = "set the graph first";
             return CXB_ERR_STATE;
         }
         CXB_CUDA(cudaSetDevice(device));
-        size_t cnt = (size_t)n_tables * 2 * K * K;
-        std::vector<unsigned char> raw(cnt * esz());
-        for (int t = 0; t < n_tables; ++t)
-            for (int i = 0; i < K; ++i)
-                for (int j = 0; j < K; ++j) {
-                    double v = tb[((size_t)t * K + i) * K + j];
-                    size_t o0 = (((size_t)t * 2 + 0) * K + i) * K + j, o1 = (((size_t)t * 2 + 1) * K + j) * K + i;
-                    if (dtype == CXB_F32) {
-                        ((float*)raw.data())[o0] = (float)v;
-                        ((float*)raw.data())[o1] = (float)v;
-                    } else {
-                        ((double*)raw.data())[o0] = v;
-                        ((double*)raw.data())[o1] = v;
+        const int S = std::min(K, 4), L = K / S, QE = 16 / (int)esz(), n_sel = 2 * n_tables;
+        tab_sel = (S * K + 8 * QE - 1) / (8 * QE) * (8 * QE);
+        tab_block = n_sel * tab_sel + QE;
+        tab_blocks = (size_t)8 * tab_block * esz() <= 96 * 1024 ? 8 : L;
+        tab_elems = tab_blocks * tab_block;
+        if ((size_t)tab_elems * esz() > 200 * 1024) {
+            err = "tables do not fit in shared memory";
+            return CXB_ERR_BAD_ARG;
+        }
+        std::vector<unsigned char> raw((size_t)tab_elems * esz(), 0);
+        for (int j = 0; j < tab_blocks; ++j)
+            for (int sel = 0; sel < n_sel; ++sel)
+                for (int r = 0; r < S; ++r)
+                    for (int bcol = 0; bcol < K; ++bcol) {
+                        const int t = sel >> 1, a = (j % L) * S + r;
+                        const double v = (sel & 1) ? tb[((size_t)t * K + bcol) * K + a] : tb[((size_t)t * K + a) * K + bcol];
+                        const size_t o = (size_t)j * tab_block + (size_t)sel * tab_sel + (size_t)r * K + bcol;
+                        if (dtype == CXB_F32)
+                            ((float*)raw.data())[o] = (float)v;
+                        else
+                            ((double*)raw.data())[o] = v;
                     }
-                }
+        CXB_CUDA(tables.reserve(raw.size()));
         CXB_CUDA(cudaMemcpyAsync(tables.p, raw.data(), raw.size(), cudaMemcpyHostToDevice, stream));
         CXB_CUDA(cudaStreamSynchronize(stream));
         have_tables = true;
@@ -707,6 +822,8 @@ struct Pairwise {
         have_msgs = true;
         return CXB_OK;
     }
+    // persistent CTAs of 256 threads: at most 8 per SM (fewer are resident when registers limit it; the rest queue)
+    unsigned grid_for(size_t threads) const { return std::min<unsigned>(cdiv(threads, 256), (unsigned)n_sm * 8u); }
     template <class T, int KK, int G>
     void launch_team(const PwView& g, size_t tb) {
         constexpr int TL = G * PwGeo<KK>::L;
@@ -715,7 +832,7 @@ struct Pairwise {
             if (!bin.n) return;
             if (tb > 48 * 1024)
                 cudaFuncSetAttribute(k_pw_team<T, KK, G, PW_MODE_FULL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tb);
-            CXB_LAUNCH((k_pw_team<T, KK, G, PW_MODE_FULL>), cdiv((size_t)bin.n * TL, 256), 256, tb, stream, g, bin.view());
+            CXB_LAUNCH((k_pw_team<T, KK, G, PW_MODE_FULL>), grid_for((size_t)bin.n * TL), 256, tb, stream, g, bin.view());
         }
     }
     template <class T, int KK, int G>
@@ -725,18 +842,14 @@ struct Pairwise {
             if (G != g_max || !chunk_bin.n) return;
             if (tb > 48 * 1024)
                 cudaFuncSetAttribute(k_pw_team<T, KK, G, PW_MODE_H1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tb);
-            CXB_LAUNCH((k_pw_team<T, KK, G, PW_MODE_H1>), cdiv((size_t)chunk_bin.n * TL, 256), 256, tb, stream, g, chunk_bin.view());
+            CXB_LAUNCH((k_pw_team<T, KK, G, PW_MODE_H1>), grid_for((size_t)chunk_bin.n * TL), 256, tb, stream, g, chunk_bin.view());
             CXB_LAUNCH((k_pw_hub_scan<T, KK>), cdiv((size_t)hub_bin.n * L, 128), 128, 0, stream, g, hub_bin.view());
-            CXB_LAUNCH((k_pw_team<T, KK, G, PW_MODE_H3>), cdiv((size_t)chunk_bin.n * TL, 256), 256, 0, stream, g, chunk_bin.view());
+            CXB_LAUNCH((k_pw_team<T, KK, G, PW_MODE_H3>), grid_for((size_t)chunk_bin.n * TL), 256, 0, stream, g, chunk_bin.view());
         }
     }
     template <class T, int KK>
     int32_t launch_k(const PwView& g) {
-        size_t tb = (size_t)n_tables * 2 * KK * KK * sizeof(T);
-        if (tb > 200 * 1024) {
-            err = "tables do not fit in shared memory";
-            return CXB_ERR_BAD_ARG;
-        }
+        size_t tb = (size_t)tab_elems * sizeof(T);
         // hubs first (their three dependent launches are the long pole), then the bins from heavy to light
         launch_hubs<T, KK, 16>(g, tb);
         launch_hubs<T, KK, 8>(g, tb);
@@ -748,7 +861,7 @@ struct Pairwise {
         launch_team<T, KK, 1>(g, tb);
         if (exact_bin.n) {
             if (tb > 48 * 1024) cudaFuncSetAttribute(k_pw_exact<T, KK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tb);
-            CXB_LAUNCH((k_pw_exact<T, KK>), cdiv((size_t)exact_bin.n * PwGeo<KK>::L, 256), 256, tb, stream, g, exact_bin.view());
+            CXB_LAUNCH((k_pw_exact<T, KK>), grid_for((size_t)exact_bin.n * PwGeo<KK>::L), 256, tb, stream, g, exact_bin.view());
         }
         return CXB_OK;
     }
@@ -773,6 +886,10 @@ struct Pairwise {
         g.opp = opp.p;
         g.tsel = tsel.p;
         g.tables = tables.p;
+        g.tab_elems = tab_elems;
+        g.tab_block = tab_block;
+        g.tab_blocks = tab_blocks;
+        g.tab_sel = tab_sel;
         g.unary = unary.p;
         g.m2f_cur = m2f[cur].p;
         g.m2f_nxt = m2f[cur ^ 1].p;
@@ -792,15 +909,17 @@ struct Pairwise {
         return CXB_OK;
     }
     // per-edge planes in factor order: out[(2f + side)][K], side 0 = the lower endpoint u, 1 = v
-    int32_t get_edges(const unsigned char* plane, void* out_host) {
+    int32_t get_edges(const unsigned char* plane, void* out_host, bool inbox) {
         CXB_CUDA(cudaSetDevice(device));
         size_t E = (size_t)2 * m;
         if (E) {
+            const int flip = inbox ? 1 : 0;  // m2f(v, f) is stored in the inbox slot of the OTHER endpoint of f
             if (dtype == CXB_F32)
-                CXB_LAUNCH(k_pw_gather<float>, cdiv(E * K, 256), 256, 0, stream, (const float*)plane, slot_of_edge.p, (float*)scratch.p, E, K);
+                CXB_LAUNCH(k_pw_gather<float>, cdiv(E * K, 256), 256, 0, stream, (const float*)plane, slot_of_edge.p, (float*)scratch.p, E, K,
+                           flip);
             else
                 CXB_LAUNCH(k_pw_gather<double>, cdiv(E * K, 256), 256, 0, stream, (const double*)plane, slot_of_edge.p, (double*)scratch.p,
-                           E, K);
+                           E, K, flip);
             CXB_CUDA(cudaMemcpyAsync(out_host, scratch.p, E * K * esz(), cudaMemcpyDeviceToHost, stream));
         }
         CXB_CUDA(cudaStreamSynchronize(stream));
@@ -881,7 +1000,7 @@ int32_t cxb_pairwise_get_messages(cxb_pairwise* g, int32_t which, void* out_host
         h->err = "which must be 0 (m2v) or 1 (m2f)";
         return CXB_ERR_BAD_ARG;
     }
-    return h->get_edges(which == 0 ? h->m2v.p : h->m2f[h->cur].p, out_host);
+    return h->get_edges(which == 0 ? h->m2v.p : h->m2f[h->cur].p, out_host, which == 1);
 }
 int64_t cxb_pairwise_algorithmic_bytes(cxb_pairwise* g) {
     Pairwise* h = PW(g);
