@@ -42,8 +42,6 @@ __device__ __forceinline__ typename Vec2<T>::type mk2(T a, T b) {
     return v;
 }
 
-constexpr int CH_TILE = 8;    // time steps whose loads are in flight together (double buffered)
-constexpr int CH_BLOCK = 64;  // 65,536 chains -> 1,024 CTAs = 6.9 per SM: <1.2% imbalance over 148 SMs
 
 // msg: [6][T][B] of (L,h) pairs. Classes: 0 m2v(x_t,lik_t)  1 m2v(x_t,tr_{t-1})  2 m2f(x_t,tr_t)
 //                                          3 m2v(x_t,tr_t)   4 m2f(x_t,tr_{t-1})  5 marginal(x_t)

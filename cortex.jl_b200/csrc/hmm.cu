@@ -17,7 +17,10 @@
 #include <cmath>
 #include <type_traits>
 
+#include <cstring>
+
 #include "common.cuh"
+#include "hmm_tc.cuh"
 
 namespace cxb {
 
@@ -390,6 +393,16 @@ struct Hmm {
     std::string err;
     DBuf<unsigned char> A, At, En, fwd, marg;
     DBuf<uint8_t> obs;
+    // tensor-core path (hmm_tc.cuh): table images (forward: rows of A^T, backward: rows of A), message operands, row sums
+    DBuf<uint16_t> tc_img_f, tc_img_b, tc_op[2];
+    DBuf<float> tc_part[2];
+    bool tc_ready = false;
+    bool tc_eligible() const {
+        if (const char* e = getenv("CXB_HMM_NO_TC"))
+            if (atoi(e)) return false;
+        return dtype == CXB_F32 && K % 64 == 0 && K >= 128 && K <= tc::MAX_K && M <= 64;
+    }
+    long long tc_bpad() const { return (B + tc::M_TILE - 1) / tc::M_TILE * tc::M_TILE; }
     bool have_tables = false, have_obs = false, ran = false;
     size_t esz() const { return dtype == CXB_F32 ? 4 : 8; }
     ~Hmm() {
@@ -445,6 +458,25 @@ struct Hmm {
         CXB_CUDA(cudaMemcpyAsync(A.p, a.data(), a.size(), cudaMemcpyHostToDevice, stream));
         CXB_CUDA(cudaMemcpyAsync(At.p, at.data(), at.size(), cudaMemcpyHostToDevice, stream));
         CXB_CUDA(cudaMemcpyAsync(En.p, en.data(), en.size(), cudaMemcpyHostToDevice, stream));
+        if (tc_eligible()) {
+            std::vector<uint16_t> img;
+            tc::build_table_image((const float*)at.data(), K, img);  // forward: pred[j] = sum_i msg[i] A[i][j] -> rows of A^T
+            CXB_CUDA(tc_img_f.reserve(img.size()));
+            CXB_CUDA(cudaMemcpyAsync(tc_img_f.p, img.data(), img.size() * 2, cudaMemcpyHostToDevice, stream));
+            CXB_CUDA(cudaStreamSynchronize(stream));
+            tc::build_table_image((const float*)a.data(), K, img);   // backward: pred[j] = sum_i A[j][i] msg[i] -> rows of A
+            CXB_CUDA(tc_img_b.reserve(img.size()));
+            CXB_CUDA(cudaMemcpyAsync(tc_img_b.p, img.data(), img.size() * 2, cudaMemcpyHostToDevice, stream));
+            const long long bpad = tc_bpad();
+            const size_t op_elems = (size_t)(bpad / tc::M_TILE) * 2 * (K / tc::K_CHUNK) * (tc::A_CHUNK_BYTES / 2);
+            for (int i = 0; i < 2; ++i) {
+                CXB_CUDA(tc_op[i].reserve(op_elems));
+                CXB_CUDA(tc_part[i].reserve((size_t)2 * (K / tc::N_TILE) * bpad));
+                CXB_CUDA(cudaMemsetAsync(tc_op[i].p, 0, op_elems * 2, stream));
+                CXB_CUDA(cudaMemsetAsync(tc_part[i].p, 0, (size_t)2 * (K / tc::N_TILE) * bpad * sizeof(float), stream));
+            }
+            tc_ready = true;
+        }
         CXB_CUDA(cudaStreamSynchronize(stream));
         have_tables = true;
         return CXB_OK;
@@ -460,6 +492,80 @@ struct Hmm {
                    (T*)fwd.p, (T*)marg.p, B, this->T, K, M, tile_rows);
         CXB_LAUNCH((k_hmm_pass<T, KK, REGA, false>), grid, HMM_WARPS * 32, smem, stream, (const T*)At.p, (const T*)En.p, obs.p,
                    (T*)fwd.p, (T*)marg.p, B, this->T, K, M, tile_rows);
+        return CXB_OK;
+    }
+    // one launch per time step and pass (hmm_tc.cuh); 2 T + 4 launches
+    int32_t launch_tc() {
+        const int bpad = (int)tc_bpad(), tiles = bpad / tc::M_TILE, n_slices = K / tc::N_TILE;
+        const size_t smem = tc::step_smem_bytes(K, M), row = (size_t)B * K;
+        CXB_CUDA(cudaFuncSetAttribute(tc::k_hmm_tc_step<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CXB_CUDA(cudaFuncSetAttribute(tc::k_hmm_tc_step<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        float *fw = (float*)fwd.p, *mg = (float*)marg.p;
+        tc::StepArgs a{};
+        a.emis_n = (const float*)En.p;
+        a.B = (int)B;
+        a.Bpad = bpad;
+        a.K = K;
+        a.n_sym = M;
+        const dim3 grid(tiles, n_slices), igrid(bpad / 128, n_slices);
+        DBuf<long long> trace;
+        const bool tracing = getenv("CXB_HMM_TC_TRACE") && atoi(getenv("CXB_HMM_TC_TRACE"));
+        const bool pdl = !(getenv("CXB_HMM_TC_NO_PDL") && atoi(getenv("CXB_HMM_TC_NO_PDL")));
+        if (tracing) {
+            CXB_CUDA(trace.reserve((size_t)tiles * n_slices * 16));
+            CXB_CUDA(cudaMemsetAsync(trace.p, 0, (size_t)tiles * n_slices * 16 * sizeof(long long), stream));
+            a.trace = trace.p;
+        }
+        for (int pass = 0; pass < 2; ++pass) {
+            const bool f = pass == 0;
+            a.tbl_img = (const __nv_bfloat16*)(f ? tc_img_f.p : tc_img_b.p);
+            float* out = f ? fw : mg;
+            for (long long s = 0; s < this->T; ++s) {
+                const long long t = f ? s : this->T - 1 - s, tp = f ? t - 1 : t + 1;
+                a.op_in = (const __nv_bfloat16*)tc_op[(s + 1) & 1].p;
+                a.op_out = (__nv_bfloat16*)tc_op[s & 1].p;
+                a.part_in = tc_part[(s + 1) & 1].p;
+                a.part_out = tc_part[s & 1].p;
+                a.obs_t = obs.p + (size_t)t * B;
+                a.raw_out = out + (size_t)t * row;
+                a.raw_prev = s ? out + (size_t)tp * row : nullptr;
+                a.fwd_t = f ? nullptr : fw + (size_t)t * row;
+                if (s == 0) {
+                    if (f)
+                        CXB_LAUNCH(tc::k_hmm_tc_init<true>, igrid, 128, 0, stream, a);
+                    else
+                        CXB_LAUNCH(tc::k_hmm_tc_init<false>, igrid, 128, 0, stream, a);
+                } else {
+                    cudaLaunchConfig_t cfg{};
+                    cfg.gridDim = grid;
+                    cfg.blockDim = dim3(tc::THREADS);
+                    cfg.dynamicSmemBytes = smem;
+                    cfg.stream = stream;
+                    cudaLaunchAttribute attr[1];
+                    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+                    attr[0].val.programmaticStreamSerializationAllowed = pdl ? 1 : 0;
+                    cfg.attrs = attr;
+                    cfg.numAttrs = 1;
+                    CXB_CUDA(cudaLaunchKernelEx(&cfg, f ? tc::k_hmm_tc_step<true> : tc::k_hmm_tc_step<false>, a));
+                    ++::cxb::g_kernel_launches;
+                }
+            }
+            const long long t_last = f ? this->T - 1 : 0;
+            CXB_LAUNCH(tc::k_hmm_tc_finish, (unsigned)B, 128, 0, stream, out + (size_t)t_last * row, tc_part[(this->T - 1) & 1].p, (int)B,
+                       bpad, K);
+        }
+        if (tracing) {  // stamps of the LAST step kernel of the backward pass, averaged over the CTAs, relative to CTA start
+            std::vector<long long> h((size_t)tiles * n_slices * 16);
+            CXB_CUDA(cudaStreamSynchronize(stream));
+            CXB_CUDA(cudaMemcpy(h.data(), trace.p, h.size() * sizeof(long long), cudaMemcpyDeviceToHost));
+            static const char* names[10] = {"start", "init+alloc done", "producer issued all", "mma: first chunk landed", "mma: last chunk landed",
+                                            "mma: all issued", "epi: prev normalised", "epi: accumulator ready", "epi: done", "exit"};
+            for (int k = 0; k < 10; ++k) {
+                double acc = 0;
+                for (int c = 0; c < tiles * n_slices; ++c) acc += (double)(h[(size_t)c * 16 + k] - h[(size_t)c * 16]);
+                fprintf(stderr, "cxb_hmm tc trace: %-26s %8.0f cycles\n", names[k], acc / (tiles * n_slices));
+            }
+        }
         return CXB_OK;
     }
     int32_t launch_k64() {
@@ -486,6 +592,7 @@ struct Hmm {
     int32_t launch_t() {
         size_t stage = ((size_t)HMM_WARPS * K + (size_t)M * K) * sizeof(T);  // per-warp staging + emission messages
         if (sizeof(T) == 4 && K == 64) return launch_k64();
+        if (sizeof(T) == 4 && tc_ready && tc_eligible()) return launch_tc();
         if (K == 32) return launch_pair<T, 32, true>(0, stage);
         size_t budget = 200 * 1024 - stage;
         int tile_rows = (int)std::min<size_t>((size_t)K, budget / ((size_t)K * sizeof(T)));

@@ -1,0 +1,422 @@
+// hmm_tc.cuh — tensor-core (tcgen05 + TMEM) path of the HMM engine for large state counts (BASELINE config 3, K = 512).
+//
+// At K >= 128 one time step of a batch of chains is a dense GEMM: pred[chain][j] = sum_i msg[chain][i] * Tbl[i][j]
+// (Tbl = A forward, A^T backward), followed by the elementwise categorical rules (emission product, marginal product,
+// normalisation).  One kernel launch = one time step of every chain (the launch boundary is the only grid-wide
+// synchronisation the recursion needs):
+//   * CTA (tile, slice) owns 128 chains (MMA M) x 64 output states (MMA N) and the full reduction over K input states;
+//   * operands are bf16 "split" pairs (hi = bf16(x), lo = bf16(x - hi)); the product is accumulated in fp32 in TMEM as
+//     hi*hi + hi*lo + lo*hi (3 x tcgen05.mma.kind::f16 per 16 input states; relative error ~2^-17 per term);
+//   * both operands stream through a 4-stage shared-memory ring (192 KB in flight per SM: the bulk-copy latency, not the
+//     MMA, is what a step waits on) by 1-D bulk async copies (cp.async.bulk, completion on mbarriers) of images that are ALREADY
+//     in the canonical K-major / no-swizzle UMMA layout: the table slices are formatted once on the host, the message
+//     operand of step t+1 is written in that layout by the epilogue of step t (so nothing is converted on the way in);
+//   * warp roles: warps 0-3 epilogue (TMEM -> registers, rules, stores) and, while the MMAs run, the exact
+//     normalisation of the PREVIOUS step's output; warp 4 bulk-copy producer; warp 5 MMA issuer (one elected thread);
+//   * normalisation is deferred exactly as in the K = 64 kernel: the carried message is scaled by the power of two
+//     2^-floor(log2 sum(prev)), each step writes its unnormalised result plus per-slice row sums, and the next launch
+//     (or the finishing kernel) divides by the exact total.
+#pragma once
+#include <cuda_bf16.h>
+
+#include "common.cuh"
+
+namespace cxb {
+namespace tc {
+
+constexpr int M_TILE = 128;   // chains per CTA (MMA M)
+constexpr int N_TILE = 64;    // output states per CTA (MMA N)
+constexpr int K_CHUNK = 64;   // input states per operand chunk (4 MMA K-steps of 16)
+constexpr int STAGES = 4;     // operand chunks in flight (48 KB each: message hi/lo 2 x 16 KB + table hi/lo 2 x 8 KB)
+constexpr int THREADS = 192;  // 4 epilogue warps + producer warp + MMA warp
+constexpr int MAX_K = 2048;   // any multiple of 64 up to here (both operands stream through the ring)
+constexpr uint32_t A_CHUNK_BYTES = M_TILE * K_CHUNK * 2;  // 16 KB per hi / lo
+constexpr uint32_t B_CHUNK_BYTES = N_TILE * K_CHUNK * 2;  //  8 KB per hi / lo
+constexpr uint32_t STAGE_BYTES = 2 * A_CHUNK_BYTES + 2 * B_CHUNK_BYTES;
+constexpr uint32_t LBO = 128;                             // bytes between core matrices adjacent in K
+constexpr uint32_t SBO = (K_CHUNK / 8) * 128;             // bytes between 8-row groups
+
+// element offset (in bf16 elements) of (row, k) inside one canonical chunk: [row/8][k/8][row%8][k%8]
+__host__ __device__ inline uint32_t chunk_elem(uint32_t row, uint32_t k) {
+    return ((row >> 3) * (K_CHUNK / 8) + (k >> 3)) * 64 + (row & 7) * 8 + (k & 7);
+}
+
+// ---- PTX wrappers ---------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "WAIT_LOOP:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE;\n\t"
+        "bra WAIT_LOOP;\n\t"
+        "DONE:\n\t"
+        "}" ::"r"(bar),
+        "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src),
+                 "r"(bytes), "r"(bar)
+                 : "memory");
+}
+__device__ __forceinline__ uint64_t smem_desc(uint32_t addr) {  // K-major, no swizzle, version 1 (Blackwell)
+    return (uint64_t)((addr & 0x3FFFFu) >> 4) | ((uint64_t)(LBO >> 4) << 16) | ((uint64_t)(SBO >> 4) << 32) | (1ull << 46);
+}
+__device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+        "}" ::"r"(d_tmem),
+        "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
+    uint32_t r[32];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+          "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
+          "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+          "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+// instruction descriptor: D = f32, A = B = bf16, both K-major, N = 64, M = 128
+constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N_TILE >> 3) << 17) | ((uint32_t)(M_TILE >> 4) << 24);
+
+__device__ __forceinline__ float pow2_inv(float s) {
+    unsigned e = (__float_as_uint(s) >> 23) & 0xffu;
+    return __uint_as_float((254u - e) << 23);
+}
+__device__ __forceinline__ float rcp_nr(float x) {  // MUFU.RCP + one Newton step
+    float q;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(q) : "f"(x));
+    return fmaf(q, fmaf(-x, q, 1.0f), q);
+}
+// split 8 consecutive values into bf16 hi / lo and store them as two 16-byte vectors
+__device__ __forceinline__ void split_store8(const float* x, __nv_bfloat16* hi_dst, __nv_bfloat16* lo_dst) {
+    uint32_t h[4], l[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        __nv_bfloat16 h0 = __float2bfloat16_rn(x[2 * i]), h1 = __float2bfloat16_rn(x[2 * i + 1]);
+        __nv_bfloat16 l0 = __float2bfloat16_rn(x[2 * i] - __bfloat162float(h0)), l1 = __float2bfloat16_rn(x[2 * i + 1] - __bfloat162float(h1));
+        h[i] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+        l[i] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+    }
+    *reinterpret_cast<uint4*>(hi_dst) = make_uint4(h[0], h[1], h[2], h[3]);
+    *reinterpret_cast<uint4*>(lo_dst) = make_uint4(l[0], l[1], l[2], l[3]);
+}
+
+struct StepArgs {
+    const __nv_bfloat16* op_in;   // [tiles][2 (hi, lo)][K / 64][8192] message operand of this step (previous step's result)
+    __nv_bfloat16* op_out;        // same layout: message operand of the next step
+    const __nv_bfloat16* tbl_img; // [K / 64 slices][2][K / 64][4096] table slices, rows = output states
+    const float* emis_n;          // [M symbols][K]
+    const uint8_t* obs_t;         // [B] symbols of this time step
+    float* raw_out;               // [B][K] this step's unnormalised result (FWD: forward message, BWD: fwd * bwd)
+    float* raw_prev;              // [B][K] previous step's unnormalised result, normalised in place by this launch (or null)
+    const float* fwd_t;           // BWD: [B][K] normalised forward message of this time step
+    const float* part_in;         // [2 (carried, result)][K / 64][Bpad] row sums of the previous step, per slice
+    float* part_out;              // same, of this step
+    int B, Bpad, K, n_sym;
+    long long* trace;             // tuning aid (CXB_HMM_TC_TRACE=1): per-CTA clock64 stamps of the pipeline events, else null
+};
+__device__ __forceinline__ void stamp(const StepArgs& a, int slot) {
+    if (a.trace) a.trace[(size_t)(blockIdx.y * gridDim.x + blockIdx.x) * 16 + slot] = clock64();
+}
+
+// rows [m][n0 .. n0 + 63] of a [B][K] fp32 plane: 16 independent 128-bit accesses per thread (one round trip)
+__device__ __forceinline__ void load_row64(const float* p, float4 (&v)[16]) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = reinterpret_cast<const float4*>(p)[i];
+}
+
+template <bool FWD>
+__global__ void __launch_bounds__(THREADS, 1) k_hmm_tc_step(const StepArgs a) {
+    extern __shared__ __align__(128) unsigned char smem[];
+    const int n_chunks = a.K / K_CHUNK;
+    unsigned char* ring = smem;  // [STAGES][message hi | message lo | table hi | table lo]
+    float* s_em = reinterpret_cast<float*>(ring + (size_t)STAGES * STAGE_BYTES);  // [n_sym][64]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(s_em + (size_t)a.n_sym * N_TILE);
+    uint64_t* full = bars;                      // [STAGES]
+    uint64_t* empty = bars + STAGES;            // [STAGES]
+    uint64_t* accum = bars + 2 * STAGES;        // [1]
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int tile = blockIdx.x, slice = blockIdx.y, n0 = slice * N_TILE;
+    if (threadIdx.x == 0) stamp(a, 0);
+    // programmatic dependent launch: the next step's grid may be scheduled now (its CTAs set up their barriers and TMEM on
+    // idle SMs and then block in griddepcontrol.wait until THIS grid has completed and flushed)
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < STAGES; ++s) {
+            mbar_init(smem_u32(&full[s]), 1);
+            mbar_init(smem_u32(&empty[s]), 1);
+        }
+        mbar_init(smem_u32(accum), 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) {  // TMEM: 64 fp32 columns x 128 lanes for the accumulator
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(N_TILE));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = *tmem_slot;
+    asm volatile("griddepcontrol.wait;" ::: "memory");  // everything below reads what the previous step's grid wrote
+    if (threadIdx.x == 0) stamp(a, 1);
+
+    if (warp == 4) {
+        // ===== producer: bulk copies of the resident table slice and of the streamed message operand =====
+        if (lane == 0) {
+            const __nv_bfloat16* tb = a.tbl_img + (size_t)slice * 2 * n_chunks * (B_CHUNK_BYTES / 2);
+            const __nv_bfloat16* op = a.op_in + (size_t)tile * 2 * n_chunks * (A_CHUNK_BYTES / 2);
+            for (int c = 0; c < n_chunks; ++c) {
+                const int s = c % STAGES;
+                const uint32_t st = smem_u32(ring + (size_t)s * STAGE_BYTES), bar = smem_u32(&full[s]);
+                mbar_wait(smem_u32(&empty[s]), ((c / STAGES) & 1) ^ 1);
+                mbar_expect_tx(bar, STAGE_BYTES);
+                bulk_g2s(st, op + (size_t)c * (A_CHUNK_BYTES / 2), A_CHUNK_BYTES, bar);
+                bulk_g2s(st + A_CHUNK_BYTES, op + (size_t)(n_chunks + c) * (A_CHUNK_BYTES / 2), A_CHUNK_BYTES, bar);
+                bulk_g2s(st + 2 * A_CHUNK_BYTES, tb + (size_t)c * (B_CHUNK_BYTES / 2), B_CHUNK_BYTES, bar);
+                bulk_g2s(st + 2 * A_CHUNK_BYTES + B_CHUNK_BYTES, tb + (size_t)(n_chunks + c) * (B_CHUNK_BYTES / 2), B_CHUNK_BYTES, bar);
+            }
+            stamp(a, 2);
+        }
+    } else if (warp == 5) {
+        // ===== MMA issuer: one thread, 3 x 4 tcgen05.mma per chunk (hi*hi + hi*lo + lo*hi, 4 K-steps of 16) =====
+        if (lane == 0) {
+            for (int c = 0; c < n_chunks; ++c) {
+                const int s = c % STAGES;
+                mbar_wait(smem_u32(&full[s]), (c / STAGES) & 1);
+                if (c == 0) stamp(a, 3);
+                if (c == n_chunks - 1) stamp(a, 4);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t a_hi = smem_u32(ring + (size_t)s * STAGE_BYTES), a_lo = a_hi + A_CHUNK_BYTES;
+                const uint32_t b_hi = a_lo + A_CHUNK_BYTES, b_lo = b_hi + B_CHUNK_BYTES;
+#pragma unroll
+                for (int ks = 0; ks < K_CHUNK / 16; ++ks) {
+                    const uint32_t off = ks * 2 * LBO;  // 16 input states = 2 core matrices along K
+                    umma_bf16(tmem_base, smem_desc(a_hi + off), smem_desc(b_hi + off), IDESC, (c | ks) != 0);
+                    umma_bf16(tmem_base, smem_desc(a_hi + off), smem_desc(b_lo + off), IDESC, 1);
+                    umma_bf16(tmem_base, smem_desc(a_lo + off), smem_desc(b_hi + off), IDESC, 1);
+                }
+                umma_commit(smem_u32(&empty[s]));  // frees the stage when these MMAs have read it
+            }
+            umma_commit(smem_u32(accum));
+            stamp(a, 5);
+        }
+    } else {
+        // ===== epilogue warps =====
+        // Arithmetic is done with thread = one chain (TMEM lane) x the 64 output states of the slice; every [B][K] fp32
+        // plane is touched with HALF A WARP PER ROW (16 lanes x 16 bytes = the row's 256 contiguous bytes), per-row scalars
+        // travel by shuffle and the tile goes through a shared-memory staging buffer (the operand ring, idle by then).
+        const int row = warp * 32 + lane;            // TMEM lane / row of the tile
+        const int m = tile * M_TILE + row;           // chain
+        const bool live = m < a.B;
+        const int hrow = lane >> 4, c4 = lane & 15;  // cooperative phase: rows 32 warp + 2 it + hrow, float4 column c4
+        for (int x = threadIdx.x; x < a.n_sym * N_TILE; x += 128)
+            s_em[x] = a.emis_n[(size_t)(x / N_TILE) * a.K + n0 + (x % N_TILE)];
+        const int n_slices = a.K / N_TILE;
+        float tot_c = 0.0f, tot_r = 0.0f;
+        for (int j = 0; j < n_slices; ++j) {
+            tot_c += a.part_in[(size_t)(0 * n_slices + j) * a.Bpad + m];
+            tot_r += a.part_in[(size_t)(1 * n_slices + j) * a.Bpad + m];
+        }
+        const float r = live ? pow2_inv(tot_c) : 0.0f;
+        const float q_prev = rcp_nr(tot_r);
+        // the previous step's rows leave exactly normalised (in place), while the MMAs of this step run
+        if (a.raw_prev) {
+            float4 pv[16];
+#pragma unroll
+            for (int it = 0; it < 16; ++it) {
+                const int mm = tile * M_TILE + warp * 32 + 2 * it + hrow;
+                if (mm < a.B) pv[it] = reinterpret_cast<const float4*>(a.raw_prev + (size_t)mm * a.K + n0)[c4];
+            }
+#pragma unroll
+            for (int it = 0; it < 16; ++it) {
+                const int mm = tile * M_TILE + warp * 32 + 2 * it + hrow;
+                const float q = __shfl_sync(0xffffffffu, q_prev, 2 * it + hrow);
+                if (mm < a.B)
+                    reinterpret_cast<float4*>(a.raw_prev + (size_t)mm * a.K + n0)[c4] =
+                        make_float4(pv[it].x * q, pv[it].y * q, pv[it].z * q, pv[it].w * q);
+            }
+        }
+        // backward: this time step's forward message, requested now, used after the accumulator is ready
+        float4 fw[16];
+        if (!FWD) {
+#pragma unroll
+            for (int it = 0; it < 16; ++it) {
+                const int mm = tile * M_TILE + warp * 32 + 2 * it + hrow;
+                fw[it] = mm < a.B ? reinterpret_cast<const float4*>(a.fwd_t + (size_t)mm * a.K + n0)[c4] : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+        }
+        if (threadIdx.x == 0) stamp(a, 6);
+        asm volatile("bar.sync 1, 128;" ::: "memory");  // s_em visible to the 4 epilogue warps
+        int o = live ? (int)a.obs_t[m] : 0;
+        if (o >= a.n_sym) o = a.n_sym - 1;
+
+        mbar_wait(smem_u32(accum), 0);
+        if (threadIdx.x == 0) stamp(a, 7);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        // every MMA has completed (accum barrier), so the ring is free: stage[row][0..63] (row stride 68 floats) takes the
+        // accumulator rows (thread = TMEM lane), everything else happens half a warp per row
+        constexpr int SROW = N_TILE + 4;
+        float* stage = reinterpret_cast<float*>(ring);
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+            float pred[32];
+            tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(half * 32), pred);
+            float4* srow = reinterpret_cast<float4*>(stage + (size_t)row * SROW + half * 32);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) srow[i] = make_float4(pred[4 * i], pred[4 * i + 1], pred[4 * i + 2], pred[4 * i + 3]);
+        }
+        __syncwarp();  // a warp only re-reads the 32 staging rows it wrote itself
+        __nv_bfloat16* op_hi = a.op_out + ((size_t)tile * 2 * n_chunks + slice) * (A_CHUNK_BYTES / 2);
+        __nv_bfloat16* op_lo = a.op_out + ((size_t)tile * 2 * n_chunks + n_chunks + slice) * (A_CHUNK_BYTES / 2);
+#pragma unroll
+        for (int it = 0; it < 16; ++it) {
+            const int src = 2 * it + hrow, rr = warp * 32 + src, mm = tile * M_TILE + rr;
+            const int o_r = __shfl_sync(0xffffffffu, o, src);
+            const float r_r = __shfl_sync(0xffffffffu, r, src);  // 0 for the padding rows of the last tile
+            const float4 pd = *reinterpret_cast<const float4*>(stage + (size_t)rr * SROW + c4 * 4);
+            const float4 e4 = *reinterpret_cast<const float4*>(s_em + o_r * N_TILE + c4 * 4);
+            const float4 cr = make_float4(e4.x * pd.x * r_r, e4.y * pd.y * r_r, e4.z * pd.z * r_r, e4.w * pd.w * r_r);  // carried message
+            float sc = (cr.x + cr.y) + (cr.z + cr.w);
+#pragma unroll
+            for (int d = 8; d > 0; d >>= 1) sc += __shfl_xor_sync(0xffffffffu, sc, d);
+            float4 res = cr;  // forward: the result IS the carried message; backward: fwd * pred
+            float sr = sc;
+            if (!FWD) {
+                res = make_float4(pd.x * fw[it].x, pd.y * fw[it].y, pd.z * fw[it].z, pd.w * fw[it].w);
+                sr = (res.x + res.y) + (res.z + res.w);
+#pragma unroll
+                for (int d = 8; d > 0; d >>= 1) sr += __shfl_xor_sync(0xffffffffu, sr, d);
+            }
+            if (c4 == 0) {
+                a.part_out[(size_t)(0 * n_slices + slice) * a.Bpad + mm] = sc;
+                a.part_out[(size_t)(1 * n_slices + slice) * a.Bpad + mm] = mm < a.B ? sr : 0.0f;
+            }
+            if (mm < a.B) reinterpret_cast<float4*>(a.raw_out + (size_t)mm * a.K + n0)[c4] = res;
+            // next step's message operand in the canonical UMMA layout (this slice = chunk `slice` of K): 4 states = 8 bytes
+            // per lane; two rows x two lanes fill whole 32-byte sectors
+            const float x4[4] = {cr.x, cr.y, cr.z, cr.w};
+            uint32_t h[2], l[2];
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+                const __nv_bfloat16 h0 = __float2bfloat16_rn(x4[2 * i]), h1 = __float2bfloat16_rn(x4[2 * i + 1]);
+                const __nv_bfloat16 l0 = __float2bfloat16_rn(x4[2 * i] - __bfloat162float(h0)),
+                                    l1 = __float2bfloat16_rn(x4[2 * i + 1] - __bfloat162float(h1));
+                h[i] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+                l[i] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+            }
+            const uint32_t e = chunk_elem((uint32_t)rr, (uint32_t)(c4 * 4));
+            *reinterpret_cast<uint2*>(op_hi + e) = make_uint2(h[0], h[1]);
+            *reinterpret_cast<uint2*>(op_lo + e) = make_uint2(l[0], l[1]);
+        }
+        if (threadIdx.x == 0) stamp(a, 8);
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (threadIdx.x == 0) stamp(a, 9);
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(N_TILE));
+}
+
+// first step of a pass: carried message = emission message; result = emission (FWD) / forward message (BWD)
+template <bool FWD>
+__global__ void k_hmm_tc_init(StepArgs a) {
+    const int m = blockIdx.x * blockDim.x + threadIdx.x;  // chain (padded)
+    const int slice = blockIdx.y, n0 = slice * N_TILE, n_chunks = a.K / K_CHUNK, n_slices = a.K / N_TILE;
+    if (m >= a.Bpad) return;
+    const bool live = m < a.B;
+    const int tile = m / M_TILE, row = m % M_TILE;
+    int o = live ? (int)a.obs_t[m] : 0;
+    if (o >= a.n_sym) o = a.n_sym - 1;
+    __nv_bfloat16* op_hi = a.op_out + ((size_t)tile * 2 * n_chunks + slice) * (A_CHUNK_BYTES / 2);
+    __nv_bfloat16* op_lo = a.op_out + ((size_t)tile * 2 * n_chunks + n_chunks + slice) * (A_CHUNK_BYTES / 2);
+    float sum_c = 0.0f, sum_r = 0.0f;
+    for (int k0 = 0; k0 < N_TILE; k0 += 8) {
+        float c[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            c[i] = live ? a.emis_n[(size_t)o * a.K + n0 + k0 + i] : 0.0f;
+            sum_c += c[i];
+            if (live) {
+                const float res = FWD ? c[i] : a.fwd_t[(size_t)m * a.K + n0 + k0 + i];
+                a.raw_out[(size_t)m * a.K + n0 + k0 + i] = res;
+                sum_r += res;
+            }
+        }
+        const uint32_t e = chunk_elem((uint32_t)row, (uint32_t)k0);
+        split_store8(c, op_hi + e, op_lo + e);
+    }
+    a.part_out[(size_t)(0 * n_slices + slice) * a.Bpad + m] = sum_c;
+    a.part_out[(size_t)(1 * n_slices + slice) * a.Bpad + m] = sum_r;
+}
+// last step of a pass: nothing follows, so its result is normalised here
+__global__ void k_hmm_tc_finish(float* raw, const float* part, int B, int Bpad, int K) {
+    const int m = blockIdx.x, n_slices = K / N_TILE;
+    if (m >= B) return;
+    float tot = 0.0f;
+    for (int j = 0; j < n_slices; ++j) tot += part[(size_t)(1 * n_slices + j) * Bpad + m];
+    const float q = rcp_nr(tot);
+    for (int n = threadIdx.x; n < K; n += blockDim.x) raw[(size_t)m * K + n] *= q;
+}
+
+inline size_t step_smem_bytes(int K, int n_sym) {
+    const size_t n_chunks = K / K_CHUNK;
+    (void)n_chunks;
+    return (size_t)STAGES * STAGE_BYTES + (size_t)n_sym * N_TILE * sizeof(float) + (2 * STAGES + 1) * sizeof(uint64_t) + 16;
+}
+
+// host: bf16 round-to-nearest-even of a float
+inline uint16_t bf16_rn_host(float x) {
+    uint32_t u;
+    memcpy(&u, &x, 4);
+    if ((u & 0x7fffffffu) > 0x7f800000u) return (uint16_t)((u >> 16) | 0x40);  // NaN
+    u += 0x7fffu + ((u >> 16) & 1u);
+    return (uint16_t)(u >> 16);
+}
+inline float bf16_to_float_host(uint16_t h) {
+    uint32_t u = (uint32_t)h << 16;
+    float x;
+    memcpy(&x, &u, 4);
+    return x;
+}
+// table image: rows[n][k] (n = output state, k = input state), fp32 -> [slice][2][chunk][4096] hi / lo in the canonical layout
+inline void build_table_image(const float* rows, int K, std::vector<uint16_t>& img) {
+    const int n_chunks = K / K_CHUNK, n_slices = K / N_TILE;
+    img.assign((size_t)n_slices * 2 * n_chunks * (B_CHUNK_BYTES / 2), 0);
+    for (int n = 0; n < K; ++n)
+        for (int k = 0; k < K; ++k) {
+            const float x = rows[(size_t)n * K + k];
+            const uint16_t hi = bf16_rn_host(x), lo = bf16_rn_host(x - bf16_to_float_host(hi));
+            const int slice = n / N_TILE, r = n % N_TILE, c = k / K_CHUNK, kk = k % K_CHUNK;
+            const size_t base = (size_t)slice * 2 * n_chunks * (B_CHUNK_BYTES / 2);
+            img[base + (size_t)c * (B_CHUNK_BYTES / 2) + chunk_elem(r, kk)] = hi;
+            img[base + (size_t)(n_chunks + c) * (B_CHUNK_BYTES / 2) + chunk_elem(r, kk)] = lo;
+        }
+}
+
+}  // namespace tc
+}  // namespace cxb

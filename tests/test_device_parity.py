@@ -358,6 +358,47 @@ def test_hmm64_kernel_lengths_and_long_chain_vs_numpy(T, M):
         np.testing.assert_allclose(got_m[:, b, :].sum(axis=-1), 1.0, rtol=0, atol=2e-6)
 
 
+@pytest.mark.parametrize("K,B,T,M", [(128, 5, 1, 4), (128, 5, 2, 4), (128, 130, 3, 7), (256, 7, 6, 32), (512, 131, 5, 32),
+                                      (512, 3, 40, 64), (320, 9, 12, 5)])
+def test_hmm_tensor_core_kernel_vs_numpy(K, B, T, M):
+    """K >= 128 fp32: tcgen05 path (bf16 split operands, fp32 TMEM accumulators, one launch per time step), ragged chain
+    tiles (B not a multiple of 128), every pipeline depth, against the dense fp64 forward-backward."""
+    rng = np.random.Generator(np.random.PCG64(2024 + K))
+    A = rng.dirichlet(np.ones(K) * 0.5, size=K)
+    E = rng.dirichlet(np.ones(K) * 0.5, size=M).T * K
+    obs = rng.integers(0, M, size=(T, B)).astype(np.uint8)
+    hm = C.HmmBatch(B, T, K, M, dtype=cap.F32)
+    hm.set_tables(A, E)
+    hm.set_observations(obs)
+    assert hm.update_marginals() == B * (6 * T - 4)
+    got_m, got_f = hm.get_marginals(), hm.get_forward()
+    A_used = A.astype(np.float32).astype(np.float64)
+    for b in sorted({0, B // 2, B - 1}):
+        want_f, want_m = _hmm_numpy(A_used, E, obs[:, b])
+        assert_close(got_f[:, b, :], want_f, cap.F32)
+        assert_close(got_m[:, b, :], want_m, cap.F32)
+        np.testing.assert_allclose(got_m[:, b, :].sum(axis=-1), 1.0, rtol=0, atol=4e-6)
+
+
+def test_hmm_tensor_core_kernel_matches_simt_kernel(monkeypatch):
+    """The tcgen05 path against the library's own fp32 SIMT path on the same inputs (K = 128)."""
+    K, B, T, M = 128, 40, 9, 6
+    rng = np.random.Generator(np.random.PCG64(5))
+    A = rng.dirichlet(np.ones(K), size=K)
+    E = rng.dirichlet(np.ones(K), size=M).T * K
+    obs = rng.integers(0, M, size=(T, B)).astype(np.uint8)
+    res = []
+    for no_tc in ("0", "1"):
+        monkeypatch.setenv("CXB_HMM_NO_TC", no_tc)
+        hm = C.HmmBatch(B, T, K, M, dtype=cap.F32)
+        hm.set_tables(A, E)
+        hm.set_observations(obs)
+        hm.update_marginals()
+        res.append((hm.get_forward(), hm.get_marginals()))
+    assert_close(res[0][0], res[1][0], cap.F32)
+    assert_close(res[0][1], res[1][1], cap.F32)
+
+
 def _pairwise_vs_oracle(oracle_api, dtype, n, edges, K, sweeps, seed=7):
     rng = np.random.Generator(np.random.PCG64(seed))
     n_tables = 5
