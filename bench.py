@@ -626,7 +626,10 @@ def main():
     traffic_file = ROOT / "profiles" / f"traffic_{args.workload}.json"
     if traffic_file.exists():
         try:
-            line["roofline"]["traffic"] = json.loads(traffic_file.read_text()).get("dram_bytes_per_launch")
+            tj = json.loads(traffic_file.read_text())
+            line["roofline"]["traffic"] = tj.get("dram_bytes_per_launch")
+            if "dram_bytes_per_chain_step" in tj:  # HMM workloads: the ncu capture ran fewer time steps
+                line["roofline"]["traffic"] = tj["dram_bytes_per_chain_step"] * args.hmm_chains * args.hmm_steps
         except Exception:
             pass
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
