@@ -42,6 +42,7 @@ struct PwView {
     int tab_block;             // elements between the blocks of consecutive lanes (lane % 8 selects the block)
     int tab_blocks;            // 8 (one block per lane of a 128-bit shared-load phase) or L (one block per lane of a group)
     int tab_sel;               // elements between consecutive (table, orientation) selections inside a block
+    int prefetch;              // issue prefetch.global.L2 for the next iteration's streams
     const void* unary;         // [n][K]
     const void* m2f_cur;       // [P][K]
     void* m2f_nxt;             // [P][K]
@@ -57,6 +58,7 @@ struct PwBin {
     const uint32_t* p0;  // first slot (of the variable, or of the hub chunk)
     const uint32_t* d;   // number of slots
     uint32_t n;
+    uint32_t base;       // global record index of record 0 (the unary evidence is stored in record order)
 };
 
 // Lane geometry: a message of K states is spread over L = K / S adjacent lanes, S = min(K, 4) states (one 16-byte
@@ -256,8 +258,8 @@ __device__ __forceinline__ void prefetch_l2(const void* p, size_t bytes) {  // e
 
 // ---- variables with <= 4 pairwise factors: one lane group per variable, the reference's n <= 5 path -----------------------
 // (src/dependencies.jl:60-88): marginal = unary * x_0 * x_1 ..., m2f(v, f_k) = unary * prod_{j != k} x_j, left to right.
-template <class T, int K>
-__global__ void __launch_bounds__(256) k_pw_exact(PwView g, PwBin bin) {
+template <class T, int K, int MINB>
+__global__ void __launch_bounds__(256, MINB) k_pw_exact(PwView g, PwBin bin) {
     constexpr int S = PwGeo<K>::S, L = PwGeo<K>::L, D = PW_EXACT_MAX;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     T* sh_tables = reinterpret_cast<T*>(smem_raw);
@@ -271,10 +273,11 @@ __global__ void __launch_bounds__(256) k_pw_exact(PwView g, PwBin bin) {
     const uint32_t first = blockIdx.x * per_cta + threadIdx.x / L;
     PwRec cur = load_rec(bin, first), nxt = load_rec(bin, first + stride);
     for (uint32_t base = blockIdx.x * per_cta; base < bin.n; base += stride) {
-    const PwRec nn = load_rec(bin, first + (base - blockIdx.x * per_cta) + 2 * stride);
-    if (nxt.live) {  // pull the next iteration's streams into L2 (lane 0 of the group: messages, last lane: indices)
+    const uint32_t gid = first + (base - blockIdx.x * per_cta), gid_next = gid + stride;
+    const PwRec nn = load_rec(bin, gid + 2 * stride);
+    if (g.prefetch && nxt.live) {  // pull the next iteration's streams into L2 (lane 0 of the group: messages, last lane: indices)
         if (li == 0) {
-            prefetch_l2((const T*)g.unary + (size_t)nxt.v * K, K * sizeof(T));
+            prefetch_l2((const T*)g.unary + (size_t)(bin.base + gid_next) * K, K * sizeof(T));
             prefetch_l2((const T*)g.m2f_cur + (size_t)nxt.p0 * K, (size_t)nxt.d * K * sizeof(T));
         }
         if (li == L - 1) {
@@ -288,7 +291,7 @@ __global__ void __launch_bounds__(256) k_pw_exact(PwView g, PwBin bin) {
     nxt = nn;
     T un[S];
     vset<T, S>(un, T(1));
-    if (live) ld_vec<T, S>((const T*)g.unary + (size_t)v * K + a0, un);
+    if (live) ld_vec<T, S>((const T*)g.unary + (size_t)(bin.base + gid) * K + a0, un);
     uint32_t op[D];
     int sel[D];
 #pragma unroll
@@ -368,11 +371,11 @@ __global__ void __launch_bounds__(256) k_pw_team(PwView g, PwBin bin) {
     for (uint32_t base = blockIdx.x * per_cta; base < bin.n; base += stride) {
     const uint32_t team = first + (base - blockIdx.x * per_cta);
     const PwRec nn = load_rec(bin, team + 2 * stride);
-    if (nxt.live) {  // pull the next iteration's streams into L2 (lane 0 of the group: messages, last lane: indices)
+    if (g.prefetch && nxt.live) {  // pull the next iteration's streams into L2 (lane 0 of the group: messages, last lane: indices)
         const uint32_t nseg = (nxt.d + G - 1) / G, nlo = min(nxt.d, (uint32_t)grp * nseg), nn_loc = min(nxt.d, nlo + nseg) - nlo;
         const uint32_t npb = nxt.p0 + nlo;
         if (li == 0) {
-            if (MODE == PW_MODE_FULL && grp == 0) prefetch_l2((const T*)g.unary + (size_t)nxt.v * K, K * sizeof(T));
+            if (MODE == PW_MODE_FULL && grp == 0) prefetch_l2((const T*)g.unary + (size_t)(bin.base + team + stride) * K, K * sizeof(T));
             if (MODE != PW_MODE_H3)
                 prefetch_l2((const T*)g.m2f_cur + (size_t)npb * K, (size_t)nn_loc * K * sizeof(T));
             else
@@ -486,7 +489,7 @@ __global__ void __launch_bounds__(256) k_pw_team(PwView g, PwBin bin) {
     vset<T, S>(ext_suf, T(1));
     if (live) {
         if (MODE == PW_MODE_FULL) {
-            ld_vec<T, S>((const T*)g.unary + (size_t)v * K + a0, ext_pre);
+            ld_vec<T, S>((const T*)g.unary + (size_t)(bin.base + team) * K + a0, ext_pre);
         } else {
             ld_vec_plain<T, S>((const T*)g.chunk_pre + (size_t)team * K + a0, ext_pre);
             ld_vec_plain<T, S>((const T*)g.chunk_suf + (size_t)team * K + a0, ext_suf);
@@ -546,7 +549,7 @@ __global__ void __launch_bounds__(128) k_pw_hub_scan(PwView g, PwBin hubs /* v, 
     for (int o = 16; o > 0; o >>= 1) ncmax = max(ncmax, __shfl_xor_sync(PW_FULL_MASK, ncmax, o));
     T run[S];
     vset<T, S>(run, T(1));
-    if (live) ld_vec<T, S>((const T*)g.unary + (size_t)v * K + a0, run);
+    if (live) ld_vec<T, S>((const T*)g.unary + (size_t)(hubs.base + gid) * K + a0, run);
     for (uint32_t cb = 0; cb < ncmax; cb += U) {  // U independent loads in flight, then the dependent product chain
         T cp[U][S];
 #pragma unroll
@@ -583,6 +586,12 @@ __global__ void __launch_bounds__(128) k_pw_hub_scan(PwView g, PwBin hubs /* v, 
     }
 }
 
+// unary evidence from variable order into record (processing) order: dst[rec_of_var[v]] = src[v]
+template <class T>
+__global__ void k_pw_permute_rows(const T* src, const uint32_t* rec_of_var, T* dst, size_t n, int K) {
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n * K) dst[(size_t)rec_of_var[i / K] * K + (i % K)] = src[i];
+}
 template <class T>
 __global__ void k_pw_fill(T* p, size_t n, T v) {
     size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -605,13 +614,13 @@ struct Pairwise {
     static constexpr int N_TEAM_BINS = 5;  // G = 1, 2, 4, 8, 16
     struct Bin {
         DBuf<uint32_t> v, p0, d;
-        uint32_t n = 0;
-        PwBin view() const { return PwBin{v.p, p0.p, d.p, n}; }
+        uint32_t n = 0, base = 0;  // base = global record index of the bin's first record (unary_rec is in record order)
+        PwBin view() const { return PwBin{v.p, p0.p, d.p, n, base}; }
     };
     Bin exact_bin, team_bin[N_TEAM_BINS], chunk_bin, hub_bin;
-    DBuf<uint32_t> opp, slot_of_edge;
+    DBuf<uint32_t> opp, slot_of_edge, rec_of_var_d;
     DBuf<uint8_t> tsel;
-    DBuf<unsigned char> tables, unary, m2f[2], m2v, marg, scratch, chunk_prod, chunk_pre, chunk_suf;
+    DBuf<unsigned char> tables, unary, unary_rec, m2f[2], m2v, marg, scratch, chunk_prod, chunk_pre, chunk_suf;
     int g_max = 16;  // largest team (groups) that fits one warp at this K
     int n_sm = 148;
     long long n_products = 0;
@@ -660,19 +669,7 @@ struct Pairwise {
             ++off[(size_t)fv[f] + 1];
         }
         for (long long i = 0; i < n; ++i) off[i + 1] += off[i];
-        std::vector<uint32_t> cursor(off.begin(), off.end() - 1), slot(P), oppv(P);
-        std::vector<uint8_t> sel(P);
-        for (long long f = 0; f < m; ++f) {  // ascending f => each adjacency is in ascending factor id
-            uint32_t pu = cursor[fu[f]]++, pv = cursor[fv[f]]++;
-            slot[2 * f] = pu;
-            slot[2 * f + 1] = pv;
-            oppv[pu] = pv;
-            oppv[pv] = pu;
-            sel[pu] = (uint8_t)(ft[f] * 2 + 0);  // u is the lower endpoint
-            sel[pv] = (uint8_t)(ft[f] * 2 + 1);
-        }
-        // degree bins (records in ascending variable id inside a bin, so that the per-variable arrays — unary, opp, tsel, the
-        // inbox and everything written — stream; sorting by degree made warps uniform but cost 2x the DRAM reads):
+        // degree bins:
         //   <= 4 factors: exact path; <= 8G: team of G groups, G = 1 .. g_max; larger: hub, cut into chunks of 8 g_max slots
         const int lanes = K / std::min(K, 4);
         g_max = std::min(16, 32 / lanes);
@@ -699,17 +696,44 @@ struct Pairwise {
             tm[b].push_back(r);
         }
         auto by_degree_desc = [](const Rec& x, const Rec& y) { return x.d > y.d; };
-        // ...but inside windows of 4,096 records the records ARE sorted by degree: the lanes of a warp then run the same
-        // trip counts, and a window's lines are all consumed while they are still in L2
-        size_t window = 4096;
-        if (const char* e = getenv("CXB_PW_WINDOW")) window = (size_t)std::max(1, atoi(e));
-        auto window_sort = [&](std::vector<Rec>& recs) {
-            for (size_t i = 0; i < recs.size(); i += window)
-                std::stable_sort(recs.begin() + i, recs.begin() + std::min(recs.size(), i + window), by_degree_desc);
-        };
-        window_sort(ex);
-        for (auto& t : tm) window_sort(t);
+        // Every bin is sorted by degree (ascending id inside a degree): the lanes of a warp run the same trip counts. The
+        // locality this would cost is restored by RENUMBERING the slots in processing order: the slots of the records of a
+        // bin are consecutive in the order the kernel visits them, so the inbox, opp, tsel and m2v of a bin are pure
+        // streams (a warp touches one contiguous block), and the unary evidence is kept in a second copy in record order.
+        std::stable_sort(ex.begin(), ex.end(), by_degree_desc);
+        for (auto& t : tm) std::stable_sort(t.begin(), t.end(), by_degree_desc);
         std::stable_sort(hubs.begin(), hubs.end(), by_degree_desc);
+        std::vector<uint32_t> newoff((size_t)n, 0), rec_of_var((size_t)n, 0);
+        {
+            uint32_t run = 0, rec = 0;
+            auto number = [&](std::vector<Rec>& recs) {
+                for (Rec& r : recs) {
+                    newoff[r.v] = run;
+                    r.p0 = run;
+                    run += r.d;
+                    rec_of_var[r.v] = rec++;
+                }
+            };
+            exact_bin.base = rec;
+            number(ex);
+            for (int b2 = 0; b2 < N_TEAM_BINS; ++b2) {
+                team_bin[b2].base = rec;
+                number(tm[b2]);
+            }
+            hub_bin.base = rec;
+            number(hubs);
+        }
+        std::vector<uint32_t> cursor(newoff), slot(P), oppv(P);
+        std::vector<uint8_t> sel(P);
+        for (long long f = 0; f < m; ++f) {  // ascending f => each adjacency is in ascending factor id
+            uint32_t pu = cursor[fu[f]]++, pv = cursor[fv[f]]++;
+            slot[2 * f] = pu;
+            slot[2 * f + 1] = pv;
+            oppv[pu] = pv;
+            oppv[pv] = pu;
+            sel[pu] = (uint8_t)(ft[f] * 2 + 0);  // u is the lower endpoint
+            sel[pv] = (uint8_t)(ft[f] * 2 + 1);
+        }
         std::vector<Rec> hub_recs;  // v, first chunk, number of chunks
         for (const Rec& h : hubs) {
             uint32_t nc = (h.d + chunk_slots - 1) / chunk_slots;
@@ -744,6 +768,7 @@ struct Pairwise {
         for (int b = 0; b < N_TEAM_BINS; ++b) CXB_CUDA(up_bin(team_bin[b], tm[b]));
         CXB_CUDA(up_bin(chunk_bin, chunks));
         CXB_CUDA(up_bin(hub_bin, hub_recs));
+        CXB_CUDA(up(rec_of_var_d, rec_of_var));
         CXB_CUDA(up(opp, oppv));
         CXB_CUDA(up(tsel, sel));
         CXB_CUDA(up(slot_of_edge, slot));
@@ -758,6 +783,7 @@ struct Pairwise {
         CXB_CUDA(scratch.reserve(pb));
         CXB_CUDA(marg.reserve(nb));
         CXB_CUDA(unary.reserve(nb));
+        CXB_CUDA(unary_rec.reserve(nb));
         CXB_CUDA(cudaMemsetAsync(m2v.p, 0, pb, stream));
         CXB_CUDA(cudaMemsetAsync(marg.p, 0, nb, stream));
         CXB_CUDA(cudaStreamSynchronize(stream));
@@ -860,8 +886,15 @@ struct Pairwise {
         launch_team<T, KK, 2>(g, tb);
         launch_team<T, KK, 1>(g, tb);
         if (exact_bin.n) {
-            if (tb > 48 * 1024) cudaFuncSetAttribute(k_pw_exact<T, KK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tb);
-            CXB_LAUNCH((k_pw_exact<T, KK>), grid_for((size_t)exact_bin.n * PwGeo<KK>::L), 256, tb, stream, g, exact_bin.view());
+            int minb = 2;
+            if (const char* e = getenv("CXB_PW_MINB")) minb = atoi(e);
+            if (minb >= 3) {
+                if (tb > 48 * 1024) cudaFuncSetAttribute(k_pw_exact<T, KK, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tb);
+                CXB_LAUNCH((k_pw_exact<T, KK, 3>), grid_for((size_t)exact_bin.n * PwGeo<KK>::L), 256, tb, stream, g, exact_bin.view());
+            } else {
+                if (tb > 48 * 1024) cudaFuncSetAttribute(k_pw_exact<T, KK, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tb);
+                CXB_LAUNCH((k_pw_exact<T, KK, 2>), grid_for((size_t)exact_bin.n * PwGeo<KK>::L), 256, tb, stream, g, exact_bin.view());
+            }
         }
         return CXB_OK;
     }
@@ -890,7 +923,9 @@ struct Pairwise {
         g.tab_block = tab_block;
         g.tab_blocks = tab_blocks;
         g.tab_sel = tab_sel;
-        g.unary = unary.p;
+        g.prefetch = 1;
+        if (const char* e = getenv("CXB_PW_PREFETCH")) g.prefetch = atoi(e);
+        g.unary = unary_rec.p;  // record order
         g.m2f_cur = m2f[cur].p;
         g.m2f_nxt = m2f[cur ^ 1].p;
         g.m2v = m2v.p;
@@ -981,6 +1016,13 @@ int32_t cxb_pairwise_set_unary(cxb_pairwise* g, const void* unary_host) {
     }
     PW_CUDA(g, cudaSetDevice(h->device));
     PW_CUDA(g, cudaMemcpyAsync(h->unary.p, unary_host, (size_t)h->n * h->K * h->esz(), cudaMemcpyHostToDevice, h->stream));
+    const size_t cnt = (size_t)h->n * h->K;
+    if (h->dtype == CXB_F32)
+        CXB_LAUNCH(cxb::k_pw_permute_rows<float>, cxb::cdiv(cnt, 256), 256, 0, h->stream, (const float*)h->unary.p, h->rec_of_var_d.p,
+                   (float*)h->unary_rec.p, (size_t)h->n, h->K);
+    else
+        CXB_LAUNCH(cxb::k_pw_permute_rows<double>, cxb::cdiv(cnt, 256), 256, 0, h->stream, (const double*)h->unary.p, h->rec_of_var_d.p,
+                   (double*)h->unary_rec.p, (size_t)h->n, h->K);
     PW_CUDA(g, cudaStreamSynchronize(h->stream));
     h->have_unary = true;
     return CXB_OK;

@@ -16,7 +16,8 @@ import numpy as np
 
 from . import _capi as capi
 from .inference_signal import (IndividualMarginal, JointMarginal, MessageToFactor, MessageToVariable, NoRuleError,
-                               ProductOfMessages, Signal, SignalStore, get_value, get_variant, _ids)
+                               ProductOfMessages, Signal, SignalStore, UndefValue, get_value, get_values, get_variant,
+                               is_computed, _ids)
 from .model_engine import (Connection, Factor, Variable, backend_get_connected_factor_ids,
                            backend_get_connected_variable_ids, backend_get_connection, backend_get_factor,
                            backend_get_factor_ids, backend_get_variable, backend_get_variable_ids,
@@ -359,6 +360,7 @@ def update_marginals(engine: InferenceEngine, variable_id_or_ids, schedule: str 
     stats = capi.UpdateStats()
     fn = engine.api.update_marginals if schedule == "lvl" else engine.api.update_marginals_seq
     engine._callback_error = None
+    before = _snapshot(engine) if engine.tracer is not None else None
     t0 = time.perf_counter_ns()
     status = fn(engine.store.h, len(ids), p, C.byref(stats))
     t1 = time.perf_counter_ns()
@@ -366,11 +368,22 @@ def update_marginals(engine: InferenceEngine, variable_id_or_ids, schedule: str 
         raise engine._callback_error
     engine.store.check(status)
     if engine.tracer is not None:
-        engine.tracer.inference_requests.append(_collect_trace(engine, ids, t1 - t0))
+        engine.tracer.inference_requests.append(_collect_trace(engine, ids, t1 - t0, before))
     return stats
 
 
-def _collect_trace(engine: InferenceEngine, ids, total_ns: int) -> TracedInferenceRequest:
+def _snapshot(engine: InferenceEngine):
+    """Values and computed flags of every signal before a traced request (tracing is a debugging aid, as in the
+    reference: src/inference_engine.jl:650-657 records `value_before_execution` per execution)."""
+    n = engine.store.n_signals()
+    if n == 0:
+        return np.zeros((0, engine.store.value_dim)), np.zeros(0, dtype=bool)
+    sigs = [Signal(engine.store, i) for i in range(n)]
+    computed = np.array([is_computed(s) for s in sigs], dtype=bool)
+    return get_values(sigs), computed
+
+
+def _collect_trace(engine: InferenceEngine, ids, total_ns: int, before=None) -> TracedInferenceRequest:
     n = engine.api.trace_get(engine.store.h, None, None, 0)
     lv = np.zeros(max(n, 1), dtype=np.int64)
     sg = np.zeros(max(n, 1), dtype=np.int64)
@@ -390,5 +403,12 @@ def _collect_trace(engine: InferenceEngine, ids, total_ns: int) -> TracedInferen
         s = Signal(engine.store, int(sg[k]))
         variant = get_variant(s)
         vid = int(var[k]) if var is not None else getattr(variant, "variable_id", None)
-        cur.executions.append(TracedInferenceExecution(engine, vid, s, max(total_ns // max(n, 1), 1), None, get_value(s)))
+        value_before = None
+        if before is not None:  # a signal runs at most once per level-synchronous request: its old value is the snapshot's
+            vals, computed = before
+            if not computed[s.sid]:
+                value_before = UndefValue()
+            else:
+                value_before = float(vals[s.sid][0]) if engine.store.value_dim == 1 else vals[s.sid].copy()
+        cur.executions.append(TracedInferenceExecution(engine, vid, s, max(total_ns // max(n, 1), 1), value_before, get_value(s)))
     return TracedInferenceRequest(engine, max(total_ns, 1), InferenceRequest(engine, tuple(ids), []), rounds)

@@ -181,6 +181,25 @@ def set_values(signals: Sequence[Signal], values) -> None:
     st.check(st.api.set_values(st.h, len(signals), p, vals.ctypes.data_as(capi.f64p), st.value_dim))
 
 
+class UndefValue:
+    """UndefValue(), src/signal.jl:9-14: the value of a signal that has never been computed or set."""
+    _instance = None
+
+    def __new__(cls):
+        if cls._instance is None:
+            cls._instance = super().__new__(cls)
+        return cls._instance
+
+    def __eq__(self, other):
+        return isinstance(other, UndefValue)
+
+    def __hash__(self):
+        return hash("UndefValue")
+
+    def __repr__(self):
+        return "UndefValue()"
+
+
 def get_values(signals: Sequence[Signal]) -> np.ndarray:
     st = signals[0].store
     out = np.zeros((len(signals), st.value_dim), dtype=np.float64)

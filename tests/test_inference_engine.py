@@ -211,8 +211,18 @@ def test_tracing_iid_model(backend):  # :1149-1280
     assert [C.get_variant(x.signal) for x in r1.executions] == [C.MessageToVariable(p, f1), C.MessageToVariable(p, f2)]
     assert [x.variable_id for x in r1.executions] == [p, p]
     assert [x.value_after_execution for x in r1.executions] == [2, 4]
+    assert all(x.value_before_execution == C.UndefValue() for x in r1.executions + r2.executions)  # :1246, 1253, 1261
     assert [C.get_variant(x.signal) for x in r2.executions] == [C.IndividualMarginal(p)]
     assert r2.executions[0].value_after_execution == 9
+    # a second traced request after ALL inputs were set again (a signal is pending only when every strong dependency is
+    # fresh, src/signal.jl:668-730): the old values are reported, no longer UndefValue()
+    C.set_value(m2f(e, o1, f1), 5)
+    C.set_value(m2f(e, o2, f2), 2)
+    C.set_value(m2v(e, p, fp), 3)
+    C.update_marginals(e, p)
+    req2 = C.get_trace(e).inference_requests[1]
+    ex = [x for r in req2.rounds for x in r.executions]
+    assert [(x.value_before_execution, x.value_after_execution) for x in ex] == [(2, 10), (4, 4), (9, 17)]
 
 
 def test_missing_rule_raises(backend):  # src/inference_engine.jl:358-360
