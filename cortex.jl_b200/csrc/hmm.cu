@@ -397,6 +397,7 @@ struct Hmm {
     DBuf<uint16_t> tc_img_f, tc_img_b, tc_op[2];
     DBuf<float> tc_part[2];
     bool tc_ready = false;
+    int tc_nt = 64;  // output states per CTA of the tensor-core step kernel (32 or 64)
     bool tc_eligible() const {
         if (const char* e = getenv("CXB_HMM_NO_TC"))
             if (atoi(e)) return false;
@@ -459,21 +460,26 @@ struct Hmm {
         CXB_CUDA(cudaMemcpyAsync(At.p, at.data(), at.size(), cudaMemcpyHostToDevice, stream));
         CXB_CUDA(cudaMemcpyAsync(En.p, en.data(), en.size(), cudaMemcpyHostToDevice, stream));
         if (tc_eligible()) {
+            // slices of 32 output states when 64-state slices would leave most SMs idle
+            int n_sm = 148;
+            cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, device);
+            tc_nt = (tc_bpad() / tc::M_TILE) * (K / 64) * 2 <= n_sm ? 32 : 64;
+            if (const char* e = getenv("CXB_HMM_TC_NT")) tc_nt = atoi(e) == 32 ? 32 : 64;
             std::vector<uint16_t> img;
-            tc::build_table_image((const float*)at.data(), K, img);  // forward: pred[j] = sum_i msg[i] A[i][j] -> rows of A^T
+            tc::build_table_image((const float*)at.data(), K, tc_nt, img);  // forward: pred[j] = sum_i msg[i] A[i][j] -> rows of A^T
             CXB_CUDA(tc_img_f.reserve(img.size()));
             CXB_CUDA(cudaMemcpyAsync(tc_img_f.p, img.data(), img.size() * 2, cudaMemcpyHostToDevice, stream));
             CXB_CUDA(cudaStreamSynchronize(stream));
-            tc::build_table_image((const float*)a.data(), K, img);   // backward: pred[j] = sum_i A[j][i] msg[i] -> rows of A
+            tc::build_table_image((const float*)a.data(), K, tc_nt, img);   // backward: pred[j] = sum_i A[j][i] msg[i] -> rows of A
             CXB_CUDA(tc_img_b.reserve(img.size()));
             CXB_CUDA(cudaMemcpyAsync(tc_img_b.p, img.data(), img.size() * 2, cudaMemcpyHostToDevice, stream));
             const long long bpad = tc_bpad();
             const size_t op_elems = (size_t)(bpad / tc::M_TILE) * 2 * (K / tc::K_CHUNK) * (tc::A_CHUNK_BYTES / 2);
             for (int i = 0; i < 2; ++i) {
                 CXB_CUDA(tc_op[i].reserve(op_elems));
-                CXB_CUDA(tc_part[i].reserve((size_t)2 * (K / tc::N_TILE) * bpad));
+                CXB_CUDA(tc_part[i].reserve((size_t)2 * (K / tc_nt) * bpad));
                 CXB_CUDA(cudaMemsetAsync(tc_op[i].p, 0, op_elems * 2, stream));
-                CXB_CUDA(cudaMemsetAsync(tc_part[i].p, 0, (size_t)2 * (K / tc::N_TILE) * bpad * sizeof(float), stream));
+                CXB_CUDA(cudaMemsetAsync(tc_part[i].p, 0, (size_t)2 * (K / tc_nt) * bpad * sizeof(float), stream));
             }
             tc_ready = true;
         }
@@ -495,11 +501,13 @@ struct Hmm {
         return CXB_OK;
     }
     // one launch per time step and pass (hmm_tc.cuh); 2 T + 4 launches
-    int32_t launch_tc() {
-        const int bpad = (int)tc_bpad(), tiles = bpad / tc::M_TILE, n_slices = K / tc::N_TILE;
-        const size_t smem = tc::step_smem_bytes(K, M), row = (size_t)B * K;
-        CXB_CUDA(cudaFuncSetAttribute(tc::k_hmm_tc_step<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        CXB_CUDA(cudaFuncSetAttribute(tc::k_hmm_tc_step<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int32_t launch_tc() { return tc_nt == 32 ? launch_tc_nt<32>() : launch_tc_nt<64>(); }
+    template <int NT>
+    int32_t launch_tc_nt() {
+        const int bpad = (int)tc_bpad(), tiles = bpad / tc::M_TILE, n_slices = K / NT;
+        const size_t smem = tc::step_smem_bytes<NT>(M), row = (size_t)B * K;
+        CXB_CUDA(cudaFuncSetAttribute(tc::k_hmm_tc_step<true, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CXB_CUDA(cudaFuncSetAttribute(tc::k_hmm_tc_step<false, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         float *fw = (float*)fwd.p, *mg = (float*)marg.p;
         tc::StepArgs a{};
         a.emis_n = (const float*)En.p;
@@ -532,9 +540,9 @@ struct Hmm {
                 a.fwd_t = f ? nullptr : fw + (size_t)t * row;
                 if (s == 0) {
                     if (f)
-                        CXB_LAUNCH(tc::k_hmm_tc_init<true>, igrid, 128, 0, stream, a);
+                        CXB_LAUNCH((tc::k_hmm_tc_init<true, NT>), igrid, 128, 0, stream, a);
                     else
-                        CXB_LAUNCH(tc::k_hmm_tc_init<false>, igrid, 128, 0, stream, a);
+                        CXB_LAUNCH((tc::k_hmm_tc_init<false, NT>), igrid, 128, 0, stream, a);
                 } else {
                     cudaLaunchConfig_t cfg{};
                     cfg.gridDim = grid;
@@ -546,13 +554,13 @@ struct Hmm {
                     attr[0].val.programmaticStreamSerializationAllowed = pdl ? 1 : 0;
                     cfg.attrs = attr;
                     cfg.numAttrs = 1;
-                    CXB_CUDA(cudaLaunchKernelEx(&cfg, f ? tc::k_hmm_tc_step<true> : tc::k_hmm_tc_step<false>, a));
+                    CXB_CUDA(cudaLaunchKernelEx(&cfg, f ? tc::k_hmm_tc_step<true, NT> : tc::k_hmm_tc_step<false, NT>, a));
                     ++::cxb::g_kernel_launches;
                 }
             }
             const long long t_last = f ? this->T - 1 : 0;
             CXB_LAUNCH(tc::k_hmm_tc_finish, (unsigned)B, 128, 0, stream, out + (size_t)t_last * row, tc_part[(this->T - 1) & 1].p, (int)B,
-                       bpad, K);
+                       bpad, K, n_slices);
         }
         if (tracing) {  // stamps of the LAST step kernel of the backward pass, averaged over the CTAs, relative to CTA start
             std::vector<long long> h((size_t)tiles * n_slices * 16);

@@ -25,14 +25,20 @@ namespace cxb {
 namespace tc {
 
 constexpr int M_TILE = 128;   // chains per CTA (MMA M)
-constexpr int N_TILE = 64;    // output states per CTA (MMA N)
+// output states per CTA (MMA N) is a template parameter NT: 64 (64 CTAs at B = 1,024, K = 512) or 32 (128 CTAs: less
+// operand ingest and half the epilogue per SM, more aggregate L2 traffic)
 constexpr int K_CHUNK = 64;   // input states per operand chunk (4 MMA K-steps of 16)
-constexpr int STAGES = 4;     // operand chunks in flight (48 KB each: message hi/lo 2 x 16 KB + table hi/lo 2 x 8 KB)
+template <int NT>
+struct Cfg {
+    static constexpr uint32_t B_CHUNK_BYTES = NT * 64 * 2;                    // table chunk, per hi / lo
+    static constexpr uint32_t STAGE_BYTES = 2 * (128 * 64 * 2) + 2 * B_CHUNK_BYTES;  // message hi/lo + table hi/lo
+    static constexpr int STAGES = NT == 64 ? 4 : 5;                           // 192 KB / 200 KB of operands in flight
+    // instruction descriptor: D = f32, A = B = bf16, both K-major, N = NT, M = 128
+    static constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(NT >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+};
 constexpr int THREADS = 192;  // 4 epilogue warps + producer warp + MMA warp
 constexpr int MAX_K = 2048;   // any multiple of 64 up to here (both operands stream through the ring)
 constexpr uint32_t A_CHUNK_BYTES = M_TILE * K_CHUNK * 2;  // 16 KB per hi / lo
-constexpr uint32_t B_CHUNK_BYTES = N_TILE * K_CHUNK * 2;  //  8 KB per hi / lo
-constexpr uint32_t STAGE_BYTES = 2 * A_CHUNK_BYTES + 2 * B_CHUNK_BYTES;
 constexpr uint32_t LBO = 128;                             // bytes between core matrices adjacent in K
 constexpr uint32_t SBO = (K_CHUNK / 8) * 128;             // bytes between 8-row groups
 
@@ -98,8 +104,6 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
 #pragma unroll
     for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
 }
-// instruction descriptor: D = f32, A = B = bf16, both K-major, N = 64, M = 128
-constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N_TILE >> 3) << 17) | ((uint32_t)(M_TILE >> 4) << 24);
 
 __device__ __forceinline__ float pow2_inv(float s) {
     unsigned e = (__float_as_uint(s) >> 23) & 0xffu;
@@ -148,8 +152,11 @@ __device__ __forceinline__ void load_row64(const float* p, float4 (&v)[16]) {
     for (int i = 0; i < 16; ++i) v[i] = reinterpret_cast<const float4*>(p)[i];
 }
 
-template <bool FWD>
+template <bool FWD, int NT>
 __global__ void __launch_bounds__(THREADS, 1) k_hmm_tc_step(const StepArgs a) {
+    constexpr int N_TILE = NT, STAGES = Cfg<NT>::STAGES;
+    constexpr uint32_t B_CHUNK_BYTES = Cfg<NT>::B_CHUNK_BYTES, STAGE_BYTES = Cfg<NT>::STAGE_BYTES, IDESC = Cfg<NT>::IDESC;
+    constexpr int LPR = N_TILE / 4, RPI = 32 / LPR, ITER = 32 / RPI;  // lanes per row, rows per instruction, iterations per warp
     extern __shared__ __align__(128) unsigned char smem[];
     const int n_chunks = a.K / K_CHUNK;
     unsigned char* ring = smem;  // [STAGES][message hi | message lo | table hi | table lo]
@@ -234,7 +241,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_hmm_tc_step(const StepArgs a) {
         const int row = warp * 32 + lane;            // TMEM lane / row of the tile
         const int m = tile * M_TILE + row;           // chain
         const bool live = m < a.B;
-        const int hrow = lane >> 4, c4 = lane & 15;  // cooperative phase: rows 32 warp + 2 it + hrow, float4 column c4
+        const int hrow = lane / LPR, c4 = lane % LPR;  // cooperative phase: rows 32 warp + RPI it + hrow, float4 column c4
         for (int x = threadIdx.x; x < a.n_sym * N_TILE; x += 128)
             s_em[x] = a.emis_n[(size_t)(x / N_TILE) * a.K + n0 + (x % N_TILE)];
         const int n_slices = a.K / N_TILE;
@@ -247,27 +254,27 @@ __global__ void __launch_bounds__(THREADS, 1) k_hmm_tc_step(const StepArgs a) {
         const float q_prev = rcp_nr(tot_r);
         // the previous step's rows leave exactly normalised (in place), while the MMAs of this step run
         if (a.raw_prev) {
-            float4 pv[16];
+            float4 pv[ITER];
 #pragma unroll
-            for (int it = 0; it < 16; ++it) {
-                const int mm = tile * M_TILE + warp * 32 + 2 * it + hrow;
+            for (int it = 0; it < ITER; ++it) {
+                const int mm = tile * M_TILE + warp * 32 + RPI * it + hrow;
                 if (mm < a.B) pv[it] = reinterpret_cast<const float4*>(a.raw_prev + (size_t)mm * a.K + n0)[c4];
             }
 #pragma unroll
-            for (int it = 0; it < 16; ++it) {
-                const int mm = tile * M_TILE + warp * 32 + 2 * it + hrow;
-                const float q = __shfl_sync(0xffffffffu, q_prev, 2 * it + hrow);
+            for (int it = 0; it < ITER; ++it) {
+                const int mm = tile * M_TILE + warp * 32 + RPI * it + hrow;
+                const float q = __shfl_sync(0xffffffffu, q_prev, RPI * it + hrow);
                 if (mm < a.B)
                     reinterpret_cast<float4*>(a.raw_prev + (size_t)mm * a.K + n0)[c4] =
                         make_float4(pv[it].x * q, pv[it].y * q, pv[it].z * q, pv[it].w * q);
             }
         }
         // backward: this time step's forward message, requested now, used after the accumulator is ready
-        float4 fw[16];
+        float4 fw[ITER];
         if (!FWD) {
 #pragma unroll
-            for (int it = 0; it < 16; ++it) {
-                const int mm = tile * M_TILE + warp * 32 + 2 * it + hrow;
+            for (int it = 0; it < ITER; ++it) {
+                const int mm = tile * M_TILE + warp * 32 + RPI * it + hrow;
                 fw[it] = mm < a.B ? reinterpret_cast<const float4*>(a.fwd_t + (size_t)mm * a.K + n0)[c4] : make_float4(0.f, 0.f, 0.f, 0.f);
             }
         }
@@ -284,7 +291,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_hmm_tc_step(const StepArgs a) {
         constexpr int SROW = N_TILE + 4;
         float* stage = reinterpret_cast<float*>(ring);
 #pragma unroll
-        for (int half = 0; half < 2; ++half) {
+        for (int half = 0; half < N_TILE / 32; ++half) {
             float pred[32];
             tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(half * 32), pred);
             float4* srow = reinterpret_cast<float4*>(stage + (size_t)row * SROW + half * 32);
@@ -292,11 +299,12 @@ __global__ void __launch_bounds__(THREADS, 1) k_hmm_tc_step(const StepArgs a) {
             for (int i = 0; i < 8; ++i) srow[i] = make_float4(pred[4 * i], pred[4 * i + 1], pred[4 * i + 2], pred[4 * i + 3]);
         }
         __syncwarp();  // a warp only re-reads the 32 staging rows it wrote itself
-        __nv_bfloat16* op_hi = a.op_out + ((size_t)tile * 2 * n_chunks + slice) * (A_CHUNK_BYTES / 2);
-        __nv_bfloat16* op_lo = a.op_out + ((size_t)tile * 2 * n_chunks + n_chunks + slice) * (A_CHUNK_BYTES / 2);
+        // this slice is columns [n0, n0 + NT) of K: chunk n0 / 64 of the next step's message operand, offset n0 % 64 inside it
+        __nv_bfloat16* op_hi = a.op_out + ((size_t)tile * 2 * n_chunks + n0 / K_CHUNK) * (A_CHUNK_BYTES / 2);
+        __nv_bfloat16* op_lo = a.op_out + ((size_t)tile * 2 * n_chunks + n_chunks + n0 / K_CHUNK) * (A_CHUNK_BYTES / 2);
 #pragma unroll
-        for (int it = 0; it < 16; ++it) {
-            const int src = 2 * it + hrow, rr = warp * 32 + src, mm = tile * M_TILE + rr;
+        for (int it = 0; it < ITER; ++it) {
+            const int src = RPI * it + hrow, rr = warp * 32 + src, mm = tile * M_TILE + rr;
             const int o_r = __shfl_sync(0xffffffffu, o, src);
             const float r_r = __shfl_sync(0xffffffffu, r, src);  // 0 for the padding rows of the last tile
             const float4 pd = *reinterpret_cast<const float4*>(stage + (size_t)rr * SROW + c4 * 4);
@@ -304,14 +312,14 @@ __global__ void __launch_bounds__(THREADS, 1) k_hmm_tc_step(const StepArgs a) {
             const float4 cr = make_float4(e4.x * pd.x * r_r, e4.y * pd.y * r_r, e4.z * pd.z * r_r, e4.w * pd.w * r_r);  // carried message
             float sc = (cr.x + cr.y) + (cr.z + cr.w);
 #pragma unroll
-            for (int d = 8; d > 0; d >>= 1) sc += __shfl_xor_sync(0xffffffffu, sc, d);
+            for (int d = LPR / 2; d > 0; d >>= 1) sc += __shfl_xor_sync(0xffffffffu, sc, d);
             float4 res = cr;  // forward: the result IS the carried message; backward: fwd * pred
             float sr = sc;
             if (!FWD) {
                 res = make_float4(pd.x * fw[it].x, pd.y * fw[it].y, pd.z * fw[it].z, pd.w * fw[it].w);
                 sr = (res.x + res.y) + (res.z + res.w);
 #pragma unroll
-                for (int d = 8; d > 0; d >>= 1) sr += __shfl_xor_sync(0xffffffffu, sr, d);
+                for (int d = LPR / 2; d > 0; d >>= 1) sr += __shfl_xor_sync(0xffffffffu, sr, d);
             }
             if (c4 == 0) {
                 a.part_out[(size_t)(0 * n_slices + slice) * a.Bpad + mm] = sc;
@@ -330,7 +338,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_hmm_tc_step(const StepArgs a) {
                 h[i] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
                 l[i] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
             }
-            const uint32_t e = chunk_elem((uint32_t)rr, (uint32_t)(c4 * 4));
+            const uint32_t e = chunk_elem((uint32_t)rr, (uint32_t)(n0 % K_CHUNK + c4 * 4));
             *reinterpret_cast<uint2*>(op_hi + e) = make_uint2(h[0], h[1]);
             *reinterpret_cast<uint2*>(op_lo + e) = make_uint2(l[0], l[1]);
         }
@@ -343,8 +351,9 @@ __global__ void __launch_bounds__(THREADS, 1) k_hmm_tc_step(const StepArgs a) {
 }
 
 // first step of a pass: carried message = emission message; result = emission (FWD) / forward message (BWD)
-template <bool FWD>
+template <bool FWD, int NT>
 __global__ void k_hmm_tc_init(StepArgs a) {
+    constexpr int N_TILE = NT;
     const int m = blockIdx.x * blockDim.x + threadIdx.x;  // chain (padded)
     const int slice = blockIdx.y, n0 = slice * N_TILE, n_chunks = a.K / K_CHUNK, n_slices = a.K / N_TILE;
     if (m >= a.Bpad) return;
@@ -352,8 +361,8 @@ __global__ void k_hmm_tc_init(StepArgs a) {
     const int tile = m / M_TILE, row = m % M_TILE;
     int o = live ? (int)a.obs_t[m] : 0;
     if (o >= a.n_sym) o = a.n_sym - 1;
-    __nv_bfloat16* op_hi = a.op_out + ((size_t)tile * 2 * n_chunks + slice) * (A_CHUNK_BYTES / 2);
-    __nv_bfloat16* op_lo = a.op_out + ((size_t)tile * 2 * n_chunks + n_chunks + slice) * (A_CHUNK_BYTES / 2);
+    __nv_bfloat16* op_hi = a.op_out + ((size_t)tile * 2 * n_chunks + n0 / K_CHUNK) * (A_CHUNK_BYTES / 2);
+    __nv_bfloat16* op_lo = a.op_out + ((size_t)tile * 2 * n_chunks + n_chunks + n0 / K_CHUNK) * (A_CHUNK_BYTES / 2);
     float sum_c = 0.0f, sum_r = 0.0f;
     for (int k0 = 0; k0 < N_TILE; k0 += 8) {
         float c[8];
@@ -367,15 +376,15 @@ __global__ void k_hmm_tc_init(StepArgs a) {
                 sum_r += res;
             }
         }
-        const uint32_t e = chunk_elem((uint32_t)row, (uint32_t)k0);
+        const uint32_t e = chunk_elem((uint32_t)row, (uint32_t)(n0 % K_CHUNK + k0));
         split_store8(c, op_hi + e, op_lo + e);
     }
     a.part_out[(size_t)(0 * n_slices + slice) * a.Bpad + m] = sum_c;
     a.part_out[(size_t)(1 * n_slices + slice) * a.Bpad + m] = sum_r;
 }
 // last step of a pass: nothing follows, so its result is normalised here
-__global__ void k_hmm_tc_finish(float* raw, const float* part, int B, int Bpad, int K) {
-    const int m = blockIdx.x, n_slices = K / N_TILE;
+__global__ void k_hmm_tc_finish(float* raw, const float* part, int B, int Bpad, int K, int n_slices) {
+    const int m = blockIdx.x;
     if (m >= B) return;
     float tot = 0.0f;
     for (int j = 0; j < n_slices; ++j) tot += part[(size_t)(1 * n_slices + j) * Bpad + m];
@@ -383,10 +392,9 @@ __global__ void k_hmm_tc_finish(float* raw, const float* part, int B, int Bpad, 
     for (int n = threadIdx.x; n < K; n += blockDim.x) raw[(size_t)m * K + n] *= q;
 }
 
-inline size_t step_smem_bytes(int K, int n_sym) {
-    const size_t n_chunks = K / K_CHUNK;
-    (void)n_chunks;
-    return (size_t)STAGES * STAGE_BYTES + (size_t)n_sym * N_TILE * sizeof(float) + (2 * STAGES + 1) * sizeof(uint64_t) + 16;
+template <int NT>
+inline size_t step_smem_bytes(int n_sym) {
+    return (size_t)Cfg<NT>::STAGES * Cfg<NT>::STAGE_BYTES + (size_t)n_sym * NT * sizeof(float) + (2 * Cfg<NT>::STAGES + 1) * sizeof(uint64_t) + 16;
 }
 
 // host: bf16 round-to-nearest-even of a float
@@ -403,9 +411,10 @@ inline float bf16_to_float_host(uint16_t h) {
     memcpy(&x, &u, 4);
     return x;
 }
-// table image: rows[n][k] (n = output state, k = input state), fp32 -> [slice][2][chunk][4096] hi / lo in the canonical layout
-inline void build_table_image(const float* rows, int K, std::vector<uint16_t>& img) {
+// table image: rows[n][k] (n = output state, k = input state), fp32 -> [slice][2][chunk][NT x 64] hi / lo in the canonical layout
+inline void build_table_image(const float* rows, int K, int N_TILE, std::vector<uint16_t>& img) {
     const int n_chunks = K / K_CHUNK, n_slices = K / N_TILE;
+    const size_t B_CHUNK_BYTES = (size_t)N_TILE * K_CHUNK * 2;
     img.assign((size_t)n_slices * 2 * n_chunks * (B_CHUNK_BYTES / 2), 0);
     for (int n = 0; n < K; ++n)
         for (int k = 0; k < K; ++k) {
