@@ -233,7 +233,7 @@ def workload_config(args, world):
     if args.workload == "potts_grid":
         return {"workload": f"2D Potts grid {args.grid}x{args.grid}, K=16, synchronous sweeps (protocol B), row-sharded "
                             f"(BASELINE configs[3])", "grid": args.grid, "K": 16, "l2": "inputs exceed L2",
-                "parallelism": f"row-shard x{world} + halo exchange"}
+                "parallelism": f"row-shard x{world} + halo exchange: {getattr(args, 'halo_transport', 'n/a')}"}
     if args.workload in ("hmm64", "hmm512"):
         k = 512 if args.workload == "hmm512" else 64
         return {"workload": f"{args.hmm_chains} HMMs per GPU, K={k}, M=32, T={args.hmm_steps} (BASELINE configs[2] K={k})",
@@ -328,10 +328,17 @@ def bench_potts_grid(args, pkg, rank, world, local):
 
     halo = pkg.HaloExchanger(dist, rank, world)
     upd = [0]
+    # fused exchange: the sweep kernel stores the cut-edge messages into the neighbour GPU's halo buffer over NVLink
+    # (cxb_grid_p2p_*); CXB_GRID_NCCL=1 (or GPUs without peer access) keeps the separate NCCL send/recv per sweep
+    fused = world > 1 and os.environ.get("CXB_GRID_NCCL", "0") != "1" and pkg.connect_row_neighbours(dist, gr, rank, world)
+    args.halo_transport = "peer stores fused in the sweep kernel (NVLink P2P)" if fused else "NCCL send/recv per sweep"
+    if world > 1:
+        gr.sync()
+        dist.barrier()
 
     def step():
         upd[0] = gr.sweep()
-        if world > 1:
+        if world > 1 and not fused:
             with torch.cuda.stream(ext):  # NCCL orders itself after the sweep on the library's stream
                 halo.exchange(tens(gr.halo_send_ptr(0)) if has_up else None, tens(gr.halo_send_ptr(1)) if has_down else None,
                               tens(gr.halo_recv_ptr(0)) if has_up else None, tens(gr.halo_recv_ptr(1)) if has_down else None)

@@ -95,6 +95,9 @@ _STRUCTURED = {
     "grid_halo_send_ptr": (vp, [vp, i32]),
     "grid_halo_recv_ptr": (vp, [vp, i32]),
     "grid_halo_elems": (i64, [vp]),
+    "grid_p2p_export": (i32, [vp, vp]),
+    "grid_p2p_connect_ipc": (i32, [vp, i32, vp]),
+    "grid_p2p_connect_local": (i32, [vp, i32, vp]),
     "grid_get_marginals": (i32, [vp, vp]),
     "grid_get_messages": (i32, [vp, i32, vp]),
     "grid_stream": (vp, [vp]),

@@ -20,6 +20,8 @@
 // (halo_send_ptr / halo_recv_ptr), see cortex.jl_b200/grid.py.
 #include <cmath>
 
+#include <cstring>
+
 #include "common.cuh"
 
 namespace cxb {
@@ -73,6 +75,10 @@ struct GridView {
     void* marg;
     const void* halo_up;    // m2f(down) of the row above the shard, [W][K]
     const void* halo_down;  // m2f(up) of the row below the shard
+    // fused halo exchange over peer memory (NVLink P2P): where the row-neighbour shard wants this sweep's boundary
+    // messages — its halo buffer of the NEXT sweep's parity — or null (no neighbour / exchange done by the caller)
+    void* peer_up;          // upper neighbour's halo_down slot: receives row 0 of plane `up`
+    void* peer_down;        // lower neighbour's halo_up slot: receives the last row of plane `down`
 };
 
 template <class T, int K, int E>
@@ -165,7 +171,27 @@ __global__ void __launch_bounds__(256) k_potts_sweep(GridView g, T w) {
 #pragma unroll
         for (int k = 0; k < E; ++k) acc[k] = acc[k] / tot;
         if (valid && ex[d]) store_vec<T, E>((T*)g.m2f_nxt[d] + o, acc);
+        // the cut edges: the same message goes straight into the neighbour GPU's halo buffer (peer store over NVLink),
+        // overlapped with the rest of the sweep; cxb_grid_sweep publishes a sweep counter after the kernel
+        if (d == 0 && valid && i == 0 && g.peer_up) store_vec<T, E>((T*)g.peer_up + (size_t)j * K + (size_t)lane * E, acc);
+        if (d == 3 && valid && i + 1 == g.H && g.peer_down) store_vec<T, E>((T*)g.peer_down + (size_t)j * K + (size_t)lane * E, acc);
     }
+}
+
+// stream-ordered hand-shake of the fused halo exchange: sweeps completed by the neighbours are counted in flags that
+// live in THIS shard's memory and are written by the neighbours' k_halo_signal
+__global__ void k_halo_wait(const volatile unsigned* flag_a, const volatile unsigned* flag_b, unsigned expected) {
+    if (flag_a)
+        while (*flag_a < expected) __nanosleep(64);
+    if (flag_b)
+        while (*flag_b < expected) __nanosleep(64);
+    __threadfence_system();
+}
+__global__ void k_halo_signal(unsigned* peer_flag_a, unsigned* peer_flag_b, unsigned value) {
+    __threadfence_system();  // the sweep kernel's peer stores (previous kernel of this stream) are visible before the flag
+    if (peer_flag_a) *(volatile unsigned*)peer_flag_a = value;
+    if (peer_flag_b) *(volatile unsigned*)peer_flag_b = value;
+    __threadfence_system();
 }
 
 template <class T>
@@ -181,12 +207,19 @@ struct Grid {
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     std::string err;
-    DBuf<unsigned char> unary, m2f[2], m2v, marg, halo_recv;  // m2f[b]: 4 planes; m2v: 4 planes; halo_recv: 2 rows
+    DBuf<unsigned char> unary, m2f[2], m2v, marg, halo_recv;  // m2f[b]: 4 planes; m2v: 4 planes; halo_recv: [2 parities][2 rows]
+    DBuf<unsigned> flags;                       // [0] sweeps completed by the upper neighbour, [1] by the lower neighbour
+    unsigned sweep_no = 0;                      // sweeps since the last reset (parity of the halo buffers)
+    unsigned char* peer_halo[2] = {nullptr, nullptr};  // the neighbours' halo_recv (direction 0 = above, 1 = below)
+    unsigned* peer_flags[2] = {nullptr, nullptr};      // the neighbours' flags
+    void* ipc_opened[4] = {nullptr, nullptr, nullptr, nullptr};
     bool have_unary = false, have_msgs = false, ran = false;
     size_t esz() const { return dtype == CXB_F32 ? 4 : 8; }
     size_t plane() const { return (size_t)H * W * K * esz(); }
     size_t row() const { return (size_t)W * K * esz(); }
     ~Grid() {
+        for (void* q : ipc_opened)
+            if (q) cudaIpcCloseMemHandle(q);
         if (ev0) cudaEventDestroy(ev0);
         if (ev1) cudaEventDestroy(ev1);
         if (stream) cudaStreamDestroy(stream);
@@ -212,7 +245,9 @@ struct Grid {
         CXB_CUDA(m2f[1].reserve(4 * plane()));
         CXB_CUDA(m2v.reserve(4 * plane()));
         CXB_CUDA(marg.reserve(plane()));
-        CXB_CUDA(halo_recv.reserve(2 * row()));
+        CXB_CUDA(halo_recv.reserve(4 * row()));
+        CXB_CUDA(flags.reserve(2));
+        CXB_CUDA(cudaMemsetAsync(flags.p, 0, 2 * sizeof(unsigned), stream));
         CXB_CUDA(cudaMemsetAsync(m2v.p, 0, 4 * plane(), stream));
         CXB_CUDA(cudaMemsetAsync(marg.p, 0, plane(), stream));
         return CXB_OK;
@@ -224,12 +259,15 @@ struct Grid {
     }
     int32_t reset() {
         CXB_CUDA(cudaSetDevice(device));
-        size_t n = (size_t)4 * H * W * K, nh = (size_t)2 * W * K;
+        size_t n = (size_t)4 * H * W * K, nh = (size_t)4 * W * K;
         double u = 1.0 / K;
         for (int b = 0; b < 2; ++b) dtype == CXB_F32 ? fill<float>(m2f[b].p, n, u) : fill<double>(m2f[b].p, n, u);
         dtype == CXB_F32 ? fill<float>(halo_recv.p, nh, u) : fill<double>(halo_recv.p, nh, u);
+        // with a fused (peer-memory) exchange every shard of the grid must be idle here: the neighbours' counters restart
+        CXB_CUDA(cudaMemsetAsync(flags.p, 0, 2 * sizeof(unsigned), stream));
         CXB_CUDA(cudaGetLastError());
         cur = 0;
+        sweep_no = 0;
         have_msgs = true;
         return CXB_OK;
     }
@@ -270,15 +308,27 @@ struct Grid {
             g.m2v[d] = m2v.p + (size_t)d * plane();
         }
         g.marg = marg.p;
-        g.halo_up = halo_recv.p;
-        g.halo_down = halo_recv.p + row();
+        // halo buffers are double buffered by sweep parity: sweep s reads parity s & 1 (written by the neighbours' sweep
+        // s - 1, or by the caller's exchange) and pushes its own boundary rows into the neighbours' parity (s + 1) & 1
+        const size_t par = (size_t)(sweep_no & 1) * 2 * row(), nxt_par = (size_t)((sweep_no + 1) & 1) * 2 * row();
+        g.halo_up = halo_recv.p + par;
+        g.halo_down = halo_recv.p + par + row();
+        g.peer_up = peer_halo[0] ? peer_halo[0] + nxt_par + row() : nullptr;   // the upper neighbour's halo_down
+        g.peer_down = peer_halo[1] ? peer_halo[1] + nxt_par : nullptr;         // the lower neighbour's halo_up
         double w = std::exp(beta) - 1.0;
+        const bool fused = peer_halo[0] || peer_halo[1];
+        if (fused && sweep_no > 0)  // the neighbours have finished sweep sweep_no - 1 (their boundary rows have landed here)
+            CXB_LAUNCH(k_halo_wait, 1, 1, 0, stream, peer_halo[0] ? flags.p + 0 : nullptr, peer_halo[1] ? flags.p + 1 : nullptr, sweep_no);
         CXB_CUDA(cudaEventRecord(ev0, stream));
         int32_t st = dtype == CXB_F32 ? launch_k<float, 4>(g, (float)w) : launch_k<double, 2>(g, w);
         if (st) return st;
         CXB_CUDA(cudaEventRecord(ev1, stream));
+        if (fused)  // tell the neighbours: my sweep sweep_no is complete (I am their lower / upper neighbour)
+            CXB_LAUNCH(k_halo_signal, 1, 1, 0, stream, peer_flags[0] ? peer_flags[0] + 1 : nullptr, peer_flags[1] ? peer_flags[1] + 0 : nullptr,
+                       sweep_no + 1);
         CXB_CUDA(cudaGetLastError());
         cur ^= 1;
+        ++sweep_no;
         ran = true;
         if (n_updates) {
             // existing (pixel, direction) pairs: vertical incl. the cut edges, horizontal inside rows
@@ -355,9 +405,57 @@ void* cxb_grid_halo_send_ptr(cxb_grid* g, int32_t direction) {
 }
 void* cxb_grid_halo_recv_ptr(cxb_grid* g, int32_t direction) {
     Grid* h = GR(g);
-    if (direction == 0) return h->halo_recv.p;             // from the upper neighbour (its `down` row)
-    if (direction == 1) return h->halo_recv.p + h->row();  // from the lower neighbour (its `up` row)
+    unsigned char* base = h->halo_recv.p + (size_t)(h->sweep_no & 1) * 2 * h->row();  // the parity the NEXT sweep reads
+    if (direction == 0) return base;             // from the upper neighbour (its `down` row)
+    if (direction == 1) return base + h->row();  // from the lower neighbour (its `up` row)
     return nullptr;
+}
+// ---- fused halo exchange over peer memory ---------------------------------------------------------------------------------
+// export: 2 x 64 bytes = cudaIpcMemHandle_t of the halo buffer and of the sweep counters of THIS shard
+int32_t cxb_grid_p2p_export(cxb_grid* g, void* handles_out) {
+    Grid* h = GR(g);
+    GR_CUDA(g, cudaSetDevice(h->device));
+    cudaIpcMemHandle_t hh[2];
+    GR_CUDA(g, cudaIpcGetMemHandle(&hh[0], h->halo_recv.p));
+    GR_CUDA(g, cudaIpcGetMemHandle(&hh[1], h->flags.p));
+    memcpy(handles_out, hh, sizeof(hh));
+    return CXB_OK;
+}
+// connect the row neighbour in `direction` (0 = above, 1 = below) that lives in ANOTHER process, by its exported handles
+int32_t cxb_grid_p2p_connect_ipc(cxb_grid* g, int32_t direction, const void* neighbour_handles) {
+    Grid* h = GR(g);
+    if (direction != 0 && direction != 1) return CXB_ERR_BAD_ARG;
+    GR_CUDA(g, cudaSetDevice(h->device));
+    cudaIpcMemHandle_t hh[2];
+    memcpy(hh, neighbour_handles, sizeof(hh));
+    void *halo = nullptr, *fl = nullptr;
+    GR_CUDA(g, cudaIpcOpenMemHandle(&halo, hh[0], cudaIpcMemLazyEnablePeerAccess));
+    GR_CUDA(g, cudaIpcOpenMemHandle(&fl, hh[1], cudaIpcMemLazyEnablePeerAccess));
+    h->ipc_opened[2 * direction] = halo;
+    h->ipc_opened[2 * direction + 1] = fl;
+    h->peer_halo[direction] = (unsigned char*)halo;
+    h->peer_flags[direction] = (unsigned*)fl;
+    return CXB_OK;
+}
+// same, for a neighbour shard owned by THIS process (several shards per process; single-GPU tests)
+int32_t cxb_grid_p2p_connect_local(cxb_grid* g, int32_t direction, cxb_grid* neighbour) {
+    Grid *h = GR(g), *nb = GR(neighbour);
+    if ((direction != 0 && direction != 1) || !nb || nb->W != h->W || nb->K != h->K || nb->dtype != h->dtype) return CXB_ERR_BAD_ARG;
+    if (nb->device != h->device) {
+        int can = 0;
+        GR_CUDA(g, cudaDeviceCanAccessPeer(&can, h->device, nb->device));
+        if (!can) {
+            h->err = "no peer access between the two devices";
+            return CXB_ERR_CUDA;
+        }
+        GR_CUDA(g, cudaSetDevice(h->device));
+        cudaError_t e = cudaDeviceEnablePeerAccess(nb->device, 0);
+        if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) GR_CUDA(g, e);
+        (void)cudaGetLastError();
+    }
+    h->peer_halo[direction] = nb->halo_recv.p;
+    h->peer_flags[direction] = nb->flags.p;
+    return CXB_OK;
 }
 int64_t cxb_grid_halo_elems(cxb_grid* g) { return GR(g)->W * GR(g)->K; }
 int32_t cxb_grid_get_marginals(cxb_grid* g, void* out_host) {

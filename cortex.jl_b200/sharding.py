@@ -49,6 +49,28 @@ class HaloExchanger:
             w.wait()
 
 
+def connect_row_neighbours(dist, grid, rank: int, world: int) -> bool:
+    """Fused halo exchange (cxb_grid_p2p_*): every rank publishes the CUDA IPC handles of its halo buffer and sweep
+    counters, opens its row neighbours' and from then on `grid.sweep()` stores the cut-edge messages straight into the
+    neighbour GPU's memory over NVLink — no separate exchange call. Returns False (and connects nothing) when any rank
+    cannot open a neighbour's handle; the caller then keeps using `HaloExchanger` (NCCL)."""
+    if world == 1:
+        return True
+    handles = [None] * world
+    dist.all_gather_object(handles, grid.p2p_export())
+    ok = 1
+    try:
+        if rank > 0:
+            grid.p2p_connect_ipc(0, handles[rank - 1])
+        if rank < world - 1:
+            grid.p2p_connect_ipc(1, handles[rank + 1])
+    except Exception:  # no peer access between the two GPUs
+        ok = 0
+    oks = [None] * world
+    dist.all_gather_object(oks, ok)
+    return all(oks)
+
+
 def device_tensor(ptr: int, n_elems: int, device_index: int, typestr: str = "<f4"):
     """Zero-copy torch view of a device buffer owned by the CUDA library (for NCCL)."""
     import torch

@@ -155,6 +155,19 @@ class PottsGrid(_Handle):
     def halo_elems(self) -> int:
         return int(self.api.grid_halo_elems(self.h))
 
+    # ---- fused halo exchange over peer memory (cxb_grid_p2p_*): after connecting, sweep() delivers the cut-edge messages
+    def p2p_export(self) -> bytes:
+        buf = C.create_string_buffer(128)
+        self.check(self.api.grid_p2p_export(self.h, buf))
+        return buf.raw
+
+    def p2p_connect_ipc(self, direction: int, handles: bytes) -> None:
+        buf = C.create_string_buffer(bytes(handles), 128)
+        self.check(self.api.grid_p2p_connect_ipc(self.h, direction, buf))
+
+    def p2p_connect_local(self, direction: int, neighbour: "PottsGrid") -> None:
+        self.check(self.api.grid_p2p_connect_local(self.h, direction, neighbour.h))
+
 
 class HmmBatch(_Handle):
     """B discrete HMMs (K states, M symbols, T steps): scaled forward-backward."""

@@ -251,6 +251,15 @@ int32_t cxb_grid_sweep(cxb_grid* g, int64_t* n_updates_out);
 void* cxb_grid_halo_send_ptr(cxb_grid* g, int32_t direction);
 void* cxb_grid_halo_recv_ptr(cxb_grid* g, int32_t direction);
 int64_t cxb_grid_halo_elems(cxb_grid* g);
+/* Fused halo exchange over peer memory (NVLink P2P): once a row neighbour is connected, cxb_grid_sweep itself delivers
+ * the messages of the cut edges — the sweep kernel stores them straight into the neighbour GPU's halo buffer and a sweep
+ * counter is published after the kernel; the next sweep waits (on the stream) for the neighbours' counters. No separate
+ * exchange call is needed for a connected direction (0 = the shard above, 1 = the shard below). The reference has no
+ * counterpart (single process, src/inference_engine.jl:559-632); SURVEY 8e.
+ * cxb_grid_p2p_export writes 128 bytes (two cudaIpcMemHandle_t); cxb_grid_reset_messages requires every shard idle. */
+int32_t cxb_grid_p2p_export(cxb_grid* g, void* handles_out);
+int32_t cxb_grid_p2p_connect_ipc(cxb_grid* g, int32_t direction, const void* neighbour_handles);
+int32_t cxb_grid_p2p_connect_local(cxb_grid* g, int32_t direction, cxb_grid* neighbour);
 /* marginals [rows][cols][K] engine dtype, D2H */
 int32_t cxb_grid_get_marginals(cxb_grid* g, void* out_host);
 /* message planes for parity: which = 0..3 m2v from (up,down,left,right) factor, 4..7 m2f to them; D2H */
