@@ -608,6 +608,11 @@ struct Pairwise {
     int device = 0, dtype = CXB_F32, K = 0, n_tables = 0, cur = 0;
     long long n = 0, m = 0;
     cudaStream_t stream = nullptr;
+    // the bins of one sweep touch disjoint variables: they are launched on side streams (fork / join with events) so that
+    // the light kernels and the three dependent hub launches fill the SMs the heavy ones leave idle
+    static constexpr int N_AUX = 3;
+    cudaStream_t aux[N_AUX] = {nullptr, nullptr, nullptr}, ls = nullptr;  // ls = stream of the launch helpers
+    cudaEvent_t ev_fork = nullptr, ev_join[N_AUX] = {nullptr, nullptr, nullptr};
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     std::string err;
     // work bins: 0 = exact path (<= 4 factors), 1 + log2(G) = teams of G groups, then hub chunks and hubs
@@ -629,6 +634,11 @@ struct Pairwise {
     ~Pairwise() {
         if (ev0) cudaEventDestroy(ev0);
         if (ev1) cudaEventDestroy(ev1);
+        if (ev_fork) cudaEventDestroy(ev_fork);
+        for (int i = 0; i < N_AUX; ++i) {
+            if (ev_join[i]) cudaEventDestroy(ev_join[i]);
+            if (aux[i]) cudaStreamDestroy(aux[i]);
+        }
         if (stream) cudaStreamDestroy(stream);
     }
     int32_t init() {
@@ -654,6 +664,12 @@ struct Pairwise {
         CXB_CUDA(cudaEventCreate(&ev0));
         CXB_CUDA(cudaEventCreate(&ev1));
         CXB_CUDA(cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, device));
+        CXB_CUDA(cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming));
+        for (int i = 0; i < N_AUX; ++i) {
+            CXB_CUDA(cudaStreamCreateWithFlags(&aux[i], cudaStreamNonBlocking));
+            CXB_CUDA(cudaEventCreateWithFlags(&ev_join[i], cudaEventDisableTiming));
+        }
+        ls = stream;
         return CXB_OK;
     }
     int32_t set_graph(const int64_t* fu, const int64_t* fv, const int32_t* ft) {
@@ -858,7 +874,7 @@ struct Pairwise {
             if (!bin.n) return;
             if (tb > 48 * 1024)
                 cudaFuncSetAttribute(k_pw_team<T, KK, G, PW_MODE_FULL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tb);
-            CXB_LAUNCH((k_pw_team<T, KK, G, PW_MODE_FULL>), grid_for((size_t)bin.n * TL), 256, tb, stream, g, bin.view());
+            CXB_LAUNCH((k_pw_team<T, KK, G, PW_MODE_FULL>), grid_for((size_t)bin.n * TL), 256, tb, ls, g, bin.view());
         }
     }
     template <class T, int KK, int G>
@@ -868,34 +884,48 @@ struct Pairwise {
             if (G != g_max || !chunk_bin.n) return;
             if (tb > 48 * 1024)
                 cudaFuncSetAttribute(k_pw_team<T, KK, G, PW_MODE_H1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tb);
-            CXB_LAUNCH((k_pw_team<T, KK, G, PW_MODE_H1>), grid_for((size_t)chunk_bin.n * TL), 256, tb, stream, g, chunk_bin.view());
-            CXB_LAUNCH((k_pw_hub_scan<T, KK>), cdiv((size_t)hub_bin.n * L, 128), 128, 0, stream, g, hub_bin.view());
-            CXB_LAUNCH((k_pw_team<T, KK, G, PW_MODE_H3>), grid_for((size_t)chunk_bin.n * TL), 256, 0, stream, g, chunk_bin.view());
+            CXB_LAUNCH((k_pw_team<T, KK, G, PW_MODE_H1>), grid_for((size_t)chunk_bin.n * TL), 256, tb, ls, g, chunk_bin.view());
+            CXB_LAUNCH((k_pw_hub_scan<T, KK>), cdiv((size_t)hub_bin.n * L, 128), 128, 0, ls, g, hub_bin.view());
+            CXB_LAUNCH((k_pw_team<T, KK, G, PW_MODE_H3>), grid_for((size_t)chunk_bin.n * TL), 256, 0, ls, g, chunk_bin.view());
         }
     }
     template <class T, int KK>
     int32_t launch_k(const PwView& g) {
         size_t tb = (size_t)tab_elems * sizeof(T);
-        // hubs first (their three dependent launches are the long pole), then the bins from heavy to light
+        const bool multi = !(getenv("CXB_PW_ONE_STREAM") && atoi(getenv("CXB_PW_ONE_STREAM")));
+        if (multi) {
+            cudaEventRecord(ev_fork, stream);
+            for (int i = 0; i < N_AUX; ++i) cudaStreamWaitEvent(aux[i], ev_fork, 0);
+        }
+        // side stream 0: hubs (three dependent launches) and the large teams; 1: teams of 4 and 2; 2: teams of 1; main: exact
+        ls = multi ? aux[0] : stream;
         launch_hubs<T, KK, 16>(g, tb);
         launch_hubs<T, KK, 8>(g, tb);
         launch_hubs<T, KK, 4>(g, tb);
         launch_team<T, KK, 16>(g, tb);
         launch_team<T, KK, 8>(g, tb);
+        ls = multi ? aux[1] : stream;
         launch_team<T, KK, 4>(g, tb);
         launch_team<T, KK, 2>(g, tb);
+        ls = multi ? aux[2] : stream;
         launch_team<T, KK, 1>(g, tb);
+        ls = stream;
         if (exact_bin.n) {
             int minb = 2;
             if (const char* e = getenv("CXB_PW_MINB")) minb = atoi(e);
             if (minb >= 3) {
                 if (tb > 48 * 1024) cudaFuncSetAttribute(k_pw_exact<T, KK, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tb);
-                CXB_LAUNCH((k_pw_exact<T, KK, 3>), grid_for((size_t)exact_bin.n * PwGeo<KK>::L), 256, tb, stream, g, exact_bin.view());
+                CXB_LAUNCH((k_pw_exact<T, KK, 3>), grid_for((size_t)exact_bin.n * PwGeo<KK>::L), 256, tb, ls, g, exact_bin.view());
             } else {
                 if (tb > 48 * 1024) cudaFuncSetAttribute(k_pw_exact<T, KK, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tb);
-                CXB_LAUNCH((k_pw_exact<T, KK, 2>), grid_for((size_t)exact_bin.n * PwGeo<KK>::L), 256, tb, stream, g, exact_bin.view());
+                CXB_LAUNCH((k_pw_exact<T, KK, 2>), grid_for((size_t)exact_bin.n * PwGeo<KK>::L), 256, tb, ls, g, exact_bin.view());
             }
         }
+        if (multi)
+            for (int i = 0; i < N_AUX; ++i) {
+                cudaEventRecord(ev_join[i], aux[i]);
+                cudaStreamWaitEvent(stream, ev_join[i], 0);
+            }
         return CXB_OK;
     }
     template <class T>
