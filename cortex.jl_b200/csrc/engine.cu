@@ -257,11 +257,8 @@ __global__ void k_pending_single(View e, uint32_t s, int* out) { *out = pending_
 // the scalar m2v rules. rule < 0 => family reduce (m2f / ProductOfMessages / marginal), left-to-right
 // (test/inference_engine_tests.jl:385-413).
 template <class T>
-__global__ void k_rule_small(View e, T* __restrict__ val, const uint32_t* list, uint32_t n, int family, int rule,
-                             const T* __restrict__ fparam, T default_param) {
-    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    uint32_t s = list[i];
+__device__ __forceinline__ void rule_small_one(const View& e, T* __restrict__ val, uint32_t s, int family, int rule,
+                                               const T* __restrict__ fparam, T default_param) {
     const int dim = e.dim;
     uint32_t off = e.dep_off[s], nd = e.dep_off[s + 1] - off;
     T acc[4] = {0, 0, 0, 0};
@@ -330,6 +327,172 @@ __global__ void k_rule_small(View e, T* __restrict__ val, const uint32_t* list, 
     }
     T* o = val + (size_t)s * dim;
     for (int k = 0; k < dim; ++k) o[k] = acc[k];
+}
+template <class T>
+__global__ void k_rule_small(View e, T* __restrict__ val, const uint32_t* list, uint32_t n, int family, int rule,
+                             const T* __restrict__ fparam, T default_param) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    rule_small_one<T>(e, val, list[i], family, rule, fparam, default_param);
+}
+
+// ---- resident level loop --------------------------------------------------------------------------------------------------
+// update_marginals! (src/inference_engine.jl:559-632) of a SMALL graph entirely on the device: one CTA runs request
+// levels, breadth-first discovery, independence check, rules, set_value! side effects, readiness and the final phase in
+// a loop with block barriers only — no kernel launch and no host round trip per level (a T = 1000 chain has 2T-1
+// levels of 2-3 signals each). Same device functions, same state machine and the same frontier sets as the
+// per-level kernels above; used for the small-value families when no trace is requested.
+constexpr int ERR_NO_RULE_KEY = 8;
+struct ResidentArgs {
+    const uint32_t* req_marg;
+    const uint32_t* link_ids;
+    uint8_t* ready;
+    uint32_t n_req, n_links;
+    uint32_t *list_a, *list_b;
+    uint32_t req_epoch, lvl_epoch0;
+    int n_keys, family;
+    const int* key_rule;       // [n_keys] rule kind of a key: -1 = family reduce, -2 = no rule registered
+    const double* key_param;   // [n_keys] default parameter of the key's rule
+    const void* fparam;        // per factor id, NaN = unset
+    long long* out;            // [0] levels [1] updates [2] final marginals [3] final linked [4] last lvl_epoch [5] key without rule
+};
+__device__ __forceinline__ void apply_one(const View& e, uint32_t s, uint32_t req_epoch, int check_mode) {
+    for (uint32_t c = e.nib_off[s]; c < e.nib_off[s + 1]; ++c) e.nib[c] &= ~ALL_F;  // unset_all_dependencies_fresh!
+    e.props[s] = P_COMPUTED;
+    if (check_mode) e.done_epoch[s] = req_epoch;
+    atomicAdd(&e.kind_count[e.kind[s]], 1ull);
+    for (uint32_t k = e.lis_off[s]; k < e.lis_off[s + 1]; ++k) notify(e, k, req_epoch, check_mode);
+}
+template <class T>
+__global__ void __launch_bounds__(1024) k_update_resident(View e, T* __restrict__ val, ResidentArgs a) {
+    __shared__ uint32_t s_cnt[2];
+    __shared__ uint32_t s_total;
+    __shared__ uint32_t s_key_cnt[256], s_key_base[256];  // per-key frontier cursors / partition starts (<= 252 keys)
+    __shared__ int s_key_rule[256];
+    const uint32_t tid = threadIdx.x, NT = blockDim.x;
+    for (int k = tid; k < a.n_keys; k += NT) {
+        s_key_base[k] = e.key_base[k];
+        s_key_rule[k] = a.key_rule[k];
+    }
+    e.key_cnt = s_key_cnt;    // frontier_push bumps the cursors in shared memory
+    e.key_base = s_key_base;
+    __syncthreads();
+    uint32_t lvl = a.lvl_epoch0;
+    long long levels = 0, updates = 0, fin[2] = {0, 0};
+
+    // the members of the current level (per-key segments of the frontier buffer): independence, rules, side effects
+    auto run_level = [&](int check_mode) {
+        for (int k = 0; k < a.n_keys; ++k) {
+            const uint32_t cnt = e.key_cnt[k], base = e.key_base[k];
+            for (uint32_t i = tid; i < cnt; i += NT) {
+                const uint32_t s = e.front[base + i];
+                for (uint32_t d = e.dep_off[s]; d < e.dep_off[s + 1]; ++d)
+                    if (e.front_epoch[e.dep_ids[d]] == lvl) atomicOr(e.err_flag, ERR_INDEPENDENCE);
+            }
+        }
+        __syncthreads();
+        for (int k = 0; k < a.n_keys; ++k) {
+            const uint32_t cnt = e.key_cnt[k], base = e.key_base[k];
+            if (!cnt) continue;
+            const int rule = s_key_rule[k];
+            if (rule == -2) {
+                if (tid == 0) {
+                    atomicOr(e.err_flag, ERR_NO_RULE_KEY);
+                    a.out[5] = k;
+                }
+                continue;
+            }
+            const T defp = (T)a.key_param[k];
+            for (uint32_t i = tid; i < cnt; i += NT) rule_small_one<T>(e, val, e.front[base + i], a.family, rule, (const T*)a.fparam, defp);
+        }
+        __syncthreads();
+        for (int k = 0; k < a.n_keys; ++k) {
+            const uint32_t cnt = e.key_cnt[k], base = e.key_base[k];
+            for (uint32_t i = tid; i < cnt; i += NT) apply_one(e, e.front[base + i], a.req_epoch, check_mode);
+        }
+        __syncthreads();
+    };
+    auto begin_level = [&]() {
+        ++lvl;
+        if (tid == 0) s_cnt[0] = s_cnt[1] = 0;
+        for (int k = tid; k < a.n_keys; k += NT) e.key_cnt[k] = 0;
+        __syncthreads();
+    };
+    auto frontier_total = [&]() -> uint32_t {
+        if (tid == 0) {
+            uint32_t t = 0;
+            for (int k = 0; k < a.n_keys; ++k) t += e.key_cnt[k];
+            s_total = t;
+        }
+        __syncthreads();
+        const uint32_t t = s_total;
+        __syncthreads();
+        return t;
+    };
+
+    while (a.n_req) {
+        begin_level();
+        for (uint32_t i = tid; i < a.n_req; i += NT)
+            if (!a.ready[i]) a.list_a[atomicAdd(&s_cnt[0], 1u)] = a.req_marg[i];  // seeds (:585)
+        __syncthreads();
+        int which = 0;
+        for (;;) {  // process_dependencies!, one breadth-first step per iteration
+            const uint32_t n_in = s_cnt[which];
+            __syncthreads();
+            if (n_in == 0) break;
+            if (tid == 0) s_cnt[which ^ 1] = 0;
+            __syncthreads();
+            const uint32_t* in = which ? a.list_b : a.list_a;
+            uint32_t* out = which ? a.list_a : a.list_b;
+            for (uint32_t i = tid; i < n_in; i += NT) {
+                const uint32_t s = in[i];
+                const uint32_t off = e.dep_off[s], nd = e.dep_off[s + 1] - off, noff = e.nib_off[s];
+                for (uint32_t k = 0; k < nd; ++k) {
+                    const uint32_t d = e.dep_ids[off + k];
+                    if (e.done_epoch[d] == a.req_epoch) continue;
+                    if (pending_eval(e, d)) {
+                        frontier_push(e, d, lvl);
+                    } else {
+                        const uint32_t nibble = (uint32_t)(e.nib[noff + (k >> 4)] >> ((k & 15) << 2)) & 0xF;
+                        if ((nibble & CXB_NIB_INTERMEDIATE) && atomicExch(&e.visit_epoch[d], lvl) != lvl)
+                            out[atomicAdd(&s_cnt[which ^ 1], 1u)] = d;
+                    }
+                }
+            }
+            __syncthreads();
+            which ^= 1;
+        }
+        const uint32_t total = frontier_total();
+        if (!total) break;
+        run_level(1);
+        if (*(volatile int*)e.err_flag) break;  // uniform: every thread reads it after the barrier that ends run_level
+        for (uint32_t i = tid; i < a.n_req; i += NT)
+            if (!a.ready[i] && pending_eval(e, a.req_marg[i])) a.ready[i] = 1;  // readiness (:593-595)
+        ++levels;
+        updates += total;
+        __syncthreads();
+    }
+    for (int mode = 0; mode < 2 && a.n_req; ++mode) {  // final phase: marginals, then linked signals (:610-628)
+        if (*(volatile int*)e.err_flag) break;
+        begin_level();
+        const uint32_t cnt = mode == 0 ? a.n_req : a.n_links;
+        for (uint32_t i = tid; i < cnt; i += NT) {
+            const uint32_t s = mode == 0 ? a.req_marg[i] : a.link_ids[i];
+            if (pending_eval(e, s)) frontier_push(e, s, lvl);
+        }
+        __syncthreads();
+        const uint32_t total = frontier_total();
+        fin[mode] = total;
+        if (total) run_level(2);
+        updates += total;
+    }
+    if (tid == 0) {
+        a.out[0] = levels;
+        a.out[1] = updates;
+        a.out[2] = fin[0];
+        a.out[3] = fin[1];
+        a.out[4] = lvl;
+    }
 }
 
 // Categorical values (dim = K states): G lanes cooperate on one signal (G = min(32, pow2 >= K)), lane l owns
@@ -479,6 +642,13 @@ struct DeviceEngine {
     DBuf<int> d_flags;  // [0] err flag, [1] scratch int
     DBuf<uint32_t> d_counters;
     DBuf<unsigned long long> d_kind_count;
+    // resident level loop (k_update_resident): per-key rule table, result slots
+    DBuf<int> d_key_rule;
+    DBuf<double> d_key_param;
+    DBuf<long long> d_res_out;
+    HBuf<long long> h_res_out;
+    std::vector<int> h_key_rule;
+    std::vector<double> h_key_param;
     HBuf<uint32_t> h_counts;
     HBuf<unsigned char> h_stage;
     HBuf<int> h_flags;
@@ -1005,6 +1175,81 @@ struct DeviceEngine {
         return CXB_OK;
     }
 
+    // the whole update on the device in one launch (k_update_resident): small graphs, small-value families, no trace
+    bool resident_ok() {
+        if (const char* e = getenv("CXB_ENGINE_RESIDENT"))
+            if (!atoi(e)) return false;
+        return !trace_on && family != CXB_FAMILY_CATEGORICAL && dim <= 4 && g.n_sig() <= 65536;
+    }
+    int32_t update_resident(unsigned long long launches0) {
+        const int nk = n_keys();
+        h_key_rule.assign((size_t)nk, -2);
+        h_key_param.assign((size_t)nk, 1.0);
+        h_key_rule[KEY_COMBINE] = -1;
+        for (int k = 1; k < nk - 1; ++k) {
+            auto it = rules.find(key_ftype[k - 1]);
+            if (it == rules.end() || it->second.kind == CXB_RULE_NONE) continue;
+            const int kind = it->second.kind;
+            if (kind == CXB_RULE_CAT_TABLE || kind == CXB_RULE_POTTS || kind == CXB_RULE_HMM_EMIT) {
+                err = "rule kind does not match the engine's value family";
+                return CXB_ERR_BAD_ARG;
+            }
+            h_key_rule[k] = kind;
+            if (!it->second.params.empty()) h_key_param[k] = it->second.params[0];
+        }
+        int32_t st;
+        if ((st = up(d_key_rule, h_key_rule.data(), (size_t)nk))) return st;
+        if ((st = up(d_key_param, h_key_param.data(), (size_t)nk))) return st;
+        CXB_CUDA(d_res_out.reserve(8));
+        CXB_CUDA(h_res_out.reserve(8));
+        CXB_CUDA(cudaMemsetAsync(d_res_out.p, 0, 8 * sizeof(long long), stream));
+        cur_use_keys = true;
+        ResidentArgs a{};
+        a.req_marg = d_req_marg.p;
+        a.link_ids = d_link_ids.p;
+        a.ready = d_ready.p;
+        a.n_req = n_req;
+        a.n_links = n_links;
+        a.list_a = d_list_a.p;
+        a.list_b = d_list_b.p;
+        a.req_epoch = req_epoch;
+        a.lvl_epoch0 = lvl_epoch;
+        a.n_keys = nk;
+        a.family = family;
+        a.key_rule = d_key_rule.p;
+        a.key_param = d_key_param.p;
+        a.fparam = d_fparam.p;
+        a.out = d_res_out.p;
+        int threads = 1024;  // measured on the T = 1000 chain: 1024 threads 19 ms, 256 threads 27 ms (the per-level passes over the requested marginals dominate)
+        if (const char* e = getenv("CXB_ENGINE_RESIDENT_THREADS")) threads = std::max(32, std::min(1024, atoi(e) / 32 * 32));
+        if (dtype == CXB_F32)
+            CXB_LAUNCH(k_update_resident<float>, 1, threads, 0, stream, view(), (float*)d_val.p, a);
+        else
+            CXB_LAUNCH(k_update_resident<double>, 1, threads, 0, stream, view(), (double*)d_val.p, a);
+        CXB_CUDA(cudaMemcpyAsync(h_res_out.p, d_res_out.p, 8 * sizeof(long long), cudaMemcpyDeviceToHost, stream));
+        CXB_CUDA(cudaMemcpyAsync(h_kind_count.p, d_kind_count.p, 6 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, stream));
+        CXB_CUDA(cudaMemcpyAsync(h_flags.p, d_flags.p, sizeof(int), cudaMemcpyDeviceToHost, stream));
+        CXB_CUDA(cudaStreamSynchronize(stream));
+        lvl_epoch = (uint32_t)h_res_out.p[4];
+        stats.levels = h_res_out.p[0];
+        stats.updates = h_res_out.p[1];
+        stats.final_marginals = h_res_out.p[2];
+        stats.final_linked = h_res_out.p[3];
+        for (int k = 0; k < 6; ++k) stats.updates_by_kind[k] = (int64_t)h_kind_count.p[k];
+        stats.kernel_launches = (int64_t)(g_kernel_launches - launches0);
+        const int f = h_flags.p[0];
+        if (f & ERR_NO_RULE_KEY) {
+            cudaMemsetAsync(d_flags.p, 0, sizeof(int), stream);
+            const int k = (int)h_res_out.p[5];
+            if (k == key_no_rule())
+                err = "Unprocessed signal variant (no rule for an Unspecified / JointMarginal signal)";
+            else
+                err = "The function `compute_message_to_variable!` is not implemented for factor type " + std::to_string(key_ftype[k - 1]);
+            return CXB_ERR_NO_RULE;
+        }
+        return flags_to_status(f);
+    }
+
     int32_t update(int64_t n, const int64_t* ids) {
         unsigned long long launches0 = g_kernel_launches;
         stats = cxb_update_stats{};
@@ -1013,6 +1258,7 @@ struct DeviceEngine {
         int32_t st = request(n, ids);
         if (st) return st;
         CXB_CUDA(cudaMemsetAsync(d_kind_count.p, 0, 8 * sizeof(unsigned long long), stream));
+        if (resident_ok()) return update_resident(launches0);
         int64_t level = 0;
         while (n_req) {
             if ((st = find_frontier(true, true))) return st;

@@ -124,6 +124,38 @@ def test_out_of_contract_is_refused_not_silently_different(device_api):
         C.update_marginals(e, vids)
 
 
+@pytest.mark.parametrize("model", ["ssm", "beta"])
+def test_resident_level_loop_equals_per_level_kernels(device_api, model, monkeypatch):
+    """update_marginals! of a small graph in ONE launch (k_update_resident) leaves exactly the state, values and
+    statistics of the per-level kernels (frontier discovery -> host -> rule kernels -> apply, one round trip per level)."""
+    out = []
+    for resident in ("1", "0"):
+        monkeypatch.setenv("CXB_ENGINE_RESIDENT", resident)
+        if model == "ssm":
+            T = 60
+            e, x, y, lik, tr = models.make_ssm_model(T, device_api, form="canon", q=0.7, r=1.3)
+            data = np.cumsum(np.random.Generator(np.random.PCG64(5)).standard_normal(T))
+            st = []
+            for rep in range(2):  # a second request with fresh data exercises the epochs
+                models.ssm_set_data(e, y, lik, data + rep)
+                st.append(C.update_marginals(e, x))
+            assert st[0].updates == 6 * T - 4 and st[1].updates == 6 * T - 4
+        else:
+            n = 40
+            e, p, o, f = models.make_beta_bernoulli_model(n, device_api)
+            obs = np.random.Generator(np.random.PCG64(6)).integers(0, 2, size=n).astype(np.float64)
+            C.set_values([C.get_connection_message_to_factor(e, o[i], f[i]) for i in range(n)], obs.reshape(-1, 1))
+            st = [C.update_marginals(e, p)]
+            assert st[0].updates == 2 * n - 1  # n m2v + (n - 2) products + 1 marginal
+        out.append((models.engine_state(e), [(s.levels, s.updates, s.final_marginals, s.final_linked, tuple(s.updates_by_kind)) for s in st],
+                    [s.kernel_launches for s in st]))
+    (state_r, stats_r, launches_r), (state_h, stats_h, launches_h) = out
+    assert stats_r == stats_h
+    assert max(launches_r) <= 3 < min(launches_h)  # request + resident loop vs a dozen launches per level
+    assert state_r[0] == state_h[0]  # computed / pending flags and dependency nibbles of every signal
+    np.testing.assert_array_equal(state_r[1], state_h[1])  # values, bit for bit
+
+
 @pytest.mark.parametrize("dtype", [cap.F64, cap.F32])
 def test_hmm_engine_parity(oracle_api, device_api, dtype):
     T, K, M = 12, 8, 5
