@@ -172,4 +172,108 @@ function get_marginals(c::GaussianChainBatch)
     return out
 end
 
+# ---- structured engines of the other model families (same pattern: opaque handle, status codes, host arrays borrowed) ----
+
+"Row shard of a Potts grid (BASELINE config 4). Neighbour shards live in other processes (one Julia process per GPU)."
+mutable struct PottsGridShard
+    handle::Ptr{Cvoid}
+    rows::Int
+    cols::Int
+    K::Int
+end
+function PottsGridShard(rows::Int, cols::Int, K::Int, beta::Float64; dtype::Integer = F32, device::Integer = 0,
+                        has_upper::Bool = false, has_lower::Bool = false)
+    href = Ref{Ptr{Cvoid}}(C_NULL)
+    st = ccall((:cxb_grid_create, LIB), Int32, (Int32, Int32, Int64, Int64, Int32, Float64, Int32, Int32, Ref{Ptr{Cvoid}}),
+               device, dtype, rows, cols, K, beta, has_upper, has_lower, href)
+    st == OK || error("cxb_grid_create failed with status $st (CUDA device required; there is no CPU fallback)")
+    g = PottsGridShard(href[], rows, cols, K)
+    finalizer(x -> ccall((:cxb_grid_destroy, LIB), Cvoid, (Ptr{Cvoid},), x.handle), g)
+    return g
+end
+grid_check(g::PottsGridShard, st::Int32) =
+    st == OK || error(unsafe_string(ccall((:cxb_grid_last_error, LIB), Cstring, (Ptr{Cvoid},), g.handle)))
+set_unary!(g::PottsGridShard, unary::Array{Float32, 3}) =            # K x cols x rows (column-major = [rows][cols][K] in C)
+    grid_check(g, ccall((:cxb_grid_set_unary, LIB), Int32, (Ptr{Cvoid}, Ptr{Cvoid}), g.handle, unary))
+reset_messages!(g::PottsGridShard) = grid_check(g, ccall((:cxb_grid_reset_messages, LIB), Int32, (Ptr{Cvoid},), g.handle))
+function sweep!(g::PottsGridShard)                                   # one synchronous sweep = protocol B of SURVEY Appendix B
+    n = Ref{Int64}(0)
+    grid_check(g, ccall((:cxb_grid_sweep, LIB), Int32, (Ptr{Cvoid}, Ref{Int64}), g.handle, n))
+    return n[]
+end
+"128 bytes (two cudaIpcMemHandle_t) to hand to the row neighbours, e.g. with MPI.Sendrecv!."
+function p2p_export(g::PottsGridShard)
+    handles = Vector{UInt8}(undef, 128)
+    grid_check(g, ccall((:cxb_grid_p2p_export, LIB), Int32, (Ptr{Cvoid}, Ptr{UInt8}), g.handle, handles))
+    return handles
+end
+"direction 0 = the shard above, 1 = the shard below; afterwards sweep! delivers the cut-edge messages itself (NVLink peer stores)."
+p2p_connect!(g::PottsGridShard, direction::Integer, neighbour_handles::Vector{UInt8}) =
+    grid_check(g, ccall((:cxb_grid_p2p_connect_ipc, LIB), Int32, (Ptr{Cvoid}, Int32, Ptr{UInt8}), g.handle, direction, neighbour_handles))
+function get_marginals(g::PottsGridShard)
+    out = Array{Float32, 3}(undef, g.K, g.cols, g.rows)
+    grid_check(g, ccall((:cxb_grid_get_marginals, LIB), Int32, (Ptr{Cvoid}, Ptr{Cvoid}), g.handle, out))
+    return out
+end
+
+"Batch of discrete HMMs (BASELINE config 3): K = 64 register kernel, K >= 128 tcgen05 path, otherwise the generic kernel."
+mutable struct HmmBatch
+    handle::Ptr{Cvoid}
+    B::Int
+    T::Int
+    K::Int
+end
+function HmmBatch(n_chains::Int, n_steps::Int, n_states::Int, n_symbols::Int; dtype::Integer = F32, device::Integer = 0)
+    href = Ref{Ptr{Cvoid}}(C_NULL)
+    st = ccall((:cxb_hmm_create, LIB), Int32, (Int32, Int32, Int64, Int64, Int32, Int32, Ref{Ptr{Cvoid}}),
+               device, dtype, n_chains, n_steps, n_states, n_symbols, href)
+    st == OK || error("cxb_hmm_create failed with status $st")
+    m = HmmBatch(href[], n_chains, n_steps, n_states)
+    finalizer(x -> ccall((:cxb_hmm_destroy, LIB), Cvoid, (Ptr{Cvoid},), x.handle), m)
+    return m
+end
+hmm_check(m::HmmBatch, st::Int32) = st == OK || error(unsafe_string(ccall((:cxb_hmm_last_error, LIB), Cstring, (Ptr{Cvoid},), m.handle)))
+set_tables!(m::HmmBatch, transition::Matrix{Float64}, emission::Matrix{Float64}) =   # row-major on the C side: pass transposes
+    hmm_check(m, ccall((:cxb_hmm_set_tables, LIB), Int32, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}), m.handle,
+                       permutedims(transition), permutedims(emission)))
+set_observations!(m::HmmBatch, obs::Matrix{UInt8}) =                 # B x T (column-major = [T][B] in C)
+    hmm_check(m, ccall((:cxb_hmm_set_observations, LIB), Int32, (Ptr{Cvoid}, Ptr{UInt8}), m.handle, obs))
+function update_marginals!(m::HmmBatch)
+    n = Ref{Int64}(0)
+    hmm_check(m, ccall((:cxb_hmm_update_marginals, LIB), Int32, (Ptr{Cvoid}, Ref{Int64}), m.handle, n))
+    return n[]
+end
+function get_marginals(m::HmmBatch, t0::Int = 0, t1::Int = m.T)      # K x B x (t1 - t0)
+    out = Array{Float32, 3}(undef, m.K, m.B, t1 - t0)
+    hmm_check(m, ccall((:cxb_hmm_get_marginals, LIB), Int32, (Ptr{Cvoid}, Int64, Int64, Ptr{Cvoid}), m.handle, t0, t1, out))
+    return out
+end
+
+"Arbitrary pairwise categorical graph, loopy BP by synchronous sweeps (BASELINE config 5). Ids are 0-based on the C side."
+mutable struct PairwiseGraph
+    handle::Ptr{Cvoid}
+    n::Int
+    K::Int
+end
+function PairwiseGraph(n_variables::Int, fac_u::Vector{Int64}, fac_v::Vector{Int64}, fac_table::Vector{Int32},
+                       tables::Array{Float64, 3}; dtype::Integer = F32, device::Integer = 0)   # tables: K x K x n_tables, [x_hi, x_lo, t]
+    K, n_tables = size(tables, 1), size(tables, 3)
+    href = Ref{Ptr{Cvoid}}(C_NULL)
+    st = ccall((:cxb_pairwise_create, LIB), Int32, (Int32, Int32, Int64, Int64, Int32, Int32, Ref{Ptr{Cvoid}}),
+               device, dtype, n_variables, length(fac_u), K, n_tables, href)
+    st == OK || error("cxb_pairwise_create failed with status $st")
+    g = PairwiseGraph(href[], n_variables, K)
+    finalizer(x -> ccall((:cxb_pairwise_destroy, LIB), Cvoid, (Ptr{Cvoid},), x.handle), g)
+    chk(s) = s == OK || error(unsafe_string(ccall((:cxb_pairwise_last_error, LIB), Cstring, (Ptr{Cvoid},), g.handle)))
+    chk(ccall((:cxb_pairwise_set_graph, LIB), Int32, (Ptr{Cvoid}, Ptr{Int64}, Ptr{Int64}, Ptr{Int32}), g.handle, fac_u .- 1, fac_v .- 1, fac_table))
+    chk(ccall((:cxb_pairwise_set_tables, LIB), Int32, (Ptr{Cvoid}, Ptr{Float64}), g.handle, tables))
+    return g
+end
+function sweep!(g::PairwiseGraph)
+    n = Ref{Int64}(0)
+    st = ccall((:cxb_pairwise_sweep, LIB), Int32, (Ptr{Cvoid}, Ref{Int64}), g.handle, n)
+    st == OK || error(unsafe_string(ccall((:cxb_pairwise_last_error, LIB), Cstring, (Ptr{Cvoid},), g.handle)))
+    return n[]
+end
+
 end # module
