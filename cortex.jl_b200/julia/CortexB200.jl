@@ -269,6 +269,15 @@ function PairwiseGraph(n_variables::Int, fac_u::Vector{Int64}, fac_v::Vector{Int
     chk(ccall((:cxb_pairwise_set_tables, LIB), Int32, (Ptr{Cvoid}, Ptr{Float64}), g.handle, tables))
     return g
 end
+pw_check(g::PairwiseGraph, st::Int32) = st == OK || error(unsafe_string(ccall((:cxb_pairwise_last_error, LIB), Cstring, (Ptr{Cvoid},), g.handle)))
+set_unary!(g::PairwiseGraph, unary::Matrix{Float32}) =               # K x n
+    pw_check(g, ccall((:cxb_pairwise_set_unary, LIB), Int32, (Ptr{Cvoid}, Ptr{Cvoid}), g.handle, unary))
+reset_messages!(g::PairwiseGraph) = pw_check(g, ccall((:cxb_pairwise_reset_messages, LIB), Int32, (Ptr{Cvoid},), g.handle))
+function get_marginals(g::PairwiseGraph)
+    out = Matrix{Float32}(undef, g.K, g.n)
+    pw_check(g, ccall((:cxb_pairwise_get_marginals, LIB), Int32, (Ptr{Cvoid}, Ptr{Cvoid}), g.handle, out))
+    return out
+end
 function sweep!(g::PairwiseGraph)
     n = Ref{Int64}(0)
     st = ccall((:cxb_pairwise_sweep, LIB), Int32, (Ptr{Cvoid}, Ref{Int64}), g.handle, n)
