@@ -65,6 +65,19 @@ __device__ __forceinline__ T group_sum(const T (&v)[E]) {
     return s;
 }
 
+// 1 / x for a positive normal x. fp32: MUFU.RCP + one Newton step (<= 1 ulp) instead of the IEEE division subroutine
+// (a CALL with a slow path, nine times per pixel); fp64: exact.
+template <class T>
+__device__ __forceinline__ T rcp_pos(T x) {
+    if constexpr (sizeof(T) == 4) {
+        float q;
+        asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(q) : "f"(x));
+        return fmaf(q, fmaf(-x, q, 1.0f), q);
+    } else {
+        return T(1) / x;
+    }
+}
+
 struct GridView {
     long long H, W;
     int has_up, has_down;
@@ -131,8 +144,9 @@ __global__ void __launch_bounds__(256) k_potts_sweep(GridView g, T w) {
         for (int k = 0; k < E; ++k) mv[d][k] = S + w * in[d][k];
         T tot = group_sum<T, E, LP>(mv[d]);
         if (ex[d]) {
+            const T inv = rcp_pos<T>(tot);
 #pragma unroll
-            for (int k = 0; k < E; ++k) mv[d][k] = mv[d][k] / tot;
+            for (int k = 0; k < E; ++k) mv[d][k] = mv[d][k] * inv;
             if (valid) store_vec<T, E>((T*)g.m2v[d] + o, mv[d]);
         } else {
 #pragma unroll
@@ -151,9 +165,9 @@ __global__ void __launch_bounds__(256) k_potts_sweep(GridView g, T w) {
             if (ex[3]) a = a * mv[3][k];
             acc[k] = a;
         }
-        T tot = group_sum<T, E, LP>(acc);
+        const T inv_tot = rcp_pos<T>(group_sum<T, E, LP>(acc));
 #pragma unroll
-        for (int k = 0; k < E; ++k) acc[k] = acc[k] / tot;
+        for (int k = 0; k < E; ++k) acc[k] = acc[k] * inv_tot;
         if (valid) store_vec<T, E>((T*)g.marg + o, acc);
     }
 #pragma unroll
@@ -167,9 +181,9 @@ __global__ void __launch_bounds__(256) k_potts_sweep(GridView g, T w) {
                 if (d2 != d && ex[d2]) a = a * mv[d2][k];
             acc[k] = a;
         }
-        T tot = group_sum<T, E, LP>(acc);
+        const T inv_tot = rcp_pos<T>(group_sum<T, E, LP>(acc));
 #pragma unroll
-        for (int k = 0; k < E; ++k) acc[k] = acc[k] / tot;
+        for (int k = 0; k < E; ++k) acc[k] = acc[k] * inv_tot;
         if (valid && ex[d]) store_vec<T, E>((T*)g.m2f_nxt[d] + o, acc);
         // the cut edges: the same message goes straight into the neighbour GPU's halo buffer (peer store over NVLink),
         // overlapped with the rest of the sweep; cxb_grid_sweep publishes a sweep counter after the kernel

@@ -142,9 +142,13 @@ __device__ __forceinline__ T gsum(T v) {  // sum over the L lanes of a group (gr
 }
 template <class T>
 __device__ __forceinline__ T recip(T x);
+// MUFU.RCP + one Newton step (<= 1 ulp on the normal, positive sums it is used on). __frcp_rn is a ~30-instruction
+// subroutine behind a CALL: it was 30 % of the stall samples of the small-degree kernel.
 template <>
 __device__ __forceinline__ float recip<float>(float x) {
-    return __frcp_rn(x);
+    float q;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(q) : "f"(x));
+    return fmaf(q, fmaf(-x, q, 1.0f), q);
 }
 template <>
 __device__ __forceinline__ double recip<double>(double x) {
@@ -345,6 +349,173 @@ __global__ void __launch_bounds__(256, MINB) k_pw_exact(PwView g, PwBin bin) {
         if (have) st_vec<true, T, S>((T*)g.m2f_nxt + (size_t)op[k] * K + a0, o);  // into the receiver's inbox
     }
     }  // grid-stride loop
+}
+
+// ---- the same path with its streams staged through shared memory by the bulk-copy engine ----------------------------------
+// After the slot renumbering the 32 / L records a warp handles in one iteration own ONE contiguous block of slots, so
+// everything the warp reads — the inbox messages, the unary evidence (record order), the opp and tsel entries — is four
+// contiguous ranges. One elected lane asks the bulk-copy engine (cp.async.bulk, completion on a per-warp mbarrier) for the
+// ranges of the iteration after next while the warp computes on the current stage: loads no longer live in registers, two
+// iterations of reads are always in flight per warp, and the compute reads 128-bit vectors from shared memory.
+namespace pwasync {
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "PW_WAIT_LOOP:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra PW_DONE;\n\t"
+        "bra PW_WAIT_LOOP;\n\t"
+        "PW_DONE:\n\t"
+        "}" ::"r"(bar),
+        "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst), "l"(src),
+                 "r"(bytes), "r"(bar)
+                 : "memory");
+}
+}  // namespace pwasync
+
+template <class T, int K>
+struct PwStage {
+    static constexpr int S = PwGeo<K>::S, L = PwGeo<K>::L, D = PW_EXACT_MAX, GPW = 32 / L;  // GPW = records per warp
+    static constexpr uint32_t INBOX_B = GPW * D * K * sizeof(T), UNARY_B = GPW * K * sizeof(T);
+    // aligned copy windows: up to 3 + 3 extra opp entries, 15 + 15 extra tsel bytes
+    static constexpr uint32_t OPP_B = (GPW * D + 8) * 4, TSEL_B = ((GPW * D + 32 + 15) / 16) * 16;
+    static constexpr uint32_t OFF_UNARY = INBOX_B, OFF_OPP = OFF_UNARY + UNARY_B, OFF_TSEL = OFF_OPP + OPP_B;
+    static constexpr uint32_t BYTES = ((OFF_TSEL + TSEL_B + 127) / 128) * 128;
+};
+template <class T, int K>
+__global__ void __launch_bounds__(256, 2) k_pw_exact_staged(PwView g, PwBin bin) {
+    using ST = PwStage<T, K>;
+    constexpr int S = ST::S, L = ST::L, D = ST::D, GPW = ST::GPW, WARPS = 8;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    T* sh_tables = reinterpret_cast<T*>(smem_raw);
+    const size_t tab_bytes = ((size_t)g.tab_elems * sizeof(T) + 127) / 128 * 128;
+    unsigned char* stages = smem_raw + tab_bytes;                                    // [WARPS][2][ST::BYTES]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(stages + (size_t)WARPS * 2 * ST::BYTES);  // [WARPS][2]
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, grp = lane / L;
+    if (lane == 0) {
+        pwasync::mbar_init(pwasync::smem_u32(&bars[warp * 2 + 0]), 1);
+        pwasync::mbar_init(pwasync::smem_u32(&bars[warp * 2 + 1]), 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    stage_tables<T>(sh_tables, g, K);  // ends with __syncthreads: barriers initialised, tables staged
+    const T* my_tab = lane_tables<T>(sh_tables, g);
+    const int tab_sel = g.tab_sel;
+    const int a0 = (lane % L) * S;
+    const uint32_t per_cta = WARPS * GPW, stride = gridDim.x * per_cta;
+    const uint32_t first = blockIdx.x * per_cta + warp * GPW + grp;
+    unsigned char* my_stage = stages + (size_t)warp * 2 * ST::BYTES;
+
+    // ask the bulk-copy engine for the four ranges of one block of records (all lanes call; lane 0 issues)
+    auto issue = [&](const PwRec& r, uint32_t rec_first, int stage) {
+        const unsigned live_mask = __ballot_sync(PW_FULL_MASK, r.live);
+        if (!live_mask) return;
+        const uint32_t blk_start = __shfl_sync(PW_FULL_MASK, r.p0, 0);
+        const uint32_t blk_end = __reduce_max_sync(PW_FULL_MASK, r.live ? r.p0 + r.d : 0u);
+        const uint32_t n_live = (uint32_t)__popc(live_mask) / L;
+        if (lane == 0) {
+            const uint32_t bar = pwasync::smem_u32(&bars[warp * 2 + stage]);
+            const uint32_t dst = pwasync::smem_u32(my_stage + (size_t)stage * ST::BYTES);
+            const uint32_t nslots = blk_end - blk_start;
+            const uint32_t o0 = blk_start & ~3u, o1 = (blk_end + 3u) & ~3u, t0 = blk_start & ~15u, t1 = (blk_end + 15u) & ~15u;
+            const uint32_t b_in = nslots * K * (uint32_t)sizeof(T), b_un = n_live * K * (uint32_t)sizeof(T);
+            const uint32_t b_op = nslots ? (o1 - o0) * 4u : 0u, b_ts = nslots ? (t1 - t0) : 0u;
+            pwasync::mbar_expect_tx(bar, b_in + b_un + b_op + b_ts);
+            if (b_in) pwasync::bulk_g2s(dst, (const T*)g.m2f_cur + (size_t)blk_start * K, b_in, bar);
+            pwasync::bulk_g2s(dst + ST::OFF_UNARY, (const T*)g.unary + (size_t)(bin.base + rec_first) * K, b_un, bar);
+            if (b_op) pwasync::bulk_g2s(dst + ST::OFF_OPP, g.opp + o0, b_op, bar);
+            if (b_ts) pwasync::bulk_g2s(dst + ST::OFF_TSEL, g.tsel + t0, b_ts, bar);
+        }
+    };
+
+    PwRec cur = load_rec(bin, first), nxt = load_rec(bin, first + stride);
+    issue(cur, first - grp, 0);
+    issue(nxt, first - grp + stride, 1);
+    uint32_t it = 0;
+    for (uint32_t base = blockIdx.x * per_cta; base < bin.n; base += stride, ++it) {
+        const uint32_t gid = first + it * stride;
+        const PwRec nn = load_rec(bin, gid + 2 * stride);
+        const bool live = cur.live;
+        const uint32_t v = cur.v, p0 = cur.p0, d = cur.d;
+        const int stage = (int)(it & 1);
+        if (__any_sync(PW_FULL_MASK, live)) {
+            const uint32_t blk_start = __shfl_sync(PW_FULL_MASK, p0, 0);
+            pwasync::mbar_wait(pwasync::smem_u32(&bars[warp * 2 + stage]), (it >> 1) & 1);
+            const unsigned char* st = my_stage + (size_t)stage * ST::BYTES;
+            const T* sm_in = reinterpret_cast<const T*>(st);
+            const T* sm_un = reinterpret_cast<const T*>(st + ST::OFF_UNARY);
+            const uint32_t* sm_op = reinterpret_cast<const uint32_t*>(st + ST::OFF_OPP);
+            const uint8_t* sm_ts = st + ST::OFF_TSEL;
+            const uint32_t rel = p0 - blk_start, o_off = blk_start & 3u, t_off = blk_start & 15u;
+            T un[S];
+            vset<T, S>(un, T(1));
+            if (live) ld_vec_plain<T, S>(sm_un + (size_t)grp * K + a0, un);
+            uint32_t op[D];
+            int sel[D];
+#pragma unroll
+            for (int k = 0; k < D; ++k) {
+                op[k] = 0;
+                sel[k] = 0;
+                if ((uint32_t)k < d) {
+                    op[k] = sm_op[rel + k + o_off];
+                    sel[k] = sm_ts[rel + k + t_off];
+                }
+            }
+            T x[D][S];
+#pragma unroll
+            for (int k = 0; k < D; ++k) {
+                vset<T, S>(x[k], T(1));
+                const bool have = (uint32_t)k < d;
+                if (!__any_sync(PW_FULL_MASK, have)) continue;
+                T in[K];
+#pragma unroll
+                for (int i = 0; i < K; ++i) in[i] = T(1);
+                if (have) ld_vec_plain<T, K>(sm_in + (size_t)(rel + k) * K, in);
+                T m[S];
+                contract<T, K>(my_tab + sel[k] * tab_sel, in, m);
+                norm1<T, K>(m);
+                if (have) {
+                    st_vec<true, T, S>((T*)g.m2v + (size_t)(p0 + k) * K + a0, m);
+                    vcopy<T, S>(x[k], m);
+                }
+            }
+            {
+                T acc[S];
+                vcopy<T, S>(acc, un);
+#pragma unroll
+                for (int k = 0; k < D; ++k) vmul<T, S>(acc, x[k]);
+                norm1<T, K>(acc);
+                if (live) st_vec<true, T, S>((T*)g.marg + (size_t)v * K + a0, acc);
+            }
+#pragma unroll
+            for (int k = 0; k < D; ++k) {
+                const bool have = (uint32_t)k < d;
+                if (!__any_sync(PW_FULL_MASK, have)) continue;
+                T o[S];
+                vcopy<T, S>(o, un);
+#pragma unroll
+                for (int j = 0; j < D; ++j)
+                    if (j != k) vmul<T, S>(o, x[j]);
+                norm1<T, K>(o);
+                if (have) st_vec<true, T, S>((T*)g.m2f_nxt + (size_t)op[k] * K + a0, o);  // into the receiver's inbox
+            }
+        }
+        __syncwarp();  // every lane has finished reading this stage before the engine overwrites it
+        issue(nn, gid - grp + 2 * stride, stage);
+        cur = nxt;
+        nxt = nn;
+    }
 }
 
 // ---- teams: G lane groups cooperate on one variable (FULL) or on one 8G-slot chunk of a hub (H1 / H3) -------------------
@@ -785,6 +956,8 @@ struct Pairwise {
         CXB_CUDA(up_bin(chunk_bin, chunks));
         CXB_CUDA(up_bin(hub_bin, hub_recs));
         CXB_CUDA(up(rec_of_var_d, rec_of_var));
+        oppv.resize(P + 16, 0);  // the bulk copies fetch 16-byte aligned windows: a few entries past the end may be read
+        sel.resize(P + 32, 0);
         CXB_CUDA(up(opp, oppv));
         CXB_CUDA(up(tsel, sel));
         CXB_CUDA(up(slot_of_edge, slot));
@@ -864,8 +1037,13 @@ struct Pairwise {
         have_msgs = true;
         return CXB_OK;
     }
-    // persistent CTAs of 256 threads: at most 8 per SM (fewer are resident when registers limit it; the rest queue)
-    unsigned grid_for(size_t threads) const { return std::min<unsigned>(cdiv(threads, 256), (unsigned)n_sm * 8u); }
+    // persistent CTAs of 256 threads: exactly as many as are resident at once (a CTA stages the table image once, ~33 KB)
+    template <class Kern>
+    unsigned grid_for(Kern kern, size_t threads, size_t smem) const {
+        int per_sm = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 256, smem) != cudaSuccess || per_sm < 1) per_sm = 1;
+        return std::min<unsigned>(cdiv(threads, 256), (unsigned)n_sm * (unsigned)per_sm);
+    }
     template <class T, int KK, int G>
     void launch_team(const PwView& g, size_t tb) {
         constexpr int TL = G * PwGeo<KK>::L;
@@ -874,7 +1052,7 @@ struct Pairwise {
             if (!bin.n) return;
             if (tb > 48 * 1024)
                 cudaFuncSetAttribute(k_pw_team<T, KK, G, PW_MODE_FULL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tb);
-            CXB_LAUNCH((k_pw_team<T, KK, G, PW_MODE_FULL>), grid_for((size_t)bin.n * TL), 256, tb, ls, g, bin.view());
+            CXB_LAUNCH((k_pw_team<T, KK, G, PW_MODE_FULL>), grid_for(k_pw_team<T, KK, G, PW_MODE_FULL>, (size_t)bin.n * TL, tb), 256, tb, ls, g, bin.view());
         }
     }
     template <class T, int KK, int G>
@@ -884,9 +1062,9 @@ struct Pairwise {
             if (G != g_max || !chunk_bin.n) return;
             if (tb > 48 * 1024)
                 cudaFuncSetAttribute(k_pw_team<T, KK, G, PW_MODE_H1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tb);
-            CXB_LAUNCH((k_pw_team<T, KK, G, PW_MODE_H1>), grid_for((size_t)chunk_bin.n * TL), 256, tb, ls, g, chunk_bin.view());
+            CXB_LAUNCH((k_pw_team<T, KK, G, PW_MODE_H1>), grid_for(k_pw_team<T, KK, G, PW_MODE_H1>, (size_t)chunk_bin.n * TL, tb), 256, tb, ls, g, chunk_bin.view());
             CXB_LAUNCH((k_pw_hub_scan<T, KK>), cdiv((size_t)hub_bin.n * L, 128), 128, 0, ls, g, hub_bin.view());
-            CXB_LAUNCH((k_pw_team<T, KK, G, PW_MODE_H3>), grid_for((size_t)chunk_bin.n * TL), 256, 0, ls, g, chunk_bin.view());
+            CXB_LAUNCH((k_pw_team<T, KK, G, PW_MODE_H3>), grid_for(k_pw_team<T, KK, G, PW_MODE_H3>, (size_t)chunk_bin.n * TL, 0), 256, 0, ls, g, chunk_bin.view());
         }
     }
     template <class T, int KK>
@@ -910,15 +1088,21 @@ struct Pairwise {
         ls = multi ? aux[2] : stream;
         launch_team<T, KK, 1>(g, tb);
         ls = stream;
-        if (exact_bin.n) {
+        const bool staged = KK * sizeof(T) >= 16 && !(getenv("CXB_PW_STAGED") && !atoi(getenv("CXB_PW_STAGED")));
+        if (exact_bin.n && staged) {
+            using ST = PwStage<T, KK>;
+            const size_t smem = (tb + 127) / 128 * 128 + (size_t)8 * 2 * ST::BYTES + 8 * 2 * sizeof(uint64_t);
+            cudaFuncSetAttribute(k_pw_exact_staged<T, KK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            CXB_LAUNCH((k_pw_exact_staged<T, KK>), grid_for(k_pw_exact_staged<T, KK>, (size_t)exact_bin.n * PwGeo<KK>::L, smem), 256, smem, ls, g, exact_bin.view());
+        } else if (exact_bin.n) {
             int minb = 2;
             if (const char* e = getenv("CXB_PW_MINB")) minb = atoi(e);
             if (minb >= 3) {
                 if (tb > 48 * 1024) cudaFuncSetAttribute(k_pw_exact<T, KK, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tb);
-                CXB_LAUNCH((k_pw_exact<T, KK, 3>), grid_for((size_t)exact_bin.n * PwGeo<KK>::L), 256, tb, ls, g, exact_bin.view());
+                CXB_LAUNCH((k_pw_exact<T, KK, 3>), grid_for(k_pw_exact<T, KK, 3>, (size_t)exact_bin.n * PwGeo<KK>::L, tb), 256, tb, ls, g, exact_bin.view());
             } else {
                 if (tb > 48 * 1024) cudaFuncSetAttribute(k_pw_exact<T, KK, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tb);
-                CXB_LAUNCH((k_pw_exact<T, KK, 2>), grid_for((size_t)exact_bin.n * PwGeo<KK>::L), 256, tb, ls, g, exact_bin.view());
+                CXB_LAUNCH((k_pw_exact<T, KK, 2>), grid_for(k_pw_exact<T, KK, 2>, (size_t)exact_bin.n * PwGeo<KK>::L, tb), 256, tb, ls, g, exact_bin.view());
             }
         }
         if (multi)
