@@ -385,6 +385,7 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t
 }
 }  // namespace pwasync
 
+constexpr int PW_STAGES = 3;
 template <class T, int K>
 struct PwStage {
     static constexpr int S = PwGeo<K>::S, L = PwGeo<K>::L, D = PW_EXACT_MAX, GPW = 32 / L;  // GPW = records per warp
@@ -397,16 +398,15 @@ struct PwStage {
 template <class T, int K>
 __global__ void __launch_bounds__(256, 2) k_pw_exact_staged(PwView g, PwBin bin) {
     using ST = PwStage<T, K>;
-    constexpr int S = ST::S, L = ST::L, D = ST::D, GPW = ST::GPW, WARPS = 8;
+    constexpr int S = ST::S, L = ST::L, D = ST::D, GPW = ST::GPW, WARPS = 8, NS = PW_STAGES;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     T* sh_tables = reinterpret_cast<T*>(smem_raw);
     const size_t tab_bytes = ((size_t)g.tab_elems * sizeof(T) + 127) / 128 * 128;
-    unsigned char* stages = smem_raw + tab_bytes;                                    // [WARPS][2][ST::BYTES]
-    uint64_t* bars = reinterpret_cast<uint64_t*>(stages + (size_t)WARPS * 2 * ST::BYTES);  // [WARPS][2]
+    unsigned char* stages = smem_raw + tab_bytes;                                     // [WARPS][NS][ST::BYTES]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(stages + (size_t)WARPS * NS * ST::BYTES);  // [WARPS][NS]
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, grp = lane / L;
     if (lane == 0) {
-        pwasync::mbar_init(pwasync::smem_u32(&bars[warp * 2 + 0]), 1);
-        pwasync::mbar_init(pwasync::smem_u32(&bars[warp * 2 + 1]), 1);
+        for (int i = 0; i < NS; ++i) pwasync::mbar_init(pwasync::smem_u32(&bars[warp * NS + i]), 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     stage_tables<T>(sh_tables, g, K);  // ends with __syncthreads: barriers initialised, tables staged
@@ -415,7 +415,7 @@ __global__ void __launch_bounds__(256, 2) k_pw_exact_staged(PwView g, PwBin bin)
     const int a0 = (lane % L) * S;
     const uint32_t per_cta = WARPS * GPW, stride = gridDim.x * per_cta;
     const uint32_t first = blockIdx.x * per_cta + warp * GPW + grp;
-    unsigned char* my_stage = stages + (size_t)warp * 2 * ST::BYTES;
+    unsigned char* my_stage = stages + (size_t)warp * NS * ST::BYTES;
 
     // ask the bulk-copy engine for the four ranges of one block of records (all lanes call; lane 0 issues)
     auto issue = [&](const PwRec& r, uint32_t rec_first, int stage) {
@@ -425,7 +425,7 @@ __global__ void __launch_bounds__(256, 2) k_pw_exact_staged(PwView g, PwBin bin)
         const uint32_t blk_end = __reduce_max_sync(PW_FULL_MASK, r.live ? r.p0 + r.d : 0u);
         const uint32_t n_live = (uint32_t)__popc(live_mask) / L;
         if (lane == 0) {
-            const uint32_t bar = pwasync::smem_u32(&bars[warp * 2 + stage]);
+            const uint32_t bar = pwasync::smem_u32(&bars[warp * NS + stage]);
             const uint32_t dst = pwasync::smem_u32(my_stage + (size_t)stage * ST::BYTES);
             const uint32_t nslots = blk_end - blk_start;
             const uint32_t o0 = blk_start & ~3u, o1 = (blk_end + 3u) & ~3u, t0 = blk_start & ~15u, t1 = (blk_end + 15u) & ~15u;
@@ -439,19 +439,22 @@ __global__ void __launch_bounds__(256, 2) k_pw_exact_staged(PwView g, PwBin bin)
         }
     };
 
-    PwRec cur = load_rec(bin, first), nxt = load_rec(bin, first + stride);
+    // records are fetched four iterations ahead (registers), the ranges of three iterations are in flight in the stages
+    PwRec cur = load_rec(bin, first), r1 = load_rec(bin, first + stride), r2 = load_rec(bin, first + 2 * stride),
+          r3 = load_rec(bin, first + 3 * stride);
     issue(cur, first - grp, 0);
-    issue(nxt, first - grp + stride, 1);
+    issue(r1, first - grp + stride, 1 % NS);
+    issue(r2, first - grp + 2 * stride, 2 % NS);
     uint32_t it = 0;
     for (uint32_t base = blockIdx.x * per_cta; base < bin.n; base += stride, ++it) {
         const uint32_t gid = first + it * stride;
-        const PwRec nn = load_rec(bin, gid + 2 * stride);
+        const PwRec r4 = load_rec(bin, gid + 4 * stride);
         const bool live = cur.live;
         const uint32_t v = cur.v, p0 = cur.p0, d = cur.d;
-        const int stage = (int)(it & 1);
+        const int stage = (int)(it % NS);
         if (__any_sync(PW_FULL_MASK, live)) {
             const uint32_t blk_start = __shfl_sync(PW_FULL_MASK, p0, 0);
-            pwasync::mbar_wait(pwasync::smem_u32(&bars[warp * 2 + stage]), (it >> 1) & 1);
+            pwasync::mbar_wait(pwasync::smem_u32(&bars[warp * NS + stage]), (it / NS) & 1);
             const unsigned char* st = my_stage + (size_t)stage * ST::BYTES;
             const T* sm_in = reinterpret_cast<const T*>(st);
             const T* sm_un = reinterpret_cast<const T*>(st + ST::OFF_UNARY);
@@ -512,9 +515,11 @@ __global__ void __launch_bounds__(256, 2) k_pw_exact_staged(PwView g, PwBin bin)
             }
         }
         __syncwarp();  // every lane has finished reading this stage before the engine overwrites it
-        issue(nn, gid - grp + 2 * stride, stage);
-        cur = nxt;
-        nxt = nn;
+        issue(r3, gid - grp + 3 * stride, stage);
+        cur = r1;
+        r1 = r2;
+        r2 = r3;
+        r3 = r4;
     }
 }
 
@@ -1091,7 +1096,7 @@ struct Pairwise {
         const bool staged = KK * sizeof(T) >= 16 && !(getenv("CXB_PW_STAGED") && !atoi(getenv("CXB_PW_STAGED")));
         if (exact_bin.n && staged) {
             using ST = PwStage<T, KK>;
-            const size_t smem = (tb + 127) / 128 * 128 + (size_t)8 * 2 * ST::BYTES + 8 * 2 * sizeof(uint64_t);
+            const size_t smem = (tb + 127) / 128 * 128 + (size_t)8 * PW_STAGES * ST::BYTES + 8 * PW_STAGES * sizeof(uint64_t);
             cudaFuncSetAttribute(k_pw_exact_staged<T, KK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
             CXB_LAUNCH((k_pw_exact_staged<T, KK>), grid_for(k_pw_exact_staged<T, KK>, (size_t)exact_bin.n * PwGeo<KK>::L, smem), 256, smem, ls, g, exact_bin.view());
         } else if (exact_bin.n) {
