@@ -1077,8 +1077,8 @@ struct Pairwise {
         size_t tb = (size_t)tab_elems * sizeof(T);
         const bool multi = !(getenv("CXB_PW_ONE_STREAM") && atoi(getenv("CXB_PW_ONE_STREAM")));
         if (multi) {
-            cudaEventRecord(ev_fork, stream);
-            for (int i = 0; i < N_AUX; ++i) cudaStreamWaitEvent(aux[i], ev_fork, 0);
+            CXB_CUDA(cudaEventRecord(ev_fork, stream));
+            for (int i = 0; i < N_AUX; ++i) CXB_CUDA(cudaStreamWaitEvent(aux[i], ev_fork, 0));
         }
         // side stream 0: hubs (three dependent launches) and the large teams; 1: teams of 4 and 2; 2: teams of 1; main: exact
         ls = multi ? aux[0] : stream;
@@ -1112,8 +1112,8 @@ struct Pairwise {
         }
         if (multi)
             for (int i = 0; i < N_AUX; ++i) {
-                cudaEventRecord(ev_join[i], aux[i]);
-                cudaStreamWaitEvent(stream, ev_join[i], 0);
+                CXB_CUDA(cudaEventRecord(ev_join[i], aux[i]));
+                CXB_CUDA(cudaStreamWaitEvent(stream, ev_join[i], 0));
             }
         return CXB_OK;
     }
