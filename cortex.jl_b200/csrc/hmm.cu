@@ -385,6 +385,202 @@ k_hmm64_pass(const float* __restrict__ tbl, const float* __restrict__ emis_n, co
     }
 }
 
+// ---- K = 64, fp32, tensor cores: one CTA of 4 warps per 8 chains (1,024 chains = 128 CTAs, one per SM) -----------------------
+// The sequential recursion leaves one 64 x 64 x 8 product per SM and step: warp w computes output states 16 w .. 16 w + 15 of
+// 8 chains with mma.sync.m16n8k16 (bf16 split operands, hi*hi + hi*lo + lo*hi, fp32 accumulate: 12 MMAs per warp and step
+// instead of 64 FFMA2 per lane), the table fragments stay in registers, the 8 carried messages are exchanged between the
+// 4 warps through a double-buffered bf16 hi/lo image in shared memory (one block barrier per step). Scaling and deferred
+// exact normalisation as in k_hmm64_pass: per-chain max / sum partials travel with the message, the previous step's result
+// is written out, exactly normalised, one step late.
+__device__ __forceinline__ void mma_bf16_m16n8k16(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+                 : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ void split_bf16(float x, uint16_t& hi, uint16_t& lo) {
+    const __nv_bfloat16 h = __float2bfloat16_rn(x);
+    hi = __bfloat16_as_ushort(h);
+    lo = __bfloat16_as_ushort(__float2bfloat16_rn(x - __bfloat162float(h)));
+}
+template <bool FWD>
+__global__ void __launch_bounds__(128, 1)
+k_hmm64_mma(const float* __restrict__ tbl, const float* __restrict__ emis_n, const uint8_t* __restrict__ obs,
+            float* __restrict__ fwd, float* __restrict__ marg, long long B, long long Tn, int n_sym) {
+    constexpr int K = 64, NB = 8, VS = 72;  // VS: bf16 elements per chain row (64 + 8: rows start 4 banks apart)
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    uint16_t* sV = reinterpret_cast<uint16_t*>(smem_raw);                  // [2 buffers][2 (hi, lo)][NB][VS]
+    float* sPart = reinterpret_cast<float*>(sV + 2 * 2 * NB * VS);         // [2 buffers][2 (max, sum)][NB][4 warps]
+    uint8_t* sObs = reinterpret_cast<uint8_t*>(sPart + 2 * 2 * NB * 4);    // [2 buffers][32 steps][NB]
+    float* sEm = reinterpret_cast<float*>(sObs + 2 * 32 * NB);             // [n_sym][64]
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+    const int j0 = 16 * warp;
+    const long long b0 = (long long)blockIdx.x * NB;
+    auto time_of = [&](long long step) { return FWD ? step : Tn - 1 - step; };
+
+    // table fragments: M[j][i] = tbl[i][j] (out[j] = sum_i tbl[i][j] v[i]), rows j0 + g / j0 + g + 8, 4 K-steps of 16
+    uint32_t ahi[4][4], alo[4][4];
+#pragma unroll
+    for (int ks = 0; ks < 4; ++ks)
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            const int j = j0 + g + 8 * (r & 1), i = 16 * ks + 2 * t + 8 * (r >> 1);
+            uint16_t h0, l0, h1, l1;
+            split_bf16(tbl[(size_t)i * K + j], h0, l0);
+            split_bf16(tbl[(size_t)(i + 1) * K + j], h1, l1);
+            ahi[ks][r] = (uint32_t)h0 | ((uint32_t)h1 << 16);
+            alo[ks][r] = (uint32_t)l0 | ((uint32_t)l1 << 16);
+        }
+    for (int x = threadIdx.x; x < n_sym * K; x += blockDim.x) sEm[x] = emis_n[x];
+    auto load_obs_block = [&](long long step0, int buf) {  // 32 steps x 8 chains, two entries per thread
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+            const int idx = threadIdx.x * 2 + e, st = idx / NB, n = idx % NB;
+            const long long step = step0 + st;
+            uint8_t o = 0;
+            if (step < Tn && b0 + n < B) o = obs[(size_t)time_of(step) * B + b0 + n];
+            sObs[(buf * 32 + st) * NB + n] = o;
+        }
+    };
+    load_obs_block(0, 0);
+    // this thread's four cells: (state j0 + g + 8 h, chain 2 t + c), h, c in {0, 1}; cell index = 2 h + c (the D fragment order)
+    auto cell_ptr = [&](float* plane, long long step, int h, int c) -> float* {
+        return plane + ((size_t)time_of(step) * B + (size_t)(b0 + 2 * t + c)) * K + j0 + g + 8 * h;
+    };
+    const bool live_c[2] = {b0 + 2 * t < B, b0 + 2 * t + 1 < B};
+    float a_cur[4] = {0, 0, 0, 0}, a_n1[4] = {0, 0, 0, 0}, a_n2[4] = {0, 0, 0, 0};  // BWD: forward message cells of steps s, s+1, s+2
+    auto load_fwd_cells = [&](long long step, float (&dst)[4]) {
+#pragma unroll
+        for (int h = 0; h < 2; ++h)
+#pragma unroll
+            for (int c = 0; c < 2; ++c)
+                dst[2 * h + c] = (step < Tn && live_c[c]) ? __ldcs(cell_ptr(fwd, step, h, c)) : 0.0f;
+    };
+    if (!FWD) {
+        load_fwd_cells(0, a_cur);
+        load_fwd_cells(1, a_n1);
+    }
+    float uprev[4] = {0, 0, 0, 0}, gprev[4] = {0, 0, 0, 0};
+    __syncthreads();
+
+    for (long long s = 0; s <= Tn; ++s) {
+        if ((s & 31) == 0) load_obs_block(s + 32, (int)(((s >> 5) + 1) & 1));  // read 32 steps from now
+        if (!FWD) {
+            load_fwd_cells(s + 2, a_n2);
+            if (s + 16 < Tn && threadIdx.x < 2 * NB)  // pull the forward messages of step s + 16 into L2 (8 chains x 256 B)
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(fwd + ((size_t)time_of(s + 16) * B + (size_t)(b0 + (threadIdx.x >> 1))) * K +
+                                                                32 * (threadIdx.x & 1)));
+        }
+        float r[2] = {1.0f, 1.0f};
+        if (s >= 1) {  // totals of step s - 1 (partials of the 4 warps), its exactly normalised write-out, this step's scale
+            const int pb = (int)((s - 1) & 1);
+#pragma unroll
+            for (int c = 0; c < 2; ++c) {
+                const int n = 2 * t + c;
+                const float4 pm = *reinterpret_cast<const float4*>(sPart + ((pb * 2 + 0) * NB + n) * 4);
+                const float4 ps = *reinterpret_cast<const float4*>(sPart + ((pb * 2 + 1) * NB + n) * 4);
+                r[c] = hmm_pow2_inv(fmaxf(fmaxf(pm.x, pm.y), fmaxf(pm.z, pm.w)));
+                const float q = hmm_rcp((ps.x + ps.y) + (ps.z + ps.w));
+                if (live_c[c]) {
+#pragma unroll
+                    for (int h = 0; h < 2; ++h)
+                        __stcs(cell_ptr(FWD ? fwd : marg, s - 1, h, c), (FWD ? uprev[2 * h + c] : gprev[2 * h + c]) * q);
+                }
+            }
+        }
+        if (s < Tn) {
+            float pred[4] = {1.0f, 1.0f, 1.0f, 1.0f};
+            if (s > 0) {
+                const uint16_t* vhi = sV + ((size_t)((s & 1) * 2 + 0) * NB + g) * VS;
+                const uint16_t* vlo = sV + ((size_t)((s & 1) * 2 + 1) * NB + g) * VS;
+                // twelve INDEPENDENT accumulators: the MMAs of a step do not wait for one another (mma.sync latency, not
+                // throughput, is what a step pays for), the partial products are added afterwards
+                float d[4][3][4];
+                uint32_t bh0[4], bh1[4], bl0[4], bl1[4];
+#pragma unroll
+                for (int ks = 0; ks < 4; ++ks) {
+                    bh0[ks] = *reinterpret_cast<const uint32_t*>(vhi + 16 * ks + 2 * t);
+                    bh1[ks] = *reinterpret_cast<const uint32_t*>(vhi + 16 * ks + 2 * t + 8);
+                    bl0[ks] = *reinterpret_cast<const uint32_t*>(vlo + 16 * ks + 2 * t);
+                    bl1[ks] = *reinterpret_cast<const uint32_t*>(vlo + 16 * ks + 2 * t + 8);
+                }
+#pragma unroll
+                for (int ks = 0; ks < 4; ++ks) {
+#pragma unroll
+                    for (int p = 0; p < 3; ++p)
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) d[ks][p][i] = 0.0f;
+                    mma_bf16_m16n8k16(d[ks][0], ahi[ks], bh0[ks], bh1[ks]);
+                    mma_bf16_m16n8k16(d[ks][1], ahi[ks], bl0[ks], bl1[ks]);
+                    mma_bf16_m16n8k16(d[ks][2], alo[ks], bh0[ks], bh1[ks]);
+                }
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const float hh = (d[0][0][i] + d[1][0][i]) + (d[2][0][i] + d[3][0][i]);
+                    const float cr = ((d[0][1][i] + d[0][2][i]) + (d[1][1][i] + d[1][2][i])) + ((d[2][1][i] + d[2][2][i]) + (d[3][1][i] + d[3][2][i]));
+                    pred[i] = hh + cr;
+                }
+            }
+            const uint8_t* ob = sObs + ((size_t)((s >> 5) & 1) * 32 + (s & 31)) * NB;
+            float unew[4], gnew[4];
+            float mx[2] = {0.0f, 0.0f}, sm[2] = {0.0f, 0.0f};
+#pragma unroll
+            for (int c = 0; c < 2; ++c) {
+                int o = ob[2 * t + c];
+                if (o >= n_sym) o = n_sym - 1;
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const float em = sEm[o * K + j0 + g + 8 * h];
+                    const int cell = 2 * h + c;
+                    unew[cell] = (s > 0) ? em * pred[cell] * r[c] : em;
+                    gnew[cell] = FWD ? unew[cell] : a_cur[cell] * pred[cell];
+                    mx[c] = fmaxf(mx[c], unew[cell]);
+                    sm[c] += gnew[cell];
+                }
+            }
+            // per-chain max / sum over this warp's 16 states: lanes with the same t (xor 4, 8, 16)
+#pragma unroll
+            for (int d = 4; d < 32; d <<= 1)
+#pragma unroll
+                for (int c = 0; c < 2; ++c) {
+                    mx[c] = fmaxf(mx[c], __shfl_xor_sync(0xffffffffu, mx[c], d));
+                    sm[c] += __shfl_xor_sync(0xffffffffu, sm[c], d);
+                }
+            const int wb = (int)(s & 1);
+            if (g == 0) {
+#pragma unroll
+                for (int c = 0; c < 2; ++c) {
+                    sPart[((wb * 2 + 0) * NB + 2 * t + c) * 4 + warp] = mx[c];
+                    sPart[((wb * 2 + 1) * NB + 2 * t + c) * 4 + warp] = sm[c];
+                }
+            }
+            // the carried message of the next step, as bf16 hi / lo rows per chain
+            const int nb = (int)((s + 1) & 1);
+#pragma unroll
+            for (int c = 0; c < 2; ++c)
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    uint16_t hi, lo;
+                    split_bf16(unew[2 * h + c], hi, lo);
+                    sV[((size_t)(nb * 2 + 0) * NB + 2 * t + c) * VS + j0 + g + 8 * h] = hi;
+                    sV[((size_t)(nb * 2 + 1) * NB + 2 * t + c) * VS + j0 + g + 8 * h] = lo;
+                }
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                uprev[i] = unew[i];
+                gprev[i] = gnew[i];
+            }
+        }
+        if (!FWD) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                a_cur[i] = a_n1[i];
+                a_n1[i] = a_n2[i];
+            }
+        }
+        __syncthreads();
+    }
+}
+
 struct Hmm {
     int device = 0, dtype = CXB_F32, K = 0, M = 0;
     long long B = 0, T = 0;
@@ -576,7 +772,23 @@ struct Hmm {
         }
         return CXB_OK;
     }
+    int32_t launch_k64_mma() {
+        const size_t smem = (size_t)2 * 2 * 8 * 72 * 2 + (size_t)2 * 2 * 8 * 4 * 4 + 2 * 32 * 8 + (size_t)M * 64 * sizeof(float);
+        const unsigned grid = (unsigned)((B + 7) / 8);
+        const float *a = (const float*)A.p, *at = (const float*)At.p, *en = (const float*)En.p;
+        if (smem > 48 * 1024) {
+            CXB_CUDA(cudaFuncSetAttribute(k_hmm64_mma<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            CXB_CUDA(cudaFuncSetAttribute(k_hmm64_mma<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        }
+        CXB_LAUNCH((k_hmm64_mma<true>), grid, 128, smem, stream, a, en, obs.p, (float*)fwd.p, (float*)marg.p, B, this->T, M);
+        CXB_LAUNCH((k_hmm64_mma<false>), grid, 128, smem, stream, at, en, obs.p, (float*)fwd.p, (float*)marg.p, B, this->T, M);
+        return CXB_OK;
+    }
     int32_t launch_k64() {
+        // The tensor-core variant (mma.sync, 8 chains per CTA, k_hmm64_mma) is kept as a measured alternative
+        // (CXB_HMM64_MMA=1): with one 64 x 64 x 8 product per SM and step it has a single warp per scheduler and pays every
+        // latency in full — 970 cycles per step against 630 for the FFMA2 kernel below (T = 4,000: 3.94 ms vs 2.55 ms).
+        if (M <= 128 && getenv("CXB_HMM64_MMA") && atoi(getenv("CXB_HMM64_MMA"))) return launch_k64_mma();
         // one warp per chain; warps per CTA chosen so that one CTA per SM holds the whole batch when it can (its warps
         // then spread evenly over the 4 schedulers): 1,024 chains -> 147 CTAs of 7 warps
         int n_sm = 148;
