@@ -575,3 +575,45 @@ def test_pairwise_kernel_big_hub_and_isolated_variables(oracle_api):
     edges += [(i, i + 1) for i in range(1122, 1147)]         # chain
     edges = sorted(edges)
     _pairwise_vs_oracle(oracle_api, cap.F32, n, edges, 8, sweeps=2)
+
+
+# ---- degenerate shapes: nothing may crash, results stay normalised / equal to the closed form ----------------------------
+def test_degenerate_shapes_of_the_structured_engines():
+    # pairwise graph without factors: marginal = normalised unary, no message updates beyond the marginals
+    n, K = 5, 8
+    unary = np.random.Generator(np.random.PCG64(1)).dirichlet(np.ones(K), size=n)
+    pw = C.PairwiseGraph(n, [], [], np.zeros(0, dtype=np.int32), np.ones((1, K, K)), dtype=cap.F64)
+    pw.set_unary(unary)
+    pw.reset_messages()
+    assert pw.sweep() == n
+    np.testing.assert_allclose(pw.get_marginals(), unary, rtol=1e-12)
+    # 1 x 1 and 1 x 7 grids: a lone pixel's marginal is its unary evidence
+    for H, W in ((1, 1), (1, 7), (6, 1)):
+        un = np.random.Generator(np.random.PCG64(2)).dirichlet(np.ones(16), size=(H, W)).astype(np.float32)
+        gr = C.PottsGrid(H, W, 16, 0.7)
+        gr.set_unary(un)
+        gr.reset_messages()
+        gr.sweep()
+        gr.sweep()
+        m = gr.get_marginals()
+        np.testing.assert_allclose(m.sum(axis=-1), 1.0, atol=1e-6)
+        if H * W == 1:
+            np.testing.assert_allclose(m, un, rtol=1e-6)
+    # one chain, one step
+    ch = C.GaussianChainBatch(1, 1, dtype=cap.F64)
+    ch.set_noise([1.0], [2.0])
+    ch.set_observations(np.array([[3.0]]))
+    assert ch.update_marginals() == 2
+    np.testing.assert_allclose(ch.get_marginals()[0, 0], [0.5, 1.5], rtol=1e-14)  # (1 / r, y / r)
+    # tensor-core HMM with a single chain (127 padding rows in the tile)
+    K, T, M = 128, 4, 3
+    rng = np.random.Generator(np.random.PCG64(3))
+    A = rng.dirichlet(np.ones(K), size=K)
+    E = rng.dirichlet(np.ones(K), size=M).T * K
+    obs = rng.integers(0, M, size=(T, 1)).astype(np.uint8)
+    hm = C.HmmBatch(1, T, K, M, dtype=cap.F32)
+    hm.set_tables(A, E)
+    hm.set_observations(obs)
+    hm.update_marginals()
+    want_f, want_m = _hmm_numpy(A.astype(np.float32).astype(np.float64), E, obs[:, 0])
+    assert_close(hm.get_marginals()[:, 0, :], want_m, cap.F32)
