@@ -281,3 +281,16 @@ def test_unimplemented_python_rule_raises(oracle_api):
     models.ssm_set_data(e, y, lik, [1.0, 2.0, 3.0])
     with pytest.raises(C.NoRuleError):
         C.update_marginals(e, x, schedule="seq")
+
+
+def test_signal_to_dot_shows_state_and_dependency_flags(backend):  # ext/GraphVizExt/GraphVizExt.jl:292-339
+    e, x, y, lik, tr = models.make_ssm_model(3, backend)
+    models.ssm_set_data(e, y, lik, [1.0, 2.0, 3.0])
+    mg = marginal(e, x[1])
+    dot_before = C.signal_to_dot(mg, max_depth=2)
+    assert dot_before.startswith("digraph G {") and dot_before.rstrip().endswith("}")
+    assert "MainSignal" in dot_before and "IndividualMarginal" in dot_before and "UndefValue()" in dot_before
+    assert 'color="gray"' in dot_before  # the marginal's dependencies are intermediate
+    C.update_marginals(e, x)
+    dot_after = C.signal_to_dot(mg, max_depth=1, show_listeners=False)
+    assert 'fillcolor="palegreen"' in dot_after and "UndefValue()" not in dot_after.split("main [")[1].split("];")[0]
