@@ -354,6 +354,9 @@ struct ResidentArgs {
     const int* key_rule;       // [n_keys] rule kind of a key: -1 = family reduce, -2 = no rule registered
     const double* key_param;   // [n_keys] default parameter of the key's rule
     const void* fparam;        // per factor id, NaN = unset
+    const void* tables;        // categorical family: every CAT_TABLE / HMM_EMIT table (engine dtype)
+    const long long* key_table;  // [n_keys] element offset of the key's table in `tables` (CAT_TABLE: [2][K][K], HMM_EMIT: [K][n_sym])
+    const int* key_nsym;       // [n_keys] HMM_EMIT: number of symbols
     long long* out;            // [0] levels [1] updates [2] final marginals [3] final linked [4] last lvl_epoch [5] key without rule
 };
 __device__ __forceinline__ void apply_one(const View& e, uint32_t s, uint32_t req_epoch, int check_mode) {
@@ -363,12 +366,79 @@ __device__ __forceinline__ void apply_one(const View& e, uint32_t s, uint32_t re
     atomicAdd(&e.kind_count[e.kind[s]], 1ull);
     for (uint32_t k = e.lis_off[s]; k < e.lis_off[s + 1]; ++k) notify(e, k, req_epoch, check_mode);
 }
+// categorical rule of ONE signal by ONE warp (lane l owns components l, l + 32; K <= 64): the body of k_rule_cat with the
+// tables read from global memory (small graphs: they sit in L1 / L2) and the incoming message staged per warp
+template <class T>
+__device__ __forceinline__ void rule_cat_warp(const View& e, T* __restrict__ val, uint32_t s, int rule, const T* __restrict__ table, int n_sym,
+                                              T potts_w, T* __restrict__ sh_in) {
+    const int K = e.dim, lane = threadIdx.x & 31;
+    const uint32_t off = e.dep_off[s], nd = e.dep_off[s + 1] - off;
+    if (nd == 0) {
+        if (lane == 0) atomicOr(e.err_flag, ERR_RULE_ARG);
+        return;
+    }
+    T acc[2] = {T(0), T(0)};
+    {
+        const T* a0 = val + (size_t)e.dep_ids[off] * K;
+#pragma unroll
+        for (int c = 0; c < 2; ++c)
+            if (lane + 32 * c < K) acc[c] = a0[lane + 32 * c];
+    }
+    if (rule < 0) {
+        for (uint32_t j = 1; j < nd; ++j) {
+            const T* b = val + (size_t)e.dep_ids[off + j] * K;
+#pragma unroll
+            for (int c = 0; c < 2; ++c)
+                if (lane + 32 * c < K) acc[c] = acc[c] * b[lane + 32 * c];
+        }
+    } else if (rule == CXB_RULE_POTTS) {
+        T part = acc[0] + acc[1];
+        for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+#pragma unroll
+        for (int c = 0; c < 2; ++c) acc[c] = (lane + 32 * c < K) ? part + potts_w * acc[c] : T(0);
+    } else if (rule == CXB_RULE_CAT_TABLE) {
+#pragma unroll
+        for (int c = 0; c < 2; ++c)
+            if (lane + 32 * c < K) sh_in[lane + 32 * c] = acc[c];
+        __syncwarp();
+        const bool u_is_low = e.svar[e.dep_ids[off]] < e.svar[s];
+        const T* tb = table + (u_is_low ? 0 : (size_t)K * K);  // [x_lo][x_hi] / its transpose
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+            const int aidx = lane + 32 * c;
+            T sum = T(0);
+            if (aidx < K)
+                for (int b = 0; b < K; ++b) sum += tb[b * K + aidx] * sh_in[b];
+            acc[c] = sum;
+        }
+        __syncwarp();
+    } else if (rule == CXB_RULE_HMM_EMIT) {
+        int o = (int)val[(size_t)e.dep_ids[off] * K];
+        if (o < 0 || o >= n_sym) {
+            if (lane == 0) atomicOr(e.err_flag, ERR_RULE_ARG);
+            o = 0;
+        }
+#pragma unroll
+        for (int c = 0; c < 2; ++c) acc[c] = (lane + 32 * c < K) ? table[(size_t)(lane + 32 * c) * n_sym + o] : T(0);
+    } else {
+        if (lane == 0) atomicOr(e.err_flag, ERR_RULE_ARG);
+        return;
+    }
+    T part = acc[0] + acc[1];
+    for (int o = 16; o > 0; o >>= 1) part += __shfl_xor_sync(0xffffffffu, part, o);
+    T* o = val + (size_t)s * K;
+#pragma unroll
+    for (int c = 0; c < 2; ++c)
+        if (lane + 32 * c < K) o[lane + 32 * c] = acc[c] / part;
+}
+
 template <class T>
 __global__ void __launch_bounds__(1024) k_update_resident(View e, T* __restrict__ val, ResidentArgs a) {
     __shared__ uint32_t s_cnt[2];
     __shared__ uint32_t s_total;
     __shared__ uint32_t s_key_cnt[256], s_key_base[256];  // per-key frontier cursors / partition starts (<= 252 keys)
     __shared__ int s_key_rule[256];
+    __shared__ T s_cat_in[32][64];  // categorical family: one incoming message per warp (K <= 64)
     const uint32_t tid = threadIdx.x, NT = blockDim.x;
     for (int k = tid; k < a.n_keys; k += NT) {
         s_key_base[k] = e.key_base[k];
@@ -403,7 +473,13 @@ __global__ void __launch_bounds__(1024) k_update_resident(View e, T* __restrict_
                 continue;
             }
             const T defp = (T)a.key_param[k];
-            for (uint32_t i = tid; i < cnt; i += NT) rule_small_one<T>(e, val, e.front[base + i], a.family, rule, (const T*)a.fparam, defp);
+            if (a.family == CXB_FAMILY_CATEGORICAL) {  // one warp per signal; key_param = Potts weight e^beta - 1
+                const T* tb = a.key_table[k] >= 0 ? (const T*)a.tables + a.key_table[k] : nullptr;
+                for (uint32_t i = tid >> 5; i < cnt; i += NT >> 5)
+                    rule_cat_warp<T>(e, val, e.front[base + i], rule, tb, a.key_nsym[k], defp, s_cat_in[tid >> 5]);
+            } else {
+                for (uint32_t i = tid; i < cnt; i += NT) rule_small_one<T>(e, val, e.front[base + i], a.family, rule, (const T*)a.fparam, defp);
+            }
         }
         __syncthreads();
         for (int k = 0; k < a.n_keys; ++k) {
@@ -647,8 +723,11 @@ struct DeviceEngine {
     DBuf<double> d_key_param;
     DBuf<long long> d_res_out;
     HBuf<long long> h_res_out;
-    std::vector<int> h_key_rule;
+    std::vector<int> h_key_rule, h_key_nsym;
     std::vector<double> h_key_param;
+    std::vector<long long> h_key_table;
+    DBuf<long long> d_key_table;
+    DBuf<int> d_key_nsym;
     HBuf<uint32_t> h_counts;
     HBuf<unsigned char> h_stage;
     HBuf<int> h_flags;
@@ -1179,27 +1258,37 @@ struct DeviceEngine {
     bool resident_ok() {
         if (const char* e = getenv("CXB_ENGINE_RESIDENT"))
             if (!atoi(e)) return false;
-        return !trace_on && family != CXB_FAMILY_CATEGORICAL && dim <= 4 && g.n_sig() <= 65536;
+        const bool small_family = family != CXB_FAMILY_CATEGORICAL && dim <= 4;
+        const bool small_categorical = family == CXB_FAMILY_CATEGORICAL && dim <= 64;
+        return !trace_on && (small_family || small_categorical) && g.n_sig() <= 65536;
     }
     int32_t update_resident(unsigned long long launches0) {
         const int nk = n_keys();
         h_key_rule.assign((size_t)nk, -2);
         h_key_param.assign((size_t)nk, 1.0);
         h_key_rule[KEY_COMBINE] = -1;
+        h_key_table.assign((size_t)nk, -1);
+        h_key_nsym.assign((size_t)nk, 0);
         for (int k = 1; k < nk - 1; ++k) {
             auto it = rules.find(key_ftype[k - 1]);
             if (it == rules.end() || it->second.kind == CXB_RULE_NONE) continue;
             const int kind = it->second.kind;
-            if (kind == CXB_RULE_CAT_TABLE || kind == CXB_RULE_POTTS || kind == CXB_RULE_HMM_EMIT) {
+            const bool cat_rule = kind == CXB_RULE_CAT_TABLE || kind == CXB_RULE_POTTS || kind == CXB_RULE_HMM_EMIT;
+            if (cat_rule != (family == CXB_FAMILY_CATEGORICAL)) {
                 err = "rule kind does not match the engine's value family";
                 return CXB_ERR_BAD_ARG;
             }
             h_key_rule[k] = kind;
             if (!it->second.params.empty()) h_key_param[k] = it->second.params[0];
+            if (kind == CXB_RULE_POTTS) h_key_param[k] = std::exp(it->second.params.empty() ? 0.0 : it->second.params[0]) - 1.0;
+            if (kind == CXB_RULE_CAT_TABLE || kind == CXB_RULE_HMM_EMIT) h_key_table[k] = (long long)table_off[key_ftype[k - 1]].first;
+            if (kind == CXB_RULE_HMM_EMIT) h_key_nsym[k] = (int)it->second.params[0];
         }
         int32_t st;
         if ((st = up(d_key_rule, h_key_rule.data(), (size_t)nk))) return st;
         if ((st = up(d_key_param, h_key_param.data(), (size_t)nk))) return st;
+        if ((st = up(d_key_table, h_key_table.data(), (size_t)nk))) return st;
+        if ((st = up(d_key_nsym, h_key_nsym.data(), (size_t)nk))) return st;
         CXB_CUDA(d_res_out.reserve(8));
         CXB_CUDA(h_res_out.reserve(8));
         CXB_CUDA(cudaMemsetAsync(d_res_out.p, 0, 8 * sizeof(long long), stream));
@@ -1219,6 +1308,9 @@ struct DeviceEngine {
         a.key_rule = d_key_rule.p;
         a.key_param = d_key_param.p;
         a.fparam = d_fparam.p;
+        a.tables = d_tables.p;
+        a.key_table = d_key_table.p;
+        a.key_nsym = d_key_nsym.p;
         a.out = d_res_out.p;
         int threads = 1024;  // measured on the T = 1000 chain: 1024 threads 19 ms, 256 threads 27 ms (the per-level passes over the requested marginals dominate)
         if (const char* e = getenv("CXB_ENGINE_RESIDENT_THREADS")) threads = std::max(32, std::min(1024, atoi(e) / 32 * 32));

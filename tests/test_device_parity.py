@@ -124,7 +124,7 @@ def test_out_of_contract_is_refused_not_silently_different(device_api):
         C.update_marginals(e, vids)
 
 
-@pytest.mark.parametrize("model", ["ssm", "beta"])
+@pytest.mark.parametrize("model", ["ssm", "beta", "hmm", "potts"])
 def test_resident_level_loop_equals_per_level_kernels(device_api, model, monkeypatch):
     """update_marginals! of a small graph in ONE launch (k_update_resident) leaves exactly the state, values and
     statistics of the per-level kernels (frontier discovery -> host -> rule kernels -> apply, one round trip per level)."""
@@ -140,6 +140,23 @@ def test_resident_level_loop_equals_per_level_kernels(device_api, model, monkeyp
                 models.ssm_set_data(e, y, lik, data + rep)
                 st.append(C.update_marginals(e, x))
             assert st[0].updates == 6 * T - 4 and st[1].updates == 6 * T - 4
+        elif model == "hmm":  # categorical family: CAT_TABLE, HMM_EMIT and family-reduce rules, one warp per signal
+            T, K, M = 9, 8, 5
+            rng = np.random.Generator(np.random.PCG64(12))
+            A = rng.dirichlet(np.ones(K), size=K)
+            E = rng.dirichlet(np.ones(K), size=M).T * K
+            e, z, yv, prior, em, tr = models.make_hmm_model(T, K, M, A, E, device_api)
+            models.hmm_set_data(e, z, yv, prior, em, rng.integers(0, M, size=T), K)
+            st = [C.update_marginals(e, z)]
+            assert st[0].updates == 6 * T - 4
+        elif model == "potts":  # loopy grid, protocol B: Potts rule + linked m2f signals in the final phase
+            H, W, K = 3, 4, 16
+            e, pix, un, pair = models.make_grid_model(H, W, K, 0.7, device_api)
+            flat = [v for row in pix for v in row]
+            usig = [C.get_connection_message_to_variable(e, pix[i][j], un[i][j]) for i in range(H) for j in range(W)]
+            unary = np.random.Generator(np.random.PCG64(13)).dirichlet(np.ones(K), size=len(flat))
+            models.protocol_b_init(e, flat, K)
+            st = [models.protocol_b_sweep(e, flat, usig, unary, schedule="lvl") for _ in range(2)]
         else:
             n = 40
             e, p, o, f = models.make_beta_bernoulli_model(n, device_api)
