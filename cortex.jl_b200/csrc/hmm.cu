@@ -594,6 +594,7 @@ struct Hmm {
     DBuf<float> tc_part[2];
     bool tc_ready = false;
     int tc_nt = 64;  // output states per CTA of the tensor-core step kernel (32 or 64)
+    int tc_np = 3;   // bf16 pieces per operand (3: fp32-level accuracy, the default; 2: ~2^-17 per term, CXB_HMM_TC_PIECES=2)
     bool tc_eligible() const {
         if (const char* e = getenv("CXB_HMM_NO_TC"))
             if (atoi(e)) return false;
@@ -661,16 +662,18 @@ struct Hmm {
             cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, device);
             tc_nt = (tc_bpad() / tc::M_TILE) * (K / 64) * 2 <= n_sm ? 32 : 64;
             if (const char* e = getenv("CXB_HMM_TC_NT")) tc_nt = atoi(e) == 32 ? 32 : 64;
+            tc_np = 3;
+            if (const char* e = getenv("CXB_HMM_TC_PIECES")) tc_np = atoi(e) == 2 ? 2 : 3;
             std::vector<uint16_t> img;
-            tc::build_table_image((const float*)at.data(), K, tc_nt, img);  // forward: pred[j] = sum_i msg[i] A[i][j] -> rows of A^T
+            tc::build_table_image((const float*)at.data(), K, tc_nt, tc_np, img);  // forward: pred[j] = sum_i msg[i] A[i][j] -> rows of A^T
             CXB_CUDA(tc_img_f.reserve(img.size()));
             CXB_CUDA(cudaMemcpyAsync(tc_img_f.p, img.data(), img.size() * 2, cudaMemcpyHostToDevice, stream));
             CXB_CUDA(cudaStreamSynchronize(stream));
-            tc::build_table_image((const float*)a.data(), K, tc_nt, img);   // backward: pred[j] = sum_i A[j][i] msg[i] -> rows of A
+            tc::build_table_image((const float*)a.data(), K, tc_nt, tc_np, img);   // backward: pred[j] = sum_i A[j][i] msg[i] -> rows of A
             CXB_CUDA(tc_img_b.reserve(img.size()));
             CXB_CUDA(cudaMemcpyAsync(tc_img_b.p, img.data(), img.size() * 2, cudaMemcpyHostToDevice, stream));
             const long long bpad = tc_bpad();
-            const size_t op_elems = (size_t)(bpad / tc::M_TILE) * 2 * (K / tc::K_CHUNK) * (tc::A_CHUNK_BYTES / 2);
+            const size_t op_elems = (size_t)(bpad / tc::M_TILE) * tc_np * (K / tc::K_CHUNK) * (tc::A_CHUNK_BYTES / 2);
             for (int i = 0; i < 2; ++i) {
                 CXB_CUDA(tc_op[i].reserve(op_elems));
                 CXB_CUDA(tc_part[i].reserve((size_t)2 * (K / tc_nt) * bpad));
@@ -697,13 +700,16 @@ struct Hmm {
         return CXB_OK;
     }
     // one launch per time step and pass (hmm_tc.cuh); 2 T + 4 launches
-    int32_t launch_tc() { return tc_nt == 32 ? launch_tc_nt<32>() : launch_tc_nt<64>(); }
-    template <int NT>
+    int32_t launch_tc() {
+        if (tc_np == 2) return tc_nt == 32 ? launch_tc_nt<32, 2>() : launch_tc_nt<64, 2>();
+        return tc_nt == 32 ? launch_tc_nt<32, 3>() : launch_tc_nt<64, 3>();
+    }
+    template <int NT, int NP>
     int32_t launch_tc_nt() {
         const int bpad = (int)tc_bpad(), tiles = bpad / tc::M_TILE, n_slices = K / NT;
-        const size_t smem = tc::step_smem_bytes<NT>(M), row = (size_t)B * K;
-        CXB_CUDA(cudaFuncSetAttribute(tc::k_hmm_tc_step<true, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        CXB_CUDA(cudaFuncSetAttribute(tc::k_hmm_tc_step<false, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        const size_t smem = tc::step_smem_bytes<NT, NP>(M), row = (size_t)B * K;
+        CXB_CUDA(cudaFuncSetAttribute(tc::k_hmm_tc_step<true, NT, NP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CXB_CUDA(cudaFuncSetAttribute(tc::k_hmm_tc_step<false, NT, NP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         float *fw = (float*)fwd.p, *mg = (float*)marg.p;
         tc::StepArgs a{};
         a.emis_n = (const float*)En.p;
@@ -736,9 +742,9 @@ struct Hmm {
                 a.fwd_t = f ? nullptr : fw + (size_t)t * row;
                 if (s == 0) {
                     if (f)
-                        CXB_LAUNCH((tc::k_hmm_tc_init<true, NT>), igrid, 128, 0, stream, a);
+                        CXB_LAUNCH((tc::k_hmm_tc_init<true, NT, NP>), igrid, 128, 0, stream, a);
                     else
-                        CXB_LAUNCH((tc::k_hmm_tc_init<false, NT>), igrid, 128, 0, stream, a);
+                        CXB_LAUNCH((tc::k_hmm_tc_init<false, NT, NP>), igrid, 128, 0, stream, a);
                 } else {
                     cudaLaunchConfig_t cfg{};
                     cfg.gridDim = grid;
@@ -750,7 +756,7 @@ struct Hmm {
                     attr[0].val.programmaticStreamSerializationAllowed = pdl ? 1 : 0;
                     cfg.attrs = attr;
                     cfg.numAttrs = 1;
-                    CXB_CUDA(cudaLaunchKernelEx(&cfg, f ? tc::k_hmm_tc_step<true, NT> : tc::k_hmm_tc_step<false, NT>, a));
+                    CXB_CUDA(cudaLaunchKernelEx(&cfg, f ? tc::k_hmm_tc_step<true, NT, NP> : tc::k_hmm_tc_step<false, NT, NP>, a));
                     ++::cxb::g_kernel_launches;
                 }
             }

@@ -28,11 +28,14 @@ constexpr int M_TILE = 128;   // chains per CTA (MMA M)
 // output states per CTA (MMA N) is a template parameter NT: 64 (64 CTAs at B = 1,024, K = 512) or 32 (128 CTAs: less
 // operand ingest and half the epilogue per SM, more aggregate L2 traffic)
 constexpr int K_CHUNK = 64;   // input states per operand chunk (4 MMA K-steps of 16)
-template <int NT>
+// NP = bf16 pieces per operand: x = p0 + p1 (+ p2), p_k = bf16(residual). NP = 2 keeps ~2^-17 per term (enough for dense
+// tables, where the 512 terms of a sum average it out; NOT for sparse ones: 1e-4 on a banded matrix), NP = 3 keeps
+// ~2^-25 (fp32-level; the default). Products p_a * q_b with a + b < NP: 3 or 6 MMAs per 16 input states.
+template <int NT, int NP>
 struct Cfg {
-    static constexpr uint32_t B_CHUNK_BYTES = NT * 64 * 2;                    // table chunk, per hi / lo
-    static constexpr uint32_t STAGE_BYTES = 2 * (128 * 64 * 2) + 2 * B_CHUNK_BYTES;  // message hi/lo + table hi/lo
-    static constexpr int STAGES = NT == 64 ? 4 : 5;                           // 192 KB / 200 KB of operands in flight
+    static constexpr uint32_t B_CHUNK_BYTES = NT * 64 * 2;                    // table chunk, per piece
+    static constexpr uint32_t STAGE_BYTES = NP * (128 * 64 * 2) + NP * B_CHUNK_BYTES;  // message pieces + table pieces
+    static constexpr int STAGES = (int)((200u * 1024u) / STAGE_BYTES);        // ~200 KB of operands in flight
     // instruction descriptor: D = f32, A = B = bf16, both K-major, N = NT, M = 128
     static constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(NT >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
 };
@@ -114,18 +117,24 @@ __device__ __forceinline__ float rcp_nr(float x) {  // MUFU.RCP + one Newton ste
     asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(q) : "f"(x));
     return fmaf(q, fmaf(-x, q, 1.0f), q);
 }
-// split 8 consecutive values into bf16 hi / lo and store them as two 16-byte vectors
-__device__ __forceinline__ void split_store8(const float* x, __nv_bfloat16* hi_dst, __nv_bfloat16* lo_dst) {
-    uint32_t h[4], l[4];
+// split 8 consecutive values into NP bf16 pieces (piece k = bf16 of what the earlier pieces left over), one 16-byte vector each
+template <int NP>
+__device__ __forceinline__ void split_store8(const float* x, __nv_bfloat16* const (&dst)[NP]) {
+    float res[8];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        __nv_bfloat16 h0 = __float2bfloat16_rn(x[2 * i]), h1 = __float2bfloat16_rn(x[2 * i + 1]);
-        __nv_bfloat16 l0 = __float2bfloat16_rn(x[2 * i] - __bfloat162float(h0)), l1 = __float2bfloat16_rn(x[2 * i + 1] - __bfloat162float(h1));
-        h[i] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
-        l[i] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+    for (int i = 0; i < 8; ++i) res[i] = x[i];
+#pragma unroll
+    for (int pc = 0; pc < NP; ++pc) {
+        uint32_t w[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const __nv_bfloat16 p0 = __float2bfloat16_rn(res[2 * i]), p1 = __float2bfloat16_rn(res[2 * i + 1]);
+            res[2 * i] -= __bfloat162float(p0);
+            res[2 * i + 1] -= __bfloat162float(p1);
+            w[i] = (uint32_t)__bfloat16_as_ushort(p0) | ((uint32_t)__bfloat16_as_ushort(p1) << 16);
+        }
+        *reinterpret_cast<uint4*>(dst[pc]) = make_uint4(w[0], w[1], w[2], w[3]);
     }
-    *reinterpret_cast<uint4*>(hi_dst) = make_uint4(h[0], h[1], h[2], h[3]);
-    *reinterpret_cast<uint4*>(lo_dst) = make_uint4(l[0], l[1], l[2], l[3]);
 }
 
 struct StepArgs {
@@ -152,10 +161,10 @@ __device__ __forceinline__ void load_row64(const float* p, float4 (&v)[16]) {
     for (int i = 0; i < 16; ++i) v[i] = reinterpret_cast<const float4*>(p)[i];
 }
 
-template <bool FWD, int NT>
+template <bool FWD, int NT, int NP>
 __global__ void __launch_bounds__(THREADS, 1) k_hmm_tc_step(const StepArgs a) {
-    constexpr int N_TILE = NT, STAGES = Cfg<NT>::STAGES;
-    constexpr uint32_t B_CHUNK_BYTES = Cfg<NT>::B_CHUNK_BYTES, STAGE_BYTES = Cfg<NT>::STAGE_BYTES, IDESC = Cfg<NT>::IDESC;
+    constexpr int N_TILE = NT, STAGES = Cfg<NT, NP>::STAGES;
+    constexpr uint32_t B_CHUNK_BYTES = Cfg<NT, NP>::B_CHUNK_BYTES, STAGE_BYTES = Cfg<NT, NP>::STAGE_BYTES, IDESC = Cfg<NT, NP>::IDESC;
     constexpr int LPR = N_TILE / 4, RPI = 32 / LPR, ITER = 32 / RPI;  // lanes per row, rows per instruction, iterations per warp
     extern __shared__ __align__(128) unsigned char smem[];
     const int n_chunks = a.K / K_CHUNK;
@@ -196,17 +205,18 @@ __global__ void __launch_bounds__(THREADS, 1) k_hmm_tc_step(const StepArgs a) {
     if (warp == 4) {
         // ===== producer: bulk copies of the resident table slice and of the streamed message operand =====
         if (lane == 0) {
-            const __nv_bfloat16* tb = a.tbl_img + (size_t)slice * 2 * n_chunks * (B_CHUNK_BYTES / 2);
-            const __nv_bfloat16* op = a.op_in + (size_t)tile * 2 * n_chunks * (A_CHUNK_BYTES / 2);
+            const __nv_bfloat16* tb = a.tbl_img + (size_t)slice * NP * n_chunks * (B_CHUNK_BYTES / 2);
+            const __nv_bfloat16* op = a.op_in + (size_t)tile * NP * n_chunks * (A_CHUNK_BYTES / 2);
             for (int c = 0; c < n_chunks; ++c) {
                 const int s = c % STAGES;
                 const uint32_t st = smem_u32(ring + (size_t)s * STAGE_BYTES), bar = smem_u32(&full[s]);
                 mbar_wait(smem_u32(&empty[s]), ((c / STAGES) & 1) ^ 1);
                 mbar_expect_tx(bar, STAGE_BYTES);
-                bulk_g2s(st, op + (size_t)c * (A_CHUNK_BYTES / 2), A_CHUNK_BYTES, bar);
-                bulk_g2s(st + A_CHUNK_BYTES, op + (size_t)(n_chunks + c) * (A_CHUNK_BYTES / 2), A_CHUNK_BYTES, bar);
-                bulk_g2s(st + 2 * A_CHUNK_BYTES, tb + (size_t)c * (B_CHUNK_BYTES / 2), B_CHUNK_BYTES, bar);
-                bulk_g2s(st + 2 * A_CHUNK_BYTES + B_CHUNK_BYTES, tb + (size_t)(n_chunks + c) * (B_CHUNK_BYTES / 2), B_CHUNK_BYTES, bar);
+#pragma unroll
+                for (int pc = 0; pc < NP; ++pc) {
+                    bulk_g2s(st + pc * A_CHUNK_BYTES, op + (size_t)(pc * n_chunks + c) * (A_CHUNK_BYTES / 2), A_CHUNK_BYTES, bar);
+                    bulk_g2s(st + NP * A_CHUNK_BYTES + pc * B_CHUNK_BYTES, tb + (size_t)(pc * n_chunks + c) * (B_CHUNK_BYTES / 2), B_CHUNK_BYTES, bar);
+                }
             }
             stamp(a, 2);
         }
@@ -219,14 +229,16 @@ __global__ void __launch_bounds__(THREADS, 1) k_hmm_tc_step(const StepArgs a) {
                 if (c == 0) stamp(a, 3);
                 if (c == n_chunks - 1) stamp(a, 4);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                const uint32_t a_hi = smem_u32(ring + (size_t)s * STAGE_BYTES), a_lo = a_hi + A_CHUNK_BYTES;
-                const uint32_t b_hi = a_lo + A_CHUNK_BYTES, b_lo = b_hi + B_CHUNK_BYTES;
+                const uint32_t a_base = smem_u32(ring + (size_t)s * STAGE_BYTES), b_base = a_base + NP * A_CHUNK_BYTES;
 #pragma unroll
                 for (int ks = 0; ks < K_CHUNK / 16; ++ks) {
                     const uint32_t off = ks * 2 * LBO;  // 16 input states = 2 core matrices along K
-                    umma_bf16(tmem_base, smem_desc(a_hi + off), smem_desc(b_hi + off), IDESC, (c | ks) != 0);
-                    umma_bf16(tmem_base, smem_desc(a_hi + off), smem_desc(b_lo + off), IDESC, 1);
-                    umma_bf16(tmem_base, smem_desc(a_lo + off), smem_desc(b_hi + off), IDESC, 1);
+#pragma unroll
+                    for (int pa = 0; pa < NP; ++pa)
+#pragma unroll
+                        for (int pb = 0; pa + pb < NP; ++pb)  // message piece pa x table piece pb
+                            umma_bf16(tmem_base, smem_desc(a_base + pa * A_CHUNK_BYTES + off), smem_desc(b_base + pb * B_CHUNK_BYTES + off), IDESC,
+                                      (c | ks | pa | pb) != 0);
                 }
                 umma_commit(smem_u32(&empty[s]));  // frees the stage when these MMAs have read it
             }
@@ -300,8 +312,10 @@ __global__ void __launch_bounds__(THREADS, 1) k_hmm_tc_step(const StepArgs a) {
         }
         __syncwarp();  // a warp only re-reads the 32 staging rows it wrote itself
         // this slice is columns [n0, n0 + NT) of K: chunk n0 / 64 of the next step's message operand, offset n0 % 64 inside it
-        __nv_bfloat16* op_hi = a.op_out + ((size_t)tile * 2 * n_chunks + n0 / K_CHUNK) * (A_CHUNK_BYTES / 2);
-        __nv_bfloat16* op_lo = a.op_out + ((size_t)tile * 2 * n_chunks + n_chunks + n0 / K_CHUNK) * (A_CHUNK_BYTES / 2);
+        __nv_bfloat16* op_pc[NP];
+#pragma unroll
+        for (int pc = 0; pc < NP; ++pc)
+            op_pc[pc] = a.op_out + ((size_t)tile * NP * n_chunks + (size_t)pc * n_chunks + n0 / K_CHUNK) * (A_CHUNK_BYTES / 2);
 #pragma unroll
         for (int it = 0; it < ITER; ++it) {
             const int src = RPI * it + hrow, rr = warp * 32 + src, mm = tile * M_TILE + rr;
@@ -328,19 +342,20 @@ __global__ void __launch_bounds__(THREADS, 1) k_hmm_tc_step(const StepArgs a) {
             if (mm < a.B) reinterpret_cast<float4*>(a.raw_out + (size_t)mm * a.K + n0)[c4] = res;
             // next step's message operand in the canonical UMMA layout (this slice = chunk `slice` of K): 4 states = 8 bytes
             // per lane; two rows x two lanes fill whole 32-byte sectors
-            const float x4[4] = {cr.x, cr.y, cr.z, cr.w};
-            uint32_t h[2], l[2];
-#pragma unroll
-            for (int i = 0; i < 2; ++i) {
-                const __nv_bfloat16 h0 = __float2bfloat16_rn(x4[2 * i]), h1 = __float2bfloat16_rn(x4[2 * i + 1]);
-                const __nv_bfloat16 l0 = __float2bfloat16_rn(x4[2 * i] - __bfloat162float(h0)),
-                                    l1 = __float2bfloat16_rn(x4[2 * i + 1] - __bfloat162float(h1));
-                h[i] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
-                l[i] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
-            }
+            float res4[4] = {cr.x, cr.y, cr.z, cr.w};  // residuals: piece k = bf16(what pieces 0 .. k-1 left over)
             const uint32_t e = chunk_elem((uint32_t)rr, (uint32_t)(n0 % K_CHUNK + c4 * 4));
-            *reinterpret_cast<uint2*>(op_hi + e) = make_uint2(h[0], h[1]);
-            *reinterpret_cast<uint2*>(op_lo + e) = make_uint2(l[0], l[1]);
+#pragma unroll
+            for (int pc = 0; pc < NP; ++pc) {
+                uint32_t w[2];
+#pragma unroll
+                for (int i = 0; i < 2; ++i) {
+                    const __nv_bfloat16 p0 = __float2bfloat16_rn(res4[2 * i]), p1 = __float2bfloat16_rn(res4[2 * i + 1]);
+                    res4[2 * i] -= __bfloat162float(p0);
+                    res4[2 * i + 1] -= __bfloat162float(p1);
+                    w[i] = (uint32_t)__bfloat16_as_ushort(p0) | ((uint32_t)__bfloat16_as_ushort(p1) << 16);
+                }
+                *reinterpret_cast<uint2*>(op_pc[pc] + e) = make_uint2(w[0], w[1]);
+            }
         }
         if (threadIdx.x == 0) stamp(a, 8);
     }
@@ -351,7 +366,7 @@ __global__ void __launch_bounds__(THREADS, 1) k_hmm_tc_step(const StepArgs a) {
 }
 
 // first step of a pass: carried message = emission message; result = emission (FWD) / forward message (BWD)
-template <bool FWD, int NT>
+template <bool FWD, int NT, int NP>
 __global__ void k_hmm_tc_init(StepArgs a) {
     constexpr int N_TILE = NT;
     const int m = blockIdx.x * blockDim.x + threadIdx.x;  // chain (padded)
@@ -361,8 +376,6 @@ __global__ void k_hmm_tc_init(StepArgs a) {
     const int tile = m / M_TILE, row = m % M_TILE;
     int o = live ? (int)a.obs_t[m] : 0;
     if (o >= a.n_sym) o = a.n_sym - 1;
-    __nv_bfloat16* op_hi = a.op_out + ((size_t)tile * 2 * n_chunks + n0 / K_CHUNK) * (A_CHUNK_BYTES / 2);
-    __nv_bfloat16* op_lo = a.op_out + ((size_t)tile * 2 * n_chunks + n_chunks + n0 / K_CHUNK) * (A_CHUNK_BYTES / 2);
     float sum_c = 0.0f, sum_r = 0.0f;
     for (int k0 = 0; k0 < N_TILE; k0 += 8) {
         float c[8];
@@ -377,7 +390,11 @@ __global__ void k_hmm_tc_init(StepArgs a) {
             }
         }
         const uint32_t e = chunk_elem((uint32_t)row, (uint32_t)(n0 % K_CHUNK + k0));
-        split_store8(c, op_hi + e, op_lo + e);
+        __nv_bfloat16* dst[NP];
+#pragma unroll
+        for (int pc = 0; pc < NP; ++pc)
+            dst[pc] = a.op_out + ((size_t)tile * NP * n_chunks + (size_t)pc * n_chunks + n0 / K_CHUNK) * (A_CHUNK_BYTES / 2) + e;
+        split_store8<NP>(c, dst);
     }
     a.part_out[(size_t)(0 * n_slices + slice) * a.Bpad + m] = sum_c;
     a.part_out[(size_t)(1 * n_slices + slice) * a.Bpad + m] = sum_r;
@@ -392,9 +409,10 @@ __global__ void k_hmm_tc_finish(float* raw, const float* part, int B, int Bpad, 
     for (int n = threadIdx.x; n < K; n += blockDim.x) raw[(size_t)m * K + n] *= q;
 }
 
-template <int NT>
+template <int NT, int NP>
 inline size_t step_smem_bytes(int n_sym) {
-    return (size_t)Cfg<NT>::STAGES * Cfg<NT>::STAGE_BYTES + (size_t)n_sym * NT * sizeof(float) + (2 * Cfg<NT>::STAGES + 1) * sizeof(uint64_t) + 16;
+    return (size_t)Cfg<NT, NP>::STAGES * Cfg<NT, NP>::STAGE_BYTES + (size_t)n_sym * NT * sizeof(float) +
+           (2 * Cfg<NT, NP>::STAGES + 1) * sizeof(uint64_t) + 16;
 }
 
 // host: bf16 round-to-nearest-even of a float
@@ -412,18 +430,20 @@ inline float bf16_to_float_host(uint16_t h) {
     return x;
 }
 // table image: rows[n][k] (n = output state, k = input state), fp32 -> [slice][2][chunk][NT x 64] hi / lo in the canonical layout
-inline void build_table_image(const float* rows, int K, int N_TILE, std::vector<uint16_t>& img) {
+inline void build_table_image(const float* rows, int K, int N_TILE, int n_pieces, std::vector<uint16_t>& img) {
     const int n_chunks = K / K_CHUNK, n_slices = K / N_TILE;
     const size_t B_CHUNK_BYTES = (size_t)N_TILE * K_CHUNK * 2;
-    img.assign((size_t)n_slices * 2 * n_chunks * (B_CHUNK_BYTES / 2), 0);
+    img.assign((size_t)n_slices * n_pieces * n_chunks * (B_CHUNK_BYTES / 2), 0);
     for (int n = 0; n < K; ++n)
         for (int k = 0; k < K; ++k) {
-            const float x = rows[(size_t)n * K + k];
-            const uint16_t hi = bf16_rn_host(x), lo = bf16_rn_host(x - bf16_to_float_host(hi));
+            float res = rows[(size_t)n * K + k];
             const int slice = n / N_TILE, r = n % N_TILE, c = k / K_CHUNK, kk = k % K_CHUNK;
-            const size_t base = (size_t)slice * 2 * n_chunks * (B_CHUNK_BYTES / 2);
-            img[base + (size_t)c * (B_CHUNK_BYTES / 2) + chunk_elem(r, kk)] = hi;
-            img[base + (size_t)(n_chunks + c) * (B_CHUNK_BYTES / 2) + chunk_elem(r, kk)] = lo;
+            const size_t base = (size_t)slice * n_pieces * n_chunks * (B_CHUNK_BYTES / 2);
+            for (int pc = 0; pc < n_pieces; ++pc) {
+                const uint16_t piece = bf16_rn_host(res);
+                res -= bf16_to_float_host(piece);
+                img[base + (size_t)(pc * n_chunks + c) * (B_CHUNK_BYTES / 2) + chunk_elem(r, kk)] = piece;
+            }
         }
 }
 

@@ -634,3 +634,52 @@ def test_degenerate_shapes_of_the_structured_engines():
     hm.update_marginals()
     want_f, want_m = _hmm_numpy(A.astype(np.float32).astype(np.float64), E, obs[:, 0])
     assert_close(hm.get_marginals()[:, 0, :], want_m, cap.F32)
+
+
+# ---- numerically awkward inputs ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("K", [64, 128])
+def test_hmm_sparse_transitions_and_peaked_emissions(K):
+    """Banded transition matrix (most entries exactly zero) and emissions spanning 8 orders of magnitude: the
+    power-of-two scaling of the K = 64 and tensor-core kernels must neither overflow nor lose the small states."""
+    B, T, M = 6, 400, 6
+    rng = np.random.Generator(np.random.PCG64(404 + K))
+    A = np.zeros((K, K))
+    for i in range(K):
+        for dlt, w in ((0, 0.6), (1, 0.3), (2, 0.1)):
+            A[i, (i + dlt) % K] += w
+    E = np.exp(rng.uniform(-18.0, 0.0, size=(K, M)))
+    obs = rng.integers(0, M, size=(T, B)).astype(np.uint8)
+    hm = C.HmmBatch(B, T, K, M, dtype=cap.F32)
+    hm.set_tables(A, E)
+    hm.set_observations(obs)
+    hm.update_marginals()
+    got_m, got_f = hm.get_marginals(), hm.get_forward()
+    assert np.all(np.isfinite(got_m)) and np.all(np.isfinite(got_f))
+    A_used = A.astype(np.float32).astype(np.float64)
+    for b in (0, B - 1):
+        want_f, want_m = _hmm_numpy(A_used, E, obs[:, b])
+        # entries far below the fp32 resolution of a normalised vector carry no information: compare above 1e-7 of the max
+        for got, want in ((got_f[:, b, :], want_f), (got_m[:, b, :], want_m)):
+            np.testing.assert_allclose(got, want, rtol=2e-5, atol=2e-5 * 1e-2)
+            np.testing.assert_allclose(got.sum(axis=-1), 1.0, atol=4e-6)
+
+
+def test_chain_batch_extreme_noise(oracle_api):
+    """q = 0 (the state is a constant), very small and very large observation noise, fp64 against the oracle."""
+    T = 30
+    rng = np.random.Generator(np.random.PCG64(9))
+    q = np.array([0.0, 1e-8, 1e6, 1.0])
+    r = np.array([1.0, 1e-6, 1e-6, 1e8])
+    B = len(q)
+    y = rng.standard_normal((T, B)) * 3.0
+    ch = C.GaussianChainBatch(B, T, dtype=cap.F64)
+    ch.set_noise(q, r)
+    ch.set_observations(y)
+    ch.update_marginals()
+    got = ch.get_marginals()
+    for b in range(B):
+        e, x, yv, lik, tr = models.make_ssm_model(T, oracle_api, form="canon", q=float(q[b]), r=float(r[b]))
+        models.ssm_set_data(e, yv, lik, y[:, b])
+        C.update_marginals(e, x, schedule="seq")
+        want = C.get_values([C.get_variable_marginal(C.get_variable(e, v)) for v in x])
+        np.testing.assert_allclose(got[:, b, :], want, rtol=1e-12, atol=0)
