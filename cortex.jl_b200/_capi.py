@@ -20,9 +20,10 @@ F32, F64 = 0, 1
 KIND_UNSPECIFIED, KIND_M2F, KIND_M2V, KIND_PRODUCT, KIND_MARGINAL, KIND_JOINT = range(6)
 DEP_INTERMEDIATE, DEP_WEAK, DEP_NO_LISTEN, DEP_NO_CHECK_COMPUTED = 1, 2, 16, 32
 NIB_INTERMEDIATE, NIB_WEAK, NIB_COMPUTED, NIB_FRESH = 1, 2, 4, 8
-FAMILY_GAUSS_CANON, FAMILY_CATEGORICAL, FAMILY_GAUSS_MV, FAMILY_BETA, FAMILY_SUM = range(5)
+(FAMILY_GAUSS_CANON, FAMILY_CATEGORICAL, FAMILY_GAUSS_MV, FAMILY_BETA, FAMILY_SUM, FAMILY_GAUSS_MP, FAMILY_GAMMA,
+ FAMILY_POINT) = range(8)
 (RULE_NONE, RULE_GAUSS_OBS, RULE_GAUSS_RW, RULE_CAT_TABLE, RULE_POTTS, RULE_HMM_EMIT, RULE_GAUSS_MV_OBS,
- RULE_GAUSS_MV_RW, RULE_BETA_BERNOULLI, RULE_SCALE2) = range(10)
+ RULE_GAUSS_MV_RW, RULE_BETA_BERNOULLI, RULE_SCALE2, RULE_NORMAL_MEAN_FIELD) = range(11)
 RESOLVER_NONE, RESOLVER_DEFAULT_BP, RESOLVER_MEAN_FIELD = range(3)
 
 i32, i64, u8p, i32p, i64p, f64p, vp = (C.c_int32, C.c_int64, C.POINTER(C.c_uint8), C.POINTER(C.c_int32),
@@ -45,6 +46,7 @@ _COMMON = {
     "graph_build": (i32, [vp, i64, u8p, i32p, i64, i64p, i64p]),
     "register_rule": (i32, [vp, i32, i32, f64p, i64]),
     "set_factor_params": (i32, [vp, i64, i64p, f64p]),
+    "set_variable_families": (i32, [vp, i64, i64p, i32p]),
     "create_signal": (i64, [vp]),
     "add_dependency": (i32, [vp, i64, i64, i32]),
     "resolve_dependencies": (i32, [vp, i32]),

@@ -38,6 +38,7 @@ struct View {
     uint8_t* props;
     const uint8_t *kind, *rkey;
     const int32_t *svar, *sfac;
+    const uint8_t* sfam;              // per-signal value family (cxb_set_variable_families), nullptr = the engine family
     uint32_t *done_epoch, *visit_epoch;
     uint32_t* front_epoch;            // == lvl_epoch: member of the current level's frontier
     uint32_t* front;                  // frontier buffer, partitioned by rule key
@@ -256,6 +257,18 @@ __global__ void k_pending_single(View e, uint32_t s, int* out) { *out = pending_
 // Small fixed-size values (dim <= 4): one thread per signal. Families GAUSS_CANON / GAUSS_MV / BETA / SUM and
 // the scalar m2v rules. rule < 0 => family reduce (m2f / ProductOfMessages / marginal), left-to-right
 // (test/inference_engine_tests.jl:385-413).
+// moments of a 2-parameter value by family (test/runtests.jl:36-38, 57-59, 68-69); POINT: the value itself, variance 0
+template <class T>
+__device__ __forceinline__ T vmp_mean(int fam, const T* v) {
+    return fam == CXB_FAMILY_GAMMA ? v[0] * v[1] : v[0];
+}
+template <class T>
+__device__ __forceinline__ T vmp_var(int fam, const T* v) {
+    if (fam == CXB_FAMILY_GAMMA) return v[0] * (v[1] * v[1]);
+    if (fam == CXB_FAMILY_GAUSS_MP) return T(1) / v[1];
+    if (fam == CXB_FAMILY_GAUSS_MV) return v[1];
+    return T(0);
+}
 template <class T>
 __device__ __forceinline__ void rule_small_one(const View& e, T* __restrict__ val, uint32_t s, int family, int rule,
                                                const T* __restrict__ fparam, T default_param) {
@@ -270,10 +283,23 @@ __device__ __forceinline__ void rule_small_one(const View& e, T* __restrict__ va
         const T* a = val + (size_t)e.dep_ids[off] * dim;
         for (int k = 0; k < dim; ++k) acc[k] = a[k];
     }
+    if (e.sfam) family = e.sfam[s];
     if (rule < 0) {
+        if (family == CXB_FAMILY_POINT) {  // an observed value has no product
+            atomicOr(e.err_flag, ERR_RULE_ARG);
+            return;
+        }
         for (uint32_t j = 1; j < nd; ++j) {
             const T* b = val + (size_t)e.dep_ids[off + j] * dim;
-            if (family == CXB_FAMILY_GAUSS_CANON || family == CXB_FAMILY_SUM) {
+            if (family == CXB_FAMILY_GAUSS_MP) {  // test/runtests.jl:89-95
+                T xi = acc[0] * acc[1] + b[0] * b[1];
+                T w = acc[1] + b[1];
+                acc[0] = (T(1) / w) * xi;
+                acc[1] = w;
+            } else if (family == CXB_FAMILY_GAMMA) {  // test/runtests.jl:97-99
+                acc[0] = acc[0] + b[0] - T(1);
+                acc[1] = (acc[1] * b[1]) / (acc[1] + b[1]);
+            } else if (family == CXB_FAMILY_GAUSS_CANON || family == CXB_FAMILY_SUM) {
                 for (int k = 0; k < dim; ++k) acc[k] = acc[k] + b[k];
             } else if (family == CXB_FAMILY_GAUSS_MV) {  // test/runtests.jl:40-46
                 T xi = acc[0] / acc[1] + b[0] / b[1];
@@ -320,6 +346,30 @@ __device__ __forceinline__ void rule_small_one(const View& e, T* __restrict__ va
             case CXB_RULE_SCALE2:
                 for (int k = 0; k < dim; ++k) acc[k] = T(2) * acc[k];
                 break;
+            case CXB_RULE_NORMAL_MEAN_FIELD: {  // test/inference_engine_tests.jl:652-695
+                if (nd != 2 || dim < 2 || !e.sfam) {
+                    atomicOr(e.err_flag, ERR_RULE_ARG);
+                    return;
+                }
+                const uint32_t da = e.dep_ids[off], db = e.dep_ids[off + 1];
+                const int fa = e.sfam[da], fb = e.sfam[db];
+                const T* a = val + (size_t)da * dim;
+                const T* b = val + (size_t)db * dim;
+                if ((fa == CXB_FAMILY_GAMMA) != (fb == CXB_FAMILY_GAMMA)) {  // towards out / mean (:666-676)
+                    const T* w = fa == CXB_FAMILY_GAMMA ? a : b;
+                    const T* o = fa == CXB_FAMILY_GAMMA ? b : a;
+                    acc[0] = vmp_mean<T>(fa == CXB_FAMILY_GAMMA ? fb : fa, o);
+                    acc[1] = w[0] * w[1];
+                } else if (fa != CXB_FAMILY_GAMMA) {  // towards the precision (:678-692)
+                    const T dm = vmp_mean<T>(fa, a) - vmp_mean<T>(fb, b);
+                    acc[0] = T(1.5);
+                    acc[1] = T(2) / (vmp_var<T>(fa, a) + vmp_var<T>(fb, b) + dm * dm);
+                } else {
+                    atomicOr(e.err_flag, ERR_RULE_ARG);
+                    return;
+                }
+                break;
+            }
             default:
                 atomicOr(e.err_flag, ERR_RULE_ARG);
                 return;
@@ -699,6 +749,9 @@ struct DeviceEngine {
     std::map<int32_t, RuleDef> rules;     // by factor type
     std::vector<int32_t> key_ftype;       // key-1 -> factor type
     std::vector<double> fparam;           // per id, NaN = unset
+    std::vector<uint8_t> var_family;      // per id, 0xFF = the engine family (cxb_set_variable_families)
+    bool has_var_family = false;
+    DBuf<uint8_t> d_sfam;
     uint32_t req_epoch = 0, lvl_epoch = 0;
     size_t n_uploaded = 0;
 
@@ -791,6 +844,7 @@ struct DeviceEngine {
         v.rkey = d_rkey.p;
         v.svar = d_svar.p;
         v.sfac = d_sfac.p;
+        v.sfam = has_var_family ? d_sfam.p : nullptr;
         v.done_epoch = d_done.p;
         v.visit_epoch = d_visit.p;
         v.front_epoch = d_front_epoch.p;
@@ -921,6 +975,15 @@ struct DeviceEngine {
                 ((double*)fp.data())[i] = v;
         }
         if ((st = up(d_fparam, fp.data(), fp.size()))) return st;
+        if (has_var_family) {  // per-signal family = family of the signal's variable
+            const size_t N = (size_t)g.n_sig();
+            std::vector<uint8_t> sfam(std::max<size_t>(N, 1), (uint8_t)family);
+            for (size_t s2 = 0; s2 < N; ++s2) {
+                const int64_t v = g.svar[s2];
+                if (v >= 0 && v < (int64_t)var_family.size() && var_family[v] != 0xFF) sfam[s2] = var_family[v];
+            }
+            if ((st = up(d_sfam, sfam.data(), sfam.size()))) return st;
+        }
         CXB_CUDA(cudaStreamSynchronize(stream));
         rules_dirty = false;
         return CXB_OK;
@@ -1597,6 +1660,25 @@ int32_t cxb_set_factor_params(cxb_engine* h, int64_t n, const int64_t* factor_id
         }
         e->fparam[f] = values[i];
     }
+    e->rules_dirty = true;
+    return CXB_OK;
+}
+int32_t cxb_set_variable_families(cxb_engine* h, int64_t n, const int64_t* variable_ids, const int32_t* families) {
+    DeviceEngine* e = E(h);
+    for (int64_t i = 0; i < n; ++i) {
+        const int64_t v = variable_ids[i];
+        if (v < 0 || v >= e->g.n_ids || e->g.is_factor[v]) {
+            e->err = "set_variable_families: not a variable id";
+            return CXB_ERR_BAD_ARG;
+        }
+        if (families[i] < 0 || families[i] > CXB_FAMILY_POINT || families[i] == CXB_FAMILY_CATEGORICAL) {
+            e->err = "set_variable_families: family must be one of the fixed-size (non-categorical) families";
+            return CXB_ERR_BAD_ARG;
+        }
+        if ((int64_t)e->var_family.size() < e->g.n_ids) e->var_family.resize((size_t)e->g.n_ids, 0xFF);
+        e->var_family[v] = (uint8_t)families[i];
+    }
+    if (n > 0) e->has_var_family = true;
     e->rules_dirty = true;
     return CXB_OK;
 }

@@ -26,7 +26,26 @@ from .model_engine import (Connection, Factor, Variable, backend_get_connected_f
 
 # ---- dependency resolvers: src/dependencies.jl:1-3 -------------------------------------------------
 class AbstractDependencyResolver:
+    """A resolver is either one of the built-in wirings (``resolver_kind``: run inside the library) or a user subclass
+    that overrides ``resolve_factor_dependencies`` / ``resolve_variable_dependencies`` and calls ``add_dependency``
+    itself, as the reference's tests do (test/inference_engine_tests.jl:597-621, 811-907)."""
     resolver_kind = capi.RESOLVER_NONE
+
+    def resolve_factor_dependencies(self, engine, factor_id):  # src/dependencies.jl:17
+        raise NotImplementedError
+
+    def resolve_variable_dependencies(self, engine, variable_id):  # src/dependencies.jl:33
+        raise NotImplementedError
+
+    def resolve_dependencies(self, engine):
+        """resolve_dependencies!(resolver, engine), src/dependencies.jl:5-15: every factor, then every variable."""
+        if self.resolver_kind != capi.RESOLVER_NONE:
+            engine.store.check(engine.api.resolve_dependencies(engine.store.h, self.resolver_kind))
+            return
+        for factor_id in get_factor_ids(engine):
+            self.resolve_factor_dependencies(engine, factor_id)
+        for variable_id in get_variable_ids(engine):
+            self.resolve_variable_dependencies(engine, variable_id)
 
 
 class DefaultDependencyResolver(AbstractDependencyResolver):
@@ -165,7 +184,7 @@ class InferenceEngine:
         if trace:
             self.store.check(self.api.trace_enable(self.store.h, 1))
         if resolve_dependencies:
-            self.store.check(self.api.resolve_dependencies(self.store.h, resolver.resolver_kind))
+            resolver.resolve_dependencies(self)
             n = self.api.get_warnings(self.store.h, None, 0)
             if n > 0:
                 buf = np.zeros(n, dtype=np.int64)
@@ -306,6 +325,15 @@ def get_connected_variable_ids(engine: InferenceEngine, factor_id: int):
 
 def get_connected_factor_ids(engine: InferenceEngine, variable_id: int):
     return backend_get_connected_factor_ids(engine.model_engine, variable_id)
+
+
+def set_variable_families(engine: InferenceEngine, variable_ids, families) -> None:
+    """Value type of the signals of each variable in a model that mixes value types (``CXB_FAMILY_*``). In the
+    reference the type travels with the Julia value (NormalMeanPrecision / Gamma / Float64, test/runtests.jl:52-99)."""
+    ids = np.ascontiguousarray(_as_ids(variable_ids), dtype=np.int64)
+    fam = np.ascontiguousarray(np.broadcast_to(np.asarray(families, dtype=np.int32), ids.shape))
+    engine.store.check(engine.api.set_variable_families(engine.store.h, len(ids), ids.ctypes.data_as(capi.i64p),
+                                                        fam.ctypes.data_as(capi.i32p)))
 
 
 def link_signal_to_variable(variable: Variable, signal: Signal) -> None:

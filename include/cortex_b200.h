@@ -80,7 +80,12 @@ enum {
     CXB_FAMILY_CATEGORICAL = 1, /* element-wise product, normalised to sum 1        */
     CXB_FAMILY_GAUSS_MV = 2,    /* (mean, variance) product of test/runtests.jl:40-46              */
     CXB_FAMILY_BETA = 3,        /* (a1+a2-1, b1+b2-1), test/inference_engine_tests.jl:273-294      */
-    CXB_FAMILY_SUM = 4          /* plain sum, test/inference_engine_tests.jl:1179                   */
+    CXB_FAMILY_SUM = 4,         /* plain sum, test/inference_engine_tests.jl:1179                   */
+    /* value types of the variational (VMP) models, test/inference_engine_tests.jl:593-809; assigned per
+     * variable with cxb_set_variable_families (a model mixes them), value_dim = 2: */
+    CXB_FAMILY_GAUSS_MP = 5,    /* NormalMeanPrecision (mean, precision): product of test/runtests.jl:89-95 */
+    CXB_FAMILY_GAMMA = 6,       /* Gamma (shape, scale): product of test/runtests.jl:97-99               */
+    CXB_FAMILY_POINT = 7        /* observed value (value[0]); has no product                              */
 };
 
 /* ---- message-to-variable rules, registered per factor type (Factor.functional_form,
@@ -95,7 +100,13 @@ enum {
     CXB_RULE_GAUSS_MV_OBS = 6, /* N(y, r)            test/inference_engine_tests.jl:425-426 (r = 1.0 there)      */
     CXB_RULE_GAUSS_MV_RW = 7,  /* N(m, v + q)        test/inference_engine_tests.jl:427-428 (q = 1.0 there)      */
     CXB_RULE_BETA_BERNOULLI = 8, /* Beta(1 + r, 2 - r) test/inference_engine_tests.jl:256-258                    */
-    CXB_RULE_SCALE2 = 9        /* 2 * x              test/inference_engine_tests.jl:1163-1166                    */
+    CXB_RULE_SCALE2 = 9,       /* 2 * x              test/inference_engine_tests.jl:1163-1166                    */
+    /* Normal node N(out | mean, precision^-1) under the mean-field factorisation; the m2v rule of BOTH factor types
+     * of test/inference_engine_tests.jl:652-695 (two dependencies = the marginals of the other two variables):
+     *   one of them Gamma (the precision) -> NormalMeanPrecision(mean(other), mean(precision))        (:666-676)
+     *   none of them Gamma (target = precision) -> Gamma(1.5, 2 / (var(a) + var(b) + (mean(a) - mean(b))^2)) (:678-692)
+     * mean / var by the dependency's family (POINT: value, 0). */
+    CXB_RULE_NORMAL_MEAN_FIELD = 10
 };
 
 /* ---- dependency resolvers: src/dependencies.jl -------------------------------------------- */
@@ -138,6 +149,10 @@ int32_t cxb_register_rule(cxb_engine* h, int32_t factor_type, int32_t rule_kind,
                           int64_t n_params);
 /* per-factor scalar parameter (noise variance of that factor); default = params[0] of its rule */
 int32_t cxb_set_factor_params(cxb_engine* h, int64_t n, const int64_t* factor_ids, const double* values);
+/* Value family of the signals of a variable (its marginal, messages, ProductOfMessages nodes) when the model mixes
+ * value types; default = the engine family given to cxb_create. In the reference the type is carried by the Julia
+ * value itself (NormalMeanPrecision / Gamma / Float64, test/runtests.jl:52-99) and `product` dispatches on it. */
+int32_t cxb_set_variable_families(cxb_engine* h, int64_t n, const int64_t* variable_ids, const int32_t* families);
 
 /* create_inference_signal(), src/inference_signal.jl:140-142 -> sid */
 int64_t cxb_create_signal(cxb_engine* h);

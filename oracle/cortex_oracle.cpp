@@ -75,6 +75,7 @@ struct Oracle {
     std::vector<int32_t> ftype;
     std::vector<double> fparam;
     std::vector<uint8_t> fparam_set;
+    std::vector<uint8_t> var_family;  // per id, 0xFF = the engine family (cxo_set_variable_families)
     std::vector<std::vector<int64_t>> nbr;
     std::vector<int64_t> variables, factors, marg_of;  // marg_of[id] = sid or -1
     std::unordered_map<uint64_t, int64_t> conn;        // (v,f) -> connection index
@@ -209,9 +210,29 @@ struct Oracle {
             return CXB_ERR_NO_RULE;
         }
         std::memcpy(out, value(s.deps[0]), sizeof(double) * dim);
+        const int family = family_of(s);  // `product` dispatches on the value type (test/runtests.jl:40-46, 89-99)
+        if (family == CXB_FAMILY_POINT) {
+            err = "combine: an observed value has no product";
+            return CXB_ERR_NO_RULE;
+        }
         for (int64_t i = 1; i < s.ndeps; ++i) {
             const double* b = value(s.deps[i]);
             switch (family) {
+                case CXB_FAMILY_GAUSS_MP: {  // test/runtests.jl:89-95
+                    double xi = out[0] * out[1] + b[0] * b[1];
+                    double w = out[1] + b[1];
+                    double precision = w;
+                    out[0] = (1 / precision) * xi;
+                    out[1] = precision;
+                    break;
+                }
+                case CXB_FAMILY_GAMMA: {  // test/runtests.jl:97-99
+                    double shape = out[0] + b[0] - 1;
+                    double scale = (out[1] * b[1]) / (out[1] + b[1]);
+                    out[0] = shape;
+                    out[1] = scale;
+                    break;
+                }
                 case CXB_FAMILY_GAUSS_CANON:
                 case CXB_FAMILY_SUM:
                     for (int k = 0; k < dim; ++k) out[k] = out[k] + b[k];
@@ -238,6 +259,18 @@ struct Oracle {
         }
         if (family == CXB_FAMILY_CATEGORICAL) normalise(out, dim);
         return CXB_OK;
+    }
+    int family_of(const Sig& s) const {
+        if (s.var >= 0 && s.var < (int64_t)var_family.size() && var_family[s.var] != 0xFF) return var_family[s.var];
+        return family;
+    }
+    // mean / var of a 2-parameter value by family (test/runtests.jl:36-38, 57-59, 68-69); POINT: the value itself, 0
+    static double vmp_mean(int fam, const double* v) { return fam == CXB_FAMILY_GAMMA ? v[0] * v[1] : v[0]; }
+    static double vmp_var(int fam, const double* v) {
+        if (fam == CXB_FAMILY_GAMMA) return v[0] * (v[1] * v[1]);
+        if (fam == CXB_FAMILY_GAUSS_MP) return 1 / v[1];
+        if (fam == CXB_FAMILY_GAUSS_MV) return v[1];
+        return 0.0;
     }
     int32_t rule_m2v(const Sig& s, double* out) {
         const Rule* r = rule_of_factor(s.fac);
@@ -280,6 +313,28 @@ struct Oracle {
             case CXB_RULE_SCALE2:  // :1163-1166
                 for (int k = 0; k < dim; ++k) out[k] = 2 * in[k];
                 return CXB_OK;
+            case CXB_RULE_NORMAL_MEAN_FIELD: {  // test/inference_engine_tests.jl:652-695
+                if (s.ndeps != 2 || dim < 2) {
+                    err = "NORMAL_MEAN_FIELD: expects the marginals of the two other variables (value_dim >= 2)";
+                    return CXB_ERR_NO_RULE;
+                }
+                const int fa = family_of(sig[s.deps[0]]), fb = family_of(sig[s.deps[1]]);
+                const double *a = value(s.deps[0]), *b = value(s.deps[1]);
+                if ((fa == CXB_FAMILY_GAMMA) != (fb == CXB_FAMILY_GAMMA)) {  // :666-676
+                    const bool a_is_w = fa == CXB_FAMILY_GAMMA;
+                    out[0] = a_is_w ? vmp_mean(fb, b) : vmp_mean(fa, a);
+                    out[1] = a_is_w ? vmp_mean(fa, a) : vmp_mean(fb, b);
+                    return CXB_OK;
+                }
+                if (fa != CXB_FAMILY_GAMMA) {  // :678-692
+                    double dm = vmp_mean(fa, a) - vmp_mean(fb, b);
+                    out[0] = 1.5;
+                    out[1] = 2 / (vmp_var(fa, a) + vmp_var(fb, b) + dm * dm);
+                    return CXB_OK;
+                }
+                err = "NORMAL_MEAN_FIELD: two Gamma dependencies";
+                return CXB_ERR_NO_RULE;
+            }
             case CXB_RULE_CAT_TABLE:
             case CXB_RULE_POTTS: {
                 if (s.ndeps != 1) {
@@ -758,6 +813,23 @@ int32_t cxo_register_rule(void* h, int32_t factor_type, int32_t rule_kind, const
     r.kind = rule_kind;
     if (params && n_params > 0) r.params.assign(params, params + n_params);
     O(h)->rules[factor_type] = r;
+    return CXB_OK;
+}
+int32_t cxo_set_variable_families(void* h, int64_t n, const int64_t* variable_ids, const int32_t* families) {
+    Oracle* o = O(h);
+    for (int64_t i = 0; i < n; ++i) {
+        int64_t v = variable_ids[i];
+        if (v < 0 || v >= o->n_ids || o->is_factor[v]) {
+            o->err = "set_variable_families: not a variable id";
+            return CXB_ERR_BAD_ARG;
+        }
+        if (families[i] < 0 || families[i] > CXB_FAMILY_POINT || families[i] == CXB_FAMILY_CATEGORICAL) {
+            o->err = "set_variable_families: family must be one of the fixed-size (non-categorical) families";
+            return CXB_ERR_BAD_ARG;
+        }
+        if ((int64_t)o->var_family.size() < o->n_ids) o->var_family.resize((size_t)o->n_ids, 0xFF);
+        o->var_family[v] = (uint8_t)families[i];
+    }
     return CXB_OK;
 }
 int32_t cxo_set_factor_params(void* h, int64_t n, const int64_t* factor_ids, const double* values) {

@@ -271,3 +271,66 @@ def chung_lu_edges_fast(n, m, alpha=2.5, seed=1234):
     if have.size > m:
         have = np.sort(rng.choice(have, size=m, replace=False))
     return np.stack([have // n, have % n], axis=1)
+
+
+# ---- variational message passing: the mean-field SSM of test/inference_engine_tests.jl:593-809 -------------------------
+def make_ssm_mean_field_model(n, api, *, dtype=cap.F64, resolver=None, processor=None):
+    """test/inference_engine_tests.jl:698-741 — ssnoise, obsnoise (Gamma), x_i (NormalMeanPrecision), y_i (observed);
+    likelihood_i (y_i, x_i, obsnoise), transition_i (x_i, x_{i+1}, ssnoise); same creation and edge order."""
+    g = C.BipartiteFactorGraph()
+    ssnoise = g.add_variable(C.Variable(name="ssnoise"))
+    obsnoise = g.add_variable(C.Variable(name="obsnoise"))
+    x = [g.add_variable(C.Variable(name="x", index=(i,))) for i in range(n)]
+    y = [g.add_variable(C.Variable(name="y", index=(i,))) for i in range(n)]
+    lik = [g.add_factor(C.Factor(functional_form="likelihood")) for _ in range(n)]
+    tr = [g.add_factor(C.Factor(functional_form="transition")) for _ in range(n - 1)]
+    for i in range(n):
+        g.add_edge(y[i], lik[i], C.Connection(label="out"))
+        g.add_edge(x[i], lik[i], C.Connection(label="out"))
+        g.add_edge(obsnoise, lik[i], C.Connection(label="out"))
+    for i in range(n - 1):
+        g.add_edge(x[i], tr[i], C.Connection(label="out"))
+        g.add_edge(x[i + 1], tr[i], C.Connection(label="in"))
+        g.add_edge(ssnoise, tr[i], C.Connection(label="out"))
+    builtin = processor is None
+    if builtin:
+        processor = C.RuleProcessor({"likelihood": (cap.RULE_NORMAL_MEAN_FIELD, []), "transition": (cap.RULE_NORMAL_MEAN_FIELD, [])},
+                                    family=cap.FAMILY_GAUSS_MP, value_dim=2)
+    engine = C.InferenceEngine(model_engine=g, dependency_resolver=resolver or C.MeanFieldResolver(),
+                               inference_request_processor=processor, dtype=dtype, api=api)
+    if builtin:  # the value types the reference carries in the Julia values themselves
+        C.set_variable_families(engine, [ssnoise, obsnoise], cap.FAMILY_GAMMA)
+        C.set_variable_families(engine, y, cap.FAMILY_POINT)
+    # initial marginals, :728-738
+    C.set_value(C.get_variable_marginal(C.get_variable(engine, ssnoise)), [1.0, 1.0])   # Gamma(1, 1)
+    C.set_value(C.get_variable_marginal(C.get_variable(engine, obsnoise)), [1.0, 1.0])
+    C.set_values([C.get_variable_marginal(C.get_variable(engine, v)) for v in x], np.tile([0.0, 1.0], (n, 1)))  # N(0, 1)
+    return engine, x, y, obsnoise, ssnoise, lik, tr
+
+
+def ssm_mean_field_experiment(engine, x, y, obsnoise, ssnoise, dataset, vmp_iterations, schedule="lvl"):
+    """`experiment` of test/inference_engine_tests.jl:743-781, call for call (including the repeated and merged updates)."""
+    n = len(dataset)
+    C.set_values([C.get_variable_marginal(C.get_variable(engine, v)) for v in y],
+                 np.stack([np.asarray(dataset, dtype=np.float64), np.zeros(n)], axis=1))
+    up = lambda ids: C.update_marginals(engine, ids, schedule=schedule)  # noqa: E731
+    for iteration in range(1, vmp_iterations + 1):
+        if iteration // 2 == 0:  # div(iteration, 2) == 0, :753
+            up(x), up(ssnoise), up(obsnoise)
+        else:
+            up(obsnoise), up(ssnoise), up(x)
+        for _ in range(3):
+            up(obsnoise)
+        for _ in range(3):
+            up(ssnoise)
+        up([ssnoise, obsnoise])
+    mg = lambda v: C.get_value(C.get_variable_marginal(C.get_variable(engine, v)))  # noqa: E731
+    return {"x": C.get_values([C.get_variable_marginal(C.get_variable(engine, v)) for v in x]),
+            "ssnoise": mg(ssnoise), "obsnoise": mg(obsnoise)}
+
+
+def ssm_mean_field_dataset(n, seed=1234, ssnoise_real=100.0, obsnoise_real=100.0):
+    """:785-796 with numpy's PCG64 instead of StableRNG (the assertions do not depend on the draws)."""
+    rng = np.random.Generator(np.random.PCG64(seed))
+    walk = np.cumsum(np.concatenate([[0.0], rng.standard_normal(n - 1) / np.sqrt(ssnoise_real)]))
+    return walk + rng.standard_normal(n) / np.sqrt(obsnoise_real)

@@ -1,0 +1,162 @@
+"""Variational message passing through weak dependencies and a custom resolver: the mean-field state-space model of
+the reference's test-suite (test/inference_engine_tests.jl:593-809) — SURVEY §8f row 2.
+
+CPU: the literal port (user-defined Python resolver + Python rules with the reference's signatures, sequential
+schedule) pins the built-in wiring (CXB_RESOLVER_MEAN_FIELD) and the built-in rule (CXB_RULE_NORMAL_MEAN_FIELD, value
+families per variable) of the oracle.  GPU: the device engine against the oracle."""
+import numpy as np
+import pytest
+
+from tests import models
+from tests._pkg import pkg
+
+C = pkg
+cap = pkg.capi
+
+
+class PyMeanFieldResolver(C.AbstractDependencyResolver):  # :597-621, literally
+    def resolve_variable_dependencies(self, engine, variable_id):
+        marginal = C.get_variable_marginal(C.get_variable(engine, variable_id))
+        for factor_id in C.get_connected_factor_ids(engine, variable_id):
+            C.add_dependency(marginal, C.get_connection_message_to_variable(engine, variable_id, factor_id), intermediate=True)
+
+    def resolve_factor_dependencies(self, engine, factor_id):
+        vs = C.get_connected_variable_ids(engine, factor_id)
+        for v1 in vs:
+            for v2 in vs:
+                if v1 != v2:
+                    C.add_dependency(C.get_connection_message_to_variable(engine, v1, factor_id),
+                                     C.get_variable_marginal(C.get_variable(engine, v2)), weak=True)
+
+
+def _name(engine, signal):  # get_name_of_variable, :623-629
+    variant = C.get_variant(signal)
+    assert isinstance(variant, C.IndividualMarginal), "Unreachable reached"
+    return C.get_variable_name(C.get_variable(engine, variant.variable_id))
+
+
+class PyMeanFieldProcessor(C.CallbackProcessor):  # SSMMeanFieldInferenceRequestProcessor, :631-696
+    """Values are pairs: NormalMeanPrecision (mean, precision), Gamma (shape, scale), observation (y, -)."""
+
+    def __init__(self):
+        super().__init__(value_dim=2)
+
+    @staticmethod
+    def _product(kind, a, b):
+        if kind == "normal":  # test/runtests.jl:89-95
+            xi = a[0] * a[1] + b[0] * b[1]
+            w = a[1] + b[1]
+            return np.array([(1 / w) * xi, w])
+        return np.array([a[0] + b[0] - 1, (a[1] * b[1]) / (a[1] + b[1])])  # Gamma, :97-99
+
+    def _reduce(self, engine, variant, dependencies):
+        kind = "normal" if C.get_variable_name(C.get_variable(engine, variant.variable_id)) == "x" else "gamma"
+        acc = C.get_value(dependencies[0])
+        for d in dependencies[1:]:
+            acc = self._product(kind, acc, C.get_value(d))
+        return acc
+
+    def compute_individual_marginal(self, engine, variant, signal, dependencies):
+        return self._reduce(engine, variant, dependencies)
+
+    def compute_message_to_factor(self, engine, variant, signal, dependencies):
+        return self._reduce(engine, variant, dependencies)
+
+    def compute_message_to_variable(self, engine, variant, signal, dependencies):
+        assert len(dependencies) == 2
+        names = [_name(engine, d) for d in dependencies]
+        find = lambda nm: names.index(nm) if nm in names else None  # noqa: E731
+        x, y, ssnoise, obsnoise = find("x"), find("y"), find("ssnoise"), find("obsnoise")
+        val = lambda i: C.get_value(dependencies[i])  # noqa: E731
+        g_mean = lambda g: g[0] * g[1]  # noqa: E731  mean(::Gamma) = shape * scale
+        if x is not None and ssnoise is not None:
+            return np.array([val(x)[0], g_mean(val(ssnoise))])
+        if y is not None and obsnoise is not None:
+            return np.array([val(y)[0], g_mean(val(obsnoise))])
+        if y is not None and x is not None:
+            q_out, q_mu = val(y)[0], val(x)
+            theta = 2 / (1 / q_mu[1] + abs(q_out - q_mu[0]) ** 2)
+            return np.array([1.5, theta])
+        if names.count("x") == 2:
+            q_out, q_mu = val(0), val(1)
+            theta = 2 / (1 / q_out[1] + 1 / q_mu[1] + abs(q_out[0] - q_mu[0]) ** 2)
+            return np.array([1.5, theta])
+        raise AssertionError("Unreachable reached")
+
+
+def _wiring(engine):
+    n = engine.store.n_signals()
+    sigs = [C.Signal(engine.store, i) for i in range(n)]
+    return [([d.sid for d in C.get_dependencies(s)], C.get_dependency_props(s),
+             [l.sid for l in C.get_listeners(s)], C.get_listenmask(s)) for s in sigs]
+
+
+def test_python_mean_field_resolver_equals_builtin_wiring(oracle_api):
+    e_py = models.make_ssm_mean_field_model(6, oracle_api, resolver=PyMeanFieldResolver())[0]
+    e_c = models.make_ssm_mean_field_model(6, oracle_api)[0]
+    assert _wiring(e_py) == _wiring(e_c)
+    # every m2v depends weakly on the marginals of the two other variables of its factor; marginals on their m2v (intermediate)
+    eng, x, y, obsnoise, ssnoise, lik, tr = models.make_ssm_mean_field_model(3, oracle_api)
+    m2v = C.get_connection_message_to_variable(eng, obsnoise, lik[1])
+    deps = C.get_dependencies(m2v)
+    assert [C.get_variant(d).variable_id for d in deps] == [x[1], y[1]]
+    assert all(p & cap.NIB_WEAK for p in C.get_dependency_props(m2v))
+    mg = C.get_variable_marginal(C.get_variable(eng, ssnoise))
+    assert len(C.get_dependencies(mg)) == 2 and all(p & cap.NIB_INTERMEDIATE for p in C.get_dependency_props(mg))
+
+
+def test_mean_field_ssm_literal_port_pins_builtin_rule(oracle_api):
+    """Python resolver + Python rules on the sequential schedule == built-in wiring + built-in rule on the level schedule,
+    bit for bit, through the reference's whole call sequence (repeated and merged updates included)."""
+    n, iters = 20, 6
+    data = models.ssm_mean_field_dataset(n)
+    m1 = models.make_ssm_mean_field_model(n, oracle_api, resolver=PyMeanFieldResolver(), processor=PyMeanFieldProcessor())
+    a = models.ssm_mean_field_experiment(m1[0], m1[1], m1[2], m1[3], m1[4], data, iters, schedule="seq")
+    m2 = models.make_ssm_mean_field_model(n, oracle_api)
+    b = models.ssm_mean_field_experiment(m2[0], m2[1], m2[2], m2[3], m2[4], data, iters, schedule="lvl")
+    m3 = models.make_ssm_mean_field_model(n, oracle_api)
+    c = models.ssm_mean_field_experiment(m3[0], m3[1], m3[2], m3[3], m3[4], data, iters, schedule="seq")
+    for k in ("x", "ssnoise", "obsnoise"):
+        assert np.array_equal(a[k], b[k]), k
+        assert np.array_equal(b[k], c[k]), k
+
+
+def test_mean_field_ssm_reference_assertions(backend):  # :783-808: n = 100, 100 VMP iterations
+    n = 100
+    data = models.ssm_mean_field_dataset(n)
+    eng, x, y, obsnoise, ssnoise, lik, tr = models.make_ssm_mean_field_model(n, backend)
+    ans = models.ssm_mean_field_experiment(eng, x, y, obsnoise, ssnoise, data, 100)
+    assert ans["obsnoise"][0] * ans["obsnoise"][1] > 50.0  # mean(answer.obsnoise) > 50.0
+    assert ans["ssnoise"][0] * ans["ssnoise"][1] > 50.0
+    assert np.all(np.isfinite(ans["x"])) and np.all(ans["x"][:, 1] > 0)
+
+
+def test_updates_through_weak_dependencies_repeat(backend):
+    """A weak dependency never blocks: the same marginal can be updated again and again (:759-771) and every call
+    recomputes its messages from the current marginals of the neighbours."""
+    eng, x, y, obsnoise, ssnoise, lik, tr = models.make_ssm_mean_field_model(5, backend)
+    C.set_values([C.get_variable_marginal(C.get_variable(eng, v)) for v in y], np.stack([np.arange(5.0), np.zeros(5)], axis=1))
+    s1 = C.update_marginals(eng, obsnoise)
+    s2 = C.update_marginals(eng, obsnoise)
+    assert s1.updates == s2.updates == 5 + 1  # five m2v(obsnoise, likelihood_i) and the marginal
+    first = C.get_value(C.get_variable_marginal(C.get_variable(eng, obsnoise)))
+    C.update_marginals(eng, x)
+    C.update_marginals(eng, obsnoise)
+    assert not np.array_equal(first, C.get_value(C.get_variable_marginal(C.get_variable(eng, obsnoise))))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("dtype", [cap.F64, cap.F32])
+def test_mean_field_ssm_device_parity(oracle_api, device_api, dtype):
+    n, iters = 64, 12
+    data = models.ssm_mean_field_dataset(n, seed=99)
+    mo = models.make_ssm_mean_field_model(n, oracle_api)
+    md = models.make_ssm_mean_field_model(n, device_api, dtype=dtype)
+    assert _wiring(mo[0]) == _wiring(md[0])
+    want = models.ssm_mean_field_experiment(mo[0], mo[1], mo[2], mo[3], mo[4], data, iters)
+    got = models.ssm_mean_field_experiment(md[0], md[1], md[2], md[3], md[4], data, iters)
+    rtol = 1e-12 if dtype == cap.F64 else 1e-5
+    for k in ("x", "ssnoise", "obsnoise"):
+        np.testing.assert_allclose(got[k], want[k], rtol=rtol, atol=rtol * 1e-3, err_msg=k)
+    # pending flags and dependency nibbles after the run are the oracle's, bit for bit
+    assert models.engine_state(md[0])[0] == models.engine_state(mo[0])[0]
