@@ -23,7 +23,7 @@ NIB_INTERMEDIATE, NIB_WEAK, NIB_COMPUTED, NIB_FRESH = 1, 2, 4, 8
 (FAMILY_GAUSS_CANON, FAMILY_CATEGORICAL, FAMILY_GAUSS_MV, FAMILY_BETA, FAMILY_SUM, FAMILY_GAUSS_MP, FAMILY_GAMMA,
  FAMILY_POINT) = range(8)
 (RULE_NONE, RULE_GAUSS_OBS, RULE_GAUSS_RW, RULE_CAT_TABLE, RULE_POTTS, RULE_HMM_EMIT, RULE_GAUSS_MV_OBS,
- RULE_GAUSS_MV_RW, RULE_BETA_BERNOULLI, RULE_SCALE2, RULE_NORMAL_MEAN_FIELD) = range(11)
+ RULE_GAUSS_MV_RW, RULE_BETA_BERNOULLI, RULE_SCALE2, RULE_NORMAL_MEAN_FIELD, RULE_NORMAL_STRUCTURED) = range(12)
 RESOLVER_NONE, RESOLVER_DEFAULT_BP, RESOLVER_MEAN_FIELD = range(3)
 
 i32, i64, u8p, i32p, i64p, f64p, vp = (C.c_int32, C.c_int64, C.POINTER(C.c_uint8), C.POINTER(C.c_int32),
@@ -50,6 +50,9 @@ _COMMON = {
     "create_signal": (i64, [vp]),
     "add_dependency": (i32, [vp, i64, i64, i32]),
     "resolve_dependencies": (i32, [vp, i32]),
+    "resolve_factor_dependencies": (i32, [vp, i32, i64]),
+    "resolve_variable_dependencies": (i32, [vp, i32, i64]),
+    "set_signal_variant": (i32, [vp, i64, i32, i64, i64]),
     "link_signal": (i32, [vp, i64, i64]),
     "link_signals": (i32, [vp, i64, i64p, i64p]),
     "n_signals": (i64, [vp]),

@@ -23,7 +23,8 @@ unsigned long long g_kernel_launches = 0;
 
 constexpr uint64_t ALL_W = 0x2222222222222222ull, ALL_C = 0x4444444444444444ull, ALL_F = 0x8888888888888888ull,
                    PASS = 0x1111111111111111ull;
-constexpr int ERR_INDEPENDENCE = 1, ERR_LISTENER_DONE = 2, ERR_RULE_ARG = 4;
+constexpr int ERR_INDEPENDENCE = 1, ERR_LISTENER_DONE = 2, ERR_RULE_ARG = 4, ERR_WEAK_BENEATH_DONE = 16;  // 8 = ERR_NO_RULE_KEY
+constexpr uint32_t PROBE_BIT = 0x80000000u;  // breadth-first list entry: the signal is only probed (see bfs_visit)
 constexpr int KEY_COMBINE = 0;  // dense rule keys: 0 = family reduce, 1..n_types = m2v of a factor type, n_types+1 = no rule
 
 
@@ -40,6 +41,7 @@ struct View {
     const int32_t *svar, *sfac;
     const uint8_t* sfam;              // per-signal value family (cxb_set_variable_families), nullptr = the engine family
     uint32_t *done_epoch, *visit_epoch;
+    uint32_t* probe_epoch;            // graphs with weak dependencies only (else nullptr): probe visits of this level
     uint32_t* front_epoch;            // == lvl_epoch: member of the current level's frontier
     uint32_t* front;                  // frontier buffer, partitioned by rule key
     const uint32_t* key_base;         // [n_keys] start of each key's partition
@@ -128,24 +130,41 @@ __device__ __forceinline__ void frontier_push(const View& e, uint32_t d, uint32_
 // visit every dependency (f(dep) = is_pending), push the pending ones to the frontier, descend through non-pending
 // *intermediate* ones. `done` signals are neither reported nor descended through (A.5). The list length lives on
 // the device (written by the previous step), so consecutive steps need no host round trip.
+// The dependencies of one list entry. A level never descends through a signal already computed in this request (`done`,
+// A.5) — the reference does when a later round reaches it again, and anything pending it finds there is computed and
+// the done signal recomputed on the retry. With strong dependencies that cannot find anything (a done signal consumed
+// fresh dependencies; a recomputed dependency is caught by ERR_LISTENER_DONE). A WEAK dependency never blocks, so it
+// can be pending underneath a done signal: graphs that have weak dependencies are therefore PROBED through their done
+// signals (same descent rule, nothing is pushed), and a pending weak dependency found there refuses the request as
+// order-dependent instead of silently leaving it for the final phase.
+template <class Push>
+__device__ __forceinline__ void bfs_visit(const View& e, uint32_t entry, uint32_t lvl_epoch, uint32_t req_epoch, int use_done, Push&& push_out) {
+    const uint32_t s = entry & ~PROBE_BIT;
+    const bool probing = (entry & PROBE_BIT) != 0;
+    const uint32_t off = e.dep_off[s], nd = e.dep_off[s + 1] - off, noff = e.nib_off[s];
+    for (uint32_t k = 0; k < nd; ++k) {
+        const uint32_t d = e.dep_ids[off + k];
+        const bool done = use_done && e.done_epoch[d] == req_epoch;
+        if (done && !e.probe_epoch) continue;
+        const uint32_t nibble = (uint32_t)(e.nib[noff + (k >> 4)] >> ((k & 15) << 2)) & 0xF;
+        if (done || probing) {
+            if (!done && pending_eval(e, d)) {
+                if (nibble & CXB_NIB_WEAK) atomicOr(e.err_flag, ERR_WEAK_BENEATH_DONE);
+            } else if ((nibble & CXB_NIB_INTERMEDIATE) && atomicExch(&e.probe_epoch[d], lvl_epoch) != lvl_epoch) {
+                push_out(d | PROBE_BIT);
+            }
+        } else if (pending_eval(e, d)) {
+            frontier_push(e, d, lvl_epoch);
+        } else if ((nibble & CXB_NIB_INTERMEDIATE) && atomicExch(&e.visit_epoch[d], lvl_epoch) != lvl_epoch) {
+            push_out(d);
+        }
+    }
+}
 __global__ void k_bfs(View e, const uint32_t* in, const uint32_t* n_in_ptr, uint32_t* out, uint32_t* n_out, uint32_t lvl_epoch,
                       uint32_t req_epoch, int use_done) {
     const uint32_t n_in = *n_in_ptr;
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_in; i += gridDim.x * blockDim.x) {
-        uint32_t s = in[i];
-        uint32_t off = e.dep_off[s], nd = e.dep_off[s + 1] - off, noff = e.nib_off[s];
-        for (uint32_t k = 0; k < nd; ++k) {
-            uint32_t d = e.dep_ids[off + k];
-            if (use_done && e.done_epoch[d] == req_epoch) continue;
-            if (pending_eval(e, d)) {
-                frontier_push(e, d, lvl_epoch);
-            } else {
-                uint32_t nibble = (uint32_t)(e.nib[noff + (k >> 4)] >> ((k & 15) << 2)) & 0xF;
-                if ((nibble & CXB_NIB_INTERMEDIATE) && atomicExch(&e.visit_epoch[d], lvl_epoch) != lvl_epoch)
-                    out[atomicAdd(n_out, 1u)] = d;
-            }
-        }
-    }
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_in; i += gridDim.x * blockDim.x)
+        bfs_visit(e, in[i], lvl_epoch, req_epoch, use_done, [&](uint32_t x) { out[atomicAdd(n_out, 1u)] = x; });
 }
 
 // final phase candidates (:610-628): the requested marginals (i < n), their linked signals (flat entries after)
@@ -274,7 +293,7 @@ __device__ __forceinline__ void rule_small_one(const View& e, T* __restrict__ va
                                                const T* __restrict__ fparam, T default_param) {
     const int dim = e.dim;
     uint32_t off = e.dep_off[s], nd = e.dep_off[s + 1] - off;
-    T acc[4] = {0, 0, 0, 0};
+    T acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     if (nd == 0) {
         atomicOr(e.err_flag, ERR_RULE_ARG);
         return;
@@ -364,6 +383,52 @@ __device__ __forceinline__ void rule_small_one(const View& e, T* __restrict__ va
                     const T dm = vmp_mean<T>(fa, a) - vmp_mean<T>(fb, b);
                     acc[0] = T(1.5);
                     acc[1] = T(2) / (vmp_var<T>(fa, a) + vmp_var<T>(fb, b) + dm * dm);
+                } else {
+                    atomicOr(e.err_flag, ERR_RULE_ARG);
+                    return;
+                }
+                break;
+            }
+            case CXB_RULE_NORMAL_STRUCTURED: {  // test/inference_engine_tests.jl:942-973, 1008-1028
+                const uint32_t d0 = e.dep_ids[off];
+                const T* v0 = val + (size_t)d0 * dim;
+                if (e.kind[s] == CXB_KIND_JOINT) {  // (m2f a, m2f b, marginal of the precision) -> MvNormalMeanPrecision
+                    if (nd != 3 || dim < 6) {
+                        atomicOr(e.err_flag, ERR_RULE_ARG);
+                        return;
+                    }
+                    const T* v1 = val + (size_t)e.dep_ids[off + 1] * dim;
+                    const T* g = val + (size_t)e.dep_ids[off + 2] * dim;
+                    const T xi_a = v0[1] * v0[0], w_a = v0[1], xi_b = v1[1] * v1[0], w_b = v1[1], w = g[0] * g[1];
+                    const T W11 = w_a + w, W12 = -w, W21 = -w, W22 = w_b + w;
+                    const T det = W11 * W22 - W12 * W21;
+                    acc[0] = (W22 * xi_a - W12 * xi_b) / det;
+                    acc[1] = (W11 * xi_b - W21 * xi_a) / det;
+                    acc[2] = W11;
+                    acc[3] = W12;
+                    acc[4] = W21;
+                    acc[5] = W22;
+                    for (int k = 6; k < dim; ++k) acc[k] = T(0);
+                } else if (nd == 2) {  // (m2f of the other state, marginal of the precision), in either order
+                    const uint32_t d1 = e.dep_ids[off + 1];
+                    const T* v1 = val + (size_t)d1 * dim;
+                    const bool first_is_msg = e.kind[d0] == CXB_KIND_M2F;
+                    if (first_is_msg == (e.kind[d1] == CXB_KIND_M2F)) {
+                        atomicOr(e.err_flag, ERR_RULE_ARG);
+                        return;
+                    }
+                    const T* m = first_is_msg ? v0 : v1;
+                    const T* g = first_is_msg ? v1 : v0;
+                    acc[0] = m[0];
+                    acc[1] = T(1) / (T(1) / m[1] + T(1) / (g[0] * g[1]));
+                    for (int k = 2; k < dim; ++k) acc[k] = T(0);
+                } else if (nd == 1 && e.kind[d0] == CXB_KIND_JOINT && dim >= 6) {  // (JointMarginal) -> Gamma
+                    const T det = v0[2] * v0[5] - v0[3] * v0[4];
+                    const T V11 = v0[5] / det, V12 = -v0[3] / det, V21 = -v0[4] / det, V22 = v0[2] / det;
+                    const T dm = v0[0] - v0[1];
+                    acc[0] = T(1.5);
+                    acc[1] = T(2) / (V11 - V12 - V21 + V22 + dm * dm);
+                    for (int k = 2; k < dim; ++k) acc[k] = T(0);
                 } else {
                     atomicOr(e.err_flag, ERR_RULE_ARG);
                     return;
@@ -570,21 +635,8 @@ __global__ void __launch_bounds__(1024) k_update_resident(View e, T* __restrict_
             __syncthreads();
             const uint32_t* in = which ? a.list_b : a.list_a;
             uint32_t* out = which ? a.list_a : a.list_b;
-            for (uint32_t i = tid; i < n_in; i += NT) {
-                const uint32_t s = in[i];
-                const uint32_t off = e.dep_off[s], nd = e.dep_off[s + 1] - off, noff = e.nib_off[s];
-                for (uint32_t k = 0; k < nd; ++k) {
-                    const uint32_t d = e.dep_ids[off + k];
-                    if (e.done_epoch[d] == a.req_epoch) continue;
-                    if (pending_eval(e, d)) {
-                        frontier_push(e, d, lvl);
-                    } else {
-                        const uint32_t nibble = (uint32_t)(e.nib[noff + (k >> 4)] >> ((k & 15) << 2)) & 0xF;
-                        if ((nibble & CXB_NIB_INTERMEDIATE) && atomicExch(&e.visit_epoch[d], lvl) != lvl)
-                            out[atomicAdd(&s_cnt[which ^ 1], 1u)] = d;
-                    }
-                }
-            }
+            for (uint32_t i = tid; i < n_in; i += NT)
+                bfs_visit(e, in[i], lvl, a.req_epoch, 1, [&](uint32_t x) { out[atomicAdd(&s_cnt[which ^ 1], 1u)] = x; });
             __syncthreads();
             which ^= 1;
         }
@@ -756,7 +808,8 @@ struct DeviceEngine {
     size_t n_uploaded = 0;
 
     // device state
-    DBuf<uint32_t> d_dep_off, d_dep_ids, d_nib_off, d_lis_off, d_lis_ids, d_lis_slot, d_done, d_visit;
+    DBuf<uint32_t> d_dep_off, d_dep_ids, d_nib_off, d_lis_off, d_lis_ids, d_lis_slot, d_done, d_visit, d_probe;
+    bool has_weak = false;  // any weak dependency in the graph: levels probe through done signals (bfs_visit)
     DBuf<uint64_t> d_nib;
     DBuf<uint8_t> d_lis_listen, d_props, d_kind, d_rkey;
     DBuf<uint32_t> d_front_epoch, d_key_base;
@@ -847,6 +900,7 @@ struct DeviceEngine {
         v.sfam = has_var_family ? d_sfam.p : nullptr;
         v.done_epoch = d_done.p;
         v.visit_epoch = d_visit.p;
+        v.probe_epoch = has_weak ? d_probe.p : nullptr;
         v.front_epoch = d_front_epoch.p;
         v.front = d_front.p;
         v.key_base = d_key_base.p;
@@ -914,8 +968,8 @@ struct DeviceEngine {
             sfac[s] = (int32_t)g.sfac[s];
             if (k == CXB_KIND_M2F || k == CXB_KIND_PRODUCT || k == CXB_KIND_MARGINAL)
                 rkey[s] = KEY_COMBINE;
-            else if (k == CXB_KIND_M2V)
-                rkey[s] = (uint8_t)key_of[g.ftype[g.sfac[s]]];
+            else if (k == CXB_KIND_M2V || (k == CXB_KIND_JOINT && g.sfac[s] >= 0 && g.sfac[s] < g.n_ids && g.is_factor[g.sfac[s]]))
+                rkey[s] = (uint8_t)key_of[g.ftype[g.sfac[s]]];  // a JointMarginal is computed by its factor's rule
             else
                 rkey[s] = (uint8_t)key_no_rule();
         }
@@ -1026,8 +1080,14 @@ struct DeviceEngine {
             CXB_CUDA(d_done.reserve(Np));
             CXB_CUDA(d_visit.reserve(Np));
             CXB_CUDA(d_front_epoch.reserve(Np));
-            CXB_CUDA(d_list_a.reserve(Np));
-            CXB_CUDA(d_list_b.reserve(Np));
+            has_weak = false;
+            for (uint8_t fl : g.e_flags) has_weak = has_weak || (fl & CXB_NIB_WEAK);
+            if (has_weak) {
+                CXB_CUDA(d_probe.reserve(Np));
+                CXB_CUDA(cudaMemsetAsync(d_probe.p, 0, Np * 4, stream));
+            }
+            CXB_CUDA(d_list_a.reserve(has_weak ? 2 * Np : Np));  // a signal enters a level's lists once, and once more as a probe
+            CXB_CUDA(d_list_b.reserve(has_weak ? 2 * Np : Np));
             CXB_CUDA(d_front.reserve(Np));
             CXB_CUDA(cudaMemsetAsync(d_done.p, 0, Np * 4, stream));
             CXB_CUDA(cudaMemsetAsync(d_visit.p, 0, Np * 4, stream));
@@ -1056,8 +1116,8 @@ struct DeviceEngine {
         T* val = (T*)d_val.p;
         const int nk = n_keys();
         bool categorical = family == CXB_FAMILY_CATEGORICAL;
-        if (!categorical && dim > 4) {
-            err = "value_dim > 4 is only supported for the categorical family";
+        if (!categorical && dim > 8) {
+            err = "value_dim > 8 is only supported for the categorical family";
             return CXB_ERR_BAD_ARG;
         }
         for (int k = 0; k < nk; ++k) {
@@ -1192,6 +1252,9 @@ struct DeviceEngine {
         }
         if (f & ERR_INDEPENDENCE)
             err = "level-synchronous schedule out of contract: frontier member depends on another member";
+        else if (f & ERR_WEAK_BENEATH_DONE)
+            err = "level-synchronous schedule out of contract: a pending weak dependency lies beneath a signal already computed in "
+                  "this request (the reference would recompute that signal: order-dependent)";
         else
             err = "level-synchronous schedule out of contract: a dependency is recomputed after its listener within one "
                   "request (order-dependent in the reference)";
@@ -1321,7 +1384,7 @@ struct DeviceEngine {
     bool resident_ok() {
         if (const char* e = getenv("CXB_ENGINE_RESIDENT"))
             if (!atoi(e)) return false;
-        const bool small_family = family != CXB_FAMILY_CATEGORICAL && dim <= 4;
+        const bool small_family = family != CXB_FAMILY_CATEGORICAL && dim <= 8;
         const bool small_categorical = family == CXB_FAMILY_CATEGORICAL && dim <= 64;
         return !trace_on && (small_family || small_categorical) && g.n_sig() <= 65536;
     }
@@ -1709,6 +1772,37 @@ int32_t cxb_resolve_dependencies(cxb_engine* h, int32_t resolver) {
     }
     e->structure_dirty = true;
     return e->g.resolve(resolver, e->err);
+}
+int32_t cxb_resolve_factor_dependencies(cxb_engine* h, int32_t resolver, int64_t factor_id) {
+    DeviceEngine* e = E(h);
+    if (int32_t st = e->sync_host()) return st;
+    e->structure_dirty = true;
+    return e->g.resolve_one(resolver, factor_id, true, e->err);
+}
+int32_t cxb_resolve_variable_dependencies(cxb_engine* h, int32_t resolver, int64_t variable_id) {
+    DeviceEngine* e = E(h);
+    if (int32_t st = e->sync_host()) return st;
+    e->structure_dirty = true;
+    return e->g.resolve_one(resolver, variable_id, false, e->err);
+}
+int32_t cxb_set_signal_variant(cxb_engine* h, int64_t s, int32_t kind, int64_t variable_id, int64_t factor_id) {
+    DeviceEngine* e = E(h);
+    CHECK_SIG(h, s);
+    if (kind < CXB_KIND_UNSPECIFIED || kind > CXB_KIND_JOINT) {
+        e->err = "set_signal_variant: unknown kind";
+        return CXB_ERR_BAD_ARG;
+    }
+    if (variable_id >= e->g.n_ids || factor_id >= e->g.n_ids || (variable_id >= 0 && e->g.is_factor[variable_id]) ||
+        (factor_id >= 0 && !e->g.is_factor[factor_id])) {
+        e->err = "set_signal_variant: bad variable / factor id";
+        return CXB_ERR_BAD_ARG;
+    }
+    if (int32_t st = e->sync_host()) return st;
+    e->g.kind[s] = (uint8_t)kind;
+    e->g.svar[s] = variable_id;
+    e->g.sfac[s] = factor_id;
+    e->structure_dirty = true;
+    return CXB_OK;
 }
 int32_t cxb_link_signal(cxb_engine* h, int64_t v, int64_t s) {
     DeviceEngine* e = E(h);

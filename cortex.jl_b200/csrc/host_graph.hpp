@@ -248,6 +248,24 @@ struct HostGraph {
         for (int64_t i = adj_off[v]; i < adj_off[v + 1]; ++i)
             add_dependency(marg_of[v], m2v_of_conn(adj_conn[i]), false, true, true, true);
     }
+    // one resolve_factor_dependencies! / resolve_variable_dependencies! call of a built-in resolver (user resolvers delegate
+    // per id, test/inference_engine_tests.jl:813-815)
+    int32_t resolve_one(int32_t resolver, int64_t id, bool factor, std::string& err) {
+        if (resolver != CXB_RESOLVER_DEFAULT_BP && resolver != CXB_RESOLVER_MEAN_FIELD) {
+            err = "unknown resolver";
+            return CXB_ERR_BAD_ARG;
+        }
+        if (id < 0 || id >= n_ids || (is_factor[id] != 0) != factor) {
+            err = factor ? "resolve_factor_dependencies: not a factor id" : "resolve_variable_dependencies: not a variable id";
+            return CXB_ERR_BAD_ARG;
+        }
+        const bool bp = resolver == CXB_RESOLVER_DEFAULT_BP;
+        if (factor)
+            bp ? resolve_factor_default(id) : resolve_factor_mean_field(id);
+        else
+            bp ? resolve_variable_default(id) : resolve_variable_mean_field(id);
+        return CXB_OK;
+    }
     int32_t resolve(int32_t resolver, std::string& err) {  // :5-15 factors first, then variables
         if (resolver == CXB_RESOLVER_NONE) return CXB_OK;
         if (resolver != CXB_RESOLVER_DEFAULT_BP && resolver != CXB_RESOLVER_MEAN_FIELD) {

@@ -32,10 +32,14 @@ class AbstractDependencyResolver:
     resolver_kind = capi.RESOLVER_NONE
 
     def resolve_factor_dependencies(self, engine, factor_id):  # src/dependencies.jl:17
-        raise NotImplementedError
+        if self.resolver_kind == capi.RESOLVER_NONE:
+            raise NotImplementedError
+        engine.store.check(engine.api.resolve_factor_dependencies(engine.store.h, self.resolver_kind, int(factor_id)))
 
     def resolve_variable_dependencies(self, engine, variable_id):  # src/dependencies.jl:33
-        raise NotImplementedError
+        if self.resolver_kind == capi.RESOLVER_NONE:
+            raise NotImplementedError
+        engine.store.check(engine.api.resolve_variable_dependencies(engine.store.h, self.resolver_kind, int(variable_id)))
 
     def resolve_dependencies(self, engine):
         """resolve_dependencies!(resolver, engine), src/dependencies.jl:5-15: every factor, then every variable."""
@@ -325,6 +329,11 @@ def get_connected_variable_ids(engine: InferenceEngine, factor_id: int):
 
 def get_connected_factor_ids(engine: InferenceEngine, variable_id: int):
     return backend_get_connected_factor_ids(engine.model_engine, variable_id)
+
+
+def create_inference_signal(engine: InferenceEngine) -> Signal:
+    """create_inference_signal(), src/inference_signal.jl:140-142 (signals live in the engine's store here)."""
+    return engine.store.Signal()
 
 
 def set_variable_families(engine: InferenceEngine, variable_ids, families) -> None:

@@ -99,6 +99,7 @@ class SignalStore:
             raise CortexError(st, "cxb_create failed (is a CUDA device present? there is no CPU fallback)")
         self.h = h
         self._neighbours = {}
+        self._joint_vars = {}
 
     def __del__(self):
         try:
@@ -307,8 +308,27 @@ def get_variant(signal: Signal):
     if kind == capi.KIND_PRODUCT:
         return ProductOfMessages(var, (r0, r1), tuple(st._neighbours.get(var, ())))
     if kind == capi.KIND_JOINT:
-        return JointMarginal(fac)
+        return JointMarginal(fac, tuple(st._joint_vars.get(signal.sid, ())))
     return Unspecified()
+
+
+def set_variant(signal: Signal, variant) -> None:
+    """set_variant!(signal, variant), src/signal.jl:185-192."""
+    st = signal.store
+    if isinstance(variant, MessageToFactor):
+        args = (capi.KIND_M2F, variant.variable_id, variant.factor_id)
+    elif isinstance(variant, MessageToVariable):
+        args = (capi.KIND_M2V, variant.variable_id, variant.factor_id)
+    elif isinstance(variant, IndividualMarginal):
+        args = (capi.KIND_MARGINAL, variant.variable_id, -1)
+    elif isinstance(variant, JointMarginal):
+        args = (capi.KIND_JOINT, -1, variant.factor_id)
+        st._joint_vars[signal.sid] = tuple(variant.variable_ids)
+    elif isinstance(variant, Unspecified):
+        args = (capi.KIND_UNSPECIFIED, -1, -1)
+    else:
+        raise TypeError(f"set_variant!: unsupported variant {variant!r}")
+    st.check(st.api.set_signal_variant(st.h, signal.sid, *args))
 
 
 def isa_variant(signal: Signal, T) -> bool:

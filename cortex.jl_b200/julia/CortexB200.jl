@@ -20,9 +20,10 @@ const LIB = get(ENV, "CORTEX_B200_LIB", "libcortex_b200.so")
 const OK, ERR_NOT_PENDING, ERR_NO_RULE, ERR_OUT_OF_CONTRACT, ERR_BAD_ARG, ERR_UNSUPPORTED_ENGINE, ERR_CUDA, ERR_STATE = 0:7
 const F32, F64 = 0, 1
 const KIND_UNSPECIFIED, KIND_M2F, KIND_M2V, KIND_PRODUCT, KIND_MARGINAL, KIND_JOINT = 0:5
-const FAMILY_GAUSS_CANON, FAMILY_CATEGORICAL, FAMILY_GAUSS_MV, FAMILY_BETA, FAMILY_SUM = 0:4
+const FAMILY_GAUSS_CANON, FAMILY_CATEGORICAL, FAMILY_GAUSS_MV, FAMILY_BETA, FAMILY_SUM,
+      FAMILY_GAUSS_MP, FAMILY_GAMMA, FAMILY_POINT = 0:7
 const RULE_NONE, RULE_GAUSS_OBS, RULE_GAUSS_RW, RULE_CAT_TABLE, RULE_POTTS, RULE_HMM_EMIT,
-      RULE_GAUSS_MV_OBS, RULE_GAUSS_MV_RW, RULE_BETA_BERNOULLI, RULE_SCALE2 = 0:9
+      RULE_GAUSS_MV_OBS, RULE_GAUSS_MV_RW, RULE_BETA_BERNOULLI, RULE_SCALE2, RULE_NORMAL_MEAN_FIELD = 0:10
 const RESOLVER_NONE, RESOLVER_DEFAULT_BP, RESOLVER_MEAN_FIELD = 0:2
 
 struct UpdateStats
@@ -102,6 +103,14 @@ message_to_variable_id(e::B200InferenceEngine, v::Int, f::Int) =
     ccall((:cxb_signal_id, LIB), Int64, (Ptr{Cvoid}, Int32, Int64, Int64), e.handle, KIND_M2V, v - 1, f - 1)
 message_to_factor_id(e::B200InferenceEngine, v::Int, f::Int) =
     ccall((:cxb_signal_id, LIB), Int64, (Ptr{Cvoid}, Int32, Int64, Int64), e.handle, KIND_M2F, v - 1, f - 1)
+
+# value type of a variable's signals in a model that mixes types (VMP: NormalMeanPrecision / Gamma / observed Float64,
+# test/runtests.jl:52-99 — in Julia the type travels with the value, the device needs it declared once)
+function set_variable_families!(e::B200InferenceEngine, variable_ids::AbstractVector{<:Integer}, families::AbstractVector{<:Integer})
+    ids = Int64[v - 1 for v in variable_ids]; fam = convert(Vector{Int32}, families)
+    check(e.handle, ccall((:cxb_set_variable_families, LIB), Int32, (Ptr{Cvoid}, Int64, Ptr{Int64}, Ptr{Int32}),
+                          e.handle, length(ids), ids, fam))
+end
 
 # ---- data in / out: set_value! (src/signal.jl:232), get_value (:171) -----------------------------------------------
 function set_values!(e::B200InferenceEngine, signal_ids::Vector{Int64}, values::Matrix{Float64})   # values: dim x n

@@ -106,7 +106,15 @@ enum {
      *   one of them Gamma (the precision) -> NormalMeanPrecision(mean(other), mean(precision))        (:666-676)
      *   none of them Gamma (target = precision) -> Gamma(1.5, 2 / (var(a) + var(b) + (mean(a) - mean(b))^2)) (:678-692)
      * mean / var by the dependency's family (POINT: value, 0). */
-    CXB_RULE_NORMAL_MEAN_FIELD = 10
+    CXB_RULE_NORMAL_MEAN_FIELD = 10,
+    /* Normal node with the two states of a transition kept JOINT (structured VMP), the :transition branch of
+     * test/inference_engine_tests.jl:942-973, 1008-1028. One registration covers every signal of the factor:
+     *   JointMarginal <- (m2f a, m2f b, marginal of the precision):  W = [Wa+w  -w; -w  Wb+w], mu = W^-1 [xi_a; xi_b],
+     *       value = (mu1, mu2, W11, W12, W21, W22) = MvNormalMeanPrecision, value_dim >= 6            (:942-973)
+     *   m2v <- (m2f of the other state, marginal of the precision): NormalMeanPrecision(mean, 1/(var + 1/w)) (:1013-1020)
+     *   m2v <- (JointMarginal): Gamma(1.5, 2 / (V11 - V12 - V21 + V22 + (mu1 - mu2)^2)), V = W^-1      (:1021-1026)
+     * with w = mean of the Gamma marginal. */
+    CXB_RULE_NORMAL_STRUCTURED = 11
 };
 
 /* ---- dependency resolvers: src/dependencies.jl -------------------------------------------- */
@@ -156,10 +164,18 @@ int32_t cxb_set_variable_families(cxb_engine* h, int64_t n, const int64_t* varia
 
 /* create_inference_signal(), src/inference_signal.jl:140-142 -> sid */
 int64_t cxb_create_signal(cxb_engine* h);
+/* set_variant!(signal, variant), src/signal.jl:185-192, for signals made by cxb_create_signal: kind = CXB_KIND_*;
+ * JointMarginal(factor_id, variable_ids): pass the factor (its registered rule computes the signal) and -1 as variable */
+int32_t cxb_set_signal_variant(cxb_engine* h, int64_t signal, int32_t kind, int64_t variable_id, int64_t factor_id);
 /* add_dependency!(signal, dependency; weak, listen, check_computed, intermediate), src/signal.jl:286-337 */
 int32_t cxb_add_dependency(cxb_engine* h, int64_t signal, int64_t dependency, int32_t flags);
 /* resolve_dependencies!(resolver, engine), src/dependencies.jl:5-15 */
 int32_t cxb_resolve_dependencies(cxb_engine* h, int32_t resolver);
+/* one call of resolve_factor_dependencies!(resolver, engine, factor_id) / resolve_variable_dependencies!(resolver,
+ * engine, variable_id), src/dependencies.jl:17-126: lets a user resolver delegate to a built-in one per id, as
+ * test/inference_engine_tests.jl:813-815 does */
+int32_t cxb_resolve_factor_dependencies(cxb_engine* h, int32_t resolver, int64_t factor_id);
+int32_t cxb_resolve_variable_dependencies(cxb_engine* h, int32_t resolver, int64_t variable_id);
 /* link_signal_to_variable!(variable, signal), src/model_engine.jl:80-83 */
 int32_t cxb_link_signal(cxb_engine* h, int64_t variable_id, int64_t signal);
 /* bulk form of the above (protocol B links every pairwise m2f: 4e7 signals at config-5 size) */

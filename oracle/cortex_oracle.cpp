@@ -335,6 +335,52 @@ struct Oracle {
                 err = "NORMAL_MEAN_FIELD: two Gamma dependencies";
                 return CXB_ERR_NO_RULE;
             }
+            case CXB_RULE_NORMAL_STRUCTURED: {  // test/inference_engine_tests.jl:942-973, 1008-1028
+                for (int k = 0; k < dim; ++k) out[k] = 0.0;
+                if (s.kind == CXB_KIND_JOINT) {  // :942-973
+                    if (s.ndeps != 3 || dim < 6) {
+                        err = "NORMAL_STRUCTURED: a joint marginal expects (m2f, m2f, marginal) and value_dim >= 6";
+                        return CXB_ERR_NO_RULE;
+                    }
+                    const double *m1 = value(s.deps[0]), *m2 = value(s.deps[1]), *g = value(s.deps[2]);
+                    double xi_out = m1[1] * m1[0], W_out = m1[1];
+                    double xi_mu = m2[1] * m2[0], W_mu = m2[1];
+                    double W_bar = g[0] * g[1];
+                    double W11 = W_out + W_bar, W12 = -W_bar, W21 = -W_bar, W22 = W_mu + W_bar;
+                    double det = W11 * W22 - W12 * W21;  // mu = inv(W) * [xi_out; xi_mu], closed-form 2x2 inverse
+                    out[0] = (W22 * xi_out - W12 * xi_mu) / det;
+                    out[1] = (W11 * xi_mu - W21 * xi_out) / det;
+                    out[2] = W11;
+                    out[3] = W12;
+                    out[4] = W21;
+                    out[5] = W22;
+                    return CXB_OK;
+                }
+                if (s.ndeps == 2) {  // :1013-1020
+                    const Sig &d0 = sig[s.deps[0]], &d1 = sig[s.deps[1]];
+                    bool first_is_msg = d0.kind == CXB_KIND_M2F;
+                    if (first_is_msg == (d1.kind == CXB_KIND_M2F)) {
+                        err = "NORMAL_STRUCTURED: expects one message and one marginal";
+                        return CXB_ERR_NO_RULE;
+                    }
+                    const double* m = value(s.deps[first_is_msg ? 0 : 1]);
+                    const double* g = value(s.deps[first_is_msg ? 1 : 0]);
+                    out[0] = m[0];
+                    out[1] = 1 / (1 / m[1] + 1 / (g[0] * g[1]));
+                    return CXB_OK;
+                }
+                if (s.ndeps == 1 && sig[s.deps[0]].kind == CXB_KIND_JOINT && dim >= 6) {  // :1021-1026
+                    const double* j = value(s.deps[0]);
+                    double det = j[2] * j[5] - j[3] * j[4];
+                    double V11 = j[5] / det, V12 = -j[3] / det, V21 = -j[4] / det, V22 = j[2] / det;
+                    double dm = j[0] - j[1];
+                    out[0] = 1.5;
+                    out[1] = 2 / (V11 - V12 - V21 + V22 + dm * dm);
+                    return CXB_OK;
+                }
+                err = "NORMAL_STRUCTURED: unreachable reached";
+                return CXB_ERR_NO_RULE;
+            }
             case CXB_RULE_CAT_TABLE:
             case CXB_RULE_POTTS: {
                 if (s.ndeps != 1) {
@@ -394,9 +440,12 @@ struct Oracle {
             case CXB_KIND_MARGINAL:
             case CXB_KIND_PRODUCT:
                 return combine(s, out);
-            case CXB_KIND_JOINT:
+            case CXB_KIND_JOINT: {  // compute_joint_marginal!: the rule registered for the factor computes it
+                const Rule* r = s.fac >= 0 && s.fac < n_ids && is_factor[s.fac] ? rule_of_factor(s.fac) : nullptr;
+                if (r && r->kind == CXB_RULE_NORMAL_STRUCTURED) return rule_m2v(s, out);
                 err = "The function `compute_joint_marginal!` is not implemented";
                 return CXB_ERR_NO_RULE;
+            }
             default:
                 if (free_strategy) return combine(s, out);
                 err = "Unprocessed signal variant";  // :506
@@ -514,6 +563,22 @@ struct Oracle {
     }
     void resolve_variable_mean_field(int64_t v) {
         for (int64_t f : nbr[v]) add_dependency(marg_of[v], m2v(v, f), false, true, true, true);
+    }
+    int32_t resolve_one(int32_t resolver, int64_t id, bool factor) {
+        if (resolver != CXB_RESOLVER_DEFAULT_BP && resolver != CXB_RESOLVER_MEAN_FIELD) {
+            err = "unknown resolver";
+            return CXB_ERR_BAD_ARG;
+        }
+        if (id < 0 || id >= n_ids || (is_factor[id] != 0) != factor) {
+            err = factor ? "resolve_factor_dependencies: not a factor id" : "resolve_variable_dependencies: not a variable id";
+            return CXB_ERR_BAD_ARG;
+        }
+        const bool bp = resolver == CXB_RESOLVER_DEFAULT_BP;
+        if (factor)
+            bp ? resolve_factor_default(id) : resolve_factor_mean_field(id);
+        else
+            bp ? resolve_variable_default(id) : resolve_variable_mean_field(id);
+        return CXB_OK;
     }
     int32_t resolve(int32_t resolver) {  // src/dependencies.jl:5-15 — factors first, then variables
         if (resolver == CXB_RESOLVER_NONE) return CXB_OK;
@@ -671,28 +736,58 @@ struct Oracle {
                 }
                 return false;
             };
-            // DFS identical to process_dependencies! except: never descend through `done`
+            // DFS identical to process_dependencies! except: never descend through `done`. The reference does descend
+            // (a later round reaches the signal again), computes whatever is pending underneath and recomputes the done
+            // signal on the retry. With strong dependencies nothing can be pending there (the done signal consumed
+            // fresh dependencies; a dependency recomputed later is caught by the listener check below); a WEAK dependency
+            // never blocks, so it can: `probe` follows the same descent rule through done signals without computing
+            // anything, and a pending weak dependency found there makes the request order-dependent -> refused.
+            bool weak_beneath_done = false;
+            std::vector<uint8_t> probed(sig.size(), 0);
             struct Rec {
                 Oracle* o;
                 std::vector<uint8_t>& done;
+                std::vector<uint8_t>& probed;
+                bool& weak_beneath_done;
                 decltype(visit)& f;
+                void probe(int64_t sid) {
+                    if (probed[sid]) return;
+                    probed[sid] = 1;
+                    for (int64_t i = 0; i < o->sig[sid].ndeps; ++i) {
+                        int64_t d = o->sig[sid].deps[i];
+                        if (!done[d] && o->is_pending(d)) {
+                            if (nib(o->sig[sid], i, MASK_W)) weak_beneath_done = true;
+                        } else if (nib(o->sig[sid], i, MASK_I)) {
+                            probe(d);
+                        }
+                    }
+                }
                 bool go(int64_t sid) {
                     bool any = false;
                     for (int64_t i = 0; i < o->sig[sid].ndeps; ++i) {
                         int64_t d = o->sig[sid].deps[i];
                         bool processed = f(d);
-                        if (!processed && nib(o->sig[sid], i, MASK_I) && !done[d]) {
-                            bool ip = go(d);
-                            if (ip) processed = f(d);
-                            any = any || ip;
+                        if (!processed && nib(o->sig[sid], i, MASK_I)) {
+                            if (done[d]) {
+                                probe(d);
+                            } else {
+                                bool ip = go(d);
+                                if (ip) processed = f(d);
+                                any = any || ip;
+                            }
                         }
                         any = any || processed;
                     }
                     return any;
                 }
-            } rec{this, done, visit};
+            } rec{this, done, probed, weak_beneath_done, visit};
             for (int64_t i = 0; i < n; ++i)
                 if (!ready[i]) rec.go(req_marg[i]);
+            if (weak_beneath_done) {
+                err = "level-synchronous schedule out of contract: a pending weak dependency lies beneath a signal already computed "
+                      "in this request (the reference would recompute that signal: order-dependent)";
+                return CXB_ERR_OUT_OF_CONTRACT;
+            }
             if (F.empty()) break;
             // contract: inside the loop phase no signal may be computed AFTER one of its listeners was
             // (then the sequential reference order is Gauss-Seidel and values are order-dependent)
@@ -700,7 +795,8 @@ struct Oracle {
                 for (int64_t l : sig[s].listeners)
                     if (done[l]) {
                         err = "level-synchronous schedule out of contract: a dependency is recomputed after its listener "
-                              "within one request (order-dependent in the reference)";
+                              "within one request (order-dependent in the reference): signal " +
+                              std::to_string(s) + " after its listener " + std::to_string(l);
                         return CXB_ERR_OUT_OF_CONTRACT;
                     }
             st = run_level(F, level);
@@ -863,6 +959,21 @@ int32_t cxo_add_dependency(void* h, int64_t s, int64_t d, int32_t flags) {
     return CXB_OK;
 }
 int32_t cxo_resolve_dependencies(void* h, int32_t resolver) { return O(h)->resolve(resolver); }
+int32_t cxo_resolve_factor_dependencies(void* h, int32_t resolver, int64_t f) { return O(h)->resolve_one(resolver, f, true); }
+int32_t cxo_resolve_variable_dependencies(void* h, int32_t resolver, int64_t v) { return O(h)->resolve_one(resolver, v, false); }
+int32_t cxo_set_signal_variant(void* h, int64_t s, int32_t kind, int64_t variable_id, int64_t factor_id) {
+    Oracle* o = O(h);
+    if (s < 0 || s >= (int64_t)o->sig.size() || kind < CXB_KIND_UNSPECIFIED || kind > CXB_KIND_JOINT ||
+        variable_id >= o->n_ids || factor_id >= o->n_ids || (variable_id >= 0 && o->is_factor[variable_id]) ||
+        (factor_id >= 0 && !o->is_factor[factor_id])) {
+        o->err = "set_signal_variant: bad argument";
+        return CXB_ERR_BAD_ARG;
+    }
+    o->sig[s].kind = kind;
+    o->sig[s].var = variable_id;
+    o->sig[s].fac = factor_id;
+    return CXB_OK;
+}
 int32_t cxo_link_signal(void* h, int64_t v, int64_t s) {
     Oracle* o = O(h);
     if (v < 0 || v >= o->n_ids || o->is_factor[v] || s < 0 || s >= (int64_t)o->sig.size()) {

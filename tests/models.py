@@ -334,3 +334,116 @@ def ssm_mean_field_dataset(n, seed=1234, ssnoise_real=100.0, obsnoise_real=100.0
     rng = np.random.Generator(np.random.PCG64(seed))
     walk = np.cumsum(np.concatenate([[0.0], rng.standard_normal(n - 1) / np.sqrt(ssnoise_real)]))
     return walk + rng.standard_normal(n) / np.sqrt(obsnoise_real)
+
+
+# ---- structured VMP: test/inference_engine_tests.jl:811-1147 ------------------------------------------------------------
+class StructuredResolver(C.AbstractDependencyResolver):
+    """:811-907, literally: mean-field (weak) dependencies around the likelihood factors; around a transition factor the
+    two states form one cluster with a JointMarginal signal (linked to both states, local marginal of the factor)."""
+
+    def resolve_variable_dependencies(self, engine, variable_id):  # :813-815
+        return C.DefaultDependencyResolver().resolve_variable_dependencies(engine, variable_id)
+
+    def resolve_factor_dependencies(self, engine, factor_id):
+        m2v = lambda v: C.get_connection_message_to_variable(engine, v, factor_id)  # noqa: E731
+        m2f = lambda v: C.get_connection_message_to_factor(engine, v, factor_id)  # noqa: E731
+        marg = lambda v: C.get_variable_marginal(C.get_variable(engine, v))  # noqa: E731
+        connected = list(C.get_connected_variable_ids(engine, factor_id))
+        if C.get_factor_functional_form(C.get_factor(engine, factor_id)) == "likelihood":
+            for v1 in connected:
+                for v2 in connected:
+                    if v1 != v2:
+                        C.add_dependency(m2v(v1), marg(v2), weak=True)
+            return
+        clusters = {}  # by variable name (:837-846); iteration = insertion order
+        for v in connected:
+            clusters.setdefault(C.get_variable_name(C.get_variable(engine, v)), []).append(v)
+        deps = []
+        for cluster in clusters.values():
+            if len(cluster) == 1:
+                deps.append(marg(cluster[0]))
+                continue
+            joint = C.create_inference_signal(engine)
+            C.set_variant(joint, C.JointMarginal(factor_id, tuple(cluster)))
+            for v in cluster:
+                C.link_signal_to_variable(C.get_variable(engine, v), joint)
+                C.add_local_marginal_to_factor(C.get_factor(engine, factor_id), joint)
+                C.add_dependency(joint, m2f(v), weak=True)
+            deps.append(joint)
+        for d1 in deps:
+            for d2 in deps:
+                if C.isa_variant(d1, C.JointMarginal) and d1 != d2:
+                    C.add_dependency(d1, d2, weak=True)
+        for index, cluster in enumerate(clusters.values()):
+            for m1 in cluster:
+                for m2 in cluster:
+                    if m1 != m2:
+                        C.add_dependency(m2v(m1), m2f(m2))
+            for m1 in cluster:
+                for another_index, other in enumerate(deps):
+                    if index != another_index:
+                        C.add_dependency(m2v(m1), other, weak=True)
+
+
+def make_ssm_structured_model(n, api, *, dtype=cap.F64, processor=None):
+    """:1031-1076. Values: NormalMeanPrecision (mean, precision), Gamma (shape, scale), observation (y), and
+    MvNormalMeanPrecision (mu1, mu2, W11, W12, W21, W22) for the joint marginals: value_dim = 6."""
+    g = C.BipartiteFactorGraph()
+    ssnoise = g.add_variable(C.Variable(name="ssnoise"))
+    obsnoise = g.add_variable(C.Variable(name="obsnoise"))
+    x = [g.add_variable(C.Variable(name="x", index=(i,))) for i in range(n)]
+    y = [g.add_variable(C.Variable(name="y", index=(i,))) for i in range(n)]
+    lik = [g.add_factor(C.Factor(functional_form="likelihood")) for _ in range(n)]
+    tr = [g.add_factor(C.Factor(functional_form="transition")) for _ in range(n - 1)]
+    for i in range(n):
+        g.add_edge(y[i], lik[i], C.Connection(label="out"))
+        g.add_edge(x[i], lik[i], C.Connection(label="out"))
+        g.add_edge(obsnoise, lik[i], C.Connection(label="out"))
+    for i in range(n - 1):
+        g.add_edge(x[i], tr[i], C.Connection(label="out"))
+        g.add_edge(x[i + 1], tr[i], C.Connection(label="in"))
+        g.add_edge(ssnoise, tr[i], C.Connection(label="out"))
+    builtin = processor is None
+    if builtin:
+        processor = C.RuleProcessor({"likelihood": (cap.RULE_NORMAL_MEAN_FIELD, []), "transition": (cap.RULE_NORMAL_STRUCTURED, [])},
+                                    family=cap.FAMILY_GAUSS_MP, value_dim=6)
+    engine = C.InferenceEngine(model_engine=g, dependency_resolver=StructuredResolver(),
+                               inference_request_processor=processor, dtype=dtype, api=api)
+    if builtin:
+        C.set_variable_families(engine, [ssnoise, obsnoise], cap.FAMILY_GAMMA)
+        C.set_variable_families(engine, y, cap.FAMILY_POINT)
+    pad = lambda a, b: [a, b, 0.0, 0.0, 0.0, 0.0]  # noqa: E731
+    C.set_value(C.get_variable_marginal(C.get_variable(engine, ssnoise)), pad(1.0, 1.0))
+    C.set_value(C.get_variable_marginal(C.get_variable(engine, obsnoise)), pad(1.0, 1.0))
+    C.set_values([C.get_variable_marginal(C.get_variable(engine, v)) for v in x], np.tile(pad(0.0, 1.0), (n, 1)))
+    return engine, x, y, obsnoise, ssnoise, lik, tr
+
+
+def ssm_structured_experiment(engine, x, y, obsnoise, ssnoise, dataset, vmp_iterations, schedule="lvl", merged_all=True):
+    """`experiment` of :1078-1120, call for call. `merged_all=False` leaves out the last call of an iteration (all
+    variables in one request): with more than 5 transition factors ssnoise goes through the segment tree of
+    src/dependencies.jl:90-173, its request then recomputes the joint marginals BEFORE the state messages they listen
+    to, i.e. the result depends on the order of the ids — the level-synchronous schedule refuses that request
+    (CXB_ERR_OUT_OF_CONTRACT) instead of returning something order-dependent."""
+    n = len(dataset)
+    vals = np.zeros((n, 6))
+    vals[:, 0] = np.asarray(dataset, dtype=np.float64)
+    C.set_values([C.get_variable_marginal(C.get_variable(engine, v)) for v in y], vals)
+    up = lambda ids: C.update_marginals(engine, ids, schedule=schedule)  # noqa: E731
+    for iteration in range(1, vmp_iterations + 1):
+        if iteration // 2 == 1:
+            up(x), up(ssnoise), up(obsnoise)
+        else:
+            up(obsnoise), up(ssnoise), up(x)
+        for _ in range(3):
+            up(ssnoise)
+        for _ in range(2):
+            up(x)
+        for _ in range(3):
+            up(obsnoise)
+        up([ssnoise, obsnoise])
+        if merged_all:
+            up([ssnoise, obsnoise] + list(x))
+    mg = lambda v: C.get_value(C.get_variable_marginal(C.get_variable(engine, v)))  # noqa: E731
+    return {"x": C.get_values([C.get_variable_marginal(C.get_variable(engine, v)) for v in x]),
+            "ssnoise": mg(ssnoise), "obsnoise": mg(obsnoise)}
