@@ -23,7 +23,8 @@ const KIND_UNSPECIFIED, KIND_M2F, KIND_M2V, KIND_PRODUCT, KIND_MARGINAL, KIND_JO
 const FAMILY_GAUSS_CANON, FAMILY_CATEGORICAL, FAMILY_GAUSS_MV, FAMILY_BETA, FAMILY_SUM,
       FAMILY_GAUSS_MP, FAMILY_GAMMA, FAMILY_POINT = 0:7
 const RULE_NONE, RULE_GAUSS_OBS, RULE_GAUSS_RW, RULE_CAT_TABLE, RULE_POTTS, RULE_HMM_EMIT,
-      RULE_GAUSS_MV_OBS, RULE_GAUSS_MV_RW, RULE_BETA_BERNOULLI, RULE_SCALE2, RULE_NORMAL_MEAN_FIELD = 0:10
+      RULE_GAUSS_MV_OBS, RULE_GAUSS_MV_RW, RULE_BETA_BERNOULLI, RULE_SCALE2, RULE_NORMAL_MEAN_FIELD,
+      RULE_NORMAL_STRUCTURED = 0:11
 const RESOLVER_NONE, RESOLVER_DEFAULT_BP, RESOLVER_MEAN_FIELD = 0:2
 
 struct UpdateStats
@@ -103,6 +104,25 @@ message_to_variable_id(e::B200InferenceEngine, v::Int, f::Int) =
     ccall((:cxb_signal_id, LIB), Int64, (Ptr{Cvoid}, Int32, Int64, Int64), e.handle, KIND_M2V, v - 1, f - 1)
 message_to_factor_id(e::B200InferenceEngine, v::Int, f::Int) =
     ccall((:cxb_signal_id, LIB), Int64, (Ptr{Cvoid}, Int32, Int64, Int64), e.handle, KIND_M2F, v - 1, f - 1)
+
+# ---- custom wiring: what a user-defined AbstractDependencyResolver calls (test/inference_engine_tests.jl:597-621, 811-907) ----
+const DEP_INTERMEDIATE, DEP_WEAK, DEP_NO_LISTEN, DEP_NO_CHECK_COMPUTED = 1, 2, 16, 32
+create_signal!(e::B200InferenceEngine) = ccall((:cxb_create_signal, LIB), Int64, (Ptr{Cvoid},), e.handle)
+function add_dependency!(e::B200InferenceEngine, signal::Int64, dependency::Int64; weak = false, listen = true,
+                         check_computed = true, intermediate = false)
+    flags = (intermediate ? DEP_INTERMEDIATE : 0) | (weak ? DEP_WEAK : 0) | (listen ? 0 : DEP_NO_LISTEN) |
+            (check_computed ? 0 : DEP_NO_CHECK_COMPUTED)
+    check(e.handle, ccall((:cxb_add_dependency, LIB), Int32, (Ptr{Cvoid}, Int64, Int64, Int32), e.handle, signal, dependency, flags))
+end
+# set_variant!(signal, JointMarginal(factor_id, variable_ids)): the rule registered for the factor computes the signal
+set_joint_marginal_variant!(e::B200InferenceEngine, signal::Int64, factor_id::Int) =
+    check(e.handle, ccall((:cxb_set_signal_variant, LIB), Int32, (Ptr{Cvoid}, Int64, Int32, Int64, Int64),
+                          e.handle, signal, KIND_JOINT, -1, factor_id - 1))
+# delegate one id to a built-in resolver (Cortex.resolve_variable_dependencies!(DefaultDependencyResolver(), engine, id))
+resolve_factor_dependencies!(e::B200InferenceEngine, resolver::Integer, factor_id::Int) =
+    check(e.handle, ccall((:cxb_resolve_factor_dependencies, LIB), Int32, (Ptr{Cvoid}, Int32, Int64), e.handle, resolver, factor_id - 1))
+resolve_variable_dependencies!(e::B200InferenceEngine, resolver::Integer, variable_id::Int) =
+    check(e.handle, ccall((:cxb_resolve_variable_dependencies, LIB), Int32, (Ptr{Cvoid}, Int32, Int64), e.handle, resolver, variable_id - 1))
 
 # value type of a variable's signals in a model that mixes types (VMP: NormalMeanPrecision / Gamma / observed Float64,
 # test/runtests.jl:52-99 — in Julia the type travels with the value, the device needs it declared once)
