@@ -385,6 +385,160 @@ k_hmm64_pass(const float* __restrict__ tbl, const float* __restrict__ emis_n, co
     }
 }
 
+// ---- K = 64, fp32: TWO warps per chain (one CTA of 64 threads per chain: 2,048 warps = 3.5 per scheduler at B = 1,024) ----
+// MEASURED ALTERNATIVE, off by default (see launch_k64): slower than one warp per chain at config-3 size.
+// With one warp per chain the batch of config 3 leaves 1.75 warps per scheduler and every step pays its dependent chain
+// (shared loads -> 64 FFMA2 -> shuffles) almost in full (630 cycles per step against a 221-cycle FMA-pipe floor). Here warp h
+// of a chain owns the output states [32 h, 32 h + 32): lane (cg = lane / 4, rg = lane % 4) holds the 16 x 4 tile
+// tbl[16 rg .. 16 rg + 15][32 h + 4 cg .. + 3] as 32 packed pairs (half the registers), does 32 FFMA2 per step on four
+// 128-bit shared loads, and a 3-shuffle transpose-reduce over the four row groups leaves output state 32 h + lane in the
+// lane (one float per lane: 128 contiguous bytes per warp in every global access). The two warps exchange the carried
+// message, the maximum of their half (exact power-of-two scaling, as above) and the partial sums of the deferred exact
+// normalisation through double-buffered shared memory with ONE 64-thread barrier per step. The exactly normalised
+// message / marginal of step s-5 leaves during step s (per-warp pipelined butterfly, 4 steps; cross-warp total, 1 more).
+template <bool FWD, bool EM_SMEM>
+__global__ void __launch_bounds__(64, 7)  // 7 chains per SM: 1,024 chains in one wave on 148 SMs
+k_hmm64_split(const float* __restrict__ tbl, const float* __restrict__ emis_n, const uint8_t* __restrict__ obs,
+              float* __restrict__ fwd, float* __restrict__ marg, long long B, long long Tn, int n_sym) {
+    constexpr int K = 64, LOOK = 8, LAG = 5, VS = 72;  // VS: states 32 .. 63 are shifted by 4 banks
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float* sh_v = reinterpret_cast<float*>(smem_raw);  // [2][VS] carried message, double buffered
+    float* sh_mx = sh_v + 2 * VS;                      // [2][2] max of each warp's half of the carried message
+    float* sh_tot = sh_mx + 4;                         // [2][2] per-warp sums of the value that leaves next
+    float* sh_em = sh_tot + 4;                         // [M][64] emission messages (if they fit)
+    const int h = threadIdx.x >> 5, lane = threadIdx.x & 31, cg = lane >> 2, rg = lane & 3;
+    const long long b = blockIdx.x;
+    float2 a2[4][8];  // a2[jj][ip] = (tbl[16 rg + 2 ip][j], tbl[16 rg + 2 ip + 1][j]), j = 32 h + 4 cg + jj
+#pragma unroll
+    for (int jj = 0; jj < 4; ++jj)
+#pragma unroll
+        for (int ip = 0; ip < 8; ++ip) {
+            const int j = 32 * h + 4 * cg + jj, i = 16 * rg + 2 * ip;
+            a2[jj][ip] = make_float2(tbl[(size_t)i * K + j], tbl[(size_t)(i + 1) * K + j]);
+        }
+    if (EM_SMEM)
+        for (int x = threadIdx.x; x < n_sym * K; x += blockDim.x) sh_em[x] = emis_n[x];
+    if (threadIdx.x < 4) {
+        sh_mx[threadIdx.x] = 1.0f;
+        sh_tot[threadIdx.x] = 1.0f;
+    }
+    __syncthreads();
+    const int my_state = 32 * h + lane;
+    const int my_slot = my_state + 4 * h;            // where this lane's state lives in sh_v
+    const int rd_off = 16 * rg + 4 * (rg >> 1);      // this lane's 16 input states
+
+    auto time_of = [&](long long step) { return FWD ? step : Tn - 1 - step; };
+    auto load_obs_block = [&](long long step0) -> int {  // lane l fetches the symbol of step0 + l
+        long long st = step0 + lane;
+        return (st < Tn) ? (int)obs[(size_t)time_of(st) * B + b] : 0;
+    };
+    auto fwd_at = [&](long long step) -> float {  // BWD: forward message of `step` for this lane's state
+        return (step < Tn) ? __ldcs(&fwd[((size_t)time_of(step) * B + b) * K + my_state]) : 0.0f;
+    };
+    int obs_cur = 0, obs_next = load_obs_block(0);
+    float a_cur[LOOK], a_nxt[LOOK];
+#pragma unroll
+    for (int u = 0; u < LOOK; ++u) {
+        a_cur[u] = 0.0f;
+        a_nxt[u] = FWD ? 0.0f : fwd_at(u);
+    }
+    float ring[LOOK];  // what steps s-1 .. s-8 leave behind (FWD: the message, BWD: fwd * bwd)
+#pragma unroll
+    for (int u = 0; u < LOOK; ++u) ring[u] = 0.0f;
+    float p1 = 0.0f, p2 = 0.0f, p3 = 0.0f;  // butterfly partial sums in flight (one level per step)
+
+    auto step = [&](auto gen_tag, long long s, int slot, float a_now) {
+        constexpr bool GEN = decltype(gen_tag)::value;
+        const int cur = (int)(s & 1), prv = cur ^ 1;
+        int o = __shfl_sync(0xffffffffu, obs_cur, (int)(s & 31));
+        if (o >= n_sym) o = n_sym - 1;
+        const float em = EM_SMEM ? sh_em[o * K + my_state] : __ldg(emis_n + (size_t)o * K + my_state);
+        // what the two warps left at the previous step: maxima of the carried message, sums of the value of step s-5
+        const float2 mx2 = *reinterpret_cast<const float2*>(sh_mx + 2 * prv);
+        const float2 tt2 = *reinterpret_cast<const float2*>(sh_tot + 2 * prv);
+        const float r = hmm_pow2_inv(fmaxf(mx2.x, mx2.y));
+        if (!GEN || (s >= LAG && s - LAG < Tn)) {
+            const float q = hmm_rcp(tt2.x + tt2.y);
+            float* dst = FWD ? fwd : marg;
+            __stcs(&dst[((size_t)time_of(s - LAG) * B + b) * K + my_state], ring[(slot + LOOK - LAG) % LOOK] * q);
+        }
+        float tot;
+        {   // pipelined butterfly over the warp's 32 states: step s-1 enters, step s-4 completes
+            const float x1 = ring[(slot + LOOK - 1) % LOOK];
+            const float n1 = x1 + __shfl_xor_sync(0xffffffffu, x1, 16);
+            const float n2 = p1 + __shfl_xor_sync(0xffffffffu, p1, 8);
+            const float n3 = p2 + __shfl_xor_sync(0xffffffffu, p2, 4);
+            const float m4 = p3 + __shfl_xor_sync(0xffffffffu, p3, 2);
+            tot = m4 + __shfl_xor_sync(0xffffffffu, m4, 1);
+            p1 = n1;
+            p2 = n2;
+            p3 = n3;
+        }
+        float unew = 0.0f;
+        if (!GEN || s < Tn) {
+            float val = 1.0f;
+            if (!GEN || s > 0) {
+                const float4* vp = reinterpret_cast<const float4*>(sh_v + cur * VS + rd_off);
+                float4 v4[4];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) v4[q] = vp[q];
+                float2 c[4], e[4];  // 8 independent FFMA2 chains of length 4
+#pragma unroll
+                for (int jj = 0; jj < 4; ++jj) c[jj] = e[jj] = make_float2(0.0f, 0.0f);
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const float2 lo = make_float2(v4[q].x, v4[q].y), hi = make_float2(v4[q].z, v4[q].w);
+#pragma unroll
+                    for (int jj = 0; jj < 4; ++jj) c[jj] = ffma2(a2[jj][2 * q], lo, c[jj]);
+#pragma unroll
+                    for (int jj = 0; jj < 4; ++jj) e[jj] = ffma2(a2[jj][2 * q + 1], hi, e[jj]);
+                }
+                float acc[4];
+#pragma unroll
+                for (int jj = 0; jj < 4; ++jj) acc[jj] = (c[jj].x + e[jj].x) + (c[jj].y + e[jj].y);
+                // transpose-reduce over the four row groups: lane rg ends with column jj = rg of its column group
+                const bool b0 = rg & 1, b1 = rg & 2;
+                const float kA = (b0 ? acc[1] : acc[0]) + __shfl_xor_sync(0xffffffffu, b0 ? acc[0] : acc[1], 1);
+                const float kB = (b0 ? acc[3] : acc[2]) + __shfl_xor_sync(0xffffffffu, b0 ? acc[2] : acc[3], 1);
+                val = (b1 ? kB : kA) + __shfl_xor_sync(0xffffffffu, b1 ? kA : kB, 2);
+            }
+            unew = (!GEN || s > 0) ? em * val * r : em;
+            ring[slot] = FWD ? unew : a_now * val;
+            sh_v[prv * VS + my_slot] = unew;
+        }
+        float mx;
+        asm("redux.sync.max.f32 %0, %1, 0xffffffff;" : "=f"(mx) : "f"(unew));
+        if (lane == 0) {
+            sh_mx[2 * cur + h] = mx;
+            sh_tot[2 * cur + h] = tot;
+        }
+        __syncthreads();  // the chain's two warps: message, maxima and sums of this step are visible
+    };
+
+    for (long long s0 = 0; s0 < Tn + LAG; s0 += LOOK) {
+        if ((s0 & 31) == 0) {
+            obs_cur = obs_next;
+            obs_next = load_obs_block(s0 + 32);
+        }
+        if (!FWD) {
+#pragma unroll
+            for (int u = 0; u < LOOK; ++u) {
+                a_cur[u] = a_nxt[u];
+                a_nxt[u] = fwd_at(s0 + LOOK + u);
+            }
+            if (s0 + 32 < Tn && lane < 2)
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(&fwd[((size_t)time_of(s0 + 32) * B + b) * K + 32 * lane]));
+        }
+        if (s0 >= LOOK && s0 + LOOK <= Tn) {
+#pragma unroll
+            for (int uu = 0; uu < LOOK; ++uu) step(std::false_type{}, s0 + uu, uu, a_cur[uu]);
+        } else {
+#pragma unroll
+            for (int uu = 0; uu < LOOK; ++uu) step(std::true_type{}, s0 + uu, uu, a_cur[uu]);
+        }
+    }
+}
+
 // ---- K = 64, fp32, tensor cores: one CTA of 4 warps per 8 chains (1,024 chains = 128 CTAs, one per SM) -----------------------
 // The sequential recursion leaves one 64 x 64 x 8 product per SM and step: warp w computes output states 16 w .. 16 w + 15 of
 // 8 chains with mma.sync.m16n8k16 (bf16 split operands, hi*hi + hi*lo + lo*hi, fp32 accumulate: 12 MMAs per warp and step
@@ -795,6 +949,27 @@ struct Hmm {
         // (CXB_HMM64_MMA=1): with one 64 x 64 x 8 product per SM and step it has a single warp per scheduler and pays every
         // latency in full — 970 cycles per step against 630 for the FFMA2 kernel below (T = 4,000: 3.94 ms vs 2.55 ms).
         if (M <= 128 && getenv("CXB_HMM64_MMA") && atoi(getenv("CXB_HMM64_MMA"))) return launch_k64_mma();
+        {   // Two warps per chain (k_hmm64_split), a measured alternative (CXB_HMM64_SPLIT=1): it halves the FFMA2 chain of a
+            // warp but every warp repeats the per-step bookkeeping (emission, scaling, butterfly, stores) and the pair meets at
+            // a barrier, so the step is issue-bound at a HIGHER instruction count: B = 1,024, T = 1e5: 80.6 ms against 63.9 ms
+            // for one warp per chain (790 vs 630 cycles per step).
+            bool split = false;
+            if (const char* e = getenv("CXB_HMM64_SPLIT")) split = atoi(e) != 0;
+            if (split) {
+                const bool em_smem = M <= 128;
+                const size_t smem = (size_t)(2 * 72 + 8) * sizeof(float) + (em_smem ? (size_t)M * 64 * sizeof(float) : 0);
+                const float *a = (const float*)A.p, *at = (const float*)At.p, *en = (const float*)En.p;
+                const unsigned grid = (unsigned)B;
+                if (em_smem) {
+                    CXB_LAUNCH((k_hmm64_split<true, true>), grid, 64, smem, stream, a, en, obs.p, (float*)fwd.p, (float*)marg.p, B, this->T, M);
+                    CXB_LAUNCH((k_hmm64_split<false, true>), grid, 64, smem, stream, at, en, obs.p, (float*)fwd.p, (float*)marg.p, B, this->T, M);
+                } else {
+                    CXB_LAUNCH((k_hmm64_split<true, false>), grid, 64, smem, stream, a, en, obs.p, (float*)fwd.p, (float*)marg.p, B, this->T, M);
+                    CXB_LAUNCH((k_hmm64_split<false, false>), grid, 64, smem, stream, at, en, obs.p, (float*)fwd.p, (float*)marg.p, B, this->T, M);
+                }
+                return CXB_OK;
+            }
+        }
         // one warp per chain; warps per CTA chosen so that one CTA per SM holds the whole batch when it can (its warps
         // then spread evenly over the 4 schedulers): 1,024 chains -> 147 CTAs of 7 warps
         int n_sm = 148;

@@ -490,6 +490,27 @@ def test_hmm_tensor_core_kernel_matches_simt_kernel(monkeypatch):
     assert_close(res[0][1], res[1][1], cap.F32)
 
 
+@pytest.mark.parametrize("B,T,M", [(1, 1, 3), (3, 2, 3), (5, 7, 4), (19, 37, 32), (8, 130, 100), (4, 300, 200)])
+def test_hmm64_two_warps_per_chain_variant_vs_numpy(B, T, M, monkeypatch):
+    """k_hmm64_split (CXB_HMM64_SPLIT=1): two warps per chain exchanging through shared memory; same tolerance as the default."""
+    monkeypatch.setenv("CXB_HMM64_SPLIT", "1")
+    K = 64
+    rng = np.random.Generator(np.random.PCG64(77 + T))
+    A = rng.dirichlet(np.ones(K), size=K)
+    E = rng.dirichlet(np.ones(K), size=M).T * K
+    obs = rng.integers(0, M, size=(T, B)).astype(np.uint8)
+    hm = C.HmmBatch(B, T, K, M, dtype=cap.F32)
+    hm.set_tables(A, E)
+    hm.set_observations(obs)
+    hm.update_marginals()
+    got_m, got_f = hm.get_marginals(), hm.get_forward()
+    A_used = A.astype(np.float32).astype(np.float64)
+    for b in (0, B - 1):
+        want_f, want_m = _hmm_numpy(A_used, E, obs[:, b])
+        assert_close(got_f[:, b, :], want_f, cap.F32)
+        assert_close(got_m[:, b, :], want_m, cap.F32)
+
+
 @pytest.mark.parametrize("B,T,M", [(5, 3, 4), (19, 37, 32), (8, 130, 100)])
 def test_hmm64_tensor_core_variant_vs_numpy(B, T, M, monkeypatch):
     """The mma.sync variant of the K = 64 kernel (CXB_HMM64_MMA=1; measured slower than the FFMA2 kernel, kept as evidence
