@@ -744,9 +744,10 @@ struct Hmm {
     DBuf<unsigned char> A, At, En, fwd, marg;
     DBuf<uint8_t> obs;
     // tensor-core path (hmm_tc.cuh): table images (forward: rows of A^T, backward: rows of A), message operands, row sums
-    DBuf<uint16_t> tc_img_f, tc_img_b, tc_op[2];
-    DBuf<float> tc_part[2];
+    DBuf<uint16_t> tc_img_f, tc_img_b, tc_op[2], tc_op_b[2];  // _b: the backward pass's own ping-pong (paired launches)
+    DBuf<float> tc_part[2], tc_part_b[2];
     bool tc_ready = false;
+    bool tc_paired = true;
     int tc_nt = 64;  // output states per CTA of the tensor-core step kernel (32 or 64)
     int tc_np = 3;   // bf16 pieces per operand (3: fp32-level accuracy, the default; 2: ~2^-17 per term, CXB_HMM_TC_PIECES=2)
     bool tc_eligible() const {
@@ -814,7 +815,10 @@ struct Hmm {
             // slices of 32 output states when 64-state slices would leave most SMs idle
             int n_sm = 148;
             cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, device);
-            tc_nt = (tc_bpad() / tc::M_TILE) * (K / 64) * 2 <= n_sm ? 32 : 64;
+            tc_paired = true;  // both passes in one launch per step (k_hmm_tc_step_pair); CXB_HMM_TC_PAIRED=0: one pass after the other
+            if (const char* e = getenv("CXB_HMM_TC_PAIRED")) tc_paired = atoi(e) != 0;
+            // the widest grid that is still resident at once: (chain tiles) x (K / NT slices) x (passes per launch) CTAs, one per SM
+            tc_nt = (tc_bpad() / tc::M_TILE) * (K / 32) * (tc_paired ? 2 : 1) <= n_sm ? 32 : 64;
             if (const char* e = getenv("CXB_HMM_TC_NT")) tc_nt = atoi(e) == 32 ? 32 : 64;
             tc_np = 3;
             if (const char* e = getenv("CXB_HMM_TC_PIECES")) tc_np = atoi(e) == 2 ? 2 : 3;
@@ -833,6 +837,12 @@ struct Hmm {
                 CXB_CUDA(tc_part[i].reserve((size_t)2 * (K / tc_nt) * bpad));
                 CXB_CUDA(cudaMemsetAsync(tc_op[i].p, 0, op_elems * 2, stream));
                 CXB_CUDA(cudaMemsetAsync(tc_part[i].p, 0, (size_t)2 * (K / tc_nt) * bpad * sizeof(float), stream));
+                if (tc_paired) {
+                    CXB_CUDA(tc_op_b[i].reserve(op_elems));
+                    CXB_CUDA(tc_part_b[i].reserve((size_t)2 * (K / tc_nt) * bpad));
+                    CXB_CUDA(cudaMemsetAsync(tc_op_b[i].p, 0, op_elems * 2, stream));
+                    CXB_CUDA(cudaMemsetAsync(tc_part_b[i].p, 0, (size_t)2 * (K / tc_nt) * bpad * sizeof(float), stream));
+                }
             }
             tc_ready = true;
         }
@@ -855,8 +865,81 @@ struct Hmm {
     }
     // one launch per time step and pass (hmm_tc.cuh); 2 T + 4 launches
     int32_t launch_tc() {
+        if (tc_paired) {
+            if (tc_np == 2) return tc_nt == 32 ? launch_tc_pair_nt<32, 2>() : launch_tc_pair_nt<64, 2>();
+            return tc_nt == 32 ? launch_tc_pair_nt<32, 3>() : launch_tc_pair_nt<64, 3>();
+        }
         if (tc_np == 2) return tc_nt == 32 ? launch_tc_nt<32, 2>() : launch_tc_nt<64, 2>();
         return tc_nt == 32 ? launch_tc_nt<32, 3>() : launch_tc_nt<64, 3>();
+    }
+    // Paired schedule: launch s runs step s of BOTH passes (forward at time s, backward at time T-1-s): T + 5 launches.
+    // The backward half writes the marginal directly once the forward message of its time step is final (normalised in
+    // place by forward launch t+1, i.e. for T-1-s <= s-2); before that it stores the normalised backward prediction and
+    // k_hmm_tc_combine multiplies the forward messages in at the end (times >= T - s_direct).
+    template <int NT, int NP>
+    int32_t launch_tc_pair_nt() {
+        const int bpad = (int)tc_bpad(), tiles = bpad / tc::M_TILE, n_slices = K / NT;
+        const size_t smem = tc::step_smem_bytes<NT, NP>(M), row = (size_t)B * K;
+        CXB_CUDA(cudaFuncSetAttribute(tc::k_hmm_tc_step_pair<NT, NP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        float *fw = (float*)fwd.p, *mg = (float*)marg.p;
+        tc::StepArgs2 p{};
+        for (int z = 0; z < 2; ++z) {
+            p.d[z].emis_n = (const float*)En.p;
+            p.d[z].B = (int)B;
+            p.d[z].Bpad = bpad;
+            p.d[z].K = K;
+            p.d[z].n_sym = M;
+        }
+        p.d[0].tbl_img = (const __nv_bfloat16*)tc_img_f.p;
+        p.d[1].tbl_img = (const __nv_bfloat16*)tc_img_b.p;
+        const dim3 grid(tiles, n_slices, 2), igrid(bpad / 128, n_slices);
+        const bool pdl = !(getenv("CXB_HMM_TC_NO_PDL") && atoi(getenv("CXB_HMM_TC_NO_PDL")));
+        const long long Tn = this->T, s_direct = (Tn + 2) / 2;  // first launch whose backward half sees a final forward message
+        for (long long s = 0; s < Tn; ++s) {
+            const long long tf = s, tb = Tn - 1 - s;
+            tc::StepArgs& f = p.d[0];
+            tc::StepArgs& b = p.d[1];
+            f.op_in = (const __nv_bfloat16*)tc_op[(s + 1) & 1].p;
+            f.op_out = (__nv_bfloat16*)tc_op[s & 1].p;
+            f.part_in = tc_part[(s + 1) & 1].p;
+            f.part_out = tc_part[s & 1].p;
+            f.obs_t = obs.p + (size_t)tf * B;
+            f.raw_out = fw + (size_t)tf * row;
+            f.raw_prev = s ? fw + (size_t)(tf - 1) * row : nullptr;
+            f.fwd_t = nullptr;
+            b.op_in = (const __nv_bfloat16*)tc_op_b[(s + 1) & 1].p;
+            b.op_out = (__nv_bfloat16*)tc_op_b[s & 1].p;
+            b.part_in = tc_part_b[(s + 1) & 1].p;
+            b.part_out = tc_part_b[s & 1].p;
+            b.obs_t = obs.p + (size_t)tb * B;
+            b.raw_out = mg + (size_t)tb * row;
+            b.raw_prev = s ? mg + (size_t)(tb + 1) * row : nullptr;
+            b.fwd_t = s >= s_direct ? fw + (size_t)tb * row : nullptr;
+            if (s == 0) {
+                CXB_LAUNCH((tc::k_hmm_tc_init<true, NT, NP>), igrid, 128, 0, stream, f);
+                CXB_LAUNCH((tc::k_hmm_tc_init<false, NT, NP>), igrid, 128, 0, stream, b);
+            } else {
+                cudaLaunchConfig_t cfg{};
+                cfg.gridDim = grid;
+                cfg.blockDim = dim3(tc::THREADS);
+                cfg.dynamicSmemBytes = smem;
+                cfg.stream = stream;
+                cudaLaunchAttribute attr[1];
+                attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+                attr[0].val.programmaticStreamSerializationAllowed = (pdl && s > 1) ? 1 : 0;  // launch 1 follows the two init kernels
+                cfg.attrs = attr;
+                cfg.numAttrs = 1;
+                CXB_CUDA(cudaLaunchKernelEx(&cfg, tc::k_hmm_tc_step_pair<NT, NP>, p));
+                ++::cxb::g_kernel_launches;
+            }
+        }
+        CXB_LAUNCH(tc::k_hmm_tc_finish, (unsigned)B, 128, 0, stream, fw + (size_t)(Tn - 1) * row, tc_part[(Tn - 1) & 1].p, (int)B, bpad, K,
+                   n_slices);
+        CXB_LAUNCH(tc::k_hmm_tc_finish, (unsigned)B, 128, 0, stream, mg, tc_part_b[(Tn - 1) & 1].p, (int)B, bpad, K, n_slices);
+        const long long t0 = Tn - std::min(s_direct, Tn), n_rows = (Tn - t0) * B;  // times the backward half ran ahead of the forward pass
+        if (n_rows > 0)
+            CXB_LAUNCH(tc::k_hmm_tc_combine, (unsigned)((n_rows + 7) / 8), 256, 0, stream, fw + (size_t)t0 * row, mg + (size_t)t0 * row, n_rows, K);
+        return CXB_OK;
     }
     template <int NT, int NP>
     int32_t launch_tc_nt() {

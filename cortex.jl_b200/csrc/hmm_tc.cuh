@@ -162,7 +162,7 @@ __device__ __forceinline__ void load_row64(const float* p, float4 (&v)[16]) {
 }
 
 template <bool FWD, int NT, int NP>
-__global__ void __launch_bounds__(THREADS, 1) k_hmm_tc_step(const StepArgs a) {
+__device__ __forceinline__ void hmm_tc_step_body(const StepArgs& a) {
     constexpr int N_TILE = NT, STAGES = Cfg<NT, NP>::STAGES;
     constexpr uint32_t B_CHUNK_BYTES = Cfg<NT, NP>::B_CHUNK_BYTES, STAGE_BYTES = Cfg<NT, NP>::STAGE_BYTES, IDESC = Cfg<NT, NP>::IDESC;
     constexpr int LPR = N_TILE / 4, RPI = 32 / LPR, ITER = 32 / RPI;  // lanes per row, rows per instruction, iterations per warp
@@ -287,7 +287,9 @@ __global__ void __launch_bounds__(THREADS, 1) k_hmm_tc_step(const StepArgs a) {
 #pragma unroll
             for (int it = 0; it < ITER; ++it) {
                 const int mm = tile * M_TILE + warp * 32 + RPI * it + hrow;
-                fw[it] = mm < a.B ? reinterpret_cast<const float4*>(a.fwd_t + (size_t)mm * a.K + n0)[c4] : make_float4(0.f, 0.f, 0.f, 0.f);
+                fw[it] = !a.fwd_t  ? make_float4(1.f, 1.f, 1.f, 1.f)  // no forward message yet: the prediction itself is stored
+                         : mm < a.B ? reinterpret_cast<const float4*>(a.fwd_t + (size_t)mm * a.K + n0)[c4]
+                                    : make_float4(0.f, 0.f, 0.f, 0.f);
             }
         }
         if (threadIdx.x == 0) stamp(a, 6);
@@ -364,6 +366,48 @@ __global__ void __launch_bounds__(THREADS, 1) k_hmm_tc_step(const StepArgs a) {
     if (threadIdx.x == 0) stamp(a, 9);
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(N_TILE));
 }
+template <bool FWD, int NT, int NP>
+__global__ void __launch_bounds__(THREADS, 1) k_hmm_tc_step(const StepArgs a) {
+    hmm_tc_step_body<FWD, NT, NP>(a);
+}
+// Both passes in ONE launch per step: blockIdx.z = 0 runs step s of the forward pass (time s), blockIdx.z = 1 step s of the
+// backward pass (time T-1-s). The two recursions are independent, so a launch holds twice the CTAs (2 x 64 at B = 1,024,
+// K = 512, NT = 64: every SM busy) and the set-up, launch gap and epilogue of one pass hide under the operand ingest of
+// the other. The backward half needs the forward message of its time step only for the MARGINAL (fwd * bwd): while the
+// forward pass has not reached that time yet (first half of the launches) it is given fwd_t = nullptr, stores the
+// normalised backward prediction instead, and k_hmm_tc_combine multiplies the forward message in afterwards.
+struct StepArgs2 {
+    StepArgs d[2];
+};
+template <int NT, int NP>
+__global__ void __launch_bounds__(THREADS, 1) k_hmm_tc_step_pair(const StepArgs2 p) {
+    if (blockIdx.z == 0)
+        hmm_tc_step_body<true, NT, NP>(p.d[0]);
+    else
+        hmm_tc_step_body<false, NT, NP>(p.d[1]);
+}
+// marginal rows the backward half left as normalised predictions: marg = normalise(fwd * marg), one warp per (time, chain) row
+__global__ void k_hmm_tc_combine(const float* __restrict__ fwd, float* __restrict__ marg, long long n_rows, int K) {
+    const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= n_rows) return;
+    const int lane = threadIdx.x & 31;
+    const float4* f = reinterpret_cast<const float4*>(fwd + (size_t)row * K);
+    float4* g = reinterpret_cast<float4*>(marg + (size_t)row * K);
+    float sum = 0.0f;
+    for (int i = lane; i < K / 4; i += 32) {
+        const float4 a = __ldcs(f + i), b = g[i];
+        const float4 r = make_float4(a.x * b.x, a.y * b.y, a.z * b.z, a.w * b.w);
+        g[i] = r;
+        sum += (r.x + r.y) + (r.z + r.w);
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, d);
+    const float q = rcp_nr(sum);
+    for (int i = lane; i < K / 4; i += 32) {
+        const float4 r = g[i];
+        __stcs(g + i, make_float4(r.x * q, r.y * q, r.z * q, r.w * q));
+    }
+}
 
 // first step of a pass: carried message = emission message; result = emission (FWD) / forward message (BWD)
 template <bool FWD, int NT, int NP>
@@ -384,7 +428,7 @@ __global__ void k_hmm_tc_init(StepArgs a) {
             c[i] = live ? a.emis_n[(size_t)o * a.K + n0 + k0 + i] : 0.0f;
             sum_c += c[i];
             if (live) {
-                const float res = FWD ? c[i] : a.fwd_t[(size_t)m * a.K + n0 + k0 + i];
+                const float res = FWD ? c[i] : a.fwd_t ? a.fwd_t[(size_t)m * a.K + n0 + k0 + i] : 1.0f;
                 a.raw_out[(size_t)m * a.K + n0 + k0 + i] = res;
                 sum_r += res;
             }
