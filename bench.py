@@ -417,9 +417,18 @@ def bench_hmm64(args, pkg, rank, world, local):
     e2e_ms = timed(hm.stream, e2e_step, e2e_steps, 1, world, local)
     clocks = sampler.stop()
     alg_bytes = B * T * (12 * K + 2)  # forward message + marginal contract
-    return {"ms": ms, "updates_per_step": hm.n_updates, "kernel_ms": statistics.mean(kernel_ms), "alg_bytes": alg_bytes,
-            "e2e_ms": e2e_ms, "e2e_steps": e2e_steps, "h2d": B * T, "d2h": tail * B * K * 4, "launches": launches,
-            "clocks": clocks, "dtype": "f32", "kernel": "k_hmm64_pass / k_hmm_pass (fwd + bwd launches)", "scaling": "weak"}
+    out = {"ms": ms, "updates_per_step": hm.n_updates, "kernel_ms": statistics.mean(kernel_ms), "alg_bytes": alg_bytes,
+           "e2e_ms": e2e_ms, "e2e_steps": e2e_steps, "h2d": B * T, "d2h": tail * B * K * 4, "launches": launches,
+           "clocks": clocks, "dtype": "f32", "scaling": "weak",
+           "kernel": "k_hmm64_pass (forward launch + backward launch, one warp per chain)"}
+    if K >= 128:
+        # tensor-core path: each fp32 product is 6 bf16 MMAs (3-piece split operands, hmm_tc.cuh), 2 passes per time step
+        pieces = 2 if os.environ.get("CXB_HMM_TC_PIECES") == "2" else 3
+        mmas = 3 if pieces == 2 else 6
+        out["kernel"] = "k_hmm_tc_step_pair (tcgen05 + TMEM; one launch per time step, forward and backward halves)"
+        out["tensor"] = {"issued_flops": 2.0 * B * K * K * mmas * 2 * T, "fp32_equivalent_flops": 2.0 * B * K * K * 2 * T,
+                         "note": f"{mmas} bf16 MMAs per fp32 product ({pieces}-piece split operands)"}
+    return out
 
 
 def bench_powerlaw(args, pkg, rank, world, local):
@@ -630,6 +639,14 @@ def main():
                          "kernel_ms": r["kernel_ms"], "algorithmic_bytes_per_launch": r["alg_bytes"]}}
     if "timer" in r:
         line["timer"] = r["timer"]
+    if "tensor" in r:  # K = 512 HMM: tensor-pipe utilisation beside the HBM figure (north star: "or tensor-pipe utilisation against peak")
+        peaks = json.loads((ROOT / "MEASURED_PEAKS.json").read_text()) if (ROOT / "MEASURED_PEAKS.json").exists() else {}
+        tpeak = float(peaks.get("bf16_tflops_sustained", 1410.1))
+        tf = r["tensor"]["issued_flops"] / (r["kernel_ms"] * 1e-3) / 1e12
+        line["roofline_tensor"] = {"bound": "tensor", "achieved": tf, "peak": tpeak, "unit": "TFLOP/s", "frac": tf / tpeak,
+                                   "fp32_equivalent_tflops": r["tensor"]["fp32_equivalent_flops"] / (r["kernel_ms"] * 1e-3) / 1e12,
+                                   "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained (cuBLAS bf16 8192^3, dense)",
+                                   "note": r["tensor"]["note"]}
     traffic_file = ROOT / "profiles" / f"traffic_{args.workload}.json"
     if traffic_file.exists():
         try:

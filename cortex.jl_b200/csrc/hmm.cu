@@ -895,6 +895,14 @@ struct Hmm {
         const dim3 grid(tiles, n_slices, 2), igrid(bpad / 128, n_slices);
         const bool pdl = !(getenv("CXB_HMM_TC_NO_PDL") && atoi(getenv("CXB_HMM_TC_NO_PDL")));
         const long long Tn = this->T, s_direct = (Tn + 2) / 2;  // first launch whose backward half sees a final forward message
+        DBuf<long long> trace;
+        const bool tracing = getenv("CXB_HMM_TC_TRACE") && atoi(getenv("CXB_HMM_TC_TRACE"));
+        const size_t n_cta = (size_t)tiles * n_slices * 2;
+        if (tracing) {
+            CXB_CUDA(trace.reserve(n_cta * 16));
+            CXB_CUDA(cudaMemsetAsync(trace.p, 0, n_cta * 16 * sizeof(long long), stream));
+            p.d[0].trace = p.d[1].trace = trace.p;
+        }
         for (long long s = 0; s < Tn; ++s) {
             const long long tf = s, tb = Tn - 1 - s;
             tc::StepArgs& f = p.d[0];
@@ -939,6 +947,21 @@ struct Hmm {
         const long long t0 = Tn - std::min(s_direct, Tn), n_rows = (Tn - t0) * B;  // times the backward half ran ahead of the forward pass
         if (n_rows > 0)
             CXB_LAUNCH(tc::k_hmm_tc_combine, (unsigned)((n_rows + 7) / 8), 256, 0, stream, fw + (size_t)t0 * row, mg + (size_t)t0 * row, n_rows, K);
+        if (tracing) {  // stamps of the LAST paired launch, averaged over the CTAs of each half, relative to the earliest CTA start
+            std::vector<long long> h(n_cta * 16);
+            CXB_CUDA(cudaStreamSynchronize(stream));
+            CXB_CUDA(cudaMemcpy(h.data(), trace.p, h.size() * sizeof(long long), cudaMemcpyDeviceToHost));
+            static const char* names[10] = {"start", "init+alloc done", "producer issued all", "mma: first chunk landed", "mma: last chunk landed",
+                                            "mma: all issued", "epi: prev normalised", "epi: accumulator ready", "epi: done", "exit"};
+            for (int z = 0; z < 2; ++z)
+                for (int k = 0; k < 10; ++k) {
+                    double acc = 0;
+                    const size_t c0 = (size_t)z * tiles * n_slices, c1 = c0 + (size_t)tiles * n_slices;
+                    for (size_t c = c0; c < c1; ++c) acc += (double)(h[c * 16 + k] - h[c * 16]);
+                    fprintf(stderr, "cxb_hmm tc trace (%s half): %-26s %8.0f cycles after the CTA's own start\n", z ? "backward" : "forward", names[k],
+                            acc / (tiles * n_slices));
+                }
+        }
         return CXB_OK;
     }
     template <int NT, int NP>

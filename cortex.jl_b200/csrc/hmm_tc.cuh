@@ -152,7 +152,7 @@ struct StepArgs {
     long long* trace;             // tuning aid (CXB_HMM_TC_TRACE=1): per-CTA clock64 stamps of the pipeline events, else null
 };
 __device__ __forceinline__ void stamp(const StepArgs& a, int slot) {
-    if (a.trace) a.trace[(size_t)(blockIdx.y * gridDim.x + blockIdx.x) * 16 + slot] = clock64();
+    if (a.trace) a.trace[(size_t)((blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x) * 16 + slot] = clock64();
 }
 
 // rows [m][n0 .. n0 + 63] of a [B][K] fp32 plane: 16 independent 128-bit accesses per thread (one round trip)
@@ -303,7 +303,9 @@ __device__ __forceinline__ void hmm_tc_step_body(const StepArgs& a) {
         // every MMA has completed (accum barrier), so the ring is free: stage[row][0..63] (row stride 68 floats) takes the
         // accumulator rows (thread = TMEM lane), everything else happens half a warp per row
         constexpr int SROW = N_TILE + 4;
+        constexpr int PSTR = LPR + 4;  // row stride of the partial sums: 128-bit reads of 8 consecutive rows hit 8 different bank groups
         float* stage = reinterpret_cast<float*>(ring);
+        float* s_sum = stage + (size_t)M_TILE * SROW;  // [2 (carried, result)][128 rows][PSTR]
 #pragma unroll
         for (int half = 0; half < N_TILE / 32; ++half) {
             float pred[32];
@@ -326,21 +328,12 @@ __device__ __forceinline__ void hmm_tc_step_body(const StepArgs& a) {
             const float4 pd = *reinterpret_cast<const float4*>(stage + (size_t)rr * SROW + c4 * 4);
             const float4 e4 = *reinterpret_cast<const float4*>(s_em + o_r * N_TILE + c4 * 4);
             const float4 cr = make_float4(e4.x * pd.x * r_r, e4.y * pd.y * r_r, e4.z * pd.z * r_r, e4.w * pd.w * r_r);  // carried message
-            float sc = (cr.x + cr.y) + (cr.z + cr.w);
-#pragma unroll
-            for (int d = LPR / 2; d > 0; d >>= 1) sc += __shfl_xor_sync(0xffffffffu, sc, d);
             float4 res = cr;  // forward: the result IS the carried message; backward: fwd * pred
-            float sr = sc;
-            if (!FWD) {
-                res = make_float4(pd.x * fw[it].x, pd.y * fw[it].y, pd.z * fw[it].z, pd.w * fw[it].w);
-                sr = (res.x + res.y) + (res.z + res.w);
-#pragma unroll
-                for (int d = LPR / 2; d > 0; d >>= 1) sr += __shfl_xor_sync(0xffffffffu, sr, d);
-            }
-            if (c4 == 0) {
-                a.part_out[(size_t)(0 * n_slices + slice) * a.Bpad + mm] = sc;
-                a.part_out[(size_t)(1 * n_slices + slice) * a.Bpad + mm] = mm < a.B ? sr : 0.0f;
-            }
+            if (!FWD) res = make_float4(pd.x * fw[it].x, pd.y * fw[it].y, pd.z * fw[it].z, pd.w * fw[it].w);
+            // row sums: the lane's 4-column partials go to shared memory and ONE lane per row adds them up after the loop
+            // (no shuffle chain per row on the path of the stores; the sums leave as one coalesced line per warp)
+            s_sum[(size_t)rr * PSTR + c4] = (cr.x + cr.y) + (cr.z + cr.w);
+            if (!FWD) s_sum[(size_t)(M_TILE + rr) * PSTR + c4] = (res.x + res.y) + (res.z + res.w);
             if (mm < a.B) reinterpret_cast<float4*>(a.raw_out + (size_t)mm * a.K + n0)[c4] = res;
             // next step's message operand in the canonical UMMA layout (this slice = chunk `slice` of K): 4 states = 8 bytes
             // per lane; two rows x two lanes fill whole 32-byte sectors
@@ -358,6 +351,22 @@ __device__ __forceinline__ void hmm_tc_step_body(const StepArgs& a) {
                 }
                 *reinterpret_cast<uint2*>(op_pc[pc] + e) = make_uint2(w[0], w[1]);
             }
+        }
+        __syncwarp();  // a warp only sums the 32 rows it wrote itself
+        {
+            float sc = 0.0f, sr = 0.0f;
+#pragma unroll
+            for (int q = 0; q < LPR / 4; ++q) {
+                const float4 x = *reinterpret_cast<const float4*>(s_sum + (size_t)row * PSTR + 4 * q);
+                sc += (x.x + x.y) + (x.z + x.w);
+                if (!FWD) {
+                    const float4 y = *reinterpret_cast<const float4*>(s_sum + (size_t)(M_TILE + row) * PSTR + 4 * q);
+                    sr += (y.x + y.y) + (y.z + y.w);
+                }
+            }
+            if (FWD) sr = sc;
+            a.part_out[(size_t)(0 * n_slices + slice) * a.Bpad + m] = sc;
+            a.part_out[(size_t)(1 * n_slices + slice) * a.Bpad + m] = live ? sr : 0.0f;
         }
         if (threadIdx.x == 0) stamp(a, 8);
     }
