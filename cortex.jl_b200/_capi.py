@@ -71,6 +71,7 @@ _COMMON = {
     "update_marginals": (i32, [vp, i64, i64p, C.POINTER(UpdateStats)]),
     "trace_enable": (i32, [vp, i32]),
     "trace_get": (i64, [vp, i64p, i64p, i64]),
+    "trace_get_times": (i64, [vp, i64p, i64]),
 }
 
 # structured engines, cxb_ only

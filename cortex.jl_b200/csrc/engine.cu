@@ -847,12 +847,15 @@ struct DeviceEngine {
     uint32_t n_req = 0;
 
     // trace of the last update
-    std::vector<int64_t> tr_level, tr_sid;
+    std::vector<int64_t> tr_level, tr_sid, tr_ns;  // tr_ns: device time of the level (CUDA events), shared evenly by its members
+    cudaEvent_t tr_ev0 = nullptr, tr_ev1 = nullptr;
     cxb_update_stats stats{};
 
     size_t esz() const { return dtype == CXB_F32 ? 4 : 8; }
 
     ~DeviceEngine() {
+        if (tr_ev0) cudaEventDestroy(tr_ev0);
+        if (tr_ev1) cudaEventDestroy(tr_ev1);
         if (stream) cudaStreamDestroy(stream);
     }
 
@@ -1292,11 +1295,19 @@ struct DeviceEngine {
             ++sg.n;
         }
         if (sg.n) chunks.push_back(sg);
+        if (trace_on) {
+            if (!tr_ev0) {
+                CXB_CUDA(cudaEventCreate(&tr_ev0));
+                CXB_CUDA(cudaEventCreate(&tr_ev1));
+            }
+            CXB_CUDA(cudaEventRecord(tr_ev0, stream));
+        }
         for (auto& c : chunks) CXB_LAUNCH(k_check_independent, cdiv(c.total, 256), 256, 0, stream, v, c, lvl_epoch);
         if ((st = launch_rules(total))) return st;
         for (auto& c : chunks) CXB_LAUNCH(k_apply, cdiv(c.total, 256), 256, 0, stream, v, c, req_epoch, check_mode);
         stats.updates += total;
         if (trace_on) {
+            CXB_CUDA(cudaEventRecord(tr_ev1, stream));
             std::vector<uint32_t> ids;
             for (int k = 0; k < nk; ++k) {
                 uint32_t cnt = h_counts.p[k];
@@ -1308,9 +1319,13 @@ struct DeviceEngine {
             }
             CXB_CUDA(cudaStreamSynchronize(stream));
             std::sort(ids.begin(), ids.end());
+            float level_ms = 0.0f;
+            CXB_CUDA(cudaEventElapsedTime(&level_ms, tr_ev0, tr_ev1));  // rules + set_value! side effects of this level, on the device
+            const int64_t each = std::max<int64_t>((int64_t)(level_ms * 1e6 / std::max<size_t>(ids.size(), 1)), 1);
             for (uint32_t s : ids) {
                 tr_level.push_back(level_tag);
                 tr_sid.push_back(s);
+                tr_ns.push_back(each);
             }
         }
         return CXB_OK;
@@ -1473,6 +1488,7 @@ struct DeviceEngine {
         stats = cxb_update_stats{};
         tr_level.clear();
         tr_sid.clear();
+        tr_ns.clear();
         int32_t st = request(n, ids);
         if (st) return st;
         CXB_CUDA(cudaMemsetAsync(d_kind_count.p, 0, 8 * sizeof(unsigned long long), stream));
@@ -1932,6 +1948,12 @@ int64_t cxb_trace_get(cxb_engine* h, int64_t* out_level, int64_t* out_sid, int64
         if (out_sid) out_sid[i] = e->tr_sid[i];
     }
     return (int64_t)e->tr_sid.size();
+}
+int64_t cxb_trace_get_times(cxb_engine* h, int64_t* out_ns, int64_t cap) {
+    DeviceEngine* e = E(h);
+    for (int64_t i = 0; i < (int64_t)e->tr_ns.size() && i < cap; ++i)
+        if (out_ns) out_ns[i] = e->tr_ns[i];
+    return (int64_t)e->tr_ns.size();
 }
 
 }  // extern "C"

@@ -425,6 +425,8 @@ def _collect_trace(engine: InferenceEngine, ids, total_ns: int, before=None) -> 
     lv = np.zeros(max(n, 1), dtype=np.int64)
     sg = np.zeros(max(n, 1), dtype=np.int64)
     engine.api.trace_get(engine.store.h, lv.ctypes.data_as(capi.i64p), sg.ctypes.data_as(capi.i64p), n)
+    ns = np.zeros(max(n, 1), dtype=np.int64)  # measured per execution (oracle) / per level, shared evenly (device)
+    engine.api.trace_get_times(engine.store.h, ns.ctypes.data_as(capi.i64p), n)
     var = None
     if hasattr(engine.api, "trace_get_variables"):
         var = np.zeros(max(n, 1), dtype=np.int64)
@@ -434,7 +436,7 @@ def _collect_trace(engine: InferenceEngine, ids, total_ns: int, before=None) -> 
     for k in range(n):
         key = int(lv[k]) if lv[k] >= 0 else -1  # the final phase (marginals, then linked signals) is ONE round, :610-628
         if key != cur_key:
-            cur = TracedInferenceRound(engine, max(total_ns // max(n, 1), 1), [])
+            cur = TracedInferenceRound(engine, 0, [])
             rounds.append(cur)  # only rounds with >= 1 execution are recorded, :818
             cur_key = key
         s = Signal(engine.store, int(sg[k]))
@@ -447,5 +449,6 @@ def _collect_trace(engine: InferenceEngine, ids, total_ns: int, before=None) -> 
                 value_before = UndefValue()
             else:
                 value_before = float(vals[s.sid][0]) if engine.store.value_dim == 1 else vals[s.sid].copy()
-        cur.executions.append(TracedInferenceExecution(engine, vid, s, max(total_ns // max(n, 1), 1), value_before, get_value(s)))
+        cur.executions.append(TracedInferenceExecution(engine, vid, s, max(int(ns[k]), 1), value_before, get_value(s)))
+        cur.total_time_in_ns += max(int(ns[k]), 1)
     return TracedInferenceRequest(engine, max(total_ns, 1), InferenceRequest(engine, tuple(ids), []), rounds)

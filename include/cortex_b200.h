@@ -223,6 +223,9 @@ int32_t cxb_update_marginals(cxb_engine* h, int64_t n, const int64_t* variable_i
  * -2 = final-phase linked signals. Within a level signals are in ascending id order. */
 int32_t cxb_trace_enable(cxb_engine* h, int32_t on);
 int64_t cxb_trace_get(cxb_engine* h, int64_t* out_level, int64_t* out_signals, int64_t cap);
+/* TracedInferenceExecution.total_time_in_ns (src/inference_engine.jl:650-657) of the same records: a level is one batch of
+ * kernels, its device time (CUDA events around the rule and set_value! kernels) is shared evenly by its members */
+int64_t cxb_trace_get_times(cxb_engine* h, int64_t* out_ns, int64_t cap);
 
 /* ===========================================================================================
  * Structured model engines: closed-form plans for the fixed-stencil graph families (SURVEY §8a,

@@ -26,6 +26,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdint>
+#include <chrono>
 #include <cstring>
 #include <map>
 #include <string>
@@ -63,7 +64,11 @@ struct Rule {
 
 struct TraceRec {
     int64_t round, var, sid;
+    int64_t ns = 0;  // measured duration of this execution (TracedInferenceExecution.total_time_in_ns, src/inference_engine.jl:650-657)
 };
+static inline int64_t now_ns() {
+    return std::chrono::duration_cast<std::chrono::nanoseconds>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
 
 struct Oracle {
     int dim = 1, family = 0;
@@ -652,12 +657,13 @@ struct Oracle {
                 bool processed = process_dependencies(req_marg[i], true, [&](int64_t d) {  // :512-525
                     if (fail) return false;
                     if (is_pending(d)) {
+                        const int64_t t0 = now_ns();
                         int32_t s2 = compute(d, false, false);
                         if (s2) {
                             fail = s2;
                             return false;
                         }
-                        trace.push_back({round, var, d});
+                        trace.push_back({round, var, d, now_ns() - t0});
                         round_had_exec = true;
                         return true;
                     }
@@ -675,16 +681,18 @@ struct Oracle {
         for (int64_t i = 0; i < n; ++i) {  // final phase, :610-628
             int64_t m = req_marg[i];
             if (is_pending(m)) {
+                const int64_t t0 = now_ns();
                 int32_t s2 = compute(m, false, false);
                 if (s2) return s2;
-                trace.push_back({-1, req_ids[i], m});
+                trace.push_back({-1, req_ids[i], m, now_ns() - t0});
                 ++stats.final_marginals;
             }
             for (int64_t l : linked[req_ids[i]]) {
                 if (!is_pending(l)) continue;
+                const int64_t t0 = now_ns();
                 int32_t s2 = compute(l, false, false);
                 if (s2) return s2;
-                trace.push_back({-1, req_ids[i], l});
+                trace.push_back({-1, req_ids[i], l, now_ns() - t0});
                 ++stats.final_linked;
             }
         }
@@ -703,6 +711,7 @@ struct Oracle {
                     return CXB_ERR_OUT_OF_CONTRACT;
                 }
         std::vector<double> tmp(F.size() * (size_t)dim);
+        const int64_t t_level0 = now_ns();
         for (size_t k = 0; k < F.size(); ++k) {
             int32_t st = eval_rule(F[k], &tmp[k * dim]);
             if (st) return st;
@@ -712,6 +721,10 @@ struct Oracle {
             ++stats.updates;
             ++stats.updates_by_kind[sig[F[k]].kind];
             trace.push_back({level_tag, sig[F[k]].var, F[k]});
+        }
+        if (!F.empty()) {  // a level is one batch: its measured time is shared evenly by its members
+            const int64_t each = std::max<int64_t>((now_ns() - t_level0) / (int64_t)F.size(), 1);
+            for (size_t k = trace.size() - F.size(); k < trace.size(); ++k) trace[k].ns = each;
         }
         return CXB_OK;
     }
@@ -1109,6 +1122,11 @@ int64_t cxo_trace_get(void* h, int64_t* out_level, int64_t* out_sid, int64_t cap
         if (out_level) out_level[i] = o->trace[i].round;
         if (out_sid) out_sid[i] = o->trace[i].sid;
     }
+    return (int64_t)o->trace.size();
+}
+int64_t cxo_trace_get_times(void* h, int64_t* out_ns, int64_t cap) {
+    Oracle* o = O(h);
+    for (int64_t i = 0; i < (int64_t)o->trace.size() && i < cap; ++i) out_ns[i] = o->trace[i].ns;
     return (int64_t)o->trace.size();
 }
 int64_t cxo_trace_get_variables(void* h, int64_t* out_var, int64_t cap) {

@@ -214,6 +214,10 @@ def test_tracing_iid_model(backend):  # :1149-1280
     assert all(x.value_before_execution == C.UndefValue() for x in r1.executions + r2.executions)  # :1246, 1253, 1261
     assert [C.get_variant(x.signal) for x in r2.executions] == [C.IndividualMarginal(p)]
     assert r2.executions[0].value_after_execution == 9
+    # times are measured (per execution on the oracle; per level on the device, CUDA events), not the request time split evenly
+    for r in (r1, r2):
+        assert all(x.total_time_in_ns > 0 for x in r.executions)
+        assert r.total_time_in_ns == sum(x.total_time_in_ns for x in r.executions) <= req.total_time_in_ns
     # a second traced request after ALL inputs were set again (a signal is pending only when every strong dependency is
     # fresh, src/signal.jl:668-730): the old values are reported, no longer UndefValue()
     C.set_value(m2f(e, o1, f1), 5)
