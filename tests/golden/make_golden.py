@@ -124,12 +124,26 @@ def oracle_pairwise(api):
                 marginals=marg)
 
 
+def oracle_vmp(api):
+    """The reference's two variational SSM models (test/inference_engine_tests.jl:593-809, 811-1147), small: posterior
+    parameters after a few VMP iterations of the reference's call sequence on the SEQUENTIAL schedule."""
+    n, iters = 12, 5
+    data = models.ssm_mean_field_dataset(n, seed=21)
+    m = models.make_ssm_mean_field_model(n, api)
+    mf = models.ssm_mean_field_experiment(m[0], m[1], m[2], m[3], m[4], data, iters, schedule="seq")
+    m = models.make_ssm_structured_model(n, api)
+    st = models.ssm_structured_experiment(m[0], m[1], m[2], m[3], m[4], data, iters, schedule="seq", merged_all=False)
+    return dict(data=data, iters=np.int64(iters), mf_x=mf["x"], mf_ssnoise=mf["ssnoise"], mf_obsnoise=mf["obsnoise"],
+                st_x=st["x"][:, :2], st_ssnoise=st["ssnoise"][:2], st_obsnoise=st["obsnoise"][:2])
+
+
 def main():
     (HERE / "reference_known_answers.json").write_text(json.dumps(reference_known_answers(), indent=1) + "\n")
     api = pkg.CApi(ORACLE_LIB, "cxo_")
     np.savez(HERE / "oracle_gauss_chain.npz", **oracle_chain(api))
     np.savez(HERE / "oracle_hmm.npz", **oracle_hmm(api))
     np.savez(HERE / "oracle_pairwise.npz", **oracle_pairwise(api))
+    np.savez(HERE / "oracle_vmp.npz", **oracle_vmp(api))
     print("wrote", sorted(p.name for p in HERE.iterdir()))
 
 

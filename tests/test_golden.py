@@ -66,7 +66,8 @@ def test_nibble_layout_constants_match_reference():  # src/signal.jl:36-45, 507-
 def test_committed_oracle_vectors_are_reproducible(oracle_api):
     from tests.golden import make_golden as mg
 
-    for name, fn in (("oracle_gauss_chain", mg.oracle_chain), ("oracle_hmm", mg.oracle_hmm), ("oracle_pairwise", mg.oracle_pairwise)):
+    for name, fn in (("oracle_gauss_chain", mg.oracle_chain), ("oracle_hmm", mg.oracle_hmm), ("oracle_pairwise", mg.oracle_pairwise),
+                     ("oracle_vmp", mg.oracle_vmp)):
         want = np.load(GOLD / f"{name}.npz")
         got = fn(oracle_api)
         assert sorted(want.files) == sorted(got)
@@ -111,3 +112,23 @@ def test_pairwise_kernel_matches_committed_vectors(dtype, tol):
         pw.sweep()
     # fp32 rounds tables and evidence on entry; the committed vectors are fp64, hence the fp32 tolerance of the north star
     np.testing.assert_allclose(pw.get_marginals(), g["marginals"], rtol=10 * tol, atol=10 * tol * float(g["marginals"].max()))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("dtype,tol", [(cap.F64, 1e-12), (cap.F32, 1e-5)])
+def test_vmp_engine_matches_committed_vectors(dtype, tol):
+    """Mean-field and structured VMP on the device engine (level-synchronous schedule) against vectors the oracle produced
+    on the reference's SEQUENTIAL schedule: weak dependencies, joint marginals, per-variable value families."""
+    from tests import models
+
+    g = np.load(GOLD / "oracle_vmp.npz")
+    data, iters = g["data"], int(g["iters"])
+    api = pkg.default_api()
+    m = models.make_ssm_mean_field_model(len(data), api, dtype=dtype)
+    got = models.ssm_mean_field_experiment(m[0], m[1], m[2], m[3], m[4], data, iters)
+    for k in ("x", "ssnoise", "obsnoise"):
+        np.testing.assert_allclose(got[k], g[f"mf_{k}"], rtol=tol, atol=tol * 1e-3, err_msg=f"mean-field {k}")
+    m = models.make_ssm_structured_model(len(data), api, dtype=dtype)
+    got = models.ssm_structured_experiment(m[0], m[1], m[2], m[3], m[4], data, iters, merged_all=False)
+    for k in ("x", "ssnoise", "obsnoise"):
+        np.testing.assert_allclose(got[k][..., :2], g[f"st_{k}"], rtol=tol, atol=tol * 1e-3, err_msg=f"structured {k}")
