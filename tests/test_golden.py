@@ -119,11 +119,9 @@ def test_pairwise_kernel_matches_committed_vectors(dtype, tol):
 def test_vmp_engine_matches_committed_vectors(dtype, tol):
     """Mean-field and structured VMP on the device engine (level-synchronous schedule) against vectors the oracle produced
     on the reference's SEQUENTIAL schedule: weak dependencies, joint marginals, per-variable value families."""
-    from tests import models
-
     g = np.load(GOLD / "oracle_vmp.npz")
     data, iters = g["data"], int(g["iters"])
-    api = pkg.default_api()
+    api = C.default_api()
     m = models.make_ssm_mean_field_model(len(data), api, dtype=dtype)
     got = models.ssm_mean_field_experiment(m[0], m[1], m[2], m[3], m[4], data, iters)
     for k in ("x", "ssnoise", "obsnoise"):
