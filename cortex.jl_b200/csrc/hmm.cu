@@ -880,7 +880,37 @@ struct Hmm {
     int32_t launch_tc_pair_nt() {
         const int bpad = (int)tc_bpad(), tiles = bpad / tc::M_TILE, n_slices = K / NT;
         const size_t smem = tc::step_smem_bytes<NT, NP>(M), row = (size_t)B * K;
-        CXB_CUDA(cudaFuncSetAttribute(tc::k_hmm_tc_step_pair<NT, NP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CXB_CUDA(cudaFuncSetAttribute(tc::k_hmm_tc_step_pair<NT, NP, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CXB_CUDA(cudaFuncSetAttribute(tc::k_hmm_tc_step_pair<NT, NP, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CXB_CUDA(cudaFuncSetAttribute(tc::k_hmm_tc_step_pair<NT, NP, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        // clusters of 4 or 8 slices of a chain tile with a multicast message operand (CXB_HMM_TC_CLUSTER=4|8), when the slices
+        // divide and every cluster of the grid is resident at once (a B200 holds 15 clusters of 8 CTAs of this size: config 3
+        // needs 16, so it falls back)
+        int cl = 1;
+        if (const char* e = getenv("CXB_HMM_TC_CLUSTER")) cl = atoi(e) == 8 ? 8 : atoi(e) == 4 ? 4 : 1;
+        if (cl > 1 && n_slices % cl) cl = 1;
+        if (cl > 1) {
+            cudaLaunchConfig_t q{};
+            q.gridDim = dim3(tiles, n_slices, 2);
+            q.blockDim = dim3(tc::THREADS);
+            q.dynamicSmemBytes = smem;
+            cudaLaunchAttribute qa[1];
+            qa[0].id = cudaLaunchAttributeClusterDimension;
+            qa[0].val.clusterDim.x = 1;
+            qa[0].val.clusterDim.y = cl;
+            qa[0].val.clusterDim.z = 1;
+            q.attrs = qa;
+            q.numAttrs = 1;
+            int n_clusters = 0;
+            const int needed = tiles * (n_slices / cl) * 2, asked = cl;
+            const cudaError_t qe = cl == 8 ? cudaOccupancyMaxActiveClusters(&n_clusters, tc::k_hmm_tc_step_pair<NT, NP, 8>, &q)
+                                           : cudaOccupancyMaxActiveClusters(&n_clusters, tc::k_hmm_tc_step_pair<NT, NP, 4>, &q);
+            if (qe != cudaSuccess || n_clusters < needed) cl = 1;
+            cudaGetLastError();
+            if (getenv("CXB_HMM_TC_VERBOSE"))
+                fprintf(stderr, "cxb_hmm tc: clusters of %d requested: %d resident at once (%s), %d needed -> cluster size %d\n", asked, n_clusters,
+                        cudaGetErrorString(qe), needed, cl);
+        }
         float *fw = (float*)fwd.p, *mg = (float*)marg.p;
         tc::StepArgs2 p{};
         for (int z = 0; z < 2; ++z) {
@@ -932,12 +962,21 @@ struct Hmm {
                 cfg.blockDim = dim3(tc::THREADS);
                 cfg.dynamicSmemBytes = smem;
                 cfg.stream = stream;
-                cudaLaunchAttribute attr[1];
+                cudaLaunchAttribute attr[2];
                 attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
                 attr[0].val.programmaticStreamSerializationAllowed = (pdl && s > 1) ? 1 : 0;  // launch 1 follows the two init kernels
+                attr[1].id = cudaLaunchAttributeClusterDimension;
+                attr[1].val.clusterDim.x = 1;
+                attr[1].val.clusterDim.y = cl;
+                attr[1].val.clusterDim.z = 1;
                 cfg.attrs = attr;
-                cfg.numAttrs = 1;
-                CXB_CUDA(cudaLaunchKernelEx(&cfg, tc::k_hmm_tc_step_pair<NT, NP>, p));
+                cfg.numAttrs = cl > 1 ? 2 : 1;
+                if (cl == 8)
+                    CXB_CUDA(cudaLaunchKernelEx(&cfg, tc::k_hmm_tc_step_pair<NT, NP, 8>, p));
+                else if (cl == 4)
+                    CXB_CUDA(cudaLaunchKernelEx(&cfg, tc::k_hmm_tc_step_pair<NT, NP, 4>, p));
+                else
+                    CXB_CUDA(cudaLaunchKernelEx(&cfg, tc::k_hmm_tc_step_pair<NT, NP, 1>, p));
                 ++::cxb::g_kernel_launches;
             }
         }

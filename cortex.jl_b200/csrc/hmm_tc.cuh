@@ -76,6 +76,16 @@ __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t
                  "r"(bytes), "r"(bar)
                  : "memory");
 }
+// the same copy delivered to the same shared-memory offset (and signalled on the same barrier offset) of every CTA in `mask`
+__device__ __forceinline__ void bulk_g2s_mc(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar, uint16_t mask) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;" ::"r"(dst),
+                 "l"(src), "r"(bytes), "r"(bar), "h"(mask)
+                 : "memory");
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
 __device__ __forceinline__ uint64_t smem_desc(uint32_t addr) {  // K-major, no swizzle, version 1 (Blackwell)
     return (uint64_t)((addr & 0x3FFFFu) >> 4) | ((uint64_t)(LBO >> 4) << 16) | ((uint64_t)(SBO >> 4) << 32) | (1ull << 46);
 }
@@ -91,6 +101,11 @@ __device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t a_desc, uint
 }
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+// arrive on the barrier at this offset in EVERY CTA of `mask` when the MMAs issued so far have completed
+__device__ __forceinline__ void umma_commit_mc(uint32_t bar, uint16_t mask) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar), "h"(mask)
+                 : "memory");
 }
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
     uint32_t r[32];
@@ -161,7 +176,12 @@ __device__ __forceinline__ void load_row64(const float* p, float4 (&v)[16]) {
     for (int i = 0; i < 16; ++i) v[i] = reinterpret_cast<const float4*>(p)[i];
 }
 
-template <bool FWD, int NT, int NP>
+// CL > 1: the CL CTAs that hold consecutive slices of ONE chain tile form a cluster; each loads 1 / CL of every message
+// chunk and multicasts it to all of them (the message operand is the same for every slice: 393 KB per CTA and step of
+// L2 -> SM traffic become 393 / CL KB issued per CTA; L2 read throughput, ~6,300 B/clk chip-wide, is what the ingest
+// of a step waits on). A stage may only be refilled when EVERY CTA of the cluster has consumed it: the empty barriers
+// count CL arrivals and every MMA commit arrives on the barrier of all CL CTAs.
+template <bool FWD, int NT, int NP, int CL = 1>
 __device__ __forceinline__ void hmm_tc_step_body(const StepArgs& a) {
     constexpr int N_TILE = NT, STAGES = Cfg<NT, NP>::STAGES;
     constexpr uint32_t B_CHUNK_BYTES = Cfg<NT, NP>::B_CHUNK_BYTES, STAGE_BYTES = Cfg<NT, NP>::STAGE_BYTES, IDESC = Cfg<NT, NP>::IDESC;
@@ -186,7 +206,7 @@ __device__ __forceinline__ void hmm_tc_step_body(const StepArgs& a) {
     if (threadIdx.x == 0) {
         for (int s = 0; s < STAGES; ++s) {
             mbar_init(smem_u32(&full[s]), 1);
-            mbar_init(smem_u32(&empty[s]), 1);
+            mbar_init(smem_u32(&empty[s]), CL);
         }
         mbar_init(smem_u32(accum), 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -199,6 +219,11 @@ __device__ __forceinline__ void hmm_tc_step_body(const StepArgs& a) {
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = *tmem_slot;
+    uint32_t crank = 0;
+    if (CL > 1) {
+        asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(crank));
+        cluster_sync_all();  // every CTA's barriers exist before anyone multicasts into them
+    }
     asm volatile("griddepcontrol.wait;" ::: "memory");  // everything below reads what the previous step's grid wrote
     if (threadIdx.x == 0) stamp(a, 1);
 
@@ -214,7 +239,14 @@ __device__ __forceinline__ void hmm_tc_step_body(const StepArgs& a) {
                 mbar_expect_tx(bar, STAGE_BYTES);
 #pragma unroll
                 for (int pc = 0; pc < NP; ++pc) {
-                    bulk_g2s(st + pc * A_CHUNK_BYTES, op + (size_t)(pc * n_chunks + c) * (A_CHUNK_BYTES / 2), A_CHUNK_BYTES, bar);
+                    if (CL == 1) {
+                        bulk_g2s(st + pc * A_CHUNK_BYTES, op + (size_t)(pc * n_chunks + c) * (A_CHUNK_BYTES / 2), A_CHUNK_BYTES, bar);
+                    } else {
+                        constexpr uint32_t PART = A_CHUNK_BYTES / CL;  // this CTA's share of the chunk, delivered to the whole cluster
+                        bulk_g2s_mc(st + pc * A_CHUNK_BYTES + crank * PART,
+                                    op + (size_t)(pc * n_chunks + c) * (A_CHUNK_BYTES / 2) + (size_t)crank * (PART / 2), PART, bar,
+                                    (uint16_t)((1u << CL) - 1u));
+                    }
                     bulk_g2s(st + NP * A_CHUNK_BYTES + pc * B_CHUNK_BYTES, tb + (size_t)(pc * n_chunks + c) * (B_CHUNK_BYTES / 2), B_CHUNK_BYTES, bar);
                 }
             }
@@ -240,7 +272,10 @@ __device__ __forceinline__ void hmm_tc_step_body(const StepArgs& a) {
                             umma_bf16(tmem_base, smem_desc(a_base + pa * A_CHUNK_BYTES + off), smem_desc(b_base + pb * B_CHUNK_BYTES + off), IDESC,
                                       (c | ks | pa | pb) != 0);
                 }
-                umma_commit(smem_u32(&empty[s]));  // frees the stage when these MMAs have read it
+                if (CL == 1)
+                    umma_commit(smem_u32(&empty[s]));  // frees the stage when these MMAs have read it
+                else
+                    umma_commit_mc(smem_u32(&empty[s]), (uint16_t)((1u << CL) - 1u));  // ... in every CTA that refills it
             }
             umma_commit(smem_u32(accum));
             stamp(a, 5);
@@ -372,6 +407,7 @@ __device__ __forceinline__ void hmm_tc_step_body(const StepArgs& a) {
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
+    if (CL > 1) cluster_sync_all();  // no CTA leaves while a peer's commit may still arrive on its barriers
     if (threadIdx.x == 0) stamp(a, 9);
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(N_TILE));
 }
@@ -388,12 +424,12 @@ __global__ void __launch_bounds__(THREADS, 1) k_hmm_tc_step(const StepArgs a) {
 struct StepArgs2 {
     StepArgs d[2];
 };
-template <int NT, int NP>
+template <int NT, int NP, int CL>
 __global__ void __launch_bounds__(THREADS, 1) k_hmm_tc_step_pair(const StepArgs2 p) {
     if (blockIdx.z == 0)
-        hmm_tc_step_body<true, NT, NP>(p.d[0]);
+        hmm_tc_step_body<true, NT, NP, CL>(p.d[0]);
     else
-        hmm_tc_step_body<false, NT, NP>(p.d[1]);
+        hmm_tc_step_body<false, NT, NP, CL>(p.d[1]);
 }
 // marginal rows the backward half left as normalised predictions: marg = normalise(fwd * marg), one warp per (time, chain) row
 __global__ void k_hmm_tc_combine(const float* __restrict__ fwd, float* __restrict__ marg, long long n_rows, int K) {

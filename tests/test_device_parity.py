@@ -451,18 +451,21 @@ def test_hmm64_kernel_lengths_and_long_chain_vs_numpy(T, M):
 
 @pytest.mark.parametrize("K,B,T,M", [(128, 5, 1, 4), (128, 5, 2, 4), (128, 130, 3, 7), (256, 7, 6, 32), (512, 131, 5, 32),
                                       (512, 3, 40, 64), (320, 9, 12, 5)])
-@pytest.mark.parametrize("schedule", ["paired", "pass_after_pass", "paired_nt64", "two_pieces"])
+@pytest.mark.parametrize("schedule", ["paired", "pass_after_pass", "paired_nt64", "two_pieces", "cluster4", "cluster8"])
 def test_hmm_tensor_core_kernel_vs_numpy(K, B, T, M, schedule, monkeypatch):
     """K >= 128 fp32: tcgen05 path (bf16 split operands, fp32 TMEM accumulators, one launch per time step), ragged chain
     tiles (B not a multiple of 128), every pipeline depth, against the dense fp64 forward-backward. Schedules: both passes
     in one launch per step (default; T = 1, 2, 3 exercise the hand-over between stored predictions and direct marginals),
-    one pass after the other, the 64-state slice variant, and the 2-piece operand split."""
+    one pass after the other, the 64-state slice variant, the 2-piece operand split, and thread-block clusters with a
+    multicast message operand."""
     if schedule == "pass_after_pass":
         monkeypatch.setenv("CXB_HMM_TC_PAIRED", "0")
     elif schedule == "paired_nt64":
         monkeypatch.setenv("CXB_HMM_TC_NT", "64")
     elif schedule == "two_pieces":
         monkeypatch.setenv("CXB_HMM_TC_PIECES", "2")
+    elif schedule in ("cluster4", "cluster8"):  # slices of a chain tile in one cluster, message operand multicast (when the slices divide)
+        monkeypatch.setenv("CXB_HMM_TC_CLUSTER", schedule[-1])
     rng = np.random.Generator(np.random.PCG64(2024 + K))
     A = rng.dirichlet(np.ones(K) * 0.5, size=K)
     E = rng.dirichlet(np.ones(K) * 0.5, size=M).T * K
