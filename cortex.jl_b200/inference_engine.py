@@ -291,6 +291,28 @@ def get_warnings(engine: InferenceEngine):
     return engine.warnings
 
 
+def add_warning(engine: InferenceEngine, description: str, context) -> None:
+    """add_warning!(engine, description, context), src/inference_engine.jl:127-129."""
+    engine.warnings.append(InferenceEngineWarning(description, context))
+
+
+def resolve_dependencies(resolver: AbstractDependencyResolver, engine: InferenceEngine) -> None:
+    """resolve_dependencies!(resolver, engine), src/dependencies.jl:5-15."""
+    resolver.resolve_dependencies(engine)
+
+
+def format_time_ns(ns: int) -> str:
+    """format_time_ns(ns), src/utils.jl:2-16 (used when a trace is printed)."""
+    ns = int(ns)
+    if ns < 1_000:
+        return f"{ns} ns"
+    for limit, div, unit in ((1_000_000, 1_000, "μs"), (1_000_000_000, 1_000_000, "ms"), (60_000_000_000, 1_000_000_000, "s"),
+                             (3_600_000_000_000, 60_000_000_000, "min"), (None, 3_600_000_000_000, "hr")):
+        if limit is None or ns < limit:
+            return f"{float(round(ns / div * 100) / 100)!r} {unit}"  # round(x, digits = 2), shortest float repr as in Julia
+    raise AssertionError("unreachable")
+
+
 def get_variable(engine: InferenceEngine, variable_id: int) -> Variable:
     return backend_get_variable(engine.model_engine, variable_id)
 

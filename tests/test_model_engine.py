@@ -172,3 +172,27 @@ def test_isa_variant_and_variant_reprs(backend):  # inference_engine_tests.jl:1-
         assert C.isa_variant(s, type(variant)) and C.get_variant(s) == variant
         assert not any(C.isa_variant(s, T) for T in others)
         assert type(variant).__name__ in repr(C.get_variant(s))
+
+
+def test_format_time_ns():  # test/util_tests.jl
+    cases = {100: "100 ns", 999: "999 ns", 1_000: "1.0 μs", 1_234: "1.23 μs", 999_999: "1000.0 μs", 999_000: "999.0 μs",
+             500_500: "500.5 μs", 1_000_000: "1.0 ms", 1_234_567: "1.23 ms", 999_000_000: "999.0 ms", 1_000_000_000: "1.0 s",
+             1_234_000_000: "1.23 s", 59_000_000_000: "59.0 s", 60_000_000_000: "1.0 min", 90_000_000_000: "1.5 min",
+             3_540_000_000_000: "59.0 min", 3_600_000_000_000: "1.0 hr", 5_400_000_000_000: "1.5 hr",
+             999_999_999: "1000.0 ms", 59_999_999_999: "60.0 s", 3_599_999_999_999: "60.0 min", 1_235: "1.24 μs",
+             1_230: "1.23 μs", 1_234_000: "1.23 ms", 1_235_000: "1.24 ms", 0: "0 ns"}
+    for ns, want in cases.items():
+        assert C.format_time_ns(ns) == want, ns
+
+
+def test_add_warning_and_resolve_dependencies_entry_points(oracle_api):  # src/inference_engine.jl:127-129, src/dependencies.jl:5-15
+    g = C.BipartiteFactorGraph()
+    v = g.add_variable(C.Variable(name="v"))
+    f = g.add_factor(C.Factor(functional_form="f"))
+    g.add_edge(v, f, C.Connection(label="out"))
+    e = C.InferenceEngine(model_engine=g, resolve_dependencies=False, api=oracle_api)
+    assert C.get_dependencies(C.get_variable_marginal(C.get_variable(e, v))) == []
+    C.resolve_dependencies(C.DefaultDependencyResolver(), e)
+    assert len(C.get_dependencies(C.get_variable_marginal(C.get_variable(e, v)))) == 1
+    C.add_warning(e, "something", 3)
+    assert [(w.description, w.context) for w in C.get_warnings(e)] == [("something", 3)]
