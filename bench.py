@@ -188,9 +188,66 @@ def cpu_baseline_chain(T=1024, budget_s=12.0):
     return n / dt, f"1 chain x T={T} explicit Signal graph, sequential update_marginals!, {reps} repetitions in {dt:.1f} s"
 
 
+def _timed_updates(one, budget_s):
+    """Repeat `one()` (returns the number of updates it performed) for about budget_s seconds -> (updates/s, reps, seconds)."""
+    one()
+    t0, n, reps = time.perf_counter(), 0, 0
+    while time.perf_counter() - t0 < budget_s:
+        n += one()
+        reps += 1
+    dt = time.perf_counter() - t0
+    return n / dt, reps, dt
+
+
+def cpu_baseline_workload(workload, budget_s=12.0):
+    """The oracle port (explicit Signal graph, sequential update_marginals!, 1 core) on a BOUNDED sample of the same
+    workload: the full-size graphs of configs 3-5 cannot be built on the host, so the sample is a reduced
+    instance of the same family, rules and protocol; the size is stated in the returned text."""
+    if workload in ("gauss_chains", "chain1k"):
+        return cpu_baseline_chain(1000 if workload == "chain1k" else 1024, budget_s)
+    from tests import models
+    from tests._pkg import ORACLE_LIB, pkg
+
+    api = pkg.CApi(ORACLE_LIB, "cxo_")
+    rng = np.random.Generator(np.random.PCG64(1234))
+    if workload == "potts_grid":
+        H = W = 64
+        K = 16
+        e, pix, un, pair = models.make_grid_model(H, W, K, 0.7, api, rule="potts", link=True)
+        vs = [v for row in pix for v in row]
+        models.protocol_b_init(e, vs, K)
+        usig = [pkg.get_connection_message_to_variable(e, pix[i][j], un[i][j]) for i in range(H) for j in range(W)]
+        unary = rng.dirichlet(np.ones(K), size=H * W)
+        v, reps, dt = _timed_updates(lambda: models.protocol_b_sweep(e, vs, usig, unary, schedule="seq").updates, budget_s)
+        return v, f"Potts grid {H}x{W}, K={K}, protocol-B sweeps on the explicit Signal graph, {reps} sweeps in {dt:.1f} s"
+    if workload in ("hmm64", "hmm512"):
+        K, M = (512, 32) if workload == "hmm512" else (64, 32)
+        T = 64 if K == 512 else 512
+        A = rng.dirichlet(np.ones(K), size=K)
+        E = rng.dirichlet(np.ones(K), size=M).T * K
+        e, z, y, prior, em, tr = models.make_hmm_model(T, K, M, A, E, api)
+        obs = rng.integers(0, M, size=T)
+
+        def one():
+            models.hmm_set_data(e, z, y, prior, em, obs, K)
+            return pkg.update_marginals(e, z, schedule="seq").updates
+
+        v, reps, dt = _timed_updates(one, budget_s)
+        return v, f"1 HMM chain, K={K}, M={M}, T={T}, explicit Signal graph, sequential update_marginals!, {reps} repetitions in {dt:.1f} s"
+    if workload in ("powerlaw", "powerlaw_engine"):
+        n = 20000
+        e, vs, un, pair, unary, tables, ttype = models.make_powerlaw_model(n, 2 * n, 8, api)
+        models.protocol_b_init(e, vs, 8)
+        usig = [pkg.get_connection_message_to_variable(e, vs[i], un[i]) for i in range(n)]
+        v, reps, dt = _timed_updates(lambda: models.protocol_b_sweep(e, vs, usig, unary, schedule="seq").updates, budget_s)
+        return v, (f"Chung-Lu power-law graph, {n} variables, {2 * n} pairwise factors, K=8, protocol-B sweeps on the explicit Signal "
+                   f"graph, {reps} sweeps in {dt:.1f} s")
+    raise ValueError(workload)
+
+
 def _ref_worker(args):
-    T, budget = args
-    v, _ = cpu_baseline_chain(T, budget)
+    workload, budget = args
+    v, _ = cpu_baseline_workload(workload, budget)
     return v
 
 
@@ -204,18 +261,18 @@ def run_reference(args):
 
     subprocess.run(["make", "-C", str(ROOT / "oracle")], check=True, stdout=subprocess.DEVNULL)
     cores = os.cpu_count() or 1
-    T = 1000 if args.workload == "chain1k" else 1024
     per_step_budget = max(1.0, min(10.0, 60.0 / max(1, args.steps + args.warmup)))
+    _, what = cpu_baseline_workload(args.workload, 0.2)  # the sample's description (and a warm build of the graph code paths)
     vals = []
     with mp.get_context("spawn").Pool(cores) as pool:
         for s in range(args.warmup + args.steps):
             t0 = time.perf_counter()
-            v = sum(pool.map(_ref_worker, [(T, per_step_budget)] * cores))
+            v = sum(pool.map(_ref_worker, [(args.workload, per_step_budget)] * cores))
             if s >= args.warmup:
                 vals.append((v, time.perf_counter() - t0))
     value = statistics.mean(v for v, _ in vals)
-    sample = (f"{cores} independent replicas (one per core; the reference is single-threaded), each: 1 chain x T={T} explicit "
-              f"Signal graph, sequential update_marginals!, ~{per_step_budget:.1f} s per step")
+    sample = (f"{cores} independent replicas (one per core; the reference is single-threaded), each: {what.split(', explicit')[0]}, explicit "
+              f"Signal graph, sequential schedule, ~{per_step_budget:.1f} s per step")
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * statistics.mean(t for _, t in vals), "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
@@ -658,7 +715,7 @@ def main():
             pass
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         subprocess.run(["make", "-C", str(ROOT / "oracle")], check=True, stdout=subprocess.DEVNULL)
-        v, sample = cpu_baseline_chain(1000 if args.workload == "chain1k" else 1024)
+        v, sample = cpu_baseline_workload(args.workload)
         line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": 1, "kind": "port", "sample": sample,
                                 "host_cores_available": os.cpu_count()}
     if rank == 0:
