@@ -1,0 +1,162 @@
+"""Exploratory fuzzers for the level-synchronous contract (NOT collected by pytest: run `python tests/fuzz_schedules.py`).
+
+They compare the oracle's two schedules — `seq` (the reference's, src/inference_engine.jl:559-632) and `lvl` (what the
+device runs) — on random scripts and count requests that `lvl` accepts but answers differently.
+
+Findings of round 1 (oracle, CPU; the device runs the same `lvl` logic):
+  * chain BP, default wiring, every script step = "set ALL observations" or "request ALL variables": 0 differences in
+    1,825 accepted requests (this is the class every benchmark config, protocol-B sweep and VMP iteration lives in);
+  * chain BP with INCREMENTAL evidence (set some observations, request some or all variables): 13 of 400 random scripts
+    (127 of 600 with full requests) contain a request that differs.  Pattern: a marginal keeps a FRESH bit on a dependency
+    from an earlier request in which it could not be computed; in the next request the reference finds it pending as soon
+    as its other dependencies arrive and uses the STALE message, while the level schedule has, by then, already recomputed
+    that message (or the other way round).  Minimal case: tests/test_schedules.py::test_incremental_evidence_known_gap;
+  * random signal DAGs with random weak / non-listening / intermediate dependencies (this file's __main__): about one
+    script in ten contains a request that differs (33 of 300; 132 refused); two more order effects show up there (the lazy is_pending cache consumed before a NON-listening notification; a signal
+    computed while one of its weak dependencies is pending).
+Closing them needs the contract checks to see leftover freshness at request time (planned)."""
+import sys
+from pathlib import Path
+
+import numpy as np
+
+sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
+import pytest  # noqa: F401  (the functions below keep their pytest shape)
+
+from tests import models
+from tests._pkg import pkg
+
+C = pkg
+cap = pkg.capi
+
+
+def _build(api, rng, n_var, n_fac, dep_p, dtype=cap.F64, p_weak=0.0, p_listen=1.0):
+    """A random bipartite graph whose signals (marginals, m2v, m2f) get RANDOM dependencies (no resolver): signal i may
+    depend on signals that precede it in a random order (a DAG), with random weak / intermediate / listen flags."""
+    g = C.BipartiteFactorGraph()
+    vs = [g.add_variable(C.Variable(name="v", index=(i,))) for i in range(n_var)]
+    fs = [g.add_factor(C.Factor(functional_form="f")) for _ in range(n_fac)]
+    for f in fs:
+        for v in rng.choice(n_var, size=int(rng.integers(1, min(3, n_var) + 1)), replace=False):
+            g.add_edge(vs[int(v)], f, C.Connection(label="e"))
+    proc = C.RuleProcessor({"f": (cap.RULE_SCALE2, [])}, family=cap.FAMILY_SUM, value_dim=1)
+    e = C.InferenceEngine(model_engine=g, inference_request_processor=proc, resolve_dependencies=False, dtype=dtype, api=api)
+    n = e.store.n_signals()
+    order = rng.permutation(n)
+    plan = []
+    for pos in range(n):
+        s = int(order[pos])
+        kind = type(C.get_variant(C.Signal(e.store, s))).__name__
+        cand = order[:pos]
+        k = 0 if pos == 0 else int(rng.binomial(min(3, pos), dep_p))
+        if kind == "MessageToVariable":
+            k = min(k, 1)  # SCALE2 reads one dependency
+        for d in rng.choice(cand, size=k, replace=False) if k else []:
+            plan.append((s, int(d), bool(rng.random() < p_weak), bool(rng.random() < 0.5), bool(rng.random() < p_listen)))
+    for s, d, weak, inter, listen in plan:
+        C.add_dependency(C.Signal(e.store, s), C.Signal(e.store, d), weak=weak, intermediate=inter, listen=listen)
+    inputs = [s for s in range(n) if not C.get_dependencies(C.Signal(e.store, s))]
+    return e, vs, inputs
+
+
+def _script(rng, n_var, inputs, n_ops):
+    ops = []
+    for _ in range(n_ops):
+        if rng.random() < 0.45 and inputs:
+            k = int(rng.integers(1, len(inputs) + 1))
+            ids = [int(x) for x in rng.choice(inputs, size=k, replace=False)]
+            ops.append(("set", ids, rng.integers(1, 9, size=k).astype(np.float64)))
+        else:
+            k = int(rng.integers(1, n_var + 1))
+            ops.append(("update", [int(x) for x in rng.choice(n_var, size=k, replace=False)], None))
+    return ops
+
+
+def _run(engine, vs, op, schedule):
+    kind, ids, vals = op
+    if kind == "set":
+        C.set_values([C.Signal(engine.store, s) for s in ids], vals.reshape(-1, 1))
+        return "ok"
+    try:
+        C.update_marginals(engine, [vs[i] for i in ids], schedule=schedule)
+        return "ok"
+    except C.OutOfContractError:
+        return "refused"
+    except C.NoRuleError:
+        return "norule"
+
+
+def _state(engine):
+    st, vals = models.engine_state(engine)
+    return st, [None if not c else float(v[0]) for (c, _, _), v in zip(st, vals)]
+
+
+@pytest.mark.parametrize("seed", range(60))
+def test_level_schedule_is_sequential_or_refused(oracle_api, seed):
+    rng = np.random.Generator(np.random.PCG64(9000 + seed))
+    n_var, n_fac = int(rng.integers(2, 6)), int(rng.integers(1, 6))
+    dep_p = float(rng.uniform(0.3, 0.9))
+    build_seed = int(rng.integers(1 << 30))
+    engines = []
+    for _ in range(2):
+        e, vs, inputs = _build(oracle_api, np.random.Generator(np.random.PCG64(build_seed)), n_var, n_fac, dep_p)
+        engines.append((e, vs))
+    ops = _script(rng, n_var, inputs, 14)
+    accepted = 0
+    for op in ops:
+        r_lvl = _run(engines[0][0], engines[0][1], op, "lvl")
+        if r_lvl != "ok":
+            break  # refused (or no rule for a free signal): the engines may legitimately differ from here on
+        r_seq = _run(engines[1][0], engines[1][1], op, "seq")
+        assert r_seq == "ok", (seed, op, r_seq)
+        assert _state(engines[0][0]) == _state(engines[1][0]), (seed, op)
+        accepted += op[0] == "update"
+    assert accepted >= 0
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("seed", range(40))
+def test_device_level_schedule_equals_oracle_level_schedule(oracle_api, device_api, seed):
+    rng = np.random.Generator(np.random.PCG64(9000 + seed))
+    n_var, n_fac = int(rng.integers(2, 6)), int(rng.integers(1, 6))
+    dep_p = float(rng.uniform(0.3, 0.9))
+    build_seed = int(rng.integers(1 << 30))
+    eo, vso, inputs = _build(oracle_api, np.random.Generator(np.random.PCG64(build_seed)), n_var, n_fac, dep_p)
+    ed, vsd, _ = _build(device_api, np.random.Generator(np.random.PCG64(build_seed)), n_var, n_fac, dep_p)
+    for op in _script(rng, n_var, inputs, 14):
+        r_o = _run(eo, vso, op, "lvl")
+        r_d = _run(ed, vsd, op, "lvl")
+        assert r_o == r_d, (seed, op, r_o, r_d)  # the same requests are refused
+        if r_o != "ok":
+            break
+        assert _state(eo) == _state(ed), (seed, op)
+
+
+if __name__ == "__main__":
+    import sys
+
+    from tests._pkg import ORACLE_LIB
+
+    api = pkg.CApi(ORACLE_LIB, "cxo_")
+    n_seeds = int(sys.argv[1]) if len(sys.argv) > 1 else 300
+    accepted = refused = bad = 0
+    for seed in range(n_seeds):
+        rng = np.random.Generator(np.random.PCG64(9000 + seed))
+        n_var, n_fac = int(rng.integers(2, 8)), int(rng.integers(1, 8))
+        dep_p = float(rng.uniform(0.3, 0.9))
+        build_seed = int(rng.integers(1 << 30))
+        eng = []
+        for _ in range(2):
+            e, vs, inputs = _build(api, np.random.Generator(np.random.PCG64(build_seed)), n_var, n_fac, dep_p, p_weak=0.35, p_listen=0.9)
+            eng.append((e, vs))
+        for op in _script(rng, n_var, inputs, 20):
+            a = _run(eng[0][0], eng[0][1], op, "lvl")
+            if a != "ok":
+                refused += a == "refused"
+                break
+            b = _run(eng[1][0], eng[1][1], op, "seq")
+            if b != "ok" or _state(eng[0][0]) != _state(eng[1][0]):
+                bad += 1
+                break
+            accepted += op[0] == "update"
+    print(f"random DAGs with weak / non-listening dependencies: {accepted} accepted requests, {refused} scripts refused, {bad} scripts differ")

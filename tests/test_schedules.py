@@ -152,3 +152,48 @@ def test_naive_loopy_protocol_is_out_of_contract_or_equal(oracle_api):
     except C.OutOfContractError:
         return
     _same_state(e_seq, e_lvl)
+
+
+# ---- random scripts: what is guaranteed, and the one known gap ----------------------------------------------------------------
+def _chain_state(e):
+    st, vals = models.engine_state(e)
+    return st, [None if not c else tuple(np.round(v, 12)) for (c, _, _), v in zip(st, vals)]
+
+
+@pytest.mark.parametrize("seed", range(25))
+def test_random_scripts_of_full_updates_and_full_requests(oracle_api, seed):
+    """Every step either sets ALL observations (new values) or requests ALL variables, in random order and number: the
+    level-synchronous schedule leaves exactly the sequential schedule's state (values, pending flags, nibbles)."""
+    rng = np.random.Generator(np.random.PCG64(777 + seed))
+    T = int(rng.integers(3, 10))
+    eng = [models.make_ssm_model(T, oracle_api, form="canon") for _ in range(2)]
+    for _ in range(12):
+        if rng.random() < 0.5:
+            vals = np.stack([rng.standard_normal(T), np.zeros(T)], axis=1)
+            for (e, x, y, lik, tr) in eng:
+                C.set_values([C.get_connection_message_to_factor(e, y[i], lik[i]) for i in range(T)], vals)
+        else:
+            for (e, x, y, lik, tr), schedule in zip(eng, ("lvl", "seq")):
+                C.update_marginals(e, x, schedule=schedule)
+            assert _chain_state(eng[0][0]) == _chain_state(eng[1][0])
+
+
+@pytest.mark.xfail(strict=True, reason="known gap: leftover freshness from a request that could not complete (DESIGN.md section 7)")
+def test_incremental_evidence_known_gap(oracle_api):
+    """The smallest script on which the level schedule answers differently from the reference (found by
+    tests/fuzz_schedules.py): the first request runs while y_0 has no value, so marg(x_0) and marg(x_1) cannot be computed
+    and keep FRESH bits on the backward messages; after all observations are set, the reference finds those marginals
+    pending as soon as their other dependencies arrive and computes them from the STALE backward messages (marg(x_1) =
+    (2.0, 5.5)), whereas the level schedule has recomputed the backward messages by then ((2.0, 6.0): the fully updated
+    answer). Parity with the reference is what counts; this test flips when the contract check for leftover freshness lands."""
+    T = 3
+    out = {}
+    for schedule in ("lvl", "seq"):
+        e, x, y, lik, tr = models.make_ssm_model(T, oracle_api, form="canon")
+        sig = [C.get_connection_message_to_factor(e, y[i], lik[i]) for i in range(T)]
+        C.set_values(sig[1:], np.array([[2.0, 0.0], [2.0, 0.0]]))
+        C.update_marginals(e, x, schedule=schedule)
+        C.set_values(sig, np.array([[3.0, 0.0]] * 3))
+        C.update_marginals(e, x, schedule=schedule)
+        out[schedule] = C.get_values([C.get_variable_marginal(C.get_variable(e, v)) for v in x])
+    assert np.array_equal(out["lvl"], out["seq"])
