@@ -23,7 +23,7 @@ unsigned long long g_kernel_launches = 0;
 
 constexpr uint64_t ALL_W = 0x2222222222222222ull, ALL_C = 0x4444444444444444ull, ALL_F = 0x8888888888888888ull,
                    PASS = 0x1111111111111111ull;
-constexpr int ERR_INDEPENDENCE = 1, ERR_LISTENER_DONE = 2, ERR_RULE_ARG = 4, ERR_WEAK_BENEATH_DONE = 16;  // 8 = ERR_NO_RULE_KEY
+constexpr int ERR_INDEPENDENCE = 1, ERR_LISTENER_DONE = 2, ERR_RULE_ARG = 4, ERR_WEAK_BENEATH_DONE = 16, ERR_LEFTOVER_FRESH = 32;  // 8 = ERR_NO_RULE_KEY
 constexpr uint32_t PROBE_BIT = 0x80000000u;  // breadth-first list entry: the signal is only probed (see bfs_visit)
 constexpr int KEY_COMBINE = 0;  // dense rule keys: 0 = family reduce, 1..n_types = m2v of a factor type, n_types+1 = no rule
 
@@ -95,6 +95,23 @@ __global__ void k_request(View e, const uint32_t* req_marg, const uint32_t* link
     } else if (i < n + n_links) {
         uint32_t d = link_ids[i - n];
         e.props[d] = (uint8_t)((e.props[d] & P_COMPUTED) | P_PP);
+    }
+}
+
+// Contract check at request time (after k_request): a requested marginal that is not pending must not hold a FRESH bit on a
+// computed, non-input dependency - leftover freshness of an earlier request that could not complete makes the reference's
+// answer depend on the order in which it visits the variables (see the oracle's update_lvl). Read-only.
+__global__ void k_request_check(View e, const uint32_t* req_marg, uint32_t n) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint32_t m = req_marg[i];
+    const uint8_t p = e.props[m];
+    if ((p & P_P) || ((p & P_PP) && criteria(e, m))) return;
+    const uint32_t off = e.dep_off[m], nd = e.dep_off[m + 1] - off, noff = e.nib_off[m];
+    for (uint32_t k = 0; k < nd; ++k) {
+        const uint32_t nibble = (uint32_t)(e.nib[noff + (k >> 4)] >> ((k & 15) << 2)) & 0xF;
+        const uint32_t d = e.dep_ids[off + k];
+        if ((nibble & CXB_NIB_FRESH) && e.dep_off[d + 1] > e.dep_off[d]) atomicOr(e.err_flag, ERR_LEFTOVER_FRESH);
     }
 }
 
@@ -564,6 +581,10 @@ __global__ void __launch_bounds__(1024) k_update_resident(View e, T* __restrict_
     __syncthreads();
     uint32_t lvl = a.lvl_epoch0;
     long long levels = 0, updates = 0, fin[2] = {0, 0};
+    if (*(volatile int*)e.err_flag) {  // refused at request time (k_request_check): nothing is computed
+        if (tid == 0) a.out[4] = lvl;
+        return;
+    }
 
     // the members of the current level (per-key segments of the frontier buffer): independence, rules, side effects
     auto run_level = [&](int check_mode) {
@@ -1255,6 +1276,9 @@ struct DeviceEngine {
         }
         if (f & ERR_INDEPENDENCE)
             err = "level-synchronous schedule out of contract: frontier member depends on another member";
+        else if (f & ERR_LEFTOVER_FRESH)
+            err = "level-synchronous schedule out of contract: a requested marginal holds leftover freshness from an earlier, incomplete "
+                  "request (order-dependent in the reference)";
         else if (f & ERR_WEAK_BENEATH_DONE)
             err = "level-synchronous schedule out of contract: a pending weak dependency lies beneath a signal already computed in "
                   "this request (the reference would recompute that signal: order-dependent)";
@@ -1492,7 +1516,9 @@ struct DeviceEngine {
         int32_t st = request(n, ids);
         if (st) return st;
         CXB_CUDA(cudaMemsetAsync(d_kind_count.p, 0, 8 * sizeof(unsigned long long), stream));
+        if (n_req) CXB_LAUNCH(k_request_check, cdiv(n_req, 256), 256, 0, stream, view(), d_req_marg.p, n_req);
         if (resident_ok()) return update_resident(launches0);
+        if ((st = check_flags())) return st;  // refused at request time: nothing is traversed or computed
         int64_t level = 0;
         while (n_req) {
             if ((st = find_frontier(true, true))) return st;

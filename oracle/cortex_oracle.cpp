@@ -734,6 +734,21 @@ struct Oracle {
         reset_stats();
         int32_t st = request(n, ids);
         if (st) return st;
+        // Contract check at request time: a requested marginal that is NOT pending must not hold a FRESH bit on a computed
+        // (non-input) dependency. Such leftover freshness comes from an earlier request that could not complete (missing
+        // evidence); with it the reference finds the marginal pending as soon as its remaining dependencies arrive and uses
+        // the stale message, which depends on the order in which the variables are visited (Gauss-Seidel) - the level
+        // schedule advances all variables at once and would answer differently. Refused before anything is computed.
+        for (int64_t i = 0; i < n; ++i) {
+            const Sig& m = sig[req_marg[i]];
+            if (m.p || (m.pp && criteria(m))) continue;
+            for (int64_t k = 0; k < m.ndeps; ++k)
+                if (nib(m, k, MASK_F) && sig[m.deps[k]].ndeps > 0) {
+                    err = "level-synchronous schedule out of contract: a requested marginal holds leftover freshness from an earlier, "
+                          "incomplete request (order-dependent in the reference)";
+                    return CXB_ERR_OUT_OF_CONTRACT;
+                }
+        }
         std::vector<uint8_t> done(sig.size(), 0), inF(sig.size(), 0);
         int64_t level = 0;
         for (;;) {

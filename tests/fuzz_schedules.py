@@ -4,17 +4,17 @@ They compare the oracle's two schedules — `seq` (the reference's, src/inferenc
 device runs) — on random scripts and count requests that `lvl` accepts but answers differently.
 
 Findings of round 1 (oracle, CPU; the device runs the same `lvl` logic):
-  * chain BP, default wiring, every script step = "set ALL observations" or "request ALL variables": 0 differences in
-    1,825 accepted requests (this is the class every benchmark config, protocol-B sweep and VMP iteration lives in);
-  * chain BP with INCREMENTAL evidence (set some observations, request some or all variables): 13 of 400 random scripts
-    (127 of 600 with full requests) contain a request that differs.  Pattern: a marginal keeps a FRESH bit on a dependency
-    from an earlier request in which it could not be computed; in the next request the reference finds it pending as soon
-    as its other dependencies arrive and uses the STALE message, while the level schedule has, by then, already recomputed
-    that message (or the other way round).  Minimal case: tests/test_schedules.py::test_incremental_evidence_known_gap;
+  * chain BP, default wiring, scripts of "set ALL observations" / "request ALL variables": 0 differences;
+  * chain BP with INCREMENTAL evidence (set some observations, request some or all variables): BEFORE the request-time
+    leftover-freshness check 13 of 400 random scripts (127 of 600 with full requests) contained a request that differed
+    (a marginal keeps a FRESH bit on a message from an earlier request in which it could not be computed; the reference
+    then uses the stale message, the level schedule the recomputed one).  WITH the check: 0 differences in 1,000 scripts
+    (tests/test_schedules.py::test_incremental_evidence_with_leftover_freshness_is_refused is the minimal case);
   * random signal DAGs with random weak / non-listening / intermediate dependencies (this file's __main__): about one
-    script in ten contains a request that differs (33 of 300; 132 refused); two more order effects show up there (the lazy is_pending cache consumed before a NON-listening notification; a signal
-    computed while one of its weak dependencies is pending).
-Closing them needs the contract checks to see leftover freshness at request time (planned)."""
+    script in ten still contains an accepted request that differs; two more order effects show up there (the lazy
+    is_pending cache consumed before a NON-listening notification; a signal computed while one of its weak dependencies
+    is pending).  Open (DESIGN.md sections 2 and 7).
+"""
 import sys
 from pathlib import Path
 

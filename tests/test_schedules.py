@@ -178,22 +178,54 @@ def test_random_scripts_of_full_updates_and_full_requests(oracle_api, seed):
             assert _chain_state(eng[0][0]) == _chain_state(eng[1][0])
 
 
-@pytest.mark.xfail(strict=True, reason="known gap: leftover freshness from a request that could not complete (DESIGN.md section 7)")
-def test_incremental_evidence_known_gap(oracle_api):
-    """The smallest script on which the level schedule answers differently from the reference (found by
-    tests/fuzz_schedules.py): the first request runs while y_0 has no value, so marg(x_0) and marg(x_1) cannot be computed
-    and keep FRESH bits on the backward messages; after all observations are set, the reference finds those marginals
-    pending as soon as their other dependencies arrive and computes them from the STALE backward messages (marg(x_1) =
-    (2.0, 5.5)), whereas the level schedule has recomputed the backward messages by then ((2.0, 6.0): the fully updated
-    answer). Parity with the reference is what counts; this test flips when the contract check for leftover freshness lands."""
+def test_incremental_evidence_with_leftover_freshness_is_refused(backend):
+    """The smallest script on which a level schedule WITHOUT the request-time check answered differently from the
+    reference (found by tests/fuzz_schedules.py): the first request runs while y_0 has no value, so marg(x_0) and
+    marg(x_1) cannot be computed and keep FRESH bits on the backward messages; after all observations are set, the
+    reference finds those marginals pending as soon as their other dependencies arrive and computes them from the STALE
+    backward messages (marg(x_1) = (2.0, 5.5)), whereas advancing all variables at once recomputes the backward messages
+    first ((2.0, 6.0)). The answer depends on the visiting order, so the request is refused - by the oracle's level
+    schedule and by the device alike - before anything is computed; the sequential oracle shows the reference's answer."""
     T = 3
-    out = {}
-    for schedule in ("lvl", "seq"):
-        e, x, y, lik, tr = models.make_ssm_model(T, oracle_api, form="canon")
-        sig = [C.get_connection_message_to_factor(e, y[i], lik[i]) for i in range(T)]
-        C.set_values(sig[1:], np.array([[2.0, 0.0], [2.0, 0.0]]))
-        C.update_marginals(e, x, schedule=schedule)
-        C.set_values(sig, np.array([[3.0, 0.0]] * 3))
-        C.update_marginals(e, x, schedule=schedule)
-        out[schedule] = C.get_values([C.get_variable_marginal(C.get_variable(e, v)) for v in x])
-    assert np.array_equal(out["lvl"], out["seq"])
+    e, x, y, lik, tr = models.make_ssm_model(T, backend, form="canon")
+    sig = [C.get_connection_message_to_factor(e, y[i], lik[i]) for i in range(T)]
+    C.set_values(sig[1:], np.array([[2.0, 0.0], [2.0, 0.0]]))
+    C.update_marginals(e, x)  # incomplete: y_0 is missing
+    C.set_values(sig, np.array([[3.0, 0.0]] * 3))
+    before = models.engine_state(e)
+    with pytest.raises(C.OutOfContractError, match="leftover freshness"):
+        C.update_marginals(e, x)
+    after = models.engine_state(e)
+    assert before[0] == after[0] and np.array_equal(before[1], after[1], equal_nan=True)  # nothing was computed
+    if not backend.is_device:
+        e2, x2, y2, lik2, _ = models.make_ssm_model(T, backend, form="canon")
+        sig2 = [C.get_connection_message_to_factor(e2, y2[i], lik2[i]) for i in range(T)]
+        C.set_values(sig2[1:], np.array([[2.0, 0.0], [2.0, 0.0]]))
+        C.update_marginals(e2, x2, schedule="seq")
+        C.set_values(sig2, np.array([[3.0, 0.0]] * 3))
+        C.update_marginals(e2, x2, schedule="seq")
+        got = C.get_values([C.get_variable_marginal(C.get_variable(e2, v)) for v in x2])
+        # canonical form (precision, precision * mean); the stale backward message shows in x_1
+        np.testing.assert_allclose(got[1], [2.0, 5.5])
+
+
+@pytest.mark.parametrize("seed", range(20))
+def test_random_scripts_of_incremental_evidence_are_sequential_or_refused(oracle_api, seed):
+    """Random scripts that set SOME observations and request SOME variables: every request the level schedule accepts leaves
+    the sequential schedule's state; the others are refused."""
+    rng = np.random.Generator(np.random.PCG64(777 + seed))
+    T = int(rng.integers(3, 10))
+    eng = [models.make_ssm_model(T, oracle_api, form="canon") for _ in range(2)]
+    for _ in range(12):
+        ids = [int(i) for i in rng.choice(T, size=int(rng.integers(1, T + 1)), replace=False)]
+        if rng.random() < 0.5:
+            vals = np.stack([rng.standard_normal(len(ids)), np.zeros(len(ids))], axis=1)
+            for (e, x, y, lik, tr) in eng:
+                C.set_values([C.get_connection_message_to_factor(e, y[i], lik[i]) for i in ids], vals)
+        else:
+            try:
+                C.update_marginals(eng[0][0], [eng[0][1][i] for i in ids], schedule="lvl")
+            except C.OutOfContractError:
+                return
+            C.update_marginals(eng[1][0], [eng[1][1][i] for i in ids], schedule="seq")
+            assert _chain_state(eng[0][0]) == _chain_state(eng[1][0])
