@@ -147,7 +147,7 @@ if __name__ == "__main__":
         build_seed = int(rng.integers(1 << 30))
         eng = []
         for _ in range(2):
-            e, vs, inputs = _build(api, np.random.Generator(np.random.PCG64(build_seed)), n_var, n_fac, dep_p, p_weak=0.35, p_listen=0.9)
+            e, vs, inputs = _build(api, np.random.Generator(np.random.PCG64(build_seed)), n_var, n_fac, dep_p, p_weak=float(__import__("os").environ.get("FZ_WEAK", "0.35")), p_listen=float(__import__("os").environ.get("FZ_LISTEN", "0.9")))
             eng.append((e, vs))
         for op in _script(rng, n_var, inputs, 20):
             a = _run(eng[0][0], eng[0][1], op, "lvl")
