@@ -26,6 +26,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdint>
+#include <cstdlib>
 #include <chrono>
 #include <cstring>
 #include <map>
@@ -729,6 +730,16 @@ struct Oracle {
         return CXB_OK;
     }
 
+    // Opt-in (CXO_STRICT_FRESHNESS=1) extension of the request-time check below to EVERY signal the first traversal of a
+    // request visits: not pending, yet FRESH on a strong, computed (non-input) dependency.
+    bool strict_freshness = std::getenv("CXO_STRICT_FRESHNESS") && std::atoi(std::getenv("CXO_STRICT_FRESHNESS")) != 0;
+    std::vector<uint32_t> lvl_visits;       // per level: visits that found the signal pending
+    std::vector<uint8_t> revisited_via_I;  // per level: found pending again through an intermediate slot
+    bool holds_leftover_freshness(const Sig& m) const {
+        for (int64_t k = 0; k < m.ndeps; ++k)
+            if (nib(m, k, MASK_F) && !nib(m, k, MASK_W) && sig[m.deps[k]].ndeps > 0) return true;
+        return false;
+    }
     // level-synchronous schedule, SURVEY Appendix A.5
     int32_t update_lvl(int64_t n, const int64_t* ids) {
         reset_stats();
@@ -739,9 +750,13 @@ struct Oracle {
         // evidence); with it the reference finds the marginal pending as soon as its remaining dependencies arrive and uses
         // the stale message, which depends on the order in which the variables are visited (Gauss-Seidel) - the level
         // schedule advances all variables at once and would answer differently. Refused before anything is computed.
+        std::vector<uint8_t> pending_at_request(n, 0);
         for (int64_t i = 0; i < n; ++i) {
             const Sig& m = sig[req_marg[i]];
-            if (m.p || (m.pp && criteria(m))) continue;
+            if (m.p || (m.pp && criteria(m))) {
+                pending_at_request[i] = 1;
+                continue;
+            }
             for (int64_t k = 0; k < m.ndeps; ++k)
                 if (nib(m, k, MASK_F) && sig[m.deps[k]].ndeps > 0) {
                     err = "level-synchronous schedule out of contract: a requested marginal holds leftover freshness from an earlier, "
@@ -751,17 +766,21 @@ struct Oracle {
         }
         std::vector<uint8_t> done(sig.size(), 0), inF(sig.size(), 0);
         int64_t level = 0;
+        bool stale_beneath = false, found_pending = false, work_beneath_pending = false;
         for (;;) {
             std::vector<int64_t> F;
             auto visit = [&](int64_t d) {
                 if (done[d]) return false;
                 if (is_pending(d)) {
+                    found_pending = true;
+                    ++lvl_visits[d];
                     if (!inF[d]) {
                         inF[d] = 1;
                         F.push_back(d);
                     }
                     return true;
                 }
+                if (strict_freshness && level == 0 && holds_leftover_freshness(sig[d])) stale_beneath = true;
                 return false;
             };
             // DFS identical to process_dependencies! except: never descend through `done`. The reference does descend
@@ -771,6 +790,8 @@ struct Oracle {
             // never blocks, so it can: `probe` follows the same descent rule through done signals without computing
             // anything, and a pending weak dependency found there makes the request order-dependent -> refused.
             bool weak_beneath_done = false;
+            lvl_visits.assign(sig.size(), 0);
+            revisited_via_I.assign(sig.size(), 0);
             std::vector<uint8_t> probed(sig.size(), 0);
             struct Rec {
                 Oracle* o;
@@ -794,7 +815,9 @@ struct Oracle {
                     bool any = false;
                     for (int64_t i = 0; i < o->sig[sid].ndeps; ++i) {
                         int64_t d = o->sig[sid].deps[i];
+                        const size_t visits_before = o->lvl_visits[d];
                         bool processed = f(d);
+                        if (processed && visits_before > 0 && nib(o->sig[sid], i, MASK_I)) o->revisited_via_I[d] = 1;
                         if (!processed && nib(o->sig[sid], i, MASK_I)) {
                             if (done[d]) {
                                 probe(d);
@@ -810,7 +833,21 @@ struct Oracle {
                 }
             } rec{this, done, probed, weak_beneath_done, visit};
             for (int64_t i = 0; i < n; ++i)
-                if (!ready[i]) rec.go(req_marg[i]);
+                if (!ready[i]) {
+                    found_pending = false;
+                    rec.go(req_marg[i]);
+                    if (strict_freshness && level == 0 && pending_at_request[i] && found_pending) work_beneath_pending = true;
+                }
+            if (work_beneath_pending) {
+                err = "level-synchronous schedule out of contract: a requested marginal was already pending when the request arrived and "
+                      "there is pending work beneath it (the reference gives it exactly one traversal: order-dependent)";
+                return CXB_ERR_OUT_OF_CONTRACT;
+            }
+            if (stale_beneath) {
+                err = "level-synchronous schedule out of contract: a signal reached by the request is not pending but holds leftover "
+                      "freshness from an earlier, incomplete request (order-dependent in the reference)";
+                return CXB_ERR_OUT_OF_CONTRACT;
+            }
             if (weak_beneath_done) {
                 err = "level-synchronous schedule out of contract: a pending weak dependency lies beneath a signal already computed "
                       "in this request (the reference would recompute that signal: order-dependent)";
@@ -827,6 +864,16 @@ struct Oracle {
                               std::to_string(s) + " after its listener " + std::to_string(l);
                         return CXB_ERR_OUT_OF_CONTRACT;
                     }
+            // A frontier member reached AGAIN through an intermediate slot: the reference computed it at the first visit, finds
+            // it not pending at the second and descends through it, computing whatever is pending beneath it after its listener.
+            if (strict_freshness)
+                for (int64_t s : F)
+                    for (int64_t d : sig[s].deps)
+                        if (revisited_via_I[s] && (sig[d].p || (sig[d].pp && criteria(sig[d])))) {
+                            err = "level-synchronous schedule out of contract: a pending signal has a pending dependency "
+                                  "(order-dependent in the reference): signal " + std::to_string(s) + ", dependency " + std::to_string(d);
+                            return CXB_ERR_OUT_OF_CONTRACT;
+                        }
             st = run_level(F, level);
             if (st) return st;
             for (int64_t s : F) {

@@ -229,3 +229,68 @@ def test_random_scripts_of_incremental_evidence_are_sequential_or_refused(oracle
                 return
             C.update_marginals(eng[1][0], [eng[1][1][i] for i in ids], schedule="seq")
             assert _chain_state(eng[0][0]) == _chain_state(eng[1][0])
+
+
+# ---- hand-wired signal DAGs (outside the default BP wiring): the oracle's STRICT level schedule --------------------
+# CXO_STRICT_FRESHNESS=1 (read when an oracle engine is created; off by default because the device does not implement
+# these three rules yet - DESIGN.md section 2) adds to the level schedule:
+#   (A) a signal the first traversal visits that is not pending but FRESH on a strong, computed, non-input dependency,
+#   (B) a requested marginal that was already pending when the request arrived and has pending work beneath it,
+#   (D) a frontier member found pending AGAIN through an intermediate slot while one of its dependencies is pending
+# -> refused. Scripts: tests/fuzz_schedules.py (random DAGs, strong listening dependencies).
+_STRICT_SEEDS_THAT_DIFFERED = [13, 147, 171, 180, 188]  # of the first 300 fuzzer seeds, before the strict rules
+
+
+def _fuzz_script(api, seed, n_ops=20):
+    from tests import fuzz_schedules as fz
+
+    rng = np.random.Generator(np.random.PCG64(9000 + seed))
+    n_var, n_fac = int(rng.integers(2, 8)), int(rng.integers(1, 8))
+    dep_p = float(rng.uniform(0.3, 0.9))
+    build_seed = int(rng.integers(1 << 30))
+    eng = []
+    for _ in range(2):
+        e, vs, inputs = fz._build(api, np.random.Generator(np.random.PCG64(build_seed)), n_var, n_fac, dep_p)
+        eng.append((e, vs))
+    outcome = "equal"
+    for op in fz._script(rng, n_var, inputs, n_ops):
+        a = fz._run(eng[0][0], eng[0][1], op, "lvl")
+        if a != "ok":
+            outcome = a
+            break
+        b = fz._run(eng[1][0], eng[1][1], op, "seq")
+        if b != "ok" or fz._state(eng[0][0]) != fz._state(eng[1][0]):
+            outcome = "differs"
+            break
+    return outcome
+
+
+@pytest.mark.parametrize("seed", _STRICT_SEEDS_THAT_DIFFERED)
+def test_strict_level_schedule_refuses_the_scripts_that_differed(oracle_api, monkeypatch, seed):
+    monkeypatch.delenv("CXO_STRICT_FRESHNESS", raising=False)
+    assert _fuzz_script(oracle_api, seed) == "differs"  # the default level schedule accepts them and answers differently
+    monkeypatch.setenv("CXO_STRICT_FRESHNESS", "1")
+    assert _fuzz_script(oracle_api, seed) == "refused"
+
+
+@pytest.mark.parametrize("seed", range(40))
+def test_strict_level_schedule_on_random_dags_is_sequential_or_refused(oracle_api, monkeypatch, seed):
+    monkeypatch.setenv("CXO_STRICT_FRESHNESS", "1")
+    assert _fuzz_script(oracle_api, seed) in ("equal", "refused", "norule")
+
+
+def test_strict_level_schedule_accepts_the_benchmark_protocols(oracle_api, monkeypatch):
+    """The strict rules refuse nothing the benchmark families need: protocol-B sweeps on a power-law graph with segment
+    trees and on a Potts grid, and the chain, run unchanged (and equal to the sequential schedule)."""
+    monkeypatch.setenv("CXO_STRICT_FRESHNESS", "1")
+    test_powerlaw_with_segment_trees_seq_equals_lvl(oracle_api)
+    for sched_pair in (("seq", "lvl"),):
+        engines = []
+        for sched in sched_pair:
+            e, x, y, lik, tr = models.make_ssm_model(12, oracle_api, form="canon")
+            sig = [C.get_connection_message_to_factor(e, y[i], lik[i]) for i in range(12)]
+            for k in range(3):
+                C.set_values(sig, np.array([[1.0 + k, 0.5 * i] for i in range(12)]))
+                C.update_marginals(e, x, schedule=sched)
+            engines.append(e)
+        _same_state(engines[0], engines[1])
