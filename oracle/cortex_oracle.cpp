@@ -815,9 +815,8 @@ struct Oracle {
                     bool any = false;
                     for (int64_t i = 0; i < o->sig[sid].ndeps; ++i) {
                         int64_t d = o->sig[sid].deps[i];
-                        const size_t visits_before = o->lvl_visits[d];
                         bool processed = f(d);
-                        if (processed && visits_before > 0 && nib(o->sig[sid], i, MASK_I)) o->revisited_via_I[d] = 1;
+                        if (processed && nib(o->sig[sid], i, MASK_I)) o->revisited_via_I[d] = 1;  // found pending through an I slot
                         if (!processed && nib(o->sig[sid], i, MASK_I)) {
                             if (done[d]) {
                                 probe(d);
@@ -864,12 +863,14 @@ struct Oracle {
                               std::to_string(s) + " after its listener " + std::to_string(l);
                         return CXB_ERR_OUT_OF_CONTRACT;
                     }
-            // A frontier member reached AGAIN through an intermediate slot: the reference computed it at the first visit, finds
-            // it not pending at the second and descends through it, computing whatever is pending beneath it after its listener.
+            // A frontier member reached more than once, at least once through an intermediate slot: the reference computed it at
+            // the first visit, finds it not pending at a later one and descends through it if that slot is intermediate,
+            // computing whatever is pending beneath it AFTER its listener. (Stated without the visiting order - "more than
+            // once, and some visit through an intermediate slot" - so that a breadth-first device traversal can evaluate it.)
             if (strict_freshness)
                 for (int64_t s : F)
                     for (int64_t d : sig[s].deps)
-                        if (revisited_via_I[s] && (sig[d].p || (sig[d].pp && criteria(sig[d])))) {
+                        if (revisited_via_I[s] && lvl_visits[s] > 1 && (sig[d].p || (sig[d].pp && criteria(sig[d])))) {
                             err = "level-synchronous schedule out of contract: a pending signal has a pending dependency "
                                   "(order-dependent in the reference): signal " + std::to_string(s) + ", dependency " + std::to_string(d);
                             return CXB_ERR_OUT_OF_CONTRACT;

@@ -236,7 +236,8 @@ def test_random_scripts_of_incremental_evidence_are_sequential_or_refused(oracle
 # these three rules yet - DESIGN.md section 2) adds to the level schedule:
 #   (A) a signal the first traversal visits that is not pending but FRESH on a strong, computed, non-input dependency,
 #   (B) a requested marginal that was already pending when the request arrived and has pending work beneath it,
-#   (D) a frontier member found pending AGAIN through an intermediate slot while one of its dependencies is pending
+#   (D) a frontier member found pending more than once, some visit through an intermediate slot, while one of its
+#       dependencies is pending
 # -> refused. Scripts: tests/fuzz_schedules.py (random DAGs, strong listening dependencies).
 _STRICT_SEEDS_THAT_DIFFERED = [13, 147, 171, 180, 188]  # of the first 300 fuzzer seeds, before the strict rules
 
