@@ -32,6 +32,7 @@
 #include <map>
 #include <string>
 #include <unordered_map>
+#include <unordered_set>
 #include <vector>
 
 #include "../include/cortex_b200.h"
@@ -191,6 +192,11 @@ struct Oracle {
                     nib_set(L, i, MASK_C);
                     break;
                 }
+            }
+            // strict rule E: signals that received a NON-listening notification during a level (checked after the level)
+            if (!s.listenmask[k] && lvl_request > 0) {
+                nl_notified.push_back(s.listeners[k]);
+                nl_touched.insert(s.listeners[k]);
             }
         }
     }
@@ -733,6 +739,10 @@ struct Oracle {
     // Opt-in (CXO_STRICT_FRESHNESS=1) extension of the request-time check below to EVERY signal the first traversal of a
     // request visits: not pending, yet FRESH on a strong, computed (non-input) dependency.
     bool strict_freshness = std::getenv("CXO_STRICT_FRESHNESS") && std::atoi(std::getenv("CXO_STRICT_FRESHNESS")) != 0;
+    int64_t lvl_request = 0;      // > 0 while a strict level-schedule request runs (its serial number)
+    int64_t lvl_serial = 0;
+    std::vector<int64_t> nl_notified;     // ... during the current level
+    std::unordered_set<int64_t> nl_touched;  // ... during the current request
     std::vector<uint32_t> lvl_visits;       // per level: visits that found the signal pending
     std::vector<uint8_t> revisited_via_I;  // per level: found pending again through an intermediate slot
     bool holds_leftover_freshness(const Sig& m) const {
@@ -745,6 +755,13 @@ struct Oracle {
         reset_stats();
         int32_t st = request(n, ids);
         if (st) return st;
+        struct Scope {  // strict rule E is armed for the duration of this request only
+            Oracle* o;
+            ~Scope() { o->lvl_request = 0; }
+        } scope{this};
+        lvl_request = strict_freshness ? ++lvl_serial : 0;
+        nl_notified.clear();
+        nl_touched.clear();
         // Contract check at request time: a requested marginal that is NOT pending must not hold a FRESH bit on a computed
         // (non-input) dependency. Such leftover freshness comes from an earlier request that could not complete (missing
         // evidence); with it the reference finds the marginal pending as soon as its remaining dependencies arrive and uses
@@ -875,8 +892,27 @@ struct Oracle {
                                   "(order-dependent in the reference): signal " + std::to_string(s) + ", dependency " + std::to_string(d);
                             return CXB_ERR_OUT_OF_CONTRACT;
                         }
+            // strict rule E, second half: a signal that received a non-listening notification EARLIER in this request becomes a
+            // frontier member - in the reference the notifications arrive in DFS order, not level by level, and a non-listening
+            // one that arrives last leaves the signal not pending
+            for (int64_t s : F)
+                if (nl_touched.count(s)) {
+                    err = "level-synchronous schedule out of contract: signal " + std::to_string(s) + " became pending after a "
+                          "non-listening notification of this request (order-dependent in the reference)";
+                    return CXB_ERR_OUT_OF_CONTRACT;
+                }
             st = run_level(F, level);
             if (st) return st;
+            // strict rule E: a NON-listening notification of this level left a signal with complete criteria. Whether the
+            // reference finds that signal pending depends on whether a listening notification armed its lazy flag and an
+            // is_pending call consumed it in between, i.e. on the order inside what is one level here.
+            for (int64_t l : nl_notified)
+                if (!done[l] && !inF[l] && criteria(sig[l])) {
+                    err = "level-synchronous schedule out of contract: a non-listening dependency completed the pending criteria of "
+                          "signal " + std::to_string(l) + " (in the reference its pending state depends on the order of this level)";
+                    return CXB_ERR_OUT_OF_CONTRACT;
+                }
+            nl_notified.clear();
             for (int64_t s : F) {
                 done[s] = 1;
                 inF[s] = 0;

@@ -14,9 +14,13 @@ Findings of round 1 (oracle, CPU; the device runs the same `lvl` logic):
     script in ten still contains an accepted request that differs; two more order effects show up there (the lazy
     is_pending cache consumed before a NON-listening notification; a signal computed while one of its weak dependencies
     is pending).  Open (DESIGN.md sections 2 and 7).
-  * the oracle's STRICT level schedule (CXO_STRICT_FRESHNESS=1, three more refusal rules, oracle only so far - see
-    tests/test_schedules.py and DESIGN.md section 2): strong listening dependencies 20 -> 2 differing scripts of 1,500
-    (0 of the first 300; 986 instead of 865 scripts refused); 35 % weak 9 -> 5 of 300; 10 % non-listening 17 -> 12.
+  * the oracle's STRICT level schedule (CXO_STRICT_FRESHNESS=1: refusal rules A, B, D, E, oracle only so far - see
+    tests/test_schedules.py and DESIGN.md section 2), differing scripts of 1,500 (scripts refused), default -> strict:
+        strong listening dependencies      20 -> 2    (865 -> 986)
+        10 % non-listening                114 -> 0    (870 -> 1,126)
+        35 % weak                          59 -> 25   (998 -> 1,135)
+        35 % weak and 10 % non-listening  137 -> 8    (956 -> 1,202)
+    Run: CXO_STRICT_FRESHNESS=1 FZ_WEAK=0.35 FZ_LISTEN=0.9 python tests/fuzz_schedules.py 1500
 """
 import sys
 from pathlib import Path
@@ -136,6 +140,7 @@ def test_device_level_schedule_equals_oracle_level_schedule(oracle_api, device_a
 
 
 if __name__ == "__main__":
+    import os
     import sys
 
     from tests._pkg import ORACLE_LIB
@@ -150,7 +155,8 @@ if __name__ == "__main__":
         build_seed = int(rng.integers(1 << 30))
         eng = []
         for _ in range(2):
-            e, vs, inputs = _build(api, np.random.Generator(np.random.PCG64(build_seed)), n_var, n_fac, dep_p, p_weak=float(__import__("os").environ.get("FZ_WEAK", "0.35")), p_listen=float(__import__("os").environ.get("FZ_LISTEN", "0.9")))
+            e, vs, inputs = _build(api, np.random.Generator(np.random.PCG64(build_seed)), n_var, n_fac, dep_p, p_weak=float(os.environ.get("FZ_WEAK", "0.35")),
+                                      p_listen=float(os.environ.get("FZ_LISTEN", "0.9")))
             eng.append((e, vs))
         for op in _script(rng, n_var, inputs, 20):
             a = _run(eng[0][0], eng[0][1], op, "lvl")
@@ -162,4 +168,5 @@ if __name__ == "__main__":
                 bad += 1
                 break
             accepted += op[0] == "update"
-    print(f"random DAGs with weak / non-listening dependencies: {accepted} accepted requests, {refused} scripts refused, {bad} scripts differ")
+    print(f"random DAGs (weak {os.environ.get('FZ_WEAK', '0.35')}, listening {os.environ.get('FZ_LISTEN', '0.9')}, strict "
+          f"{os.environ.get('CXO_STRICT_FRESHNESS', '0')}): {accepted} accepted requests, {refused} scripts refused, {bad} scripts differ")

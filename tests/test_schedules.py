@@ -237,12 +237,14 @@ def test_random_scripts_of_incremental_evidence_are_sequential_or_refused(oracle
 #   (A) a signal the first traversal visits that is not pending but FRESH on a strong, computed, non-input dependency,
 #   (B) a requested marginal that was already pending when the request arrived and has pending work beneath it,
 #   (D) a frontier member found pending more than once, some visit through an intermediate slot, while one of its
-#       dependencies is pending
+#       dependencies is pending,
+#   (E) a NON-listening notification that leaves a signal with complete criteria at the end of a level, or a signal that
+#       becomes a frontier member after a non-listening notification of the same request
 # -> refused. Scripts: tests/fuzz_schedules.py (random DAGs, strong listening dependencies).
 _STRICT_SEEDS_THAT_DIFFERED = [13, 147, 171, 180, 188]  # of the first 300 fuzzer seeds, before the strict rules
 
 
-def _fuzz_script(api, seed, n_ops=20):
+def _fuzz_script(api, seed, n_ops=20, p_weak=0.0, p_listen=1.0):
     from tests import fuzz_schedules as fz
 
     rng = np.random.Generator(np.random.PCG64(9000 + seed))
@@ -251,7 +253,8 @@ def _fuzz_script(api, seed, n_ops=20):
     build_seed = int(rng.integers(1 << 30))
     eng = []
     for _ in range(2):
-        e, vs, inputs = fz._build(api, np.random.Generator(np.random.PCG64(build_seed)), n_var, n_fac, dep_p)
+        e, vs, inputs = fz._build(api, np.random.Generator(np.random.PCG64(build_seed)), n_var, n_fac, dep_p, p_weak=p_weak,
+                                  p_listen=p_listen)
         eng.append((e, vs))
     outcome = "equal"
     for op in fz._script(rng, n_var, inputs, n_ops):
@@ -278,6 +281,23 @@ def test_strict_level_schedule_refuses_the_scripts_that_differed(oracle_api, mon
 def test_strict_level_schedule_on_random_dags_is_sequential_or_refused(oracle_api, monkeypatch, seed):
     monkeypatch.setenv("CXO_STRICT_FRESHNESS", "1")
     assert _fuzz_script(oracle_api, seed) in ("equal", "refused", "norule")
+
+
+_NONLISTENING_SEEDS_THAT_DIFFERED = [21, 37, 46, 56, 150, 159, 185, 216, 229, 252, 254, 281]  # 10 % non-listening dependencies
+
+
+@pytest.mark.parametrize("seed", _NONLISTENING_SEEDS_THAT_DIFFERED)
+def test_strict_level_schedule_refuses_the_non_listening_scripts_that_differed(oracle_api, monkeypatch, seed):
+    monkeypatch.delenv("CXO_STRICT_FRESHNESS", raising=False)
+    assert _fuzz_script(oracle_api, seed, p_listen=0.9) == "differs"
+    monkeypatch.setenv("CXO_STRICT_FRESHNESS", "1")
+    assert _fuzz_script(oracle_api, seed, p_listen=0.9) == "refused"
+
+
+@pytest.mark.parametrize("seed", range(300, 340))
+def test_strict_level_schedule_with_non_listening_dependencies_is_sequential_or_refused(oracle_api, monkeypatch, seed):
+    monkeypatch.setenv("CXO_STRICT_FRESHNESS", "1")
+    assert _fuzz_script(oracle_api, seed, p_listen=0.9) in ("equal", "refused", "norule")
 
 
 def test_strict_level_schedule_accepts_the_benchmark_protocols(oracle_api, monkeypatch):
