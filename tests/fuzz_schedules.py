@@ -63,6 +63,7 @@ def _build(api, rng, n_var, n_fac, dep_p, dtype=cap.F64, p_weak=0.0, p_listen=1.
     for s, d, weak, inter, listen in plan:
         C.add_dependency(C.Signal(e.store, s), C.Signal(e.store, d), weak=weak, intermediate=inter, listen=listen)
     inputs = [s for s in range(n) if not C.get_dependencies(C.Signal(e.store, s))]
+    e.fuzz_plan = plan  # (signal, dependency, weak, intermediate, listen) in add_dependency! order (tests/test_pyref_witness.py)
     return e, vs, inputs
 
 
