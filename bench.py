@@ -293,10 +293,15 @@ def workload_config(args, world):
                 "parallelism": f"row-shard x{world} + halo exchange: {getattr(args, 'halo_transport', 'n/a')}"}
     if args.workload in ("hmm64", "hmm512"):
         k = 512 if args.workload == "hmm512" else 64
-        return {"workload": f"{args.hmm_chains} HMMs per GPU, K={k}, M=32, T={args.hmm_steps} (BASELINE configs[2] K={k})",
-                "l2": "inputs exceed L2", "parallelism": f"batch-shard x{world}",
-                "e2e_result": "observations in (all T), marginals of the last min(T, 256) time steps out (the full plane is "
-                              f"{args.hmm_chains * args.hmm_steps * k * 4 / 1e9:.0f} GB; fetch any window with cxb_hmm_get_marginals)"}
+        cfg = {"workload": f"{args.hmm_chains} HMMs per GPU, K={k}, M=32, T={args.hmm_steps} (BASELINE configs[2] K={k})",
+               "l2": "inputs exceed L2", "parallelism": f"batch-shard x{world}",
+               "e2e_result": "observations in (all T), marginals of the last min(T, 256) time steps out (the full plane is "
+                             f"{args.hmm_chains * args.hmm_steps * k * 4 / 1e9:.0f} GB; fetch any window with cxb_hmm_get_marginals)"}
+        if k == 512 and args.hmm_steps < 100000:
+            cfg["T_note"] = ("BASELINE names T=1e5: at K=512 the forward and marginal planes of 1,024 chains x 1e5 steps are "
+                             "2 x 210 GB and do not fit one 180 GB GPU (SURVEY 8d), so a slice of the same recursion is timed; "
+                             "the step cost does not depend on T (one launch per time step), pass --hmm-steps to change it")
+        return cfg
     if args.workload in ("powerlaw", "powerlaw_engine"):
         eng = "fused CSR sweep engine" if args.workload == "powerlaw" else "generic reactive engine"
         return {"workload": f"Chung-Lu power-law graph, {args.pl_vars} variables, {2 * args.pl_vars} pairwise factors, K=8, "
