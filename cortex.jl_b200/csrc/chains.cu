@@ -452,7 +452,7 @@ static inline Chains* CH(cxb_chains* c) { return reinterpret_cast<Chains*>(c); }
 
 extern "C" {
 
-int32_t cxb_chains_create(int32_t device, int32_t dtype, int64_t n_chains, int64_t n_steps, cxb_chains** out) {
+int32_t cxb_chains_create(int32_t device, int32_t dtype, int64_t n_chains, int64_t n_steps, cxb_chains** out) try {
     if (!out || (dtype != CXB_F32 && dtype != CXB_F64)) return CXB_ERR_BAD_ARG;
     *out = nullptr;
     Chains* c = new Chains();
@@ -468,7 +468,7 @@ int32_t cxb_chains_create(int32_t device, int32_t dtype, int64_t n_chains, int64
     }
     *out = reinterpret_cast<cxb_chains*>(c);
     return CXB_OK;
-}
+} CXB_ABI_CATCH(CXB_ERR_INTERNAL)
 void cxb_chains_destroy(cxb_chains* c) {
     if (c) {
         cudaSetDevice(CH(c)->device);
@@ -487,30 +487,30 @@ int32_t cxb_chains_set_noise(cxb_chains* c, const double* q, const double* r) { 
         }                                                       \
     } while (0)
 
-int32_t cxb_chains_set_observations(cxb_chains* c, const void* y_host) {
+int32_t cxb_chains_set_observations(cxb_chains* c, const void* y_host) try {
     Chains* h = CH(c);
     CH_CUDA(c, cudaSetDevice(h->device));
     CH_CUDA(c, cudaMemcpyAsync(h->y.p, y_host, (size_t)h->T * h->B * h->esz(), cudaMemcpyHostToDevice, h->stream));
     CH_CUDA(c, cudaStreamSynchronize(h->stream));
     h->have_obs = true;
     return CXB_OK;
-}
-int32_t cxb_chains_set_observations_device(cxb_chains* c, const void* y_dev) {
+} CXB_ABI_CATCH(CXB_ERR_INTERNAL)
+int32_t cxb_chains_set_observations_device(cxb_chains* c, const void* y_dev) try {
     Chains* h = CH(c);
     CH_CUDA(c, cudaSetDevice(h->device));
     if (y_dev != h->y.p)
         CH_CUDA(c, cudaMemcpyAsync(h->y.p, y_dev, (size_t)h->T * h->B * h->esz(), cudaMemcpyDeviceToDevice, h->stream));
     h->have_obs = true;
     return CXB_OK;
-}
-int32_t cxb_chains_update_marginals(cxb_chains* c, int64_t* n_updates_out) {
+} CXB_ABI_CATCH(CXB_ERR_INTERNAL)
+int32_t cxb_chains_update_marginals(cxb_chains* c, int64_t* n_updates_out) try {
     Chains* h = CH(c);
     int32_t st = h->launch();
     if (st) return st;
     if (n_updates_out) *n_updates_out = h->B * (6 * h->T - 4);
     return CXB_OK;
-}
-int32_t cxb_chains_get_messages(cxb_chains* c, int32_t m, void* out_host) {
+} CXB_ABI_CATCH(CXB_ERR_INTERNAL)
+int32_t cxb_chains_get_messages(cxb_chains* c, int32_t m, void* out_host) try {
     Chains* h = CH(c);
     if (m < 0 || m > 5) {
         h->err = "message class must be 0..5";
@@ -525,7 +525,7 @@ int32_t cxb_chains_get_messages(cxb_chains* c, int32_t m, void* out_host) {
                                h->stream));
     CH_CUDA(c, cudaStreamSynchronize(h->stream));
     return CXB_OK;
-}
+} CXB_ABI_CATCH(CXB_ERR_INTERNAL)
 int32_t cxb_chains_get_marginals(cxb_chains* c, void* out_host) { return cxb_chains_get_messages(c, 5, out_host); }
 void* cxb_chains_device_ptr(cxb_chains* c, int32_t which) {
     Chains* h = CH(c);
@@ -533,15 +533,15 @@ void* cxb_chains_device_ptr(cxb_chains* c, int32_t which) {
     if (which == 6) return h->y.p;
     return nullptr;
 }
-int32_t cxb_chains_infer_host(cxb_chains* c, const void* y_host, void* marg_out, int64_t* n_updates_out) {
+int32_t cxb_chains_infer_host(cxb_chains* c, const void* y_host, void* marg_out, int64_t* n_updates_out) try {
     Chains* h = CH(c);
     int32_t st = h->infer_host(y_host, marg_out);
     if (st) return st;
     if (n_updates_out) *n_updates_out = h->B * (6 * h->T - 4);
     return CXB_OK;
-}
+} CXB_ABI_CATCH(CXB_ERR_INTERNAL)
 void* cxb_chains_stream(cxb_chains* c) { return (void*)CH(c)->stream; }
-int32_t cxb_chains_last_kernel_ms(cxb_chains* c, float* ms_out) {
+int32_t cxb_chains_last_kernel_ms(cxb_chains* c, float* ms_out) try {
     Chains* h = CH(c);
     if (!h->ran) {
         h->err = "no update has run yet";
@@ -550,10 +550,10 @@ int32_t cxb_chains_last_kernel_ms(cxb_chains* c, float* ms_out) {
     CH_CUDA(c, cudaEventSynchronize(h->ev1));
     CH_CUDA(c, cudaEventElapsedTime(ms_out, h->ev0, h->ev1));
     return CXB_OK;
-}
-int32_t cxb_chains_sync(cxb_chains* c) {
+} CXB_ABI_CATCH(CXB_ERR_INTERNAL)
+int32_t cxb_chains_sync(cxb_chains* c) try {
     CH_CUDA(c, cudaStreamSynchronize(CH(c)->stream));
     return CXB_OK;
-}
+} CXB_ABI_CATCH(CXB_ERR_INTERNAL)
 
 }  // extern "C"

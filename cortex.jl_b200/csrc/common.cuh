@@ -1,5 +1,7 @@
 // common.cuh — shared helpers of the sm_100a kernels (error handling, device buffers, launch counting).
 #pragma once
+#include <cstdio>
+#include <exception>
 #include <cuda_runtime.h>
 
 #include <cstdint>
@@ -80,5 +82,21 @@ struct HBuf {
 };
 
 inline unsigned cdiv(size_t a, size_t b) { return (unsigned)((a + b - 1) / b); }
+
+}  // namespace cxb
+
+// No C++ exception may cross the C ABI (the callers are Julia ccall / Python ctypes / C): every entry point that does host
+// allocation is a function-try-block closed by this handler. The engine's last-error text is left as it was.
+#define CXB_ABI_CATCH(ret)                                                             \
+    catch (const std::exception& ex) {                                                 \
+        fprintf(stderr, "cortex_b200: C++ exception at the ABI boundary: %s\n", ex.what()); \
+        return ret;                                                                    \
+    }                                                                                  \
+    catch (...) {                                                                      \
+        fprintf(stderr, "cortex_b200: unknown C++ exception at the ABI boundary\n");   \
+        return ret;                                                                    \
+    }
+
+namespace cxb {
 
 }  // namespace cxb

@@ -1714,7 +1714,7 @@ extern "C" {
 const char* cxb_version(void) { return "cortex_b200 0.1.0 (sm_100a)"; }
 uint64_t cxb_kernel_launches(void) { return (uint64_t)cxb::g_kernel_launches; }
 
-int32_t cxb_create(int32_t device, int32_t dtype, int32_t value_dim, int32_t family, cxb_engine** out) {
+int32_t cxb_create(int32_t device, int32_t dtype, int32_t value_dim, int32_t family, cxb_engine** out) try {
     if (!out || value_dim < 1 || (dtype != CXB_F32 && dtype != CXB_F64)) return CXB_ERR_BAD_ARG;
     *out = nullptr;
     DeviceEngine* e = new DeviceEngine();
@@ -1730,7 +1730,7 @@ int32_t cxb_create(int32_t device, int32_t dtype, int32_t value_dim, int32_t fam
     }
     *out = reinterpret_cast<cxb_engine*>(e);
     return CXB_OK;
-}
+} CXB_ABI_CATCH(CXB_ERR_INTERNAL)
 void cxb_destroy(cxb_engine* h) {
     if (h) {
         cudaSetDevice(E(h)->device);
@@ -1740,22 +1740,22 @@ void cxb_destroy(cxb_engine* h) {
 const char* cxb_last_error(cxb_engine* h) { return h ? E(h)->err.c_str() : "null handle"; }
 
 int32_t cxb_graph_build(cxb_engine* h, int64_t n_ids, const uint8_t* is_factor, const int32_t* factor_type, int64_t n_edges,
-                        const int64_t* edge_var, const int64_t* edge_fac) {
+                        const int64_t* edge_var, const int64_t* edge_fac) try {
     DeviceEngine* e = E(h);
     int32_t st = e->g.build(n_ids, is_factor, factor_type, n_edges, edge_var, edge_fac, e->err);
     e->fparam.assign((size_t)n_ids, NAN);
     e->structure_dirty = true;
     return st;
-}
-int32_t cxb_register_rule(cxb_engine* h, int32_t factor_type, int32_t rule_kind, const double* params, int64_t n_params) {
+} CXB_ABI_CATCH(CXB_ERR_INTERNAL)
+int32_t cxb_register_rule(cxb_engine* h, int32_t factor_type, int32_t rule_kind, const double* params, int64_t n_params) try {
     cxb::RuleDef r;
     r.kind = rule_kind;
     if (params && n_params > 0) r.params.assign(params, params + n_params);
     E(h)->rules[factor_type] = r;
     E(h)->rules_dirty = true;
     return CXB_OK;
-}
-int32_t cxb_set_factor_params(cxb_engine* h, int64_t n, const int64_t* factor_ids, const double* values) {
+} CXB_ABI_CATCH(CXB_ERR_INTERNAL)
+int32_t cxb_set_factor_params(cxb_engine* h, int64_t n, const int64_t* factor_ids, const double* values) try {
     DeviceEngine* e = E(h);
     for (int64_t i = 0; i < n; ++i) {
         int64_t f = factor_ids[i];
@@ -1767,8 +1767,8 @@ int32_t cxb_set_factor_params(cxb_engine* h, int64_t n, const int64_t* factor_id
     }
     e->rules_dirty = true;
     return CXB_OK;
-}
-int32_t cxb_set_variable_families(cxb_engine* h, int64_t n, const int64_t* variable_ids, const int32_t* families) {
+} CXB_ABI_CATCH(CXB_ERR_INTERNAL)
+int32_t cxb_set_variable_families(cxb_engine* h, int64_t n, const int64_t* variable_ids, const int32_t* families) try {
     DeviceEngine* e = E(h);
     for (int64_t i = 0; i < n; ++i) {
         const int64_t v = variable_ids[i];
@@ -1786,14 +1786,14 @@ int32_t cxb_set_variable_families(cxb_engine* h, int64_t n, const int64_t* varia
     if (n > 0) e->has_var_family = true;
     e->rules_dirty = true;
     return CXB_OK;
-}
-int64_t cxb_create_signal(cxb_engine* h) {
+} CXB_ABI_CATCH(CXB_ERR_INTERNAL)
+int64_t cxb_create_signal(cxb_engine* h) try {
     DeviceEngine* e = E(h);
     if (e->sync_host()) return -1;  // pull the dynamic state before growing the structure
     e->structure_dirty = true;
     return e->g.new_signal();
-}
-int32_t cxb_add_dependency(cxb_engine* h, int64_t s, int64_t d, int32_t flags) {
+} CXB_ABI_CATCH(-1)
+int32_t cxb_add_dependency(cxb_engine* h, int64_t s, int64_t d, int32_t flags) try {
     DeviceEngine* e = E(h);
     CHECK_SIG(h, s);
     CHECK_SIG(h, d);
@@ -1805,8 +1805,8 @@ int32_t cxb_add_dependency(cxb_engine* h, int64_t s, int64_t d, int32_t flags) {
                         !(flags & CXB_DEP_NO_CHECK_COMPUTED), flags & CXB_DEP_INTERMEDIATE);
     e->structure_dirty = true;
     return CXB_OK;
-}
-int32_t cxb_resolve_dependencies(cxb_engine* h, int32_t resolver) {
+} CXB_ABI_CATCH(CXB_ERR_INTERNAL)
+int32_t cxb_resolve_dependencies(cxb_engine* h, int32_t resolver) try {
     DeviceEngine* e = E(h);
     {
         int32_t st = e->sync_host();
@@ -1814,20 +1814,20 @@ int32_t cxb_resolve_dependencies(cxb_engine* h, int32_t resolver) {
     }
     e->structure_dirty = true;
     return e->g.resolve(resolver, e->err);
-}
-int32_t cxb_resolve_factor_dependencies(cxb_engine* h, int32_t resolver, int64_t factor_id) {
+} CXB_ABI_CATCH(CXB_ERR_INTERNAL)
+int32_t cxb_resolve_factor_dependencies(cxb_engine* h, int32_t resolver, int64_t factor_id) try {
     DeviceEngine* e = E(h);
     if (int32_t st = e->sync_host()) return st;
     e->structure_dirty = true;
     return e->g.resolve_one(resolver, factor_id, true, e->err);
-}
-int32_t cxb_resolve_variable_dependencies(cxb_engine* h, int32_t resolver, int64_t variable_id) {
+} CXB_ABI_CATCH(CXB_ERR_INTERNAL)
+int32_t cxb_resolve_variable_dependencies(cxb_engine* h, int32_t resolver, int64_t variable_id) try {
     DeviceEngine* e = E(h);
     if (int32_t st = e->sync_host()) return st;
     e->structure_dirty = true;
     return e->g.resolve_one(resolver, variable_id, false, e->err);
-}
-int32_t cxb_set_signal_variant(cxb_engine* h, int64_t s, int32_t kind, int64_t variable_id, int64_t factor_id) {
+} CXB_ABI_CATCH(CXB_ERR_INTERNAL)
+int32_t cxb_set_signal_variant(cxb_engine* h, int64_t s, int32_t kind, int64_t variable_id, int64_t factor_id) try {
     DeviceEngine* e = E(h);
     CHECK_SIG(h, s);
     if (kind < CXB_KIND_UNSPECIFIED || kind > CXB_KIND_JOINT) {
@@ -1845,8 +1845,8 @@ int32_t cxb_set_signal_variant(cxb_engine* h, int64_t s, int32_t kind, int64_t v
     e->g.sfac[s] = factor_id;
     e->structure_dirty = true;
     return CXB_OK;
-}
-int32_t cxb_link_signal(cxb_engine* h, int64_t v, int64_t s) {
+} CXB_ABI_CATCH(CXB_ERR_INTERNAL)
+int32_t cxb_link_signal(cxb_engine* h, int64_t v, int64_t s) try {
     DeviceEngine* e = E(h);
     CHECK_SIG(h, s);
     if (v < 0 || v >= e->g.n_ids || e->g.is_factor[v]) {
@@ -1857,16 +1857,16 @@ int32_t cxb_link_signal(cxb_engine* h, int64_t v, int64_t s) {
     e->req_uploaded = false;
     e->links_dirty = true;
     return CXB_OK;
-}
-int32_t cxb_link_signals(cxb_engine* h, int64_t n, const int64_t* vs, const int64_t* ss) {
+} CXB_ABI_CATCH(CXB_ERR_INTERNAL)
+int32_t cxb_link_signals(cxb_engine* h, int64_t n, const int64_t* vs, const int64_t* ss) try {
     for (int64_t i = 0; i < n; ++i) {
         int32_t st = cxb_link_signal(h, vs[i], ss[i]);
         if (st) return st;
     }
     return CXB_OK;
-}
+} CXB_ABI_CATCH(CXB_ERR_INTERNAL)
 int64_t cxb_n_signals(cxb_engine* h) { return E(h)->g.n_sig(); }
-int64_t cxb_signal_id(cxb_engine* h, int32_t kind, int64_t v, int64_t f) {
+int64_t cxb_signal_id(cxb_engine* h, int32_t kind, int64_t v, int64_t f) try {
     DeviceEngine* e = E(h);
     if (v < 0 || v >= e->g.n_ids || e->g.is_factor[v]) return -1;
     if (kind == CXB_KIND_MARGINAL) return e->g.marg_of[v];
@@ -1876,8 +1876,8 @@ int64_t cxb_signal_id(cxb_engine* h, int32_t kind, int64_t v, int64_t f) {
     if (kind == CXB_KIND_M2V) return e->g.m2v_of_conn(c);
     if (kind == CXB_KIND_M2F) return e->g.m2f_of_conn(c);
     return -1;
-}
-int32_t cxb_signal_info(cxb_engine* h, int64_t s, int64_t out[5]) {
+} CXB_ABI_CATCH(-1)
+int32_t cxb_signal_info(cxb_engine* h, int64_t s, int64_t out[5]) try {
     CHECK_SIG(h, s);
     const cxb::HostGraph& g = E(h)->g;
     out[0] = g.kind[s];
@@ -1886,9 +1886,9 @@ int32_t cxb_signal_info(cxb_engine* h, int64_t s, int64_t out[5]) {
     out[3] = g.r0[s];
     out[4] = g.r1[s];
     return CXB_OK;
-}
+} CXB_ABI_CATCH(CXB_ERR_INTERNAL)
 // dependency lists with the live 4-bit props: the structure comes from the log, the C/F bits from the device
-int64_t cxb_get_dependencies(cxb_engine* h, int64_t s, int64_t* out_ids, uint8_t* out_nib, int64_t cap) {
+int64_t cxb_get_dependencies(cxb_engine* h, int64_t s, int64_t* out_ids, uint8_t* out_nib, int64_t cap) try {
     DeviceEngine* e = E(h);
     if (s < 0 || s >= (int64_t)e->g.n_sig()) return -1;
     int64_t nd = e->g.dep_count[s];
@@ -1902,8 +1902,8 @@ int64_t cxb_get_dependencies(cxb_engine* h, int64_t s, int64_t* out_ids, uint8_t
         if (out_nib) out_nib[i] = (uint8_t)((ch[i >> 4] >> ((i & 15) << 2)) & 0xF);
     }
     return nd;
-}
-int64_t cxb_get_listeners(cxb_engine* h, int64_t s, int64_t* out_ids, uint8_t* out_listen, int64_t cap) {
+} CXB_ABI_CATCH(-1)
+int64_t cxb_get_listeners(cxb_engine* h, int64_t s, int64_t* out_ids, uint8_t* out_listen, int64_t cap) try {
     DeviceEngine* e = E(h);
     if (s < 0 || s >= (int64_t)e->g.n_sig()) return -1;
     int64_t nl = e->g.lis_count[s];
@@ -1917,69 +1917,69 @@ int64_t cxb_get_listeners(cxb_engine* h, int64_t s, int64_t* out_ids, uint8_t* o
         if (out_listen) out_listen[i] = e->csr.lis_listen[off + i];
     }
     return nl;
-}
-int64_t cxb_get_warnings(cxb_engine* h, int64_t* out, int64_t cap) {
+} CXB_ABI_CATCH(-1)
+int64_t cxb_get_warnings(cxb_engine* h, int64_t* out, int64_t cap) try {
     const auto& w = E(h)->g.warnings;
     for (int64_t i = 0; i < (int64_t)w.size() && i < cap; ++i) out[i] = w[i];
     return (int64_t)w.size();
-}
-int32_t cxb_set_values(cxb_engine* h, int64_t n, const int64_t* sids, const double* values, int64_t stride) {
+} CXB_ABI_CATCH(-1)
+int32_t cxb_set_values(cxb_engine* h, int64_t n, const int64_t* sids, const double* values, int64_t stride) try {
     return E(h)->set_values(n, sids, values, stride);
-}
-int32_t cxb_get_values(cxb_engine* h, int64_t n, const int64_t* sids, double* out, int64_t stride) {
+} CXB_ABI_CATCH(CXB_ERR_INTERNAL)
+int32_t cxb_get_values(cxb_engine* h, int64_t n, const int64_t* sids, double* out, int64_t stride) try {
     return E(h)->get_values(n, sids, out, stride);
-}
-int32_t cxb_is_pending(cxb_engine* h, int64_t s) {
+} CXB_ABI_CATCH(CXB_ERR_INTERNAL)
+int32_t cxb_is_pending(cxb_engine* h, int64_t s) try {
     if (s < 0 || s >= (int64_t)E(h)->g.n_sig()) return -1;
     int r = 0;
     if (E(h)->is_pending(s, r)) return -1;
     return r;
-}
-int32_t cxb_is_computed(cxb_engine* h, int64_t s) {
+} CXB_ABI_CATCH(CXB_ERR_INTERNAL)
+int32_t cxb_is_computed(cxb_engine* h, int64_t s) try {
     if (s < 0 || s >= (int64_t)E(h)->g.n_sig()) return -1;
     int r = 0;
     if (E(h)->is_computed(s, r)) return -1;
     return r;
-}
-int32_t cxb_compute(cxb_engine* h, int64_t s, int32_t force, int32_t skip) {
+} CXB_ABI_CATCH(CXB_ERR_INTERNAL)
+int32_t cxb_compute(cxb_engine* h, int64_t s, int32_t force, int32_t skip) try {
     CHECK_SIG(h, s);
     return E(h)->compute(s, force != 0, skip != 0);
-}
-int32_t cxb_request_inference(cxb_engine* h, int64_t n, const int64_t* ids) {
+} CXB_ABI_CATCH(CXB_ERR_INTERNAL)
+int32_t cxb_request_inference(cxb_engine* h, int64_t n, const int64_t* ids) try {
     DeviceEngine* e = E(h);
     int32_t st = e->request(n, ids);
     if (st) return st;
     if (cudaStreamSynchronize(e->stream) != cudaSuccess) return CXB_ERR_CUDA;
     return CXB_OK;
-}
-int64_t cxb_scan(cxb_engine* h, int64_t* out, int64_t cap) {
+} CXB_ABI_CATCH(CXB_ERR_INTERNAL)
+int64_t cxb_scan(cxb_engine* h, int64_t* out, int64_t cap) try {
     std::vector<int64_t> v;
     if (E(h)->scan(v)) return -1;
     for (int64_t i = 0; i < (int64_t)v.size() && i < cap; ++i) out[i] = v[i];
     return (int64_t)v.size();
-}
-int32_t cxb_update_marginals(cxb_engine* h, int64_t n, const int64_t* ids, cxb_update_stats* stats) {
+} CXB_ABI_CATCH(-1)
+int32_t cxb_update_marginals(cxb_engine* h, int64_t n, const int64_t* ids, cxb_update_stats* stats) try {
     int32_t st = E(h)->update(n, ids);
     if (stats) *stats = E(h)->stats;
     return st;
-}
-int32_t cxb_trace_enable(cxb_engine* h, int32_t on) {
+} CXB_ABI_CATCH(CXB_ERR_INTERNAL)
+int32_t cxb_trace_enable(cxb_engine* h, int32_t on) try {
     E(h)->trace_on = on != 0;
     return CXB_OK;
-}
-int64_t cxb_trace_get(cxb_engine* h, int64_t* out_level, int64_t* out_sid, int64_t cap) {
+} CXB_ABI_CATCH(CXB_ERR_INTERNAL)
+int64_t cxb_trace_get(cxb_engine* h, int64_t* out_level, int64_t* out_sid, int64_t cap) try {
     DeviceEngine* e = E(h);
     for (int64_t i = 0; i < (int64_t)e->tr_sid.size() && i < cap; ++i) {
         if (out_level) out_level[i] = e->tr_level[i];
         if (out_sid) out_sid[i] = e->tr_sid[i];
     }
     return (int64_t)e->tr_sid.size();
-}
-int64_t cxb_trace_get_times(cxb_engine* h, int64_t* out_ns, int64_t cap) {
+} CXB_ABI_CATCH(-1)
+int64_t cxb_trace_get_times(cxb_engine* h, int64_t* out_ns, int64_t cap) try {
     DeviceEngine* e = E(h);
     for (int64_t i = 0; i < (int64_t)e->tr_ns.size() && i < cap; ++i)
         if (out_ns) out_ns[i] = e->tr_ns[i];
     return (int64_t)e->tr_ns.size();
-}
+} CXB_ABI_CATCH(-1)
 
 }  // extern "C"

@@ -370,7 +370,7 @@ static inline Grid* GR(cxb_grid* g) { return reinterpret_cast<Grid*>(g); }
 extern "C" {
 
 int32_t cxb_grid_create(int32_t device, int32_t dtype, int64_t rows, int64_t cols, int32_t n_labels, double beta,
-                        int32_t has_upper, int32_t has_lower, cxb_grid** out) {
+                        int32_t has_upper, int32_t has_lower, cxb_grid** out) try {
     if (!out || (dtype != CXB_F32 && dtype != CXB_F64)) return CXB_ERR_BAD_ARG;
     *out = nullptr;
     Grid* g = new Grid();
@@ -390,7 +390,7 @@ int32_t cxb_grid_create(int32_t device, int32_t dtype, int64_t rows, int64_t col
     }
     *out = reinterpret_cast<cxb_grid*>(g);
     return CXB_OK;
-}
+} CXB_ABI_CATCH(CXB_ERR_INTERNAL)
 void cxb_grid_destroy(cxb_grid* g) {
     if (g) {
         cudaSetDevice(GR(g)->device);
@@ -398,14 +398,14 @@ void cxb_grid_destroy(cxb_grid* g) {
     }
 }
 const char* cxb_grid_last_error(cxb_grid* g) { return g ? GR(g)->err.c_str() : "null handle"; }
-int32_t cxb_grid_set_unary(cxb_grid* g, const void* unary_host) {
+int32_t cxb_grid_set_unary(cxb_grid* g, const void* unary_host) try {
     Grid* h = GR(g);
     GR_CUDA(g, cudaSetDevice(h->device));
     GR_CUDA(g, cudaMemcpyAsync(h->unary.p, unary_host, h->plane(), cudaMemcpyHostToDevice, h->stream));
     GR_CUDA(g, cudaStreamSynchronize(h->stream));
     h->have_unary = true;
     return CXB_OK;
-}
+} CXB_ABI_CATCH(CXB_ERR_INTERNAL)
 int32_t cxb_grid_reset_messages(cxb_grid* g) { return GR(g)->reset(); }
 int32_t cxb_grid_sweep(cxb_grid* g, int64_t* n_updates_out) { return GR(g)->sweep(n_updates_out); }
 // the messages computed by the LAST sweep that the neighbour shard needs: row 0 of plane `up` (direction 0),
@@ -426,7 +426,7 @@ void* cxb_grid_halo_recv_ptr(cxb_grid* g, int32_t direction) {
 }
 // ---- fused halo exchange over peer memory ---------------------------------------------------------------------------------
 // export: 2 x 64 bytes = cudaIpcMemHandle_t of the halo buffer and of the sweep counters of THIS shard
-int32_t cxb_grid_p2p_export(cxb_grid* g, void* handles_out) {
+int32_t cxb_grid_p2p_export(cxb_grid* g, void* handles_out) try {
     Grid* h = GR(g);
     GR_CUDA(g, cudaSetDevice(h->device));
     cudaIpcMemHandle_t hh[2];
@@ -434,9 +434,9 @@ int32_t cxb_grid_p2p_export(cxb_grid* g, void* handles_out) {
     GR_CUDA(g, cudaIpcGetMemHandle(&hh[1], h->flags.p));
     memcpy(handles_out, hh, sizeof(hh));
     return CXB_OK;
-}
+} CXB_ABI_CATCH(CXB_ERR_INTERNAL)
 // connect the row neighbour in `direction` (0 = above, 1 = below) that lives in ANOTHER process, by its exported handles
-int32_t cxb_grid_p2p_connect_ipc(cxb_grid* g, int32_t direction, const void* neighbour_handles) {
+int32_t cxb_grid_p2p_connect_ipc(cxb_grid* g, int32_t direction, const void* neighbour_handles) try {
     Grid* h = GR(g);
     if (direction != 0 && direction != 1) return CXB_ERR_BAD_ARG;
     GR_CUDA(g, cudaSetDevice(h->device));
@@ -450,9 +450,9 @@ int32_t cxb_grid_p2p_connect_ipc(cxb_grid* g, int32_t direction, const void* nei
     h->peer_halo[direction] = (unsigned char*)halo;
     h->peer_flags[direction] = (unsigned*)fl;
     return CXB_OK;
-}
+} CXB_ABI_CATCH(CXB_ERR_INTERNAL)
 // same, for a neighbour shard owned by THIS process (several shards per process; single-GPU tests)
-int32_t cxb_grid_p2p_connect_local(cxb_grid* g, int32_t direction, cxb_grid* neighbour) {
+int32_t cxb_grid_p2p_connect_local(cxb_grid* g, int32_t direction, cxb_grid* neighbour) try {
     Grid *h = GR(g), *nb = GR(neighbour);
     if ((direction != 0 && direction != 1) || !nb || nb->W != h->W || nb->K != h->K || nb->dtype != h->dtype) return CXB_ERR_BAD_ARG;
     if (nb->device != h->device) {
@@ -470,17 +470,17 @@ int32_t cxb_grid_p2p_connect_local(cxb_grid* g, int32_t direction, cxb_grid* nei
     h->peer_halo[direction] = nb->halo_recv.p;
     h->peer_flags[direction] = nb->flags.p;
     return CXB_OK;
-}
+} CXB_ABI_CATCH(CXB_ERR_INTERNAL)
 int64_t cxb_grid_halo_elems(cxb_grid* g) { return GR(g)->W * GR(g)->K; }
-int32_t cxb_grid_get_marginals(cxb_grid* g, void* out_host) {
+int32_t cxb_grid_get_marginals(cxb_grid* g, void* out_host) try {
     Grid* h = GR(g);
     GR_CUDA(g, cudaSetDevice(h->device));
     GR_CUDA(g, cudaMemcpyAsync(out_host, h->marg.p, h->plane(), cudaMemcpyDeviceToHost, h->stream));
     GR_CUDA(g, cudaStreamSynchronize(h->stream));
     return CXB_OK;
-}
+} CXB_ABI_CATCH(CXB_ERR_INTERNAL)
 // which: 0..3 = m2v from the (up, left, right, down) factor; 4..7 = m2f towards them (current buffer)
-int32_t cxb_grid_get_messages(cxb_grid* g, int32_t which, void* out_host) {
+int32_t cxb_grid_get_messages(cxb_grid* g, int32_t which, void* out_host) try {
     Grid* h = GR(g);
     if (which < 0 || which > 7) {
         h->err = "message plane must be 0..7";
@@ -491,9 +491,9 @@ int32_t cxb_grid_get_messages(cxb_grid* g, int32_t which, void* out_host) {
     GR_CUDA(g, cudaMemcpyAsync(out_host, src, h->plane(), cudaMemcpyDeviceToHost, h->stream));
     GR_CUDA(g, cudaStreamSynchronize(h->stream));
     return CXB_OK;
-}
+} CXB_ABI_CATCH(CXB_ERR_INTERNAL)
 void* cxb_grid_stream(cxb_grid* g) { return (void*)GR(g)->stream; }
-int32_t cxb_grid_last_kernel_ms(cxb_grid* g, float* ms_out) {
+int32_t cxb_grid_last_kernel_ms(cxb_grid* g, float* ms_out) try {
     Grid* h = GR(g);
     if (!h->ran) {
         h->err = "no sweep has run yet";
@@ -502,10 +502,10 @@ int32_t cxb_grid_last_kernel_ms(cxb_grid* g, float* ms_out) {
     GR_CUDA(g, cudaEventSynchronize(h->ev1));
     GR_CUDA(g, cudaEventElapsedTime(ms_out, h->ev0, h->ev1));
     return CXB_OK;
-}
-int32_t cxb_grid_sync(cxb_grid* g) {
+} CXB_ABI_CATCH(CXB_ERR_INTERNAL)
+int32_t cxb_grid_sync(cxb_grid* g) try {
     GR_CUDA(g, cudaStreamSynchronize(GR(g)->stream));
     return CXB_OK;
-}
+} CXB_ABI_CATCH(CXB_ERR_INTERNAL)
 
 }  // extern "C"

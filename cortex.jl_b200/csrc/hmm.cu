@@ -1180,7 +1180,7 @@ static inline Hmm* HM(cxb_hmm* m) { return reinterpret_cast<Hmm*>(m); }
 extern "C" {
 
 int32_t cxb_hmm_create(int32_t device, int32_t dtype, int64_t n_chains, int64_t n_steps, int32_t n_states, int32_t n_symbols,
-                       cxb_hmm** out) {
+                       cxb_hmm** out) try {
     if (!out || (dtype != CXB_F32 && dtype != CXB_F64)) return CXB_ERR_BAD_ARG;
     *out = nullptr;
     Hmm* m = new Hmm();
@@ -1198,7 +1198,7 @@ int32_t cxb_hmm_create(int32_t device, int32_t dtype, int64_t n_chains, int64_t 
     }
     *out = reinterpret_cast<cxb_hmm*>(m);
     return CXB_OK;
-}
+} CXB_ABI_CATCH(CXB_ERR_INTERNAL)
 void cxb_hmm_destroy(cxb_hmm* m) {
     if (m) {
         cudaSetDevice(HM(m)->device);
@@ -1206,24 +1206,24 @@ void cxb_hmm_destroy(cxb_hmm* m) {
     }
 }
 const char* cxb_hmm_last_error(cxb_hmm* m) { return m ? HM(m)->err.c_str() : "null handle"; }
-int32_t cxb_hmm_set_tables(cxb_hmm* m, const double* transition, const double* emission) {
+int32_t cxb_hmm_set_tables(cxb_hmm* m, const double* transition, const double* emission) try {
     return HM(m)->set_tables(transition, emission);
-}
-int32_t cxb_hmm_set_observations(cxb_hmm* m, const uint8_t* obs_host) {
+} CXB_ABI_CATCH(CXB_ERR_INTERNAL)
+int32_t cxb_hmm_set_observations(cxb_hmm* m, const uint8_t* obs_host) try {
     Hmm* h = HM(m);
     HM_CUDA(m, cudaSetDevice(h->device));
     HM_CUDA(m, cudaMemcpyAsync(h->obs.p, obs_host, (size_t)h->T * h->B, cudaMemcpyHostToDevice, h->stream));
     HM_CUDA(m, cudaStreamSynchronize(h->stream));
     h->have_obs = true;
     return CXB_OK;
-}
-int32_t cxb_hmm_update_marginals(cxb_hmm* m, int64_t* n_updates_out) {
+} CXB_ABI_CATCH(CXB_ERR_INTERNAL)
+int32_t cxb_hmm_update_marginals(cxb_hmm* m, int64_t* n_updates_out) try {
     Hmm* h = HM(m);
     int32_t st = h->launch();
     if (st) return st;
     if (n_updates_out) *n_updates_out = h->B * (6 * h->T - 4);
     return CXB_OK;
-}
+} CXB_ABI_CATCH(CXB_ERR_INTERNAL)
 static int32_t hmm_get(cxb_hmm* m, const unsigned char* src, int64_t t0, int64_t t1, void* out_host) {
     Hmm* h = HM(m);
     if (!h->ran || t0 < 0 || t1 > h->T || t0 >= t1) {
@@ -1239,7 +1239,7 @@ static int32_t hmm_get(cxb_hmm* m, const unsigned char* src, int64_t t0, int64_t
 int32_t cxb_hmm_get_marginals(cxb_hmm* m, int64_t t0, int64_t t1, void* out_host) { return hmm_get(m, HM(m)->marg.p, t0, t1, out_host); }
 int32_t cxb_hmm_get_forward(cxb_hmm* m, int64_t t0, int64_t t1, void* out_host) { return hmm_get(m, HM(m)->fwd.p, t0, t1, out_host); }
 void* cxb_hmm_stream(cxb_hmm* m) { return (void*)HM(m)->stream; }
-int32_t cxb_hmm_last_kernel_ms(cxb_hmm* m, float* ms_out) {
+int32_t cxb_hmm_last_kernel_ms(cxb_hmm* m, float* ms_out) try {
     Hmm* h = HM(m);
     if (!h->ran) {
         h->err = "no update has run yet";
@@ -1248,10 +1248,10 @@ int32_t cxb_hmm_last_kernel_ms(cxb_hmm* m, float* ms_out) {
     HM_CUDA(m, cudaEventSynchronize(h->ev1));
     HM_CUDA(m, cudaEventElapsedTime(ms_out, h->ev0, h->ev1));
     return CXB_OK;
-}
-int32_t cxb_hmm_sync(cxb_hmm* m) {
+} CXB_ABI_CATCH(CXB_ERR_INTERNAL)
+int32_t cxb_hmm_sync(cxb_hmm* m) try {
     HM_CUDA(m, cudaStreamSynchronize(HM(m)->stream));
     return CXB_OK;
-}
+} CXB_ABI_CATCH(CXB_ERR_INTERNAL)
 
 }  // extern "C"

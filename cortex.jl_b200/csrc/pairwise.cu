@@ -1197,7 +1197,7 @@ static inline Pairwise* PW(cxb_pairwise* g) { return reinterpret_cast<Pairwise*>
 extern "C" {
 
 int32_t cxb_pairwise_create(int32_t device, int32_t dtype, int64_t n_variables, int64_t n_factors, int32_t n_states,
-                            int32_t n_tables, cxb_pairwise** out) {
+                            int32_t n_tables, cxb_pairwise** out) try {
     if (!out || (dtype != CXB_F32 && dtype != CXB_F64)) return CXB_ERR_BAD_ARG;
     *out = nullptr;
     Pairwise* g = new Pairwise();
@@ -1215,7 +1215,7 @@ int32_t cxb_pairwise_create(int32_t device, int32_t dtype, int64_t n_variables, 
     }
     *out = reinterpret_cast<cxb_pairwise*>(g);
     return CXB_OK;
-}
+} CXB_ABI_CATCH(CXB_ERR_INTERNAL)
 void cxb_pairwise_destroy(cxb_pairwise* g) {
     if (g) {
         cudaSetDevice(PW(g)->device);
@@ -1223,11 +1223,11 @@ void cxb_pairwise_destroy(cxb_pairwise* g) {
     }
 }
 const char* cxb_pairwise_last_error(cxb_pairwise* g) { return g ? PW(g)->err.c_str() : "null handle"; }
-int32_t cxb_pairwise_set_graph(cxb_pairwise* g, const int64_t* fac_u, const int64_t* fac_v, const int32_t* fac_table) {
+int32_t cxb_pairwise_set_graph(cxb_pairwise* g, const int64_t* fac_u, const int64_t* fac_v, const int32_t* fac_table) try {
     return PW(g)->set_graph(fac_u, fac_v, fac_table);
-}
+} CXB_ABI_CATCH(CXB_ERR_INTERNAL)
 int32_t cxb_pairwise_set_tables(cxb_pairwise* g, const double* tables) { return PW(g)->set_tables(tables); }
-int32_t cxb_pairwise_set_unary(cxb_pairwise* g, const void* unary_host) {
+int32_t cxb_pairwise_set_unary(cxb_pairwise* g, const void* unary_host) try {
     Pairwise* h = PW(g);
     if (!h->have_graph) {
         h->err = "set the graph first";
@@ -1245,31 +1245,31 @@ int32_t cxb_pairwise_set_unary(cxb_pairwise* g, const void* unary_host) {
     PW_CUDA(g, cudaStreamSynchronize(h->stream));
     h->have_unary = true;
     return CXB_OK;
-}
+} CXB_ABI_CATCH(CXB_ERR_INTERNAL)
 int32_t cxb_pairwise_reset_messages(cxb_pairwise* g) { return PW(g)->reset(); }
 int32_t cxb_pairwise_sweep(cxb_pairwise* g, int64_t* n_updates_out) { return PW(g)->sweep(n_updates_out); }
-int32_t cxb_pairwise_get_marginals(cxb_pairwise* g, void* out_host) {
+int32_t cxb_pairwise_get_marginals(cxb_pairwise* g, void* out_host) try {
     Pairwise* h = PW(g);
     PW_CUDA(g, cudaSetDevice(h->device));
     PW_CUDA(g, cudaMemcpyAsync(out_host, h->marg.p, (size_t)h->n * h->K * h->esz(), cudaMemcpyDeviceToHost, h->stream));
     PW_CUDA(g, cudaStreamSynchronize(h->stream));
     return CXB_OK;
-}
-int32_t cxb_pairwise_get_messages(cxb_pairwise* g, int32_t which, void* out_host) {
+} CXB_ABI_CATCH(CXB_ERR_INTERNAL)
+int32_t cxb_pairwise_get_messages(cxb_pairwise* g, int32_t which, void* out_host) try {
     Pairwise* h = PW(g);
     if (which != 0 && which != 1) {
         h->err = "which must be 0 (m2v) or 1 (m2f)";
         return CXB_ERR_BAD_ARG;
     }
     return h->get_edges(which == 0 ? h->m2v.p : h->m2f[h->cur].p, out_host, which == 1);
-}
-int64_t cxb_pairwise_algorithmic_bytes(cxb_pairwise* g) {
+} CXB_ABI_CATCH(CXB_ERR_INTERNAL)
+int64_t cxb_pairwise_algorithmic_bytes(cxb_pairwise* g) try {
     Pairwise* h = PW(g);
     // per variable of degree d: (d + 1) messages read, (2d + 1) written (no ProductOfMessages traffic)
     return (int64_t)((size_t)(2 * h->m + h->n) + (size_t)(4 * h->m + h->n)) * h->K * (int64_t)h->esz();
-}
+} CXB_ABI_CATCH(-1)
 void* cxb_pairwise_stream(cxb_pairwise* g) { return (void*)PW(g)->stream; }
-int32_t cxb_pairwise_last_kernel_ms(cxb_pairwise* g, float* ms_out) {
+int32_t cxb_pairwise_last_kernel_ms(cxb_pairwise* g, float* ms_out) try {
     Pairwise* h = PW(g);
     if (!h->ran) {
         h->err = "no sweep has run yet";
@@ -1278,10 +1278,10 @@ int32_t cxb_pairwise_last_kernel_ms(cxb_pairwise* g, float* ms_out) {
     PW_CUDA(g, cudaEventSynchronize(h->ev1));
     PW_CUDA(g, cudaEventElapsedTime(ms_out, h->ev0, h->ev1));
     return CXB_OK;
-}
-int32_t cxb_pairwise_sync(cxb_pairwise* g) {
+} CXB_ABI_CATCH(CXB_ERR_INTERNAL)
+int32_t cxb_pairwise_sync(cxb_pairwise* g) try {
     PW_CUDA(g, cudaStreamSynchronize(PW(g)->stream));
     return CXB_OK;
-}
+} CXB_ABI_CATCH(CXB_ERR_INTERNAL)
 
 }  // extern "C"

@@ -48,7 +48,8 @@ enum {
     CXB_ERR_BAD_ARG = 4,
     CXB_ERR_UNSUPPORTED_ENGINE = 5, /* -> UnsupportedModelEngineError, src/model_engine.jl:252 */
     CXB_ERR_CUDA = 6,
-    CXB_ERR_STATE = 7            /* call order violated (e.g. compute before graph build)    */
+    CXB_ERR_STATE = 7,           /* call order violated (e.g. compute before graph build)    */
+    CXB_ERR_INTERNAL = 8         /* host allocation failure / C++ exception stopped at the ABI */
 };
 
 /* ---- dtype ------------------------------------------------------------------------------- */

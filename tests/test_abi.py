@@ -54,3 +54,16 @@ def test_no_cpu_fallback_without_gpu():
         pkg.PottsGrid(4, 4, 4, 0.5)
     with pytest.raises(pkg.CortexError):
         pkg.HmmBatch(2, 8, 4, 3)
+
+
+@pytest.mark.gpu
+def test_cxx_exceptions_do_not_cross_the_abi(device_api):
+    """A host-side C++ exception (here: std::length_error from a negative id count in cxb_graph_build) is stopped at the C
+    boundary and reported as a status; without the function-try-blocks it would terminate the calling Julia / Python
+    process."""
+    import numpy as np
+
+    store = pkg.SignalStore(device_api, value_dim=1, family=pkg.capi.FAMILY_SUM, dtype=pkg.capi.F64)
+    isf = np.zeros(1, dtype=np.uint8)
+    st = device_api.graph_build(store.h, -1, isf.ctypes.data_as(pkg.capi.u8p), None, 0, None, None)
+    assert st in (pkg.capi.ERR_INTERNAL, pkg.capi.ERR_BAD_ARG)
