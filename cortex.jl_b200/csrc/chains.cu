@@ -476,7 +476,7 @@ void cxb_chains_destroy(cxb_chains* c) {
     }
 }
 const char* cxb_chains_last_error(cxb_chains* c) { return c ? CH(c)->err.c_str() : "null handle"; }
-int32_t cxb_chains_set_noise(cxb_chains* c, const double* q, const double* r) { return CH(c)->set_noise(q, r); }
+int32_t cxb_chains_set_noise(cxb_chains* c, const double* q, const double* r) try { return CH(c)->set_noise(q, r); } CXB_ABI_CATCH(CXB_ERR_INTERNAL)
 
 #define CH_CUDA(c, expr)                                        \
     do {                                                        \
@@ -526,7 +526,7 @@ int32_t cxb_chains_get_messages(cxb_chains* c, int32_t m, void* out_host) try {
     CH_CUDA(c, cudaStreamSynchronize(h->stream));
     return CXB_OK;
 } CXB_ABI_CATCH(CXB_ERR_INTERNAL)
-int32_t cxb_chains_get_marginals(cxb_chains* c, void* out_host) { return cxb_chains_get_messages(c, 5, out_host); }
+int32_t cxb_chains_get_marginals(cxb_chains* c, void* out_host) try { return cxb_chains_get_messages(c, 5, out_host); } CXB_ABI_CATCH(CXB_ERR_INTERNAL)
 void* cxb_chains_device_ptr(cxb_chains* c, int32_t which) {
     Chains* h = CH(c);
     if (which >= 0 && which <= 5) return h->msg.p + (size_t)which * h->plane_bytes();

@@ -1865,7 +1865,7 @@ int32_t cxb_link_signals(cxb_engine* h, int64_t n, const int64_t* vs, const int6
     }
     return CXB_OK;
 } CXB_ABI_CATCH(CXB_ERR_INTERNAL)
-int64_t cxb_n_signals(cxb_engine* h) { return E(h)->g.n_sig(); }
+int64_t cxb_n_signals(cxb_engine* h) try { return E(h)->g.n_sig(); } CXB_ABI_CATCH(-1)
 int64_t cxb_signal_id(cxb_engine* h, int32_t kind, int64_t v, int64_t f) try {
     DeviceEngine* e = E(h);
     if (v < 0 || v >= e->g.n_ids || e->g.is_factor[v]) return -1;

@@ -406,8 +406,8 @@ int32_t cxb_grid_set_unary(cxb_grid* g, const void* unary_host) try {
     h->have_unary = true;
     return CXB_OK;
 } CXB_ABI_CATCH(CXB_ERR_INTERNAL)
-int32_t cxb_grid_reset_messages(cxb_grid* g) { return GR(g)->reset(); }
-int32_t cxb_grid_sweep(cxb_grid* g, int64_t* n_updates_out) { return GR(g)->sweep(n_updates_out); }
+int32_t cxb_grid_reset_messages(cxb_grid* g) try { return GR(g)->reset(); } CXB_ABI_CATCH(CXB_ERR_INTERNAL)
+int32_t cxb_grid_sweep(cxb_grid* g, int64_t* n_updates_out) try { return GR(g)->sweep(n_updates_out); } CXB_ABI_CATCH(CXB_ERR_INTERNAL)
 // the messages computed by the LAST sweep that the neighbour shard needs: row 0 of plane `up` (direction 0),
 // last row of plane `down` (direction 1) of the current buffer
 void* cxb_grid_halo_send_ptr(cxb_grid* g, int32_t direction) {
@@ -471,7 +471,7 @@ int32_t cxb_grid_p2p_connect_local(cxb_grid* g, int32_t direction, cxb_grid* nei
     h->peer_flags[direction] = nb->flags.p;
     return CXB_OK;
 } CXB_ABI_CATCH(CXB_ERR_INTERNAL)
-int64_t cxb_grid_halo_elems(cxb_grid* g) { return GR(g)->W * GR(g)->K; }
+int64_t cxb_grid_halo_elems(cxb_grid* g) try { return GR(g)->W * GR(g)->K; } CXB_ABI_CATCH(-1)
 int32_t cxb_grid_get_marginals(cxb_grid* g, void* out_host) try {
     Grid* h = GR(g);
     GR_CUDA(g, cudaSetDevice(h->device));

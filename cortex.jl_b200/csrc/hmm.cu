@@ -1236,8 +1236,8 @@ static int32_t hmm_get(cxb_hmm* m, const unsigned char* src, int64_t t0, int64_t
     HM_CUDA(m, cudaStreamSynchronize(h->stream));
     return CXB_OK;
 }
-int32_t cxb_hmm_get_marginals(cxb_hmm* m, int64_t t0, int64_t t1, void* out_host) { return hmm_get(m, HM(m)->marg.p, t0, t1, out_host); }
-int32_t cxb_hmm_get_forward(cxb_hmm* m, int64_t t0, int64_t t1, void* out_host) { return hmm_get(m, HM(m)->fwd.p, t0, t1, out_host); }
+int32_t cxb_hmm_get_marginals(cxb_hmm* m, int64_t t0, int64_t t1, void* out_host) try { return hmm_get(m, HM(m)->marg.p, t0, t1, out_host); } CXB_ABI_CATCH(CXB_ERR_INTERNAL)
+int32_t cxb_hmm_get_forward(cxb_hmm* m, int64_t t0, int64_t t1, void* out_host) try { return hmm_get(m, HM(m)->fwd.p, t0, t1, out_host); } CXB_ABI_CATCH(CXB_ERR_INTERNAL)
 void* cxb_hmm_stream(cxb_hmm* m) { return (void*)HM(m)->stream; }
 int32_t cxb_hmm_last_kernel_ms(cxb_hmm* m, float* ms_out) try {
     Hmm* h = HM(m);

@@ -80,6 +80,10 @@ struct HostGraph {
             err = "graph already built (build the graph before creating free signals)";
             return CXB_ERR_STATE;
         }
+        if (n < 0 || n_edges < 0 || (n > 0 && !isf) || (n_edges > 0 && (!ev || !ef))) {
+            err = "graph_build: negative size or null array";
+            return CXB_ERR_BAD_ARG;
+        }
         if ((n + 2 * n_edges) >= (int64_t)2000000000) {
             err = "graph too large for 32-bit signal ids";
             return CXB_ERR_BAD_ARG;

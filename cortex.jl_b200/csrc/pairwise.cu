@@ -1226,7 +1226,7 @@ const char* cxb_pairwise_last_error(cxb_pairwise* g) { return g ? PW(g)->err.c_s
 int32_t cxb_pairwise_set_graph(cxb_pairwise* g, const int64_t* fac_u, const int64_t* fac_v, const int32_t* fac_table) try {
     return PW(g)->set_graph(fac_u, fac_v, fac_table);
 } CXB_ABI_CATCH(CXB_ERR_INTERNAL)
-int32_t cxb_pairwise_set_tables(cxb_pairwise* g, const double* tables) { return PW(g)->set_tables(tables); }
+int32_t cxb_pairwise_set_tables(cxb_pairwise* g, const double* tables) try { return PW(g)->set_tables(tables); } CXB_ABI_CATCH(CXB_ERR_INTERNAL)
 int32_t cxb_pairwise_set_unary(cxb_pairwise* g, const void* unary_host) try {
     Pairwise* h = PW(g);
     if (!h->have_graph) {
@@ -1246,8 +1246,8 @@ int32_t cxb_pairwise_set_unary(cxb_pairwise* g, const void* unary_host) try {
     h->have_unary = true;
     return CXB_OK;
 } CXB_ABI_CATCH(CXB_ERR_INTERNAL)
-int32_t cxb_pairwise_reset_messages(cxb_pairwise* g) { return PW(g)->reset(); }
-int32_t cxb_pairwise_sweep(cxb_pairwise* g, int64_t* n_updates_out) { return PW(g)->sweep(n_updates_out); }
+int32_t cxb_pairwise_reset_messages(cxb_pairwise* g) try { return PW(g)->reset(); } CXB_ABI_CATCH(CXB_ERR_INTERNAL)
+int32_t cxb_pairwise_sweep(cxb_pairwise* g, int64_t* n_updates_out) try { return PW(g)->sweep(n_updates_out); } CXB_ABI_CATCH(CXB_ERR_INTERNAL)
 int32_t cxb_pairwise_get_marginals(cxb_pairwise* g, void* out_host) try {
     Pairwise* h = PW(g);
     PW_CUDA(g, cudaSetDevice(h->device));
