@@ -1743,6 +1743,7 @@ int32_t cxb_graph_build(cxb_engine* h, int64_t n_ids, const uint8_t* is_factor, 
                         const int64_t* edge_var, const int64_t* edge_fac) try {
     DeviceEngine* e = E(h);
     int32_t st = e->g.build(n_ids, is_factor, factor_type, n_edges, edge_var, edge_fac, e->err);
+    if (st) return st;
     e->fparam.assign((size_t)n_ids, NAN);
     e->structure_dirty = true;
     return st;
