@@ -300,3 +300,25 @@ def form_segment_tree_dependency(model, rng, fs, v):  # :128-173
     add_dependency(product, left, intermediate=True)
     add_dependency(product, right, intermediate=True)
     return product
+
+
+def request_inference_for(marginals, linked_signals):  # src/inference_engine.jl:298-323
+    for marginal, linked in zip(marginals, linked_signals):
+        for dependency in marginal.dependencies:
+            dependency.potentially_pending, dependency.pending = True, False
+        for ls in linked:
+            ls.potentially_pending, ls.pending = True, False
+
+
+def scan_inference_request(marginals):  # :528-546 — the scanner's process! only collects, nothing is computed
+    found = []
+
+    def f(dependency):
+        if is_pending(dependency):
+            found.append(dependency)
+            return True
+        return False
+
+    for marginal in marginals:
+        process_dependencies(f, marginal, retry=True)
+    return found

@@ -62,7 +62,7 @@ def test_oracle_sequential_schedule_equals_the_object_graph_witness(oracle_api, 
     index_of = {id(s): i for i, s in enumerate(sigs)}
     marg = [C.get_variable_marginal(C.get_variable(e, v)).sid for v in vs]
     assert fz._state(e) == _py_state(sigs)
-    n_updates = 0
+    n_updates = n_scanned = 0
     for op in fz._script(rng, n_var, inputs, 20):
         kind, ids, vals = op
         if kind == "set":
@@ -70,12 +70,26 @@ def test_oracle_sequential_schedule_equals_the_object_graph_witness(oracle_api, 
             for s, v in zip(ids, vals):
                 R.set_value(sigs[s], float(v))
         else:
+            # the scanner first (src/inference_engine.jl:540-546): same pending signals in the same DFS order, duplicates included
+            request = C.request_inference_for(e, [vs[i] for i in ids])
+            scanned = [s.sid for s in C.scan_inference_request(request, order="dfs")]
+            R.request_inference_for([sigs[marg[i]] for i in ids], [[] for _ in ids])
+            assert [index_of[id(s)] for s in R.scan_inference_request([sigs[marg[i]] for i in ids])] == scanned, (seed, op)
+            n_scanned += len(scanned)
             C.update_marginals(e, [vs[i] for i in ids], schedule="seq")
             executed = R.update_marginals([sigs[marg[i]] for i in ids], [[] for _ in ids], _strategy)
             assert [index_of[id(s)] for s in executed] == _trace(e)[1].tolist(), (seed, op)  # same executions, same order
             n_updates += len(executed)
         assert fz._state(e) == _py_state(sigs), (seed, op)
-    assert n_updates >= 0
+    assert n_updates >= 0 and n_scanned >= 0
+    _SCANNED.append(n_scanned)
+
+
+_SCANNED = []
+
+
+def test_scanner_comparisons_were_not_vacuous():
+    assert sum(_SCANNED) > 200, sum(_SCANNED)
 
 
 def test_witness_pending_criteria_across_chunk_boundaries():
