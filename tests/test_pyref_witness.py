@@ -226,3 +226,46 @@ def test_default_wiring_equals_the_object_graph_witness(oracle_api, seed, shape)
 def test_wired_graph_requests_executed_something():
     """Guards the test above against vacuity (runs after it): the requests on the wired graphs did compute signals."""
     assert len(_EXECUTED_ON_WIRED_GRAPHS) == 12 and min(_EXECUTED_ON_WIRED_GRAPHS) > 20, _EXECUTED_ON_WIRED_GRAPHS
+
+
+@pytest.mark.parametrize("seed", range(20))
+def test_duplicate_circular_and_self_dependencies_on_both(oracle_api, seed):
+    """The edge cases of test/signal_tests.jl:442-521 at random: duplicate dependencies (only the FIRST matching slot is ever
+    notified), cycles and self dependencies (ignored), any mix of flags, dependencies added between computed and uncomputed
+    signals (check_computed on and off) - `set_value!` / `compute!(force)` on random signals, identical state on both."""
+    rng = np.random.Generator(np.random.PCG64(777 + seed))
+    store = pkg.SignalStore(oracle_api, value_dim=1, family=pkg.capi.FAMILY_SUM, dtype=pkg.capi.F64)
+    n = int(rng.integers(2, 9))
+    co = [C.Signal(store, store.api.create_signal(store.h)) for _ in range(n)]
+    py = [R.Signal() for _ in range(n)]
+
+    def same():
+        for a, b in zip(co, py):
+            assert C.is_computed(a) == R.is_computed(b)
+            assert C.is_pending(a) == R.is_pending(b)
+            assert tuple(C.get_dependency_props(a)) == tuple(b.dependencies_props.nibble(i) for i in range(1, b.dependencies_props.length + 1))
+            assert [x.sid for x in C.get_dependencies(a)] == [py.index(x) for x in b.dependencies]
+            assert [x.sid for x in C.get_listeners(a)] == [py.index(x) for x in b.listeners]
+            assert [bool(x) for x in C.get_listenmask(a)] == [bool(x) for x in b.listenmask]
+            if C.is_computed(a):
+                assert float(C.get_values([a])[0][0]) == float(b.value)
+
+    for _ in range(40):
+        r = rng.random()
+        if r < 0.45:
+            s, d = int(rng.integers(n)), int(rng.integers(n))  # s == d: self dependency; repeated pairs: duplicates
+            kw = dict(weak=bool(rng.random() < 0.3), listen=bool(rng.random() < 0.8), check_computed=bool(rng.random() < 0.8),
+                      intermediate=bool(rng.random() < 0.5))
+            C.add_dependency(co[s], co[d], **kw)
+            R.add_dependency(py[s], py[d], **kw)
+        elif r < 0.85:
+            s, v = int(rng.integers(n)), float(rng.integers(1, 9))
+            C.set_values([co[s]], np.array([[v]]))
+            R.set_value(py[s], v)
+        else:
+            s = int(rng.integers(n))
+            if py[s].dependencies and all(R.is_computed(d) for d in py[s].dependencies):
+                for d in co[s:s + 1]:
+                    C.compute(d, force=True)  # family SUM: the left-to-right sum of the dependencies
+                R.compute(lambda sig, deps: float(sum(x.value for x in deps)), py[s], force=True)
+        same()
