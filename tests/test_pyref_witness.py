@@ -61,6 +61,14 @@ def test_oracle_sequential_schedule_equals_the_object_graph_witness(oracle_api, 
     sigs = _mirror(e)
     index_of = {id(s): i for i, s in enumerate(sigs)}
     marg = [C.get_variable_marginal(C.get_variable(e, v)).sid for v in vs]
+    # linked signals (src/model_engine.jl:80-83; the final phase of update_marginals! computes the pending ones, :620-627):
+    # a few random non-input signals linked to random variables, in the same order on both
+    linked = {i: [] for i in range(n_var)}
+    candidates = [s for s in range(len(sigs)) if sigs[s].dependencies]
+    for s in (rng.choice(candidates, size=min(3, len(candidates)), replace=False) if candidates else []):
+        i = int(rng.integers(n_var))
+        C.link_signal_to_variable(C.get_variable(e, vs[i]), C.Signal(e.store, int(s)))
+        linked[i].append(sigs[int(s)])
     assert fz._state(e) == _py_state(sigs)
     n_updates = n_scanned = 0
     for op in fz._script(rng, n_var, inputs, 20):
@@ -73,11 +81,11 @@ def test_oracle_sequential_schedule_equals_the_object_graph_witness(oracle_api, 
             # the scanner first (src/inference_engine.jl:540-546): same pending signals in the same DFS order, duplicates included
             request = C.request_inference_for(e, [vs[i] for i in ids])
             scanned = [s.sid for s in C.scan_inference_request(request, order="dfs")]
-            R.request_inference_for([sigs[marg[i]] for i in ids], [[] for _ in ids])
+            R.request_inference_for([sigs[marg[i]] for i in ids], [linked[i] for i in ids])
             assert [index_of[id(s)] for s in R.scan_inference_request([sigs[marg[i]] for i in ids])] == scanned, (seed, op)
             n_scanned += len(scanned)
             C.update_marginals(e, [vs[i] for i in ids], schedule="seq")
-            executed = R.update_marginals([sigs[marg[i]] for i in ids], [[] for _ in ids], _strategy)
+            executed = R.update_marginals([sigs[marg[i]] for i in ids], [linked[i] for i in ids], _strategy)
             assert [index_of[id(s)] for s in executed] == _trace(e)[1].tolist(), (seed, op)  # same executions, same order
             n_updates += len(executed)
         assert fz._state(e) == _py_state(sigs), (seed, op)
