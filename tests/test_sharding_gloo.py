@@ -1,4 +1,4 @@
-"""N>1 host logic on CPU: world_size-2 gloo run of the row-sharded Potts grid.
+"""N>1 host logic on CPU: world_size-2 and -3 gloo runs of the row-sharded Potts grid.
 Each rank owns a row block as an explicit oracle graph with a ghost row for the neighbour shard; every sweep
 the cut-edge m2f messages travel through `HaloExchanger` (the same code bench.py drives over NCCL). The sharded
 result must be bit-identical to the single-graph result."""
@@ -89,7 +89,8 @@ def test_row_and_batch_shard_cover_everything():
         C.row_shard(2, 3, 2)
 
 
-def test_two_rank_gloo_halo_exchange_matches_single_graph(oracle_api):
+@pytest.mark.parametrize("world", [2, 3])  # 3 ranks: the middle shard exchanges with both neighbours in the same sweep
+def test_gloo_halo_exchange_matches_single_graph(oracle_api, world):
     import torch.multiprocessing as mp
 
     with socket.socket() as s:
@@ -97,6 +98,7 @@ def test_two_rank_gloo_halo_exchange_matches_single_graph(oracle_api):
         port = s.getsockname()[1]
     mgr = mp.Manager()
     out = mgr.dict()
-    mp.spawn(_worker, args=(2, port, out), nprocs=2, join=True)
+    mp.spawn(_worker, args=(world, port, out), nprocs=world, join=True)
+    assert sorted(out.keys()) == list(range(world))
     got = np.concatenate([out[r][1] for r in sorted(out.keys())], axis=0)
     assert np.array_equal(got, _run_full(oracle_api))
