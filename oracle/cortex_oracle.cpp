@@ -157,7 +157,10 @@ struct Oracle {
         Sig& d = sig[did];
         int64_t idx = s.ndeps++;
         if ((size_t)((4 * s.ndeps - 1) / 64 + 1) > s.chunks.size()) s.chunks.push_back(0);
-        if (weak) nib_set(s, idx, MASK_W);
+        if (weak) {
+            nib_set(s, idx, MASK_W);
+            has_weak_dep = true;
+        }
         if (intermediate) nib_set(s, idx, MASK_I);
         s.deps.push_back(did);
         d.listenmask.push_back(listen ? 1 : 0);
@@ -739,6 +742,7 @@ struct Oracle {
     // Opt-in (CXO_STRICT_FRESHNESS=1) extension of the request-time check below to EVERY signal the first traversal of a
     // request visits: not pending, yet FRESH on a strong, computed (non-input) dependency.
     bool strict_freshness = std::getenv("CXO_STRICT_FRESHNESS") && std::atoi(std::getenv("CXO_STRICT_FRESHNESS")) != 0;
+    bool has_weak_dep = false;    // any weak dependency in the graph (the device allocates its probe marks only then)
     int64_t lvl_request = 0;      // > 0 while a strict level-schedule request runs (its serial number)
     int64_t lvl_serial = 0;
     std::vector<int64_t> nl_notified;     // ... during the current level
@@ -836,7 +840,7 @@ struct Oracle {
                         if (processed && nib(o->sig[sid], i, MASK_I)) o->revisited_via_I[d] = 1;  // found pending through an I slot
                         if (!processed && nib(o->sig[sid], i, MASK_I)) {
                             if (done[d]) {
-                                probe(d);
+                                if (o->has_weak_dep) probe(d);  // like the device: graphs without weak dependencies are not probed
                             } else {
                                 bool ip = go(d);
                                 if (ip) processed = f(d);
