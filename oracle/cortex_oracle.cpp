@@ -975,6 +975,10 @@ int32_t cxo_graph_build(void* h, int64_t n_ids, const uint8_t* is_factor, const 
         o->err = "graph already built (build the graph before creating free signals)";
         return CXB_ERR_STATE;
     }
+    if (n_ids < 0 || n_edges < 0 || (n_ids > 0 && !is_factor) || (n_edges > 0 && (!edge_var || !edge_fac))) {
+        o->err = "graph_build: negative size or null array";
+        return CXB_ERR_BAD_ARG;
+    }
     o->n_ids = n_ids;
     o->is_factor.assign(is_factor, is_factor + n_ids);
     o->ftype.assign(n_ids, 0);

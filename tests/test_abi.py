@@ -67,3 +67,14 @@ def test_cxx_exceptions_do_not_cross_the_abi(device_api):
     isf = np.zeros(1, dtype=np.uint8)
     st = device_api.graph_build(store.h, -1, isf.ctypes.data_as(pkg.capi.u8p), None, 0, None, None)
     assert st in (pkg.capi.ERR_INTERNAL, pkg.capi.ERR_BAD_ARG)
+
+
+def test_graph_build_refuses_negative_sizes(oracle_api):
+    """Same answer as the device library (host_graph.hpp): CXB_ERR_BAD_ARG, and the handle stays usable."""
+    import numpy as np
+
+    store = pkg.SignalStore(oracle_api, value_dim=1, family=pkg.capi.FAMILY_SUM, dtype=pkg.capi.F64)
+    isf = np.zeros(1, dtype=np.uint8)
+    assert oracle_api.graph_build(store.h, -1, isf.ctypes.data_as(pkg.capi.u8p), None, 0, None, None) == pkg.capi.ERR_BAD_ARG
+    assert oracle_api.graph_build(store.h, 1, isf.ctypes.data_as(pkg.capi.u8p), None, -3, None, None) == pkg.capi.ERR_BAD_ARG
+    assert oracle_api.graph_build(store.h, 1, isf.ctypes.data_as(pkg.capi.u8p), None, 0, None, None) == pkg.capi.OK
