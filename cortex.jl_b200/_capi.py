@@ -25,6 +25,7 @@ NIB_INTERMEDIATE, NIB_WEAK, NIB_COMPUTED, NIB_FRESH = 1, 2, 4, 8
 (RULE_NONE, RULE_GAUSS_OBS, RULE_GAUSS_RW, RULE_CAT_TABLE, RULE_POTTS, RULE_HMM_EMIT, RULE_GAUSS_MV_OBS,
  RULE_GAUSS_MV_RW, RULE_BETA_BERNOULLI, RULE_SCALE2, RULE_NORMAL_MEAN_FIELD, RULE_NORMAL_STRUCTURED) = range(12)
 RESOLVER_NONE, RESOLVER_DEFAULT_BP, RESOLVER_MEAN_FIELD = range(3)
+SCHEDULE_AUTO, SCHEDULE_LEVEL, SCHEDULE_SEQUENTIAL, RAN_REPLAY, RAN_PLAN = range(5)
 
 i32, i64, u8p, i32p, i64p, f64p, vp = (C.c_int32, C.c_int64, C.POINTER(C.c_uint8), C.POINTER(C.c_int32),
                                        C.POINTER(C.c_int64), C.POINTER(C.c_double), C.c_void_p)
@@ -69,6 +70,11 @@ _COMMON = {
     "request_inference": (i32, [vp, i64, i64p]),
     "scan": (i64, [vp, i64p, i64]),
     "update_marginals": (i32, [vp, i64, i64p, C.POINTER(UpdateStats)]),
+    "set_schedule": (i32, [vp, i32]),
+    "last_schedule": (i32, [vp]),
+    "scan_dfs": (i64, [vp, i64p, i64]),
+    "process_dependencies_table": (i64, [vp, i64, i32, u8p, i64p, i64, i32p]),
+    "trace_get_variables": (i64, [vp, i64p, i64]),
     "trace_enable": (i32, [vp, i32]),
     "trace_get": (i64, [vp, i64p, i64p, i64]),
     "trace_get_times": (i64, [vp, i64p, i64]),
@@ -140,9 +146,7 @@ _STRUCTURED = {
 _ORACLE_EXTRA = {
     "set_rule_callback": (i32, [vp, RULE_CB, vp]),
     "raw_props": (i32, [vp, i64]),
-    "scan_dfs": (i64, [vp, i64p, i64]),
     "update_marginals_seq": (i32, [vp, i64, i64p, C.POINTER(UpdateStats)]),
-    "trace_get_variables": (i64, [vp, i64p, i64]),
     "count_is_pending_calls": (i64, [vp]),
     "process_dependencies": (i32, [vp, i64, i32, VISIT_CB, vp]),
     "chains_reference": (i32, [i64, i64, f64p, f64p, f64p, f64p]),

@@ -24,7 +24,17 @@ unsigned long long g_kernel_launches = 0;
 constexpr uint64_t ALL_W = 0x2222222222222222ull, ALL_C = 0x4444444444444444ull, ALL_F = 0x8888888888888888ull,
                    PASS = 0x1111111111111111ull;
 constexpr int ERR_INDEPENDENCE = 1, ERR_LISTENER_DONE = 2, ERR_RULE_ARG = 4, ERR_WEAK_BENEATH_DONE = 16, ERR_LEFTOVER_FRESH = 32;  // 8 = ERR_NO_RULE_KEY
+// strict rules of the level schedule (the oracle's update_lvl states them in the same words)
+constexpr int ERR_STALE_BENEATH = 64;          // A: a visited, non-pending signal holds leftover freshness (first level)
+constexpr int ERR_WORK_BENEATH_PENDING = 128;  // B: a marginal already pending at request time has pending work beneath it
+constexpr int ERR_REVISITED = 256;             // D: a member found pending more than once, once through an intermediate slot, with a pending dependency
+constexpr int ERR_NONLISTEN = 512;             // E: non-listening notifications (order inside a level / a request matters)
+constexpr int ERR_FINAL_ORDER = 1024;          // F: final-phase candidates that depend on each other across the per-variable order
+constexpr int ERR_SEQ_OVERFLOW = 2048;         // sequential executor: traversal deeper than the stack (a dependency cycle)
 constexpr uint32_t PROBE_BIT = 0x80000000u;  // breadth-first list entry: the signal is only probed (see bfs_visit)
+constexpr uint32_t MULTI_BIT = 0x40000000u;  // breadth-first list entry: the reference's depth-first traversal reaches the signal more than once
+constexpr uint32_t ENTRY_ID = 0x3FFFFFFFu;
+constexpr uint32_t MK_VIS2 = 1, MK_VIA_I = 2, MK_MULTI = 4;  // View::mark2 flags (low 3 bits, level epoch above)
 constexpr int KEY_COMBINE = 0;  // dense rule keys: 0 = family reduce, 1..n_types = m2v of a factor type, n_types+1 = no rule
 
 
@@ -42,6 +52,11 @@ struct View {
     const uint8_t* sfam;              // per-signal value family (cxb_set_variable_families), nullptr = the engine family
     uint32_t *done_epoch, *visit_epoch;
     uint32_t* probe_epoch;            // graphs with weak dependencies only (else nullptr): probe visits of this level
+    uint32_t* mark2;                  // (lvl_epoch << 3) | MK_*: visit multiplicities of the current level (strict rule D)
+    uint32_t* nl_epoch;               // graphs with non-listening dependencies only (else nullptr): req_epoch of the last such notification
+    uint32_t* nl_list;                // ... signals that received one during the current level, count in *nl_cnt
+    uint32_t* nl_cnt;
+    int strict;                       // strict rules A / B / D / E armed
     uint32_t* front_epoch;            // == lvl_epoch: member of the current level's frontier
     uint32_t* front;                  // frontier buffer, partitioned by rule key
     const uint32_t* key_base;         // [n_keys] start of each key's partition
@@ -101,12 +116,22 @@ __global__ void k_request(View e, const uint32_t* req_marg, const uint32_t* link
 // Contract check at request time (after k_request): a requested marginal that is not pending must not hold a FRESH bit on a
 // computed, non-input dependency - leftover freshness of an earlier request that could not complete makes the reference's
 // answer depend on the order in which it visits the variables (see the oracle's update_lvl). Read-only.
-__global__ void k_request_check(View e, const uint32_t* req_marg, uint32_t n) {
+__device__ __forceinline__ bool pending_now(const View& e, uint32_t s) {  // is_pending without the caching side effect
+    const uint8_t p = e.props[s];
+    return (p & P_P) || ((p & P_PP) && criteria(e, s));
+}
+// pend_at_req[i] = the marginal was already pending when the request arrived (strict rule B); *n_pend counts them
+__global__ void k_request_check(View e, const uint32_t* req_marg, uint32_t n, uint8_t* pend_at_req, int* n_pend) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const uint32_t m = req_marg[i];
     const uint8_t p = e.props[m];
-    if ((p & P_P) || ((p & P_PP) && criteria(e, m))) return;
+    if ((p & P_P) || ((p & P_PP) && criteria(e, m))) {
+        pend_at_req[i] = 1;
+        atomicAdd(n_pend, 1);
+        return;
+    }
+    pend_at_req[i] = 0;
     const uint32_t off = e.dep_off[m], nd = e.dep_off[m + 1] - off, noff = e.nib_off[m];
     for (uint32_t k = 0; k < nd; ++k) {
         const uint32_t nibble = (uint32_t)(e.nib[noff + (k >> 4)] >> ((k & 15) << 2)) & 0xF;
@@ -116,9 +141,9 @@ __global__ void k_request_check(View e, const uint32_t* req_marg, uint32_t n) {
 }
 
 // seeds of one level: marginals of the requested variables that are not ready yet (:585)
-__global__ void k_seeds(const uint32_t* req_marg, const uint8_t* ready, uint32_t n, uint32_t* out, uint32_t* n_out) {
+__global__ void k_seeds(const uint32_t* req_marg, const uint8_t* sel, uint8_t want, uint32_t n, uint32_t* out, uint32_t* n_out) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    bool take = i < n && !ready[i];
+    bool take = i < n && sel[i] == want;
     unsigned m = __ballot_sync(0xffffffffu, take);
     if (!m) return;
     int lane = threadIdx.x & 31;
@@ -131,8 +156,34 @@ __global__ void k_seeds(const uint32_t* req_marg, const uint8_t* ready, uint32_t
 // Append a pending signal to the frontier of this level, grouped by rule key: the frontier buffer is partitioned
 // statically by key (key_base[k] = number of signals with a smaller key), the per-key cursors are bumped with
 // warp-aggregated atomics (one atomic per distinct key per warp: __match_any over the active lanes).
-__device__ __forceinline__ void frontier_push(const View& e, uint32_t d, uint32_t lvl_epoch) {
-    if (atomicExch(&e.front_epoch[d], lvl_epoch) == lvl_epoch) return;  // already in this level's frontier
+__device__ __forceinline__ uint32_t mark_or(uint32_t* m, uint32_t lvl, uint32_t f) {  // returns the flags the level had before
+    uint32_t old = *m, assumed;
+    do {
+        assumed = old;
+        const uint32_t cur = (assumed >> 3) == lvl ? assumed : (lvl << 3);
+        if ((cur & f) == f && (assumed >> 3) == lvl) return cur & 7u;
+        old = atomicCAS(m, assumed, cur | f);
+    } while (old != assumed);
+    return (assumed >> 3) == lvl ? (assumed & 7u) : 0u;
+}
+__device__ __forceinline__ uint32_t mark_get(const uint32_t* m, uint32_t lvl) {
+    const uint32_t v = *m;
+    return (v >> 3) == lvl ? (v & 7u) : 0u;
+}
+// leftover freshness (strict rule A; the oracle's holds_leftover_freshness): FRESH on a strong dependency that is not an input
+__device__ __forceinline__ bool holds_leftover(const View& e, uint32_t s) {
+    const uint32_t off = e.dep_off[s], nd = e.dep_off[s + 1] - off, noff = e.nib_off[s];
+    for (uint32_t k = 0; k < nd; ++k) {
+        const uint32_t nibble = (uint32_t)(e.nib[noff + (k >> 4)] >> ((k & 15) << 2)) & 0xF;
+        if ((nibble & CXB_NIB_FRESH) && !(nibble & CXB_NIB_WEAK)) {
+            const uint32_t d = e.dep_ids[off + k];
+            if (e.dep_off[d + 1] > e.dep_off[d]) return true;
+        }
+    }
+    return false;
+}
+__device__ __forceinline__ bool frontier_push(const View& e, uint32_t d, uint32_t lvl_epoch) {
+    if (atomicExch(&e.front_epoch[d], lvl_epoch) == lvl_epoch) return false;  // already in this level's frontier
     int key = e.use_keys ? e.rkey[d] : 0;
     unsigned act = __activemask();
     unsigned same = __match_any_sync(act, key);
@@ -141,6 +192,7 @@ __device__ __forceinline__ void frontier_push(const View& e, uint32_t d, uint32_
     if (lane == leader) base = atomicAdd(&e.key_cnt[key], (uint32_t)__popc(same));
     base = __shfl_sync(same, base, leader);
     e.front[e.key_base[key] + base + __popc(same & ((1u << lane) - 1))] = d;
+    return true;
 }
 
 // One breadth-first step of process_dependencies! (src/signal.jl:466-490) over a list of signals:
@@ -154,14 +206,21 @@ __device__ __forceinline__ void frontier_push(const View& e, uint32_t d, uint32_
 // can be pending underneath a done signal: graphs that have weak dependencies are therefore PROBED through their done
 // signals (same descent rule, nothing is pushed), and a pending weak dependency found there refuses the request as
 // order-dependent instead of silently leaving it for the final phase.
+// Strict rules evaluated here (use_done bit 1 = first level of a request): A - a visited signal that is not pending but holds
+// leftover freshness; D - visit multiplicities. The reference's traversal is depth-first WITHOUT a visited set: a signal
+// reached along two paths is traversed twice and everything beneath it is visited twice. A breadth-first traversal visits
+// each signal once, so the multiplicity ("more than once") is propagated instead: the second arrival at a traversed signal
+// re-queues it once more with MULTI_BIT, and a traversal carrying MULTI_BIT counts double for everything it visits.
 template <class Push>
 __device__ __forceinline__ void bfs_visit(const View& e, uint32_t entry, uint32_t lvl_epoch, uint32_t req_epoch, int use_done, Push&& push_out) {
-    const uint32_t s = entry & ~PROBE_BIT;
-    const bool probing = (entry & PROBE_BIT) != 0;
+    const uint32_t s = entry & ENTRY_ID;
+    const bool probing = (entry & PROBE_BIT) != 0, multi = (entry & MULTI_BIT) != 0;
+    const bool first_level = (use_done & 2) != 0;
+    const bool skip_done = (use_done & 1) != 0;
     const uint32_t off = e.dep_off[s], nd = e.dep_off[s + 1] - off, noff = e.nib_off[s];
     for (uint32_t k = 0; k < nd; ++k) {
         const uint32_t d = e.dep_ids[off + k];
-        const bool done = use_done && e.done_epoch[d] == req_epoch;
+        const bool done = skip_done && e.done_epoch[d] == req_epoch;
         if (done && !e.probe_epoch) continue;
         const uint32_t nibble = (uint32_t)(e.nib[noff + (k >> 4)] >> ((k & 15) << 2)) & 0xF;
         if (done || probing) {
@@ -171,9 +230,21 @@ __device__ __forceinline__ void bfs_visit(const View& e, uint32_t entry, uint32_
                 push_out(d | PROBE_BIT);
             }
         } else if (pending_eval(e, d)) {
-            frontier_push(e, d, lvl_epoch);
-        } else if ((nibble & CXB_NIB_INTERMEDIATE) && atomicExch(&e.visit_epoch[d], lvl_epoch) != lvl_epoch) {
-            push_out(d);
+            const bool first = frontier_push(e, d, lvl_epoch);
+            if (e.strict) {
+                const uint32_t f = ((nibble & CXB_NIB_INTERMEDIATE) ? MK_VIA_I : 0u) | ((!first || multi) ? MK_VIS2 : 0u);
+                if (f) mark_or(&e.mark2[d], lvl_epoch, f);
+            }
+        } else {
+            if (e.strict && first_level && holds_leftover(e, d)) atomicOr(e.err_flag, ERR_STALE_BENEATH);
+            if (nibble & CXB_NIB_INTERMEDIATE) {
+                if (atomicExch(&e.visit_epoch[d], lvl_epoch) != lvl_epoch) {
+                    if (multi && e.strict) mark_or(&e.mark2[d], lvl_epoch, MK_MULTI);
+                    push_out(d | (multi && e.strict ? MULTI_BIT : 0u));
+                } else if (e.strict && !(mark_or(&e.mark2[d], lvl_epoch, MK_MULTI) & MK_MULTI)) {
+                    push_out(d | MULTI_BIT);  // second arrival: everything beneath is visited (at least) twice
+                }
+            }
         }
     }
 }
@@ -224,9 +295,14 @@ __device__ __forceinline__ void notify(const View& e, uint32_t k, uint32_t req_e
     atomicOr((unsigned long long*)&e.nib[e.nib_off[L] + (slot >> 4)],
              (unsigned long long)(CXB_NIB_COMPUTED | CXB_NIB_FRESH) << ((slot & 15) << 2));
     if (check_mode == 1 && e.done_epoch[L] == req_epoch) atomicOr(e.err_flag, ERR_LISTENER_DONE);
+    if (check_mode == 1 && e.nl_epoch && !e.lis_listen[k]) {  // strict rule E: remember non-listening notifications
+        e.nl_epoch[L] = req_epoch;
+        e.nl_list[atomicAdd(e.nl_cnt, 1u)] = L;
+    }
 }
 __global__ void k_apply(View e, Segs sg, uint32_t req_epoch, int check_mode) {
     __shared__ unsigned int kc[6];
+    if (*(volatile int*)e.err_flag) return;  // the level was refused by its checks: nothing is applied
     if (threadIdx.x < 6) kc[threadIdx.x] = 0;
     __syncthreads();
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -266,12 +342,40 @@ __global__ void k_apply_list(View e, const uint32_t* list, uint32_t n, uint32_t 
 }
 // independence of a level (A.5): no member may depend on another member. Members are recognisable by
 // front_epoch == lvl_epoch (set when they were pushed); runs BEFORE the rules.
-__global__ void k_check_independent(View e, Segs sg, uint32_t lvl_epoch) {
+// The other contract checks of a level live here too, so that a refused level has not been applied (the rule and
+// set_value! kernels of the level return at once when the error flag is up): the listener-done rule (check_mode 1: no
+// member may have a listener already computed in this request), strict rule D and the first half of strict rule E.
+__device__ __forceinline__ void check_member(const View& e, uint32_t s, uint32_t lvl_epoch, uint32_t req_epoch, int check_mode) {
+    int err = 0;
+    const uint32_t off = e.dep_off[s], end = e.dep_off[s + 1];
+    for (uint32_t k = off; k < end; ++k)
+        if (e.front_epoch[e.dep_ids[k]] == lvl_epoch) err |= ERR_INDEPENDENCE;
+    if (check_mode == 1) {
+        for (uint32_t k = e.lis_off[s]; k < e.lis_off[s + 1]; ++k)
+            if (e.done_epoch[e.lis_ids[k]] == req_epoch) err |= ERR_LISTENER_DONE;
+        if (e.strict) {
+            const uint32_t mk = mark_get(&e.mark2[s], lvl_epoch);
+            if ((mk & MK_VIS2) && (mk & MK_VIA_I))
+                for (uint32_t k = off; k < end; ++k)
+                    if (pending_now(e, e.dep_ids[k])) err |= ERR_REVISITED;
+            if (e.nl_epoch && e.nl_epoch[s] == req_epoch) err |= ERR_NONLISTEN;
+        }
+    }
+    if (err) atomicOr(e.err_flag, err);
+}
+__global__ void k_check_independent(View e, Segs sg, uint32_t lvl_epoch, uint32_t req_epoch, int check_mode) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= sg.total) return;
-    uint32_t s = seg_member(sg, e.front, i);
-    for (uint32_t k = e.dep_off[s]; k < e.dep_off[s + 1]; ++k)
-        if (e.front_epoch[e.dep_ids[k]] == lvl_epoch) atomicOr(e.err_flag, ERR_INDEPENDENCE);
+    check_member(e, seg_member(sg, e.front, i), lvl_epoch, req_epoch, check_mode);
+}
+// strict rule E, second half (after the set_value! effects of a level): a non-listening notification of this level left a
+// signal that is neither done nor a member with complete criteria
+__global__ void k_check_nl(View e, uint32_t req_epoch) {
+    const uint32_t n = *e.nl_cnt;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const uint32_t L = e.nl_list[i];
+        if (e.done_epoch[L] != req_epoch && criteria(e, L)) atomicOr(e.err_flag, ERR_NONLISTEN);
+    }
 }
 
 // ---- values ------------------------------------------------------------------------------------------------
@@ -464,7 +568,7 @@ template <class T>
 __global__ void k_rule_small(View e, T* __restrict__ val, const uint32_t* list, uint32_t n, int family, int rule,
                              const T* __restrict__ fparam, T default_param) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
+    if (i >= n || *(volatile int*)e.err_flag) return;  // refused level: no value is written
     rule_small_one<T>(e, val, list[i], family, rule, fparam, default_param);
 }
 
@@ -490,7 +594,15 @@ struct ResidentArgs {
     const long long* key_table;  // [n_keys] element offset of the key's table in `tables` (CAT_TABLE: [2][K][K], HMM_EMIT: [K][n_sym])
     const int* key_nsym;       // [n_keys] HMM_EMIT: number of symbols
     long long* out;            // [0] levels [1] updates [2] final marginals [3] final linked [4] last lvl_epoch [5] key without rule
+    const uint8_t* pend_at_req;  // [n_req] strict rule B (k_request_check)
+    const uint32_t *hz_m, *hz_l;  // rule F: signals that must not be pending when the marginal / linked level of the final phase starts
+    uint32_t n_hz_m, n_hz_l;
 };
+// rule F (final phase): see DeviceEngine::request for how the lists are made
+__global__ void k_check_not_pending(View e, const uint32_t* list, uint32_t n) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n && pending_now(e, list[i])) atomicOr(e.err_flag, ERR_FINAL_ORDER);
+}
 __device__ __forceinline__ void apply_one(const View& e, uint32_t s, uint32_t req_epoch, int check_mode) {
     for (uint32_t c = e.nib_off[s]; c < e.nib_off[s + 1]; ++c) e.nib[c] &= ~ALL_F;  // unset_all_dependencies_fresh!
     e.props[s] = P_COMPUTED;
@@ -590,13 +702,10 @@ __global__ void __launch_bounds__(1024) k_update_resident(View e, T* __restrict_
     auto run_level = [&](int check_mode) {
         for (int k = 0; k < a.n_keys; ++k) {
             const uint32_t cnt = e.key_cnt[k], base = e.key_base[k];
-            for (uint32_t i = tid; i < cnt; i += NT) {
-                const uint32_t s = e.front[base + i];
-                for (uint32_t d = e.dep_off[s]; d < e.dep_off[s + 1]; ++d)
-                    if (e.front_epoch[e.dep_ids[d]] == lvl) atomicOr(e.err_flag, ERR_INDEPENDENCE);
-            }
+            for (uint32_t i = tid; i < cnt; i += NT) check_member(e, e.front[base + i], lvl, a.req_epoch, check_mode);
         }
         __syncthreads();
+        if (*(volatile int*)e.err_flag) return;  // refused before anything of this level is computed or applied (uniform)
         for (int k = 0; k < a.n_keys; ++k) {
             const uint32_t cnt = e.key_cnt[k], base = e.key_base[k];
             if (!cnt) continue;
@@ -618,11 +727,22 @@ __global__ void __launch_bounds__(1024) k_update_resident(View e, T* __restrict_
             }
         }
         __syncthreads();
+        if (*(volatile int*)e.err_flag) return;  // a rule rejected its arguments
         for (int k = 0; k < a.n_keys; ++k) {
             const uint32_t cnt = e.key_cnt[k], base = e.key_base[k];
             for (uint32_t i = tid; i < cnt; i += NT) apply_one(e, e.front[base + i], a.req_epoch, check_mode);
         }
         __syncthreads();
+        if (check_mode == 1 && e.nl_epoch) {  // strict rule E, second half
+            const uint32_t n_nl = *e.nl_cnt;
+            for (uint32_t i = tid; i < n_nl; i += NT) {
+                const uint32_t L = e.nl_list[i];
+                if (e.done_epoch[L] != a.req_epoch && criteria(e, L)) atomicOr(e.err_flag, ERR_NONLISTEN);
+            }
+            __syncthreads();
+            if (tid == 0) *e.nl_cnt = 0;
+            __syncthreads();
+        }
     };
     auto begin_level = [&]() {
         ++lvl;
@@ -642,13 +762,10 @@ __global__ void __launch_bounds__(1024) k_update_resident(View e, T* __restrict_
         return t;
     };
 
-    while (a.n_req) {
-        begin_level();
-        for (uint32_t i = tid; i < a.n_req; i += NT)
-            if (!a.ready[i]) a.list_a[atomicAdd(&s_cnt[0], 1u)] = a.req_marg[i];  // seeds (:585)
-        __syncthreads();
+    bool first_level = true;
+    auto bfs_all = [&](int flags) {  // process_dependencies! from the seeds in list_a, one breadth-first step per iteration
         int which = 0;
-        for (;;) {  // process_dependencies!, one breadth-first step per iteration
+        for (;;) {
             const uint32_t n_in = s_cnt[which];
             __syncthreads();
             if (n_in == 0) break;
@@ -657,11 +774,37 @@ __global__ void __launch_bounds__(1024) k_update_resident(View e, T* __restrict_
             const uint32_t* in = which ? a.list_b : a.list_a;
             uint32_t* out = which ? a.list_a : a.list_b;
             for (uint32_t i = tid; i < n_in; i += NT)
-                bfs_visit(e, in[i], lvl, a.req_epoch, 1, [&](uint32_t x) { out[atomicAdd(&s_cnt[which ^ 1], 1u)] = x; });
+                bfs_visit(e, in[i], lvl, a.req_epoch, flags, [&](uint32_t x) { out[atomicAdd(&s_cnt[which ^ 1], 1u)] = x; });
             __syncthreads();
             which ^= 1;
         }
+    };
+    while (a.n_req) {
+        begin_level();
+        if (first_level && e.strict) {
+            // strict rule B: the marginals that were pending when the request arrived are traversed first, alone - the
+            // reference gives such a variable one traversal and takes its marginal, so nothing may be pending beneath it
+            for (uint32_t i = tid; i < a.n_req; i += NT)
+                if (a.pend_at_req[i]) a.list_a[atomicAdd(&s_cnt[0], 1u)] = a.req_marg[i];
+            __syncthreads();
+            bfs_all(3);
+            if (frontier_total()) {
+                if (tid == 0) atomicOr(e.err_flag, ERR_WORK_BENEATH_PENDING);
+                break;
+            }
+            if (tid == 0) s_cnt[0] = s_cnt[1] = 0;
+            __syncthreads();
+            for (uint32_t i = tid; i < a.n_req; i += NT)
+                if (!a.pend_at_req[i]) a.list_a[atomicAdd(&s_cnt[0], 1u)] = a.req_marg[i];
+        } else {
+            for (uint32_t i = tid; i < a.n_req; i += NT)
+                if (!a.ready[i]) a.list_a[atomicAdd(&s_cnt[0], 1u)] = a.req_marg[i];  // seeds (:585)
+        }
+        __syncthreads();
+        bfs_all(first_level ? 3 : 1);
+        first_level = false;
         const uint32_t total = frontier_total();
+        if (*(volatile int*)e.err_flag) break;  // refused by a traversal rule (A, weak beneath done): nothing of this level runs
         if (!total) break;
         run_level(1);
         if (*(volatile int*)e.err_flag) break;  // uniform: every thread reads it after the barrier that ends run_level
@@ -672,7 +815,18 @@ __global__ void __launch_bounds__(1024) k_update_resident(View e, T* __restrict_
         __syncthreads();
     }
     for (int mode = 0; mode < 2 && a.n_req; ++mode) {  // final phase: marginals, then linked signals (:610-628)
+        __syncthreads();
         if (*(volatile int*)e.err_flag) break;
+        {  // rule F: candidates that depend on each other across the reference's per-variable order
+            const uint32_t* hz = mode == 0 ? a.hz_m : a.hz_l;
+            const uint32_t n_hz = mode == 0 ? a.n_hz_m : a.n_hz_l;
+            for (uint32_t i = tid; i < n_hz; i += NT)
+                if (pending_now(e, hz[i])) atomicOr(e.err_flag, ERR_FINAL_ORDER);
+            if (n_hz) {
+                __syncthreads();
+                if (*(volatile int*)e.err_flag) break;
+            }
+        }
         begin_level();
         const uint32_t cnt = mode == 0 ? a.n_req : a.n_links;
         for (uint32_t i = tid; i < cnt; i += NT) {
@@ -694,6 +848,221 @@ __global__ void __launch_bounds__(1024) k_update_resident(View e, T* __restrict_
     }
 }
 
+// ---- sequential executor -----------------------------------------------------------------------------------------------
+// update_marginals! (src/inference_engine.jl:559-632), request scanning (:540-546) and process_dependencies!
+// (src/signal.jl:466-490) LITERALLY, statement by statement, on the device: one warp walks the reference's depth-first
+// traversal with an explicit stack, evaluates is_pending with its caching side effect, runs the rule of each pending
+// signal the moment the reference would and applies set_value! before going on. Exact for any wiring (weak,
+// non-listening, duplicate, hand-made dependencies; Gauss-Seidel orders) because it IS the reference order; one signal at
+// a time, so it is the schedule of hand-wired graphs and the fallback of requests the level schedule refuses, not the
+// throughput path. All 32 lanes execute the same control flow on the same data (loads are broadcasts); lane 0 alone
+// stores, and a __syncwarp() after every store orders it before the warp's next loads; categorical rules use the lanes.
+struct SeqArgs {
+    const uint32_t *req_marg, *link_off, *link_ids;  // link_off[n_req + 1]: linked signals of requested variable i
+    uint8_t* ready;
+    uint32_t n_req;
+    uint32_t* stack;  // frames of 3 words
+    uint32_t stack_cap;
+    int mode;  // 0 update_marginals!, 1 scan_inference_request (records pending signals, computes nothing), 2 process_dependencies!(table)
+    int n_keys, family;
+    const int* key_rule;
+    const double* key_param;
+    const void* fparam;
+    const void* tables;
+    const long long* key_table;
+    const int* key_nsym;
+    uint32_t* rec;  // mode 0: trace triples (round, request position, signal) when rec_cap > 0; modes 1, 2: visited / pending signals
+    uint32_t rec_cap;
+    const uint8_t* answers;  // mode 2: f(dep) = answers[dep]; nullptr: f = is_pending
+    uint32_t root;
+    int retry;
+    long long* out;  // [0] rounds that executed something [1] updates [2] final marginals [3] final linked [5] key without rule [6] records [7] return value
+};
+template <class T>
+__global__ void __launch_bounds__(32) k_seq(View e, T* __restrict__ val, SeqArgs a) {
+    __shared__ T s_cat_in[64];
+    const int lane = threadIdx.x;
+    long long n_rec = 0, updates = 0;
+    bool failed = false;
+
+    auto is_pending = [&](uint32_t s) -> bool {  // src/signal.jl:141-154
+        const uint8_t p = e.props[s];
+        bool r = false;
+        if (p & P_P) {
+            r = true;
+        } else if (p & P_PP) {
+            r = criteria(e, s);
+            __syncwarp();
+            if (lane == 0) e.props[s] = (uint8_t)((p & P_COMPUTED) | (r ? P_P : 0));
+        }
+        __syncwarp();
+        return r;
+    };
+    auto record3 = [&](uint32_t x, uint32_t y, uint32_t z) {
+        if (a.rec_cap && (unsigned long long)(n_rec + 1) * 3 <= a.rec_cap && lane == 0) {
+            a.rec[n_rec * 3] = x;
+            a.rec[n_rec * 3 + 1] = y;
+            a.rec[n_rec * 3 + 2] = z;
+        }
+        ++n_rec;
+    };
+    auto record1 = [&](uint32_t x) {
+        if ((unsigned long long)n_rec < a.rec_cap && lane == 0) a.rec[n_rec] = x;
+        ++n_rec;
+    };
+    // compute!(rule, signal) = rule + set_value! (src/signal.jl:392-410, 232-253): process! dispatch by rule key
+    auto execute = [&](uint32_t s, uint32_t round, uint32_t pos) {
+        const int key = e.rkey[s];
+        const int rule = a.key_rule[key];
+        if (rule == -2) {
+            if (lane == 0) {
+                atomicOr(e.err_flag, ERR_NO_RULE_KEY);
+                a.out[5] = key;
+            }
+            failed = true;
+            __syncwarp();
+            return;
+        }
+        const T defp = (T)a.key_param[key];
+        if (a.family == CXB_FAMILY_CATEGORICAL) {
+            const T* tb = a.key_table[key] >= 0 ? (const T*)a.tables + a.key_table[key] : nullptr;
+            rule_cat_warp<T>(e, val, s, rule, tb, a.key_nsym[key], defp, s_cat_in);
+        } else if (lane == 0) {
+            rule_small_one<T>(e, val, s, a.family, rule, (const T*)a.fparam, defp);
+        }
+        __syncwarp();
+        if (*(volatile int*)e.err_flag) {
+            failed = true;
+            return;
+        }
+        if (lane == 0) apply_one(e, s, 0u, 0);
+        __syncwarp();
+        record3(round, pos, s);
+        ++updates;
+    };
+    // process_dependencies!(f, root; retry), src/signal.jl:466-490, with the recursion unrolled onto a.stack
+    auto process_dependencies = [&](uint32_t root, bool retry, auto&& f) -> bool {
+        uint32_t sp = 0, s = root, i = 0;
+        bool any = false;
+        for (;;) {
+            if (failed) return any;
+            const uint32_t off = e.dep_off[s], nd = e.dep_off[s + 1] - off;
+            if (i == nd) {
+                if (sp == 0) return any;
+                const bool ip = any;  // what the recursive call returned
+                --sp;
+                s = a.stack[3 * sp];
+                i = a.stack[3 * sp + 1];
+                any = a.stack[3 * sp + 2] != 0;
+                bool pr = false;
+                if (ip && retry) pr = f(e.dep_ids[e.dep_off[s] + i]);
+                any = any || ip || pr;
+                ++i;
+                continue;
+            }
+            const uint32_t d = e.dep_ids[off + i];
+            const bool pr = f(d);
+            if (!pr) {
+                const uint32_t nibble = (uint32_t)(e.nib[e.nib_off[s] + (i >> 4)] >> ((i & 15) << 2)) & 0xF;
+                if (nibble & CXB_NIB_INTERMEDIATE) {
+                    if (sp == a.stack_cap) {
+                        if (lane == 0) atomicOr(e.err_flag, ERR_SEQ_OVERFLOW);
+                        failed = true;
+                        __syncwarp();
+                        return any;
+                    }
+                    if (lane == 0) {
+                        a.stack[3 * sp] = s;
+                        a.stack[3 * sp + 1] = i;
+                        a.stack[3 * sp + 2] = any ? 1u : 0u;
+                    }
+                    __syncwarp();
+                    ++sp;
+                    s = d;
+                    i = 0;
+                    any = false;
+                    continue;
+                }
+            }
+            any = any || pr;
+            ++i;
+        }
+    };
+
+    if (a.mode == 2) {
+        const bool r = process_dependencies(a.root, a.retry != 0, [&](uint32_t d) -> bool {
+            record1(d);
+            return a.answers ? a.answers[d] != 0 : is_pending(d);
+        });
+        if (lane == 0) {
+            a.out[6] = n_rec;
+            a.out[7] = r ? 1 : 0;
+        }
+        return;
+    }
+    if (a.mode == 1) {  // scan_inference_request, src/inference_engine.jl:540-546
+        for (uint32_t i = 0; i < a.n_req; ++i)
+            process_dependencies(a.req_marg[i], true, [&](uint32_t d) -> bool {
+                if (is_pending(d)) {
+                    record1(d);
+                    return true;
+                }
+                return false;
+            });
+        if (lane == 0) a.out[6] = n_rec;
+        return;
+    }
+    long long rounds_exec = 0, fm = 0, fl = 0;
+    bool should_continue = a.n_req > 0, reverse = false;
+    uint32_t round = 0;
+    while (should_continue && !failed) {  // :575-608
+        bool cont = false;
+        const long long updates0 = updates;
+        for (uint32_t k = 0; k < a.n_req && !failed; ++k) {
+            const uint32_t i = reverse ? a.n_req - 1 - k : k;
+            if (a.ready[i]) continue;
+            const bool processed = process_dependencies(a.req_marg[i], true, [&](uint32_t d) -> bool {  // :512-525
+                if (failed) return false;
+                if (is_pending(d)) {
+                    execute(d, round, i);
+                    return !failed;
+                }
+                return false;
+            });
+            if (failed) break;
+            if (is_pending(a.req_marg[i])) {  // :593-595
+                if (lane == 0) a.ready[i] = 1;
+                __syncwarp();
+            }
+            cont = cont || processed;
+        }
+        if (updates > updates0) ++rounds_exec;
+        reverse = !reverse;
+        should_continue = cont;
+        ++round;
+    }
+    for (uint32_t i = 0; i < a.n_req && !failed; ++i) {  // final phase, :610-628: marginal, then the linked signals, variable by variable
+        const uint32_t m = a.req_marg[i];
+        if (is_pending(m)) {
+            execute(m, 0xFFFFFFFFu, i);
+            ++fm;
+        }
+        for (uint32_t k = a.link_off[i]; k < a.link_off[i + 1] && !failed; ++k) {
+            const uint32_t l = a.link_ids[k];
+            if (!is_pending(l)) continue;
+            execute(l, 0xFFFFFFFFu, i);
+            ++fl;
+        }
+    }
+    if (lane == 0) {
+        a.out[0] = rounds_exec;
+        a.out[1] = updates;
+        a.out[2] = fm;
+        a.out[3] = fl;
+        a.out[6] = n_rec;
+    }
+}
+
 // Categorical values (dim = K states): G lanes cooperate on one signal (G = min(32, pow2 >= K)), lane l owns
 // components l, l+G, ... . rule < 0: element-wise product of the dependencies, normalised (App. C);
 // CAT_TABLE: out[a] = sum_b psi(a,b) in[b] with the table staged in shared memory; POTTS: closed form;
@@ -703,6 +1072,7 @@ __global__ void k_rule_cat(View e, T* __restrict__ val, const uint32_t* list, ui
                            const T* __restrict__ table, const T* __restrict__ table_t, int n_sym, T potts_w) {
     extern __shared__ unsigned char smem_raw[];
     T* sh = reinterpret_cast<T*>(smem_raw);
+    if (*(volatile int*)e.err_flag) return;  // refused level: no value is written (uniform for the whole grid)
     const int K = e.dim;
     const int groups_per_block = blockDim.x / G;
     T* sh_table = sh;                                   // K*K (both orientations) when CAT_TABLE
@@ -827,6 +1197,21 @@ struct DeviceEngine {
     DBuf<uint8_t> d_sfam;
     uint32_t req_epoch = 0, lvl_epoch = 0;
     size_t n_uploaded = 0;
+    // schedules (cxb_set_schedule): see include/cortex_b200.h
+    int schedule = CXB_SCHEDULE_AUTO, last_ran = 0;
+    bool hand_wired = false;  // cxb_create_signal / cxb_add_dependency were used: AUTO runs the sequential executor
+    bool strict = true;       // strict rules A / B / D / E of the level schedule (CXB_STRICT=0: the round-1 rules)
+    bool has_nl = false;      // any non-listening dependency in the graph (strict rule E keeps marks only then)
+    DBuf<uint32_t> d_mark2, d_nl_epoch, d_nl_list, d_link_off, d_hz_m, d_hz_l, d_seq_stack, d_seq_rec;
+    DBuf<uint8_t> d_pend_req, d_answers;
+    std::vector<uint32_t> h_hz_m, h_hz_l;
+    // pre-request snapshot of the dynamic state: a refused request is rolled back (side-effect free) and may then be
+    // answered by the sequential executor
+    DBuf<uint8_t> d_snap_props;
+    DBuf<uint64_t> d_snap_nib;
+    DBuf<unsigned char> d_snap_val;
+    bool snap_valid = false;
+    std::vector<int64_t> tr_var;  // trace: TracedInferenceExecution.variable_id
 
     // device state
     DBuf<uint32_t> d_dep_off, d_dep_ids, d_nib_off, d_lis_off, d_lis_ids, d_lis_slot, d_done, d_visit, d_probe;
@@ -893,6 +1278,7 @@ struct DeviceEngine {
         }
         CXB_CUDA(cudaSetDevice(device));
         CXB_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+        if (const char* e = getenv("CXB_STRICT")) strict = atoi(e) != 0;
         CXB_CUDA(d_flags.reserve(4));
         CXB_CUDA(d_counters.reserve(8));
         CXB_CUDA(d_kind_count.reserve(8));
@@ -900,6 +1286,7 @@ struct DeviceEngine {
         CXB_CUDA(h_flags.reserve(4));
         CXB_CUDA(h_kind_count.reserve(8));
         CXB_CUDA(cudaMemsetAsync(d_flags.p, 0, 4 * sizeof(int), stream));
+        CXB_CUDA(cudaMemsetAsync(d_counters.p, 0, 8 * sizeof(uint32_t), stream));
         CXB_CUDA(cudaMemsetAsync(d_kind_count.p, 0, 8 * sizeof(unsigned long long), stream));
         return CXB_OK;
     }
@@ -925,6 +1312,11 @@ struct DeviceEngine {
         v.done_epoch = d_done.p;
         v.visit_epoch = d_visit.p;
         v.probe_epoch = has_weak ? d_probe.p : nullptr;
+        v.mark2 = d_mark2.p;
+        v.nl_epoch = (has_nl && strict) ? d_nl_epoch.p : nullptr;
+        v.nl_list = d_nl_list.p;
+        v.nl_cnt = d_counters.p + 4;
+        v.strict = strict ? 1 : 0;
         v.front_epoch = d_front_epoch.p;
         v.front = d_front.p;
         v.key_base = d_key_base.p;
@@ -992,7 +1384,7 @@ struct DeviceEngine {
             sfac[s] = (int32_t)g.sfac[s];
             if (k == CXB_KIND_M2F || k == CXB_KIND_PRODUCT || k == CXB_KIND_MARGINAL)
                 rkey[s] = KEY_COMBINE;
-            else if (k == CXB_KIND_M2V || (k == CXB_KIND_JOINT && g.sfac[s] >= 0 && g.sfac[s] < g.n_ids && g.is_factor[g.sfac[s]]))
+            else if ((k == CXB_KIND_M2V || k == CXB_KIND_JOINT) && g.sfac[s] >= 0 && g.sfac[s] < g.n_ids && g.is_factor[g.sfac[s]])
                 rkey[s] = (uint8_t)key_of[g.ftype[g.sfac[s]]];  // a JointMarginal is computed by its factor's rule
             else
                 rkey[s] = (uint8_t)key_no_rule();
@@ -1110,13 +1502,20 @@ struct DeviceEngine {
                 CXB_CUDA(d_probe.reserve(Np));
                 CXB_CUDA(cudaMemsetAsync(d_probe.p, 0, Np * 4, stream));
             }
-            CXB_CUDA(d_list_a.reserve(has_weak ? 2 * Np : Np));  // a signal enters a level's lists once, and once more as a probe
-            CXB_CUDA(d_list_b.reserve(has_weak ? 2 * Np : Np));
+            // a signal enters a level's lists once, once more with MULTI_BIT (strict rule D), and once more as a probe
+            CXB_CUDA(d_list_a.reserve((has_weak ? 3 : 2) * Np));
+            CXB_CUDA(d_list_b.reserve((has_weak ? 3 : 2) * Np));
             CXB_CUDA(d_front.reserve(Np));
-            CXB_CUDA(cudaMemsetAsync(d_done.p, 0, Np * 4, stream));
-            CXB_CUDA(cudaMemsetAsync(d_visit.p, 0, Np * 4, stream));
-            CXB_CUDA(cudaMemsetAsync(d_front_epoch.p, 0, Np * 4, stream));
-            req_epoch = lvl_epoch = 0;
+            CXB_CUDA(d_mark2.reserve(Np));
+            size_t n_nl = 0;
+            for (uint8_t fl : g.e_flags) n_nl += (fl & E_LISTEN) ? 0 : 1;
+            has_nl = n_nl > 0;
+            if (has_nl) {
+                CXB_CUDA(d_nl_epoch.reserve(Np));
+                CXB_CUDA(d_nl_list.reserve(n_nl));
+            }
+            if ((st = reset_epochs())) return st;
+            snap_valid = false;
             if ((st = build_keys())) return st;
             CXB_CUDA(d_key_count.reserve(512));
             CXB_CUDA(cudaStreamSynchronize(stream));
@@ -1128,6 +1527,45 @@ struct DeviceEngine {
         }
         if (rules_dirty && (st = upload_rules())) return st;
         host_state_valid = false;  // whatever runs next may mutate the device state
+        return CXB_OK;
+    }
+
+    // epoch stamps replace clearing; before a counter can wrap (the level epoch has 29 bits in mark2) everything is cleared
+    int32_t reset_epochs() {
+        const size_t Np = std::max<size_t>((size_t)g.n_sig(), 1);
+        CXB_CUDA(cudaMemsetAsync(d_done.p, 0, Np * 4, stream));
+        CXB_CUDA(cudaMemsetAsync(d_visit.p, 0, Np * 4, stream));
+        CXB_CUDA(cudaMemsetAsync(d_front_epoch.p, 0, Np * 4, stream));
+        CXB_CUDA(cudaMemsetAsync(d_mark2.p, 0, Np * 4, stream));
+        if (has_weak) CXB_CUDA(cudaMemsetAsync(d_probe.p, 0, Np * 4, stream));
+        if (has_nl) CXB_CUDA(cudaMemsetAsync(d_nl_epoch.p, 0, Np * 4, stream));
+        CXB_CUDA(cudaMemsetAsync(d_counters.p, 0, 8 * sizeof(uint32_t), stream));
+        req_epoch = lvl_epoch = 0;
+        return CXB_OK;
+    }
+    int32_t take_snapshot() {
+        snap_valid = false;
+        const size_t N = n_uploaded, vb = N * dim * esz();
+        if (d_snap_props.reserve(std::max<size_t>(N, 1)) != cudaSuccess || d_snap_nib.reserve(std::max<size_t>(csr.nib.size(), 1)) != cudaSuccess ||
+            d_snap_val.reserve(std::max<size_t>(vb, 1)) != cudaSuccess) {
+            cudaGetLastError();  // not enough memory for a copy of the state: run without rollback
+            return CXB_OK;
+        }
+        if (N) CXB_CUDA(cudaMemcpyAsync(d_snap_props.p, d_props.p, N, cudaMemcpyDeviceToDevice, stream));
+        if (!csr.nib.empty()) CXB_CUDA(cudaMemcpyAsync(d_snap_nib.p, d_nib.p, csr.nib.size() * sizeof(uint64_t), cudaMemcpyDeviceToDevice, stream));
+        if (vb) CXB_CUDA(cudaMemcpyAsync(d_snap_val.p, d_val.p, vb, cudaMemcpyDeviceToDevice, stream));
+        snap_valid = true;
+        return CXB_OK;
+    }
+    int32_t restore_snapshot() {
+        if (!snap_valid) return CXB_OK;
+        const size_t N = n_uploaded, vb = N * dim * esz();
+        if (N) CXB_CUDA(cudaMemcpyAsync(d_props.p, d_snap_props.p, N, cudaMemcpyDeviceToDevice, stream));
+        if (!csr.nib.empty()) CXB_CUDA(cudaMemcpyAsync(d_nib.p, d_snap_nib.p, csr.nib.size() * sizeof(uint64_t), cudaMemcpyDeviceToDevice, stream));
+        if (vb) CXB_CUDA(cudaMemcpyAsync(d_val.p, d_snap_val.p, vb, cudaMemcpyDeviceToDevice, stream));
+        CXB_CUDA(cudaMemsetAsync(d_flags.p, 0, 4 * sizeof(int), stream));
+        CXB_CUDA(cudaMemsetAsync(d_counters.p, 0, 8 * sizeof(uint32_t), stream));
+        CXB_CUDA(cudaStreamSynchronize(stream));
         return CXB_OK;
     }
 
@@ -1232,7 +1670,7 @@ struct DeviceEngine {
 
     // breadth-first reachability from the seeds in d_list_a (length in d_counters[0]): pushes pending signals to the
     // frontier. `bfs_guess` steps are launched back to back; the host only looks at the result afterwards.
-    int32_t bfs(bool use_done) {
+    int32_t bfs(int visit_flags) {  // bit 0: skip (probe) signals done in this request, bit 1: first level of a request (strict rule A)
         View v = view();
         uint32_t N = (uint32_t)g.n_sig();
         int which = 0;  // list holding the current input
@@ -1242,7 +1680,7 @@ struct DeviceEngine {
                 uint32_t* out = which ? d_list_a.p : d_list_b.p;
                 CXB_CUDA(cudaMemsetAsync(d_counters.p + (which ^ 1), 0, sizeof(uint32_t), stream));
                 CXB_LAUNCH(k_bfs, stride_grid(N), 256, 0, stream, v, in, d_counters.p + which, out, d_counters.p + (which ^ 1),
-                           lvl_epoch, req_epoch, use_done ? 1 : 0);
+                           lvl_epoch, req_epoch, visit_flags);
                 which ^= 1;
             }
             // one round trip: remaining BFS work + per-key frontier sizes + error flag
@@ -1274,8 +1712,28 @@ struct DeviceEngine {
             err = "rule kernel rejected its arguments (no dependencies, symbol out of range or unknown rule kind)";
             return CXB_ERR_NO_RULE;
         }
+        if (f & ERR_SEQ_OVERFLOW) {
+            err = "sequential schedule: the traversal is deeper than the number of signals (a cycle of intermediate dependencies; the reference "
+                  "recurses without end here)";
+            return CXB_ERR_STATE;
+        }
         if (f & ERR_INDEPENDENCE)
             err = "level-synchronous schedule out of contract: frontier member depends on another member";
+        else if (f & ERR_WORK_BENEATH_PENDING)
+            err = "level-synchronous schedule out of contract: a requested marginal was already pending when the request arrived and there is "
+                  "pending work beneath it (the reference gives it exactly one traversal: order-dependent)";
+        else if (f & ERR_STALE_BENEATH)
+            err = "level-synchronous schedule out of contract: a signal reached by the request is not pending but holds leftover freshness "
+                  "from an earlier, incomplete request (order-dependent in the reference)";
+        else if (f & ERR_REVISITED)
+            err = "level-synchronous schedule out of contract: a pending signal reached more than once has a pending dependency "
+                  "(order-dependent in the reference)";
+        else if (f & ERR_NONLISTEN)
+            err = "level-synchronous schedule out of contract: a non-listening notification decides a pending state "
+                  "(in the reference it depends on the order inside this level / request)";
+        else if (f & ERR_FINAL_ORDER)
+            err = "level-synchronous schedule out of contract: a final-phase signal depends on another final-phase signal across the "
+                  "reference's per-variable order (marginal, then linked signals, variable by variable)";
         else if (f & ERR_LEFTOVER_FRESH)
             err = "level-synchronous schedule out of contract: a requested marginal holds leftover freshness from an earlier, incomplete "
                   "request (order-dependent in the reference)";
@@ -1326,9 +1784,13 @@ struct DeviceEngine {
             }
             CXB_CUDA(cudaEventRecord(tr_ev0, stream));
         }
-        for (auto& c : chunks) CXB_LAUNCH(k_check_independent, cdiv(c.total, 256), 256, 0, stream, v, c, lvl_epoch);
-        if ((st = launch_rules(total))) return st;
+        for (auto& c : chunks) CXB_LAUNCH(k_check_independent, cdiv(c.total, 256), 256, 0, stream, v, c, lvl_epoch, req_epoch, check_mode);
+        if ((st = launch_rules(total))) return st;  // rule and set_value! kernels return at once when a check refused the level
         for (auto& c : chunks) CXB_LAUNCH(k_apply, cdiv(c.total, 256), 256, 0, stream, v, c, req_epoch, check_mode);
+        if (check_mode == 1 && v.nl_epoch) {  // strict rule E, second half
+            CXB_LAUNCH(k_check_nl, std::min(cdiv(std::max<size_t>(d_nl_list.cap, 1), 256), 1184u), 256, 0, stream, v, req_epoch);
+            CXB_CUDA(cudaMemsetAsync(d_counters.p + 4, 0, sizeof(uint32_t), stream));
+        }
         stats.updates += total;
         if (trace_on) {
             CXB_CUDA(cudaEventRecord(tr_ev1, stream));
@@ -1350,6 +1812,7 @@ struct DeviceEngine {
                 tr_level.push_back(level_tag);
                 tr_sid.push_back(s);
                 tr_ns.push_back(each);
+                tr_var.push_back(g.svar[s]);
             }
         }
         return CXB_OK;
@@ -1358,11 +1821,15 @@ struct DeviceEngine {
     int32_t request(int64_t n, const int64_t* ids) {
         int32_t st = ensure_device();
         if (st) return st;
+        if (n < 0 || (n > 0 && !ids)) {
+            err = "request_inference_for: bad id list";
+            return CXB_ERR_BAD_ARG;
+        }
         bool same = req_uploaded && (int64_t)req_ids.size() == n && (n == 0 || !std::memcmp(req_ids.data(), ids, n * 8));
         if (!same) {
-            req_ids.assign(ids, ids + n);
-            h_req_marg.resize(n);
-            h_link_ids.clear();
+            // everything is validated and built in temporaries; the cached request is replaced only after a successful upload
+            req_uploaded = false;
+            std::vector<uint32_t> marg((size_t)n), loff((size_t)n + 1, 0), lids;
             // linked signals per variable, in link order (src/model_engine.jl:80-83)
             if (links_dirty) {
                 lnk_off.assign((size_t)g.n_ids + 1, 0);
@@ -1379,31 +1846,142 @@ struct DeviceEngine {
                     err = "request_inference_for: not a variable id";
                     return CXB_ERR_BAD_ARG;
                 }
-                h_req_marg[i] = (uint32_t)g.marg_of[v];
-                for (uint32_t k = lnk_off[v]; k < lnk_off[v + 1]; ++k) h_link_ids.push_back(lnk_ids[k]);
+                marg[i] = (uint32_t)g.marg_of[v];
+                for (uint32_t k = lnk_off[v]; k < lnk_off[v + 1]; ++k) lids.push_back(lnk_ids[k]);
+                loff[i + 1] = (uint32_t)lids.size();
             }
-            if ((st = up(d_req_marg, h_req_marg.data(), (size_t)n))) return st;
-            if ((st = up(d_link_ids, h_link_ids.data(), h_link_ids.size()))) return st;
+            std::vector<uint32_t> hzm, hzl;
+            final_phase_hazards(marg, loff, lids, hzm, hzl);
+            if ((st = up(d_req_marg, marg.data(), (size_t)n))) return st;
+            if ((st = up(d_link_ids, lids.data(), lids.size()))) return st;
+            if ((st = up(d_link_off, loff.data(), loff.size()))) return st;
+            if ((st = up(d_hz_m, hzm.data(), hzm.size()))) return st;
+            if ((st = up(d_hz_l, hzl.data(), hzl.size()))) return st;
             CXB_CUDA(d_ready.reserve(std::max<size_t>(n, 1)));
+            CXB_CUDA(d_pend_req.reserve(std::max<size_t>(n, 1)));
             CXB_CUDA(cudaStreamSynchronize(stream));
+            req_ids.assign(ids, ids + n);
+            h_req_marg.swap(marg);
+            h_link_ids.swap(lids);
+            h_link_off.swap(loff);
+            h_hz_m.swap(hzm);
+            h_hz_l.swap(hzl);
             req_uploaded = true;
         }
         n_req = (uint32_t)n;
         n_links = (uint32_t)h_link_ids.size();
+        if (req_epoch > 0xFFFF0000u || lvl_epoch > 0x1F000000u)  // before an epoch counter can wrap: clear the stamps
+            if ((st = reset_epochs())) return st;
         ++req_epoch;
         CXB_CUDA(cudaMemsetAsync(d_ready.p, 0, std::max<size_t>(n, 1), stream));
         if (n_req + n_links)
             CXB_LAUNCH(k_request, cdiv((size_t)n_req + n_links, 256), 256, 0, stream, view(), d_req_marg.p, d_link_ids.p, n_req, n_links);
         return CXB_OK;
     }
+    // Rule F of the level schedule (the oracle's update_lvl states it in the same words). The reference's final phase goes
+    // variable by variable - marginal(v_i), then the linked signals of v_i (src/inference_engine.jl:610-628) - while a level
+    // schedule computes all pending marginals, then all pending linked signals. The orders differ only when one final-phase
+    // candidate depends on another across that order. From the request and the dependency lists (host, once per distinct
+    // request) two lists are made: signals that must NOT be pending when the marginal level starts (F1: a marginal that a
+    // linked signal of an EARLIER requested variable depends on; F2: a marginal that depends on a linked signal of an earlier
+    // variable; F4: a requested marginal another requested marginal depends on) and when the linked level starts (F3: a
+    // linked signal another linked signal depends on). The device tests them with k_check_not_pending.
+    void final_phase_hazards(const std::vector<uint32_t>& marg, const std::vector<uint32_t>& loff, const std::vector<uint32_t>& lids,
+                             std::vector<uint32_t>& hzm, std::vector<uint32_t>& hzl) {
+        const size_t n = marg.size();
+        if (n == 0) return;
+        // kinds that can be a hazard target at all: dependencies are looked up only when their kind is among them
+        unsigned link_kinds = 0;
+        for (uint32_t l : lids) link_kinds |= 1u << g.kind[l];
+        std::vector<std::pair<uint32_t, uint32_t>> req_pos, link_pos;  // (signal, last request position) / (signal, first position)
+        auto build_req = [&]() {
+            req_pos.reserve(n);
+            for (size_t i = 0; i < n; ++i) req_pos.emplace_back(marg[i], (uint32_t)i);
+            std::sort(req_pos.begin(), req_pos.end());
+            size_t w = 0;
+            for (size_t r = 0; r < req_pos.size(); ++r) {  // keep the LAST position of a repeated marginal
+                if (w && req_pos[w - 1].first == req_pos[r].first) req_pos[w - 1].second = req_pos[r].second;
+                else req_pos[w++] = req_pos[r];
+            }
+            req_pos.resize(w);
+        };
+        auto build_link = [&]() {
+            link_pos.reserve(lids.size());
+            for (size_t i = 0; i < n; ++i)
+                for (uint32_t k = loff[i]; k < loff[i + 1]; ++k) link_pos.emplace_back(lids[k], (uint32_t)i);
+            std::sort(link_pos.begin(), link_pos.end());
+            size_t w = 0;
+            for (size_t r = 0; r < link_pos.size(); ++r)  // sorted: the FIRST position of a repeated signal comes first
+                if (!w || link_pos[w - 1].first != link_pos[r].first) link_pos[w++] = link_pos[r];
+            link_pos.resize(w);
+        };
+        auto find = [](const std::vector<std::pair<uint32_t, uint32_t>>& v, uint32_t sid) -> int64_t {
+            auto it = std::lower_bound(v.begin(), v.end(), std::make_pair(sid, 0u));
+            return (it != v.end() && it->first == sid) ? (int64_t)it->second : -1;
+        };
+        const unsigned marg_kind = 1u << CXB_KIND_MARGINAL;
+        bool req_built = false, link_built = false;
+        for (size_t i = 0; i < n; ++i) {
+            const uint32_t m = marg[i];
+            for (uint32_t k = csr.dep_off[m]; k < csr.dep_off[m + 1]; ++k) {
+                const uint32_t d = csr.dep_ids[k];
+                const unsigned kb = 1u << g.kind[d];
+                if ((kb & marg_kind) && d != m) {  // F4
+                    if (!req_built) build_req(), req_built = true;
+                    if (find(req_pos, d) >= 0) hzm.push_back(d);
+                }
+                if (kb & link_kinds) {  // F2
+                    if (!link_built) build_link(), link_built = true;
+                    const int64_t j = find(link_pos, d);
+                    if (j >= 0 && j < (int64_t)i) hzm.push_back(m);
+                }
+            }
+            for (uint32_t q = loff[i]; q < loff[i + 1]; ++q) {
+                const uint32_t l = lids[q];
+                for (uint32_t k = csr.dep_off[l]; k < csr.dep_off[l + 1]; ++k) {
+                    const uint32_t d = csr.dep_ids[k];
+                    const unsigned kb = 1u << g.kind[d];
+                    if (kb & marg_kind) {  // F1
+                        if (!req_built) build_req(), req_built = true;
+                        const int64_t j = find(req_pos, d);
+                        if (j > (int64_t)i) hzm.push_back(d);
+                    }
+                    if ((kb & link_kinds) && d != l) {  // F3
+                        if (!link_built) build_link(), link_built = true;
+                        if (find(link_pos, d) >= 0) hzl.push_back(d);
+                    }
+                }
+            }
+        }
+        std::sort(hzm.begin(), hzm.end());
+        hzm.erase(std::unique(hzm.begin(), hzm.end()), hzm.end());
+        std::sort(hzl.begin(), hzl.end());
+        hzl.erase(std::unique(hzl.begin(), hzl.end()), hzl.end());
+    }
 
     // one level of the frontier: seeds -> BFS -> per-key segments on the host
-    int32_t find_frontier(bool use_done, bool use_keys) {
+    int32_t find_frontier(bool use_done, bool use_keys, bool first_level = false) {
         int32_t st = begin_level(use_keys);
         if (st) return st;
-        if (n_req) CXB_LAUNCH(k_seeds, cdiv(n_req, 256), 256, 0, stream, d_req_marg.p, d_ready.p, n_req, d_list_a.p, d_counters.p);
-        return bfs(use_done);
+        const int flags = (use_done ? 1 : 0) | (first_level ? 2 : 0);
+        if (first_level && strict && n_pend_at_req > 0) {
+            // strict rule B: the marginals that were pending when the request arrived are traversed first, alone - the
+            // reference gives such a variable one traversal and takes its marginal, so nothing may be pending beneath it
+            CXB_LAUNCH(k_seeds, cdiv(n_req, 256), 256, 0, stream, d_req_marg.p, d_pend_req.p, (uint8_t)1, n_req, d_list_a.p, d_counters.p);
+            if ((st = bfs(flags))) return st;
+            if (cur_total) {
+                err = "level-synchronous schedule out of contract: a requested marginal was already pending when the request arrived and "
+                      "there is pending work beneath it (the reference gives it exactly one traversal: order-dependent)";
+                return CXB_ERR_OUT_OF_CONTRACT;
+            }
+            CXB_CUDA(cudaMemsetAsync(d_counters.p, 0, 2 * sizeof(uint32_t), stream));
+            CXB_LAUNCH(k_seeds, cdiv(n_req, 256), 256, 0, stream, d_req_marg.p, d_pend_req.p, (uint8_t)0, n_req, d_list_a.p, d_counters.p);
+            return bfs(flags);
+        }
+        if (n_req) CXB_LAUNCH(k_seeds, cdiv(n_req, 256), 256, 0, stream, d_req_marg.p, d_ready.p, (uint8_t)0, n_req, d_list_a.p, d_counters.p);
+        return bfs(flags);
     }
+    int n_pend_at_req = 0;
 
     int32_t scan(std::vector<int64_t>& out) {
         if (!req_uploaded) {
@@ -1428,6 +2006,106 @@ struct DeviceEngine {
         return !trace_on && (small_family || small_categorical) && g.n_sig() <= 65536;
     }
     int32_t update_resident(unsigned long long launches0) {
+        const int nk = n_keys();
+        int32_t st = upload_key_tables();
+        if (st) return st;
+        cur_use_keys = true;
+        ResidentArgs a{};
+        a.req_marg = d_req_marg.p;
+        a.link_ids = d_link_ids.p;
+        a.ready = d_ready.p;
+        a.n_req = n_req;
+        a.n_links = n_links;
+        a.list_a = d_list_a.p;
+        a.list_b = d_list_b.p;
+        a.req_epoch = req_epoch;
+        a.lvl_epoch0 = lvl_epoch;
+        a.n_keys = nk;
+        a.family = family;
+        a.key_rule = d_key_rule.p;
+        a.key_param = d_key_param.p;
+        a.fparam = d_fparam.p;
+        a.tables = d_tables.p;
+        a.key_table = d_key_table.p;
+        a.key_nsym = d_key_nsym.p;
+        a.out = d_res_out.p;
+        a.pend_at_req = d_pend_req.p;
+        a.hz_m = d_hz_m.p;
+        a.hz_l = d_hz_l.p;
+        a.n_hz_m = (uint32_t)h_hz_m.size();
+        a.n_hz_l = (uint32_t)h_hz_l.size();
+        int threads = 1024;  // measured on the T = 1000 chain: 1024 threads 19 ms, 256 threads 27 ms (the per-level passes over the requested marginals dominate)
+        if (const char* e = getenv("CXB_ENGINE_RESIDENT_THREADS")) threads = std::max(32, std::min(1024, atoi(e) / 32 * 32));
+        if (dtype == CXB_F32)
+            CXB_LAUNCH(k_update_resident<float>, 1, threads, 0, stream, view(), (float*)d_val.p, a);
+        else
+            CXB_LAUNCH(k_update_resident<double>, 1, threads, 0, stream, view(), (double*)d_val.p, a);
+        CXB_CUDA(cudaMemcpyAsync(h_res_out.p, d_res_out.p, 8 * sizeof(long long), cudaMemcpyDeviceToHost, stream));
+        CXB_CUDA(cudaMemcpyAsync(h_kind_count.p, d_kind_count.p, 6 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, stream));
+        CXB_CUDA(cudaMemcpyAsync(h_flags.p, d_flags.p, sizeof(int), cudaMemcpyDeviceToHost, stream));
+        CXB_CUDA(cudaStreamSynchronize(stream));
+        lvl_epoch = (uint32_t)h_res_out.p[4];
+        stats.levels = h_res_out.p[0];
+        stats.updates = h_res_out.p[1];
+        stats.final_marginals = h_res_out.p[2];
+        stats.final_linked = h_res_out.p[3];
+        for (int k = 0; k < 6; ++k) stats.updates_by_kind[k] = (int64_t)h_kind_count.p[k];
+        stats.kernel_launches = (int64_t)(g_kernel_launches - launches0);
+        const int f = h_flags.p[0];
+        if (f & ERR_NO_RULE_KEY) return no_rule_status();
+        return flags_to_status(f);
+    }
+
+    // Can the sequential executor (and the resident level loop) evaluate this model's rules? (small fixed-size values,
+    // categorical values up to 64 states)
+    bool small_values() const {
+        return (family != CXB_FAMILY_CATEGORICAL && dim <= 8) || (family == CXB_FAMILY_CATEGORICAL && dim <= 64);
+    }
+    static constexpr int64_t SEQ_FALLBACK_LIMIT = 1 << 22;  // signals: above it a refused request stays refused under AUTO
+
+    // update_marginals!(engine, ids), src/inference_engine.jl:559-632: schedule selection (include/cortex_b200.h)
+    int32_t update(int64_t n, const int64_t* ids) {
+        const unsigned long long launches0 = g_kernel_launches;
+        stats = cxb_update_stats{};
+        tr_level.clear();
+        tr_sid.clear();
+        tr_ns.clear();
+        tr_var.clear();
+        last_ran = 0;
+        int32_t st = ensure_device();
+        if (st) return st;
+        CXB_CUDA(cudaMemsetAsync(d_kind_count.p, 0, 8 * sizeof(unsigned long long), stream));
+        if (schedule == CXB_SCHEDULE_SEQUENTIAL || (schedule == CXB_SCHEDULE_AUTO && hand_wired && small_values())) {
+            if (!small_values()) {
+                err = "the sequential schedule evaluates small fixed-size values and categorical values up to 64 states only";
+                return CXB_ERR_BAD_ARG;
+            }
+            st = update_seq(n, ids);
+            stats.kernel_launches = (int64_t)(g_kernel_launches - launches0);
+            return st;
+        }
+        if ((st = take_snapshot())) return st;  // a refused request is rolled back
+        st = update_level(n, ids, launches0);
+        if (st == CXB_ERR_OUT_OF_CONTRACT && snap_valid) {
+            const std::string why = err;
+            int32_t st2 = restore_snapshot();
+            if (st2) return st2;
+            err = why;
+            if (schedule == CXB_SCHEDULE_AUTO && small_values() && g.n_sig() <= SEQ_FALLBACK_LIMIT) {
+                stats = cxb_update_stats{};
+                tr_level.clear();
+                tr_sid.clear();
+                tr_ns.clear();
+                CXB_CUDA(cudaMemsetAsync(d_kind_count.p, 0, 8 * sizeof(unsigned long long), stream));
+                st = update_seq(n, ids);
+            }
+        }
+        stats.kernel_launches = (int64_t)(g_kernel_launches - launches0);
+        return st;
+    }
+
+    // per-key rule tables of the single-launch kernels (k_update_resident, k_seq)
+    int32_t upload_key_tables() {
         const int nk = n_keys();
         h_key_rule.assign((size_t)nk, -2);
         h_key_param.assign((size_t)nk, 1.0);
@@ -1457,18 +2135,31 @@ struct DeviceEngine {
         CXB_CUDA(d_res_out.reserve(8));
         CXB_CUDA(h_res_out.reserve(8));
         CXB_CUDA(cudaMemsetAsync(d_res_out.p, 0, 8 * sizeof(long long), stream));
+        return CXB_OK;
+    }
+
+    // one launch of the sequential executor (k_seq). mode 0: update_marginals!, 1: scan, 2: process_dependencies!(table)
+    int32_t run_seq(int mode, uint32_t root, bool retry, const uint8_t* answers, size_t rec_cap) {
+        int32_t st = upload_key_tables();
+        if (st) return st;
+        const size_t N = std::max<size_t>((size_t)g.n_sig(), 1);
+        CXB_CUDA(d_seq_stack.reserve(3 * (N + 1)));
+        CXB_CUDA(d_seq_rec.reserve(std::max<size_t>(rec_cap, 1)));
+        if (answers) {
+            CXB_CUDA(d_answers.reserve(N));
+            CXB_CUDA(cudaMemcpyAsync(d_answers.p, answers, (size_t)g.n_sig(), cudaMemcpyHostToDevice, stream));
+        }
         cur_use_keys = true;
-        ResidentArgs a{};
+        SeqArgs a{};
         a.req_marg = d_req_marg.p;
+        a.link_off = d_link_off.p;
         a.link_ids = d_link_ids.p;
         a.ready = d_ready.p;
-        a.n_req = n_req;
-        a.n_links = n_links;
-        a.list_a = d_list_a.p;
-        a.list_b = d_list_b.p;
-        a.req_epoch = req_epoch;
-        a.lvl_epoch0 = lvl_epoch;
-        a.n_keys = nk;
+        a.n_req = mode == 2 ? 0u : n_req;
+        a.stack = d_seq_stack.p;
+        a.stack_cap = (uint32_t)N + 1;
+        a.mode = mode;
+        a.n_keys = n_keys();
         a.family = family;
         a.key_rule = d_key_rule.p;
         a.key_param = d_key_param.p;
@@ -1476,60 +2167,139 @@ struct DeviceEngine {
         a.tables = d_tables.p;
         a.key_table = d_key_table.p;
         a.key_nsym = d_key_nsym.p;
+        a.rec = d_seq_rec.p;
+        a.rec_cap = (uint32_t)std::min<size_t>(rec_cap, 0xFFFFFFFFu);
+        a.answers = answers ? d_answers.p : nullptr;
+        a.root = root;
+        a.retry = retry ? 1 : 0;
         a.out = d_res_out.p;
-        int threads = 1024;  // measured on the T = 1000 chain: 1024 threads 19 ms, 256 threads 27 ms (the per-level passes over the requested marginals dominate)
-        if (const char* e = getenv("CXB_ENGINE_RESIDENT_THREADS")) threads = std::max(32, std::min(1024, atoi(e) / 32 * 32));
         if (dtype == CXB_F32)
-            CXB_LAUNCH(k_update_resident<float>, 1, threads, 0, stream, view(), (float*)d_val.p, a);
+            CXB_LAUNCH(k_seq<float>, 1, 32, 0, stream, view(), (float*)d_val.p, a);
         else
-            CXB_LAUNCH(k_update_resident<double>, 1, threads, 0, stream, view(), (double*)d_val.p, a);
+            CXB_LAUNCH(k_seq<double>, 1, 32, 0, stream, view(), (double*)d_val.p, a);
         CXB_CUDA(cudaMemcpyAsync(h_res_out.p, d_res_out.p, 8 * sizeof(long long), cudaMemcpyDeviceToHost, stream));
         CXB_CUDA(cudaMemcpyAsync(h_kind_count.p, d_kind_count.p, 6 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, stream));
         CXB_CUDA(cudaMemcpyAsync(h_flags.p, d_flags.p, sizeof(int), cudaMemcpyDeviceToHost, stream));
         CXB_CUDA(cudaStreamSynchronize(stream));
-        lvl_epoch = (uint32_t)h_res_out.p[4];
+        return CXB_OK;
+    }
+    int32_t no_rule_status() {
+        cudaMemsetAsync(d_flags.p, 0, sizeof(int), stream);
+        const int k = (int)h_res_out.p[5];
+        if (k == key_no_rule())
+            err = "Unprocessed signal variant (no rule for an Unspecified / JointMarginal signal)";
+        else
+            err = "The function `compute_message_to_variable!` is not implemented for factor type " + std::to_string(key_ftype[k - 1]);
+        return CXB_ERR_NO_RULE;
+    }
+    // the reference loop literally (k_seq); with a trace: the reference's round numbers, execution order and variable ids
+    int32_t update_seq(int64_t n, const int64_t* ids) {
+        int32_t st = request(n, ids);
+        if (st) return st;
+        const size_t N = std::max<size_t>((size_t)g.n_sig(), 1);
+        const size_t rec_cap = trace_on ? 3 * std::max<size_t>(8 * N, 65536) : 0;
+        if (trace_on) {
+            if (!tr_ev0) {
+                CXB_CUDA(cudaEventCreate(&tr_ev0));
+                CXB_CUDA(cudaEventCreate(&tr_ev1));
+            }
+            CXB_CUDA(cudaEventRecord(tr_ev0, stream));
+        }
+        if ((st = run_seq(0, 0, true, nullptr, rec_cap))) return st;
+        last_ran = CXB_SCHEDULE_SEQUENTIAL;
         stats.levels = h_res_out.p[0];
         stats.updates = h_res_out.p[1];
         stats.final_marginals = h_res_out.p[2];
         stats.final_linked = h_res_out.p[3];
         for (int k = 0; k < 6; ++k) stats.updates_by_kind[k] = (int64_t)h_kind_count.p[k];
-        stats.kernel_launches = (int64_t)(g_kernel_launches - launches0);
-        const int f = h_flags.p[0];
-        if (f & ERR_NO_RULE_KEY) {
-            cudaMemsetAsync(d_flags.p, 0, sizeof(int), stream);
-            const int k = (int)h_res_out.p[5];
-            if (k == key_no_rule())
-                err = "Unprocessed signal variant (no rule for an Unspecified / JointMarginal signal)";
-            else
-                err = "The function `compute_message_to_variable!` is not implemented for factor type " + std::to_string(key_ftype[k - 1]);
-            return CXB_ERR_NO_RULE;
+        if (trace_on) {
+            CXB_CUDA(cudaEventRecord(tr_ev1, stream));
+            const size_t cnt = std::min<size_t>((size_t)h_res_out.p[6], rec_cap / 3);
+            std::vector<uint32_t> rec(3 * cnt);
+            if (cnt) CXB_CUDA(cudaMemcpyAsync(rec.data(), d_seq_rec.p, rec.size() * 4, cudaMemcpyDeviceToHost, stream));
+            CXB_CUDA(cudaStreamSynchronize(stream));
+            float ms = 0.0f;
+            CXB_CUDA(cudaEventElapsedTime(&ms, tr_ev0, tr_ev1));
+            const int64_t each = std::max<int64_t>((int64_t)(ms * 1e6 / std::max<size_t>(cnt, 1)), 1);
+            for (size_t k = 0; k < cnt; ++k) {
+                tr_level.push_back(rec[3 * k] == 0xFFFFFFFFu ? -1 : (int64_t)rec[3 * k]);
+                tr_var.push_back(req_ids[rec[3 * k + 1]]);
+                tr_sid.push_back(rec[3 * k + 2]);
+                tr_ns.push_back(each);
+            }
         }
+        const int f = h_flags.p[0];
+        if (f & ERR_NO_RULE_KEY) return no_rule_status();
         return flags_to_status(f);
     }
+    // scan_inference_request in the reference's own order (duplicates included)
+    int32_t scan_dfs(std::vector<int64_t>& out) {
+        if (!req_uploaded) {
+            err = "scan_inference_request: no request";
+            return CXB_ERR_STATE;
+        }
+        if (!small_values()) {
+            err = "scan in depth-first order needs the sequential executor (small values)";
+            return CXB_ERR_BAD_ARG;
+        }
+        size_t cap = std::max<size_t>(4 * (size_t)g.n_sig(), 1024);
+        for (;;) {
+            int32_t st = run_seq(1, 0, true, nullptr, cap);
+            if (st) return st;
+            if ((st = flags_to_status(h_flags.p[0]))) return st;
+            const size_t cnt = (size_t)h_res_out.p[6];
+            if (cnt > cap) {  // scanning only caches is_pending: running it again with more room is harmless
+                cap = cnt;
+                continue;
+            }
+            std::vector<uint32_t> rec(cnt);
+            if (cnt) CXB_CUDA(cudaMemcpy(rec.data(), d_seq_rec.p, cnt * 4, cudaMemcpyDeviceToHost));
+            out.assign(rec.begin(), rec.end());
+            return CXB_OK;
+        }
+    }
+    int32_t process_dependencies_table(int64_t s, bool retry, const uint8_t* answers, std::vector<int64_t>& visited, bool& processed) {
+        int32_t st = ensure_device();
+        if (st) return st;
+        size_t cap = std::max<size_t>(8 * (size_t)g.n_sig(), 1024);
+        if ((st = run_seq(2, (uint32_t)s, retry, answers, cap))) return st;
+        if ((st = flags_to_status(h_flags.p[0]))) return st;
+        const size_t cnt = std::min<size_t>((size_t)h_res_out.p[6], cap);
+        std::vector<uint32_t> rec(cnt);
+        if (cnt) CXB_CUDA(cudaMemcpy(rec.data(), d_seq_rec.p, cnt * 4, cudaMemcpyDeviceToHost));
+        visited.assign(rec.begin(), rec.end());
+        processed = h_res_out.p[7] != 0;
+        return CXB_OK;
+    }
 
-    int32_t update(int64_t n, const int64_t* ids) {
-        unsigned long long launches0 = g_kernel_launches;
-        stats = cxb_update_stats{};
-        tr_level.clear();
-        tr_sid.clear();
-        tr_ns.clear();
+    // the level-synchronous schedule under its contract checks
+    int32_t update_level(int64_t n, const int64_t* ids, unsigned long long launches0) {
         int32_t st = request(n, ids);
         if (st) return st;
-        CXB_CUDA(cudaMemsetAsync(d_kind_count.p, 0, 8 * sizeof(unsigned long long), stream));
-        if (n_req) CXB_LAUNCH(k_request_check, cdiv(n_req, 256), 256, 0, stream, view(), d_req_marg.p, n_req);
+        last_ran = CXB_SCHEDULE_LEVEL;
+        CXB_CUDA(cudaMemsetAsync(d_flags.p + 2, 0, sizeof(int), stream));
+        if (n_req) CXB_LAUNCH(k_request_check, cdiv(n_req, 256), 256, 0, stream, view(), d_req_marg.p, n_req, d_pend_req.p, d_flags.p + 2);
         if (resident_ok()) return update_resident(launches0);
+        CXB_CUDA(cudaMemcpyAsync(h_flags.p + 2, d_flags.p + 2, sizeof(int), cudaMemcpyDeviceToHost, stream));
         if ((st = check_flags())) return st;  // refused at request time: nothing is traversed or computed
+        n_pend_at_req = h_flags.p[2];
         int64_t level = 0;
         while (n_req) {
-            if ((st = find_frontier(true, true))) return st;
+            if ((st = find_frontier(true, true, level == 0))) return st;
             if (!cur_total) break;
             if ((st = run_level(1, level))) return st;
             CXB_LAUNCH(k_ready, cdiv(n_req, 256), 256, 0, stream, view(), d_req_marg.p, d_ready.p, n_req);
             ++stats.levels;
             ++level;
         }
+        if ((st = check_flags())) return st;  // checks of the last level
         for (int mode = 0; mode < 2 && n_req; ++mode) {  // final phase: marginals, then linked signals
             uint32_t cnt = mode == 0 ? n_req : n_links;
+            const std::vector<uint32_t>& hz = mode == 0 ? h_hz_m : h_hz_l;
+            if (!hz.empty()) {  // rule F
+                CXB_LAUNCH(k_check_not_pending, cdiv(hz.size(), 256), 256, 0, stream, view(), mode == 0 ? d_hz_m.p : d_hz_l.p, (uint32_t)hz.size());
+                if ((st = check_flags())) return st;
+            }
             if ((st = begin_level(true))) return st;
             if (cnt)
                 CXB_LAUNCH(k_final_flags, cdiv(cnt, 256), 256, 0, stream, view(), d_req_marg.p, d_link_ids.p, n_req, n_links, mode, lvl_epoch);
@@ -1540,7 +2310,6 @@ struct DeviceEngine {
         CXB_CUDA(cudaMemcpyAsync(h_kind_count.p, d_kind_count.p, 6 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, stream));
         if ((st = check_flags())) return st;
         for (int k = 0; k < 6; ++k) stats.updates_by_kind[k] = (int64_t)h_kind_count.p[k];
-        stats.kernel_launches = (int64_t)(g_kernel_launches - launches0);
         return CXB_OK;
     }
 
@@ -1686,8 +2455,13 @@ struct DeviceEngine {
         int key = g.kind[s] == CXB_KIND_M2V ? -2 : KEY_COMBINE;
         for (int k = 0; k < 2 * n_keys(); ++k) h_counts.p[k] = 0;
         if (key == -2) {
+            if (g.sfac[s] < 0 || g.sfac[s] >= g.n_ids) {
+                err = "compute!: the message has no factor to take a rule from";
+                return CXB_ERR_NO_RULE;
+            }
             for (size_t k = 0; k < key_ftype.size(); ++k)
                 if (key_ftype[k] == g.ftype[g.sfac[s]]) key = (int)k + 1;
+            if (key == -2) key = key_no_rule();
         }
         h_counts.p[key] = 1;
         if ((st = launch_rules(1))) return st;
@@ -1792,6 +2566,7 @@ int64_t cxb_create_signal(cxb_engine* h) try {
     DeviceEngine* e = E(h);
     if (e->sync_host()) return -1;  // pull the dynamic state before growing the structure
     e->structure_dirty = true;
+    e->hand_wired = true;
     return e->g.new_signal();
 } CXB_ABI_CATCH(-1)
 int32_t cxb_add_dependency(cxb_engine* h, int64_t s, int64_t d, int32_t flags) try {
@@ -1805,6 +2580,7 @@ int32_t cxb_add_dependency(cxb_engine* h, int64_t s, int64_t d, int32_t flags) t
     e->g.add_dependency((int32_t)s, (int32_t)d, flags & CXB_DEP_WEAK, !(flags & CXB_DEP_NO_LISTEN),
                         !(flags & CXB_DEP_NO_CHECK_COMPUTED), flags & CXB_DEP_INTERMEDIATE);
     e->structure_dirty = true;
+    e->hand_wired = true;
     return CXB_OK;
 } CXB_ABI_CATCH(CXB_ERR_INTERNAL)
 int32_t cxb_resolve_dependencies(cxb_engine* h, int32_t resolver) try {
@@ -1837,6 +2613,18 @@ int32_t cxb_set_signal_variant(cxb_engine* h, int64_t s, int32_t kind, int64_t v
     }
     if (variable_id >= e->g.n_ids || factor_id >= e->g.n_ids || (variable_id >= 0 && e->g.is_factor[variable_id]) ||
         (factor_id >= 0 && !e->g.is_factor[factor_id])) {
+        e->err = "set_signal_variant: bad variable / factor id";
+        return CXB_ERR_BAD_ARG;
+    }
+    if ((kind == CXB_KIND_M2V || kind == CXB_KIND_M2F) && (variable_id < 0 || factor_id < 0)) {
+        e->err = "set_signal_variant: a message variant needs a variable id and a factor id";
+        return CXB_ERR_BAD_ARG;
+    }
+    if ((kind == CXB_KIND_MARGINAL || kind == CXB_KIND_PRODUCT) && variable_id < 0) {
+        e->err = "set_signal_variant: the variant needs a variable id";
+        return CXB_ERR_BAD_ARG;
+    }
+    if (variable_id < -1 || factor_id < -1) {
         e->err = "set_signal_variant: bad variable / factor id";
         return CXB_ERR_BAD_ARG;
     }
@@ -1964,6 +2752,37 @@ int32_t cxb_update_marginals(cxb_engine* h, int64_t n, const int64_t* ids, cxb_u
     if (stats) *stats = E(h)->stats;
     return st;
 } CXB_ABI_CATCH(CXB_ERR_INTERNAL)
+int32_t cxb_set_schedule(cxb_engine* h, int32_t schedule) try {
+    if (schedule < CXB_SCHEDULE_AUTO || schedule > CXB_SCHEDULE_SEQUENTIAL) {
+        E(h)->err = "set_schedule: unknown schedule";
+        return CXB_ERR_BAD_ARG;
+    }
+    E(h)->schedule = schedule;
+    return CXB_OK;
+} CXB_ABI_CATCH(CXB_ERR_INTERNAL)
+int32_t cxb_last_schedule(cxb_engine* h) try { return E(h)->last_ran; } CXB_ABI_CATCH(-1)
+int64_t cxb_scan_dfs(cxb_engine* h, int64_t* out, int64_t cap) try {
+    std::vector<int64_t> v;
+    if (E(h)->scan_dfs(v)) return -1;
+    for (int64_t i = 0; i < (int64_t)v.size() && i < cap; ++i) out[i] = v[i];
+    return (int64_t)v.size();
+} CXB_ABI_CATCH(-1)
+int64_t cxb_process_dependencies_table(cxb_engine* h, int64_t s, int32_t retry, const uint8_t* answers, int64_t* out_visited,
+                                       int64_t cap, int32_t* processed_out) try {
+    if (s < 0 || s >= (int64_t)E(h)->g.n_sig()) return -1;
+    std::vector<int64_t> v;
+    bool processed = false;
+    if (E(h)->process_dependencies_table(s, retry != 0, answers, v, processed)) return -1;
+    if (processed_out) *processed_out = processed ? 1 : 0;
+    for (int64_t i = 0; i < (int64_t)v.size() && i < cap; ++i) out_visited[i] = v[i];
+    return (int64_t)v.size();
+} CXB_ABI_CATCH(-1)
+int64_t cxb_trace_get_variables(cxb_engine* h, int64_t* out, int64_t cap) try {
+    DeviceEngine* e = E(h);
+    for (int64_t i = 0; i < (int64_t)e->tr_var.size() && i < cap; ++i)
+        if (out) out[i] = e->tr_var[i];
+    return (int64_t)e->tr_var.size();
+} CXB_ABI_CATCH(-1)
 int32_t cxb_trace_enable(cxb_engine* h, int32_t on) try {
     E(h)->trace_on = on != 0;
     return CXB_OK;

@@ -87,36 +87,6 @@ class RuleProcessor(AbstractInferenceRequestProcessor):
         self.value_dim = value_dim
 
 
-class CallbackProcessor(AbstractInferenceRequestProcessor):
-    """User-defined Python rules (oracle backend only: the device engine runs registered kernels).
-
-    Subclasses override the five compute_* methods with the reference signature
-    ``(engine, variant, signal, dependencies) -> value``.
-    """
-
-    def __init__(self, value_dim: int = 1):
-        self.value_dim = value_dim
-        self.family = capi.FAMILY_SUM
-
-    def _missing(self, name):
-        raise NoRuleError(f"The function `{name}` is not implemented for the processor of type {type(self).__name__}")
-
-    def compute_message_to_variable(self, engine, variant, signal, dependencies):
-        self._missing("compute_message_to_variable!")
-
-    def compute_message_to_factor(self, engine, variant, signal, dependencies):
-        self._missing("compute_message_to_factor!")
-
-    def compute_individual_marginal(self, engine, variant, signal, dependencies):
-        self._missing("compute_individual_marginal!")
-
-    def compute_product_of_messages(self, engine, variant, signal, dependencies):
-        self._missing("compute_product_of_messages!")
-
-    def compute_joint_marginal(self, engine, variant, signal, dependencies):
-        self._missing("compute_joint_marginal!")
-
-
 @dataclass
 class InferenceEngineWarning:  # src/inference_engine.jl:11-14
     description: str
@@ -183,8 +153,8 @@ class InferenceEngine:
         self.store = SignalStore(self.api, processor.value_dim, processor.family, dtype, device)
         self._ingest()
         self._register_rules()
-        if isinstance(processor, CallbackProcessor):
-            self._install_callback(processor)
+        if hasattr(processor, "install"):  # processors that hook into the engine themselves (tests/oracle_frontend.py)
+            processor.install(self)
         if trace:
             self.store.check(self.api.trace_enable(self.store.h, 1))
         if resolve_dependencies:
@@ -236,39 +206,6 @@ class InferenceEngine:
             p = np.ascontiguousarray(np.asarray(params, dtype=np.float64).ravel())
             st.check(self.api.register_rule(st.h, self._type_of_form[form], int(kind),
                                             p.ctypes.data_as(capi.f64p) if p.size else None, p.size))
-
-    def _install_callback(self, processor: CallbackProcessor):
-        if not hasattr(self.api, "set_rule_callback"):
-            raise NoRuleError("Python rule callbacks are not available on the device engine: register rule kernels "
-                              "by factor type (RuleProcessor)")
-        engine, st, dim = self, self.store, self.store.value_dim
-
-        def cb(_user, sid, kind, var, fac, ndeps, dep_ids, dep_values, out):
-            try:
-                signal = Signal(st, sid)
-                deps = [Signal(st, dep_ids[i]) for i in range(ndeps)]
-                variant = get_variant(signal)
-                fn = {capi.KIND_M2V: processor.compute_message_to_variable,
-                      capi.KIND_M2F: processor.compute_message_to_factor,
-                      capi.KIND_MARGINAL: processor.compute_individual_marginal,
-                      capi.KIND_PRODUCT: processor.compute_product_of_messages,
-                      capi.KIND_JOINT: processor.compute_joint_marginal}.get(kind)
-                if fn is None:
-                    raise NoRuleError(f"Unprocessed signal variant: {variant}")  # :506
-                val = np.atleast_1d(np.asarray(fn(engine, variant, signal, deps), dtype=np.float64)).ravel()
-                for k in range(dim):
-                    out[k] = val[k] if k < val.size else 0.0
-                return capi.OK
-            except NoRuleError as e:
-                self._callback_error = e
-                return capi.ERR_NO_RULE
-            except Exception as e:  # noqa: BLE001 - surfaced to the caller of update_marginals
-                self._callback_error = e
-                return capi.ERR_NO_RULE
-
-        self._callback_error = None
-        self._cb = capi.RULE_CB(cb)  # keep alive
-        st.check(self.api.set_rule_callback(st.h, self._cb, None))
 
     def __repr__(self):  # src/inference_engine.jl:92-100
         return f"InferenceEngine(trace = {'true' if self.tracer is not None else 'false'})"
@@ -390,11 +327,12 @@ def request_inference_for(engine: InferenceEngine, variable_id_or_ids) -> Infere
     return InferenceRequest(engine, ids, [get_variable(engine, v).marginal for v in ids])
 
 
-def scan_inference_request(request: InferenceRequest, order: str = "id") -> List[Signal]:
+def scan_inference_request(request: InferenceRequest, order: str = "dfs") -> List[Signal]:
     """scan_inference_request(request), src/inference_engine.jl:540-546.
 
-    ``order="id"``: pending signals in ascending signal id, de-duplicated (device and oracle);
-    ``order="dfs"``: the reference's literal DFS visit order (oracle only).
+    ``order="dfs"`` (default): the reference's own order - the depth-first visit order of ``process_dependencies!``,
+    duplicates included (the sequential device traversal, ``cxb_scan_dfs``);
+    ``order="id"``: the same set in ascending signal id, de-duplicated (the breadth-first frontier scan).
     """
     eng = request.engine
     fn = eng.api.scan if order == "id" else eng.api.scan_dfs
@@ -407,21 +345,27 @@ def scan_inference_request(request: InferenceRequest, order: str = "id") -> List
     return [Signal(eng.store, s) for s in buf[:n]]
 
 
-def update_marginals(engine: InferenceEngine, variable_id_or_ids, schedule: str = "lvl") -> capi.UpdateStats:
+SCHEDULES = {"auto": capi.SCHEDULE_AUTO, "lvl": capi.SCHEDULE_LEVEL, "seq": capi.SCHEDULE_SEQUENTIAL}
+
+
+def update_marginals(engine: InferenceEngine, variable_id_or_ids, schedule: str = "auto") -> capi.UpdateStats:
     """update_marginals!(engine, ids), src/inference_engine.jl:553-632.
 
-    ``schedule="lvl"``: the level-synchronous schedule the device runs (SURVEY A.5);
-    ``schedule="seq"``: the reference's sequential in-place schedule (oracle backend only).
+    ``schedule`` (``cxb_set_schedule``): ``"auto"`` (default) always answers as the reference does - the level-synchronous
+    frontier schedule where its contract holds (graphs wired by the built-in resolvers; memoised / closed-form plans when
+    the request was seen before), the literal sequential loop on the device for hand-wired graphs and for requests the
+    level schedule refuses; ``"lvl"``: the level schedule alone (``OutOfContractError`` when it would differ from the
+    reference, the engine left untouched); ``"seq"``: the sequential loop alone.
     Returns the per-call statistics (the reference returns ``nothing``).
     """
     ids = _as_ids(variable_id_or_ids)
     arr, p = _ids(ids)
     stats = capi.UpdateStats()
-    fn = engine.api.update_marginals if schedule == "lvl" else engine.api.update_marginals_seq
+    engine.store.check(engine.api.set_schedule(engine.store.h, SCHEDULES[schedule]))
     engine._callback_error = None
     before = _snapshot(engine) if engine.tracer is not None else None
     t0 = time.perf_counter_ns()
-    status = fn(engine.store.h, len(ids), p, C.byref(stats))
+    status = engine.api.update_marginals(engine.store.h, len(ids), p, C.byref(stats))
     t1 = time.perf_counter_ns()
     if status != capi.OK and getattr(engine, "_callback_error", None) is not None:
         raise engine._callback_error
@@ -429,6 +373,12 @@ def update_marginals(engine: InferenceEngine, variable_id_or_ids, schedule: str 
     if engine.tracer is not None:
         engine.tracer.inference_requests.append(_collect_trace(engine, ids, t1 - t0, before))
     return stats
+
+
+def last_schedule(engine: InferenceEngine) -> int:
+    """Which path answered the last ``update_marginals``: ``capi.SCHEDULE_LEVEL`` / ``SCHEDULE_SEQUENTIAL`` / ``RAN_REPLAY`` /
+    ``RAN_PLAN`` (``cxb_last_schedule``)."""
+    return int(engine.api.last_schedule(engine.store.h))
 
 
 def _snapshot(engine: InferenceEngine):
@@ -449,12 +399,12 @@ def _collect_trace(engine: InferenceEngine, ids, total_ns: int, before=None) -> 
     engine.api.trace_get(engine.store.h, lv.ctypes.data_as(capi.i64p), sg.ctypes.data_as(capi.i64p), n)
     ns = np.zeros(max(n, 1), dtype=np.int64)  # measured per execution (oracle) / per level, shared evenly (device)
     engine.api.trace_get_times(engine.store.h, ns.ctypes.data_as(capi.i64p), n)
-    var = None
-    if hasattr(engine.api, "trace_get_variables"):
-        var = np.zeros(max(n, 1), dtype=np.int64)
-        engine.api.trace_get_variables(engine.store.h, var.ctypes.data_as(capi.i64p), n)
+    var = np.zeros(max(n, 1), dtype=np.int64)
+    if engine.api.trace_get_variables(engine.store.h, var.ctypes.data_as(capi.i64p), n) != n:
+        var = None
     rounds: List[TracedInferenceRound] = []
     cur_key, cur = None, None
+    seen_after: Dict[int, Any] = {}
     for k in range(n):
         key = int(lv[k]) if lv[k] >= 0 else -1  # the final phase (marginals, then linked signals) is ONE round, :610-628
         if key != cur_key:
@@ -465,12 +415,16 @@ def _collect_trace(engine: InferenceEngine, ids, total_ns: int, before=None) -> 
         variant = get_variant(s)
         vid = int(var[k]) if var is not None else getattr(variant, "variable_id", None)
         value_before = None
-        if before is not None:  # a signal runs at most once per level-synchronous request: its old value is the snapshot's
+        if before is not None:  # first execution of the signal in this request: its old value is the snapshot's
             vals, computed = before
-            if not computed[s.sid]:
+            if s.sid in seen_after:  # executed before in this request (sequential schedule only): the value it left then
+                value_before = seen_after[s.sid]
+            elif not computed[s.sid]:
                 value_before = UndefValue()
             else:
                 value_before = float(vals[s.sid][0]) if engine.store.value_dim == 1 else vals[s.sid].copy()
-        cur.executions.append(TracedInferenceExecution(engine, vid, s, max(int(ns[k]), 1), value_before, get_value(s)))
+        value_after = get_value(s)  # of the signal's LAST execution in the request
+        cur.executions.append(TracedInferenceExecution(engine, vid, s, max(int(ns[k]), 1), value_before, value_after))
+        seen_after[s.sid] = value_after
         cur.total_time_in_ns += max(int(ns[k]), 1)
     return TracedInferenceRequest(engine, max(total_ns, 1), InferenceRequest(engine, tuple(ids), []), rounds)

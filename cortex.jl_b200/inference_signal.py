@@ -9,7 +9,7 @@ from __future__ import annotations
 
 import ctypes as C
 from dataclasses import dataclass
-from typing import List, Sequence, Tuple
+from typing import List, Optional, Sequence, Tuple
 
 import numpy as np
 
@@ -248,17 +248,28 @@ def compute(signal: Signal, *, force: bool = False, skip_if_no_listeners: bool =
     st.check(st.api.compute(st.h, signal.sid, int(force), int(skip_if_no_listeners)))
 
 
-def process_dependencies(f, signal: Signal, *, retry: bool = False) -> bool:
-    """process_dependencies!(f, signal; retry), src/signal.jl:466-490 — host callback form (oracle backend;
-    the device engine runs the same traversal as a level-synchronous frontier scan)."""
+def process_dependencies(f, signal: Signal, *, retry: bool = False, visited: Optional[list] = None) -> bool:
+    """process_dependencies!(f, signal; retry), src/signal.jl:466-490, run on the device in the reference's depth-first
+    order (``cxb_process_dependencies_table``).
+
+    ``f`` is ``None`` (the scanner's callback: ``is_pending``, with its caching side effect) or a PURE predicate on
+    signals: it is tabulated over every signal of the engine before the traversal starts and the traversal reads the
+    table. The visit sequence (every call of ``f``, retries included) is appended to ``visited``."""
     st = signal.store
-    if not hasattr(st.api, "process_dependencies"):
-        raise NotImplementedError("callback traversal is provided by the oracle backend only")
-    cb = capi.VISIT_CB(lambda _u, d: 1 if f(Signal(st, d)) else 0)
-    r = st.api.process_dependencies(st.h, signal.sid, int(retry), cb, None)
-    if r < 0:
+    n = st.n_signals()
+    table = None
+    if f is not None:
+        table = np.ascontiguousarray([1 if f(Signal(st, i)) else 0 for i in range(n)], dtype=np.uint8)
+    cap = 8 * max(n, 1) + 1024
+    out = np.zeros(cap, dtype=np.int64)
+    processed = C.c_int32(0)
+    cnt = st.api.process_dependencies_table(st.h, signal.sid, int(retry), table.ctypes.data_as(capi.u8p) if table is not None else None,
+                                            out.ctypes.data_as(capi.i64p), cap, C.byref(processed))
+    if cnt < 0:
         st.check(capi.ERR_BAD_ARG)
-    return bool(r)
+    if visited is not None:
+        visited.extend(Signal(st, int(i)) for i in out[:min(cnt, cap)])
+    return bool(processed.value)
 
 
 def _list(fn, signal: Signal):

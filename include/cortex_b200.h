@@ -125,6 +125,21 @@ enum {
     CXB_RESOLVER_MEAN_FIELD = 2  /* MeanFieldResolver of test/inference_engine_tests.jl:597-621     */
 };
 
+/* ---- schedules of update_marginals! (cxb_set_schedule) ---------------------------------------
+ * The reference loop (src/inference_engine.jl:559-632) is sequential and in place. The device has three ways to run it:
+ *   LEVEL       the level-synchronous frontier schedule under its contract checks: equal to the reference
+ *               order or CXB_ERR_OUT_OF_CONTRACT, and a refused request leaves the engine exactly as it was;
+ *   SEQUENTIAL  the reference loop literally, statement by statement, by one warp on the device (exact by construction,
+ *               any wiring; one signal at a time);
+ *   AUTO        (default) hand-wired graphs (cxb_create_signal / cxb_add_dependency were used) run SEQUENTIAL; graphs
+ *               wired by the built-in resolvers run LEVEL (through a memoised schedule or a closed-form plan when the
+ *               request and the flag state were seen before) and fall back to SEQUENTIAL when LEVEL refuses.
+ * So with AUTO the answer is always the reference's. */
+enum { CXB_SCHEDULE_AUTO = 0, CXB_SCHEDULE_LEVEL = 1, CXB_SCHEDULE_SEQUENTIAL = 2 };
+/* what answered the last cxb_update_marginals (cxb_last_schedule): LEVEL / SEQUENTIAL as above, or */
+enum { CXB_RAN_REPLAY = 3, /* memoised level schedule replayed (same request, same flag state as a recorded run) */
+       CXB_RAN_PLAN = 4    /* same, values by the closed-form kernel of a recognised structure (chains / grid / pairwise) */ };
+
 /* statistics of one update_marginals! call */
 typedef struct cxb_update_stats {
     int64_t levels;           /* level-synchronous loop levels that executed >= 1 signal           */
@@ -219,6 +234,18 @@ int64_t cxb_scan(cxb_engine* h, int64_t* out_signals, int64_t cap);
 /* update_marginals!(engine, ids), src/inference_engine.jl:559-632 — level-synchronous schedule
  * (SURVEY Appendix A.5). stats may be NULL. */
 int32_t cxb_update_marginals(cxb_engine* h, int64_t n, const int64_t* variable_ids, cxb_update_stats* stats);
+/* schedule selection (see CXB_SCHEDULE_*) and which path answered the last request */
+int32_t cxb_set_schedule(cxb_engine* h, int32_t schedule);
+int32_t cxb_last_schedule(cxb_engine* h);
+/* scan_inference_request in the reference's literal order: the DFS visit order of process_dependencies!, duplicates
+ * included (src/inference_engine.jl:540-546, src/signal.jl:466-490), by the sequential device traversal */
+int64_t cxb_scan_dfs(cxb_engine* h, int64_t* out_signals, int64_t cap);
+/* process_dependencies!(f, signal; retry), src/signal.jl:466-490, run on the device in the reference's visit order.
+ * The callback is a table: f(dep) = answers[dep] != 0 (one byte per signal); answers == NULL: f = is_pending (the
+ * scanner's callback, with its caching side effect). Writes the visit sequence (every call of f, retries included),
+ * returns the number of visits (may exceed cap, <0 on error); *processed_out = the function's return value. */
+int64_t cxb_process_dependencies_table(cxb_engine* h, int64_t signal, int32_t retry, const uint8_t* answers,
+                                       int64_t* out_visited, int64_t cap, int32_t* processed_out);
 /* Execution trace of the last cxb_update_marginals (InferenceEngineTracer, src/inference_engine.jl:650-862):
  * enable with cxb_trace_enable(h, 1). out_level: 0-based loop level, -1 = final-phase marginals,
  * -2 = final-phase linked signals. Within a level signals are in ascending id order. */
@@ -227,6 +254,10 @@ int64_t cxb_trace_get(cxb_engine* h, int64_t* out_level, int64_t* out_signals, i
 /* TracedInferenceExecution.total_time_in_ns (src/inference_engine.jl:650-657) of the same records: a level is one batch of
  * kernels, its device time (CUDA events around the rule and set_value! kernels) is shared evenly by its members */
 int64_t cxb_trace_get_times(cxb_engine* h, int64_t* out_ns, int64_t cap);
+/* TracedInferenceExecution.variable_id of the same records: under the SEQUENTIAL schedule the requested variable whose
+ * traversal executed the signal (and out_level of cxb_trace_get is the reference's round number, executions in the
+ * reference's order); under LEVEL the variable of the signal's variant (-1 if none) */
+int64_t cxb_trace_get_variables(cxb_engine* h, int64_t* out_variable_ids, int64_t cap);
 
 /* ===========================================================================================
  * Structured model engines: closed-form plans for the fixed-stencil graph families (SURVEY §8a,
@@ -297,7 +328,7 @@ int32_t cxb_grid_p2p_connect_ipc(cxb_grid* g, int32_t direction, const void* nei
 int32_t cxb_grid_p2p_connect_local(cxb_grid* g, int32_t direction, cxb_grid* neighbour);
 /* marginals [rows][cols][K] engine dtype, D2H */
 int32_t cxb_grid_get_marginals(cxb_grid* g, void* out_host);
-/* message planes for parity: which = 0..3 m2v from (up,down,left,right) factor, 4..7 m2f to them; D2H */
+/* message planes for parity: which = 0..3 m2v from the (up,left,right,down) factor, 4..7 m2f to them; D2H */
 int32_t cxb_grid_get_messages(cxb_grid* g, int32_t which, void* out_host);
 void* cxb_grid_stream(cxb_grid* g);
 int32_t cxb_grid_last_kernel_ms(cxb_grid* g, float* ms_out);

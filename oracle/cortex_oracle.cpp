@@ -741,7 +741,10 @@ struct Oracle {
 
     // Opt-in (CXO_STRICT_FRESHNESS=1) extension of the request-time check below to EVERY signal the first traversal of a
     // request visits: not pending, yet FRESH on a strong, computed (non-input) dependency.
-    bool strict_freshness = std::getenv("CXO_STRICT_FRESHNESS") && std::atoi(std::getenv("CXO_STRICT_FRESHNESS")) != 0;
+    // Strict refusal rules A / B / D / E of the level schedule: on by default on the oracle and on the
+    // device alike; CXO_STRICT_FRESHNESS=0 restores the round-1 rules (kept for tests/fuzz_strict_cost.py).
+    bool strict_freshness = !(std::getenv("CXO_STRICT_FRESHNESS") && std::atoi(std::getenv("CXO_STRICT_FRESHNESS")) == 0);
+    int schedule = CXB_SCHEDULE_AUTO;  // cxo_set_schedule: AUTO and SEQUENTIAL = the reference loop, LEVEL = update_lvl
     bool has_weak_dep = false;    // any weak dependency in the graph (the device allocates its probe marks only then)
     int64_t lvl_request = 0;      // > 0 while a strict level-schedule request runs (its serial number)
     int64_t lvl_serial = 0;
@@ -926,6 +929,44 @@ struct Oracle {
             ++stats.levels;
             ++level;
         }
+        // Final-phase contract (rule F). The reference interleaves per variable: marginal(v_i), then the linked signals of
+        // v_i, then v_{i+1} (src/inference_engine.jl:610-628); the level schedule computes every pending marginal, then every
+        // pending linked signal. The two differ only when a final-phase candidate depends on another one whose turn comes on
+        // the other side of it, so those wirings are refused (statically, from the request and the dependency lists; the
+        // pending tests are evaluated without caching):
+        //   F1 a linked signal of v_i depends on the marginal of a LATER requested variable that is pending now;
+        //   F2 a pending requested marginal depends on a linked signal of an EARLIER requested variable;
+        //   F4 a requested marginal depends on another requested marginal that is pending now;
+        //   F3 (below, before the linked level) a linked signal depends on a linked signal that is pending then.
+        auto pending_now = [&](int64_t s) { return sig[s].p || (sig[s].pp && criteria(sig[s])); };
+        {
+            std::unordered_map<int64_t, int64_t> last_req;   // marginal sid -> last request position
+            std::unordered_map<int64_t, int64_t> first_link;  // linked sid -> first request position that links it
+            for (int64_t i = 0; i < n; ++i) last_req[req_marg[i]] = i;
+            for (int64_t i = 0; i < n; ++i)
+                for (int64_t l : linked[req_ids[i]])
+                    if (!first_link.count(l)) first_link[l] = i;
+            bool hazard = false;
+            for (int64_t i = 0; i < n && !hazard; ++i) {
+                const int64_t m = req_marg[i];
+                for (int64_t d : sig[m].deps) {
+                    auto r = last_req.find(d);
+                    if (r != last_req.end() && d != m && pending_now(d)) hazard = true;                      // F4
+                    auto l = first_link.find(d);
+                    if (l != first_link.end() && l->second < i && pending_now(m)) hazard = true;             // F2
+                }
+                for (int64_t l : linked[req_ids[i]])
+                    for (int64_t d : sig[l].deps) {
+                        auto r = last_req.find(d);
+                        if (r != last_req.end() && r->second > i && pending_now(d)) hazard = true;           // F1
+                    }
+            }
+            if (hazard) {
+                err = "level-synchronous schedule out of contract: a final-phase signal depends on another final-phase signal across "
+                      "the reference's per-variable order (marginal, then linked signals, variable by variable)";
+                return CXB_ERR_OUT_OF_CONTRACT;
+            }
+        }
         // final phase: pending marginals, then pending linked signals (both snapshot-style)
         std::vector<int64_t> M;
         for (int64_t i = 0; i < n; ++i)
@@ -937,6 +978,18 @@ struct Oracle {
         if (st) return st;
         for (int64_t s : M) inF[s] = 0;
         stats.final_marginals = (int64_t)M.size();
+        {  // F3
+            std::unordered_set<int64_t> is_link;
+            for (int64_t i = 0; i < n; ++i)
+                for (int64_t l : linked[req_ids[i]]) is_link.insert(l);
+            for (int64_t l : is_link)
+                for (int64_t d : sig[l].deps)
+                    if (d != l && is_link.count(d) && pending_now(d)) {
+                        err = "level-synchronous schedule out of contract: a linked signal depends on another linked signal that is "
+                              "pending in the final phase (the reference computes them one after the other)";
+                        return CXB_ERR_OUT_OF_CONTRACT;
+                    }
+        }
         std::vector<int64_t> L;
         for (int64_t i = 0; i < n; ++i)
             for (int64_t l : linked[req_ids[i]])
@@ -1211,8 +1264,15 @@ int64_t cxo_scan(void* h, int64_t* out, int64_t cap) {
     for (int64_t i = 0; i < (int64_t)v.size() && i < cap; ++i) out[i] = v[i];
     return (int64_t)v.size();
 }
-int32_t cxo_update_marginals(void* h, int64_t n, const int64_t* ids, cxb_update_stats* stats) {  // lvl
-    int32_t st = O(h)->update_lvl(n, ids);
+// cxb_set_schedule: AUTO / SEQUENTIAL = the reference's own loop (seq), LEVEL = the level-synchronous schedule
+int32_t cxo_set_schedule(void* h, int32_t schedule) {
+    if (schedule < CXB_SCHEDULE_AUTO || schedule > CXB_SCHEDULE_SEQUENTIAL) return CXB_ERR_BAD_ARG;
+    O(h)->schedule = schedule;
+    return CXB_OK;
+}
+int32_t cxo_last_schedule(void* h) { return O(h)->schedule == CXB_SCHEDULE_LEVEL ? CXB_SCHEDULE_LEVEL : CXB_SCHEDULE_SEQUENTIAL; }
+int32_t cxo_update_marginals(void* h, int64_t n, const int64_t* ids, cxb_update_stats* stats) {
+    int32_t st = O(h)->schedule == CXB_SCHEDULE_LEVEL ? O(h)->update_lvl(n, ids) : O(h)->update_seq(n, ids);
     if (stats) *stats = O(h)->stats;
     return st;
 }
@@ -1248,6 +1308,21 @@ int32_t cxo_compute(void* h, int64_t s, int32_t force, int32_t skip_if_no_listen
     Oracle* o = O(h);
     if (s < 0 || s >= (int64_t)o->sig.size()) return CXB_ERR_BAD_ARG;
     return o->compute(s, force != 0, skip_if_no_listeners != 0, true);
+}
+// process_dependencies!(f, signal; retry) with the callback given as a table: f(dep) = answers[dep] (answers == NULL:
+// f = is_pending, the scanner's callback). Writes the visit sequence; returns the number of visits (may exceed cap).
+int64_t cxo_process_dependencies_table(void* h, int64_t s, int32_t retry, const uint8_t* answers, int64_t* out_visited, int64_t cap,
+                                       int32_t* processed_out) {
+    Oracle* o = O(h);
+    if (s < 0 || s >= (int64_t)o->sig.size()) return -1;
+    std::vector<int64_t> seen;
+    bool r = o->process_dependencies(s, retry != 0, [&](int64_t d) {
+        seen.push_back(d);
+        return answers ? answers[d] != 0 : o->is_pending(d);
+    });
+    if (processed_out) *processed_out = r ? 1 : 0;
+    for (int64_t i = 0; i < (int64_t)seen.size() && i < cap; ++i) out_visited[i] = seen[i];
+    return (int64_t)seen.size();
 }
 // process_dependencies!(f, signal; retry), src/signal.jl:466-490
 int32_t cxo_process_dependencies(void* h, int64_t s, int32_t retry, visit_cb_t f, void* user) {

@@ -122,24 +122,6 @@ def test_level_schedule_is_sequential_or_refused(oracle_api, seed):
     assert accepted >= 0
 
 
-@pytest.mark.gpu
-@pytest.mark.parametrize("seed", range(40))
-def test_device_level_schedule_equals_oracle_level_schedule(oracle_api, device_api, seed):
-    rng = np.random.Generator(np.random.PCG64(9000 + seed))
-    n_var, n_fac = int(rng.integers(2, 6)), int(rng.integers(1, 6))
-    dep_p = float(rng.uniform(0.3, 0.9))
-    build_seed = int(rng.integers(1 << 30))
-    eo, vso, inputs = _build(oracle_api, np.random.Generator(np.random.PCG64(build_seed)), n_var, n_fac, dep_p)
-    ed, vsd, _ = _build(device_api, np.random.Generator(np.random.PCG64(build_seed)), n_var, n_fac, dep_p)
-    for op in _script(rng, n_var, inputs, 14):
-        r_o = _run(eo, vso, op, "lvl")
-        r_d = _run(ed, vsd, op, "lvl")
-        assert r_o == r_d, (seed, op, r_o, r_d)  # the same requests are refused
-        if r_o != "ok":
-            break
-        assert _state(eo) == _state(ed), (seed, op)
-
-
 if __name__ == "__main__":
     import os
     import sys

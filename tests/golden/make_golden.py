@@ -66,11 +66,17 @@ def reference_known_answers():
     }
 
 
+def f32(a):
+    """Inputs are made fp32-representable, so that the fp32 engine sees exactly the numbers the fp64 oracle saw and the
+    north-star tolerance (rel 1e-5) covers arithmetic only."""
+    return np.asarray(a, dtype=np.float32).astype(np.float64)
+
+
 def oracle_chain(api):
     rng = np.random.Generator(np.random.PCG64(42))
     T, B = 6, 3
-    q, r = rng.uniform(0.5, 2.0, B), rng.uniform(0.5, 2.0, B)
-    y = np.cumsum(rng.standard_normal((T, B)), axis=0) + rng.standard_normal((T, B))
+    q, r = f32(rng.uniform(0.5, 2.0, B)), f32(rng.uniform(0.5, 2.0, B))
+    y = f32(np.cumsum(rng.standard_normal((T, B)), axis=0) + rng.standard_normal((T, B)))
     marg = np.zeros((T, B, 2))
     for b in range(B):
         e, x, yv, lik, tr = models.make_ssm_model(T, api, form="canon", q=float(q[b]), r=float(r[b]))
@@ -83,8 +89,8 @@ def oracle_chain(api):
 def oracle_hmm(api):
     rng = np.random.Generator(np.random.PCG64(43))
     T, K, M, B = 7, 8, 5, 2
-    A = rng.dirichlet(np.ones(K), size=K)
-    E = rng.dirichlet(np.ones(K), size=M).T * K
+    A = f32(rng.dirichlet(np.ones(K), size=K))
+    E = f32(rng.dirichlet(np.ones(K), size=M).T * K)
     obs = rng.integers(0, M, size=(T, B)).astype(np.uint8)
     marg = np.zeros((T, B, K))
     for b in range(B):
@@ -99,9 +105,9 @@ def oracle_pairwise(api):
     rng = np.random.Generator(np.random.PCG64(44))
     n, K, n_tables, sweeps = 30, 8, 3, 2
     edges = models.chung_lu_edges(n, 60, seed=3)
-    tables = np.exp(rng.standard_normal((n_tables, K, K)))
+    tables = f32(np.exp(rng.standard_normal((n_tables, K, K))))
     ttype = rng.integers(0, n_tables, size=len(edges))
-    unary = rng.dirichlet(np.ones(K), size=n)
+    unary = f32(rng.dirichlet(np.ones(K), size=n))
     g = C.BipartiteFactorGraph()
     vs = [g.add_variable(C.Variable(name="v", index=(i,))) for i in range(n)]
     un = [g.add_factor(C.Factor(functional_form="unary")) for _ in range(n)]

@@ -185,6 +185,42 @@ def engine_state(engine):
     return out, vals
 
 
+TOL = {cap.F64: 1e-12, cap.F32: 1e-5}  # north_star: rel 1e-5 (fp32) / 1e-12 (fp64) on marginals
+
+
+def assert_values_close(got, want, dtype, kind="prob", err_msg=""):
+    """Element-wise comparison at the north-star tolerance.
+
+    kind="prob": normalised categorical vectors - |got - want| <= tol * |want| + tol * 1e-3 (the absolute term is the floor of
+    a vector that sums to one: 1e-8 in fp32, 1e-15 in fp64; a state of probability 1e-6 must still be right to 1 %).
+    kind="canon": Gaussian messages in canonical form (precision, precision * mean), last axis 2: the precision element-wise
+    (rel tol), and as (mean, variance) - SURVEY Appendix C "marginals reported as (mean, variance)" - the variance rel tol,
+    the mean to tol * (|mean| + standard deviation): a mean that crosses zero has no relative error of its own, its
+    natural scale is the posterior standard deviation. The vacuous message (0, 0) must be reproduced exactly.
+    kind="plain": element-wise rel tol with the 1e-3 * tol floor."""
+    tol = TOL[dtype]
+    got = np.asarray(got, dtype=np.float64)
+    want = np.asarray(want, dtype=np.float64)
+    assert got.shape == want.shape, (got.shape, want.shape, err_msg)
+    if kind in ("prob", "plain"):
+        np.testing.assert_allclose(got, want, rtol=tol, atol=tol * 1e-3, err_msg=err_msg)
+        return
+    assert kind == "canon" and want.shape[-1] == 2
+    lam_w, eta_w, lam_g, eta_g = want[..., 0], want[..., 1], got[..., 0], got[..., 1]
+    vac = lam_w == 0
+    assert np.array_equal(lam_g[vac], lam_w[vac]) and np.array_equal(eta_g[vac], eta_w[vac]), err_msg
+    other = lam_w < 0  # not a Gaussian message (an engine stores the observations y_t in the same array): plain comparison
+    np.testing.assert_allclose(got[other], want[other], rtol=tol, atol=tol * 1e-3, err_msg=err_msg)
+    ok = lam_w > 0
+    lw, ew, lg, eg = lam_w[ok], eta_w[ok], lam_g[ok], eta_g[ok]
+    np.testing.assert_allclose(lg, lw, rtol=tol, atol=0, err_msg=err_msg + " (precision)")
+    np.testing.assert_allclose(1.0 / lg, 1.0 / lw, rtol=tol, atol=0, err_msg=err_msg + " (variance)")
+    mean_w, mean_g = ew / lw, eg / lg
+    bound = tol * (np.abs(mean_w) + np.sqrt(1.0 / lw))
+    bad = np.abs(mean_g - mean_w) > bound
+    assert not bad.any(), f"{err_msg} (mean): {int(bad.sum())} of {bad.size} differ, worst ratio {np.max(np.abs(mean_g - mean_w) / bound):.3g}"
+
+
 def canon_to_mv(v):
     v = np.asarray(v, dtype=np.float64)
     return np.stack([v[..., 1] / v[..., 0], 1.0 / v[..., 0]], axis=-1)

@@ -96,7 +96,7 @@ def test_hmm_kernel_matches_committed_vectors(dtype, tol):
     hm.set_tables(g["A"], g["E"])
     hm.set_observations(g["obs"])
     hm.update_marginals()
-    np.testing.assert_allclose(hm.get_marginals(), g["marginals"], rtol=tol, atol=tol * float(g["marginals"].max()))
+    np.testing.assert_allclose(hm.get_marginals(), g["marginals"], rtol=tol, atol=tol * 1e-3)  # element-wise
 
 
 @pytest.mark.gpu
@@ -104,14 +104,14 @@ def test_hmm_kernel_matches_committed_vectors(dtype, tol):
 def test_pairwise_kernel_matches_committed_vectors(dtype, tol):
     g = np.load(GOLD / "oracle_pairwise.npz")
     n = g["unary"].shape[0]
-    tables = g["tables"] if dtype == cap.F64 else g["tables"]
+    tables = g["tables"]
     pw = C.PairwiseGraph(n, g["edges"][:, 0], g["edges"][:, 1], g["ttype"], tables, dtype=dtype)
     pw.set_unary(g["unary"])
     pw.reset_messages()
     for _ in range(int(g["sweeps"])):
         pw.sweep()
-    # fp32 rounds tables and evidence on entry; the committed vectors are fp64, hence the fp32 tolerance of the north star
-    np.testing.assert_allclose(pw.get_marginals(), g["marginals"], rtol=10 * tol, atol=10 * tol * float(g["marginals"].max()))
+    # the committed inputs are fp32-representable (make_golden.f32): the tolerance covers arithmetic only, element-wise
+    np.testing.assert_allclose(pw.get_marginals(), g["marginals"], rtol=tol, atol=tol * 1e-3)
 
 
 @pytest.mark.gpu

@@ -5,6 +5,7 @@ import numpy as np
 import pytest
 
 from tests._pkg import pkg
+from tests.oracle_frontend import CallbackProcessor
 from tests import models
 
 C = pkg
@@ -237,7 +238,7 @@ def test_missing_rule_raises(backend):  # src/inference_engine.jl:358-360
 
 
 # ---- oracle-only: user-defined (Python) rules, the reference's own extension mechanism ---------------
-class _SSMCallback(C.CallbackProcessor):  # :383-432, literally
+class _SSMCallback(CallbackProcessor):  # :383-432, literally
     def __init__(self):
         super().__init__(value_dim=2)
 
@@ -281,7 +282,7 @@ def test_user_defined_python_rules_match_builtin(oracle_api):
 
 
 def test_unimplemented_python_rule_raises(oracle_api):
-    e, x, y, lik, tr = models.make_ssm_model(3, oracle_api, processor=C.CallbackProcessor(value_dim=2))
+    e, x, y, lik, tr = models.make_ssm_model(3, oracle_api, processor=CallbackProcessor(value_dim=2))
     models.ssm_set_data(e, y, lik, [1.0, 2.0, 3.0])
     with pytest.raises(C.NoRuleError):
         C.update_marginals(e, x, schedule="seq")

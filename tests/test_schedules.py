@@ -190,23 +190,29 @@ def test_incremental_evidence_with_leftover_freshness_is_refused(backend):
     e, x, y, lik, tr = models.make_ssm_model(T, backend, form="canon")
     sig = [C.get_connection_message_to_factor(e, y[i], lik[i]) for i in range(T)]
     C.set_values(sig[1:], np.array([[2.0, 0.0], [2.0, 0.0]]))
-    C.update_marginals(e, x)  # incomplete: y_0 is missing
+    C.update_marginals(e, x, schedule="lvl")  # incomplete: y_0 is missing
     C.set_values(sig, np.array([[3.0, 0.0]] * 3))
     before = models.engine_state(e)
     with pytest.raises(C.OutOfContractError, match="leftover freshness"):
-        C.update_marginals(e, x)
+        C.update_marginals(e, x, schedule="lvl")
     after = models.engine_state(e)
-    assert before[0] == after[0] and np.array_equal(before[1], after[1], equal_nan=True)  # nothing was computed
-    if not backend.is_device:
-        e2, x2, y2, lik2, _ = models.make_ssm_model(T, backend, form="canon")
-        sig2 = [C.get_connection_message_to_factor(e2, y2[i], lik2[i]) for i in range(T)]
-        C.set_values(sig2[1:], np.array([[2.0, 0.0], [2.0, 0.0]]))
-        C.update_marginals(e2, x2, schedule="seq")
-        C.set_values(sig2, np.array([[3.0, 0.0]] * 3))
-        C.update_marginals(e2, x2, schedule="seq")
-        got = C.get_values([C.get_variable_marginal(C.get_variable(e2, v)) for v in x2])
-        # canonical form (precision, precision * mean); the stale backward message shows in x_1
-        np.testing.assert_allclose(got[1], [2.0, 5.5])
+    assert before[0] == after[0] and np.array_equal(before[1], after[1], equal_nan=True)  # a refusal changes nothing
+    # the default schedule answers as the reference does: on the device the refused request is rolled back and run by the
+    # sequential executor; the stale backward message shows in x_1 (canonical form: precision, precision * mean)
+    C.update_marginals(e, x)
+    assert C.last_schedule(e) == C.capi.SCHEDULE_SEQUENTIAL
+    got = C.get_values([C.get_variable_marginal(C.get_variable(e, v)) for v in x])
+    np.testing.assert_allclose(got[1], [2.0, 5.5])
+    e2, x2, y2, lik2, _ = models.make_ssm_model(T, backend, form="canon")
+    sig2 = [C.get_connection_message_to_factor(e2, y2[i], lik2[i]) for i in range(T)]
+    C.set_values(sig2[1:], np.array([[2.0, 0.0], [2.0, 0.0]]))
+    C.update_marginals(e2, x2, schedule="seq")
+    C.set_values(sig2, np.array([[3.0, 0.0]] * 3))
+    C.update_marginals(e2, x2, schedule="seq")
+    got2 = C.get_values([C.get_variable_marginal(C.get_variable(e2, v)) for v in x2])
+    np.testing.assert_allclose(got2[1], [2.0, 5.5])
+    a, b = models.engine_state(e), models.engine_state(e2)
+    assert a[0] == b[0] and np.array_equal(a[1], b[1], equal_nan=True)
 
 
 @pytest.mark.parametrize("seed", range(20))
@@ -232,8 +238,8 @@ def test_random_scripts_of_incremental_evidence_are_sequential_or_refused(oracle
 
 
 # ---- hand-wired signal DAGs (outside the default BP wiring): the oracle's STRICT level schedule --------------------
-# CXO_STRICT_FRESHNESS=1 (read when an oracle engine is created; off by default because the device does not implement
-# these three rules yet - DESIGN.md section 2) adds to the level schedule:
+# On by default on the oracle and on the device (CXO_STRICT_FRESHNESS=0 / CXB_STRICT=0, read when an engine is created, give
+# the round-1 rules). They add to the level schedule:
 #   (A) a signal the first traversal visits that is not pending but FRESH on a strong, computed, non-input dependency,
 #   (B) a requested marginal that was already pending when the request arrived and has pending work beneath it,
 #   (D) a frontier member found pending more than once, some visit through an intermediate slot, while one of its
@@ -271,7 +277,7 @@ def _fuzz_script(api, seed, n_ops=20, p_weak=0.0, p_listen=1.0):
 
 @pytest.mark.parametrize("seed", _STRICT_SEEDS_THAT_DIFFERED)
 def test_strict_level_schedule_refuses_the_scripts_that_differed(oracle_api, monkeypatch, seed):
-    monkeypatch.delenv("CXO_STRICT_FRESHNESS", raising=False)
+    monkeypatch.setenv("CXO_STRICT_FRESHNESS", "0")
     assert _fuzz_script(oracle_api, seed) == "differs"  # the default level schedule accepts them and answers differently
     monkeypatch.setenv("CXO_STRICT_FRESHNESS", "1")
     assert _fuzz_script(oracle_api, seed) == "refused"
@@ -288,7 +294,7 @@ _NONLISTENING_SEEDS_THAT_DIFFERED = [21, 37, 46, 56, 150, 159, 185, 216, 229, 25
 
 @pytest.mark.parametrize("seed", _NONLISTENING_SEEDS_THAT_DIFFERED)
 def test_strict_level_schedule_refuses_the_non_listening_scripts_that_differed(oracle_api, monkeypatch, seed):
-    monkeypatch.delenv("CXO_STRICT_FRESHNESS", raising=False)
+    monkeypatch.setenv("CXO_STRICT_FRESHNESS", "0")
     assert _fuzz_script(oracle_api, seed, p_listen=0.9) == "differs"
     monkeypatch.setenv("CXO_STRICT_FRESHNESS", "1")
     assert _fuzz_script(oracle_api, seed, p_listen=0.9) == "refused"

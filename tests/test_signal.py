@@ -355,12 +355,8 @@ def test_intermediate_dependencies_can_be_added(pool):  # :919-931
     assert C.get_dependency_props(d) == [C.capi.NIB_INTERMEDIATE]
 
 
-# ---- process_dependencies! traversal (host-callback form: oracle only) -----------------------------
-@pytest.fixture
-def opool(oracle_api):
-    return C.SignalStore(oracle_api, 1)
-
-
+# ---- process_dependencies! traversal: the reference's visit order, on the oracle and on the device ------------------
+# (the callback is a pure predicate, tabulated before the traversal: cxb_process_dependencies_table)
 def _chain(p, intermediate):
     src, mid, d = p.Signal(), p.Signal(), p.Signal()
     add_dependency(mid, src)
@@ -369,43 +365,69 @@ def _chain(p, intermediate):
 
 
 @pytest.mark.parametrize("retry", [False, True])
-def test_process_dependencies_steps_down_callback_false(opool, retry):  # :943-973
-    src, mid, d = _chain(opool, True)
+def test_process_dependencies_steps_down_callback_false(pool, retry):  # :943-973
+    src, mid, d = _chain(pool, True)
     seen = []
-    r = C.process_dependencies(lambda dep: (seen.append(dep), False)[1], d, retry=retry)
+    r = C.process_dependencies(lambda dep: False, d, retry=retry, visited=seen)
     assert seen == [mid, src] and not r
 
 
 @pytest.mark.parametrize("retry", [False, True])
-def test_process_dependencies_callback_true(opool, retry):  # :975-999
-    src, mid, d = _chain(opool, True)
+def test_process_dependencies_callback_true(pool, retry):  # :975-999
+    src, mid, d = _chain(pool, True)
     seen = []
-    r = C.process_dependencies(lambda dep: (seen.append(dep), True)[1], d, retry=retry)
+    r = C.process_dependencies(lambda dep: True, d, retry=retry, visited=seen)
     assert seen == [mid] and r
 
 
-def test_process_dependencies_retry_order(opool):  # :1001-1028
-    src, mid, d = _chain(opool, True)
+def test_process_dependencies_retry_order(pool):  # :1001-1028
+    src, mid, d = _chain(pool, True)
     seen = []
-    r = C.process_dependencies(lambda dep: (seen.append(dep), dep != mid)[1], d, retry=False)
+    r = C.process_dependencies(lambda dep: dep != mid, d, retry=False, visited=seen)
     assert seen == [mid, src] and r
     seen = []
-    r = C.process_dependencies(lambda dep: (seen.append(dep), dep != mid)[1], d, retry=True)
+    r = C.process_dependencies(lambda dep: dep != mid, d, retry=True, visited=seen)
     assert seen == [mid, src, mid] and r  # retried on the intermediate
 
 
 @pytest.mark.parametrize("retry", [False, True])
 @pytest.mark.parametrize("ret", [False, True])
-def test_process_dependencies_not_intermediate(opool, retry, ret):  # :1031-1059
-    src, mid, d = _chain(opool, False)
+def test_process_dependencies_not_intermediate(pool, retry, ret):  # :1031-1059
+    src, mid, d = _chain(pool, False)
     seen = []
-    r = C.process_dependencies(lambda dep: (seen.append(dep), ret)[1], d, retry=retry)
+    r = C.process_dependencies(lambda dep: ret, d, retry=retry, visited=seen)
     assert seen == [mid] and r == ret
 
 
 @pytest.mark.parametrize("retry", [False, True])
-def test_process_dependencies_returns_true_if_any(opool, retry):  # :1061-1082
-    src, mid, d = _chain(opool, True)
+def test_process_dependencies_returns_true_if_any(pool, retry):  # :1061-1082
+    src, mid, d = _chain(pool, True)
     seen = []
-    assert C.process_dependencies(lambda dep: (seen.append(dep), dep == src)[1], d, retry=retry)
+    assert C.process_dependencies(lambda dep: dep == src, d, retry=retry, visited=seen)
     assert len(seen) >= 1
+
+
+def test_process_dependencies_scanner_callback_and_arbitrary_python_callback(pool, oracle_api):
+    """f = None is the scanner's is_pending callback; the oracle additionally accepts any Python callable
+    (tests/oracle_frontend.py) and must visit in the same order."""
+    from tests.oracle_frontend import process_dependencies_callback
+
+    def build(p):
+        a, b, c, top = p.Signal(), p.Signal(), p.Signal(), p.Signal()
+        add_dependency(b, a)
+        add_dependency(c, b, intermediate=True)
+        add_dependency(top, c, intermediate=True)
+        add_dependency(top, a, intermediate=True)
+        C.set_value(a, 1.0)
+        return a, b, c, top
+
+    a, b, c, top = build(pool)
+    seen = []
+    r = C.process_dependencies(None, top, retry=True, visited=seen)
+    # c is not pending -> descend; b is pending (a is fresh) -> processed; retry asks c again; a has no dependencies
+    assert seen == [c, b, c, a] and r
+    op = C.SignalStore(oracle_api, 1)
+    a2, b2, c2, top2 = build(op)
+    seen2 = []
+    r2 = process_dependencies_callback(lambda dep: (seen2.append(dep), C.is_pending(dep))[1], top2, retry=True)
+    assert [s.sid for s in seen2] == [s.sid for s in seen] and r2 == r

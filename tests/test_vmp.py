@@ -8,6 +8,7 @@ import numpy as np
 import pytest
 
 from tests import models
+from tests.oracle_frontend import CallbackProcessor
 from tests._pkg import pkg
 
 C = pkg
@@ -35,7 +36,7 @@ def _name(engine, signal):  # get_name_of_variable, :623-629
     return C.get_variable_name(C.get_variable(engine, variant.variable_id))
 
 
-class PyMeanFieldProcessor(C.CallbackProcessor):  # SSMMeanFieldInferenceRequestProcessor, :631-696
+class PyMeanFieldProcessor(CallbackProcessor):  # SSMMeanFieldInferenceRequestProcessor, :631-696
     """Values are pairs: NormalMeanPrecision (mean, precision), Gamma (shape, scale), observation (y, -)."""
 
     def __init__(self):
@@ -169,7 +170,7 @@ def test_mean_field_ssm_device_parity(oracle_api, device_api, dtype):
 
 
 # ---- structured VMP: JointMarginal signals, linked signals, a user resolver that delegates (:811-1147) ---------------
-class PyStructuredProcessor(C.CallbackProcessor):  # SSMStructuredInferenceRequestProcessor, :909-1029
+class PyStructuredProcessor(CallbackProcessor):  # SSMStructuredInferenceRequestProcessor, :909-1029
     def __init__(self):
         super().__init__(value_dim=6)
 
@@ -313,5 +314,13 @@ def test_structured_ssm_device_parity(oracle_api, device_api, dtype):
     for k in ("x", "ssnoise", "obsnoise"):
         np.testing.assert_allclose(got[k][..., :2], want[k][..., :2], rtol=rtol, atol=rtol * 1e-3, err_msg=k)
     assert models.engine_state(md[0])[0] == models.engine_state(mo[0])[0]
-    with pytest.raises(C.OutOfContractError):  # refused on the device exactly as in the oracle
-        C.update_marginals(md[0], [md[4], md[3]] + list(md[1]))
+    merged = lambda m: [m[4], m[3]] + list(m[1])  # noqa: E731  [ssnoise, obsnoise, x...], test/inference_engine_tests.jl:1113
+    with pytest.raises(C.OutOfContractError):  # the LEVEL schedule refuses it on the device exactly as in the oracle ...
+        C.update_marginals(md[0], merged(md), schedule="lvl")
+    assert models.engine_state(md[0])[0] == models.engine_state(mo[0])[0]  # ... and leaves the engine untouched
+    C.update_marginals(md[0], merged(md))  # the default schedule answers it as the reference does
+    C.update_marginals(mo[0], merged(mo), schedule="seq")
+    assert models.engine_state(md[0])[0] == models.engine_state(mo[0])[0]
+    vd = C.get_values([C.get_variable_marginal(C.get_variable(md[0], v)) for v in md[1]])
+    vo = C.get_values([C.get_variable_marginal(C.get_variable(mo[0], v)) for v in mo[1]])
+    np.testing.assert_allclose(vd[..., :2], vo[..., :2], rtol=rtol, atol=rtol * 1e-3)
