@@ -1,16 +1,20 @@
 #!/usr/bin/env python
 """bench.py — message-updates/sec of the update_marginals! hot path on B200 (BASELINE.json metric).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload gauss_chains|potts_grid|hmm64|powerlaw|chain1k]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload potts_grid|gauss_chains|hmm64|hmm512|powerlaw|powerlaw_engine|chain1k|chains_engine]
     python bench.py --impl reference ...     # the CPU oracle port of the reference, on the host cores
 
 One "step" = one pass of the hot path over one batch of synthetic input:
-  gauss_chains (default, BASELINE configs[1]): update_marginals! over 65,536 chains x T=1,024 (fp32);
-  potts_grid  (configs[3]): one synchronous sweep of the 8192^2, K=16 grid, row-sharded over N GPUs;
-  hmm64       (configs[2], K=64): scaled forward-backward of 1,024 HMMs x T (see --hmm-steps);
-  powerlaw    (configs[4]): one protocol-B sweep of the generic CSR engine on a Chung-Lu graph;
-  chain1k     (configs[0]): update_marginals! on one T=1,000 chain through the generic engine (latency).
-Prints ONE JSON line (rank 0). Nothing here reads /root/reference.
+  potts_grid  (default at every N, BASELINE configs[3]): 50 synchronous sweeps of the 8192^2, K=16 grid, row-sharded over the
+              N GPUs with the halo exchange fused into the sweep kernel (strong scaling: the north star's 1 -> 8 target);
+  gauss_chains (configs[1]): update_marginals! over 65,536 chains x T=1,024 per GPU (fp32 / fp64);
+  hmm64 / hmm512 (configs[2]): scaled forward-backward of 1,024 HMMs x T=1e5, batch-sharded (K=512: 1,024/N chains per GPU,
+              at most 128: the marginal planes of more do not fit one GPU);
+  powerlaw    (configs[4]): one protocol-B sweep of the fused CSR engine on a 10M-variable Chung-Lu graph;
+  powerlaw_engine / chain1k (configs[0]) / chains_engine: the same models through cxb_graph_build + cxb_update_marginals (the
+              reference's single entry point; memoised schedules and closed-form plans behind it).
+The default run prints ONE JSON line (rank 0): the potts_grid record, with one sub-record per other config under "others".
+Nothing here reads /root/reference.
 """
 from __future__ import annotations
 
@@ -93,10 +97,37 @@ def dist_setup(n_gpus):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
+    bind_to_gpu_numa_node(local)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     return rank, world, local
+
+
+NUMA_NOTE = {}
+
+
+def bind_to_gpu_numa_node(local):
+    """Run this rank (and first-touch its pinned buffers) on the CPU cores of the NUMA node its GPU hangs off
+    (/sys/bus/pci/devices/<bdf>/local_cpulist): on an 8-GPU box the host side of the host<->device copies of all ranks
+    otherwise ends up behind one memory controller / PCIe root (round 1: per-GPU e2e fell 4.9x from 1 to 8 GPUs)."""
+    import torch
+
+    try:
+        pr = torch.cuda.get_device_properties(local)
+        bdf = f"{pr.pci_domain_id:04x}:{pr.pci_bus_id:02x}:{pr.pci_device_id:02x}.0"
+        path = Path("/sys/bus/pci/devices") / bdf / "local_cpulist"
+        cpus = set()
+        for part in path.read_text().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            node = (Path("/sys/bus/pci/devices") / bdf / "numa_node").read_text().strip()
+            NUMA_NOTE.update({"gpu": local, "pci": bdf, "numa_node": int(node), "cpus": len(cpus)})
+    except Exception as e:  # noqa: BLE001 - binding is an optimisation; say why it did not happen
+        NUMA_NOTE.update({"gpu": local, "unbound": repr(e)[:120]})
 
 
 def barrier(world):
@@ -135,23 +166,30 @@ class DevArr:
         self.__cuda_array_interface__ = {"shape": (n,), "typestr": typestr, "data": (int(ptr), False), "version": 2}
 
 
-def timed(stream_ptr, fn, steps, warmup, world, local):
-    """W warm-up + K timed steps on the library's stream; returns (elapsed_ms max over ranks)."""
+def timed(stream_ptr, fn, steps, warmup, world, local, min_ms=0.0):
+    """W warm-up + K timed steps on the library's stream; returns the elapsed ms (max over ranks). With min_ms the step
+    count is raised until the timed region is at least that long (sub-records: >= 1 s, so that the clock sampler sees
+    the region); the count actually timed is left in timed.last_steps."""
     import torch
 
     ext = torch.cuda.ExternalStream(stream_ptr, device=local)
     for _ in range(warmup):
         fn()
     ext.synchronize()
-    barrier(world)
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record(ext)
-    for _ in range(steps):
-        fn()
-    e1.record(ext)
-    e1.synchronize()
-    barrier(world)
-    return max_over_ranks(e0.elapsed_time(e1), world, local)
+    while True:
+        barrier(world)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(ext)
+        for _ in range(steps):
+            fn()
+        e1.record(ext)
+        e1.synchronize()
+        barrier(world)
+        ms = max_over_ranks(e0.elapsed_time(e1), world, local)
+        if ms >= min_ms or steps >= 1 << 20:
+            timed.last_steps = steps
+            return ms
+        steps = int(min(1 << 20, max(steps * 2, steps * 1.25 * min_ms / max(ms, 1e-3)))) + 1
 
 
 # ---------------------------------------------------------------------------------------------------------------
@@ -261,7 +299,7 @@ def run_reference(args):
 
     subprocess.run(["make", "-C", str(ROOT / "oracle")], check=True, stdout=subprocess.DEVNULL)
     cores = os.cpu_count() or 1
-    per_step_budget = max(1.0, min(10.0, 60.0 / max(1, args.steps + args.warmup)))
+    per_step_budget = max(1.0, min(10.0, 75.0 / max(1, args.steps + args.warmup)))
     _, what = cpu_baseline_workload(args.workload, 0.2)  # the sample's description (and a warm build of the graph code paths)
     vals = []
     with mp.get_context("spawn").Pool(cores) as pool:
@@ -271,12 +309,15 @@ def run_reference(args):
             if s >= args.warmup:
                 vals.append((v, time.perf_counter() - t0))
     value = statistics.mean(v for v, _ in vals)
-    sample = (f"{cores} independent replicas (one per core; the reference is single-threaded), each: {what.split(', explicit')[0]}, explicit "
-              f"Signal graph, sequential schedule, ~{per_step_budget:.1f} s per step")
+    sample = (f"SAMPLED: {cores} independent replicas (one per core; the reference is single-threaded), each: {what.split(', explicit')[0]}, "
+              f"explicit Signal graph, sequential schedule, ~{per_step_budget:.1f} s of work per step (ms_per_step is that time budget, not "
+              f"the time of the full-size workload)")
+    cfg = workload_config(args, max(1, args.gpus))  # the GPU arm's config; what the CPU actually ran is in "sampled" / cpu_baseline.sample
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * statistics.mean(t for _, t in vals), "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": workload_config(args, 1),
+            "config": cfg,
+            "sampled": what.split(", explicit")[0] + " per core (the full-size explicit Signal graph does not fit / build on the host)",
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
@@ -288,19 +329,21 @@ def workload_config(args, world):
                             f"canonical-form forward-backward (BASELINE configs[1])", "chains_per_gpu": args.chains,
                 "T": args.chain_steps, "l2": "inputs exceed L2 (4.3 GB touched per step)", "parallelism": f"batch-shard x{world}"}
     if args.workload == "potts_grid":
-        return {"workload": f"2D Potts grid {args.grid}x{args.grid}, K=16, synchronous sweeps (protocol B), row-sharded "
-                            f"(BASELINE configs[3])", "grid": args.grid, "K": 16, "l2": "inputs exceed L2",
-                "parallelism": f"row-shard x{world} + halo exchange: {getattr(args, 'halo_transport', 'n/a')}"}
+        return {"workload": f"2D Potts grid {args.grid}x{args.grid}, K=16, {args.sweeps} synchronous sweeps (protocol B) per step, "
+                            f"row-sharded (BASELINE configs[3])", "grid": args.grid, "K": 16, "sweeps_per_step": args.sweeps,
+                "l2": "inputs exceed L2 (60 GB touched per sweep)",
+                "parallelism": f"row-shard x{world}" + (", halo exchange of the cut-edge messages every sweep (transport: see comm)" if world > 1 else ""),
+                "e2e_step": "unary evidence host->device, the sweeps, marginals device->host (each rank its rows)"}
     if args.workload in ("hmm64", "hmm512"):
         k = 512 if args.workload == "hmm512" else 64
         cfg = {"workload": f"{args.hmm_chains} HMMs per GPU, K={k}, M=32, T={args.hmm_steps} (BASELINE configs[2] K={k})",
                "l2": "inputs exceed L2", "parallelism": f"batch-shard x{world}",
                "e2e_result": "observations in (all T), marginals of the last min(T, 256) time steps out (the full plane is "
                              f"{args.hmm_chains * args.hmm_steps * k * 4 / 1e9:.0f} GB; fetch any window with cxb_hmm_get_marginals)"}
-        if k == 512 and args.hmm_steps < 100000:
-            cfg["T_note"] = ("BASELINE names T=1e5: at K=512 the forward and marginal planes of 1,024 chains x 1e5 steps are "
-                             "2 x 210 GB and do not fit one 180 GB GPU (SURVEY 8d), so a slice of the same recursion is timed; "
-                             "the step cost does not depend on T (one launch per time step), pass --hmm-steps to change it")
+        if k == 512 and args.hmm_chains < 1024:
+            cfg["batch_tile"] = (f"BASELINE names 1,024 chains: at K=512 their forward and marginal planes are 2 x 210 GB, so the job runs "
+                                 f"in batch tiles of {args.hmm_chains} chains per GPU (SURVEY 8d: '<= 256 chains per GPU, or 128 chains/GPU on "
+                                 f"8 GPUs'); one tile is timed, the rate is the job's")
         return cfg
     if args.workload in ("powerlaw", "powerlaw_engine"):
         eng = "fused CSR sweep engine" if args.workload == "powerlaw" else "generic reactive engine"
@@ -344,7 +387,8 @@ def bench_gauss_chains(args, pkg, rank, world, local):
     sampler = ClockSampler(local)
     sampler.start()
     launches0 = pkg.default_api().kernel_launches()
-    ms = timed(ch.stream, step, args.steps, 0, world, local)
+    ms = timed(ch.stream, step, args.steps, 0, world, local, min_ms=args.min_ms)
+    steps_timed = timed.last_steps
     launches = pkg.default_api().kernel_launches() - launches0
     # per-launch kernel duration from the library's own CUDA events (same stream)
     for _ in range(min(args.steps, 10)):
@@ -354,14 +398,14 @@ def bench_gauss_chains(args, pkg, rank, world, local):
     def e2e_step():
         ch.infer_host(y_host.data_ptr(), out_host.data_ptr())
 
-    e2e_ms = timed(ch.stream, e2e_step, max(2, min(args.steps, 5)), 1, world, local)
-    e2e_steps = max(2, min(args.steps, 5))
+    e2e_ms = timed(ch.stream, e2e_step, max(2, min(args.steps, 5)), 1, world, local, min_ms=args.min_ms)
+    e2e_steps = timed.last_steps
     clocks = sampler.stop()
     esz = 4 if dtype == cap.F32 else 8
     alg_bytes = B * T * (16 * esz)  # 64 B (fp32) / 128 B (fp64) per variable: SURVEY §8d config 2
     return {"ms": ms, "updates_per_step": n_upd, "kernel_ms": statistics.mean(kernel_ms), "alg_bytes": alg_bytes,
             "e2e_ms": e2e_ms, "e2e_steps": e2e_steps, "h2d": B * T * esz, "d2h": B * T * 2 * esz, "launches": launches,
-            "clocks": clocks, "dtype": args.dtype, "kernel": "k_chains_fwd_bwd", "scaling": "weak"}
+            "clocks": clocks, "dtype": args.dtype, "kernel": "k_chains_fwd_bwd", "scaling": "weak", "steps_timed": steps_timed}
 
 
 def bench_potts_grid(args, pkg, rank, world, local):
@@ -400,12 +444,18 @@ def bench_potts_grid(args, pkg, rank, world, local):
         gr.sync()
         dist.barrier()
 
-    def step():
+    def sweep():
         upd[0] = gr.sweep()
         if world > 1 and not fused:
             with torch.cuda.stream(ext):  # NCCL orders itself after the sweep on the library's stream
                 halo.exchange(tens(gr.halo_send_ptr(0)) if has_up else None, tens(gr.halo_send_ptr(1)) if has_down else None,
                               tens(gr.halo_recv_ptr(0)) if has_up else None, tens(gr.halo_recv_ptr(1)) if has_down else None)
+
+    sweeps = args.sweeps
+
+    def step():  # BASELINE configs[3]: 50 synchronous sweeps
+        for _ in range(sweeps):
+            sweep()
 
     for _ in range(args.warmup):
         step()
@@ -416,10 +466,10 @@ def bench_potts_grid(args, pkg, rank, world, local):
     ms = timed(gr.stream, step, args.steps, 0, world, local)
     launches = pkg.default_api().kernel_launches() - launches0
     kernel_ms = []
-    for _ in range(min(args.steps, 10)):
-        step()
+    for _ in range(10):
+        sweep()
         kernel_ms.append(gr.last_kernel_ms())
-    # end to end: evidence from pinned host memory, one sweep, marginals back
+    # end to end: evidence from pinned host memory, the 50 sweeps, marginals back to pinned host memory
     marg_host = torch.empty((rows, N, K), dtype=torch.float32).pin_memory()
 
     def e2e_step():
@@ -427,17 +477,22 @@ def bench_potts_grid(args, pkg, rank, world, local):
         step()
         gr.api.grid_get_marginals(gr.h, marg_host.data_ptr())
 
-    e2e_steps = 2
+    e2e_steps = max(2, min(args.steps, 3))
     e2e_ms = timed(gr.stream, e2e_step, e2e_steps, 1, world, local)
     clocks = sampler.stop()
-    total_updates = sum_over_ranks(upd[0], world, local)
+    total_updates = sum_over_ranks(upd[0], world, local) * sweeps
     pix = rows * N
     # 64 B x [(4 m2f + unary) reads + (4 m2v + 4 m2f + marginal) writes] for interior pixels; exact count from the updates
     m2v_local = (upd[0] - pix) // 2
     alg_bytes = 64 * ((m2v_local + pix) + (2 * m2v_local + pix))
+    transport = None
+    if world > 1:
+        transport = {"kind": "peer stores over NVLink (CUDA IPC), fused in k_potts_sweep" if fused else "NCCL send/recv per sweep",
+                     "bytes_per_boundary_per_sweep": 2 * N * K * 4, "boundaries": world - 1}
     return {"ms": ms, "updates_per_step": total_updates, "kernel_ms": statistics.mean(kernel_ms), "alg_bytes": alg_bytes,
             "e2e_ms": e2e_ms, "e2e_steps": e2e_steps, "h2d": pix * K * 4, "d2h": pix * K * 4, "launches": launches,
-            "clocks": clocks, "dtype": "f32", "kernel": "k_potts_sweep", "scaling": "strong", "already_global": True}
+            "clocks": clocks, "dtype": "f32", "kernel": "k_potts_sweep", "scaling": "strong", "already_global": True,
+            "comm": transport, "bytes_are_per_rank": world > 1}
 
 
 def bench_hmm64(args, pkg, rank, world, local):
@@ -463,7 +518,8 @@ def bench_hmm64(args, pkg, rank, world, local):
     sampler = ClockSampler(local)
     sampler.start()
     launches0 = pkg.default_api().kernel_launches()
-    ms = timed(hm.stream, step, args.steps, 0, world, local)
+    ms = timed(hm.stream, step, args.steps, 0, world, local, min_ms=args.min_ms)
+    steps_timed = timed.last_steps
     launches = pkg.default_api().kernel_launches() - launches0
     kernel_ms = []
     for _ in range(min(args.steps, 3)):
@@ -483,7 +539,7 @@ def bench_hmm64(args, pkg, rank, world, local):
     alg_bytes = B * T * (12 * K + 2)  # forward message + marginal contract
     out = {"ms": ms, "updates_per_step": hm.n_updates, "kernel_ms": statistics.mean(kernel_ms), "alg_bytes": alg_bytes,
            "e2e_ms": e2e_ms, "e2e_steps": e2e_steps, "h2d": B * T, "d2h": tail * B * K * 4, "launches": launches,
-           "clocks": clocks, "dtype": "f32", "scaling": "weak",
+           "clocks": clocks, "dtype": "f32", "scaling": "weak", "steps_timed": steps_timed,
            "kernel": "k_hmm64_pass (forward launch + backward launch, one warp per chain)"}
     if K >= 128:
         # tensor-core path: each fp32 product is 6 bf16 MMAs (3-piece split operands, hmm_tc.cuh), 2 passes per time step
@@ -524,7 +580,8 @@ def bench_powerlaw(args, pkg, rank, world, local):
     sampler = ClockSampler(local)
     sampler.start()
     launches0 = pkg.default_api().kernel_launches()
-    ms = timed(pw.stream, step, args.steps, 0, world, local)
+    ms = timed(pw.stream, step, args.steps, 0, world, local, min_ms=args.min_ms)
+    steps_timed = timed.last_steps
     launches = pkg.default_api().kernel_launches() - launches0
     kernel_ms = []
     for _ in range(min(args.steps, 10)):
@@ -537,12 +594,12 @@ def bench_powerlaw(args, pkg, rank, world, local):
         step()
         pw.api.pairwise_get_marginals(pw.h, marg_host.data_ptr())
 
-    e2e_steps = max(2, min(args.steps, 5))
-    e2e_ms = timed(pw.stream, e2e_step, e2e_steps, 1, world, local)
+    e2e_ms = timed(pw.stream, e2e_step, max(2, min(args.steps, 5)), 1, world, local, min_ms=args.min_ms)
+    e2e_steps = timed.last_steps
     clocks = sampler.stop()
     return {"ms": ms, "updates_per_step": upd[0], "kernel_ms": statistics.mean(kernel_ms), "alg_bytes": pw.algorithmic_bytes,
             "e2e_ms": e2e_ms, "e2e_steps": e2e_steps, "h2d": n * K * 4, "d2h": n * K * 4, "launches": launches,
-            "clocks": clocks, "dtype": "f32", "kernel": "k_pw_small + k_pw_hub (one sweep)", "scaling": "weak"}
+            "clocks": clocks, "dtype": "f32", "kernel": "k_pw_small + k_pw_hub (one sweep)", "scaling": "weak", "steps_timed": steps_timed}
 
 
 def bench_engine_graph(args, pkg, rank, world, local, which):
@@ -643,33 +700,115 @@ def bench_engine_graph(args, pkg, rank, world, local, which):
     torch.cuda.synchronize()
     sampler = ClockSampler(local)
     sampler.start()
-    barrier(world)
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        step()
-    torch.cuda.synchronize()
-    ms = max_over_ranks(1e3 * (time.perf_counter() - t0), world, local)
+    steps = args.steps
+    while True:
+        barrier(world)
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            step()
+        torch.cuda.synchronize()
+        ms = max_over_ranks(1e3 * (time.perf_counter() - t0), world, local)
+        if ms >= args.min_ms or steps >= 1 << 16:
+            break
+        steps = int(max(steps * 2, steps * 1.25 * args.min_ms / max(ms, 1e-3))) + 1
     clocks = sampler.stop()
     launches = api.kernel_launches() - launches0 - 0
-    return {"ms": ms, "updates_per_step": upd, "kernel_ms": ms / args.steps, "alg_bytes": alg_bytes, "e2e_ms": ms,
-            "e2e_steps": args.steps, "h2d": int(vals.nbytes) if which == "chain1k" else int(unary.nbytes), "d2h": 0,
-            "launches": launches, "clocks": clocks, "dtype": dtype,
+    ran = {1: "level schedule", 2: "sequential executor", 3: "memoised level schedule (replay)", 4: "closed-form plan"}.get(
+        int(api.last_schedule(store.h)), "?")
+    return {"ms": ms, "updates_per_step": upd, "kernel_ms": ms / steps, "alg_bytes": alg_bytes, "e2e_ms": ms, "steps_timed": steps,
+            "e2e_steps": steps, "h2d": int(vals.nbytes) if which == "chain1k" else int(unary.nbytes), "d2h": 0,
+            "launches": launches, "clocks": clocks, "dtype": dtype, "answered_by": ran,
             "kernel": "generic engine (k_bfs / k_ms_* / k_rule_* / k_apply)", "scaling": "weak",
             "timer": "host wall clock around synchronous ABI calls (each call ends with a stream sync)"}
 
 
 # ---------------------------------------------------------------------------------------------------------------
+WORKLOADS = ["potts_grid", "gauss_chains", "hmm64", "hmm512", "powerlaw", "powerlaw_engine", "chain1k"]
+BENCH_FN = {"gauss_chains": bench_gauss_chains, "potts_grid": bench_potts_grid, "hmm64": bench_hmm64, "hmm512": bench_hmm64,
+            "powerlaw": bench_powerlaw, "powerlaw_engine": lambda *a: bench_engine_graph(*a, "powerlaw"),
+            "chain1k": lambda *a: bench_engine_graph(*a, "chain1k")}
+
+
+def run_workload(args, name, pkg, rank, world, local, main_record):
+    """One workload -> its record (the bench line without the keys that only the top-level line carries)."""
+    import copy
+    import gc
+
+    import torch
+
+    a = copy.copy(args)
+    a.workload = name
+    a.min_ms = 0.0 if main_record else 1000.0  # the main record times exactly --steps; sub-records run for >= 1 s
+    if name == "hmm512":  # the forward + marginal planes of 1,024 x 1e5 x 512 are 2 x 210 GB: batch tiles of <= 256 chains per GPU (SURVEY 8d)
+        a.hmm_chains = min(args.hmm_chains, max(1, min(256, 1024 // world)))
+    elif name == "hmm64":
+        a.hmm_chains = min(args.hmm_chains, max(1, 1024 // world)) if world > 1 else args.hmm_chains
+    if not main_record:
+        a.steps, a.warmup = min(args.steps, 3), 3
+        if name == "powerlaw_engine":
+            a.pl_vars = min(args.pl_vars, 1000000)  # the explicit Signal graph of 10M variables takes minutes to build on the host
+    r = BENCH_FN[name](a, pkg, rank, world, local)
+    peak, peak_src, _ = measured_peaks()
+    steps = r.get("steps_timed", a.steps)
+    ms_per_step = r["ms"] / steps
+    total_updates = r["updates_per_step"] if r.get("already_global") else r["updates_per_step"] * world
+    value = total_updates / (ms_per_step * 1e-3)
+    e2e_value = total_updates / (r["e2e_ms"] / r["e2e_steps"] * 1e-3)
+    achieved = r["alg_bytes"] / (r["kernel_ms"] * 1e-3) / 1e9 if r["alg_bytes"] else None
+    rec = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps, "warmup": a.warmup,
+           "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": r["scaling"], "vs_baseline": None,
+           "dtype": r["dtype"], "data": "synthetic", "config": workload_config(a, world),
+           "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(sum_over_ranks(r["h2d"], world, local)),
+                   "d2h_bytes_per_step": int(sum_over_ranks(r["d2h"], world, local)), "steps": r["e2e_steps"],
+                   "ms_per_step": r["e2e_ms"] / r["e2e_steps"]},
+           "gpu_launches": int(r["launches"]), "clocks": r["clocks"],
+           "roofline": {"bound": "hbm", "kernel": r["kernel"], "achieved": achieved, "peak": peak, "unit": "GB/s",
+                        "frac": (achieved / peak) if achieved else None, "traffic": None, "peak_source": peak_src,
+                        "kernel_ms": r["kernel_ms"], "algorithmic_bytes_per_launch": r["alg_bytes"]}}
+    for k in ("timer", "comm", "answered_by"):
+        if r.get(k) is not None:
+            rec[k] = r[k]
+    if "tensor" in r:  # K = 512 HMM: tensor-pipe utilisation beside the HBM figure (north star: "or tensor-pipe utilisation against peak")
+        peaks = json.loads((ROOT / "MEASURED_PEAKS.json").read_text()) if (ROOT / "MEASURED_PEAKS.json").exists() else {}
+        tpeak = float(peaks.get("bf16_tflops_sustained", 1410.1))
+        tf = r["tensor"]["issued_flops"] / (r["kernel_ms"] * 1e-3) / 1e12
+        rec["roofline_tensor"] = {"bound": "tensor", "achieved": tf, "peak": tpeak, "unit": "TFLOP/s", "frac": tf / tpeak,
+                                  "fp32_equivalent_tflops": r["tensor"]["fp32_equivalent_flops"] / (r["kernel_ms"] * 1e-3) / 1e12,
+                                  "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained (cuBLAS bf16 8192^3, dense)",
+                                  "note": r["tensor"]["note"]}
+    traffic_file = ROOT / "profiles" / f"traffic_{name}.json"
+    if traffic_file.exists():
+        try:
+            tj = json.loads(traffic_file.read_text())
+            rec["roofline"]["traffic"] = tj.get("dram_bytes_per_launch")
+            if "dram_bytes_per_chain_step" in tj:  # HMM workloads: the ncu capture ran fewer time steps
+                rec["roofline"]["traffic"] = tj["dram_bytes_per_chain_step"] * a.hmm_chains * a.hmm_steps
+        except Exception:
+            pass
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        v, sample = cpu_baseline_workload(name, 12.0 if main_record else 5.0)
+        rec["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": 1, "kind": "port", "sample": sample,
+                               "host_cores_available": os.cpu_count()}
+    del r
+    gc.collect()
+    torch.cuda.synchronize()
+    return rec
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="gauss_chains", choices=["gauss_chains", "potts_grid", "hmm64", "hmm512", "powerlaw", "powerlaw_engine", "chain1k"])
+    ap.add_argument("--workload", default="potts_grid", choices=WORKLOADS)
+    ap.add_argument("--others", default=None, help="comma-separated sub-records to attach (default: every other config when the "
+                                                   "default workload runs; 'none' to skip)")
     ap.add_argument("--dtype", default="f32", choices=["f32", "f64"])
     ap.add_argument("--chains", type=int, default=65536)
     ap.add_argument("--chain-steps", type=int, default=1024)
     ap.add_argument("--grid", type=int, default=8192)
+    ap.add_argument("--sweeps", type=int, default=50)
     ap.add_argument("--hmm-chains", type=int, default=1024)
     ap.add_argument("--hmm-steps", type=int, default=100000)
     ap.add_argument("--pl-vars", type=int, default=10000000)
@@ -682,49 +821,24 @@ def main():
 
     pkg = entry.load_package()
     rank, world, local = dist_setup(args.gpus)
-    if args.workload == "hmm512" and args.hmm_steps == 100000:
-        args.hmm_steps = 2000  # 1,024 x 1e5 x 512 marginals do not fit one GPU: time a 2,000-step slice
-    fn = {"gauss_chains": bench_gauss_chains, "potts_grid": bench_potts_grid, "hmm64": bench_hmm64, "hmm512": bench_hmm64,
-          "powerlaw": bench_powerlaw, "powerlaw_engine": lambda *a: bench_engine_graph(*a, "powerlaw"), "chain1k": lambda *a: bench_engine_graph(*a, "chain1k")}[args.workload]
-    r = fn(args, pkg, rank, world, local)
-    peak, peak_src, _ = measured_peaks()
-    ms_per_step = r["ms"] / args.steps
-    total_updates = r["updates_per_step"] if r.get("already_global") else r["updates_per_step"] * world
-    value = total_updates / (ms_per_step * 1e-3)
-    e2e_value = total_updates / (r["e2e_ms"] / r["e2e_steps"] * 1e-3)
-    achieved = r["alg_bytes"] / (r["kernel_ms"] * 1e-3) / 1e9 if r["alg_bytes"] else None
-    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": r["scaling"], "vs_baseline": None,
-            "dtype": r["dtype"], "data": "synthetic", "config": workload_config(args, world),
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": r["h2d"], "d2h_bytes_per_step": r["d2h"]},
-            "gpu_launches": int(r["launches"]), "clocks": r["clocks"],
-            "roofline": {"bound": "hbm", "kernel": r["kernel"], "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": (achieved / peak) if achieved else None, "traffic": None, "peak_source": peak_src,
-                         "kernel_ms": r["kernel_ms"], "algorithmic_bytes_per_launch": r["alg_bytes"]}}
-    if "timer" in r:
-        line["timer"] = r["timer"]
-    if "tensor" in r:  # K = 512 HMM: tensor-pipe utilisation beside the HBM figure (north star: "or tensor-pipe utilisation against peak")
-        peaks = json.loads((ROOT / "MEASURED_PEAKS.json").read_text()) if (ROOT / "MEASURED_PEAKS.json").exists() else {}
-        tpeak = float(peaks.get("bf16_tflops_sustained", 1410.1))
-        tf = r["tensor"]["issued_flops"] / (r["kernel_ms"] * 1e-3) / 1e12
-        line["roofline_tensor"] = {"bound": "tensor", "achieved": tf, "peak": tpeak, "unit": "TFLOP/s", "frac": tf / tpeak,
-                                   "fp32_equivalent_tflops": r["tensor"]["fp32_equivalent_flops"] / (r["kernel_ms"] * 1e-3) / 1e12,
-                                   "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained (cuBLAS bf16 8192^3, dense)",
-                                   "note": r["tensor"]["note"]}
-    traffic_file = ROOT / "profiles" / f"traffic_{args.workload}.json"
-    if traffic_file.exists():
-        try:
-            tj = json.loads(traffic_file.read_text())
-            line["roofline"]["traffic"] = tj.get("dram_bytes_per_launch")
-            if "dram_bytes_per_chain_step" in tj:  # HMM workloads: the ncu capture ran fewer time steps
-                line["roofline"]["traffic"] = tj["dram_bytes_per_chain_step"] * args.hmm_chains * args.hmm_steps
-        except Exception:
-            pass
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+    if rank == 0 and not args.no_cpu_baseline:
         subprocess.run(["make", "-C", str(ROOT / "oracle")], check=True, stdout=subprocess.DEVNULL)
-        v, sample = cpu_baseline_workload(args.workload)
-        line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": 1, "kind": "port", "sample": sample,
-                                "host_cores_available": os.cpu_count()}
+    line = run_workload(args, args.workload, pkg, rank, world, local, main_record=True)
+    if NUMA_NOTE:
+        line["host_binding"] = dict(NUMA_NOTE)
+    if args.others is None:
+        others = [w for w in WORKLOADS if w != "potts_grid"] if args.workload == "potts_grid" else []
+        if world > 1:  # the batch-sharded configs only; the single-GPU ones are on the N = 1 line
+            others = [w for w in others if w in ("gauss_chains", "hmm64", "hmm512")]
+    else:
+        others = [w for w in args.others.split(",") if w and w != "none"]
+    if others:
+        line["others"] = {}
+        for name in others:
+            try:
+                line["others"][name] = run_workload(args, name, pkg, rank, world, local, main_record=False)
+            except Exception as e:  # noqa: BLE001 - a failing sub-record must not take the main record down; it is reported
+                line["others"][name] = {"error": f"{type(e).__name__}: {str(e)[:300]}"}
     if rank == 0:
         print(json.dumps(line))
     if world > 1:
