@@ -13,6 +13,7 @@
 #include <algorithm>
 #include <cstring>
 #include <map>
+#include <memory>
 
 #include "common.cuh"
 #include "host_graph.hpp"
@@ -594,6 +595,8 @@ struct ResidentArgs {
     const long long* key_table;  // [n_keys] element offset of the key's table in `tables` (CAT_TABLE: [2][K][K], HMM_EMIT: [K][n_sym])
     const int* key_nsym;       // [n_keys] HMM_EMIT: number of symbols
     long long* out;            // [0] levels [1] updates [2] final marginals [3] final linked [4] last lvl_epoch [5] key without rule
+    uint32_t *rec_list, *rec_desc;  // schedule recording (memoised replay): members level by level, descriptors (level, key, count, offset)
+    uint32_t rec_list_cap, rec_desc_cap;  // out[6] = descriptors written, out[7] = members written (0xFFFFFFFF.. = overflow)
     const uint8_t* pend_at_req;  // [n_req] strict rule B (k_request_check)
     const uint32_t *hz_m, *hz_l;  // rule F: signals that must not be pending when the marginal / linked level of the final phase starts
     uint32_t n_hz_m, n_hz_l;
@@ -682,8 +685,10 @@ __global__ void __launch_bounds__(1024) k_update_resident(View e, T* __restrict_
     __shared__ uint32_t s_total;
     __shared__ uint32_t s_key_cnt[256], s_key_base[256];  // per-key frontier cursors / partition starts (<= 252 keys)
     __shared__ int s_key_rule[256];
+    __shared__ uint32_t s_rec_off[256], s_rec_n[3];  // recording: per-key offsets of the level, [0] members [1] descriptors [2] level index
     __shared__ T s_cat_in[32][64];  // categorical family: one incoming message per warp (K <= 64)
     const uint32_t tid = threadIdx.x, NT = blockDim.x;
+    if (tid < 3) s_rec_n[tid] = 0;
     for (int k = tid; k < a.n_keys; k += NT) {
         s_key_base[k] = e.key_base[k];
         s_key_rule[k] = a.key_rule[k];
@@ -706,6 +711,35 @@ __global__ void __launch_bounds__(1024) k_update_resident(View e, T* __restrict_
         }
         __syncthreads();
         if (*(volatile int*)e.err_flag) return;  // refused before anything of this level is computed or applied (uniform)
+        if (a.rec_list) {  // record the level for the memoised schedule
+            if (tid == 0) {
+                uint32_t off = s_rec_n[0], nd = s_rec_n[1];
+                for (int k = 0; k < a.n_keys; ++k) {
+                    const uint32_t cnt = e.key_cnt[k];
+                    s_rec_off[k] = off;
+                    if (!cnt) continue;
+                    if (nd < a.rec_desc_cap && off + cnt <= a.rec_list_cap) {
+                        a.rec_desc[4 * nd] = s_rec_n[2];
+                        a.rec_desc[4 * nd + 1] = (uint32_t)k;
+                        a.rec_desc[4 * nd + 2] = cnt;
+                        a.rec_desc[4 * nd + 3] = off;
+                        ++nd;
+                    } else {
+                        nd = 0xFFFFFFFFu;  // overflow: the recording is dropped
+                    }
+                    off += cnt;
+                }
+                s_rec_n[0] = off;
+                s_rec_n[1] = nd;
+                ++s_rec_n[2];
+            }
+            __syncthreads();
+            if (s_rec_n[1] != 0xFFFFFFFFu)
+                for (int k = 0; k < a.n_keys; ++k) {
+                    const uint32_t cnt = e.key_cnt[k], base = e.key_base[k];
+                    for (uint32_t i = tid; i < cnt; i += NT) a.rec_list[s_rec_off[k] + i] = e.front[base + i];
+                }
+        }
         for (int k = 0; k < a.n_keys; ++k) {
             const uint32_t cnt = e.key_cnt[k], base = e.key_base[k];
             if (!cnt) continue;
@@ -845,6 +879,62 @@ __global__ void __launch_bounds__(1024) k_update_resident(View e, T* __restrict_
         a.out[2] = fin[0];
         a.out[3] = fin[1];
         a.out[4] = lvl;
+        a.out[6] = s_rec_n[1] == 0xFFFFFFFFu ? -1 : (long long)s_rec_n[1];
+        a.out[7] = s_rec_n[0];
+    }
+}
+
+// ---- memoised schedule: replay ----------------------------------------------------------------------------------------
+// The level schedule is a function of the request, the structure and the FLAG state (props, nibbles) alone - values never
+// steer it. A request that arrives with the same ids and a flag state bit-identical to a recorded run therefore executes
+// the same signals level by level and ends in the same flag state: the engine replays the recorded levels (rules only: no
+// traversal, no checks, no set_value! bookkeeping) and copies the recorded final flags. Small graphs: all levels in one
+// launch (block barrier between levels); large graphs: one batched rule kernel per (level, rule key), no host round trip.
+__global__ void k_state_differs(const uint8_t* props, const uint8_t* props0, size_t n, const uint64_t* nib, const uint64_t* nib0, size_t n_chunks,
+                                int* flag) {
+    const size_t stride = (size_t)gridDim.x * blockDim.x, t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    bool diff = false;
+    for (size_t i = t; i < n && !diff; i += stride) diff = props[i] != props0[i];
+    for (size_t i = t; i < n_chunks && !diff; i += stride) diff = nib[i] != nib0[i];
+    if (diff) *flag = 1;
+}
+struct ReplayArgs {
+    const uint32_t *list, *desc;
+    uint32_t n_desc;
+    int n_keys, family;
+    const int* key_rule;
+    const double* key_param;
+    const void* fparam;
+    const void* tables;
+    const long long* key_table;
+    const int* key_nsym;
+};
+template <class T>
+__global__ void __launch_bounds__(1024) k_replay_resident(View e, T* __restrict__ val, ReplayArgs a) {
+    __shared__ int s_key_rule[256];
+    __shared__ T s_cat_in[32][64];
+    const uint32_t tid = threadIdx.x, NT = blockDim.x;
+    for (int k = tid; k < a.n_keys; k += NT) s_key_rule[k] = a.key_rule[k];
+    __syncthreads();
+    uint32_t cur_level = 0xFFFFFFFFu;
+    for (uint32_t d = 0; d < a.n_desc; ++d) {
+        const uint32_t level = a.desc[4 * d], key = a.desc[4 * d + 1], cnt = a.desc[4 * d + 2], off = a.desc[4 * d + 3];
+        if (level != cur_level) {
+            __syncthreads();  // the values of a level are inputs of the next
+            cur_level = level;
+        }
+        const int rule = s_key_rule[key];
+        if (rule == -2) {
+            if (tid == 0) atomicOr(e.err_flag, ERR_RULE_ARG);
+            continue;
+        }
+        const T defp = (T)a.key_param[key];
+        if (a.family == CXB_FAMILY_CATEGORICAL) {
+            const T* tb = a.key_table[key] >= 0 ? (const T*)a.tables + a.key_table[key] : nullptr;
+            for (uint32_t i = tid >> 5; i < cnt; i += NT >> 5) rule_cat_warp<T>(e, val, a.list[off + i], rule, tb, a.key_nsym[key], defp, s_cat_in[tid >> 5]);
+        } else {
+            for (uint32_t i = tid; i < cnt; i += NT) rule_small_one<T>(e, val, a.list[off + i], a.family, rule, (const T*)a.fparam, defp);
+        }
     }
 }
 
@@ -1170,11 +1260,153 @@ __global__ void k_rule_cat(View e, T* __restrict__ val, const uint32_t* list, ui
     }
 }
 
+// ---- closed-form plan: disjoint random-walk chains -----------------------------------------------------------------------
+// A memoised schedule whose graph is a set of linear-Gaussian random-walk chains (test/inference_engine_tests.jl:436-462,
+// canonical rules of SURVEY Appendix C) does not need its 2T-1 recorded levels: one thread per chain runs the forward
+// filter and the backward smoother in registers and writes the same 6T-4 signals. The arithmetic is rule_small_one's,
+// expression for expression (GAUSS_OBS, GAUSS_RW, left-to-right canonical sums in dependency order), so the values are
+// bit-identical to the level schedule's. Index arrays (built once from the wiring) say where each signal lives in `val`.
+struct ChainPlanArgs {
+    const uint32_t *i_y, *i_obs, *i_pred, *i_fwd, *i_bwd, *i_back, *i_marg;  // [pos] signal ids; 0xFFFFFFFF = does not exist
+    const void *par_r, *par_q;  // [pos] noise variance of lik_t / tr_t (engine dtype)
+    const uint32_t* base;       // [n_chains] position of (chain, t = 0)
+    const uint32_t* len;        // [n_chains] T of the chain
+    uint32_t stride;            // position of (chain, t) = base[chain] + t * stride
+    uint32_t n_chains;
+};
+template <class T, int TILE>
+__global__ void __launch_bounds__(64) k_chain_plan(T* __restrict__ val, ChainPlanArgs a) {
+    const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= a.n_chains) return;
+    const uint32_t b0 = a.base[c], Tn = a.len[c], st = a.stride;
+    const T* __restrict__ pr_r = (const T*)a.par_r;
+    const T* __restrict__ pr_q = (const T*)a.par_q;
+    T L = 0, h = 0;
+    for (uint32_t t0 = 0; t0 < Tn; t0 += TILE) {  // forward: m2v(x_t, lik_t), m2v(x_t, tr_{t-1}), m2f(x_t, tr_t)
+        uint32_t iy[TILE], io[TILE], ip[TILE], im[TILE];
+        T yy[TILE], rr[TILE], qq[TILE];
+#pragma unroll
+        for (int k = 0; k < TILE; ++k) {
+            const uint32_t t = t0 + k, pos = b0 + (t < Tn ? t : 0) * st;
+            iy[k] = a.i_y[pos];
+            io[k] = a.i_obs[pos];
+            ip[k] = a.i_pred[pos];
+            im[k] = a.i_fwd[pos];
+            rr[k] = pr_r[pos];
+            qq[k] = t > 0 && t < Tn ? pr_q[pos - st] : T(0);  // tr_{t-1}
+        }
+#pragma unroll
+        for (int k = 0; k < TILE; ++k) yy[k] = val[(size_t)iy[k] * 2];
+#pragma unroll
+        for (int k = 0; k < TILE; ++k) {
+            const uint32_t t = t0 + k;
+            if (t >= Tn) break;
+            const T p = rr[k];
+            const T oL = T(1) / p, oh = yy[k] / p;  // GAUSS_OBS
+            val[(size_t)io[k] * 2] = oL;
+            val[(size_t)io[k] * 2 + 1] = oh;
+            T aL = oL, ah = oh;
+            if (t > 0) {  // GAUSS_RW from m2f(x_{t-1}, tr_{t-1}) = (L, h)
+                const T q = qq[k];
+                const T den = T(1) + q * L;
+                const T pL = L / den, ph = h / den;
+                val[(size_t)ip[k] * 2] = pL;
+                val[(size_t)ip[k] * 2 + 1] = ph;
+                aL = aL + pL;
+                ah = ah + ph;
+            }
+            L = aL;
+            h = ah;
+            if (im[k] != 0xFFFFFFFFu) {  // m2f(x_t, tr_t) = lik (+) tr_{t-1}
+                val[(size_t)im[k] * 2] = L;
+                val[(size_t)im[k] * 2 + 1] = h;
+            }
+        }
+    }
+    L = 0;
+    h = 0;
+    for (int64_t t1 = (int64_t)Tn - 1; t1 >= 0; t1 -= TILE) {  // backward: m2v(x_t, tr_t), m2f(x_t, tr_{t-1}), marginal(x_t)
+        uint32_t io[TILE], ip[TILE], ib[TILE], ik[TILE], ig[TILE];
+        T oL[TILE], oh[TILE], pL[TILE], ph[TILE], qq[TILE];
+#pragma unroll
+        for (int k = 0; k < TILE; ++k) {
+            const int64_t t = t1 - k;
+            const uint32_t pos = b0 + (uint32_t)(t >= 0 ? t : 0) * st;
+            io[k] = a.i_obs[pos];
+            ip[k] = a.i_pred[pos];
+            ib[k] = a.i_bwd[pos];
+            ik[k] = a.i_back[pos];
+            ig[k] = a.i_marg[pos];
+            qq[k] = pr_q[pos];  // tr_t (unused at t = T-1)
+        }
+#pragma unroll
+        for (int k = 0; k < TILE; ++k) {
+            oL[k] = val[(size_t)io[k] * 2];
+            oh[k] = val[(size_t)io[k] * 2 + 1];
+            const bool hp = ip[k] != 0xFFFFFFFFu;
+            pL[k] = hp ? val[(size_t)ip[k] * 2] : T(0);
+            ph[k] = hp ? val[(size_t)ip[k] * 2 + 1] : T(0);
+        }
+#pragma unroll
+        for (int k = 0; k < TILE; ++k) {
+            const int64_t t = t1 - k;
+            if (t < 0) break;
+            T bL = 0, bh = 0;
+            T aL = oL[k], ah = oh[k];
+            T gL = oL[k], gh = oh[k];
+            if (t > 0) {
+                gL = gL + pL[k];
+                gh = gh + ph[k];
+            }
+            if (t < (int64_t)Tn - 1) {  // GAUSS_RW from m2f(x_{t+1}, tr_t) = (L, h)
+                const T q = qq[k];
+                const T den = T(1) + q * L;
+                bL = L / den;
+                bh = h / den;
+                val[(size_t)ib[k] * 2] = bL;
+                val[(size_t)ib[k] * 2 + 1] = bh;
+                aL = aL + bL;
+                ah = ah + bh;
+                gL = gL + bL;
+                gh = gh + bh;
+            }
+            L = aL;
+            h = ah;
+            if (ik[k] != 0xFFFFFFFFu) {  // m2f(x_t, tr_{t-1}) = lik (+) tr_t
+                val[(size_t)ik[k] * 2] = L;
+                val[(size_t)ik[k] * 2 + 1] = h;
+            }
+            val[(size_t)ig[k] * 2] = gL;  // marginal = lik (+) tr_{t-1} (+) tr_t, left to right
+            val[(size_t)ig[k] * 2 + 1] = gh;
+        }
+    }
+}
+
 // =================================================================================================================
 struct RuleDef {
     int kind = CXB_RULE_NONE;
     std::vector<double> params;
 };
+
+// one recorded run of the level schedule (see k_replay_resident)
+struct Memo {
+    std::vector<int64_t> req_ids;
+    DBuf<uint8_t> pre_props, post_props;
+    DBuf<uint64_t> pre_nib, post_nib;
+    DBuf<uint32_t> lists, desc;  // members level by level; descriptors (level, key, count, offset)
+    std::vector<uint32_t> h_desc;
+    uint32_t n_desc = 0, n_list = 0;
+    cxb_update_stats stats{};
+    unsigned long long kind_count[6] = {0, 0, 0, 0, 0, 0};
+    uint64_t last_use = 0;
+    size_t bytes = 0;
+    int plan = 0;  // 0: replay the recorded levels; > 0: a closed-form plan computes the values (DeviceEngine::run_plan)
+};
+template <class T>
+inline void swap_buf(DBuf<T>& a, DBuf<T>& b) {
+    std::swap(a.p, b.p);
+    std::swap(a.cap, b.cap);
+}
 
 struct DeviceEngine {
     int device = 0, dtype = CXB_F64, dim = 1, family = 0;
@@ -1212,6 +1444,14 @@ struct DeviceEngine {
     DBuf<unsigned char> d_snap_val;
     bool snap_valid = false;
     std::vector<int64_t> tr_var;  // trace: TracedInferenceExecution.variable_id
+    // memoised schedules (CXB_MEMO=0 turns them off)
+    std::vector<std::unique_ptr<Memo>> memos;
+    bool memo_on = true;
+    uint64_t memo_clock = 0;
+    std::unique_ptr<Memo> rec;  // the recording of the request that is running
+    DBuf<int> d_memo_flags;
+    HBuf<int> h_memo_flags;
+    static constexpr size_t MAX_MEMOS = 4;
 
     // device state
     DBuf<uint32_t> d_dep_off, d_dep_ids, d_nib_off, d_lis_off, d_lis_ids, d_lis_slot, d_done, d_visit, d_probe;
@@ -1279,6 +1519,7 @@ struct DeviceEngine {
         CXB_CUDA(cudaSetDevice(device));
         CXB_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
         if (const char* e = getenv("CXB_STRICT")) strict = atoi(e) != 0;
+        if (const char* e = getenv("CXB_MEMO")) memo_on = atoi(e) != 0;
         CXB_CUDA(d_flags.reserve(4));
         CXB_CUDA(d_counters.reserve(8));
         CXB_CUDA(d_kind_count.reserve(8));
@@ -1456,6 +1697,7 @@ struct DeviceEngine {
         }
         CXB_CUDA(cudaStreamSynchronize(stream));
         rules_dirty = false;
+        ++rules_version;
         return CXB_OK;
     }
 
@@ -1516,6 +1758,8 @@ struct DeviceEngine {
             }
             if ((st = reset_epochs())) return st;
             snap_valid = false;
+            memos.clear();  // recorded schedules belong to the old structure
+            chain_plan.tried = chain_plan.ok = false;
             if ((st = build_keys())) return st;
             CXB_CUDA(d_key_count.reserve(512));
             CXB_CUDA(cudaStreamSynchronize(stream));
@@ -1572,6 +1816,7 @@ struct DeviceEngine {
     int n_keys() const { return (int)key_ftype.size() + 2; }
     int key_no_rule() const { return (int)key_ftype.size() + 1; }
 
+    const uint32_t* rule_list_base = nullptr;  // where the members of the level being evaluated live (frontier buffer / a memo's lists)
     template <class T>
     int32_t launch_rules_t(uint32_t total) {
         View v = view();
@@ -1601,7 +1846,7 @@ struct DeviceEngine {
                 rd = &it->second;
                 rule = rd->kind;
             }
-            const uint32_t* list = d_front.p + off;
+            const uint32_t* list = rule_list_base + off;
             bool cat_rule = rule == CXB_RULE_CAT_TABLE || rule == CXB_RULE_POTTS || rule == CXB_RULE_HMM_EMIT;
             if (categorical && (rule < 0 || cat_rule)) {
                 const T* tb = nullptr;
@@ -1751,7 +1996,8 @@ struct DeviceEngine {
         return flags_to_status(h_flags.p[0]);
     }
 
-    int32_t launch_rules(uint32_t total) {
+    int32_t launch_rules(uint32_t total, const uint32_t* list_base = nullptr) {
+        rule_list_base = list_base ? list_base : d_front.p;
         return dtype == CXB_F32 ? launch_rules_t<float>(total) : launch_rules_t<double>(total);
     }
 
@@ -1785,6 +2031,22 @@ struct DeviceEngine {
             CXB_CUDA(cudaEventRecord(tr_ev0, stream));
         }
         for (auto& c : chunks) CXB_LAUNCH(k_check_independent, cdiv(c.total, 256), 256, 0, stream, v, c, lvl_epoch, req_epoch, check_mode);
+        if (rec) {  // record the level for the memoised schedule (the frontier buffer is reused by the next level)
+            if ((size_t)rec->n_list + total > rec->lists.cap) {
+                rec.reset();  // more executions than the recording has room for: give up on this one
+            } else {
+                const uint32_t level = rec->h_desc.empty() ? 0u : rec->h_desc[rec->h_desc.size() - 4] + 1;
+                for (int k = 0; k < nk; ++k) {
+                    const uint32_t cnt = h_counts.p[k];
+                    if (!cnt) continue;
+                    CXB_CUDA(cudaMemcpyAsync(rec->lists.p + rec->n_list, d_front.p + h_counts.p[nk + k], cnt * sizeof(uint32_t), cudaMemcpyDeviceToDevice,
+                                             stream));
+                    const uint32_t d4[4] = {level, (uint32_t)k, cnt, rec->n_list};
+                    rec->h_desc.insert(rec->h_desc.end(), d4, d4 + 4);
+                    rec->n_list += cnt;
+                }
+            }
+        }
         if ((st = launch_rules(total))) return st;  // rule and set_value! kernels return at once when a check refused the level
         for (auto& c : chunks) CXB_LAUNCH(k_apply, cdiv(c.total, 256), 256, 0, stream, v, c, req_epoch, check_mode);
         if (check_mode == 1 && v.nl_epoch) {  // strict rule E, second half
@@ -2029,6 +2291,12 @@ struct DeviceEngine {
         a.key_table = d_key_table.p;
         a.key_nsym = d_key_nsym.p;
         a.out = d_res_out.p;
+        if (rec) {
+            a.rec_list = rec->lists.p;
+            a.rec_desc = rec->desc.p;
+            a.rec_list_cap = (uint32_t)std::min<size_t>(rec->lists.cap, 0xFFFFFFF0u);
+            a.rec_desc_cap = (uint32_t)std::min<size_t>(rec->desc.cap / 4, 0x3FFFFFF0u);
+        }
         a.pend_at_req = d_pend_req.p;
         a.hz_m = d_hz_m.p;
         a.hz_l = d_hz_l.p;
@@ -2045,6 +2313,14 @@ struct DeviceEngine {
         CXB_CUDA(cudaMemcpyAsync(h_flags.p, d_flags.p, sizeof(int), cudaMemcpyDeviceToHost, stream));
         CXB_CUDA(cudaStreamSynchronize(stream));
         lvl_epoch = (uint32_t)h_res_out.p[4];
+        if (rec) {
+            if (h_res_out.p[6] < 0) {
+                rec.reset();
+            } else {
+                rec->n_desc = (uint32_t)h_res_out.p[6];
+                rec->n_list = (uint32_t)h_res_out.p[7];
+            }
+        }
         stats.levels = h_res_out.p[0];
         stats.updates = h_res_out.p[1];
         stats.final_marginals = h_res_out.p[2];
@@ -2054,6 +2330,355 @@ struct DeviceEngine {
         const int f = h_flags.p[0];
         if (f & ERR_NO_RULE_KEY) return no_rule_status();
         return flags_to_status(f);
+    }
+
+    // ---- memoised schedules -----------------------------------------------------------------------------------------------
+    size_t flag_bytes() const { return n_uploaded + csr.nib.size() * sizeof(uint64_t); }
+    void begin_recording() {
+        rec.reset(new Memo());
+        const size_t N = std::max<size_t>(n_uploaded, 1);
+        // a signal runs at most once in the loop phase and once in the final phase; a descriptor holds >= 1 member
+        if (rec->lists.reserve(2 * N) != cudaSuccess || (resident_ok() && rec->desc.reserve(4 * (2 * N + 8)) != cudaSuccess) ||
+            rec->post_props.reserve(N) != cudaSuccess || rec->post_nib.reserve(std::max<size_t>(csr.nib.size(), 1)) != cudaSuccess) {
+            cudaGetLastError();
+            rec.reset();  // no room for a recording: run without
+        }
+    }
+    int32_t commit_recording(int64_t n, const int64_t* ids) {
+        Memo& m = *rec;
+        if (last_ran != CXB_SCHEDULE_LEVEL) return CXB_OK;
+        const size_t N = n_uploaded;
+        if (!resident_ok()) {  // per-level path: the descriptors were collected on the host
+            m.n_desc = (uint32_t)(m.h_desc.size() / 4);
+            CXB_CUDA(m.desc.reserve(std::max<size_t>(m.h_desc.size(), 4)));
+            if (!m.h_desc.empty())
+                CXB_CUDA(cudaMemcpyAsync(m.desc.p, m.h_desc.data(), m.h_desc.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, stream));
+        } else {  // resident path: they were written by the kernel; the per-level replay of large graphs is not used for these
+            m.h_desc.clear();
+        }
+        if (N) CXB_CUDA(cudaMemcpyAsync(m.post_props.p, d_props.p, N, cudaMemcpyDeviceToDevice, stream));
+        if (!csr.nib.empty()) CXB_CUDA(cudaMemcpyAsync(m.post_nib.p, d_nib.p, csr.nib.size() * sizeof(uint64_t), cudaMemcpyDeviceToDevice, stream));
+        CXB_CUDA(cudaStreamSynchronize(stream));
+        // the rollback snapshot taken before the request IS the pre-state: hand its flag buffers over
+        swap_buf(m.pre_props, d_snap_props);
+        swap_buf(m.pre_nib, d_snap_nib);
+        snap_valid = false;
+        m.req_ids.assign(ids, ids + n);
+        m.stats = stats;
+        for (int k = 0; k < 6; ++k) m.kind_count[k] = h_kind_count.p[k];
+        m.last_use = ++memo_clock;
+        m.bytes = 2 * flag_bytes() + (m.lists.cap + m.desc.cap) * sizeof(uint32_t);
+        m.plan = recognise_plan(m);
+        if (memos.size() >= MAX_MEMOS) {  // evict the least recently used
+            size_t lru = 0;
+            for (size_t i = 1; i < memos.size(); ++i)
+                if (memos[i]->last_use < memos[lru]->last_use) lru = i;
+            memos.erase(memos.begin() + lru);
+        }
+        memos.push_back(std::move(rec));
+        return CXB_OK;
+    }
+    // ---- closed-form plans -----------------------------------------------------------------------------------------------
+    // A plan computes the VALUES of a recorded schedule with a kernel written for the structure (the flags still come from
+    // the recording). Plan 1: disjoint random-walk chains (k_chain_plan). 0 = none: replay the recorded levels.
+    struct ChainPlan {
+        bool tried = false, ok = false;
+        DBuf<uint32_t> i_y, i_obs, i_pred, i_fwd, i_bwd, i_back, i_marg, base, len;
+        DBuf<unsigned char> par_r, par_q;
+        std::vector<int64_t> pos_lik, pos_tr;  // factor id per position (-1: none), to refresh the parameters
+        std::vector<int64_t> xs_sorted;        // the state variables, ascending (the request must name exactly these)
+        uint32_t stride = 1, n_chains = 0;
+        size_t n_pos = 0;
+        int64_t upd_m2v = 0, upd_m2f = 0, upd_marg = 0;
+        uint64_t params_version = ~0ull;
+    } chain_plan;
+    uint64_t rules_version = 0;  // bumped by upload_rules
+
+    bool build_chain_plan() {
+        ChainPlan& P = chain_plan;
+        P.tried = true;
+        P.ok = false;
+        if (family != CXB_FAMILY_GAUSS_CANON || dim != 2 || has_var_family || !g.links.empty()) return false;
+        if ((int64_t)g.n_sig() != g.n_var + 2 * g.n_conn) return false;  // free signals: not the plain BP wiring
+        auto rule_kind = [&](int64_t f) {
+            auto it = rules.find(g.ftype[f]);
+            return it == rules.end() ? (int)CXB_RULE_NONE : it->second.kind;
+        };
+        auto deg = [&](int64_t id) { return g.adj_off[id + 1] - g.adj_off[id]; };
+        const uint32_t NONE = 0xFFFFFFFFu;
+        // classify: y (degree 1, on a GAUSS_OBS factor), x (one GAUSS_OBS factor + at most two GAUSS_RW factors)
+        std::vector<int64_t> lik_of(g.n_ids, -1), y_of(g.n_ids, -1), tr_a(g.n_ids, -1), tr_b(g.n_ids, -1);
+        for (int64_t f : g.factors) {
+            if (deg(f) != 2) return false;
+            const int64_t u = g.adj_nbr[g.adj_off[f]], w = g.adj_nbr[g.adj_off[f] + 1];
+            const int kind = rule_kind(f);
+            if (kind == CXB_RULE_GAUSS_OBS) {
+                const bool u_is_y = deg(u) == 1, w_is_y = deg(w) == 1;
+                if (u_is_y == w_is_y) return false;
+                const int64_t x = u_is_y ? w : u, y = u_is_y ? u : w;
+                if (lik_of[x] >= 0) return false;
+                lik_of[x] = f;
+                y_of[x] = y;
+            } else if (kind == CXB_RULE_GAUSS_RW) {
+                for (int64_t x : {u, w}) {
+                    if (tr_a[x] < 0) tr_a[x] = f;
+                    else if (tr_b[x] < 0) tr_b[x] = f;
+                    else return false;
+                }
+            } else {
+                return false;
+            }
+        }
+        std::vector<int64_t> xs;
+        for (int64_t v : g.variables) {
+            if (lik_of[v] >= 0) {
+                if (deg(v) != 1 + (tr_a[v] >= 0) + (tr_b[v] >= 0)) return false;
+                xs.push_back(v);
+            } else if (deg(v) != 1 || tr_a[v] >= 0) {
+                return false;  // neither a state nor an observation variable
+            }
+        }
+        if (xs.empty()) return false;
+        // walk the paths from their ends; the end whose transition factor has the smaller id comes first
+        auto other = [&](int64_t f, int64_t x) {
+            const int64_t u = g.adj_nbr[g.adj_off[f]], w = g.adj_nbr[g.adj_off[f] + 1];
+            return u == x ? w : u;
+        };
+        std::vector<uint8_t> seen(g.n_ids, 0);
+        std::vector<std::vector<int64_t>> chains;
+        std::vector<int64_t> ends;
+        for (int64_t x : xs)
+            if (tr_b[x] < 0) ends.push_back(x);
+        std::sort(ends.begin(), ends.end(), [&](int64_t p, int64_t q) { return std::make_pair(tr_a[p], p) < std::make_pair(tr_a[q], q); });
+        for (int64_t e0 : ends) {
+            if (seen[e0]) continue;
+            std::vector<int64_t> path;
+            int64_t x = e0, via = -1;
+            while (true) {
+                seen[x] = 1;
+                path.push_back(x);
+                const int64_t nf = tr_a[x] != via && tr_a[x] >= 0 ? tr_a[x] : (tr_b[x] != via && tr_b[x] >= 0 ? tr_b[x] : -1);
+                if (nf < 0) break;
+                const int64_t nx = other(nf, x);
+                if (seen[nx]) return false;
+                via = nf;
+                x = nx;
+            }
+            chains.push_back(std::move(path));
+        }
+        size_t total = 0;
+        for (auto& c : chains) total += c.size();
+        if (total != xs.size()) return false;  // a cycle of transitions
+        bool same_len = true;
+        for (auto& c : chains) same_len = same_len && c.size() == chains[0].size();
+        const size_t B = chains.size();
+        P.n_chains = (uint32_t)B;
+        P.n_pos = total;
+        P.stride = same_len ? (uint32_t)B : 1u;
+        std::vector<uint32_t> base(B), len(B), iy(total), io(total), ip(total, NONE), im(total, NONE), ib(total, NONE), ik(total, NONE), ig(total);
+        P.pos_lik.assign(total, -1);
+        P.pos_tr.assign(total, -1);
+        size_t off = 0;
+        P.upd_m2v = P.upd_m2f = P.upd_marg = 0;
+        auto deps_are = [&](uint32_t s2, std::initializer_list<uint32_t> want) {
+            size_t n = 0;
+            for (uint32_t w : want) n += w != NONE;
+            if (csr.dep_off[s2 + 1] - csr.dep_off[s2] != n) return false;
+            size_t k = csr.dep_off[s2];
+            for (uint32_t w : want)
+                if (w != NONE && csr.dep_ids[k++] != w) return false;
+            return true;
+        };
+        for (size_t b = 0; b < B; ++b) {
+            const auto& c = chains[b];
+            const size_t Tn = c.size();
+            base[b] = same_len ? (uint32_t)b : (uint32_t)off;
+            len[b] = (uint32_t)Tn;
+            auto pos = [&](size_t t) { return same_len ? t * B + b : off + t; };
+            for (size_t t = 0; t < Tn; ++t) {
+                const int64_t x = c[t], lik = lik_of[x];
+                const int64_t trn = t + 1 < Tn ? (other(tr_a[x], x) == c[t + 1] ? tr_a[x] : tr_b[x]) : -1;
+                const int64_t trp = t > 0 ? (other(tr_a[x], x) == c[t - 1] ? tr_a[x] : tr_b[x]) : -1;
+                const size_t p = pos(t);
+                iy[p] = (uint32_t)g.m2f_of_conn(g.conn_of(y_of[x], lik));
+                io[p] = (uint32_t)g.m2v_of_conn(g.conn_of(x, lik));
+                ig[p] = (uint32_t)g.marg_of[x];
+                if (trp >= 0) {
+                    ip[p] = (uint32_t)g.m2v_of_conn(g.conn_of(x, trp));
+                    ik[p] = (uint32_t)g.m2f_of_conn(g.conn_of(x, trp));
+                }
+                if (trn >= 0) {
+                    ib[p] = (uint32_t)g.m2v_of_conn(g.conn_of(x, trn));
+                    im[p] = (uint32_t)g.m2f_of_conn(g.conn_of(x, trn));
+                }
+                P.pos_lik[p] = lik;
+                P.pos_tr[p] = trn;
+            }
+            // the wiring must be exactly the one the kernel's arithmetic stands for (dependency ORDER included)
+            for (size_t t = 0; t < Tn; ++t) {
+                const size_t p = pos(t);
+                if (!deps_are(io[p], {iy[p]})) return false;
+                if (t > 0 && !deps_are(ip[p], {im[pos(t - 1)]})) return false;
+                if (t + 1 < Tn && !deps_are(ib[p], {ik[pos(t + 1)]})) return false;
+                if (im[p] != NONE && !deps_are(im[p], {io[p], ip[p]})) return false;
+                if (ik[p] != NONE && !deps_are(ik[p], {io[p], ib[p]})) return false;
+                if (!deps_are(ig[p], {io[p], ip[p], ib[p]})) return false;
+                if (csr.dep_off[iy[p] + 1] != csr.dep_off[iy[p]]) return false;  // the observation is an input
+            }
+            P.upd_m2v += (int64_t)(3 * Tn - 2);
+            P.upd_m2f += (int64_t)(2 * Tn - 2);
+            P.upd_marg += (int64_t)Tn;
+            off += Tn;
+        }
+        auto upl = [&](DBuf<uint32_t>& d, const std::vector<uint32_t>& v) { return up(d, v.data(), v.size()) == CXB_OK; };
+        if (!(upl(P.i_y, iy) && upl(P.i_obs, io) && upl(P.i_pred, ip) && upl(P.i_fwd, im) && upl(P.i_bwd, ib) && upl(P.i_back, ik) && upl(P.i_marg, ig) &&
+              upl(P.base, base) && upl(P.len, len)))
+            return false;
+        if (P.par_r.reserve(total * esz()) != cudaSuccess || P.par_q.reserve(total * esz()) != cudaSuccess) return false;
+        if (cudaStreamSynchronize(stream) != cudaSuccess) return false;
+        P.xs_sorted = xs;
+        std::sort(P.xs_sorted.begin(), P.xs_sorted.end());
+        P.params_version = ~0ull;
+        P.ok = true;
+        return true;
+    }
+    int recognise_plan(const Memo& m) {
+        if (getenv("CXB_PLAN") && !atoi(getenv("CXB_PLAN"))) return 0;
+        if (!chain_plan.tried) build_chain_plan();
+        const ChainPlan& P = chain_plan;
+        if (!P.ok) return 0;
+        std::vector<int64_t> ids(m.req_ids);
+        std::sort(ids.begin(), ids.end());
+        if (ids != P.xs_sorted) return 0;
+        // the recorded run must have executed exactly the signals the kernel writes
+        if (m.stats.updates_by_kind[CXB_KIND_M2V] != P.upd_m2v || m.stats.updates_by_kind[CXB_KIND_M2F] != P.upd_m2f ||
+            m.stats.updates_by_kind[CXB_KIND_MARGINAL] != P.upd_marg || m.stats.updates != P.upd_m2v + P.upd_m2f + P.upd_marg)
+            return 0;
+        return 1;
+    }
+    int32_t run_plan(const Memo&) {
+        ChainPlan& P = chain_plan;
+        if (P.params_version != rules_version) {  // noise variances: per-factor parameter, else the rule's default
+            std::vector<unsigned char> r(P.n_pos * esz()), q(P.n_pos * esz());
+            auto param = [&](int64_t f) {
+                if (f < 0) return 0.0;
+                const double v = f < (int64_t)fparam.size() ? fparam[f] : NAN;
+                if (v == v) return v;
+                auto it = rules.find(g.ftype[f]);
+                return (it != rules.end() && !it->second.params.empty()) ? it->second.params[0] : 1.0;
+            };
+            for (size_t p = 0; p < P.n_pos; ++p) {
+                const double rv = param(P.pos_lik[p]), qv = param(P.pos_tr[p]);
+                if (dtype == CXB_F32) {
+                    ((float*)r.data())[p] = (float)rv;
+                    ((float*)q.data())[p] = (float)qv;
+                } else {
+                    ((double*)r.data())[p] = rv;
+                    ((double*)q.data())[p] = qv;
+                }
+            }
+            CXB_CUDA(cudaMemcpyAsync(P.par_r.p, r.data(), r.size(), cudaMemcpyHostToDevice, stream));
+            CXB_CUDA(cudaMemcpyAsync(P.par_q.p, q.data(), q.size(), cudaMemcpyHostToDevice, stream));
+            CXB_CUDA(cudaStreamSynchronize(stream));
+            P.params_version = rules_version;
+        }
+        ChainPlanArgs a{};
+        a.i_y = P.i_y.p;
+        a.i_obs = P.i_obs.p;
+        a.i_pred = P.i_pred.p;
+        a.i_fwd = P.i_fwd.p;
+        a.i_bwd = P.i_bwd.p;
+        a.i_back = P.i_back.p;
+        a.i_marg = P.i_marg.p;
+        a.par_r = P.par_r.p;
+        a.par_q = P.par_q.p;
+        a.base = P.base.p;
+        a.len = P.len.p;
+        a.stride = P.stride;
+        a.n_chains = P.n_chains;
+        if (dtype == CXB_F32)
+            CXB_LAUNCH((k_chain_plan<float, 8>), cdiv(P.n_chains, 64), 64, 0, stream, (float*)d_val.p, a);
+        else
+            CXB_LAUNCH((k_chain_plan<double, 8>), cdiv(P.n_chains, 64), 64, 0, stream, (double*)d_val.p, a);
+        return CXB_OK;
+    }
+
+    // Same request and bit-identical flag state as a recorded run? Then replay it.
+    int32_t try_replay(int64_t n, const int64_t* ids, bool& hit) {
+        hit = false;
+        std::vector<Memo*> cand;
+        for (auto& m : memos)
+            if ((int64_t)m->req_ids.size() == n && !std::memcmp(m->req_ids.data(), ids, (size_t)n * 8)) cand.push_back(m.get());
+        if (cand.empty()) return CXB_OK;
+        const size_t N = n_uploaded, NC = csr.nib.size();
+        CXB_CUDA(d_memo_flags.reserve(MAX_MEMOS));
+        CXB_CUDA(h_memo_flags.reserve(MAX_MEMOS));
+        CXB_CUDA(cudaMemsetAsync(d_memo_flags.p, 0, MAX_MEMOS * sizeof(int), stream));
+        const unsigned grid = std::max(1u, std::min(cdiv(std::max(N, NC), 256), 148u * 8u));
+        for (size_t c = 0; c < cand.size(); ++c)
+            CXB_LAUNCH(k_state_differs, grid, 256, 0, stream, d_props.p, cand[c]->pre_props.p, N, d_nib.p, cand[c]->pre_nib.p, NC, d_memo_flags.p + c);
+        CXB_CUDA(cudaMemcpyAsync(h_memo_flags.p, d_memo_flags.p, MAX_MEMOS * sizeof(int), cudaMemcpyDeviceToHost, stream));
+        CXB_CUDA(cudaStreamSynchronize(stream));
+        Memo* m = nullptr;
+        for (size_t c = 0; c < cand.size() && !m; ++c)
+            if (!h_memo_flags.p[c]) m = cand[c];
+        if (!m) return CXB_OK;
+        int32_t st;
+        if (m->plan > 0) {
+            if ((st = run_plan(*m))) return st;
+            last_ran = CXB_RAN_PLAN;
+        } else {
+            if ((st = replay_levels(*m))) return st;
+            last_ran = CXB_RAN_REPLAY;
+        }
+        if (N) CXB_CUDA(cudaMemcpyAsync(d_props.p, m->post_props.p, N, cudaMemcpyDeviceToDevice, stream));
+        if (NC) CXB_CUDA(cudaMemcpyAsync(d_nib.p, m->post_nib.p, NC * sizeof(uint64_t), cudaMemcpyDeviceToDevice, stream));
+        if ((st = check_flags())) return st;  // a rule rejected its arguments (the only error a replay can meet)
+        stats = m->stats;
+        m->last_use = ++memo_clock;
+        hit = true;
+        return CXB_OK;
+    }
+    int32_t replay_levels(const Memo& m) {
+        int32_t st;
+        if (resident_ok()) {
+            if ((st = upload_key_tables())) return st;
+            ReplayArgs a{};
+            a.list = m.lists.p;
+            a.desc = m.desc.p;
+            a.n_desc = m.n_desc;
+            a.n_keys = n_keys();
+            a.family = family;
+            a.key_rule = d_key_rule.p;
+            a.key_param = d_key_param.p;
+            a.fparam = d_fparam.p;
+            a.tables = d_tables.p;
+            a.key_table = d_key_table.p;
+            a.key_nsym = d_key_nsym.p;
+            cur_use_keys = true;
+            if (dtype == CXB_F32)
+                CXB_LAUNCH(k_replay_resident<float>, 1, 1024, 0, stream, view(), (float*)d_val.p, a);
+            else
+                CXB_LAUNCH(k_replay_resident<double>, 1, 1024, 0, stream, view(), (double*)d_val.p, a);
+            return CXB_OK;
+        }
+        // large graphs: one batched rule kernel per (level, rule key), back to back on the stream
+        const int nk = n_keys();
+        size_t d = 0;
+        const size_t nd = m.h_desc.size() / 4;
+        while (d < nd) {
+            const uint32_t level = m.h_desc[4 * d];
+            for (int k = 0; k < 2 * nk; ++k) h_counts.p[k] = 0;
+            uint32_t total = 0;
+            for (; d < nd && m.h_desc[4 * d] == level; ++d) {
+                const uint32_t key = m.h_desc[4 * d + 1];
+                h_counts.p[key] = m.h_desc[4 * d + 2];
+                h_counts.p[nk + key] = m.h_desc[4 * d + 3];
+                total += m.h_desc[4 * d + 2];
+            }
+            if ((st = launch_rules(total, m.lists.p))) return st;
+        }
+        return CXB_OK;
     }
 
     // Can the sequential executor (and the resident level loop) evaluate this model's rules? (small fixed-size values,
@@ -2084,8 +2709,22 @@ struct DeviceEngine {
             stats.kernel_launches = (int64_t)(g_kernel_launches - launches0);
             return st;
         }
+        const bool memo_ok = memo_on && !trace_on && n > 0 && ids;
+        if (memo_ok) {
+            bool hit = false;
+            if ((st = try_replay(n, ids, hit))) return st;
+            if (hit) {
+                stats.kernel_launches = (int64_t)(g_kernel_launches - launches0);
+                return CXB_OK;
+            }
+        }
         if ((st = take_snapshot())) return st;  // a refused request is rolled back
+        if (memo_ok && snap_valid) begin_recording();
         st = update_level(n, ids, launches0);
+        if (rec) {
+            if (st == CXB_OK) st = commit_recording(n, ids);
+            rec.reset();
+        }
         if (st == CXB_ERR_OUT_OF_CONTRACT && snap_valid) {
             const std::string why = err;
             int32_t st2 = restore_snapshot();

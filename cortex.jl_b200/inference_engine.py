@@ -18,7 +18,7 @@ from . import _capi as capi
 from .inference_signal import (IndividualMarginal, JointMarginal, MessageToFactor, MessageToVariable, NoRuleError,
                                ProductOfMessages, Signal, SignalStore, UndefValue, get_value, get_values, get_variant,
                                is_computed, _ids)
-from .model_engine import (Connection, Factor, Variable, backend_get_connected_factor_ids,
+from .model_engine import (B200ModelEngine, Connection, Factor, Variable, backend_get_connected_factor_ids,
                            backend_get_connected_variable_ids, backend_get_connection, backend_get_factor,
                            backend_get_factor_ids, backend_get_variable, backend_get_variable_ids,
                            throw_if_engine_unsupported)
@@ -85,6 +85,22 @@ class RuleProcessor(AbstractInferenceRequestProcessor):
         self.rules = dict(rules)
         self.family = family
         self.value_dim = value_dim
+
+
+class _LazyNeighbours:
+    """variable id -> tuple of connected factor ids, computed on demand (ProductOfMessages variants of a lazy model engine)."""
+
+    def __init__(self, model_engine):
+        self.me = model_engine
+
+    def get(self, v, default=()):
+        try:
+            return tuple(self.me.get_connected_factor_ids(v))
+        except KeyError:
+            return default
+
+    def __setitem__(self, k, v):
+        pass
 
 
 @dataclass
@@ -167,8 +183,26 @@ class InferenceEngine:
                     self.warnings.append(InferenceEngineWarning("Variable has no connected factors", int(v)))
 
     # -- graph ingestion through the 7 generics (src/model_engine.jl:329-391) ---------------------------
+    def _ingest_lazy(self):
+        """B200ModelEngine: the graph arrives as flat arrays; no Variable / Factor / Connection object is created here - the
+        model engine materialises views on demand (mirror of julia/CortexB200.jl)."""
+        me, st = self.model_engine, self.store
+        self._type_of_form: Dict[Any, int] = {}
+        ftype = np.zeros(max(me.n_ids, 1), dtype=np.int32)
+        forms = me.functional_forms
+        for f in np.flatnonzero(me.is_factor):
+            ftype[f] = self._type_of_form.setdefault(forms[int(f)], len(self._type_of_form))
+        st.check(self.api.graph_build(st.h, me.n_ids, me.is_factor.ctypes.data_as(capi.u8p), ftype.ctypes.data_as(capi.i32p),
+                                      len(me.edge_variable), me.edge_variable.ctypes.data_as(capi.i64p),
+                                      me.edge_factor.ctypes.data_as(capi.i64p)))
+        me._engine = self
+        st._neighbours = _LazyNeighbours(me)
+
     def _ingest(self):
         me = self.model_engine
+        self._links: Dict[int, List[Signal]] = {}
+        if isinstance(me, B200ModelEngine):
+            return self._ingest_lazy()
         vids = [int(v) for v in backend_get_variable_ids(me)]
         fids = [int(f) for f in backend_get_factor_ids(me)]
         n_ids = (max(vids + fids) + 1) if (vids or fids) else 0
@@ -310,6 +344,7 @@ def link_signal_to_variable(variable: Variable, signal: Signal) -> None:
     eng = getattr(variable, "_engine", None)
     if eng is None:
         raise RuntimeError("link_signal_to_variable!: the variable is not bound to an InferenceEngine yet")
+    eng._links.setdefault(variable._id, []).append(signal)  # views of a lazy model engine are rebuilt from this
     eng.store.check(eng.api.link_signal(eng.store.h, variable._id, signal.sid))
 
 

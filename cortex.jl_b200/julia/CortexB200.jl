@@ -1,18 +1,31 @@
-# CortexB200.jl — the `ccall` glue a Cortex.jl maintainer adds to put the B200 engine behind the existing API.
+# CortexB200.jl — puts the B200 engine behind Cortex.jl's own API (SURVEY §8b / §8f.3).
 #
-# NOT executed in this repository's CI: the build image has no `julia` (see DESIGN.md §1). It is a 1:1, mechanically
-# checkable mirror of include/cortex_b200.h; the same ABI is exercised by the Python ctypes frontend in the tests.
-#
-# Usage (on a machine with Julia, Cortex.jl, BipartiteFactorGraphs.jl and libcortex_b200.so):
 #     using Cortex, BipartiteFactorGraphs, CortexB200
-#     engine = CortexB200.B200InferenceEngine(graph; rules = Dict(:likelihood => (CortexB200.RULE_GAUSS_OBS, [1.0]),
-#                                                               :transition => (CortexB200.RULE_GAUSS_RW,  [1.0])),
-#                                             family = CortexB200.FAMILY_GAUSS_CANON, value_dim = 2)
-#     CortexB200.set_value!(engine, Cortex.get_connection_message_to_factor(...)-equivalent signal id, value)
-#     Cortex.update_marginals!(engine, variable_ids)          # dispatches to cxb_update_marginals
+#     model  = CortexB200.B200ModelEngine(graph;                       # any supported model engine, walked ONCE
+#                  rules = Dict(:likelihood => (CortexB200.RULE_GAUSS_OBS, [1.0]), :transition => (CortexB200.RULE_GAUSS_RW, [1.0])),
+#                  family = CortexB200.FAMILY_GAUSS_CANON, value_dim = 2)
+#     engine = Cortex.InferenceEngine(model_engine = model, prepare_signals_metadata = false, resolve_dependencies = false)
+#     CortexB200.set_message_to_factor!(model, y[t], likelihood[t], [obs, 0.0])        # set_value!(m2f(y_t, lik_t), ...)
+#     Cortex.update_marginals!(engine, x)                                              # -> cxb_update_marginals
+#     Cortex.get_value(Cortex.get_variable_marginal(Cortex.get_variable(engine, x[1])))  # fetched from the device
+#
+# `B200ModelEngine` is a model-engine BACKEND in the reference's sense (src/model_engine.jl:269-391): it implements the trait
+# and the seven generics, LAZILY — the device owns every signal; `get_variable` / `get_connection` materialise a `Variable` /
+# `Connection` VIEW whose signals are fresh host `InferenceSignal`s carrying the device's current value and variant (nothing is
+# allocated per signal up front: a 10^8-signal graph stays a few flat arrays). Signal variants and dependencies are made by
+# the library (`cxb_graph_build`, `cxb_resolve_dependencies`), hence `prepare_signals_metadata = false, resolve_dependencies =
+# false` in the `InferenceEngine` constructor (src/inference_engine.jl:60-89). The hot path is a MORE SPECIFIC method
+# `Cortex.update_marginals!(::InferenceEngine{<:B200ModelEngine}, ids)` (the reference's are at src/inference_engine.jl:555,
+# 559), so every other `InferenceEngine` keeps running the reference loop.
+#
+# NOT executed in this repository: the build image and the GPU boxes have no `julia` (DESIGN.md §1). The same ABI, call for
+# call, is exercised by the Python ctypes frontend (`cortex.jl_b200/model_engine.py::B200ModelEngine` mirrors this file and is
+# tested on the GPU: tests/test_b200_model_engine.py).
 module CortexB200
 
 using Cortex
+import Cortex: is_engine_supported, get_variable, get_factor, get_variable_ids, get_factor_ids, get_connection,
+               get_connected_variable_ids, get_connected_factor_ids, update_marginals!, request_inference_for
 
 const LIB = get(ENV, "CORTEX_B200_LIB", "libcortex_b200.so")
 
@@ -26,6 +39,8 @@ const RULE_NONE, RULE_GAUSS_OBS, RULE_GAUSS_RW, RULE_CAT_TABLE, RULE_POTTS, RULE
       RULE_GAUSS_MV_OBS, RULE_GAUSS_MV_RW, RULE_BETA_BERNOULLI, RULE_SCALE2, RULE_NORMAL_MEAN_FIELD,
       RULE_NORMAL_STRUCTURED = 0:11
 const RESOLVER_NONE, RESOLVER_DEFAULT_BP, RESOLVER_MEAN_FIELD = 0:2
+const SCHEDULE_AUTO, SCHEDULE_LEVEL, SCHEDULE_SEQUENTIAL, RAN_REPLAY, RAN_PLAN = 0:4
+const DEP_INTERMEDIATE, DEP_WEAK, DEP_NO_LISTEN, DEP_NO_CHECK_COMPUTED = 1, 2, 16, 32
 
 struct UpdateStats
     levels::Int64
@@ -36,282 +51,264 @@ struct UpdateStats
     kernel_launches::Int64
 end
 
+"The level-synchronous schedule would differ from the reference's order (only with `schedule = SCHEDULE_LEVEL`)."
+struct OutOfContractError <: Exception
+    msg::String
+end
+
 # ---- error mapping (SURVEY §8b): status -> the exception the reference throws on that path ------------------------
-function check(h::Ptr{Cvoid}, status::Int32)
+function check(h::Ptr{Cvoid}, status::Integer)
     status == OK && return nothing
     msg = unsafe_string(ccall((:cxb_last_error, LIB), Cstring, (Ptr{Cvoid},), h))
     status == ERR_NOT_PENDING && throw(ArgumentError(msg))                      # src/signal.jl:399-405
     status == ERR_NO_RULE && error(msg)                                         # src/inference_engine.jl:358-360
-    status == ERR_UNSUPPORTED_ENGINE && throw(Cortex.UnsupportedModelEngineError(nothing, nothing))
+    status == ERR_OUT_OF_CONTRACT && throw(OutOfContractError(msg))
+    status == ERR_BAD_ARG && throw(ArgumentError(msg))
     error("cortex_b200 status $status: $msg")
 end
 
 """
-    B200InferenceEngine(model_engine; rules, family, value_dim, dtype = F32, device = 0,
-                        dependency_resolver = RESOLVER_DEFAULT_BP)
+    B200ModelEngine(source; rules, family, value_dim, dtype = F32, device = 0, dependency_resolver = RESOLVER_DEFAULT_BP,
+                    decode = identity, encode = identity)
 
-Walks the 7 backend generics of the model engine once (src/model_engine.jl:329-391) and hands flat arrays to
-`cxb_graph_build`; registers one rule kernel per `Factor.functional_form`; resolves dependencies on the host side of the
-library exactly as `DefaultDependencyResolver` does (src/dependencies.jl).
+A Cortex model-engine backend whose signals live on a B200. `source` is any supported model engine (e.g. a
+`BipartiteFactorGraph`): its seven generics are walked once (src/model_engine.jl:329-391) and the graph handed to the library
+as flat arrays; or use `B200ModelEngine(n_ids, is_factor, functional_forms, edge_variable, edge_factor; ...)` for graphs that
+never exist as host objects. `rules` maps `Factor.functional_form` to a registered rule kernel `(RULE_*, params)` — the
+counterpart of methods of `compute_message_to_variable!` dispatching on the functional form
+(test/inference_engine_tests.jl:256-259). `decode` / `encode` convert between the `value_dim` numbers of a device value and
+the Julia value the user wants to see (e.g. `v -> NormalCanonical(v[1], v[2])`).
 """
-mutable struct B200InferenceEngine{M}
-    model_engine::M
+mutable struct B200ModelEngine
     handle::Ptr{Cvoid}
-    id_offset::Int              # Julia ids are 1-based, the library's 0-based
-    type_of_form::Dict{Any, Int32}
+    variable_ids::Vector{Int}
+    factor_ids::Vector{Int}
+    forms::Dict{Int, Any}                  # factor id -> Factor.functional_form
+    names::Dict{Int, Tuple{Symbol, Any}}   # variable id -> (name, index), kept from the source engine
+    labels::Dict{Tuple{Int, Int}, Tuple{Symbol, Int}}  # (variable, factor) -> connection (label, index)
+    factors_of::Dict{Int, Vector{Int}}     # ascending ids (the order contract of ext/BipartiteFactorGraphsExt/...:26-48)
+    variables_of::Dict{Int, Vector{Int}}
+    value_dim::Int
+    dtype::Int
+    decode::Any
+    encode::Any
+    trace::Bool
 end
 
-function B200InferenceEngine(model_engine::M; rules::Dict, family::Integer, value_dim::Integer, dtype::Integer = F32,
-                             device::Integer = 0, dependency_resolver::Integer = RESOLVER_DEFAULT_BP) where {M}
-    Cortex.throw_if_engine_unsupported(model_engine)
+is_engine_supported(::B200ModelEngine) = Cortex.SupportedModelEngine()   # src/model_engine.jl:269-310
+
+function B200ModelEngine(source; rules::AbstractDict, family::Integer, value_dim::Integer, dtype::Integer = F32, device::Integer = 0,
+                         dependency_resolver::Integer = RESOLVER_DEFAULT_BP, decode = identity, encode = identity)
+    Cortex.throw_if_engine_unsupported(source)
+    vids = sort!(collect(Int, Cortex.get_variable_ids(source)))
+    fids = sort!(collect(Int, Cortex.get_factor_ids(source)))
+    forms = Dict{Int, Any}(f => Cortex.get_factor_functional_form(Cortex.get_factor(source, f)) for f in fids)
+    names = Dict{Int, Tuple{Symbol, Any}}()
+    for v in vids
+        var = Cortex.get_variable(source, v)
+        names[v] = (Cortex.get_variable_name(var), Cortex.get_variable_index(var))
+    end
+    ev = Int[]; ef = Int[]
+    labels = Dict{Tuple{Int, Int}, Tuple{Symbol, Int}}()
+    for f in fids, v in sort!(collect(Int, Cortex.get_connected_variable_ids(source, f)))
+        push!(ev, v); push!(ef, f)
+        c = Cortex.get_connection(source, v, f)
+        labels[(v, f)] = (Cortex.get_connection_label(c), Cortex.get_connection_index(c))
+    end
+    n_ids = maximum(vcat(vids, fids); init = 0)
+    is_factor = zeros(UInt8, n_ids)
+    is_factor[fids] .= 1
+    return B200ModelEngine(n_ids, is_factor, forms, ev, ef; rules, family, value_dim, dtype, device, dependency_resolver, decode, encode,
+                           names, labels)
+end
+
+function B200ModelEngine(n_ids::Integer, is_factor::Vector{UInt8}, forms::AbstractDict, edge_variable::Vector{Int}, edge_factor::Vector{Int};
+                         rules::AbstractDict, family::Integer, value_dim::Integer, dtype::Integer = F32, device::Integer = 0,
+                         dependency_resolver::Integer = RESOLVER_DEFAULT_BP, decode = identity, encode = identity,
+                         names = Dict{Int, Tuple{Symbol, Any}}(), labels = Dict{Tuple{Int, Int}, Tuple{Symbol, Int}}())
     href = Ref{Ptr{Cvoid}}(C_NULL)
     st = ccall((:cxb_create, LIB), Int32, (Int32, Int32, Int32, Int32, Ref{Ptr{Cvoid}}), device, dtype, value_dim, family, href)
     st == OK || error("cxb_create failed with status $st (a CUDA device is required; there is no CPU fallback)")
     h = href[]
-    vids = collect(Int, Cortex.get_variable_ids(model_engine))
-    fids = collect(Int, Cortex.get_factor_ids(model_engine))
-    n_ids = maximum(vcat(vids, fids); init = 0)
-    is_factor = zeros(UInt8, n_ids); ftype = zeros(Int32, n_ids)
     type_of_form = Dict{Any, Int32}()
-    for f in fids
-        is_factor[f] = 1
-        form = Cortex.get_factor_functional_form(Cortex.get_factor(model_engine, f))
-        ftype[f] = get!(type_of_form, form, Int32(length(type_of_form)))
+    ftype = zeros(Int32, n_ids)
+    for f in 1:n_ids
+        is_factor[f] == 1 || continue
+        ftype[f] = get!(type_of_form, forms[f], Int32(length(type_of_form)))
     end
-    ev = Int64[]; ef = Int64[]
-    for f in fids, v in Cortex.get_connected_variable_ids(model_engine, f)
-        push!(ev, v - 1); push!(ef, f - 1)
-    end
-    check(h, ccall((:cxb_graph_build, LIB), Int32,
-                   (Ptr{Cvoid}, Int64, Ptr{UInt8}, Ptr{Int32}, Int64, Ptr{Int64}, Ptr{Int64}),
-                   h, n_ids, is_factor, ftype, length(ev), ev, ef))
+    ev0 = Int64.(edge_variable .- 1); ef0 = Int64.(edge_factor .- 1)          # Julia ids are 1-based, the library's 0-based
+    check(h, ccall((:cxb_graph_build, LIB), Int32, (Ptr{Cvoid}, Int64, Ptr{UInt8}, Ptr{Int32}, Int64, Ptr{Int64}, Ptr{Int64}),
+                   h, n_ids, is_factor, ftype, length(ev0), ev0, ef0))
     for (form, (kind, params)) in rules
         haskey(type_of_form, form) || continue
-        p = convert(Vector{Float64}, params)
-        check(h, ccall((:cxb_register_rule, LIB), Int32, (Ptr{Cvoid}, Int32, Int32, Ptr{Float64}, Int64),
-                       h, type_of_form[form], kind, p, length(p)))
+        p = convert(Vector{Float64}, collect(params))
+        check(h, ccall((:cxb_register_rule, LIB), Int32, (Ptr{Cvoid}, Int32, Int32, Ptr{Float64}, Int64), h, type_of_form[form], kind, p, length(p)))
     end
-    check(h, ccall((:cxb_resolve_dependencies, LIB), Int32, (Ptr{Cvoid}, Int32), h, dependency_resolver))
-    engine = B200InferenceEngine{M}(model_engine, h, 1, type_of_form)
-    finalizer(e -> ccall((:cxb_destroy, LIB), Cvoid, (Ptr{Cvoid},), e.handle), engine)
+    check(h, ccall((:cxb_resolve_dependencies, LIB), Int32, (Ptr{Cvoid}, Int32), h, dependency_resolver))   # src/dependencies.jl:5-173
+    factors_of = Dict{Int, Vector{Int}}(); variables_of = Dict{Int, Vector{Int}}()
+    for (v, f) in zip(edge_variable, edge_factor)
+        push!(get!(factors_of, v, Int[]), f); push!(get!(variables_of, f, Int[]), v)
+    end
+    foreach(sort!, values(factors_of)); foreach(sort!, values(variables_of))
+    vids = [i for i in 1:n_ids if is_factor[i] == 0]; fids = [i for i in 1:n_ids if is_factor[i] == 1]
+    m = B200ModelEngine(h, vids, fids, Dict{Int, Any}(forms), names, labels, factors_of, variables_of, value_dim, dtype, decode, encode, false)
+    finalizer(e -> ccall((:cxb_destroy, LIB), Cvoid, (Ptr{Cvoid},), e.handle), m)
+    return m
+end
+
+# ---- signals: dense ids on the device, views on the host ---------------------------------------------------------------
+signal_id(m::B200ModelEngine, kind::Integer, v::Integer, f::Integer = 0) =
+    ccall((:cxb_signal_id, LIB), Int64, (Ptr{Cvoid}, Int32, Int64, Int64), m.handle, kind, v - 1, f - 1)
+
+function device_is_computed(m::B200ModelEngine, sid::Int64)
+    r = ccall((:cxb_is_computed, LIB), Int32, (Ptr{Cvoid}, Int64), m.handle, sid)
+    r < 0 && throw(ArgumentError("bad signal id"))
+    return r == 1
+end
+function device_value(m::B200ModelEngine, sid::Int64)
+    out = zeros(Float64, m.value_dim); ids = [sid]
+    check(m.handle, ccall((:cxb_get_values, LIB), Int32, (Ptr{Cvoid}, Int64, Ptr{Int64}, Ptr{Float64}, Int64), m.handle, 1, ids, out, m.value_dim))
+    return m.decode(out)
+end
+"A host `InferenceSignal` showing the device signal `sid`: its current value (`UndefValue()` if never computed) and variant."
+function signal_view(m::B200ModelEngine, sid::Int64, variant)
+    value = device_is_computed(m, sid) ? device_value(m, sid) : Cortex.UndefValue()
+    return Cortex.Signal(Any, Cortex.InferenceSignalVariant, value, variant)      # src/signal.jl:94-104
+end
+function linked_signal_views(m::B200ModelEngine, v::Int)
+    # linked signals are m2f messages (protocol B) or user signals; their ids come back from the library
+    return Cortex.InferenceSignal[]   # the device keeps the links (cxb_link_signal); views are made on request with signal_view
+end
+
+# ---- the seven backend generics, src/model_engine.jl:329-391 ------------------------------------------------------------
+get_variable_ids(m::B200ModelEngine) = m.variable_ids
+get_factor_ids(m::B200ModelEngine) = m.factor_ids
+get_connected_variable_ids(m::B200ModelEngine, factor_id::Int) = get(m.variables_of, factor_id, Int[])
+get_connected_factor_ids(m::B200ModelEngine, variable_id::Int) = get(m.factors_of, variable_id, Int[])
+function get_variable(m::B200ModelEngine, variable_id::Int)::Cortex.Variable
+    sid = signal_id(m, KIND_MARGINAL, variable_id)
+    sid < 0 && throw(ArgumentError("not a variable id: $variable_id"))
+    name, index = get(m.names, variable_id, (:variable, variable_id))
+    marginal = signal_view(m, sid, Cortex.InferenceSignalVariants.IndividualMarginal(variable_id))
+    return Cortex.Variable(name = name, index = index, marginal = marginal, linked_signals = linked_signal_views(m, variable_id))
+end
+function get_factor(m::B200ModelEngine, factor_id::Int)::Cortex.Factor
+    haskey(m.forms, factor_id) || throw(ArgumentError("not a factor id: $factor_id"))
+    return Cortex.Factor(functional_form = m.forms[factor_id])
+end
+function get_connection(m::B200ModelEngine, variable_id::Int, factor_id::Int)::Cortex.Connection
+    s2v = signal_id(m, KIND_M2V, variable_id, factor_id); s2f = signal_id(m, KIND_M2F, variable_id, factor_id)
+    (s2v < 0 || s2f < 0) && throw(ArgumentError("no connection between variable $variable_id and factor $factor_id"))
+    label, index = get(m.labels, (variable_id, factor_id), (:edge, 0))
+    return Cortex.Connection(label = label, index = index,
+        message_to_variable = signal_view(m, s2v, Cortex.InferenceSignalVariants.MessageToVariable(variable_id, factor_id)),
+        message_to_factor = signal_view(m, s2f, Cortex.InferenceSignalVariants.MessageToFactor(variable_id, factor_id)))
+end
+
+# ---- data in: set_value!(signal, v) of src/signal.jl:232-253 addressed by what the signal IS -------------------------------
+function set_device_values!(m::B200ModelEngine, sids::Vector{Int64}, values)
+    flat = zeros(Float64, m.value_dim, length(sids))
+    for (k, v) in enumerate(values)
+        e = m.encode(v); flat[1:length(e), k] .= e
+    end
+    check(m.handle, ccall((:cxb_set_values, LIB), Int32, (Ptr{Cvoid}, Int64, Ptr{Int64}, Ptr{Float64}, Int64), m.handle, length(sids), sids, flat, m.value_dim))
+end
+set_message_to_factor!(m::B200ModelEngine, v::Int, f::Int, value) = set_device_values!(m, [signal_id(m, KIND_M2F, v, f)], [value])
+set_message_to_variable!(m::B200ModelEngine, v::Int, f::Int, value) = set_device_values!(m, [signal_id(m, KIND_M2V, v, f)], [value])
+set_marginal!(m::B200ModelEngine, v::Int, value) = set_device_values!(m, [signal_id(m, KIND_MARGINAL, v)], [value])
+"Bulk form: one host->device copy and one notification kernel for a whole vector of (variable, factor) observations."
+set_messages_to_factor!(m::B200ModelEngine, vs, fs, values) =
+    set_device_values!(m, Int64[signal_id(m, KIND_M2F, v, f) for (v, f) in zip(vs, fs)], values)
+"link_signal_to_variable!(variable, m2f(variable, factor)), src/model_engine.jl:80-83 (protocol B of SURVEY Appendix B)."
+link_message_to_factor!(m::B200ModelEngine, v::Int, f::Int) =
+    check(m.handle, ccall((:cxb_link_signal, LIB), Int32, (Ptr{Cvoid}, Int64, Int64), m.handle, v - 1, signal_id(m, KIND_M2F, v, f)))
+set_schedule!(m::B200ModelEngine, schedule::Integer) = check(m.handle, ccall((:cxb_set_schedule, LIB), Int32, (Ptr{Cvoid}, Int32), m.handle, schedule))
+last_schedule(m::B200ModelEngine) = ccall((:cxb_last_schedule, LIB), Int32, (Ptr{Cvoid},), m.handle)
+
+# custom wiring for user resolvers (test/inference_engine_tests.jl:597-621, 811-907): signals are addressed by id
+create_signal!(m::B200ModelEngine) = ccall((:cxb_create_signal, LIB), Int64, (Ptr{Cvoid},), m.handle)
+function add_dependency!(m::B200ModelEngine, signal::Int64, dependency::Int64; weak = false, listen = true, check_computed = true, intermediate = false)
+    flags = (intermediate ? DEP_INTERMEDIATE : 0) | (weak ? DEP_WEAK : 0) | (listen ? 0 : DEP_NO_LISTEN) | (check_computed ? 0 : DEP_NO_CHECK_COMPUTED)
+    check(m.handle, ccall((:cxb_add_dependency, LIB), Int32, (Ptr{Cvoid}, Int64, Int64, Int32), m.handle, signal, dependency, flags))
+end
+
+# ---- warnings, src/inference_engine.jl:11-14 + src/dependencies.jl:40-43 ------------------------------------------------
+function collect_warnings!(engine::Cortex.InferenceEngine{<:B200ModelEngine})
+    m = Cortex.get_model_engine(engine)
+    n = ccall((:cxb_get_warnings, LIB), Int64, (Ptr{Cvoid}, Ptr{Int64}, Int64), m.handle, C_NULL, 0)
+    n <= 0 && return engine
+    buf = zeros(Int64, n)
+    ccall((:cxb_get_warnings, LIB), Int64, (Ptr{Cvoid}, Ptr{Int64}, Int64), m.handle, buf, n)
+    for v in buf
+        Cortex.add_warning!(engine, "Variable has no connected factors", Int(v) + 1)
+    end
     return engine
 end
 
-# ---- signal ids (get_variable_marginal / get_connection_message_to_* equivalents) ---------------------------------
-marginal_id(e::B200InferenceEngine, v::Int) =
-    ccall((:cxb_signal_id, LIB), Int64, (Ptr{Cvoid}, Int32, Int64, Int64), e.handle, KIND_MARGINAL, v - 1, -1)
-message_to_variable_id(e::B200InferenceEngine, v::Int, f::Int) =
-    ccall((:cxb_signal_id, LIB), Int64, (Ptr{Cvoid}, Int32, Int64, Int64), e.handle, KIND_M2V, v - 1, f - 1)
-message_to_factor_id(e::B200InferenceEngine, v::Int, f::Int) =
-    ccall((:cxb_signal_id, LIB), Int64, (Ptr{Cvoid}, Int32, Int64, Int64), e.handle, KIND_M2F, v - 1, f - 1)
-
-# ---- custom wiring: what a user-defined AbstractDependencyResolver calls (test/inference_engine_tests.jl:597-621, 811-907) ----
-const DEP_INTERMEDIATE, DEP_WEAK, DEP_NO_LISTEN, DEP_NO_CHECK_COMPUTED = 1, 2, 16, 32
-create_signal!(e::B200InferenceEngine) = ccall((:cxb_create_signal, LIB), Int64, (Ptr{Cvoid},), e.handle)
-function add_dependency!(e::B200InferenceEngine, signal::Int64, dependency::Int64; weak = false, listen = true,
-                         check_computed = true, intermediate = false)
-    flags = (intermediate ? DEP_INTERMEDIATE : 0) | (weak ? DEP_WEAK : 0) | (listen ? 0 : DEP_NO_LISTEN) |
-            (check_computed ? 0 : DEP_NO_CHECK_COMPUTED)
-    check(e.handle, ccall((:cxb_add_dependency, LIB), Int32, (Ptr{Cvoid}, Int64, Int64, Int32), e.handle, signal, dependency, flags))
-end
-# set_variant!(signal, JointMarginal(factor_id, variable_ids)): the rule registered for the factor computes the signal
-set_joint_marginal_variant!(e::B200InferenceEngine, signal::Int64, factor_id::Int) =
-    check(e.handle, ccall((:cxb_set_signal_variant, LIB), Int32, (Ptr{Cvoid}, Int64, Int32, Int64, Int64),
-                          e.handle, signal, KIND_JOINT, -1, factor_id - 1))
-# delegate one id to a built-in resolver (Cortex.resolve_variable_dependencies!(DefaultDependencyResolver(), engine, id))
-resolve_factor_dependencies!(e::B200InferenceEngine, resolver::Integer, factor_id::Int) =
-    check(e.handle, ccall((:cxb_resolve_factor_dependencies, LIB), Int32, (Ptr{Cvoid}, Int32, Int64), e.handle, resolver, factor_id - 1))
-resolve_variable_dependencies!(e::B200InferenceEngine, resolver::Integer, variable_id::Int) =
-    check(e.handle, ccall((:cxb_resolve_variable_dependencies, LIB), Int32, (Ptr{Cvoid}, Int32, Int64), e.handle, resolver, variable_id - 1))
-
-# value type of a variable's signals in a model that mixes types (VMP: NormalMeanPrecision / Gamma / observed Float64,
-# test/runtests.jl:52-99 — in Julia the type travels with the value, the device needs it declared once)
-function set_variable_families!(e::B200InferenceEngine, variable_ids::AbstractVector{<:Integer}, families::AbstractVector{<:Integer})
-    ids = Int64[v - 1 for v in variable_ids]; fam = convert(Vector{Int32}, families)
-    check(e.handle, ccall((:cxb_set_variable_families, LIB), Int32, (Ptr{Cvoid}, Int64, Ptr{Int64}, Ptr{Int32}),
-                          e.handle, length(ids), ids, fam))
+# ---- the hot path: more specific than src/inference_engine.jl:555 and :559 ------------------------------------------------
+update_marginals!(engine::Cortex.InferenceEngine{<:B200ModelEngine}, variable_id::Integer) = update_marginals!(engine, (variable_id,))
+function update_marginals!(engine::Cortex.InferenceEngine{<:B200ModelEngine}, variable_ids::Union{AbstractVector, Tuple})
+    m = Cortex.get_model_engine(engine)
+    ids = Int64[Int64(v) - 1 for v in variable_ids]
+    tracer = Cortex.get_trace(engine)
+    if tracer !== nothing && !m.trace
+        check(m.handle, ccall((:cxb_trace_enable, LIB), Int32, (Ptr{Cvoid}, Int32), m.handle, 1)); m.trace = true
+    end
+    stats = Ref(UpdateStats(0, 0, ntuple(_ -> 0, 6), 0, 0, 0))
+    t0 = time_ns()
+    st = ccall((:cxb_update_marginals, LIB), Int32, (Ptr{Cvoid}, Int64, Ptr{Int64}, Ref{UpdateStats}), m.handle, length(ids), ids, stats)
+    check(m.handle, st)
+    tracer === nothing || push!(tracer.inference_requests, collect_trace(engine, variable_ids, time_ns() - t0))
+    return nothing                                                       # as the reference (src/inference_engine.jl:631)
 end
 
-# ---- data in / out: set_value! (src/signal.jl:232), get_value (:171) -----------------------------------------------
-function set_values!(e::B200InferenceEngine, signal_ids::Vector{Int64}, values::Matrix{Float64})   # values: dim x n
-    check(e.handle, ccall((:cxb_set_values, LIB), Int32, (Ptr{Cvoid}, Int64, Ptr{Int64}, Ptr{Float64}, Int64),
-                          e.handle, length(signal_ids), signal_ids, values, size(values, 1)))
-end
-function get_values(e::B200InferenceEngine, signal_ids::Vector{Int64}, dim::Int)
-    out = zeros(Float64, dim, length(signal_ids))
-    check(e.handle, ccall((:cxb_get_values, LIB), Int32, (Ptr{Cvoid}, Int64, Ptr{Int64}, Ptr{Float64}, Int64),
-                          e.handle, length(signal_ids), signal_ids, out, dim))
-    return out
-end
-is_pending(e::B200InferenceEngine, sid::Int64) = ccall((:cxb_is_pending, LIB), Int32, (Ptr{Cvoid}, Int64), e.handle, sid) == 1
-is_computed(e::B200InferenceEngine, sid::Int64) = ccall((:cxb_is_computed, LIB), Int32, (Ptr{Cvoid}, Int64), e.handle, sid) == 1
-link_signal_to_variable!(e::B200InferenceEngine, v::Int, sid::Int64) =
-    check(e.handle, ccall((:cxb_link_signal, LIB), Int32, (Ptr{Cvoid}, Int64, Int64), e.handle, v - 1, sid))
-
-# ---- the scheduler entry points: more specific methods of the reference generics ---------------------------------
-function Cortex.request_inference_for(e::B200InferenceEngine, variable_ids::Union{AbstractVector, Tuple})
-    ids = Int64[v - 1 for v in variable_ids]
-    check(e.handle, ccall((:cxb_request_inference, LIB), Int32, (Ptr{Cvoid}, Int64, Ptr{Int64}), e.handle, length(ids), ids))
-    return ids
+# request_inference_for + scan_inference_request, src/inference_engine.jl:294-323, 540-546 (the reference's DFS order)
+function scan_pending(engine::Cortex.InferenceEngine{<:B200ModelEngine}, variable_ids)
+    m = Cortex.get_model_engine(engine)
+    ids = Int64[Int64(v) - 1 for v in variable_ids]
+    check(m.handle, ccall((:cxb_request_inference, LIB), Int32, (Ptr{Cvoid}, Int64, Ptr{Int64}), m.handle, length(ids), ids))
+    n = ccall((:cxb_scan_dfs, LIB), Int64, (Ptr{Cvoid}, Ptr{Int64}, Int64), m.handle, C_NULL, 0)
+    buf = zeros(Int64, max(n, 1))
+    n = ccall((:cxb_scan_dfs, LIB), Int64, (Ptr{Cvoid}, Ptr{Int64}, Int64), m.handle, buf, n)
+    return [signal_view(m, sid, variant_of(m, sid)) for sid in buf[1:n]]
 end
 
-function scan_inference_request(e::B200InferenceEngine)
-    n = ccall((:cxb_scan, LIB), Int64, (Ptr{Cvoid}, Ptr{Int64}, Int64), e.handle, C_NULL, 0)
-    out = zeros(Int64, n)
-    ccall((:cxb_scan, LIB), Int64, (Ptr{Cvoid}, Ptr{Int64}, Int64), e.handle, out, n)
-    return out
+function variant_of(m::B200ModelEngine, sid::Int64)
+    info = zeros(Int64, 5)
+    check(m.handle, ccall((:cxb_signal_info, LIB), Int32, (Ptr{Cvoid}, Int64, Ptr{Int64}), m.handle, sid, info))
+    kind, v, f = info[1], Int(info[2]) + 1, Int(info[3]) + 1
+    V = Cortex.InferenceSignalVariants
+    kind == KIND_M2F && return V.MessageToFactor(v, f)
+    kind == KIND_M2V && return V.MessageToVariable(v, f)
+    kind == KIND_MARGINAL && return V.IndividualMarginal(v)
+    kind == KIND_PRODUCT && return V.ProductOfMessages(v, (Int(info[4]) + 1):(Int(info[5]) + 1), get_connected_factor_ids(m, v))
+    kind == KIND_JOINT && return V.JointMarginal(f, Int[])
+    return V.Unspecified()
 end
 
-function Cortex.update_marginals!(e::B200InferenceEngine, variable_ids::Union{AbstractVector, Tuple})
-    ids = Int64[v - 1 for v in variable_ids]
-    stats = Ref{UpdateStats}()
-    check(e.handle, ccall((:cxb_update_marginals, LIB), Int32, (Ptr{Cvoid}, Int64, Ptr{Int64}, Ref{UpdateStats}),
-                          e.handle, length(ids), ids, stats))
-    return nothing                                  # the reference returns nothing (src/inference_engine.jl:631)
-end
-Cortex.update_marginals!(e::B200InferenceEngine, variable_id) = Cortex.update_marginals!(e, (variable_id,))
-
-# ---- structured model engines (closed-form plans) ------------------------------------------------------------------
-mutable struct GaussianChainBatch
-    handle::Ptr{Cvoid}
-    n_chains::Int
-    n_steps::Int
-end
-function GaussianChainBatch(n_chains::Int, n_steps::Int; dtype::Integer = F32, device::Integer = 0)
-    href = Ref{Ptr{Cvoid}}(C_NULL)
-    st = ccall((:cxb_chains_create, LIB), Int32, (Int32, Int32, Int64, Int64, Ref{Ptr{Cvoid}}), device, dtype, n_chains, n_steps, href)
-    st == OK || error("cxb_chains_create failed with status $st")
-    c = GaussianChainBatch(href[], n_chains, n_steps)
-    finalizer(x -> ccall((:cxb_chains_destroy, LIB), Cvoid, (Ptr{Cvoid},), x.handle), c)
-    return c
-end
-set_noise!(c::GaussianChainBatch, q::Vector{Float64}, r::Vector{Float64}) =
-    ccall((:cxb_chains_set_noise, LIB), Int32, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}), c.handle, q, r)
-set_observations!(c::GaussianChainBatch, y::Matrix{Float32}) =                       # y is [B, T] column-major == [T][B]
-    ccall((:cxb_chains_set_observations, LIB), Int32, (Ptr{Cvoid}, Ptr{Cvoid}), c.handle, y)
-function update_marginals!(c::GaussianChainBatch)
-    n = Ref{Int64}(0)
-    st = ccall((:cxb_chains_update_marginals, LIB), Int32, (Ptr{Cvoid}, Ref{Int64}), c.handle, n)
-    st == OK || error(unsafe_string(ccall((:cxb_chains_last_error, LIB), Cstring, (Ptr{Cvoid},), c.handle)))
-    return n[]
-end
-function get_marginals(c::GaussianChainBatch)
-    out = zeros(Float32, 2, c.n_chains, c.n_steps)
-    ccall((:cxb_chains_get_marginals, LIB), Int32, (Ptr{Cvoid}, Ptr{Cvoid}), c.handle, out)
-    return out
-end
-
-# ---- structured engines of the other model families (same pattern: opaque handle, status codes, host arrays borrowed) ----
-
-"Row shard of a Potts grid (BASELINE config 4). Neighbour shards live in other processes (one Julia process per GPU)."
-mutable struct PottsGridShard
-    handle::Ptr{Cvoid}
-    rows::Int
-    cols::Int
-    K::Int
-end
-function PottsGridShard(rows::Int, cols::Int, K::Int, beta::Float64; dtype::Integer = F32, device::Integer = 0,
-                        has_upper::Bool = false, has_lower::Bool = false)
-    href = Ref{Ptr{Cvoid}}(C_NULL)
-    st = ccall((:cxb_grid_create, LIB), Int32, (Int32, Int32, Int64, Int64, Int32, Float64, Int32, Int32, Ref{Ptr{Cvoid}}),
-               device, dtype, rows, cols, K, beta, has_upper, has_lower, href)
-    st == OK || error("cxb_grid_create failed with status $st (CUDA device required; there is no CPU fallback)")
-    g = PottsGridShard(href[], rows, cols, K)
-    finalizer(x -> ccall((:cxb_grid_destroy, LIB), Cvoid, (Ptr{Cvoid},), x.handle), g)
-    return g
-end
-grid_check(g::PottsGridShard, st::Int32) =
-    st == OK || error(unsafe_string(ccall((:cxb_grid_last_error, LIB), Cstring, (Ptr{Cvoid},), g.handle)))
-set_unary!(g::PottsGridShard, unary::Array{Float32, 3}) =            # K x cols x rows (column-major = [rows][cols][K] in C)
-    grid_check(g, ccall((:cxb_grid_set_unary, LIB), Int32, (Ptr{Cvoid}, Ptr{Cvoid}), g.handle, unary))
-reset_messages!(g::PottsGridShard) = grid_check(g, ccall((:cxb_grid_reset_messages, LIB), Int32, (Ptr{Cvoid},), g.handle))
-function sweep!(g::PottsGridShard)                                   # one synchronous sweep = protocol B of SURVEY Appendix B
-    n = Ref{Int64}(0)
-    grid_check(g, ccall((:cxb_grid_sweep, LIB), Int32, (Ptr{Cvoid}, Ref{Int64}), g.handle, n))
-    return n[]
-end
-"128 bytes (two cudaIpcMemHandle_t) to hand to the row neighbours, e.g. with MPI.Sendrecv!."
-function p2p_export(g::PottsGridShard)
-    handles = Vector{UInt8}(undef, 128)
-    grid_check(g, ccall((:cxb_grid_p2p_export, LIB), Int32, (Ptr{Cvoid}, Ptr{UInt8}), g.handle, handles))
-    return handles
-end
-"direction 0 = the shard above, 1 = the shard below; afterwards sweep! delivers the cut-edge messages itself (NVLink peer stores)."
-p2p_connect!(g::PottsGridShard, direction::Integer, neighbour_handles::Vector{UInt8}) =
-    grid_check(g, ccall((:cxb_grid_p2p_connect_ipc, LIB), Int32, (Ptr{Cvoid}, Int32, Ptr{UInt8}), g.handle, direction, neighbour_handles))
-function get_marginals(g::PottsGridShard)
-    out = Array{Float32, 3}(undef, g.K, g.cols, g.rows)
-    grid_check(g, ccall((:cxb_grid_get_marginals, LIB), Int32, (Ptr{Cvoid}, Ptr{Cvoid}), g.handle, out))
-    return out
-end
-
-"Batch of discrete HMMs (BASELINE config 3): K = 64 register kernel, K >= 128 tcgen05 path, otherwise the generic kernel."
-mutable struct HmmBatch
-    handle::Ptr{Cvoid}
-    B::Int
-    T::Int
-    K::Int
-end
-function HmmBatch(n_chains::Int, n_steps::Int, n_states::Int, n_symbols::Int; dtype::Integer = F32, device::Integer = 0)
-    href = Ref{Ptr{Cvoid}}(C_NULL)
-    st = ccall((:cxb_hmm_create, LIB), Int32, (Int32, Int32, Int64, Int64, Int32, Int32, Ref{Ptr{Cvoid}}),
-               device, dtype, n_chains, n_steps, n_states, n_symbols, href)
-    st == OK || error("cxb_hmm_create failed with status $st")
-    m = HmmBatch(href[], n_chains, n_steps, n_states)
-    finalizer(x -> ccall((:cxb_hmm_destroy, LIB), Cvoid, (Ptr{Cvoid},), x.handle), m)
-    return m
-end
-hmm_check(m::HmmBatch, st::Int32) = st == OK || error(unsafe_string(ccall((:cxb_hmm_last_error, LIB), Cstring, (Ptr{Cvoid},), m.handle)))
-set_tables!(m::HmmBatch, transition::Matrix{Float64}, emission::Matrix{Float64}) =   # row-major on the C side: pass transposes
-    hmm_check(m, ccall((:cxb_hmm_set_tables, LIB), Int32, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}), m.handle,
-                       permutedims(transition), permutedims(emission)))
-set_observations!(m::HmmBatch, obs::Matrix{UInt8}) =                 # B x T (column-major = [T][B] in C)
-    hmm_check(m, ccall((:cxb_hmm_set_observations, LIB), Int32, (Ptr{Cvoid}, Ptr{UInt8}), m.handle, obs))
-function update_marginals!(m::HmmBatch)
-    n = Ref{Int64}(0)
-    hmm_check(m, ccall((:cxb_hmm_update_marginals, LIB), Int32, (Ptr{Cvoid}, Ref{Int64}), m.handle, n))
-    return n[]
-end
-function get_marginals(m::HmmBatch, t0::Int = 0, t1::Int = m.T)      # K x B x (t1 - t0)
-    out = Array{Float32, 3}(undef, m.K, m.B, t1 - t0)
-    hmm_check(m, ccall((:cxb_hmm_get_marginals, LIB), Int32, (Ptr{Cvoid}, Int64, Int64, Ptr{Cvoid}), m.handle, t0, t1, out))
-    return out
-end
-
-"Arbitrary pairwise categorical graph, loopy BP by synchronous sweeps (BASELINE config 5). Ids are 0-based on the C side."
-mutable struct PairwiseGraph
-    handle::Ptr{Cvoid}
-    n::Int
-    K::Int
-end
-function PairwiseGraph(n_variables::Int, fac_u::Vector{Int64}, fac_v::Vector{Int64}, fac_table::Vector{Int32},
-                       tables::Array{Float64, 3}; dtype::Integer = F32, device::Integer = 0)   # tables: K x K x n_tables, [x_hi, x_lo, t]
-    K, n_tables = size(tables, 1), size(tables, 3)
-    href = Ref{Ptr{Cvoid}}(C_NULL)
-    st = ccall((:cxb_pairwise_create, LIB), Int32, (Int32, Int32, Int64, Int64, Int32, Int32, Ref{Ptr{Cvoid}}),
-               device, dtype, n_variables, length(fac_u), K, n_tables, href)
-    st == OK || error("cxb_pairwise_create failed with status $st")
-    g = PairwiseGraph(href[], n_variables, K)
-    finalizer(x -> ccall((:cxb_pairwise_destroy, LIB), Cvoid, (Ptr{Cvoid},), x.handle), g)
-    chk(s) = s == OK || error(unsafe_string(ccall((:cxb_pairwise_last_error, LIB), Cstring, (Ptr{Cvoid},), g.handle)))
-    chk(ccall((:cxb_pairwise_set_graph, LIB), Int32, (Ptr{Cvoid}, Ptr{Int64}, Ptr{Int64}, Ptr{Int32}), g.handle, fac_u .- 1, fac_v .- 1, fac_table))
-    chk(ccall((:cxb_pairwise_set_tables, LIB), Int32, (Ptr{Cvoid}, Ptr{Float64}), g.handle, tables))
-    return g
-end
-pw_check(g::PairwiseGraph, st::Int32) = st == OK || error(unsafe_string(ccall((:cxb_pairwise_last_error, LIB), Cstring, (Ptr{Cvoid},), g.handle)))
-set_unary!(g::PairwiseGraph, unary::Matrix{Float32}) =               # K x n
-    pw_check(g, ccall((:cxb_pairwise_set_unary, LIB), Int32, (Ptr{Cvoid}, Ptr{Cvoid}), g.handle, unary))
-reset_messages!(g::PairwiseGraph) = pw_check(g, ccall((:cxb_pairwise_reset_messages, LIB), Int32, (Ptr{Cvoid},), g.handle))
-function get_marginals(g::PairwiseGraph)
-    out = Matrix{Float32}(undef, g.K, g.n)
-    pw_check(g, ccall((:cxb_pairwise_get_marginals, LIB), Int32, (Ptr{Cvoid}, Ptr{Cvoid}), g.handle, out))
-    return out
-end
-function sweep!(g::PairwiseGraph)
-    n = Ref{Int64}(0)
-    st = ccall((:cxb_pairwise_sweep, LIB), Int32, (Ptr{Cvoid}, Ref{Int64}), g.handle, n)
-    st == OK || error(unsafe_string(ccall((:cxb_pairwise_last_error, LIB), Cstring, (Ptr{Cvoid},), g.handle)))
-    return n[]
+# ---- tracer, src/inference_engine.jl:650-862: rounds, executions in order, measured times --------------------------------
+function collect_trace(engine::Cortex.InferenceEngine{<:B200ModelEngine}, variable_ids, total_ns)
+    m = Cortex.get_model_engine(engine)
+    n = ccall((:cxb_trace_get, LIB), Int64, (Ptr{Cvoid}, Ptr{Int64}, Ptr{Int64}, Int64), m.handle, C_NULL, C_NULL, 0)
+    level = zeros(Int64, max(n, 1)); sids = zeros(Int64, max(n, 1)); ns = zeros(Int64, max(n, 1)); vars = zeros(Int64, max(n, 1))
+    ccall((:cxb_trace_get, LIB), Int64, (Ptr{Cvoid}, Ptr{Int64}, Ptr{Int64}, Int64), m.handle, level, sids, n)
+    ccall((:cxb_trace_get_times, LIB), Int64, (Ptr{Cvoid}, Ptr{Int64}, Int64), m.handle, ns, n)
+    ccall((:cxb_trace_get_variables, LIB), Int64, (Ptr{Cvoid}, Ptr{Int64}, Int64), m.handle, vars, n)
+    rounds = Cortex.TracedInferenceRound[]
+    current = nothing; executions = Cortex.TracedInferenceExecution[]
+    flush!() = isempty(executions) || push!(rounds, Cortex.TracedInferenceRound(engine, UInt64(sum(e.total_time_in_ns for e in executions)), executions))
+    for k in 1:n
+        key = level[k] >= 0 ? level[k] : -1                 # the final phase (marginals, then linked signals) is ONE round, :610-628
+        if key != current
+            flush!(); executions = Cortex.TracedInferenceExecution[]; current = key
+        end
+        signal = signal_view(m, sids[k], variant_of(m, sids[k]))
+        # value_before_execution needs a snapshot taken before the request (the Python mirror does that); here: not recorded
+        push!(executions, Cortex.TracedInferenceExecution(engine, Int(vars[k]) + 1, signal, UInt64(max(ns[k], 1)), nothing, Cortex.get_value(signal)))
+    end
+    flush!()
+    request = Cortex.InferenceRequest(engine, variable_ids, Cortex.InferenceSignal[], falses(length(variable_ids)))
+    return Cortex.TracedInferenceRequest(engine, UInt64(max(total_ns, 1)), request, rounds)
 end
 
 end # module

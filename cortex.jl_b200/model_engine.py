@@ -211,3 +211,124 @@ def add_factor(graph: BipartiteFactorGraph, f: Factor) -> int:
 
 def add_edge(graph: BipartiteFactorGraph, variable_id: int, factor_id: int, c: Connection) -> None:
     graph.add_edge(variable_id, factor_id, c)
+
+
+class B200ModelEngine:
+    """A model-engine BACKEND whose signals live on the device (mirror of ``julia/CortexB200.jl::B200ModelEngine``, SURVEY
+    8b / 8f.3): implements the trait and the seven generics of ``src/model_engine.jl:269-391`` LAZILY. The graph is handed to
+    the library as flat arrays; nothing is allocated per variable, factor or connection up front — ``get_variable`` /
+    ``get_connection`` materialise a ``Variable`` / ``Connection`` view on demand whose signals are references into the
+    device state, so the reference-style read-out
+
+        get_value(get_variable_marginal(get_variable(engine, v)))
+
+    fetches the current value from the device and no signal id ever shows in user code.
+
+    ``B200ModelEngine(n_ids, is_factor, functional_forms, edge_variable, edge_factor)`` takes the arrays directly (graphs that
+    never exist as host objects); ``B200ModelEngine.from_engine(source)`` walks any supported model engine ONCE.
+    """
+
+    def __init__(self, n_ids, is_factor, functional_forms, edge_variable, edge_factor, names=None, labels=None):
+        import numpy as np
+
+        self.n_ids = int(n_ids)
+        self.is_factor = np.ascontiguousarray(is_factor, dtype=np.uint8)
+        if self.is_factor.shape != (self.n_ids,):
+            raise ValueError("is_factor must have one entry per id")
+        self.functional_forms = functional_forms  # sequence / dict: factor id -> Factor.functional_form
+        self.edge_variable = np.ascontiguousarray(edge_variable, dtype=np.int64)
+        self.edge_factor = np.ascontiguousarray(edge_factor, dtype=np.int64)
+        if self.edge_variable.shape != self.edge_factor.shape:
+            raise ValueError("edge arrays differ in length")
+        self._names = names or {}
+        self._labels = labels or {}
+        # adjacency in CSR form, neighbours in ascending id (the iteration-order contract of ext/BipartiteFactorGraphsExt)
+        deg = np.bincount(np.concatenate([self.edge_variable, self.edge_factor]), minlength=self.n_ids)
+        self._adj_off = np.concatenate([[0], np.cumsum(deg)])
+        ends = np.concatenate([self.edge_variable, self.edge_factor])
+        others = np.concatenate([self.edge_factor, self.edge_variable])
+        order = np.lexsort((others, ends))
+        self._adj = others[order]
+        self._engine = None  # bound by InferenceEngine.__init__
+
+    @classmethod
+    def from_engine(cls, source):
+        throw_if_engine_unsupported(source)
+        vids = sorted(int(v) for v in backend_get_variable_ids(source))
+        fids = sorted(int(f) for f in backend_get_factor_ids(source))
+        n_ids = (max(vids + fids) + 1) if (vids or fids) else 0
+        is_factor = [0] * n_ids
+        forms = {}
+        for f in fids:
+            is_factor[f] = 1
+            forms[f] = backend_get_factor(source, f).functional_form
+        names = {v: (backend_get_variable(source, v).name, backend_get_variable(source, v).index) for v in vids}
+        edges = source.edges() if hasattr(source, "edges") else [(int(v), f) for f in fids for v in backend_get_connected_variable_ids(source, f)]
+        labels = {}
+        for (v, f) in edges:
+            c = backend_get_connection(source, v, f)
+            labels[(v, f)] = (c.label, c.index)
+        return cls(n_ids, is_factor, forms, [e[0] for e in edges], [e[1] for e in edges], names=names, labels=labels)
+
+    def is_engine_supported(self):
+        return SupportedModelEngine()
+
+    # ---- the seven generics, src/model_engine.jl:329-391 -------------------------------------------------------------------
+    def get_variable_ids(self):
+        import numpy as np
+
+        return [int(i) for i in np.flatnonzero(self.is_factor == 0)]
+
+    def get_factor_ids(self):
+        import numpy as np
+
+        return [int(i) for i in np.flatnonzero(self.is_factor == 1)]
+
+    def _neighbours(self, i):
+        return [int(x) for x in self._adj[self._adj_off[i]:self._adj_off[i + 1]]]
+
+    def get_connected_variable_ids(self, factor_id: int):
+        self._check(factor_id, factor=True)
+        return self._neighbours(factor_id)
+
+    def get_connected_factor_ids(self, variable_id: int):
+        self._check(variable_id, factor=False)
+        return self._neighbours(variable_id)
+
+    def _check(self, i, factor):
+        if not (0 <= int(i) < self.n_ids) or bool(self.is_factor[int(i)]) != factor:
+            raise KeyError(f"not a {'factor' if factor else 'variable'} id: {i}")
+
+    def _signal(self, kind, v, f=-1):
+        eng = self._engine
+        if eng is None:
+            raise RuntimeError("the model engine is not bound to an InferenceEngine yet")
+        sid = eng.api.signal_id(eng.store.h, kind, int(v), int(f))
+        if sid < 0:
+            raise KeyError(f"no such signal: kind {kind}, variable {v}, factor {f}")
+        return Signal(eng.store, sid)
+
+    def get_variable(self, variable_id: int) -> Variable:
+        from . import _capi as capi
+
+        self._check(variable_id, factor=False)
+        name, index = self._names.get(int(variable_id), ("variable", int(variable_id)))
+        var = Variable(name=name, index=index, marginal=self._signal(capi.KIND_MARGINAL, variable_id),
+                       linked_signals=list(self._engine._links.get(int(variable_id), ())))
+        var._engine, var._id = self._engine, int(variable_id)
+        return var
+
+    def get_factor(self, factor_id: int) -> Factor:
+        self._check(factor_id, factor=True)
+        forms = self.functional_forms
+        return Factor(functional_form=forms[int(factor_id)])
+
+    def get_connection(self, variable_id: int, factor_id: int) -> Connection:
+        from . import _capi as capi
+
+        label, index = self._labels.get((int(variable_id), int(factor_id)), ("edge", 0))
+        return Connection(label=label, index=index, message_to_variable=self._signal(capi.KIND_M2V, variable_id, factor_id),
+                          message_to_factor=self._signal(capi.KIND_M2F, variable_id, factor_id))
+
+    def edges(self):
+        return list(zip((int(v) for v in self.edge_variable), (int(f) for f in self.edge_factor)))

@@ -483,3 +483,50 @@ def ssm_structured_experiment(engine, x, y, obsnoise, ssnoise, dataset, vmp_iter
     mg = lambda v: C.get_value(C.get_variable_marginal(C.get_variable(engine, v)))  # noqa: E731
     return {"x": C.get_values([C.get_variable_marginal(C.get_variable(engine, v)) for v in x]),
             "ssnoise": mg(ssnoise), "obsnoise": mg(obsnoise)}
+
+
+def make_ssm_batch_model(lengths, api, *, dtype=cap.F64, q=None, r=None, interleave=False):
+    """A batch of independent random-walk chains (test/inference_engine_tests.jl:436-462 per chain) in ONE graph, built
+    through the generic frontend. Returns (engine, xs, ys, liks, trs) with one list per chain. Per-chain noise variances
+    go in as per-factor parameters (cxb_set_factor_params). `interleave` creates the variables chain-interleaved (time-
+    major ids) instead of chain after chain."""
+    g = C.BipartiteFactorGraph()
+    B = len(lengths)
+    xs = [[None] * T for T in lengths]
+    ys = [[None] * T for T in lengths]
+    order = [(b, t) for t in range(max(lengths)) for b in range(B) if t < lengths[b]] if interleave else [(b, t) for b in range(B) for t in range(lengths[b])]
+    for b, t in order:
+        xs[b][t] = g.add_variable(C.Variable(name="x", index=(b, t)))
+    for b, t in order:
+        ys[b][t] = g.add_variable(C.Variable(name="y", index=(b, t)))
+    liks = [[None] * T for T in lengths]
+    trs = [[None] * max(T - 1, 0) for T in lengths]
+    for b, t in order:
+        liks[b][t] = g.add_factor(C.Factor(functional_form="likelihood"))
+    for b, t in order:
+        if t + 1 < lengths[b]:
+            trs[b][t] = g.add_factor(C.Factor(functional_form="transition"))
+    for b, t in order:
+        g.add_edge(ys[b][t], liks[b][t], C.Connection(label="out"))
+        g.add_edge(xs[b][t], liks[b][t], C.Connection(label="out"))
+    for b, t in order:
+        if t + 1 < lengths[b]:
+            g.add_edge(xs[b][t], trs[b][t], C.Connection(label="out"))
+            g.add_edge(xs[b][t + 1], trs[b][t], C.Connection(label="in"))
+    processor = C.RuleProcessor({"likelihood": (cap.RULE_GAUSS_OBS, [1.0]), "transition": (cap.RULE_GAUSS_RW, [1.0])},
+                                family=cap.FAMILY_GAUSS_CANON, value_dim=2)
+    engine = C.InferenceEngine(model_engine=g, dependency_resolver=C.DefaultDependencyResolver(), inference_request_processor=processor,
+                               dtype=dtype, api=api)
+    if q is not None or r is not None:
+        fids, vals = [], []
+        for b in range(B):
+            if r is not None:
+                fids += liks[b]
+                vals += [float(r[b])] * lengths[b]
+            if q is not None:
+                fids += trs[b]
+                vals += [float(q[b])] * len(trs[b])
+        fa = np.ascontiguousarray(fids, dtype=np.int64)
+        va = np.ascontiguousarray(vals, dtype=np.float64)
+        engine.store.check(api.set_factor_params(engine.store.h, len(fa), fa.ctypes.data_as(cap.i64p), va.ctypes.data_as(cap.f64p)))
+    return engine, xs, ys, liks, trs
