@@ -194,11 +194,26 @@ __global__ void __launch_bounds__(256) k_potts_sweep(GridView g, T w) {
 
 // stream-ordered hand-shake of the fused halo exchange: sweeps completed by the neighbours are counted in flags that
 // live in THIS shard's memory and are written by the neighbours' k_halo_signal
-__global__ void k_halo_wait(const volatile unsigned* flag_a, const volatile unsigned* flag_b, unsigned expected) {
-    if (flag_a)
-        while (*flag_a < expected) __nanosleep(64);
-    if (flag_b)
-        while (*flag_b < expected) __nanosleep(64);
+// The spin is BOUNDED (a row neighbour that died or never enqueued its sweep must not hang the stream for ever): after
+// `timeout_ns` of waiting the kernel records which neighbour is missing in *timed_out and returns; the host finds the flag at
+// the next cxb_grid_sync / cxb_grid_get_* and reports CXB_ERR_STATE (the shard's messages are then not to be trusted).
+__global__ void k_halo_wait(const volatile unsigned* flag_a, const volatile unsigned* flag_b, unsigned expected, unsigned long long timeout_ns,
+                            unsigned* timed_out) {
+    unsigned long long t0;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+    auto wait = [&](const volatile unsigned* f, unsigned bit) {
+        while (*f < expected) {
+            __nanosleep(64);
+            unsigned long long t;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+            if (t - t0 > timeout_ns) {
+                atomicOr(timed_out, bit);
+                return;
+            }
+        }
+    };
+    if (flag_a) wait(flag_a, 1u);
+    if (flag_b) wait(flag_b, 2u);
     __threadfence_system();
 }
 __global__ void k_halo_signal(unsigned* peer_flag_a, unsigned* peer_flag_b, unsigned value) {
@@ -224,6 +239,17 @@ struct Grid {
     DBuf<unsigned char> unary, m2f[2], m2v, marg, halo_recv;  // m2f[b]: 4 planes; m2v: 4 planes; halo_recv: [2 parities][2 rows]
     DBuf<unsigned> flags;                       // [0] sweeps completed by the upper neighbour, [1] by the lower neighbour
     unsigned sweep_no = 0;                      // sweeps since the last reset (parity of the halo buffers)
+    unsigned long long halo_timeout_ns = 20ull * 1000000000ull;  // CXB_GRID_HALO_TIMEOUT_MS overrides (tests)
+    // after a stream sync: did a halo wait give up on a neighbour?
+    int32_t check_halo() {
+        if (!peer_halo[0] && !peer_halo[1]) return CXB_OK;
+        unsigned t = 0;
+        if (cudaMemcpy(&t, flags.p + 2, sizeof(unsigned), cudaMemcpyDeviceToHost) != cudaSuccess) return CXB_ERR_CUDA;
+        if (!t) return CXB_OK;
+        err = std::string("fused halo exchange: the row neighbour ") + ((t & 1) ? "above" : "below") +
+              " did not deliver its boundary messages in time (its sweep was never enqueued, or the process is gone)";
+        return CXB_ERR_STATE;
+    }
     unsigned char* peer_halo[2] = {nullptr, nullptr};  // the neighbours' halo_recv (direction 0 = above, 1 = below)
     unsigned* peer_flags[2] = {nullptr, nullptr};      // the neighbours' flags
     void* ipc_opened[4] = {nullptr, nullptr, nullptr, nullptr};
@@ -252,6 +278,7 @@ struct Grid {
         }
         CXB_CUDA(cudaSetDevice(device));
         CXB_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+        if (const char* e = getenv("CXB_GRID_HALO_TIMEOUT_MS")) halo_timeout_ns = (unsigned long long)std::max(1, atoi(e)) * 1000000ull;
         CXB_CUDA(cudaEventCreate(&ev0));
         CXB_CUDA(cudaEventCreate(&ev1));
         CXB_CUDA(unary.reserve(plane()));
@@ -260,8 +287,8 @@ struct Grid {
         CXB_CUDA(m2v.reserve(4 * plane()));
         CXB_CUDA(marg.reserve(plane()));
         CXB_CUDA(halo_recv.reserve(4 * row()));
-        CXB_CUDA(flags.reserve(2));
-        CXB_CUDA(cudaMemsetAsync(flags.p, 0, 2 * sizeof(unsigned), stream));
+        CXB_CUDA(flags.reserve(4));  // [0], [1] sweep counters written by the neighbours; [2] halo wait timed out (bit 0 above, bit 1 below)
+        CXB_CUDA(cudaMemsetAsync(flags.p, 0, 4 * sizeof(unsigned), stream));
         CXB_CUDA(cudaMemsetAsync(m2v.p, 0, 4 * plane(), stream));
         CXB_CUDA(cudaMemsetAsync(marg.p, 0, plane(), stream));
         return CXB_OK;
@@ -278,8 +305,12 @@ struct Grid {
         for (int b = 0; b < 2; ++b) dtype == CXB_F32 ? fill<float>(m2f[b].p, n, u) : fill<double>(m2f[b].p, n, u);
         dtype == CXB_F32 ? fill<float>(halo_recv.p, nh, u) : fill<double>(halo_recv.p, nh, u);
         // with a fused (peer-memory) exchange every shard of the grid must be idle here: the neighbours' counters restart
-        CXB_CUDA(cudaMemsetAsync(flags.p, 0, 2 * sizeof(unsigned), stream));
+        CXB_CUDA(cudaMemsetAsync(flags.p, 0, 4 * sizeof(unsigned), stream));
         CXB_CUDA(cudaGetLastError());
+        // synchronous: a neighbour shard that starts sweeping right after ITS reset stores its boundary messages into this
+        // shard's halo buffer; were this fill still queued behind the large message planes it would overwrite them with the
+        // uniform message (found at 1024^2 and larger by tests/test_fullsize_parity.py; the small grids never showed it)
+        CXB_CUDA(cudaStreamSynchronize(stream));
         cur = 0;
         sweep_no = 0;
         have_msgs = true;
@@ -332,7 +363,8 @@ struct Grid {
         double w = std::exp(beta) - 1.0;
         const bool fused = peer_halo[0] || peer_halo[1];
         if (fused && sweep_no > 0)  // the neighbours have finished sweep sweep_no - 1 (their boundary rows have landed here)
-            CXB_LAUNCH(k_halo_wait, 1, 1, 0, stream, peer_halo[0] ? flags.p + 0 : nullptr, peer_halo[1] ? flags.p + 1 : nullptr, sweep_no);
+            CXB_LAUNCH(k_halo_wait, 1, 1, 0, stream, peer_halo[0] ? flags.p + 0 : nullptr, peer_halo[1] ? flags.p + 1 : nullptr, sweep_no,
+                       halo_timeout_ns, flags.p + 2);
         CXB_CUDA(cudaEventRecord(ev0, stream));
         int32_t st = dtype == CXB_F32 ? launch_k<float, 4>(g, (float)w) : launch_k<double, 2>(g, w);
         if (st) return st;
@@ -477,7 +509,7 @@ int32_t cxb_grid_get_marginals(cxb_grid* g, void* out_host) try {
     GR_CUDA(g, cudaSetDevice(h->device));
     GR_CUDA(g, cudaMemcpyAsync(out_host, h->marg.p, h->plane(), cudaMemcpyDeviceToHost, h->stream));
     GR_CUDA(g, cudaStreamSynchronize(h->stream));
-    return CXB_OK;
+    return h->check_halo();
 } CXB_ABI_CATCH(CXB_ERR_INTERNAL)
 // which: 0..3 = m2v from the (up, left, right, down) factor; 4..7 = m2f towards them (current buffer)
 int32_t cxb_grid_get_messages(cxb_grid* g, int32_t which, void* out_host) try {
@@ -505,7 +537,7 @@ int32_t cxb_grid_last_kernel_ms(cxb_grid* g, float* ms_out) try {
 } CXB_ABI_CATCH(CXB_ERR_INTERNAL)
 int32_t cxb_grid_sync(cxb_grid* g) try {
     GR_CUDA(g, cudaStreamSynchronize(GR(g)->stream));
-    return CXB_OK;
+    return GR(g)->check_halo();
 } CXB_ABI_CATCH(CXB_ERR_INTERNAL)
 
 }  // extern "C"

@@ -205,6 +205,12 @@ def assert_values_close(got, want, dtype, kind="prob", err_msg=""):
     if kind in ("prob", "plain"):
         np.testing.assert_allclose(got, want, rtol=tol, atol=tol * 1e-3, err_msg=err_msg)
         return
+    if kind == "mp":  # NormalMeanPrecision (mean, precision): the precision rel tol, the mean to tol * (|mean| + standard deviation)
+        np.testing.assert_allclose(got[..., 1], want[..., 1], rtol=tol, atol=0, err_msg=err_msg + " (precision)")
+        bound = tol * (np.abs(want[..., 0]) + 1.0 / np.sqrt(want[..., 1]))
+        bad = np.abs(got[..., 0] - want[..., 0]) > bound
+        assert not bad.any(), f"{err_msg} (mean): {int(bad.sum())} of {bad.size} differ"
+        return
     assert kind == "canon" and want.shape[-1] == 2
     lam_w, eta_w, lam_g, eta_g = want[..., 0], want[..., 1], got[..., 0], got[..., 1]
     vac = lam_w == 0

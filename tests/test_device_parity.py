@@ -179,7 +179,7 @@ def test_resident_level_loop_equals_per_level_kernels(device_api, model, monkeyp
                     [s.kernel_launches for s in st]))
     (state_r, stats_r, launches_r), (state_h, stats_h, launches_h) = out
     assert stats_r == stats_h
-    assert max(launches_r) <= 3 < min(launches_h)  # request + resident loop vs a dozen launches per level
+    assert max(launches_r) <= 6 < min(launches_h)  # request, checks, memo look-up + ONE resident loop vs a dozen launches per level
     assert state_r[0] == state_h[0]  # computed / pending flags and dependency nibbles of every signal
     np.testing.assert_array_equal(state_r[1], state_h[1])  # values, bit for bit
 
@@ -727,3 +727,22 @@ def test_chain_batch_extreme_noise(oracle_api):
         C.update_marginals(e, x, schedule="seq")
         want = C.get_values([C.get_variable_marginal(C.get_variable(e, v)) for v in x])
         np.testing.assert_allclose(got[:, b, :], want, rtol=1e-12, atol=0)
+
+
+def test_potts_grid_halo_wait_is_bounded(monkeypatch):
+    """A row neighbour that never enqueues its sweep must not hang the stream: the wait gives up after the time-out and the
+    next synchronising call reports it (k_halo_wait spun for ever)."""
+    monkeypatch.setenv("CXB_GRID_HALO_TIMEOUT_MS", "50")
+    H, W, K = 6, 5, 8
+    unary = np.random.Generator(np.random.PCG64(8)).dirichlet(np.ones(K), size=(H, W)).astype(np.float32)
+    top = C.PottsGrid(3, W, K, 0.4, dtype=cap.F32, has_lower=True)
+    bottom = C.PottsGrid(3, W, K, 0.4, dtype=cap.F32, has_upper=True)
+    for g, rows in ((top, unary[:3]), (bottom, unary[3:])):
+        g.set_unary(rows)
+        g.reset_messages()
+    top.p2p_connect_local(1, bottom)
+    bottom.p2p_connect_local(0, top)
+    top.sweep()
+    top.sweep()  # waits for the sweep counter of `bottom`, which never sweeps
+    with pytest.raises(C.CortexError, match="did not deliver"):
+        top.sync()

@@ -188,10 +188,10 @@ def test_powerlaw_graph_of_config_5_at_full_size(oracle_api):
         f = inc // 2
         nbr_u = edges[f, 1 - (inc % 2)]
         want_marg, want_m2v, want_m2f = _oracle_star(oracle_api, v, nbr_u, ttype[f], K, tables, unary)
-        rows = 2 * f + (inc % 2)
+        side = inc % 2  # get_messages: [factor][endpoint side][K]
         models.assert_values_close(marg[v], want_marg, cap.F32, kind="prob", err_msg=f"marginal of variable {v} (degree {deg[v]})")
-        models.assert_values_close(m2v[rows], want_m2v, cap.F32, kind="prob", err_msg=f"m2v of variable {v} (degree {deg[v]})")
-        models.assert_values_close(m2f[rows], want_m2f, cap.F32, kind="prob", err_msg=f"m2f of variable {v} (degree {deg[v]})")
+        models.assert_values_close(m2v[f, side], want_m2v, cap.F32, kind="prob", err_msg=f"m2v of variable {v} (degree {deg[v]})")
+        models.assert_values_close(m2f[f, side], want_m2f, cap.F32, kind="prob", err_msg=f"m2f of variable {v} (degree {deg[v]})")
 
 
 def test_hmm_k64_of_config_3_at_t_1e5():

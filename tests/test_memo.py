@@ -31,6 +31,7 @@ def _quiet_state(e):
 @pytest.mark.parametrize("resident", ["1", "0"])
 def test_chain_requests_are_replayed(oracle_api, device_api, monkeypatch, resident):
     monkeypatch.setenv("CXB_ENGINE_RESIDENT", resident)
+    monkeypatch.setenv("CXB_PLAN", "0")  # the recorded levels themselves (a chain would otherwise go to k_chain_plan: tests/test_routing.py)
     T = 40
     rng = np.random.Generator(np.random.PCG64(3))
     em = models.make_ssm_model(T, device_api, form="canon", q=0.7, r=1.3)
@@ -102,9 +103,9 @@ def test_a_different_flag_state_is_not_replayed(device_api):
     for _ in range(3):
         models.ssm_set_data(e, y, lik, data)
         C.update_marginals(e, x)
-    assert C.last_schedule(e) == cap.RAN_REPLAY
+    assert C.last_schedule(e) in (cap.RAN_REPLAY, cap.RAN_PLAN)
     sig = [C.get_connection_message_to_factor(e, y[i], lik[i]) for i in range(T)]
     C.set_values(sig[1:], np.stack([data[1:], np.zeros(T - 1)], axis=1))  # y_0 not refreshed
     st = C.update_marginals(e, x)
-    assert C.last_schedule(e) != cap.RAN_REPLAY
+    assert C.last_schedule(e) not in (cap.RAN_REPLAY, cap.RAN_PLAN)
     assert st.updates < 6 * T - 4  # an incomplete request, run by the full schedule

@@ -323,4 +323,4 @@ def test_structured_ssm_device_parity(oracle_api, device_api, dtype):
     assert models.engine_state(md[0])[0] == models.engine_state(mo[0])[0]
     vd = C.get_values([C.get_variable_marginal(C.get_variable(md[0], v)) for v in md[1]])
     vo = C.get_values([C.get_variable_marginal(C.get_variable(mo[0], v)) for v in mo[1]])
-    np.testing.assert_allclose(vd[..., :2], vo[..., :2], rtol=rtol, atol=rtol * 1e-3)
+    models.assert_values_close(vd[..., :2], vo[..., :2], dtype, kind="mp")  # a posterior mean may sit next to zero
