@@ -350,7 +350,11 @@ def workload_config(args, world):
         return {"workload": f"Chung-Lu power-law graph, {args.pl_vars} variables, {2 * args.pl_vars} pairwise factors, K=8, "
                             f"protocol-B sweeps on the {eng} (BASELINE configs[4])", "l2": "inputs exceed L2 at full size",
                 "parallelism": "replicas only"}
-    return {"workload": "1-D Gaussian random-walk chain T=1000 through the generic engine (BASELINE configs[0])",
+    if args.workload == "chains_engine":
+        return {"workload": f"{args.engine_chains} Gaussian random-walk chains x T=1000 as ONE explicit graph through cxb_graph_build + "
+                            f"cxb_update_marginals (the reference's single entry point; cf. gauss_chains for the structured engine)",
+                "l2": "inputs exceed L2", "parallelism": "replicas only"}
+    return {"workload": "1-D Gaussian random-walk chain T=1000 through cxb_graph_build + cxb_update_marginals (BASELINE configs[0])",
             "l2": "fits L2 (latency config)", "parallelism": "replicas only"}
 
 
@@ -610,22 +614,23 @@ def bench_engine_graph(args, pkg, rank, world, local, which):
 
     cap = pkg.capi
     api = pkg.default_api()
-    if which == "chain1k":
+    if which in ("chain1k", "chains_engine"):
+        # B chains of T steps as ONE explicit graph (ids time-major: x[t][b], y[t][b], likelihood[t][b], transition[t][b]):
+        # chain1k = BASELINE configs[0] (B = 1, fp64, latency); chains_engine = a batch through the same single entry point
         T = 1000
+        B = 1 if which == "chain1k" else args.engine_chains
+        edt = cap.F64 if which == "chain1k" else cap.F32
         rng = np.random.Generator(np.random.PCG64(1234))
-        n_ids = 4 * T - 1
+        nx = T * B
+        n_ids = 3 * nx + (T - 1) * B
         is_factor = np.zeros(n_ids, dtype=np.uint8)
-        is_factor[2 * T:] = 1
+        is_factor[2 * nx:] = 1
         ftype = np.zeros(n_ids, dtype=np.int32)
-        ftype[3 * T:] = 1
-        ev, ef = [], []
-        for i in range(T):
-            ev += [T + i, i]
-            ef += [2 * T + i, 2 * T + i]
-        for i in range(T - 1):
-            ev += [i, i + 1]
-            ef += [3 * T + i, 3 * T + i]
-        store = pkg.SignalStore(api, 2, cap.FAMILY_GAUSS_CANON, cap.F64, local)
+        ftype[3 * nx:] = 1
+        xid = np.arange(nx, dtype=np.int64)  # x[t][b] = t * B + b
+        ev = np.concatenate([np.stack([nx + xid, xid], axis=1).ravel(), np.stack([xid[:nx - B], xid[B:]], axis=1).ravel()])
+        ef = np.concatenate([np.repeat(2 * nx + xid, 2), np.repeat(3 * nx + xid[:nx - B], 2)])
+        store = pkg.SignalStore(api, 2, cap.FAMILY_GAUSS_CANON, edt, local)
         ev, ef = np.ascontiguousarray(ev, dtype=np.int64), np.ascontiguousarray(ef, dtype=np.int64)
         store.check(api.graph_build(store.h, n_ids, is_factor.ctypes.data_as(cap.u8p), ftype.ctypes.data_as(cap.i32p), len(ev),
                                     ev.ctypes.data_as(cap.i64p), ef.ctypes.data_as(cap.i64p)))
@@ -633,20 +638,24 @@ def bench_engine_graph(args, pkg, rank, world, local, which):
         store.check(api.register_rule(store.h, 0, cap.RULE_GAUSS_OBS, one.ctypes.data_as(cap.f64p), 1))
         store.check(api.register_rule(store.h, 1, cap.RULE_GAUSS_RW, one.ctypes.data_as(cap.f64p), 1))
         store.check(api.resolve_dependencies(store.h, cap.RESOLVER_DEFAULT_BP))
-        obs_sig = np.ascontiguousarray([api.signal_id(store.h, cap.KIND_M2F, T + i, 2 * T + i) for i in range(T)], dtype=np.int64)
-        vals = np.zeros((T, 2))
-        vals[:, 0] = np.cumsum(rng.standard_normal(T)) + rng.standard_normal(T)
-        xs = np.arange(T, dtype=np.int64)
+        obs_sig = np.ascontiguousarray(2 * nx + 2 * (2 * xid) + 1, dtype=np.int64)  # m2f(y_i, likelihood_i) = n_var + 2c + 1, c = 2i, n_var = 2 nx
+        assert int(obs_sig[5 % nx]) == api.signal_id(store.h, cap.KIND_M2F, nx + 5 % nx, 2 * nx + 5 % nx)
+        vals = np.zeros((nx, 2))
+        vals[:, 0] = (np.cumsum(rng.standard_normal((T, B)), axis=0) + rng.standard_normal((T, B))).ravel()
+        xs = np.ascontiguousarray(xid)
         stats = cap.UpdateStats()
 
         def step():
-            store.check(api.set_values(store.h, T, obs_sig.ctypes.data_as(cap.i64p), vals.ctypes.data_as(cap.f64p), 2))
-            store.check(api.update_marginals(store.h, T, xs.ctypes.data_as(cap.i64p), ctypes.byref(stats)))
+            store.check(api.set_values(store.h, nx, obs_sig.ctypes.data_as(cap.i64p), vals.ctypes.data_as(cap.f64p), 2))
+            store.check(api.update_marginals(store.h, nx, xs.ctypes.data_as(cap.i64p), ctypes.byref(stats)))
 
         step()
-        upd = 6 * T - 4
+        upd = B * (6 * T - 4)
         assert stats.updates == upd, stats.updates
-        alg_bytes, dtype = 0, "f64"
+        # the same algorithmic bytes as the structured engine (64 B fp32 per variable); the index arrays of
+        # the plan kernel come on top
+        alg_bytes, dtype = (0, "f64") if which == "chain1k" else (nx * 64, "f32")
+        unary = vals
     else:
         from tests import models  # graph generator only (numpy); no oracle code is executed
 
@@ -716,17 +725,17 @@ def bench_engine_graph(args, pkg, rank, world, local, which):
     ran = {1: "level schedule", 2: "sequential executor", 3: "memoised level schedule (replay)", 4: "closed-form plan"}.get(
         int(api.last_schedule(store.h)), "?")
     return {"ms": ms, "updates_per_step": upd, "kernel_ms": ms / steps, "alg_bytes": alg_bytes, "e2e_ms": ms, "steps_timed": steps,
-            "e2e_steps": steps, "h2d": int(vals.nbytes) if which == "chain1k" else int(unary.nbytes), "d2h": 0,
+            "e2e_steps": steps, "h2d": int(unary.nbytes), "d2h": 0,
             "launches": launches, "clocks": clocks, "dtype": dtype, "answered_by": ran,
-            "kernel": "generic engine (k_bfs / k_ms_* / k_rule_* / k_apply)", "scaling": "weak",
+            "kernel": "generic engine entry point: k_state_differs + k_chain_plan / k_replay_resident / k_rule_* (memoised), k_bfs / k_apply (first run)", "scaling": "weak",
             "timer": "host wall clock around synchronous ABI calls (each call ends with a stream sync)"}
 
 
 # ---------------------------------------------------------------------------------------------------------------
-WORKLOADS = ["potts_grid", "gauss_chains", "hmm64", "hmm512", "powerlaw", "powerlaw_engine", "chain1k"]
+WORKLOADS = ["potts_grid", "gauss_chains", "hmm64", "hmm512", "powerlaw", "powerlaw_engine", "chain1k", "chains_engine"]
 BENCH_FN = {"gauss_chains": bench_gauss_chains, "potts_grid": bench_potts_grid, "hmm64": bench_hmm64, "hmm512": bench_hmm64,
             "powerlaw": bench_powerlaw, "powerlaw_engine": lambda *a: bench_engine_graph(*a, "powerlaw"),
-            "chain1k": lambda *a: bench_engine_graph(*a, "chain1k")}
+            "chain1k": lambda *a: bench_engine_graph(*a, "chain1k"), "chains_engine": lambda *a: bench_engine_graph(*a, "chains_engine")}
 
 
 def run_workload(args, name, pkg, rank, world, local, main_record):
@@ -781,6 +790,9 @@ def run_workload(args, name, pkg, rank, world, local, main_record):
         try:
             tj = json.loads(traffic_file.read_text())
             rec["roofline"]["traffic"] = tj.get("dram_bytes_per_launch")
+            if rec["roofline"]["traffic"] and tj.get("algorithmic_bytes_per_launch") and r["alg_bytes"]:
+                # the capture was taken on the full single-GPU launch: scale to this launch (a row shard moves its share)
+                rec["roofline"]["traffic"] = rec["roofline"]["traffic"] * r["alg_bytes"] / tj["algorithmic_bytes_per_launch"]
             if "dram_bytes_per_chain_step" in tj:  # HMM workloads: the ncu capture ran fewer time steps
                 rec["roofline"]["traffic"] = tj["dram_bytes_per_chain_step"] * a.hmm_chains * a.hmm_steps
         except Exception:
@@ -812,6 +824,7 @@ def main():
     ap.add_argument("--hmm-chains", type=int, default=1024)
     ap.add_argument("--hmm-steps", type=int, default=100000)
     ap.add_argument("--pl-vars", type=int, default=10000000)
+    ap.add_argument("--engine-chains", type=int, default=4096)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup

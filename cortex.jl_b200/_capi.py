@@ -23,7 +23,9 @@ NIB_INTERMEDIATE, NIB_WEAK, NIB_COMPUTED, NIB_FRESH = 1, 2, 4, 8
 (FAMILY_GAUSS_CANON, FAMILY_CATEGORICAL, FAMILY_GAUSS_MV, FAMILY_BETA, FAMILY_SUM, FAMILY_GAUSS_MP, FAMILY_GAMMA,
  FAMILY_POINT) = range(8)
 (RULE_NONE, RULE_GAUSS_OBS, RULE_GAUSS_RW, RULE_CAT_TABLE, RULE_POTTS, RULE_HMM_EMIT, RULE_GAUSS_MV_OBS,
- RULE_GAUSS_MV_RW, RULE_BETA_BERNOULLI, RULE_SCALE2, RULE_NORMAL_MEAN_FIELD, RULE_NORMAL_STRUCTURED) = range(12)
+ RULE_GAUSS_MV_RW, RULE_BETA_BERNOULLI, RULE_SCALE2, RULE_NORMAL_MEAN_FIELD, RULE_NORMAL_STRUCTURED, RULE_PROGRAM) = range(13)
+(OP_DEP, OP_CONST, OP_PARAM, OP_ADD, OP_SUB, OP_MUL, OP_DIV, OP_NEG, OP_EXP, OP_LOG, OP_SQRT, OP_STORE, OP_TSET, OP_TGET,
+ OP_NDEPS) = range(1, 16)
 RESOLVER_NONE, RESOLVER_DEFAULT_BP, RESOLVER_MEAN_FIELD = range(3)
 SCHEDULE_AUTO, SCHEDULE_LEVEL, SCHEDULE_SEQUENTIAL, RAN_REPLAY, RAN_PLAN = range(5)
 

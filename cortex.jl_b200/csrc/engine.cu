@@ -410,9 +410,79 @@ __device__ __forceinline__ T vmp_var(int fam, const T* v) {
     if (fam == CXB_FAMILY_GAUSS_MV) return v[1];
     return T(0);
 }
+// CXB_RULE_PROGRAM: the user's stack program (include/cortex_b200.h, CXB_OP_*; the oracle's run_program is the same machine).
+// prog = { n_consts, consts..., code... } in the engine dtype, n_prog elements.
+template <class T>
+__device__ bool run_program(const T* __restrict__ prog, int n_prog, const View& e, const T* __restrict__ val, uint32_t off, uint32_t nd, T param,
+                            T* __restrict__ out) {
+    const int dim = e.dim;
+    if (n_prog < 1) return false;
+    const int nc = (int)prog[0];
+    if (nc < 0 || nc + 1 > n_prog) return false;
+    const T* consts = prog + 1;
+    const T* code = consts + nc;
+    const int n_code = n_prog - 1 - nc;
+    T st[16], tmp[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    int sp = 0, pc = 0;
+    while (pc < n_code) {
+        const int op = (int)code[pc++];
+        int a = 0, b = 0;
+        if (op == CXB_OP_DEP || op == CXB_OP_CONST || op == CXB_OP_STORE || op == CXB_OP_TSET || op == CXB_OP_TGET) {
+            if (pc >= n_code) return false;
+            a = (int)code[pc++];
+        }
+        if (op == CXB_OP_DEP) {
+            if (pc >= n_code) return false;
+            b = (int)code[pc++];
+        }
+        switch (op) {
+            case CXB_OP_DEP:
+                if (a < 0 || a >= (int)nd || b < 0 || b >= dim || sp >= 16) return false;
+                st[sp++] = val[(size_t)e.dep_ids[off + a] * dim + b];
+                break;
+            case CXB_OP_CONST:
+                if (a < 0 || a >= nc || sp >= 16) return false;
+                st[sp++] = consts[a];
+                break;
+            case CXB_OP_PARAM:
+                if (sp >= 16) return false;
+                st[sp++] = param;
+                break;
+            case CXB_OP_NDEPS:
+                if (sp >= 16) return false;
+                st[sp++] = (T)nd;
+                break;
+            case CXB_OP_ADD: case CXB_OP_SUB: case CXB_OP_MUL: case CXB_OP_DIV: {
+                if (sp < 2) return false;
+                const T y = st[--sp], x = st[--sp];
+                st[sp++] = op == CXB_OP_ADD ? x + y : op == CXB_OP_SUB ? x - y : op == CXB_OP_MUL ? x * y : x / y;
+                break;
+            }
+            case CXB_OP_NEG: case CXB_OP_EXP: case CXB_OP_LOG: case CXB_OP_SQRT:
+                if (sp < 1) return false;
+                st[sp - 1] = op == CXB_OP_NEG ? -st[sp - 1] : op == CXB_OP_EXP ? exp(st[sp - 1]) : op == CXB_OP_LOG ? log(st[sp - 1]) : sqrt(st[sp - 1]);
+                break;
+            case CXB_OP_STORE:
+                if (a < 0 || a >= dim || a >= 8 || sp < 1) return false;
+                out[a] = st[--sp];
+                break;
+            case CXB_OP_TSET:
+                if (a < 0 || a >= 8 || sp < 1) return false;
+                tmp[a] = st[--sp];
+                break;
+            case CXB_OP_TGET:
+                if (a < 0 || a >= 8 || sp >= 16) return false;
+                st[sp++] = tmp[a];
+                break;
+            default:
+                return false;
+        }
+    }
+    return true;
+}
 template <class T>
 __device__ __forceinline__ void rule_small_one(const View& e, T* __restrict__ val, uint32_t s, int family, int rule,
-                                               const T* __restrict__ fparam, T default_param) {
+                                               const T* __restrict__ fparam, T default_param, const T* __restrict__ prog = nullptr, int n_prog = 0) {
     const int dim = e.dim;
     uint32_t off = e.dep_off[s], nd = e.dep_off[s + 1] - off;
     T acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
@@ -487,6 +557,14 @@ __device__ __forceinline__ void rule_small_one(const View& e, T* __restrict__ va
             case CXB_RULE_SCALE2:
                 for (int k = 0; k < dim; ++k) acc[k] = T(2) * acc[k];
                 break;
+            case CXB_RULE_PROGRAM: {
+                for (int k = 0; k < 8; ++k) acc[k] = T(0);
+                if (!prog || !run_program<T>(prog, n_prog, e, val, off, nd, p, acc)) {
+                    atomicOr(e.err_flag, ERR_RULE_ARG);
+                    return;
+                }
+                break;
+            }
             case CXB_RULE_NORMAL_MEAN_FIELD: {  // test/inference_engine_tests.jl:652-695
                 if (nd != 2 || dim < 2 || !e.sfam) {
                     atomicOr(e.err_flag, ERR_RULE_ARG);
@@ -567,10 +645,10 @@ __device__ __forceinline__ void rule_small_one(const View& e, T* __restrict__ va
 }
 template <class T>
 __global__ void k_rule_small(View e, T* __restrict__ val, const uint32_t* list, uint32_t n, int family, int rule,
-                             const T* __restrict__ fparam, T default_param) {
+                             const T* __restrict__ fparam, T default_param, const T* __restrict__ prog, int n_prog) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n || *(volatile int*)e.err_flag) return;  // refused level: no value is written
-    rule_small_one<T>(e, val, list[i], family, rule, fparam, default_param);
+    rule_small_one<T>(e, val, list[i], family, rule, fparam, default_param, prog, n_prog);
 }
 
 // ---- resident level loop --------------------------------------------------------------------------------------------------
@@ -757,7 +835,9 @@ __global__ void __launch_bounds__(1024) k_update_resident(View e, T* __restrict_
                 for (uint32_t i = tid >> 5; i < cnt; i += NT >> 5)
                     rule_cat_warp<T>(e, val, e.front[base + i], rule, tb, a.key_nsym[k], defp, s_cat_in[tid >> 5]);
             } else {
-                for (uint32_t i = tid; i < cnt; i += NT) rule_small_one<T>(e, val, e.front[base + i], a.family, rule, (const T*)a.fparam, defp);
+                for (uint32_t i = tid; i < cnt; i += NT)
+                    rule_small_one<T>(e, val, e.front[base + i], a.family, rule, (const T*)a.fparam, defp,
+                                      a.key_table[k] >= 0 ? (const T*)a.tables + a.key_table[k] : nullptr, a.key_nsym[k]);
             }
         }
         __syncthreads();
@@ -933,7 +1013,9 @@ __global__ void __launch_bounds__(1024) k_replay_resident(View e, T* __restrict_
             const T* tb = a.key_table[key] >= 0 ? (const T*)a.tables + a.key_table[key] : nullptr;
             for (uint32_t i = tid >> 5; i < cnt; i += NT >> 5) rule_cat_warp<T>(e, val, a.list[off + i], rule, tb, a.key_nsym[key], defp, s_cat_in[tid >> 5]);
         } else {
-            for (uint32_t i = tid; i < cnt; i += NT) rule_small_one<T>(e, val, a.list[off + i], a.family, rule, (const T*)a.fparam, defp);
+            for (uint32_t i = tid; i < cnt; i += NT)
+                rule_small_one<T>(e, val, a.list[off + i], a.family, rule, (const T*)a.fparam, defp,
+                                  a.key_table[key] >= 0 ? (const T*)a.tables + a.key_table[key] : nullptr, a.key_nsym[key]);
         }
     }
 }
@@ -1018,7 +1100,8 @@ __global__ void __launch_bounds__(32) k_seq(View e, T* __restrict__ val, SeqArgs
             const T* tb = a.key_table[key] >= 0 ? (const T*)a.tables + a.key_table[key] : nullptr;
             rule_cat_warp<T>(e, val, s, rule, tb, a.key_nsym[key], defp, s_cat_in);
         } else if (lane == 0) {
-            rule_small_one<T>(e, val, s, a.family, rule, (const T*)a.fparam, defp);
+            rule_small_one<T>(e, val, s, a.family, rule, (const T*)a.fparam, defp, a.key_table[key] >= 0 ? (const T*)a.tables + a.key_table[key] : nullptr,
+                              a.key_nsym[key]);
         }
         __syncwarp();
         if (*(volatile int*)e.err_flag) {
@@ -1658,6 +1741,13 @@ struct DeviceEngine {
                 all.insert(all.end(), r.params.begin(), r.params.end());
                 for (int a = 0; a < dim; ++a)
                     for (int b = 0; b < dim; ++b) all.push_back(r.params[(size_t)b * dim + a]);  // transpose
+            } else if (r.kind == CXB_RULE_PROGRAM) {
+                if (r.params.empty() || r.params[0] < 0 || (size_t)r.params[0] + 1 > r.params.size()) {
+                    err = "PROGRAM needs {n_consts, consts..., code...} parameters";
+                    return CXB_ERR_BAD_ARG;
+                }
+                table_off[kv.first] = {all.size(), r.params.size()};
+                all.insert(all.end(), r.params.begin(), r.params.end());
             } else if (r.kind == CXB_RULE_HMM_EMIT) {
                 if (r.params.empty() || (int64_t)r.params.size() != 1 + (int64_t)dim * (int64_t)r.params[0]) {
                     err = "HMM_EMIT needs {M, E[K][M]} parameters";
@@ -1892,8 +1982,15 @@ struct DeviceEngine {
 #undef CAT_LAUNCH
             } else if (!categorical && !cat_rule) {
                 T defp = (T)((rd && !rd->params.empty()) ? rd->params[0] : 1.0);
+                const T* prog = nullptr;
+                int n_prog = 0;
+                if (rule == CXB_RULE_PROGRAM) {  // default parameter = consts[0]; the program sits with the tables
+                    defp = (T)((rd->params.size() > 1 && rd->params[0] >= 1) ? rd->params[1] : 1.0);
+                    prog = (const T*)d_tables.p + table_off[key_ftype[k - 1]].first;
+                    n_prog = (int)table_off[key_ftype[k - 1]].second;
+                }
                 CXB_LAUNCH(k_rule_small<T>, cdiv(cnt, 256), 256, 0, stream, v, val, list, cnt, family, rule,
-                           (const T*)d_fparam.p, defp);
+                           (const T*)d_fparam.p, defp, prog, n_prog);
             } else {
                 err = "rule kind does not match the engine's value family";
                 return CXB_ERR_BAD_ARG;
@@ -2765,6 +2862,11 @@ struct DeviceEngine {
             if (kind == CXB_RULE_POTTS) h_key_param[k] = std::exp(it->second.params.empty() ? 0.0 : it->second.params[0]) - 1.0;
             if (kind == CXB_RULE_CAT_TABLE || kind == CXB_RULE_HMM_EMIT) h_key_table[k] = (long long)table_off[key_ftype[k - 1]].first;
             if (kind == CXB_RULE_HMM_EMIT) h_key_nsym[k] = (int)it->second.params[0];
+            if (kind == CXB_RULE_PROGRAM) {  // the program lives with the tables; key_nsym carries its length
+                h_key_table[k] = (long long)table_off[key_ftype[k - 1]].first;
+                h_key_nsym[k] = (int)table_off[key_ftype[k - 1]].second;
+                h_key_param[k] = (it->second.params.size() > 1 && it->second.params[0] >= 1) ? it->second.params[1] : 1.0;
+            }
         }
         int32_t st;
         if ((st = up(d_key_rule, h_key_rule.data(), (size_t)nk))) return st;

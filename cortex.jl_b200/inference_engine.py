@@ -103,6 +103,78 @@ class _LazyNeighbours:
         pass
 
 
+class RuleProgram:
+    """A user-defined message-to-variable rule for fixed-size values (``CXB_RULE_PROGRAM``): the counterpart of writing a new
+    method of ``compute_message_to_variable!`` (src/inference_engine.jl:351-361) - a new factor type needs no rebuild of the
+    library. Build the program in postfix order, e.g. the random-walk rule (L, h) -> (L / (1 + q L), h / (1 + q L)):
+
+        p = RuleProgram(default_param=1.0)
+        p.const(1.0).param().dep(0, 0).mul().add().tset(0)          # den = 1 + q * L
+        p.dep(0, 0).tget(0).div().store(0).dep(0, 1).tget(0).div().store(1)
+        RuleProcessor({"transition": p.rule()}, family=FAMILY_GAUSS_CANON, value_dim=2)
+    """
+
+    def __init__(self, default_param: float = 1.0):
+        self.consts: List[float] = [float(default_param)]  # consts[0] is the default of the per-factor parameter
+        self.code: List[float] = []
+
+    def _emit(self, *xs):
+        self.code.extend(float(x) for x in xs)
+        return self
+
+    def dep(self, i, k):
+        return self._emit(capi.OP_DEP, i, k)
+
+    def const(self, c):
+        c = float(c)
+        if c not in self.consts[1:]:
+            self.consts.append(c)
+        return self._emit(capi.OP_CONST, 1 + self.consts[1:].index(c))
+
+    def param(self):
+        return self._emit(capi.OP_PARAM)
+
+    def ndeps(self):
+        return self._emit(capi.OP_NDEPS)
+
+    def add(self):
+        return self._emit(capi.OP_ADD)
+
+    def sub(self):
+        return self._emit(capi.OP_SUB)
+
+    def mul(self):
+        return self._emit(capi.OP_MUL)
+
+    def div(self):
+        return self._emit(capi.OP_DIV)
+
+    def neg(self):
+        return self._emit(capi.OP_NEG)
+
+    def exp(self):
+        return self._emit(capi.OP_EXP)
+
+    def log(self):
+        return self._emit(capi.OP_LOG)
+
+    def sqrt(self):
+        return self._emit(capi.OP_SQRT)
+
+    def store(self, k):
+        return self._emit(capi.OP_STORE, k)
+
+    def tset(self, j):
+        return self._emit(capi.OP_TSET, j)
+
+    def tget(self, j):
+        return self._emit(capi.OP_TGET, j)
+
+    def rule(self) -> Tuple[int, List[float]]:
+        """``(CXB_RULE_PROGRAM, params)`` for a ``RuleProcessor``."""
+        return capi.RULE_PROGRAM, [float(len(self.consts))] + self.consts + self.code
+
+
 @dataclass
 class InferenceEngineWarning:  # src/inference_engine.jl:11-14
     description: str

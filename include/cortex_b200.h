@@ -115,7 +115,26 @@ enum {
      *   m2v <- (m2f of the other state, marginal of the precision): NormalMeanPrecision(mean, 1/(var + 1/w)) (:1013-1020)
      *   m2v <- (JointMarginal): Gamma(1.5, 2 / (V11 - V12 - V21 + V22 + (mu1 - mu2)^2)), V = W^-1      (:1021-1026)
      * with w = mean of the Gamma marginal. */
-    CXB_RULE_NORMAL_STRUCTURED = 11
+    CXB_RULE_NORMAL_STRUCTURED = 11,
+    /* USER-DEFINED rule: a small stack program evaluated per signal, so that a new factor type needs no rebuild of the library
+     * (the counterpart of writing a new method of compute_message_to_variable!, src/inference_engine.jl:351-361, for fixed-size
+     * values, value_dim <= 8). params = { n_consts, consts[n_consts], code... }; code is a sequence of opcodes with their
+     * immediate operands, all stored as doubles (CXB_OP_*). The per-factor parameter (cxb_set_factor_params) defaults to
+     * consts[0]. A program error (stack under/overflow, dependency or component out of range) fails the request with
+     * CXB_ERR_NO_RULE. The oracle evaluates the same program (cortex_oracle.cpp::run_program). */
+    CXB_RULE_PROGRAM = 12
+};
+/* opcodes of CXB_RULE_PROGRAM (stack of 16, 8 temporaries) */
+enum {
+    CXB_OP_DEP = 1,    /* DEP i k   : push component k of dependency i (in add_dependency! order)      */
+    CXB_OP_CONST = 2,  /* CONST j   : push consts[j]                                                      */
+    CXB_OP_PARAM = 3,  /* PARAM     : push the factor's parameter                                         */
+    CXB_OP_ADD = 4, CXB_OP_SUB = 5, CXB_OP_MUL = 6, CXB_OP_DIV = 7, /* a b -> a (op) b                    */
+    CXB_OP_NEG = 8, CXB_OP_EXP = 9, CXB_OP_LOG = 10, CXB_OP_SQRT = 11,
+    CXB_OP_STORE = 12, /* STORE k   : pop -> component k of the result                                    */
+    CXB_OP_TSET = 13,  /* TSET j    : pop -> temporary j                                                  */
+    CXB_OP_TGET = 14,  /* TGET j    : push temporary j                                                    */
+    CXB_OP_NDEPS = 15  /* NDEPS     : push the number of dependencies                                     */
 };
 
 /* ---- dependency resolvers: src/dependencies.jl -------------------------------------------- */

@@ -287,6 +287,70 @@ struct Oracle {
         if (fam == CXB_FAMILY_GAUSS_MV) return v[1];
         return 0.0;
     }
+    bool run_program(const Sig& s, const Rule& r, double* out) {
+        const std::vector<double>& p = r.params;
+        if (p.empty()) return false;
+        const int nc = (int)p[0];
+        if (nc < 0 || (size_t)nc + 1 > p.size()) return false;
+        const double* consts = p.data() + 1;
+        const double* code = consts + nc;
+        const int n_code = (int)p.size() - 1 - nc;
+        const double param = fparam_set[s.fac] ? fparam[s.fac] : (nc > 0 ? consts[0] : 1.0);
+        double st[16], tmp[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        int sp = 0, pc = 0;
+        auto imm = [&](int& v) {
+            if (pc >= n_code) return false;
+            v = (int)code[pc++];
+            return true;
+        };
+        while (pc < n_code) {
+            const int op = (int)code[pc++];
+            int a = 0, b = 0;
+            switch (op) {
+                case CXB_OP_DEP:
+                    if (!imm(a) || !imm(b) || a < 0 || a >= s.ndeps || b < 0 || b >= dim || sp >= 16) return false;
+                    st[sp++] = value(s.deps[a])[b];
+                    break;
+                case CXB_OP_CONST:
+                    if (!imm(a) || a < 0 || a >= nc || sp >= 16) return false;
+                    st[sp++] = consts[a];
+                    break;
+                case CXB_OP_PARAM:
+                    if (sp >= 16) return false;
+                    st[sp++] = param;
+                    break;
+                case CXB_OP_NDEPS:
+                    if (sp >= 16) return false;
+                    st[sp++] = (double)s.ndeps;
+                    break;
+                case CXB_OP_ADD: case CXB_OP_SUB: case CXB_OP_MUL: case CXB_OP_DIV: {
+                    if (sp < 2) return false;
+                    const double y = st[--sp], x = st[--sp];
+                    st[sp++] = op == CXB_OP_ADD ? x + y : op == CXB_OP_SUB ? x - y : op == CXB_OP_MUL ? x * y : x / y;
+                    break;
+                }
+                case CXB_OP_NEG: case CXB_OP_EXP: case CXB_OP_LOG: case CXB_OP_SQRT:
+                    if (sp < 1) return false;
+                    st[sp - 1] = op == CXB_OP_NEG ? -st[sp - 1] : op == CXB_OP_EXP ? std::exp(st[sp - 1]) : op == CXB_OP_LOG ? std::log(st[sp - 1]) : std::sqrt(st[sp - 1]);
+                    break;
+                case CXB_OP_STORE:
+                    if (!imm(a) || a < 0 || a >= dim || sp < 1) return false;
+                    out[a] = st[--sp];
+                    break;
+                case CXB_OP_TSET:
+                    if (!imm(a) || a < 0 || a >= 8 || sp < 1) return false;
+                    tmp[a] = st[--sp];
+                    break;
+                case CXB_OP_TGET:
+                    if (!imm(a) || a < 0 || a >= 8 || sp >= 16) return false;
+                    st[sp++] = tmp[a];
+                    break;
+                default:
+                    return false;
+            }
+        }
+        return true;
+    }
     int32_t rule_m2v(const Sig& s, double* out) {
         const Rule* r = rule_of_factor(s.fac);
         if (!r || r->kind == CXB_RULE_NONE) {
@@ -395,6 +459,14 @@ struct Oracle {
                 }
                 err = "NORMAL_STRUCTURED: unreachable reached";
                 return CXB_ERR_NO_RULE;
+            }
+            case CXB_RULE_PROGRAM: {  // user-defined stack program (include/cortex_b200.h, CXB_OP_*)
+                for (int k = 0; k < dim; ++k) out[k] = 0.0;
+                if (!run_program(s, *r, out)) {
+                    err = "CXB_RULE_PROGRAM: malformed program (stack, dependency or component out of range)";
+                    return CXB_ERR_NO_RULE;
+                }
+                return CXB_OK;
             }
             case CXB_RULE_CAT_TABLE:
             case CXB_RULE_POTTS: {
