@@ -72,6 +72,11 @@ _COMMON = {
     "request_inference": (i32, [vp, i64, i64p]),
     "scan": (i64, [vp, i64p, i64]),
     "update_marginals": (i32, [vp, i64, i64p, C.POINTER(UpdateStats)]),
+    "prepare_signals": (i64, [vp, i64, i64p]),
+    "set_values_prepared": (i32, [vp, i64, vp, i32]),
+    "get_values_prepared": (i32, [vp, i64, vp, i32]),
+    "prepare_request": (i64, [vp, i64, i64p]),
+    "update_marginals_prepared": (i32, [vp, i64, C.POINTER(UpdateStats)]),
     "set_schedule": (i32, [vp, i32]),
     "last_schedule": (i32, [vp]),
     "scan_dfs": (i64, [vp, i64p, i64]),
@@ -84,6 +89,7 @@ _COMMON = {
 
 # structured engines, cxb_ only
 _STRUCTURED = {
+    "stream": (vp, [vp]),
     "version": (C.c_char_p, []),
     "kernel_launches": (C.c_uint64, []),
     "chains_create": (i32, [i32, i32, i64, i64, C.POINTER(vp)]),

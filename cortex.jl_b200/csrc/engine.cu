@@ -1484,6 +1484,7 @@ struct Memo {
     uint64_t last_use = 0;
     size_t bytes = 0;
     int plan = 0;  // 0: replay the recorded levels; > 0: a closed-form plan computes the values (DeviceEngine::run_plan)
+    int64_t prepared = -1;  // recorded from this prepared request (ids need not be compared again)
 };
 template <class T>
 inline void swap_buf(DBuf<T>& a, DBuf<T>& b) {
@@ -1570,6 +1571,9 @@ struct DeviceEngine {
     std::map<int32_t, std::pair<size_t, size_t>> table_off;  // factor type -> (offset, count) in d_tables (elements)
 
     // request
+    const int64_t* req_src = nullptr;
+    bool req_src_prepared = false;
+    int64_t current_prepared = -1;
     std::vector<int64_t> req_ids;
     std::vector<uint32_t> h_req_marg, h_link_off, h_link_ids;
     bool req_uploaded = false;
@@ -1849,6 +1853,7 @@ struct DeviceEngine {
             if ((st = reset_epochs())) return st;
             snap_valid = false;
             memos.clear();  // recorded schedules belong to the old structure
+            lists.clear();  // prepared signal lists too (handles become invalid: prepare again after a structural change)
             chain_plan.tried = chain_plan.ok = false;
             if ((st = build_keys())) return st;
             CXB_CUDA(d_key_count.reserve(512));
@@ -2184,7 +2189,10 @@ struct DeviceEngine {
             err = "request_inference_for: bad id list";
             return CXB_ERR_BAD_ARG;
         }
-        bool same = req_uploaded && (int64_t)req_ids.size() == n && (n == 0 || !std::memcmp(req_ids.data(), ids, n * 8));
+        bool same = req_uploaded && (int64_t)req_ids.size() == n &&
+                    (n == 0 || (ids == req_src && req_src_prepared) || !std::memcmp(req_ids.data(), ids, n * 8));
+        req_src = ids;
+        req_src_prepared = current_prepared >= 0;  // a prepared request's id vector is immutable: same pointer = same ids
         if (!same) {
             // everything is validated and built in temporaries; the cached request is replaced only after a successful upload
             req_uploaded = false;
@@ -2461,6 +2469,7 @@ struct DeviceEngine {
         swap_buf(m.pre_nib, d_snap_nib);
         snap_valid = false;
         m.req_ids.assign(ids, ids + n);
+        m.prepared = current_prepared;
         m.stats = stats;
         for (int k = 0; k < 6; ++k) m.kind_count[k] = h_kind_count.p[k];
         m.last_use = ++memo_clock;
@@ -2705,7 +2714,8 @@ struct DeviceEngine {
         hit = false;
         std::vector<Memo*> cand;
         for (auto& m : memos)
-            if ((int64_t)m->req_ids.size() == n && !std::memcmp(m->req_ids.data(), ids, (size_t)n * 8)) cand.push_back(m.get());
+            if ((int64_t)m->req_ids.size() == n && ((current_prepared >= 0 && m->prepared == current_prepared) || !std::memcmp(m->req_ids.data(), ids, (size_t)n * 8)))
+                cand.push_back(m.get());
         if (cand.empty()) return CXB_OK;
         const size_t N = n_uploaded, NC = csr.nib.size();
         CXB_CUDA(d_memo_flags.reserve(MAX_MEMOS));
@@ -3052,6 +3062,120 @@ struct DeviceEngine {
         if ((st = check_flags())) return st;
         for (int k = 0; k < 6; ++k) stats.updates_by_kind[k] = (int64_t)h_kind_count.p[k];
         return CXB_OK;
+    }
+
+    // ---- prepared signal lists and requests (the "prepare once, run many" form of the bulk calls) ----------------------
+    // cxb_set_values / cxb_update_marginals take host id arrays and float64 values: at 10^6-10^7 signals per call the host
+    // side (id validation, independence test, float64 -> engine dtype, staging, id upload) costs far more than the kernels.
+    // A prepared list / request does that work ONCE and keeps the ids on the device; values then arrive in the engine dtype
+    // from host OR device memory. (The reference's InferenceRequest object, src/inference_engine.jl:265-323, is the same idea.)
+    struct PreparedList {
+        DBuf<uint32_t> ids;
+        uint32_t n = 0;
+    };
+    std::vector<std::unique_ptr<PreparedList>> lists;
+    std::vector<std::vector<int64_t>> prepared_requests;
+    int64_t prepare_list(int64_t n, const int64_t* sids) {
+        if (ensure_device()) return -1;
+        const int64_t N = g.n_sig();
+        if (n <= 0 || !sids) {
+            err = "prepare_signals: empty list";
+            return -1;
+        }
+        if (host_mark.size() < (size_t)N) host_mark.assign((size_t)N, 0);
+        if (++host_mark_tag == 0) {
+            std::fill(host_mark.begin(), host_mark.end(), 0u);
+            host_mark_tag = 1;
+        }
+        std::vector<uint32_t> ids32((size_t)n);
+        for (int64_t i = 0; i < n; ++i) {
+            if (sids[i] < 0 || sids[i] >= N) {
+                err = "prepare_signals: bad signal id";
+                return -1;
+            }
+            if (host_mark[sids[i]] == host_mark_tag) {
+                err = "prepare_signals: a signal appears twice (sequential set_value! semantics need cxb_set_values)";
+                return -1;
+            }
+            host_mark[sids[i]] = host_mark_tag;
+            ids32[i] = (uint32_t)sids[i];
+        }
+        for (int64_t i = 0; i < n; ++i)
+            for (uint32_t k = csr.dep_off[ids32[i]]; k < csr.dep_off[ids32[i] + 1]; ++k)
+                if (host_mark[csr.dep_ids[k]] == host_mark_tag) {
+                    err = "prepare_signals: the signals depend on each other (sequential set_value! semantics need cxb_set_values)";
+                    return -1;
+                }
+        std::unique_ptr<PreparedList> L(new PreparedList());
+        L->n = (uint32_t)n;
+        if (up(L->ids, ids32.data(), ids32.size()) || cudaStreamSynchronize(stream) != cudaSuccess) return -1;
+        lists.push_back(std::move(L));
+        return (int64_t)lists.size() - 1;
+    }
+    // set_value! of every signal of a prepared list: values[n][value_dim] in the ENGINE dtype, host or device memory
+    int32_t set_values_prepared(int64_t list, const void* values, bool on_device) {
+        int32_t st = ensure_device();
+        if (st) return st;
+        if (list < 0 || list >= (int64_t)lists.size() || !values) {
+            err = "set_values_prepared: bad list handle / null values";
+            return CXB_ERR_BAD_ARG;
+        }
+        PreparedList& L = *lists[(size_t)list];
+        const size_t bytes = (size_t)L.n * dim * esz();
+        const void* src = values;
+        if (!on_device) {
+            CXB_CUDA(d_stage_val.reserve(bytes));
+            CXB_CUDA(cudaMemcpyAsync(d_stage_val.p, values, bytes, cudaMemcpyHostToDevice, stream));
+            src = d_stage_val.p;
+        }
+        const unsigned grid = cdiv((size_t)L.n * dim, 256);
+        if (dtype == CXB_F32)
+            CXB_LAUNCH(k_write_values<float>, grid, 256, 0, stream, (float*)d_val.p, dim, L.ids.p, (const float*)src, L.n);
+        else
+            CXB_LAUNCH(k_write_values<double>, grid, 256, 0, stream, (double*)d_val.p, dim, L.ids.p, (const double*)src, L.n);
+        CXB_LAUNCH(k_apply_list, cdiv(L.n, 256), 256, 0, stream, view(), L.ids.p, L.n, req_epoch);
+        if (!on_device) CXB_CUDA(cudaStreamSynchronize(stream));  // the caller's host buffer is free again
+        return CXB_OK;
+    }
+    // get_value of every signal of a prepared list: out[n][value_dim] in the engine dtype, host or device memory
+    int32_t get_values_prepared(int64_t list, void* out, bool on_device) {
+        int32_t st = ensure_device();
+        if (st) return st;
+        if (list < 0 || list >= (int64_t)lists.size() || !out) {
+            err = "get_values_prepared: bad list handle / null output";
+            return CXB_ERR_BAD_ARG;
+        }
+        PreparedList& L = *lists[(size_t)list];
+        const size_t bytes = (size_t)L.n * dim * esz();
+        void* dst = out;
+        if (!on_device) {
+            CXB_CUDA(d_stage_val.reserve(bytes));
+            dst = d_stage_val.p;
+        }
+        const unsigned grid = cdiv((size_t)L.n * dim, 256);
+        if (dtype == CXB_F32)
+            CXB_LAUNCH(k_gather_values<float>, grid, 256, 0, stream, (const float*)d_val.p, dim, L.ids.p, (float*)dst, L.n);
+        else
+            CXB_LAUNCH(k_gather_values<double>, grid, 256, 0, stream, (const double*)d_val.p, dim, L.ids.p, (double*)dst, L.n);
+        if (!on_device) {
+            CXB_CUDA(cudaMemcpyAsync(out, dst, bytes, cudaMemcpyDeviceToHost, stream));
+            CXB_CUDA(cudaStreamSynchronize(stream));
+        }
+        return CXB_OK;
+    }
+    int64_t prepare_request(int64_t n, const int64_t* ids) {
+        if (ensure_device()) return -1;
+        if (n < 0 || (n > 0 && !ids)) {
+            err = "prepare_request: bad id list";
+            return -1;
+        }
+        for (int64_t i = 0; i < n; ++i)
+            if (ids[i] < 0 || ids[i] >= g.n_ids || g.is_factor[ids[i]] || g.marg_of[ids[i]] < 0) {
+                err = "prepare_request: not a variable id";
+                return -1;
+            }
+        prepared_requests.emplace_back(ids, ids + n);
+        return (int64_t)prepared_requests.size() - 1;
     }
 
     // bulk set_value!: sequential semantics; members that depend on each other are applied one by one
@@ -3493,6 +3617,28 @@ int32_t cxb_update_marginals(cxb_engine* h, int64_t n, const int64_t* ids, cxb_u
     if (stats) *stats = E(h)->stats;
     return st;
 } CXB_ABI_CATCH(CXB_ERR_INTERNAL)
+int64_t cxb_prepare_signals(cxb_engine* h, int64_t n, const int64_t* signals) try { return E(h)->prepare_list(n, signals); } CXB_ABI_CATCH(-1)
+int32_t cxb_set_values_prepared(cxb_engine* h, int64_t list, const void* values, int32_t values_on_device) try {
+    return E(h)->set_values_prepared(list, values, values_on_device != 0);
+} CXB_ABI_CATCH(CXB_ERR_INTERNAL)
+int32_t cxb_get_values_prepared(cxb_engine* h, int64_t list, void* out, int32_t out_on_device) try {
+    return E(h)->get_values_prepared(list, out, out_on_device != 0);
+} CXB_ABI_CATCH(CXB_ERR_INTERNAL)
+int64_t cxb_prepare_request(cxb_engine* h, int64_t n, const int64_t* variable_ids) try { return E(h)->prepare_request(n, variable_ids); } CXB_ABI_CATCH(-1)
+int32_t cxb_update_marginals_prepared(cxb_engine* h, int64_t request, cxb_update_stats* stats) try {
+    DeviceEngine* e = E(h);
+    if (request < 0 || request >= (int64_t)e->prepared_requests.size()) {
+        e->err = "update_marginals_prepared: bad request handle";
+        return CXB_ERR_BAD_ARG;
+    }
+    const std::vector<int64_t>& ids = e->prepared_requests[(size_t)request];
+    e->current_prepared = request;
+    int32_t st = e->update((int64_t)ids.size(), ids.data());
+    e->current_prepared = -1;
+    if (stats) *stats = e->stats;
+    return st;
+} CXB_ABI_CATCH(CXB_ERR_INTERNAL)
+void* cxb_stream(cxb_engine* h) { return (void*)E(h)->stream; }
 int32_t cxb_set_schedule(cxb_engine* h, int32_t schedule) try {
     if (schedule < CXB_SCHEDULE_AUTO || schedule > CXB_SCHEDULE_SEQUENTIAL) {
         E(h)->err = "set_schedule: unknown schedule";

@@ -465,14 +465,18 @@ def update_marginals(engine: InferenceEngine, variable_id_or_ids, schedule: str 
     reference, the engine left untouched); ``"seq"``: the sequential loop alone.
     Returns the per-call statistics (the reference returns ``nothing``).
     """
-    ids = _as_ids(variable_id_or_ids)
-    arr, p = _ids(ids)
+    prepared = variable_id_or_ids if isinstance(variable_id_or_ids, PreparedRequest) else None
+    ids = prepared.variable_ids if prepared else _as_ids(variable_id_or_ids)
     stats = capi.UpdateStats()
     engine.store.check(engine.api.set_schedule(engine.store.h, SCHEDULES[schedule]))
     engine._callback_error = None
     before = _snapshot(engine) if engine.tracer is not None else None
     t0 = time.perf_counter_ns()
-    status = engine.api.update_marginals(engine.store.h, len(ids), p, C.byref(stats))
+    if prepared:
+        status = engine.api.update_marginals_prepared(engine.store.h, prepared.handle, C.byref(stats))
+    else:
+        arr, p = _ids(ids)
+        status = engine.api.update_marginals(engine.store.h, len(ids), p, C.byref(stats))
     t1 = time.perf_counter_ns()
     if status != capi.OK and getattr(engine, "_callback_error", None) is not None:
         raise engine._callback_error
@@ -480,6 +484,72 @@ def update_marginals(engine: InferenceEngine, variable_id_or_ids, schedule: str 
     if engine.tracer is not None:
         engine.tracer.inference_requests.append(_collect_trace(engine, ids, t1 - t0, before))
     return stats
+
+
+class PreparedSignals:
+    """Handle of ``prepare_signals`` (``cxb_prepare_signals``)."""
+
+    def __init__(self, engine, handle, n):
+        self.engine, self.handle, self.n = engine, int(handle), int(n)
+
+
+class PreparedRequest:
+    """Handle of ``prepare_request`` (``cxb_prepare_request``): the ids of an inference request, validated once."""
+
+    def __init__(self, engine, handle, ids):
+        self.engine, self.handle, self.variable_ids = engine, int(handle), tuple(ids)
+
+
+def engine_np_dtype(engine: InferenceEngine):
+    return np.float32 if engine.store.dtype == capi.F32 else np.float64
+
+
+def prepare_signals(engine: InferenceEngine, signals: Sequence[Signal]) -> PreparedSignals:
+    """Validate and upload a list of signals once; ``set_values_prepared`` then sets all of them per call without any per-call
+    host work on ids. The signals must be distinct and must not depend on each other (e.g. all observations)."""
+    arr, p = _ids([s.sid for s in signals])
+    h = engine.api.prepare_signals(engine.store.h, len(arr), p)
+    if h < 0:
+        engine.store.check(capi.ERR_BAD_ARG)
+    return PreparedSignals(engine, h, len(arr))
+
+
+def set_values_prepared(prepared: PreparedSignals, values, device_pointer: Optional[int] = None) -> None:
+    """Bulk ``set_value!`` of a prepared list. ``values``: array ``[n][value_dim]`` (converted to the engine dtype if needed);
+    or pass ``device_pointer`` (engine dtype, same layout, device memory): the call is then asynchronous on the engine's
+    stream and nothing crosses the host."""
+    e = prepared.engine
+    if device_pointer is not None:
+        e.store.check(e.api.set_values_prepared(e.store.h, prepared.handle, C.c_void_p(int(device_pointer)), 1))
+        return
+    v = np.ascontiguousarray(np.asarray(values).reshape(prepared.n, -1), dtype=engine_np_dtype(e) if e.api.is_device else np.float64)
+    if v.shape[1] != e.store.value_dim:
+        w = np.zeros((prepared.n, e.store.value_dim), dtype=v.dtype)
+        w[:, : v.shape[1]] = v
+        v = w
+    e.store.check(e.api.set_values_prepared(e.store.h, prepared.handle, v.ctypes.data_as(C.c_void_p), 0))
+
+
+def get_values_prepared(prepared: PreparedSignals, device_pointer: Optional[int] = None):
+    """Bulk ``get_value`` of a prepared list in the engine dtype: returns ``[n][value_dim]`` (or fills ``device_pointer``)."""
+    e = prepared.engine
+    if device_pointer is not None:
+        e.store.check(e.api.get_values_prepared(e.store.h, prepared.handle, C.c_void_p(int(device_pointer)), 1))
+        return None
+    out = np.zeros((prepared.n, e.store.value_dim), dtype=engine_np_dtype(e) if e.api.is_device else np.float64)
+    e.store.check(e.api.get_values_prepared(e.store.h, prepared.handle, out.ctypes.data_as(C.c_void_p), 0))
+    return out
+
+
+def prepare_request(engine: InferenceEngine, variable_id_or_ids) -> PreparedRequest:
+    """The ids of a request, validated once (``update_marginals(engine, prepared_request)``): the counterpart of keeping the
+    reference's ``InferenceRequest`` object (src/inference_engine.jl:265-323) around."""
+    ids = _as_ids(variable_id_or_ids)
+    arr, p = _ids(ids)
+    h = engine.api.prepare_request(engine.store.h, len(ids), p)
+    if h < 0:
+        engine.store.check(capi.ERR_BAD_ARG)
+    return PreparedRequest(engine, h, ids)
 
 
 def last_schedule(engine: InferenceEngine) -> int:

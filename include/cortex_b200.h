@@ -253,6 +253,20 @@ int64_t cxb_scan(cxb_engine* h, int64_t* out_signals, int64_t cap);
 /* update_marginals!(engine, ids), src/inference_engine.jl:559-632 — level-synchronous schedule
  * (SURVEY Appendix A.5). stats may be NULL. */
 int32_t cxb_update_marginals(cxb_engine* h, int64_t n, const int64_t* variable_ids, cxb_update_stats* stats);
+/* "Prepare once, run many" forms of the two bulk calls. cxb_set_values / cxb_update_marginals take host id arrays and
+ * float64 values; at 10^6..10^7 signals per call that host work dwarfs the kernels. A prepared signal list / request
+ * validates and uploads its ids ONCE (the reference's InferenceRequest object, src/inference_engine.jl:265-323, is the same
+ * idea); values then come in the ENGINE dtype, [n][value_dim] contiguous, from host memory or (values_on_device != 0) from
+ * device memory - in which case the call is asynchronous on the engine's stream (cxb_stream). The signals of a list must be
+ * distinct and must not depend on each other (bulk set_value! of independent signals, e.g. all observations). Handles
+ * (>= 0; -1 on error) stay valid until the structure changes. */
+int64_t cxb_prepare_signals(cxb_engine* h, int64_t n, const int64_t* signals);
+int32_t cxb_set_values_prepared(cxb_engine* h, int64_t list, const void* values, int32_t values_on_device);
+int32_t cxb_get_values_prepared(cxb_engine* h, int64_t list, void* out, int32_t out_on_device);
+int64_t cxb_prepare_request(cxb_engine* h, int64_t n, const int64_t* variable_ids);
+int32_t cxb_update_marginals_prepared(cxb_engine* h, int64_t request, cxb_update_stats* stats);
+/* the CUDA stream the engine launches on (cudaStream_t as void*) */
+void* cxb_stream(cxb_engine* h);
 /* schedule selection (see CXB_SCHEDULE_*) and which path answered the last request */
 int32_t cxb_set_schedule(cxb_engine* h, int32_t schedule);
 int32_t cxb_last_schedule(cxb_engine* h);

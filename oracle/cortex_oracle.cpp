@@ -92,6 +92,7 @@ struct Oracle {
     rule_cb_t cb = nullptr;
     void* cb_user = nullptr;
     std::vector<int64_t> warnings;
+    std::vector<std::vector<int64_t>> lists, prepared;  // cxo_prepare_signals / cxo_prepare_request
     // request state, src/inference_engine.jl:265-270
     std::vector<int64_t> req_ids, req_marg;
     std::vector<uint8_t> ready;
@@ -1336,6 +1337,46 @@ int64_t cxo_scan(void* h, int64_t* out, int64_t cap) {
     for (int64_t i = 0; i < (int64_t)v.size() && i < cap; ++i) out[i] = v[i];
     return (int64_t)v.size();
 }
+// prepared signal lists / requests (include/cortex_b200.h): the oracle's engine dtype is float64
+int64_t cxo_prepare_signals(void* h, int64_t n, const int64_t* signals) {
+    Oracle* o = O(h);
+    if (n <= 0 || !signals) return -1;
+    std::unordered_set<int64_t> seen;
+    for (int64_t i = 0; i < n; ++i) {
+        if (signals[i] < 0 || signals[i] >= (int64_t)o->sig.size() || !seen.insert(signals[i]).second) {
+            o->err = "prepare_signals: bad or repeated signal id";
+            return -1;
+        }
+    }
+    for (int64_t i = 0; i < n; ++i)
+        for (int64_t d : o->sig[signals[i]].deps)
+            if (seen.count(d)) {
+                o->err = "prepare_signals: the signals depend on each other (sequential set_value! semantics need cxb_set_values)";
+                return -1;
+            }
+    o->lists.emplace_back(signals, signals + n);
+    return (int64_t)o->lists.size() - 1;
+}
+int32_t cxo_set_values_prepared(void* h, int64_t list, const void* values, int32_t /*values_on_device*/) {
+    Oracle* o = O(h);
+    if (list < 0 || list >= (int64_t)o->lists.size() || !values) return CXB_ERR_BAD_ARG;
+    const std::vector<int64_t>& L = o->lists[(size_t)list];
+    for (size_t i = 0; i < L.size(); ++i) o->set_value(L[i], (const double*)values + i * o->dim);
+    return CXB_OK;
+}
+int32_t cxo_get_values_prepared(void* h, int64_t list, void* out, int32_t /*out_on_device*/) {
+    Oracle* o = O(h);
+    if (list < 0 || list >= (int64_t)o->lists.size() || !out) return CXB_ERR_BAD_ARG;
+    const std::vector<int64_t>& L = o->lists[(size_t)list];
+    for (size_t i = 0; i < L.size(); ++i) std::memcpy((double*)out + i * o->dim, o->value(L[i]), sizeof(double) * o->dim);
+    return CXB_OK;
+}
+int64_t cxo_prepare_request(void* h, int64_t n, const int64_t* ids) {
+    Oracle* o = O(h);
+    if (n < 0 || (n > 0 && !ids)) return -1;
+    o->prepared.emplace_back(ids, ids + n);
+    return (int64_t)o->prepared.size() - 1;
+}
 // cxb_set_schedule: AUTO / SEQUENTIAL = the reference's own loop (seq), LEVEL = the level-synchronous schedule
 int32_t cxo_set_schedule(void* h, int32_t schedule) {
     if (schedule < CXB_SCHEDULE_AUTO || schedule > CXB_SCHEDULE_SEQUENTIAL) return CXB_ERR_BAD_ARG;
@@ -1347,6 +1388,12 @@ int32_t cxo_update_marginals(void* h, int64_t n, const int64_t* ids, cxb_update_
     int32_t st = O(h)->schedule == CXB_SCHEDULE_LEVEL ? O(h)->update_lvl(n, ids) : O(h)->update_seq(n, ids);
     if (stats) *stats = O(h)->stats;
     return st;
+}
+int32_t cxo_update_marginals_prepared(void* h, int64_t request, cxb_update_stats* stats) {
+    Oracle* o = O(h);
+    if (request < 0 || request >= (int64_t)o->prepared.size()) return CXB_ERR_BAD_ARG;
+    const std::vector<int64_t> ids = o->prepared[(size_t)request];
+    return cxo_update_marginals(h, (int64_t)ids.size(), ids.data(), stats);
 }
 int32_t cxo_update_marginals_seq(void* h, int64_t n, const int64_t* ids, cxb_update_stats* stats) {
     int32_t st = O(h)->update_seq(n, ids);

@@ -89,3 +89,40 @@ def test_chain_plan_follows_changed_noise_parameters(oracle_api, device_api):
     got = C.get_values([C.get_variable_marginal(C.get_variable(ep[0], v)) for c in ep[1] for v in c])
     want = C.get_values([C.get_variable_marginal(C.get_variable(eo[0], v)) for c in eo[1] for v in c])
     models.assert_values_close(got, want, cap.F64, kind="canon")
+
+
+@pytest.mark.parametrize("which", ["oracle", "device"])
+def test_prepared_lists_and_requests(oracle_api, device_api, which):
+    """cxb_prepare_signals / cxb_set_values_prepared / cxb_prepare_request / cxb_update_marginals_prepared leave exactly what
+    the per-call forms leave (host values; on the device also values taken from a device buffer)."""
+    import torch
+
+    api = oracle_api if which == "oracle" else device_api
+    lengths = [20] * 6
+    a = models.make_ssm_batch_model(lengths, api)
+    b = models.make_ssm_batch_model(lengths, api)
+    sig = lambda m: [C.get_connection_message_to_factor(m[0], m[2][c][t], m[3][c][t]) for c in range(6) for t in range(20)]  # noqa: E731
+    ids = lambda m: [v for chain in m[1] for v in chain]  # noqa: E731
+    plist, preq = C.prepare_signals(b[0], sig(b)), C.prepare_request(b[0], ids(b))
+    rng = np.random.Generator(np.random.PCG64(9))
+    for rep in range(4):
+        vals = np.stack([rng.standard_normal(120), np.zeros(120)], axis=1)
+        C.set_values(sig(a), vals)
+        C.update_marginals(a[0], ids(a))
+        if which == "device" and rep % 2 == 1:  # from device memory
+            dev = torch.tensor(vals, dtype=torch.float64, device="cuda")
+            torch.cuda.synchronize()
+            C.set_values_prepared(plist, None, device_pointer=dev.data_ptr())
+        else:
+            C.set_values_prepared(plist, vals)
+        C.update_marginals(b[0], preq)
+    sa, va = models.engine_state(a[0])
+    sb, vb = models.engine_state(b[0])
+    assert sa == sb
+    np.testing.assert_array_equal(va, vb)
+    marg = C.prepare_signals(b[0], [C.get_variable_marginal(C.get_variable(b[0], v)) for v in ids(b)])
+    np.testing.assert_array_equal(C.get_values_prepared(marg), C.get_values([C.get_variable_marginal(C.get_variable(a[0], v)) for v in ids(a)]))
+    if which == "device":
+        assert C.last_schedule(b[0]) == cap.RAN_PLAN
+    with pytest.raises(ValueError):
+        C.prepare_signals(b[0], sig(b)[:3] + sig(b)[:1])  # a repeated signal
