@@ -119,6 +119,7 @@ _STRUCTURED = {
     "grid_p2p_connect_ipc": (i32, [vp, i32, vp]),
     "grid_p2p_connect_local": (i32, [vp, i32, vp]),
     "grid_get_marginals": (i32, [vp, vp]),
+    "grid_infer_host": (i32, [vp, vp, vp, i32, i64p]),
     "grid_get_messages": (i32, [vp, i32, vp]),
     "grid_stream": (vp, [vp]),
     "grid_last_kernel_ms": (i32, [vp, C.POINTER(C.c_float)]),

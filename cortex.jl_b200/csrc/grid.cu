@@ -238,6 +238,13 @@ struct Grid {
     std::string err;
     DBuf<unsigned char> unary, m2f[2], m2v, marg, halo_recv;  // m2f[b]: 4 planes; m2v: 4 planes; halo_recv: [2 parities][2 rows]
     DBuf<unsigned> flags;                       // [0] sweeps completed by the upper neighbour, [1] by the lower neighbour
+    // pipelined host entry point (infer_host): job j uses unary buffer j & 1 and marginal buffer j & 1, so that the evidence of
+    // job j + 1 travels host -> device and the marginals of job j - 1 device -> host while the sweeps of job j run
+    DBuf<unsigned char> unary_alt, marg_alt;
+    unsigned char *cur_unary = nullptr, *cur_marg = nullptr;  // what sweep() reads / writes (default: unary.p / marg.p)
+    cudaStream_t s_in = nullptr, s_out = nullptr;
+    cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_sw[2] = {nullptr, nullptr}, ev_out[2] = {nullptr, nullptr};
+    unsigned long long job_no = 0;
     unsigned sweep_no = 0;                      // sweeps since the last reset (parity of the halo buffers)
     unsigned long long halo_timeout_ns = 20ull * 1000000000ull;  // CXB_GRID_HALO_TIMEOUT_MS overrides (tests)
     // after a stream sync: did a halo wait give up on a neighbour?
@@ -262,6 +269,13 @@ struct Grid {
             if (q) cudaIpcCloseMemHandle(q);
         if (ev0) cudaEventDestroy(ev0);
         if (ev1) cudaEventDestroy(ev1);
+        for (int i = 0; i < 2; ++i) {
+            if (ev_in[i]) cudaEventDestroy(ev_in[i]);
+            if (ev_sw[i]) cudaEventDestroy(ev_sw[i]);
+            if (ev_out[i]) cudaEventDestroy(ev_out[i]);
+        }
+        if (s_in) cudaStreamDestroy(s_in);
+        if (s_out) cudaStreamDestroy(s_out);
         if (stream) cudaStreamDestroy(stream);
     }
     int32_t init() {
@@ -346,13 +360,13 @@ struct Grid {
         g.W = W;
         g.has_up = has_up;
         g.has_down = has_down;
-        g.unary = unary.p;
+        g.unary = cur_unary ? cur_unary : unary.p;
         for (int d = 0; d < 4; ++d) {
             g.m2f_cur[d] = m2f[cur].p + (size_t)d * plane();
             g.m2f_nxt[d] = m2f[cur ^ 1].p + (size_t)d * plane();
             g.m2v[d] = m2v.p + (size_t)d * plane();
         }
-        g.marg = marg.p;
+        g.marg = cur_marg ? cur_marg : marg.p;
         // halo buffers are double buffered by sweep parity: sweep s reads parity s & 1 (written by the neighbours' sweep
         // s - 1, or by the caller's exchange) and pushes its own boundary rows into the neighbours' parity (s + 1) & 1
         const size_t par = (size_t)(sweep_no & 1) * 2 * row(), nxt_par = (size_t)((sweep_no + 1) & 1) * 2 * row();
@@ -383,6 +397,60 @@ struct Grid {
             *n_updates = 2 * (vert + horz) + H * W;  // m2v + m2f + marginals
         }
         return CXB_OK;
+    }
+    // Host entry point of one JOB: evidence from (pinned) host memory, n_sweeps synchronous sweeps, marginals back to host
+    // memory - asynchronous and pipelined over three streams: the call returns once everything is enqueued; the host -> device
+    // copy of the NEXT job's evidence and the device -> host copy of the PREVIOUS job's marginals overlap this job's sweeps.
+    // marginals_out_host of job j is complete when cxb_grid_sync returns (or after two further jobs). The messages carry
+    // over from the previous job (no reset: with a fused halo a reset needs every shard idle).
+    int32_t infer_host(const void* unary_host, void* marg_out_host, int n_sweeps, int64_t* n_updates) {
+        if (!have_msgs) {
+            err = "reset the messages first";
+            return CXB_ERR_STATE;
+        }
+        CXB_CUDA(cudaSetDevice(device));
+        if (!s_in) {
+            CXB_CUDA(unary_alt.reserve(plane()));
+            CXB_CUDA(marg_alt.reserve(plane()));
+            CXB_CUDA(cudaStreamCreateWithFlags(&s_in, cudaStreamNonBlocking));
+            CXB_CUDA(cudaStreamCreateWithFlags(&s_out, cudaStreamNonBlocking));
+            for (int i = 0; i < 2; ++i) {
+                CXB_CUDA(cudaEventCreateWithFlags(&ev_in[i], cudaEventDisableTiming));
+                CXB_CUDA(cudaEventCreateWithFlags(&ev_sw[i], cudaEventDisableTiming));
+                CXB_CUDA(cudaEventCreateWithFlags(&ev_out[i], cudaEventDisableTiming));
+            }
+            CXB_CUDA(cudaStreamSynchronize(stream));  // earlier set_unary / sweeps on the compute stream are done
+        }
+        const int b = (int)(job_no & 1);
+        unsigned char* U = b ? unary_alt.p : unary.p;
+        unsigned char* M = b ? marg_alt.p : marg.p;
+        if (job_no >= 2) CXB_CUDA(cudaStreamWaitEvent(s_in, ev_sw[b], 0));  // the sweeps of job j - 2 have read this evidence buffer
+        CXB_CUDA(cudaMemcpyAsync(U, unary_host, plane(), cudaMemcpyHostToDevice, s_in));
+        CXB_CUDA(cudaEventRecord(ev_in[b], s_in));
+        CXB_CUDA(cudaStreamWaitEvent(stream, ev_in[b], 0));
+        if (job_no >= 2) CXB_CUDA(cudaStreamWaitEvent(stream, ev_out[b], 0));  // job j - 2's marginals have left this buffer
+        cur_unary = U;
+        cur_marg = M;
+        have_unary = true;
+        int64_t upd = 0;
+        for (int k = 0; k < n_sweeps; ++k) {
+            int32_t st = sweep(&upd);
+            if (st) return st;
+        }
+        CXB_CUDA(cudaEventRecord(ev_sw[b], stream));
+        CXB_CUDA(cudaStreamWaitEvent(s_out, ev_sw[b], 0));
+        CXB_CUDA(cudaMemcpyAsync(marg_out_host, M, plane(), cudaMemcpyDeviceToHost, s_out));
+        CXB_CUDA(cudaEventRecord(ev_out[b], s_out));
+        ++job_no;
+        if (n_updates) *n_updates = upd * n_sweeps;
+        return CXB_OK;
+    }
+    int32_t sync_all() {
+        CXB_CUDA(cudaSetDevice(device));
+        CXB_CUDA(cudaStreamSynchronize(stream));
+        if (s_in) CXB_CUDA(cudaStreamSynchronize(s_in));
+        if (s_out) CXB_CUDA(cudaStreamSynchronize(s_out));
+        return check_halo();
     }
 };
 
@@ -433,7 +501,7 @@ const char* cxb_grid_last_error(cxb_grid* g) { return g ? GR(g)->err.c_str() : "
 int32_t cxb_grid_set_unary(cxb_grid* g, const void* unary_host) try {
     Grid* h = GR(g);
     GR_CUDA(g, cudaSetDevice(h->device));
-    GR_CUDA(g, cudaMemcpyAsync(h->unary.p, unary_host, h->plane(), cudaMemcpyHostToDevice, h->stream));
+    GR_CUDA(g, cudaMemcpyAsync(h->cur_unary ? h->cur_unary : h->unary.p, unary_host, h->plane(), cudaMemcpyHostToDevice, h->stream));
     GR_CUDA(g, cudaStreamSynchronize(h->stream));
     h->have_unary = true;
     return CXB_OK;
@@ -507,7 +575,7 @@ int64_t cxb_grid_halo_elems(cxb_grid* g) try { return GR(g)->W * GR(g)->K; } CXB
 int32_t cxb_grid_get_marginals(cxb_grid* g, void* out_host) try {
     Grid* h = GR(g);
     GR_CUDA(g, cudaSetDevice(h->device));
-    GR_CUDA(g, cudaMemcpyAsync(out_host, h->marg.p, h->plane(), cudaMemcpyDeviceToHost, h->stream));
+    GR_CUDA(g, cudaMemcpyAsync(out_host, h->cur_marg ? h->cur_marg : h->marg.p, h->plane(), cudaMemcpyDeviceToHost, h->stream));
     GR_CUDA(g, cudaStreamSynchronize(h->stream));
     return h->check_halo();
 } CXB_ABI_CATCH(CXB_ERR_INTERNAL)
@@ -535,9 +603,11 @@ int32_t cxb_grid_last_kernel_ms(cxb_grid* g, float* ms_out) try {
     GR_CUDA(g, cudaEventElapsedTime(ms_out, h->ev0, h->ev1));
     return CXB_OK;
 } CXB_ABI_CATCH(CXB_ERR_INTERNAL)
+int32_t cxb_grid_infer_host(cxb_grid* g, const void* unary_host, void* marginals_out_host, int32_t n_sweeps, int64_t* n_updates_out) try {
+    return GR(g)->infer_host(unary_host, marginals_out_host, n_sweeps, n_updates_out);
+} CXB_ABI_CATCH(CXB_ERR_INTERNAL)
 int32_t cxb_grid_sync(cxb_grid* g) try {
-    GR_CUDA(g, cudaStreamSynchronize(GR(g)->stream));
-    return GR(g)->check_halo();
+    return GR(g)->sync_all();
 } CXB_ABI_CATCH(CXB_ERR_INTERNAL)
 
 }  // extern "C"

@@ -140,6 +140,13 @@ class PottsGrid(_Handle):
         self.check(self.api.grid_get_marginals(self.h, out.ctypes.data))
         return out
 
+    def infer_host(self, unary_ptr: int, marginals_out_ptr: int, n_sweeps: int) -> int:
+        """One job through (pinned) host buffers, asynchronous and pipelined across calls (``cxb_grid_infer_host``): the
+        results are complete after ``sync()``."""
+        n = C.c_int64()
+        self.check(self.api.grid_infer_host(self.h, C.c_void_p(int(unary_ptr)), C.c_void_p(int(marginals_out_ptr)), int(n_sweeps), C.byref(n)))
+        return int(n.value)
+
     def get_messages(self, which: int):
         out = np.empty((self.H, self.W, self.K), dtype=self.np_dtype)
         self.check(self.api.grid_get_messages(self.h, which, out.ctypes.data))

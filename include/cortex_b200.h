@@ -361,6 +361,12 @@ int32_t cxb_grid_p2p_connect_ipc(cxb_grid* g, int32_t direction, const void* nei
 int32_t cxb_grid_p2p_connect_local(cxb_grid* g, int32_t direction, cxb_grid* neighbour);
 /* marginals [rows][cols][K] engine dtype, D2H */
 int32_t cxb_grid_get_marginals(cxb_grid* g, void* out_host);
+/* One JOB through host buffers (the e2e path of config 4): unary evidence [rows][cols][K] from (pinned) host memory, n_sweeps
+ * synchronous sweeps, marginals back to (pinned) host memory. Asynchronous and pipelined over three streams: the call returns
+ * when everything is enqueued; the evidence of the next job travels in and the marginals of the previous job travel out
+ * while this job's sweeps run (two evidence and two marginal buffers). marginals_out_host is complete when cxb_grid_sync
+ * returns. Messages carry over from the previous job (call cxb_grid_reset_messages, all shards idle, for a cold start). */
+int32_t cxb_grid_infer_host(cxb_grid* g, const void* unary_host, void* marginals_out_host, int32_t n_sweeps, int64_t* n_updates_out);
 /* message planes for parity: which = 0..3 m2v from the (up,left,right,down) factor, 4..7 m2f to them; D2H */
 int32_t cxb_grid_get_messages(cxb_grid* g, int32_t which, void* out_host);
 void* cxb_grid_stream(cxb_grid* g);

@@ -746,3 +746,31 @@ def test_potts_grid_halo_wait_is_bounded(monkeypatch):
     top.sweep()  # waits for the sweep counter of `bottom`, which never sweeps
     with pytest.raises(C.CortexError, match="did not deliver"):
         top.sync()
+
+
+def test_potts_grid_pipelined_host_jobs_equal_the_plain_calls():
+    """cxb_grid_infer_host: evidence in, sweeps, marginals out, pipelined over three streams across jobs - bit-identical to
+    set_unary / sweep / get_marginals one after the other (the messages carry over from job to job in both)."""
+    import torch
+
+    H, W, K, sweeps, jobs = 37, 29, 16, 3, 5
+    rng = np.random.Generator(np.random.PCG64(21))
+    unaries = [rng.dirichlet(np.ones(K), size=(H, W)).astype(np.float32) for _ in range(jobs)]
+    plain = C.PottsGrid(H, W, K, 0.7, dtype=cap.F32)
+    plain.reset_messages()
+    want = []
+    for u in unaries:
+        plain.set_unary(u)
+        for _ in range(sweeps):
+            plain.sweep()
+        want.append(plain.get_marginals())
+    piped = C.PottsGrid(H, W, K, 0.7, dtype=cap.F32)
+    piped.reset_messages()
+    host_in = [torch.from_numpy(u).pin_memory() for u in unaries]
+    host_out = [torch.empty((H, W, K), dtype=torch.float32).pin_memory() for _ in range(jobs)]
+    for j in range(jobs):  # nothing waits between the calls
+        assert piped.infer_host(host_in[j].data_ptr(), host_out[j].data_ptr(), sweeps) > 0
+    piped.sync()
+    for j in range(jobs):
+        assert np.array_equal(host_out[j].numpy(), want[j]), f"job {j}"
+    assert np.array_equal(piped.get_marginals(), want[-1])
