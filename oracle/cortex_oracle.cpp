@@ -722,6 +722,11 @@ struct Oracle {
         trace.clear();
     }
 
+    // On wirings with cycles of listening dependencies the reference's `while should_continue` loop (:575-608) need not end:
+    // every round recomputes signals that make each other pending again. The reference would hang; the oracle and the device's
+    // sequential executor stop after this many executions and report CXB_ERR_STATE (a terminating request recomputes a signal
+    // a handful of times at most).
+    int64_t seq_execution_cap() const { return 8 * (int64_t)sig.size() + 4096; }
     // update_marginals!, :559-632 — sequential, in place (the reference schedule)
     int32_t update_seq(int64_t n, const int64_t* ids) {
         reset_stats();
@@ -740,6 +745,12 @@ struct Oracle {
                 bool processed = process_dependencies(req_marg[i], true, [&](int64_t d) {  // :512-525
                     if (fail) return false;
                     if (is_pending(d)) {
+                        if (stats.updates > seq_execution_cap()) {  // the reference loop itself would never return (see below)
+                            err = "update_marginals!: the sequential loop does not terminate on this request (signals keep refreshing "
+                                  "each other round after round)";
+                            fail = CXB_ERR_STATE;
+                            return false;
+                        }
                         const int64_t t0 = now_ns();
                         int32_t s2 = compute(d, false, false);
                         if (s2) {
@@ -817,6 +828,11 @@ struct Oracle {
     // Strict refusal rules A / B / D / E of the level schedule: on by default on the oracle and on the
     // device alike; CXO_STRICT_FRESHNESS=0 restores the round-1 rules (kept for tests/fuzz_strict_cost.py).
     bool strict_freshness = !(std::getenv("CXO_STRICT_FRESHNESS") && std::atoi(std::getenv("CXO_STRICT_FRESHNESS")) == 0);
+    std::unordered_set<int64_t> linked_requested;  // linked signals of the requested variables (rule G)
+    bool strong_beneath_done = false, waits_on_leaf = false;
+    // EXPERIMENT, off by default and oracle-only (tests/fuzz_bp_graphs.py documents what it buys): rule G, CXO_RULE_G=2. The device
+    // does not need it: AUTO certifies every recorded level schedule against the sequential executor.
+    int rule_g = std::getenv("CXO_RULE_G") ? std::atoi(std::getenv("CXO_RULE_G")) : 0;
     int schedule = CXB_SCHEDULE_AUTO;  // cxo_set_schedule: AUTO and SEQUENTIAL = the reference loop, LEVEL = update_lvl
     bool has_weak_dep = false;    // any weak dependency in the graph (the device allocates its probe marks only then)
     int64_t lvl_request = 0;      // > 0 while a strict level-schedule request runs (its serial number)
@@ -862,6 +878,10 @@ struct Oracle {
                 }
         }
         std::vector<uint8_t> done(sig.size(), 0), inF(sig.size(), 0);
+        linked_requested.clear();
+        strong_beneath_done = false;
+        for (int64_t i = 0; i < n; ++i)
+            for (int64_t l : linked[req_ids[i]]) linked_requested.insert(l);
         int64_t level = 0;
         bool stale_beneath = false, found_pending = false, work_beneath_pending = false;
         for (;;) {
@@ -874,6 +894,7 @@ struct Oracle {
                     if (!inF[d]) {
                         inF[d] = 1;
                         F.push_back(d);
+                        if (level > 0 && sig[d].kind != CXB_KIND_PRODUCT) waits_on_leaf = true;  // rule G: a late message, not a cascade node
                     }
                     return true;
                 }
@@ -887,6 +908,7 @@ struct Oracle {
             // never blocks, so it can: `probe` follows the same descent rule through done signals without computing
             // anything, and a pending weak dependency found there makes the request order-dependent -> refused.
             bool weak_beneath_done = false;
+            strong_beneath_done = waits_on_leaf = false;
             lvl_visits.assign(sig.size(), 0);
             revisited_via_I.assign(sig.size(), 0);
             std::vector<uint8_t> probed(sig.size(), 0);
@@ -903,6 +925,7 @@ struct Oracle {
                         int64_t d = o->sig[sid].deps[i];
                         if (!done[d] && o->is_pending(d)) {
                             if (nib(o->sig[sid], i, MASK_W)) weak_beneath_done = true;
+                            else if (o->rule_g >= 2) o->strong_beneath_done = true;
                         } else if (nib(o->sig[sid], i, MASK_I)) {
                             probe(d);
                         }
@@ -916,8 +939,14 @@ struct Oracle {
                         if (processed && nib(o->sig[sid], i, MASK_I)) o->revisited_via_I[d] = 1;  // found pending through an I slot
                         if (!processed && nib(o->sig[sid], i, MASK_I)) {
                             if (done[d]) {
-                                if (o->has_weak_dep) probe(d);  // like the device: graphs without weak dependencies are not probed
+                                if (o->has_weak_dep || o->rule_g >= 2) probe(d);  // like the device: graphs without weak dependencies are not probed
                             } else {
+                                // rule G: the variable WAITS for a message of another variable's making (a dependency that is
+                                // neither pending nor computed in this request, whose slot is not satisfied, and that is not a
+                                // ProductOfMessages node of an ordinary cascade)
+                                if (o->sig[d].kind != CXB_KIND_PRODUCT && o->sig[d].ndeps > 0 &&
+                                    !(nib(o->sig[sid], i, MASK_C) && (nib(o->sig[sid], i, MASK_W) || nib(o->sig[sid], i, MASK_F))))
+                                    o->waits_on_leaf = true;
                                 bool ip = go(d);
                                 if (ip) processed = f(d);
                                 any = any || ip;
@@ -942,6 +971,20 @@ struct Oracle {
             if (stale_beneath) {
                 err = "level-synchronous schedule out of contract: a signal reached by the request is not pending but holds leftover "
                       "freshness from an earlier, incomplete request (order-dependent in the reference)";
+                return CXB_ERR_OUT_OF_CONTRACT;
+            }
+            // Rule G. The reference re-traverses a variable that is not ready yet in every later round - THROUGH the signals it
+            // computed earlier in the request: a dependency that has become pending beneath such a signal is computed there and
+            // the signal recomputed (Gauss-Seidel), which a level schedule never does. Beneath a done signal a pending dependency
+            // is harmless only when no later round comes by, i.e. when every variable completes by its own cascade of
+            // ProductOfMessages nodes (protocol B on graphs with segment trees: the linked m2f are pending beneath the done m2v
+            // and wait for the final phase). So: a pending strong dependency beneath a done signal is refused when, in the same
+            // traversal, some variable depends on a message of another variable's making - it WAITS for one, or one arrives late
+            // (a member of a level after the first that is not a ProductOfMessages node) - (`waits_on_leaf`), or when the
+            // traversal is the last one (nothing left to compute, yet a variable is not ready).
+            if (strong_beneath_done && (waits_on_leaf || F.empty())) {
+                err = "level-synchronous schedule out of contract: a pending dependency lies beneath a signal already computed in this "
+                      "request (the reference recomputes that signal when a later round reaches it: order-dependent)";
                 return CXB_ERR_OUT_OF_CONTRACT;
             }
             if (weak_beneath_done) {

@@ -154,3 +154,15 @@ def test_incremental_chain_scripts_default_schedule_equals_reference(oracle_api,
                 assert so[0] == sd[0], (seed, ids)
                 np.testing.assert_allclose(sd[1], so[1], rtol=1e-12, atol=0, equal_nan=True)
     assert fell_back > 0  # some requests were refused by the level schedule and answered by the sequential executor
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("seed", list(range(40)) + [112, 768, 949, 482])
+def test_default_schedule_on_resolver_built_graphs_equals_the_reference(oracle_api, device_api, seed):
+    """Graphs wired only by the default resolver (AUTO = level schedule, certified against the sequential executor when first
+    recorded): random bipartite graphs with loops, leaves and hubs, messages overwritten by the user, random links, random
+    request subsets and orders (tests/fuzz_bp_graphs.py). Seeds 112, 768, 949: scripts on which the oracle's level schedule
+    ACCEPTS a request and answers differently from the reference; 482: the reference's own loop does not terminate."""
+    from tests import fuzz_bp_graphs as fb
+
+    assert fb.one_seed(device_api, oracle_api, seed, "auto", "seq") in ("equal", "diverges")
