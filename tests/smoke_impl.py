@@ -28,10 +28,10 @@ def run_smoke():
     assert ch.update_marginals() == B * (6 * T - 4)
     ref = np.zeros((6, T, B, 2))
     y64 = np.ascontiguousarray(y.astype(np.float64))
-    oracle.chains_reference(B, T, q.ctypes.data_as(cap.f64p), r.ctypes.data_as(cap.f64p), y64.ctypes.data_as(cap.f64p),
+    q32, r32 = q.astype(np.float32).astype(np.float64), r.astype(np.float32).astype(np.float64)  # what the fp32 engine holds
+    oracle.chains_reference(B, T, q32.ctypes.data_as(cap.f64p), r32.ctypes.data_as(cap.f64p), y64.ctypes.data_as(cap.f64p),
                             ref.ctypes.data_as(cap.f64p))
-    for comp in range(2):  # rel 1e-5 of the magnitude (north_star fp32 tolerance)
-        np.testing.assert_allclose(ch.get_marginals()[..., comp], ref[5][..., comp], rtol=1e-5, atol=1e-5 * np.abs(ref[5][..., comp]).max())
+    models.assert_values_close(ch.get_marginals(), ref[5], cap.F32, kind="canon")  # element-wise: precision, mean, variance at 1e-5
     # 2. generic engine: explicit Signal graph of one chain, device frontier vs oracle (levels, values)
     Tn = 16
     data = np.cumsum(rng.standard_normal(Tn))
@@ -39,9 +39,14 @@ def run_smoke():
     for name, api in (("o", oracle), ("d", dev)):
         e, x, yv, lik, tr = models.make_ssm_model(Tn, api, form="canon", trace=True)
         models.ssm_set_data(e, yv, lik, data)
-        st = C.update_marginals(e, x)
+        st = C.update_marginals(e, x, schedule="lvl")  # the level-synchronous frontier: per-level lists must be bit-exact
         res[name] = (st.updates, st.levels, models.level_trace(e),
                      C.get_values([C.get_variable_marginal(C.get_variable(e, v)) for v in x]))
+        # and the default schedule (device: level schedule certified against the sequential executor; oracle: the reference loop)
+        models.ssm_set_data(e, yv, lik, data + 1.0)
+        C.update_marginals(e, x)
+        res[name] += (C.get_values([C.get_variable_marginal(C.get_variable(e, v)) for v in x]),)
     assert res["o"][:3] == res["d"][:3]
     np.testing.assert_allclose(res["d"][3], res["o"][3], rtol=1e-12)
+    np.testing.assert_allclose(res["d"][4], res["o"][4], rtol=1e-12)
     print(f"smoke ok: {dev.kernel_launches() - l0} CUDA kernel launches, chains kernel {ch.last_kernel_ms():.3f} ms")
