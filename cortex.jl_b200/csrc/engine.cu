@@ -1379,6 +1379,9 @@ struct ChainPlanArgs {
     uint32_t stride;            // position of (chain, t) = base[chain] + t * stride
     uint32_t n_chains;
 };
+// blockIdx.y = 0: forward filter (m2v(x_t, lik_t), m2v(x_t, tr_{t-1}), m2f(x_t, tr_t)); blockIdx.y = 1: backward recursion
+// (m2v(x_t, tr_t), m2f(x_t, tr_{t-1})), which recomputes the observation message from y with the same expression instead of
+// waiting for the forward thread. The two recursions of a chain run concurrently; the marginals follow in k_chain_plan_marg.
 template <class T, int TILE>
 __global__ void __launch_bounds__(64) k_chain_plan(T* __restrict__ val, ChainPlanArgs a) {
     const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
@@ -1387,93 +1390,80 @@ __global__ void __launch_bounds__(64) k_chain_plan(T* __restrict__ val, ChainPla
     const T* __restrict__ pr_r = (const T*)a.par_r;
     const T* __restrict__ pr_q = (const T*)a.par_q;
     T L = 0, h = 0;
-    for (uint32_t t0 = 0; t0 < Tn; t0 += TILE) {  // forward: m2v(x_t, lik_t), m2v(x_t, tr_{t-1}), m2f(x_t, tr_t)
-        uint32_t iy[TILE], io[TILE], ip[TILE], im[TILE];
+    if (blockIdx.y == 0) {
+        for (uint32_t t0 = 0; t0 < Tn; t0 += TILE) {
+            uint32_t iy[TILE], io[TILE], ip[TILE], im[TILE];
+            T yy[TILE], rr[TILE], qq[TILE];
+#pragma unroll
+            for (int k = 0; k < TILE; ++k) {
+                const uint32_t t = t0 + k, pos = b0 + (t < Tn ? t : 0) * st;
+                iy[k] = a.i_y[pos];
+                io[k] = a.i_obs[pos];
+                ip[k] = a.i_pred[pos];
+                im[k] = a.i_fwd[pos];
+                rr[k] = pr_r[pos];
+                qq[k] = t > 0 && t < Tn ? pr_q[pos - st] : T(0);  // tr_{t-1}
+            }
+#pragma unroll
+            for (int k = 0; k < TILE; ++k) yy[k] = val[(size_t)iy[k] * 2];
+#pragma unroll
+            for (int k = 0; k < TILE; ++k) {
+                const uint32_t t = t0 + k;
+                if (t >= Tn) break;
+                const T p = rr[k];
+                const T oL = T(1) / p, oh = yy[k] / p;  // GAUSS_OBS
+                val[(size_t)io[k] * 2] = oL;
+                val[(size_t)io[k] * 2 + 1] = oh;
+                T aL = oL, ah = oh;
+                if (t > 0) {  // GAUSS_RW from m2f(x_{t-1}, tr_{t-1}) = (L, h)
+                    const T q = qq[k];
+                    const T den = T(1) + q * L;
+                    const T pL = L / den, ph = h / den;
+                    val[(size_t)ip[k] * 2] = pL;
+                    val[(size_t)ip[k] * 2 + 1] = ph;
+                    aL = aL + pL;
+                    ah = ah + ph;
+                }
+                L = aL;
+                h = ah;
+                if (im[k] != 0xFFFFFFFFu) {  // m2f(x_t, tr_t) = lik (+) tr_{t-1}
+                    val[(size_t)im[k] * 2] = L;
+                    val[(size_t)im[k] * 2 + 1] = h;
+                }
+            }
+        }
+        return;
+    }
+    for (int64_t t1 = (int64_t)Tn - 1; t1 >= 0; t1 -= TILE) {
+        uint32_t iy[TILE], ib[TILE], ik[TILE];
         T yy[TILE], rr[TILE], qq[TILE];
 #pragma unroll
         for (int k = 0; k < TILE; ++k) {
-            const uint32_t t = t0 + k, pos = b0 + (t < Tn ? t : 0) * st;
+            const int64_t t = t1 - k;
+            const uint32_t pos = b0 + (uint32_t)(t >= 0 ? t : 0) * st;
             iy[k] = a.i_y[pos];
-            io[k] = a.i_obs[pos];
-            ip[k] = a.i_pred[pos];
-            im[k] = a.i_fwd[pos];
+            ib[k] = a.i_bwd[pos];
+            ik[k] = a.i_back[pos];
             rr[k] = pr_r[pos];
-            qq[k] = t > 0 && t < Tn ? pr_q[pos - st] : T(0);  // tr_{t-1}
+            qq[k] = pr_q[pos];  // tr_t (unused at t = T-1)
         }
 #pragma unroll
         for (int k = 0; k < TILE; ++k) yy[k] = val[(size_t)iy[k] * 2];
 #pragma unroll
         for (int k = 0; k < TILE; ++k) {
-            const uint32_t t = t0 + k;
-            if (t >= Tn) break;
-            const T p = rr[k];
-            const T oL = T(1) / p, oh = yy[k] / p;  // GAUSS_OBS
-            val[(size_t)io[k] * 2] = oL;
-            val[(size_t)io[k] * 2 + 1] = oh;
-            T aL = oL, ah = oh;
-            if (t > 0) {  // GAUSS_RW from m2f(x_{t-1}, tr_{t-1}) = (L, h)
-                const T q = qq[k];
-                const T den = T(1) + q * L;
-                const T pL = L / den, ph = h / den;
-                val[(size_t)ip[k] * 2] = pL;
-                val[(size_t)ip[k] * 2 + 1] = ph;
-                aL = aL + pL;
-                ah = ah + ph;
-            }
-            L = aL;
-            h = ah;
-            if (im[k] != 0xFFFFFFFFu) {  // m2f(x_t, tr_t) = lik (+) tr_{t-1}
-                val[(size_t)im[k] * 2] = L;
-                val[(size_t)im[k] * 2 + 1] = h;
-            }
-        }
-    }
-    L = 0;
-    h = 0;
-    for (int64_t t1 = (int64_t)Tn - 1; t1 >= 0; t1 -= TILE) {  // backward: m2v(x_t, tr_t), m2f(x_t, tr_{t-1}), marginal(x_t)
-        uint32_t io[TILE], ip[TILE], ib[TILE], ik[TILE], ig[TILE];
-        T oL[TILE], oh[TILE], pL[TILE], ph[TILE], qq[TILE];
-#pragma unroll
-        for (int k = 0; k < TILE; ++k) {
-            const int64_t t = t1 - k;
-            const uint32_t pos = b0 + (uint32_t)(t >= 0 ? t : 0) * st;
-            io[k] = a.i_obs[pos];
-            ip[k] = a.i_pred[pos];
-            ib[k] = a.i_bwd[pos];
-            ik[k] = a.i_back[pos];
-            ig[k] = a.i_marg[pos];
-            qq[k] = pr_q[pos];  // tr_t (unused at t = T-1)
-        }
-#pragma unroll
-        for (int k = 0; k < TILE; ++k) {
-            oL[k] = val[(size_t)io[k] * 2];
-            oh[k] = val[(size_t)io[k] * 2 + 1];
-            const bool hp = ip[k] != 0xFFFFFFFFu;
-            pL[k] = hp ? val[(size_t)ip[k] * 2] : T(0);
-            ph[k] = hp ? val[(size_t)ip[k] * 2 + 1] : T(0);
-        }
-#pragma unroll
-        for (int k = 0; k < TILE; ++k) {
             const int64_t t = t1 - k;
             if (t < 0) break;
-            T bL = 0, bh = 0;
-            T aL = oL[k], ah = oh[k];
-            T gL = oL[k], gh = oh[k];
-            if (t > 0) {
-                gL = gL + pL[k];
-                gh = gh + ph[k];
-            }
+            const T p = rr[k];
+            const T oL = T(1) / p, oh = yy[k] / p;  // the observation message, expression for expression as the forward thread
+            T aL = oL, ah = oh;
             if (t < (int64_t)Tn - 1) {  // GAUSS_RW from m2f(x_{t+1}, tr_t) = (L, h)
                 const T q = qq[k];
                 const T den = T(1) + q * L;
-                bL = L / den;
-                bh = h / den;
+                const T bL = L / den, bh = h / den;
                 val[(size_t)ib[k] * 2] = bL;
                 val[(size_t)ib[k] * 2 + 1] = bh;
                 aL = aL + bL;
                 ah = ah + bh;
-                gL = gL + bL;
-                gh = gh + bh;
             }
             L = aL;
             h = ah;
@@ -1481,10 +1471,26 @@ __global__ void __launch_bounds__(64) k_chain_plan(T* __restrict__ val, ChainPla
                 val[(size_t)ik[k] * 2] = L;
                 val[(size_t)ik[k] * 2 + 1] = h;
             }
-            val[(size_t)ig[k] * 2] = gL;  // marginal = lik (+) tr_{t-1} (+) tr_t, left to right
-            val[(size_t)ig[k] * 2 + 1] = gh;
         }
     }
+}
+// marginal(x_t) = lik (+) tr_{t-1} (+) tr_t, left to right: one thread per (chain, t) position
+template <class T>
+__global__ void k_chain_plan_marg(T* __restrict__ val, ChainPlanArgs a, size_t n_pos) {
+    const size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n_pos) return;
+    const uint32_t io = a.i_obs[p], ip = a.i_pred[p], ib = a.i_bwd[p], ig = a.i_marg[p];
+    T gL = val[(size_t)io * 2], gh = val[(size_t)io * 2 + 1];
+    if (ip != 0xFFFFFFFFu) {
+        gL = gL + val[(size_t)ip * 2];
+        gh = gh + val[(size_t)ip * 2 + 1];
+    }
+    if (ib != 0xFFFFFFFFu) {
+        gL = gL + val[(size_t)ib * 2];
+        gh = gh + val[(size_t)ib * 2 + 1];
+    }
+    val[(size_t)ig * 2] = gL;
+    val[(size_t)ig * 2 + 1] = gh;
 }
 
 // =================================================================================================================
@@ -2800,10 +2806,14 @@ struct DeviceEngine {
         a.len = P.len.p;
         a.stride = P.stride;
         a.n_chains = P.n_chains;
-        if (dtype == CXB_F32)
-            CXB_LAUNCH((k_chain_plan<float, 8>), cdiv(P.n_chains, 64), 64, 0, stream, (float*)d_val.p, a);
-        else
-            CXB_LAUNCH((k_chain_plan<double, 8>), cdiv(P.n_chains, 64), 64, 0, stream, (double*)d_val.p, a);
+        const dim3 grid(cdiv(P.n_chains, 64), 2);  // y: forward / backward recursion of the same chains, side by side
+        if (dtype == CXB_F32) {
+            CXB_LAUNCH((k_chain_plan<float, 8>), grid, 64, 0, stream, (float*)d_val.p, a);
+            CXB_LAUNCH(k_chain_plan_marg<float>, cdiv(P.n_pos, 256), 256, 0, stream, (float*)d_val.p, a, P.n_pos);
+        } else {
+            CXB_LAUNCH((k_chain_plan<double, 8>), grid, 64, 0, stream, (double*)d_val.p, a);
+            CXB_LAUNCH(k_chain_plan_marg<double>, cdiv(P.n_pos, 256), 256, 0, stream, (double*)d_val.p, a, P.n_pos);
+        }
         return CXB_OK;
     }
 
@@ -2812,8 +2822,10 @@ struct DeviceEngine {
         hit = false;
         std::vector<Memo*> cand;
         for (auto& m : memos)
-            if ((int64_t)m->req_ids.size() == n && ((current_prepared >= 0 && m->prepared == current_prepared) || !std::memcmp(m->req_ids.data(), ids, (size_t)n * 8)))
+            if ((int64_t)m->req_ids.size() == n && ((current_prepared >= 0 && m->prepared == current_prepared) || !std::memcmp(m->req_ids.data(), ids, (size_t)n * 8))) {
+                if (current_prepared >= 0) m->prepared = current_prepared;  // next time the handle alone identifies the ids
                 cand.push_back(m.get());
+            }
         if (cand.empty()) return CXB_OK;
         const size_t N = n_uploaded, NC = csr.nib.size();
         CXB_CUDA(d_memo_flags.reserve(MAX_MEMOS));
