@@ -1513,7 +1513,8 @@ struct Memo {
     size_t bytes = 0;
     int plan = 0;  // 0: replay the recorded levels; > 0: a closed-form plan computes the values (DeviceEngine::run_plan)
     int64_t prepared = -1;  // recorded from this prepared request (ids need not be compared again)
-    bool seq_only = false;  // certification failed: for this (request, flag state) the level schedule differs from the reference
+    bool seq_only = false;  // certification failed (or the level schedule refused): this (request, flag state) is answered sequentially
+    bool certified = false; // the recorded level run was compared with the sequential executor's answer and found equal
 };
 template <class T>
 inline void swap_buf(DBuf<T>& a, DBuf<T>& b) {
@@ -2520,6 +2521,24 @@ struct DeviceEngine {
         memos.push_back(std::move(rec));
         return CXB_OK;
     }
+    // the level schedule refused this request on this flag state (the rollback snapshot = the pre-state): a negative memo
+    void remember_sequential_only(int64_t n, const int64_t* ids) {
+        std::unique_ptr<Memo> m(new Memo());
+        swap_buf(m->pre_props, d_snap_props);
+        swap_buf(m->pre_nib, d_snap_nib);
+        snap_valid = false;
+        m->req_ids.assign(ids, ids + n);
+        m->prepared = current_prepared;
+        m->seq_only = true;
+        m->last_use = ++memo_clock;
+        if (memos.size() >= MAX_MEMOS) {
+            size_t lru = 0;
+            for (size_t i = 1; i < memos.size(); ++i)
+                if (memos[i]->last_use < memos[lru]->last_use) lru = i;
+            memos.erase(memos.begin() + lru);
+        }
+        memos.push_back(std::move(m));
+    }
     // ---- certification --------------------------------------------------------------------------------------------------------
     // The contract checks of the level schedule are sufficient on the benchmark families and on everything the fuzzers of
     // round 1 produced, but not complete: tests/fuzz_bp_graphs.py (random default-resolver graphs with loops and hubs, messages
@@ -2573,6 +2592,7 @@ struct DeviceEngine {
         CXB_CUDA(cudaStreamSynchronize(stream));
         if (!h_memo_flags.p[0]) {  // certified: the engine holds the (identical) state; report the level run
             ++n_certified;
+            m.certified = true;
             stats = level_stats;
             for (int k = 0; k < 6; ++k) h_kind_count.p[k] = level_kinds[k];
             last_ran = CXB_SCHEDULE_LEVEL;
@@ -2836,10 +2856,15 @@ struct DeviceEngine {
             CXB_LAUNCH(k_state_differs, grid, 256, 0, stream, d_props.p, cand[c]->pre_props.p, N, d_nib.p, cand[c]->pre_nib.p, NC, d_memo_flags.p + c);
         CXB_CUDA(cudaMemcpyAsync(h_memo_flags.p, d_memo_flags.p, MAX_MEMOS * sizeof(int), cudaMemcpyDeviceToHost, stream));
         CXB_CUDA(cudaStreamSynchronize(stream));
+        // under AUTO a graph small enough to be certified replays only what WAS certified (a memo recorded under an explicit
+        // LEVEL schedule is not)
+        const bool need_cert = schedule == CXB_SCHEDULE_AUTO && small_values() && g.n_sig() <= CERTIFY_LIMIT &&
+                               !(getenv("CXB_CERTIFY") && !atoi(getenv("CXB_CERTIFY")));
         Memo* m = nullptr;
         for (size_t c = 0; c < cand.size() && !m; ++c)
-            if (!h_memo_flags.p[c]) m = cand[c];
+            if (!h_memo_flags.p[c] && (!need_cert || cand[c]->certified || cand[c]->seq_only)) m = cand[c];
         if (!m) return CXB_OK;
+        if (m->seq_only && schedule != CXB_SCHEDULE_AUTO) return CXB_OK;  // an explicit LEVEL request gets the level schedule (and its refusal)
         int32_t st;
         if (m->seq_only) {  // certification found the level schedule wrong for this request and flag state
             if ((st = update_seq(n, ids))) return st;
@@ -2958,6 +2983,7 @@ struct DeviceEngine {
             if (st2) return st2;
             err = why;
             if (schedule == CXB_SCHEDULE_AUTO && small_values() && g.n_sig() <= SEQ_FALLBACK_LIMIT) {
+                if (memo_ok) remember_sequential_only(n, ids);  // next time this request meets this flag state: straight to k_seq
                 stats = cxb_update_stats{};
                 tr_level.clear();
                 tr_sid.clear();
