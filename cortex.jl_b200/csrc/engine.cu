@@ -2934,7 +2934,7 @@ struct DeviceEngine {
     bool small_values() const {
         return (family != CXB_FAMILY_CATEGORICAL && dim <= 8) || (family == CXB_FAMILY_CATEGORICAL && dim <= 64);
     }
-    static constexpr int64_t SEQ_FALLBACK_LIMIT = 1 << 22;  // signals: above it a refused request stays refused under AUTO
+    static constexpr int64_t SEQ_FALLBACK_LIMIT = 1 << 20;  // signals: above it a refused request stays refused under AUTO (k_seq: ~microseconds per executed signal)
 
     // update_marginals!(engine, ids), src/inference_engine.jl:559-632: schedule selection (include/cortex_b200.h)
     int32_t update(int64_t n, const int64_t* ids) {
