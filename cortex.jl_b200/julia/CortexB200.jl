@@ -37,7 +37,11 @@ const FAMILY_GAUSS_CANON, FAMILY_CATEGORICAL, FAMILY_GAUSS_MV, FAMILY_BETA, FAMI
       FAMILY_GAUSS_MP, FAMILY_GAMMA, FAMILY_POINT = 0:7
 const RULE_NONE, RULE_GAUSS_OBS, RULE_GAUSS_RW, RULE_CAT_TABLE, RULE_POTTS, RULE_HMM_EMIT,
       RULE_GAUSS_MV_OBS, RULE_GAUSS_MV_RW, RULE_BETA_BERNOULLI, RULE_SCALE2, RULE_NORMAL_MEAN_FIELD,
-      RULE_NORMAL_STRUCTURED = 0:11
+      RULE_NORMAL_STRUCTURED, RULE_PROGRAM = 0:12
+# opcodes of RULE_PROGRAM (a user-defined rule as a stack program: params = [n_consts, consts..., code...]; see
+# include/cortex_b200.h and `rule_program` below)
+const OP_DEP, OP_CONST, OP_PARAM, OP_ADD, OP_SUB, OP_MUL, OP_DIV, OP_NEG, OP_EXP, OP_LOG, OP_SQRT, OP_STORE, OP_TSET, OP_TGET,
+      OP_NDEPS = 1:15
 const RESOLVER_NONE, RESOLVER_DEFAULT_BP, RESOLVER_MEAN_FIELD = 0:2
 const SCHEDULE_AUTO, SCHEDULE_LEVEL, SCHEDULE_SEQUENTIAL, RAN_REPLAY, RAN_PLAN = 0:4
 const DEP_INTERMEDIATE, DEP_WEAK, DEP_NO_LISTEN, DEP_NO_CHECK_COMPUTED = 1, 2, 16, 32
@@ -155,6 +159,18 @@ function B200ModelEngine(n_ids::Integer, is_factor::Vector{UInt8}, forms::Abstra
     finalizer(e -> ccall((:cxb_destroy, LIB), Cvoid, (Ptr{Cvoid},), e.handle), m)
     return m
 end
+
+"""
+    rule_program(consts::Vector{Float64}, code::Vector) -> (RULE_PROGRAM, params)
+
+A user-defined message-to-variable rule for fixed-size values without rebuilding the library (the counterpart of a new method of
+`compute_message_to_variable!`, src/inference_engine.jl:351-361). `consts[1]` is the default of the per-factor parameter; `code`
+is the postfix program, e.g. the random-walk rule `(L, h) -> (L / (1 + q L), h / (1 + q L))`:
+
+    rule_program([1.0, 1.0], [OP_CONST, 1, OP_PARAM, OP_DEP, 0, 0, OP_MUL, OP_ADD, OP_TSET, 0,
+                              OP_DEP, 0, 0, OP_TGET, 0, OP_DIV, OP_STORE, 0, OP_DEP, 0, 1, OP_TGET, 0, OP_DIV, OP_STORE, 1])
+"""
+rule_program(consts::Vector{Float64}, code::Vector) = (RULE_PROGRAM, vcat(Float64(length(consts)), consts, Float64.(code)))
 
 # ---- signals: dense ids on the device, views on the host ---------------------------------------------------------------
 signal_id(m::B200ModelEngine, kind::Integer, v::Integer, f::Integer = 0) =
