@@ -1281,7 +1281,10 @@ __global__ void k_rule_cat(View e, T* __restrict__ val, const uint32_t* list, ui
     __syncthreads();
     const int g = threadIdx.x / G, lane = threadIdx.x % G;
     const unsigned gmask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << ((threadIdx.x & 31) / G * G));
-    uint32_t i = blockIdx.x * groups_per_block + g;
+    // persistent blocks: the table is staged once per block and serves every batch of groups_per_block signals the block takes
+    // (one block per 32 signals re-staged it 7,800 times per launch on the power-law graph)
+    for (uint32_t i0 = blockIdx.x * groups_per_block; i0 < n; i0 += gridDim.x * groups_per_block) {
+    const uint32_t i = i0 + g;
     const bool active = i < n;
     uint32_t s = active ? list[i] : 0;
     uint32_t off = active ? e.dep_off[s] : 0, nd = active ? e.dep_off[s + 1] - off : 0;
@@ -1363,6 +1366,7 @@ __global__ void k_rule_cat(View e, T* __restrict__ val, const uint32_t* list, ui
             if (k < K) o[k] = acc[c] / part;
         }
     }
+    }  // batches of this block
 }
 
 // ---- closed-form plan: disjoint random-walk chains -----------------------------------------------------------------------
@@ -1999,7 +2003,7 @@ struct DeviceEngine {
                     err = "categorical value_dim too large for the generic engine (use the structured HMM engine)";
                     return CXB_ERR_BAD_ARG;
                 }
-                unsigned grid = cdiv(cnt, gpb);
+                unsigned grid = std::min(cdiv(cnt, gpb), 148u * 8u);  // persistent: 8 blocks of 256 threads per SM
 #define CAT_LAUNCH(GG, MC)                                                                                        \
     do {                                                                                                          \
         if (smem > 48 * 1024)                                                                                     \
@@ -2550,7 +2554,9 @@ struct DeviceEngine {
     // not on the rule set. Different: the sequential result stands and the (request, flag state) pair is remembered as
     // sequential-only. Graphs above CERTIFY_LIMIT signals (the benchmark-size graphs, wired by the default resolver and
     // driven by the proven protocols) are not certified: there the rules are the guarantee.
-    static constexpr int64_t CERTIFY_LIMIT = 1 << 20;
+    // k_seq costs ~4 us per executed signal: 2^18 signals bound a certification to about a second. CXB_CERTIFY_LIMIT (signals)
+    // moves the bound, CXB_CERTIFY=0 switches certification off.
+    int64_t CERTIFY_LIMIT = getenv("CXB_CERTIFY_LIMIT") ? atoll(getenv("CXB_CERTIFY_LIMIT")) : (1 << 18);
     int32_t certify_last_memo(int64_t n, const int64_t* ids) {
         Memo& m = *memos.back();
         const size_t N = n_uploaded, NC = csr.nib.size(), vb = N * dim * esz();
