@@ -1,5 +1,5 @@
 import sys, time, ctypes, numpy as np, torch
-sys.path.insert(0, '/root/repo')
+sys.path.insert(0, str(__import__('pathlib').Path(__file__).resolve().parent.parent))
 import __graft_entry__ as entry
 pkg = entry.load_package(); cap = pkg.capi; api = pkg.default_api()
 T, B = 1000, int(sys.argv[1]) if len(sys.argv) > 1 else 4096

@@ -1,5 +1,5 @@
 import sys, time, numpy as np
-sys.path.insert(0, '/root/repo')
+sys.path.insert(0, str(__import__('pathlib').Path(__file__).resolve().parent.parent))
 from tests import models
 from tests._pkg import pkg as C
 cap = C.capi
