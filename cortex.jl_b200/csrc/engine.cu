@@ -1382,100 +1382,134 @@ struct ChainPlanArgs {
     const uint32_t* len;        // [n_chains] T of the chain
     uint32_t stride;            // position of (chain, t) = base[chain] + t * stride
     uint32_t n_chains;
+    int along_t;                // positions and signal ids are contiguous along t (else along the chains)
 };
 // blockIdx.y = 0: forward filter (m2v(x_t, lik_t), m2v(x_t, tr_{t-1}), m2f(x_t, tr_t)); blockIdx.y = 1: backward recursion
 // (m2v(x_t, tr_t), m2f(x_t, tr_{t-1})), which recomputes the observation message from y with the same expression instead of
-// waiting for the forward thread. The two recursions of a chain run concurrently; the marginals follow in k_chain_plan_marg.
-template <class T, int TILE>
-__global__ void __launch_bounds__(64) k_chain_plan(T* __restrict__ val, ChainPlanArgs a) {
-    const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= a.n_chains) return;
-    const uint32_t b0 = a.base[c], Tn = a.len[c], st = a.stride;
+// waiting for the forward recursion. The two recursions of a chain run concurrently; the marginals follow in k_chain_plan_marg.
+//
+// A block owns 32 chains and walks them in tiles of 32 steps (tau = steps from the recursion's start). The only serial part
+// is the two divisions per step, so the tile is split in three phases and the block's W warps take tiles round-robin:
+//   A (all lanes, off the critical path): gather y / noise through the index tables with the lanes along the direction in
+//     which the positions AND the signal ids are contiguous (along_t: lane = step, else lane = chain), compute the
+//     observation message, park (oL, oh, q) in shared memory as [step][chain];
+//   B (lane = chain): wait for the (L, h) the previous tile handed over (named barrier, producer/consumer), run 32 steps
+//     from shared memory, hand (L, h) to the next tile's warp;
+//   C (all lanes, off the critical path): scatter the messages to `val` with the phase-A lane mapping.
+// While one warp is in B the other W-1 prefetch / drain their tiles, so a chain advances at the latency of its arithmetic.
+template <class T>
+struct ChainTile {
+    T oL[32][33], oh[32][33], q[32][33], pL[32][33], ph[32][33];  // [step in tile][chain lane], padded: both lane mappings conflict-free
+};
+__device__ __forceinline__ void named_bar_sync(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
+__device__ __forceinline__ void named_bar_arrive(int id, int n) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(n) : "memory"); }
+__device__ __forceinline__ void store_pair(float* p, float a, float b) { *reinterpret_cast<float2*>(p) = make_float2(a, b); }
+__device__ __forceinline__ void store_pair(double* p, double a, double b) { *reinterpret_cast<double2*>(p) = make_double2(a, b); }
+template <class T, int W>
+__global__ void __launch_bounds__(W * 32) k_chain_plan(T* __restrict__ val, ChainPlanArgs a) {
+    extern __shared__ __align__(16) unsigned char chain_smem[];
+    ChainTile<T>* tiles = reinterpret_cast<ChainTile<T>*>(chain_smem);
+    T* hand = reinterpret_cast<T*>(tiles + W);  // [2][32]: (L, h) of the 32 chains after the last finished tile
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const bool bwd = blockIdx.y == 1, along_t = a.along_t != 0;
+    const uint32_t c0 = blockIdx.x * 32, NONE = 0xFFFFFFFFu, st = a.stride;
+    const uint32_t nc = min(32u, a.n_chains - c0);
+    const uint32_t my_len = (uint32_t)lane < nc ? a.len[c0 + lane] : 0u;
+    const uint32_t my_base = (uint32_t)lane < nc ? a.base[c0 + lane] : 0u;
+    const uint32_t n_tiles = (__reduce_max_sync(0xFFFFFFFFu, my_len) + 31) / 32;
     const T* __restrict__ pr_r = (const T*)a.par_r;
     const T* __restrict__ pr_q = (const T*)a.par_q;
-    T L = 0, h = 0;
-    if (blockIdx.y == 0) {
-        for (uint32_t t0 = 0; t0 < Tn; t0 += TILE) {
-            uint32_t iy[TILE], io[TILE], ip[TILE], im[TILE];
-            T yy[TILE], rr[TILE], qq[TILE];
+    ChainTile<T>& S = tiles[warp];
+    const int n_it = along_t ? (int)nc : 32;  // along_t: iteration = chain, lane = step; else iteration = step, lane = chain
+    constexpr int CH = sizeof(T) == 4 ? 16 : 8;
+    for (uint32_t k = warp; k < n_tiles; k += W) {
+        const uint32_t tau0 = k * 32;
+        // ---- A: gather + observation message (CH positions per lane in flight: two memory latencies per chunk)
+        for (int i0 = 0; i0 < n_it; i0 += CH) {
+            uint32_t iy[CH], io[CH];
+            T rr[CH], qq[CH], yy[CH];
+            bool on[CH];
 #pragma unroll
-            for (int k = 0; k < TILE; ++k) {
-                const uint32_t t = t0 + k, pos = b0 + (t < Tn ? t : 0) * st;
-                iy[k] = a.i_y[pos];
-                io[k] = a.i_obs[pos];
-                ip[k] = a.i_pred[pos];
-                im[k] = a.i_fwd[pos];
-                rr[k] = pr_r[pos];
-                qq[k] = t > 0 && t < Tn ? pr_q[pos - st] : T(0);  // tr_{t-1}
+            for (int u = 0; u < CH; ++u) {
+                const int i = i0 + u, cc = along_t ? i : lane, tt = along_t ? lane : i;
+                const uint32_t len_c = __shfl_sync(0xFFFFFFFFu, my_len, cc & 31), base_c = __shfl_sync(0xFFFFFFFFu, my_base, cc & 31);
+                const uint32_t tau = tau0 + tt;
+                on[u] = i < n_it && tau < len_c;
+                const uint32_t pos = on[u] ? base_c + (bwd ? len_c - 1 - tau : tau) * st : 0u;
+                iy[u] = on[u] ? a.i_y[pos] : 0u;
+                io[u] = on[u] && !bwd ? a.i_obs[pos] : NONE;
+                rr[u] = on[u] ? pr_r[pos] : T(1);
+                qq[u] = on[u] && tau > 0 ? (bwd ? pr_q[pos] : pr_q[pos - st]) : T(0);
             }
 #pragma unroll
-            for (int k = 0; k < TILE; ++k) yy[k] = val[(size_t)iy[k] * 2];
+            for (int u = 0; u < CH; ++u) yy[u] = on[u] ? val[(size_t)iy[u] * 2] : T(0);
 #pragma unroll
-            for (int k = 0; k < TILE; ++k) {
-                const uint32_t t = t0 + k;
-                if (t >= Tn) break;
-                const T p = rr[k];
-                const T oL = T(1) / p, oh = yy[k] / p;  // GAUSS_OBS
-                val[(size_t)io[k] * 2] = oL;
-                val[(size_t)io[k] * 2 + 1] = oh;
-                T aL = oL, ah = oh;
-                if (t > 0) {  // GAUSS_RW from m2f(x_{t-1}, tr_{t-1}) = (L, h)
-                    const T q = qq[k];
-                    const T den = T(1) + q * L;
-                    const T pL = L / den, ph = h / den;
-                    val[(size_t)ip[k] * 2] = pL;
-                    val[(size_t)ip[k] * 2 + 1] = ph;
-                    aL = aL + pL;
-                    ah = ah + ph;
-                }
-                L = aL;
-                h = ah;
-                if (im[k] != 0xFFFFFFFFu) {  // m2f(x_t, tr_t) = lik (+) tr_{t-1}
-                    val[(size_t)im[k] * 2] = L;
-                    val[(size_t)im[k] * 2 + 1] = h;
-                }
+            for (int u = 0; u < CH; ++u) {
+                if (!on[u]) continue;
+                const int i = i0 + u, cc = along_t ? i : lane, tt = along_t ? lane : i;
+                const T p = rr[u];
+                const T oL = T(1) / p, oh = yy[u] / p;  // GAUSS_OBS
+                S.oL[tt][cc] = oL;
+                S.oh[tt][cc] = oh;
+                S.q[tt][cc] = qq[u];
+                if (io[u] != NONE) store_pair(val + (size_t)io[u] * 2, oL, oh);
             }
         }
-        return;
-    }
-    for (int64_t t1 = (int64_t)Tn - 1; t1 >= 0; t1 -= TILE) {
-        uint32_t iy[TILE], ib[TILE], ik[TILE];
-        T yy[TILE], rr[TILE], qq[TILE];
-#pragma unroll
-        for (int k = 0; k < TILE; ++k) {
-            const int64_t t = t1 - k;
-            const uint32_t pos = b0 + (uint32_t)(t >= 0 ? t : 0) * st;
-            iy[k] = a.i_y[pos];
-            ib[k] = a.i_bwd[pos];
-            ik[k] = a.i_back[pos];
-            rr[k] = pr_r[pos];
-            qq[k] = pr_q[pos];  // tr_t (unused at t = T-1)
+        __syncwarp();
+        // ---- B: the recursion, lane = chain
+        T L = 0, h = 0;
+        if (k > 0) {
+            named_bar_sync(1 + (int)((k - 1) % W), 64);
+            L = hand[lane];
+            h = hand[32 + lane];
         }
-#pragma unroll
-        for (int k = 0; k < TILE; ++k) yy[k] = val[(size_t)iy[k] * 2];
-#pragma unroll
-        for (int k = 0; k < TILE; ++k) {
-            const int64_t t = t1 - k;
-            if (t < 0) break;
-            const T p = rr[k];
-            const T oL = T(1) / p, oh = yy[k] / p;  // the observation message, expression for expression as the forward thread
-            T aL = oL, ah = oh;
-            if (t < (int64_t)Tn - 1) {  // GAUSS_RW from m2f(x_{t+1}, tr_t) = (L, h)
-                const T q = qq[k];
+        const uint32_t n_here = my_len > tau0 ? min(32u, my_len - tau0) : 0u;
+#pragma unroll 4
+        for (uint32_t tt = 0; tt < n_here; ++tt) {
+            const T oL = S.oL[tt][lane], oh = S.oh[tt][lane];
+            if (tau0 + tt > 0) {  // GAUSS_RW from the neighbour's m2f = (L, h), then lik (+) it
+                const T q = S.q[tt][lane];
                 const T den = T(1) + q * L;
-                const T bL = L / den, bh = h / den;
-                val[(size_t)ib[k] * 2] = bL;
-                val[(size_t)ib[k] * 2 + 1] = bh;
-                aL = aL + bL;
-                ah = ah + bh;
+                const T pL = L / den, ph = h / den;
+                S.pL[tt][lane] = pL;
+                S.ph[tt][lane] = ph;
+                L = oL + pL;
+                h = oh + ph;
+            } else {
+                L = oL;
+                h = oh;
             }
-            L = aL;
-            h = ah;
-            if (ik[k] != 0xFFFFFFFFu) {  // m2f(x_t, tr_{t-1}) = lik (+) tr_t
-                val[(size_t)ik[k] * 2] = L;
-                val[(size_t)ik[k] * 2 + 1] = h;
+            S.oL[tt][lane] = L;
+            S.oh[tt][lane] = h;
+        }
+        if (k + 1 < n_tiles) {
+            hand[lane] = L;
+            hand[32 + lane] = h;
+            __threadfence_block();
+            named_bar_arrive(1 + (int)(k % W), 64);
+        }
+        __syncwarp();
+        // ---- C: scatter (index loads of a chunk first, then its stores)
+        for (int i0 = 0; i0 < n_it; i0 += CH) {
+            uint32_t irw[CH], iout[CH];
+#pragma unroll
+            for (int u = 0; u < CH; ++u) {
+                const int i = i0 + u, cc = along_t ? i : lane, tt = along_t ? lane : i;
+                const uint32_t len_c = __shfl_sync(0xFFFFFFFFu, my_len, cc & 31), base_c = __shfl_sync(0xFFFFFFFFu, my_base, cc & 31);
+                const uint32_t tau = tau0 + tt;
+                const bool on = i < n_it && tau < len_c;
+                const uint32_t pos = on ? base_c + (bwd ? len_c - 1 - tau : tau) * st : 0u;
+                irw[u] = on && tau > 0 ? (bwd ? a.i_bwd[pos] : a.i_pred[pos]) : NONE;
+                iout[u] = on ? (bwd ? a.i_back[pos] : a.i_fwd[pos]) : NONE;
+            }
+#pragma unroll
+            for (int u = 0; u < CH; ++u) {
+                const int i = i0 + u, cc = (along_t ? i : lane) & 31, tt = (along_t ? lane : i) & 31;
+                if (irw[u] != NONE) store_pair(val + (size_t)irw[u] * 2, S.pL[tt][cc], S.ph[tt][cc]);
+                if (iout[u] != NONE) store_pair(val + (size_t)iout[u] * 2, S.oL[tt][cc], S.oh[tt][cc]);
             }
         }
+        __syncwarp();
     }
 }
 // marginal(x_t) = lik (+) tr_{t-1} (+) tr_t, left to right: one thread per (chain, t) position
@@ -2624,6 +2658,7 @@ struct DeviceEngine {
         std::vector<int64_t> pos_lik, pos_tr;  // factor id per position (-1: none), to refresh the parameters
         std::vector<int64_t> xs_sorted;        // the state variables, ascending (the request must name exactly these)
         uint32_t stride = 1, n_chains = 0;
+        bool along_t = true;
         size_t n_pos = 0;
         int64_t upd_m2v = 0, upd_m2f = 0, upd_marg = 0;
         uint64_t params_version = ~0ull;
@@ -2710,7 +2745,15 @@ struct DeviceEngine {
         const size_t B = chains.size();
         P.n_chains = (uint32_t)B;
         P.n_pos = total;
-        P.stride = same_len ? (uint32_t)B : 1u;
+        // Position layout = the direction in which the graph's own signal ids are contiguous, so that the kernel's gathers
+        // and scatters coalesce: chain after chain (lanes along t) unless the chains were created interleaved.
+        bool interleaved = false;
+        if (same_len && B >= 32 && chains[0].size() > 1) {
+            auto obs_sig = [&](size_t b, size_t t) { return (int64_t)g.m2v_of_conn(g.conn_of(chains[b][t], lik_of[chains[b][t]])); };
+            interleaved = std::llabs(obs_sig(1, 0) - obs_sig(0, 0)) < std::llabs(obs_sig(0, 1) - obs_sig(0, 0));
+        }
+        P.along_t = !interleaved;
+        P.stride = interleaved ? (uint32_t)B : 1u;
         std::vector<uint32_t> base(B), len(B), iy(total), io(total), ip(total, NONE), im(total, NONE), ib(total, NONE), ik(total, NONE), ig(total);
         P.pos_lik.assign(total, -1);
         P.pos_tr.assign(total, -1);
@@ -2728,9 +2771,9 @@ struct DeviceEngine {
         for (size_t b = 0; b < B; ++b) {
             const auto& c = chains[b];
             const size_t Tn = c.size();
-            base[b] = same_len ? (uint32_t)b : (uint32_t)off;
+            base[b] = interleaved ? (uint32_t)b : (uint32_t)off;
             len[b] = (uint32_t)Tn;
-            auto pos = [&](size_t t) { return same_len ? t * B + b : off + t; };
+            auto pos = [&](size_t t) { return interleaved ? t * B + b : off + t; };
             for (size_t t = 0; t < Tn; ++t) {
                 const int64_t x = c[t], lik = lik_of[x];
                 const int64_t trn = t + 1 < Tn ? (other(tr_a[x], x) == c[t + 1] ? tr_a[x] : tr_b[x]) : -1;
@@ -2832,12 +2875,20 @@ struct DeviceEngine {
         a.len = P.len.p;
         a.stride = P.stride;
         a.n_chains = P.n_chains;
-        const dim3 grid(cdiv(P.n_chains, 64), 2);  // y: forward / backward recursion of the same chains, side by side
+        a.along_t = P.along_t ? 1 : 0;
+        const dim3 grid(cdiv(P.n_chains, 32), 2);  // y: forward / backward recursion of the same chains, side by side
+        constexpr int W = 4;
         if (dtype == CXB_F32) {
-            CXB_LAUNCH((k_chain_plan<float, 8>), grid, 64, 0, stream, (float*)d_val.p, a);
+            const size_t smem = W * sizeof(ChainTile<float>) + 64 * sizeof(float);
+            auto kf = k_chain_plan<float, W>;
+            CXB_CUDA(cudaFuncSetAttribute(kf, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            CXB_LAUNCH((k_chain_plan<float, W>), grid, W * 32, smem, stream, (float*)d_val.p, a);
             CXB_LAUNCH(k_chain_plan_marg<float>, cdiv(P.n_pos, 256), 256, 0, stream, (float*)d_val.p, a, P.n_pos);
         } else {
-            CXB_LAUNCH((k_chain_plan<double, 8>), grid, 64, 0, stream, (double*)d_val.p, a);
+            const size_t smem = W * sizeof(ChainTile<double>) + 64 * sizeof(double);
+            auto kf = k_chain_plan<double, W>;
+            CXB_CUDA(cudaFuncSetAttribute(kf, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            CXB_LAUNCH((k_chain_plan<double, W>), grid, W * 32, smem, stream, (double*)d_val.p, a);
             CXB_LAUNCH(k_chain_plan_marg<double>, cdiv(P.n_pos, 256), 256, 0, stream, (double*)d_val.p, a, P.n_pos);
         }
         return CXB_OK;

@@ -19,7 +19,9 @@ def _values(e):
 
 
 @pytest.mark.parametrize("dtype", [cap.F64, cap.F32])
-@pytest.mark.parametrize("lengths,interleave", [([50], False), ([2, 3, 17, 40], False), ([24] * 9, False), ([24] * 9, True)])
+@pytest.mark.parametrize("lengths,interleave", [([50], False), ([2, 3, 17, 40], False), ([24] * 9, False), ([24] * 9, True),
+                                                # more than one 32-step tile / 32-chain block, both lane mappings, ragged tails, more tiles than warps
+                                                ([70] * 40, True), ([70] * 40, False), ([2, 33, 64, 65, 200] * 8, False), ([161], False)])
 def test_chain_batches_are_routed_to_the_plan_kernel(oracle_api, device_api, monkeypatch, dtype, lengths, interleave):
     rng = np.random.Generator(np.random.PCG64(11))
     B = len(lengths)
