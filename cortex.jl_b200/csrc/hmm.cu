@@ -21,6 +21,7 @@
 
 #include "common.cuh"
 #include "hmm_tc.cuh"
+#include "hmm64_tc.cuh"
 
 namespace cxb {
 
@@ -1089,7 +1090,26 @@ struct Hmm {
         CXB_LAUNCH((k_hmm64_mma<false>), grid, 128, smem, stream, at, en, obs.p, (float*)fwd.p, (float*)marg.p, B, this->T, M);
         return CXB_OK;
     }
+    // Measured alternative for K = 64, fp32 (CXB_HMM64_TC=1): both recursions in one launch on mma.sync tensor cores with
+    // three-piece bf16 operands, meeting in the middle (hmm64_tc.cuh). Parity-green, but slower than the FFMA2 register
+    // kernel below: 216 instructions per warp and step on a mostly serial dependency chain run at 0.31 instructions per
+    // cycle and scheduler with the two warps a scheduler gets (1,430 cycles per step of both recursions against
+    // 2 x 605 for the two FFMA2 passes; profiles/r02_hmm64_tc_ncu.txt).
+    int32_t launch_k64_tc() {
+        const size_t smem = h64::smem_bytes(M, true);
+        const unsigned grid = (unsigned)((B + h64::NB - 1) / h64::NB);
+        CXB_CUDA(cudaFuncSetAttribute(h64::k_hmm64_tc<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CXB_LAUNCH((h64::k_hmm64_tc<true>), grid, 256, smem, stream, (const float*)A.p, (const float*)At.p, (const float*)En.p, obs.p,
+                   (float*)fwd.p, (float*)marg.p, B, this->T, M);
+        return CXB_OK;
+    }
     int32_t launch_k64() {
+        {
+            bool tc64 = false;
+            if (const char* e = getenv("CXB_HMM64_TC")) tc64 = atoi(e) != 0;
+            const bool other = (getenv("CXB_HMM64_MMA") && atoi(getenv("CXB_HMM64_MMA"))) || (getenv("CXB_HMM64_SPLIT") && atoi(getenv("CXB_HMM64_SPLIT")));
+            if (tc64 && !other) return launch_k64_tc();
+        }
         // The tensor-core variant (mma.sync, 8 chains per CTA, k_hmm64_mma) is kept as a measured alternative
         // (CXB_HMM64_MMA=1): with one 64 x 64 x 8 product per SM and step it has a single warp per scheduler and pays every
         // latency in full — 970 cycles per step against 630 for the FFMA2 kernel below (T = 4,000: 3.94 ms vs 2.55 ms).
