@@ -36,8 +36,15 @@ struct Cfg {
     static constexpr uint32_t B_CHUNK_BYTES = NT * 64 * 2;                    // table chunk, per piece
     static constexpr uint32_t STAGE_BYTES = NP * (128 * 64 * 2) + NP * B_CHUNK_BYTES;  // message pieces + table pieces
     static constexpr int STAGES = (int)((200u * 1024u) / STAGE_BYTES);        // ~200 KB of operands in flight
-    // instruction descriptor: D = f32, A = B = bf16, both K-major, N = NT, M = 128
-    static constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(NT >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+    // instruction descriptor: D = f32, A = B = bf16, both K-major, N = n, M = 128
+    static constexpr uint32_t idesc(uint32_t n) { return (1u << 4) | (1u << 7) | (1u << 10) | ((n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24); }
+    // The table pieces of a chunk lie one after the other in the stage, which makes them ONE B operand of NP x NT rows:
+    // message piece a is multiplied with table pieces 0 .. NP-1-a in a single tcgen05.mma of N = (NP - a) NT that
+    // accumulates into TMEM columns [0, N): column block b ends up with sum_a msg_a tbl_b, the epilogue adds the blocks
+    // (small to large). NP MMAs per 16 input states instead of NP (NP + 1) / 2 — the step was bound by the issue rate
+    // of one thread's tcgen05.mma stream (~60 cycles per instruction at N = 32), not by the tensor pipe or the ingest.
+    static constexpr uint32_t TMEM_COLS = NP * NT <= 32 ? 32 : NP * NT <= 64 ? 64 : NP * NT <= 128 ? 128 : 256;
+    static_assert(NP * NT <= 256, "accumulator blocks must fit one MMA (N <= 256)");
 };
 constexpr int THREADS = 192;  // 4 epilogue warps + producer warp + MMA warp
 constexpr int MAX_K = 2048;   // any multiple of 64 up to here (both operands stream through the ring)
@@ -153,9 +160,9 @@ __device__ __forceinline__ void split_store8(const float* x, __nv_bfloat16* cons
 }
 
 struct StepArgs {
-    const __nv_bfloat16* op_in;   // [tiles][2 (hi, lo)][K / 64][8192] message operand of this step (previous step's result)
+    const __nv_bfloat16* op_in;   // [tiles][K / 64 chunks][NP pieces][8192] message operand of this step (previous step's result)
     __nv_bfloat16* op_out;        // same layout: message operand of the next step
-    const __nv_bfloat16* tbl_img; // [K / 64 slices][2][K / 64][4096] table slices, rows = output states
+    const __nv_bfloat16* tbl_img; // [K / NT slices][K / 64 chunks][NP pieces][NT x 64] table slices, rows = output states
     const float* emis_n;          // [M symbols][K]
     const uint8_t* obs_t;         // [B] symbols of this time step
     float* raw_out;               // [B][K] this step's unnormalised result (FWD: forward message, BWD: fwd * bwd)
@@ -184,7 +191,7 @@ __device__ __forceinline__ void load_row64(const float* p, float4 (&v)[16]) {
 template <bool FWD, int NT, int NP, int CL = 1>
 __device__ __forceinline__ void hmm_tc_step_body(const StepArgs& a) {
     constexpr int N_TILE = NT, STAGES = Cfg<NT, NP>::STAGES;
-    constexpr uint32_t B_CHUNK_BYTES = Cfg<NT, NP>::B_CHUNK_BYTES, STAGE_BYTES = Cfg<NT, NP>::STAGE_BYTES, IDESC = Cfg<NT, NP>::IDESC;
+    constexpr uint32_t B_CHUNK_BYTES = Cfg<NT, NP>::B_CHUNK_BYTES, STAGE_BYTES = Cfg<NT, NP>::STAGE_BYTES, TMEM_COLS = Cfg<NT, NP>::TMEM_COLS;
     constexpr int LPR = N_TILE / 4, RPI = 32 / LPR, ITER = 32 / RPI;  // lanes per row, rows per instruction, iterations per warp
     extern __shared__ __align__(128) unsigned char smem[];
     const int n_chunks = a.K / K_CHUNK;
@@ -211,8 +218,8 @@ __device__ __forceinline__ void hmm_tc_step_body(const StepArgs& a) {
         mbar_init(smem_u32(accum), 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == 0) {  // TMEM: 64 fp32 columns x 128 lanes for the accumulator
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(N_TILE));
+    if (warp == 0) {  // TMEM: NP blocks of NT fp32 columns x 128 lanes for the accumulators
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(TMEM_COLS));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -237,18 +244,17 @@ __device__ __forceinline__ void hmm_tc_step_body(const StepArgs& a) {
                 const uint32_t st = smem_u32(ring + (size_t)s * STAGE_BYTES), bar = smem_u32(&full[s]);
                 mbar_wait(smem_u32(&empty[s]), ((c / STAGES) & 1) ^ 1);
                 mbar_expect_tx(bar, STAGE_BYTES);
-#pragma unroll
-                for (int pc = 0; pc < NP; ++pc) {
-                    if (CL == 1) {
-                        bulk_g2s(st + pc * A_CHUNK_BYTES, op + (size_t)(pc * n_chunks + c) * (A_CHUNK_BYTES / 2), A_CHUNK_BYTES, bar);
-                    } else {
-                        constexpr uint32_t PART = A_CHUNK_BYTES / CL;  // this CTA's share of the chunk, delivered to the whole cluster
-                        bulk_g2s_mc(st + pc * A_CHUNK_BYTES + crank * PART,
-                                    op + (size_t)(pc * n_chunks + c) * (A_CHUNK_BYTES / 2) + (size_t)crank * (PART / 2), PART, bar,
-                                    (uint16_t)((1u << CL) - 1u));
-                    }
-                    bulk_g2s(st + NP * A_CHUNK_BYTES + pc * B_CHUNK_BYTES, tb + (size_t)(pc * n_chunks + c) * (B_CHUNK_BYTES / 2), B_CHUNK_BYTES, bar);
+                // the NP pieces of a chunk are contiguous in global memory (message: [tile][chunk][piece], table: [slice][chunk][piece])
+                // and in the stage: ONE bulk copy per operand and stage. The copy engine of an SM moves a 60 KB stage at
+                // 98 B/clk as one copy but at 55 B/clk as six (profiles/r02_bulk_ingest.log) - the ingest is what a step waits on.
+                if (CL == 1) {
+                    bulk_g2s(st, op + (size_t)c * NP * (A_CHUNK_BYTES / 2), NP * A_CHUNK_BYTES, bar);
+                } else {
+                    constexpr uint32_t PART = NP * A_CHUNK_BYTES / CL;  // this CTA's share of the chunk, delivered to the whole cluster
+                    bulk_g2s_mc(st + crank * PART, op + (size_t)c * NP * (A_CHUNK_BYTES / 2) + (size_t)crank * (PART / 2), PART, bar,
+                                (uint16_t)((1u << CL) - 1u));
                 }
+                bulk_g2s(st + NP * A_CHUNK_BYTES, tb + (size_t)c * NP * (B_CHUNK_BYTES / 2), NP * B_CHUNK_BYTES, bar);
             }
             stamp(a, 2);
         }
@@ -266,11 +272,9 @@ __device__ __forceinline__ void hmm_tc_step_body(const StepArgs& a) {
                 for (int ks = 0; ks < K_CHUNK / 16; ++ks) {
                     const uint32_t off = ks * 2 * LBO;  // 16 input states = 2 core matrices along K
 #pragma unroll
-                    for (int pa = 0; pa < NP; ++pa)
-#pragma unroll
-                        for (int pb = 0; pa + pb < NP; ++pb)  // message piece pa x table piece pb
-                            umma_bf16(tmem_base, smem_desc(a_base + pa * A_CHUNK_BYTES + off), smem_desc(b_base + pb * B_CHUNK_BYTES + off), IDESC,
-                                      (c | ks | pa | pb) != 0);
+                    for (int pa = 0; pa < NP; ++pa)  // message piece pa x table pieces 0 .. NP-1-pa (one operand of (NP - pa) NT rows)
+                        umma_bf16(tmem_base, smem_desc(a_base + pa * A_CHUNK_BYTES + off), smem_desc(b_base + off),
+                                  Cfg<NT, NP>::idesc((uint32_t)((NP - pa) * NT)), (c | ks) != 0 || (pa != 0));
                 }
                 if (CL == 1)
                     umma_commit(smem_u32(&empty[s]));  // frees the stage when these MMAs have read it
@@ -344,7 +348,14 @@ __device__ __forceinline__ void hmm_tc_step_body(const StepArgs& a) {
 #pragma unroll
         for (int half = 0; half < N_TILE / 32; ++half) {
             float pred[32];
-            tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(half * 32), pred);
+            tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)((NP - 1) * N_TILE + half * 32), pred);
+#pragma unroll
+            for (int blk = NP - 2; blk >= 0; --blk) {  // + the accumulator blocks of the larger table pieces, small to large
+                float more[32];
+                tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(blk * N_TILE + half * 32), more);
+#pragma unroll
+                for (int i = 0; i < 32; ++i) pred[i] += more[i];
+            }
             float4* srow = reinterpret_cast<float4*>(stage + (size_t)row * SROW + half * 32);
 #pragma unroll
             for (int i = 0; i < 8; ++i) srow[i] = make_float4(pred[4 * i], pred[4 * i + 1], pred[4 * i + 2], pred[4 * i + 3]);
@@ -354,7 +365,7 @@ __device__ __forceinline__ void hmm_tc_step_body(const StepArgs& a) {
         __nv_bfloat16* op_pc[NP];
 #pragma unroll
         for (int pc = 0; pc < NP; ++pc)
-            op_pc[pc] = a.op_out + ((size_t)tile * NP * n_chunks + (size_t)pc * n_chunks + n0 / K_CHUNK) * (A_CHUNK_BYTES / 2);
+            op_pc[pc] = a.op_out + ((size_t)tile * NP * n_chunks + (size_t)(n0 / K_CHUNK) * NP + pc) * (A_CHUNK_BYTES / 2);
 #pragma unroll
         for (int it = 0; it < ITER; ++it) {
             const int src = RPI * it + hrow, rr = warp * 32 + src, mm = tile * M_TILE + rr;
@@ -409,7 +420,7 @@ __device__ __forceinline__ void hmm_tc_step_body(const StepArgs& a) {
     __syncthreads();
     if (CL > 1) cluster_sync_all();  // no CTA leaves while a peer's commit may still arrive on its barriers
     if (threadIdx.x == 0) stamp(a, 9);
-    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(N_TILE));
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS));
 }
 template <bool FWD, int NT, int NP>
 __global__ void __launch_bounds__(THREADS, 1) k_hmm_tc_step(const StepArgs a) {
@@ -482,7 +493,7 @@ __global__ void k_hmm_tc_init(StepArgs a) {
         __nv_bfloat16* dst[NP];
 #pragma unroll
         for (int pc = 0; pc < NP; ++pc)
-            dst[pc] = a.op_out + ((size_t)tile * NP * n_chunks + (size_t)pc * n_chunks + n0 / K_CHUNK) * (A_CHUNK_BYTES / 2) + e;
+            dst[pc] = a.op_out + ((size_t)tile * NP * n_chunks + (size_t)(n0 / K_CHUNK) * NP + pc) * (A_CHUNK_BYTES / 2) + e;
         split_store8<NP>(c, dst);
     }
     a.part_out[(size_t)(0 * n_slices + slice) * a.Bpad + m] = sum_c;
@@ -518,7 +529,7 @@ inline float bf16_to_float_host(uint16_t h) {
     memcpy(&x, &u, 4);
     return x;
 }
-// table image: rows[n][k] (n = output state, k = input state), fp32 -> [slice][2][chunk][NT x 64] hi / lo in the canonical layout
+// table image: rows[n][k] (n = output state, k = input state), fp32 -> [slice][chunk][piece][NT x 64] in the canonical layout
 inline void build_table_image(const float* rows, int K, int N_TILE, int n_pieces, std::vector<uint16_t>& img) {
     const int n_chunks = K / K_CHUNK, n_slices = K / N_TILE;
     const size_t B_CHUNK_BYTES = (size_t)N_TILE * K_CHUNK * 2;
@@ -531,7 +542,7 @@ inline void build_table_image(const float* rows, int K, int N_TILE, int n_pieces
             for (int pc = 0; pc < n_pieces; ++pc) {
                 const uint16_t piece = bf16_rn_host(res);
                 res -= bf16_to_float_host(piece);
-                img[base + (size_t)(pc * n_chunks + c) * (B_CHUNK_BYTES / 2) + chunk_elem(r, kk)] = piece;
+                img[base + (size_t)(c * n_pieces + pc) * (B_CHUNK_BYTES / 2) + chunk_elem(r, kk)] = piece;
             }
         }
 }

@@ -557,6 +557,31 @@ def test_hmm64_tensor_core_variant_vs_numpy(B, T, M, monkeypatch):
         np.testing.assert_allclose(got_m[:, b, :], want_m, rtol=2e-5, atol=1e-8)
 
 
+@pytest.mark.gpu
+@pytest.mark.parametrize("B,T,M", [(1, 1, 3), (3, 2, 3), (5, 3, 4), (8, 4, 4), (9, 5, 7), (19, 37, 32), (8, 130, 100), (4, 301, 200), (11, 3000, 32)])
+def test_hmm64_both_recursions_on_tensor_cores_variant_vs_numpy(B, T, M, monkeypatch):
+    """k_hmm64_tc (CXB_HMM64_TC=1, hmm64_tc.cuh): forward and backward recursion of 8 chains in one CTA on mma.sync with
+    three-piece bf16 operands, meeting in the middle (T odd / even, T below the pipeline depth, ragged chain groups, the
+    two-step-delayed damped scaling over a long chain). Held to the north-star tolerance like the default kernel."""
+    monkeypatch.setenv("CXB_HMM64_TC", "1")
+    K = 64
+    rng = np.random.Generator(np.random.PCG64(91 + T))
+    A = rng.dirichlet(np.ones(K) * 0.3, size=K)
+    E = rng.dirichlet(np.ones(K) * 0.5, size=M).T * K
+    obs = rng.integers(0, M, size=(T, B)).astype(np.uint8)
+    hm = C.HmmBatch(B, T, K, M, dtype=cap.F32)
+    hm.set_tables(A, E)
+    hm.set_observations(obs)
+    assert hm.update_marginals() == B * (6 * T - 4)
+    got_m, got_f = hm.get_marginals(), hm.get_forward()
+    A_used = A.astype(np.float32).astype(np.float64)
+    for b in sorted({0, B // 2, B - 1}):
+        want_f, want_m = _hmm_numpy(A_used, E, obs[:, b])
+        assert_close(got_f[:, b, :], want_f, cap.F32)
+        assert_close(got_m[:, b, :], want_m, cap.F32)
+        np.testing.assert_allclose(got_m[:, b, :].sum(axis=-1), 1.0, rtol=0, atol=2e-6)
+
+
 def _pairwise_vs_oracle(oracle_api, dtype, n, edges, K, sweeps, seed=7):
     rng = np.random.Generator(np.random.PCG64(seed))
     n_tables = 5
