@@ -43,10 +43,13 @@ struct Cfg {
     // accumulates into TMEM columns [0, N): column block b ends up with sum_a msg_a tbl_b, the epilogue adds the blocks
     // (small to large). NP MMAs per 16 input states instead of NP (NP + 1) / 2 — the step was bound by the issue rate
     // of one thread's tcgen05.mma stream (~60 cycles per instruction at N = 32), not by the tensor pipe or the ingest.
-    static constexpr uint32_t TMEM_COLS = NP * NT <= 32 ? 32 : NP * NT <= 64 ? 64 : NP * NT <= 128 ? 128 : 256;
+    // TWO issuer threads take the chunks alternately, each into its own set of accumulator blocks (the epilogue adds the
+    // sets): the issue streams overlap, the tensor pipe has room for both.
+    static constexpr uint32_t SET_COLS = NP * NT;
+    static constexpr uint32_t TMEM_COLS = 2 * SET_COLS <= 32 ? 32 : 2 * SET_COLS <= 64 ? 64 : 2 * SET_COLS <= 128 ? 128 : 2 * SET_COLS <= 256 ? 256 : 512;
     static_assert(NP * NT <= 256, "accumulator blocks must fit one MMA (N <= 256)");
 };
-constexpr int THREADS = 192;  // 4 epilogue warps + producer warp + MMA warp
+constexpr int THREADS = 224;  // 4 epilogue warps + producer warp + 2 MMA issuer warps
 constexpr int MAX_K = 2048;   // any multiple of 64 up to here (both operands stream through the ring)
 constexpr uint32_t A_CHUNK_BYTES = M_TILE * K_CHUNK * 2;  // 16 KB per hi / lo
 constexpr uint32_t LBO = 128;                             // bytes between core matrices adjacent in K
@@ -114,6 +117,18 @@ __device__ __forceinline__ void umma_commit_mc(uint32_t bar, uint16_t mask) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar), "h"(mask)
                  : "memory");
 }
+__device__ __forceinline__ void tmem_ld32_issue(uint32_t taddr, uint32_t (&r)[32]) {  // no wait: several loads in flight
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+          "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
+          "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+          "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
     uint32_t r[32];
     asm volatile(
@@ -215,7 +230,7 @@ __device__ __forceinline__ void hmm_tc_step_body(const StepArgs& a) {
             mbar_init(smem_u32(&full[s]), 1);
             mbar_init(smem_u32(&empty[s]), CL);
         }
-        mbar_init(smem_u32(accum), 1);
+        mbar_init(smem_u32(accum), 2);  // both issuers commit
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 0) {  // TMEM: NP blocks of NT fp32 columns x 128 lanes for the accumulators
@@ -258,10 +273,12 @@ __device__ __forceinline__ void hmm_tc_step_body(const StepArgs& a) {
             }
             stamp(a, 2);
         }
-    } else if (warp == 5) {
-        // ===== MMA issuer: one thread, 3 x 4 tcgen05.mma per chunk (hi*hi + hi*lo + lo*hi, 4 K-steps of 16) =====
+    } else if (warp == 5 || warp == 6) {
+        // ===== MMA issuers: one thread each; issuer i takes chunks i, i + 2, ... into accumulator set i =====
         if (lane == 0) {
-            for (int c = 0; c < n_chunks; ++c) {
+            const int me = warp - 5;
+            const uint32_t tmem_set = tmem_base + (uint32_t)me * Cfg<NT, NP>::SET_COLS;
+            for (int c = me; c < n_chunks; c += 2) {
                 const int s = c % STAGES;
                 mbar_wait(smem_u32(&full[s]), (c / STAGES) & 1);
                 if (c == 0) stamp(a, 3);
@@ -273,8 +290,8 @@ __device__ __forceinline__ void hmm_tc_step_body(const StepArgs& a) {
                     const uint32_t off = ks * 2 * LBO;  // 16 input states = 2 core matrices along K
 #pragma unroll
                     for (int pa = 0; pa < NP; ++pa)  // message piece pa x table pieces 0 .. NP-1-pa (one operand of (NP - pa) NT rows)
-                        umma_bf16(tmem_base, smem_desc(a_base + pa * A_CHUNK_BYTES + off), smem_desc(b_base + off),
-                                  Cfg<NT, NP>::idesc((uint32_t)((NP - pa) * NT)), (c | ks) != 0 || (pa != 0));
+                        umma_bf16(tmem_set, smem_desc(a_base + pa * A_CHUNK_BYTES + off), smem_desc(b_base + off),
+                                  Cfg<NT, NP>::idesc((uint32_t)((NP - pa) * NT)), (c != me) || (ks != 0) || (pa != 0));
                 }
                 if (CL == 1)
                     umma_commit(smem_u32(&empty[s]));  // frees the stage when these MMAs have read it
@@ -282,7 +299,7 @@ __device__ __forceinline__ void hmm_tc_step_body(const StepArgs& a) {
                     umma_commit_mc(smem_u32(&empty[s]), (uint16_t)((1u << CL) - 1u));  // ... in every CTA that refills it
             }
             umma_commit(smem_u32(accum));
-            stamp(a, 5);
+            if (me == 0) stamp(a, 5);
         }
     } else {
         // ===== epilogue warps =====
@@ -348,13 +365,22 @@ __device__ __forceinline__ void hmm_tc_step_body(const StepArgs& a) {
 #pragma unroll
         for (int half = 0; half < N_TILE / 32; ++half) {
             float pred[32];
-            tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)((NP - 1) * N_TILE + half * 32), pred);
 #pragma unroll
-            for (int blk = NP - 2; blk >= 0; --blk) {  // + the accumulator blocks of the larger table pieces, small to large
-                float more[32];
-                tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(blk * N_TILE + half * 32), more);
+            for (int i = 0; i < 32; ++i) pred[i] = 0.0f;
 #pragma unroll
-                for (int i = 0; i < 32; ++i) pred[i] += more[i];
+            for (int set = 0; set < 2; ++set) {  // the accumulator blocks of one issuer's set are requested together
+                uint32_t blkv[NP][32];
+#pragma unroll
+                for (int blk = 0; blk < NP; ++blk)
+                    tmem_ld32_issue(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)set * Cfg<NT, NP>::SET_COLS + (uint32_t)(blk * N_TILE + half * 32), blkv[blk]);
+                tmem_ld_wait();
+#pragma unroll
+                for (int i = 0; i < 32; ++i) {
+                    float acc = __uint_as_float(blkv[NP - 1][i]);  // small to large
+#pragma unroll
+                    for (int blk = NP - 2; blk >= 0; --blk) acc += __uint_as_float(blkv[blk][i]);
+                    pred[i] += acc;
+                }
             }
             float4* srow = reinterpret_cast<float4*>(stage + (size_t)row * SROW + half * 32);
 #pragma unroll
