@@ -4,15 +4,21 @@
 // (Tbl = A forward, A^T backward), followed by the elementwise categorical rules (emission product, marginal product,
 // normalisation).  One kernel launch = one time step of every chain (the launch boundary is the only grid-wide
 // synchronisation the recursion needs):
-//   * CTA (tile, slice) owns 128 chains (MMA M) x 64 output states (MMA N) and the full reduction over K input states;
-//   * operands are bf16 "split" pairs (hi = bf16(x), lo = bf16(x - hi)); the product is accumulated in fp32 in TMEM as
-//     hi*hi + hi*lo + lo*hi (3 x tcgen05.mma.kind::f16 per 16 input states; relative error ~2^-17 per term);
-//   * both operands stream through a 4-stage shared-memory ring (192 KB in flight per SM: the bulk-copy latency, not the
-//     MMA, is what a step waits on) by 1-D bulk async copies (cp.async.bulk, completion on mbarriers) of images that are ALREADY
-//     in the canonical K-major / no-swizzle UMMA layout: the table slices are formatted once on the host, the message
-//     operand of step t+1 is written in that layout by the epilogue of step t (so nothing is converted on the way in);
+//   * CTA (tile, slice) owns 128 chains (MMA M) x NT = 32 or 64 output states and the full reduction over K input states;
+//   * operands are bf16 "split" pieces (x = p0 + p1 + p2, piece k = bf16 of what the earlier pieces left over); the product
+//     is accumulated in fp32 in TMEM from the piece products p_a q_b with a + b < 3 (fp32-level accuracy; NP = 2 pieces:
+//     ~2^-17 per term). The table pieces of a chunk lie one after the other in the stage, so message piece a meets table
+//     pieces 0 .. NP-1-a in ONE tcgen05.mma.kind::f16 of N = (NP - a) NT: NP instructions per 16 input states instead of
+//     NP (NP + 1) / 2, into NP accumulator blocks that the epilogue adds small to large;
+//   * both operands stream through a 3-stage shared-memory ring (~180 KB in flight per SM) by 1-D bulk async copies
+//     (cp.async.bulk, completion on mbarriers), ONE copy per operand and stage, of images that are ALREADY in the canonical
+//     K-major / no-swizzle UMMA layout: the table slices are formatted once on the host ([slice][chunk][piece]), the message
+//     operand of step t+1 is written in that layout ([tile][chunk][piece]) by the epilogue of step t;
 //   * warp roles: warps 0-3 epilogue (TMEM -> registers, rules, stores) and, while the MMAs run, the exact
-//     normalisation of the PREVIOUS step's output; warp 4 bulk-copy producer; warp 5 MMA issuer (one elected thread);
+//     normalisation of the PREVIOUS step's output; warp 4 bulk-copy producer; warps 5 and 6 MMA issuers (one elected
+//     thread each, alternate chunks, separate accumulator sets): what a step waits on is the issue rate of a thread's
+//     tcgen05.mma stream (~60-80 cycles per instruction at these small N; measured with the clock stamps of
+//     CXB_HMM_TC_TRACE=1), not the tensor pipe (N = 32 .. 96: 16 .. 48 cycles) and not the ingest (~77 B/clk per SM);
 //   * normalisation is deferred exactly as in the K = 64 kernel: the carried message is scaled by the power of two
 //     2^-floor(log2 sum(prev)), each step writes its unnormalised result plus per-slice row sums, and the next launch
 //     (or the finishing kernel) divides by the exact total.
@@ -250,7 +256,8 @@ __device__ __forceinline__ void hmm_tc_step_body(const StepArgs& a) {
     if (threadIdx.x == 0) stamp(a, 1);
 
     if (warp == 4) {
-        // ===== producer: bulk copies of the resident table slice and of the streamed message operand =====
+        // ===== producer: bulk copies of the table slice and of the streamed message operand (ONE thread, chunks in order: a
+        // waiter on an mbarrier may be at most one phase behind it, which two producers sharing three stages would not be) =====
         if (lane == 0) {
             const __nv_bfloat16* tb = a.tbl_img + (size_t)slice * NP * n_chunks * (B_CHUNK_BYTES / 2);
             const __nv_bfloat16* op = a.op_in + (size_t)tile * NP * n_chunks * (A_CHUNK_BYTES / 2);
@@ -274,12 +281,16 @@ __device__ __forceinline__ void hmm_tc_step_body(const StepArgs& a) {
             stamp(a, 2);
         }
     } else if (warp == 5 || warp == 6) {
-        // ===== MMA issuers: one thread each; issuer i takes chunks i, i + 2, ... into accumulator set i =====
+        // ===== MMA issuers: one thread each, its own accumulator set. A STAGE belongs to one issuer (even stages: issuer 0,
+        // odd stages: issuer 1), so the only waiter of a stage's mbarrier sees every one of its phases (a parity wait cannot
+        // tell phases two apart) =====
         if (lane == 0) {
             const int me = warp - 5;
             const uint32_t tmem_set = tmem_base + (uint32_t)me * Cfg<NT, NP>::SET_COLS;
-            for (int c = me; c < n_chunks; c += 2) {
+            bool first = true;
+            for (int c = 0; c < n_chunks; ++c) {
                 const int s = c % STAGES;
+                if ((s & 1) != me) continue;
                 mbar_wait(smem_u32(&full[s]), (c / STAGES) & 1);
                 if (c == 0) stamp(a, 3);
                 if (c == n_chunks - 1) stamp(a, 4);
@@ -291,8 +302,9 @@ __device__ __forceinline__ void hmm_tc_step_body(const StepArgs& a) {
 #pragma unroll
                     for (int pa = 0; pa < NP; ++pa)  // message piece pa x table pieces 0 .. NP-1-pa (one operand of (NP - pa) NT rows)
                         umma_bf16(tmem_set, smem_desc(a_base + pa * A_CHUNK_BYTES + off), smem_desc(b_base + off),
-                                  Cfg<NT, NP>::idesc((uint32_t)((NP - pa) * NT)), (c != me) || (ks != 0) || (pa != 0));
+                                  Cfg<NT, NP>::idesc((uint32_t)((NP - pa) * NT)), !first || (ks != 0) || (pa != 0));
                 }
+                first = false;
                 if (CL == 1)
                     umma_commit(smem_u32(&empty[s]));  // frees the stage when these MMAs have read it
                 else

@@ -1,5 +1,5 @@
-python -m pytest tests/test_device_parity.py tests/test_fullsize_parity.py -x -q -m gpu -k "tensor_core or hmm_sparse or hmm_kernels_against" 2>&1 | tail -3
-run() { echo "== $*"; env "$@" python bench.py --workload hmm512 --hmm-chains ${HC:-256} --hmm-steps 2000 --steps 2 --warmup 1 --no-cpu-baseline --others none 2>/dev/null | python -c "
+timeout 90 python -m pytest tests/test_device_parity.py tests/test_fullsize_parity.py -x -q -m gpu -k "tensor_core or hmm_sparse or hmm_kernels_against" 2>&1 | tail -3
+run() { echo "== $*"; timeout 45 env "$@" python bench.py --workload hmm512 --hmm-chains ${HC:-256} --hmm-steps 2000 --steps 2 --warmup 1 --no-cpu-baseline --others none 2>/dev/null | python -c "
 import json,sys
 for l in sys.stdin:
     l=l.strip()
@@ -9,6 +9,3 @@ for l in sys.stdin:
 export HC=256; run A=1
 run CXB_HMM_TC_NT=64
 run CXB_HMM_TC_PIECES=2
-export HC=1024; run A=1
-run CXB_HMM_TC_NT=32
-export HC=128; run A=1
