@@ -563,7 +563,7 @@ def bench_hmm64(args, pkg, rank, world, local):
         # tensor-core path: each fp32 product is 6 bf16 MMAs (3-piece split operands, hmm_tc.cuh), 2 passes per time step
         pieces = 2 if os.environ.get("CXB_HMM_TC_PIECES") == "2" else 3
         mmas = 3 if pieces == 2 else 6
-        out["kernel"] = "k_hmm_tc_step_pair (tcgen05 + TMEM; one launch per time step, forward and backward halves)"
+        out["kernel"] = "k_hmm_tc_step_pair (tcgen05 + TMEM; one launch per time step, forward and backward halves; wide-N piece products, two MMA issuers)"
         out["tensor"] = {"issued_flops": 2.0 * B * K * K * mmas * 2 * T, "fp32_equivalent_flops": 2.0 * B * K * K * 2 * T,
                          "note": f"{mmas} bf16 MMAs per fp32 product ({pieces}-piece split operands)"}
     return out
@@ -623,7 +623,8 @@ def bench_powerlaw(args, pkg, rank, world, local):
     clocks = sampler.stop()
     return {"ms": ms, "updates_per_step": upd[0] * sweeps, "kernel_ms": statistics.mean(kernel_ms), "alg_bytes": pw.algorithmic_bytes,
             "e2e_ms": e2e_ms, "e2e_steps": e2e_steps, "h2d": n * K * 4, "d2h": n * K * 4, "launches": launches,
-            "clocks": clocks, "dtype": "f32", "kernel": "k_pw_small + k_pw_hub (one sweep)", "scaling": "weak", "steps_timed": steps_timed}
+            "clocks": clocks, "dtype": "f32", "kernel": "k_pw_exact_staged + k_pw_team + k_pw_hub_scan (one sweep)", "scaling": "weak",
+            "steps_timed": steps_timed, "scatters": 2 * m}
 
 
 def bench_engine_graph(args, pkg, rank, world, local, which):
@@ -831,6 +832,18 @@ def run_workload(args, name, pkg, rank, world, local, main_record):
                                   "fp32_equivalent_tflops": r["tensor"]["fp32_equivalent_flops"] / (r["kernel_ms"] * 1e-3) / 1e12,
                                   "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained (cuBLAS bf16 8192^3, dense)",
                                   "note": r["tensor"]["note"]}
+    if name == "powerlaw" and r.get("scatters"):
+        # What the memory system gives to THIS access pattern (profiles/micro/scatter_bw.cu on a B200, profiles/r02_scatter_bw.log):
+        # random 32-byte sector scatters run at 35.1 G/s whatever else is going on (1.14 ms for the 40 M messages of a sweep),
+        # streams at 6.4 TB/s, and the two ADD (a kernel that streams 64 B and scatters 32 B per slot takes the sum of both
+        # times). The copy bandwidth above is therefore not reachable by a sweep that scatters one message per directed edge.
+        stream_gbs, scatter_gps = 6404.0, 35.1
+        stream_bytes = r["alg_bytes"] - 32 * r["scatters"] + 5 * r["scatters"]  # + the opp / tsel index streams
+        floor_ms = stream_bytes / (stream_gbs * 1e6) + r["scatters"] / (scatter_gps * 1e6)
+        rec["roofline"]["access_pattern_ceiling"] = {
+            "model": "streamed bytes / 6404 GB/s + scattered 32-byte messages / 35.1 G/s (measured, additive)",
+            "floor_ms_per_sweep": floor_ms, "frac_of_ceiling": floor_ms / r["kernel_ms"],
+            "source": "profiles/r02_scatter_bw.log (profiles/micro/scatter_bw.cu)"}
     traffic_file = ROOT / "profiles" / f"traffic_{name}.json"
     if traffic_file.exists():
         try:

@@ -1,11 +1,5 @@
-timeout 90 python -m pytest tests/test_device_parity.py tests/test_fullsize_parity.py -x -q -m gpu -k "tensor_core or hmm_sparse or hmm_kernels_against" 2>&1 | tail -3
-run() { echo "== $*"; timeout 45 env "$@" python bench.py --workload hmm512 --hmm-chains ${HC:-256} --hmm-steps 2000 --steps 2 --warmup 1 --no-cpu-baseline --others none 2>/dev/null | python -c "
-import json,sys
-for l in sys.stdin:
-    l=l.strip()
-    if l.startswith('{'):
-        d=json.loads(l); print('ms_per_step', d.get('ms_per_step'), 'value', d.get('value'))
-"; }
-export HC=256; run A=1
-run CXB_HMM_TC_NT=64
-run CXB_HMM_TC_PIECES=2
+timeout 600 python -m pytest tests -x -q -m gpu > gpurun_out/r02_gpu_tests_final.log 2>&1; tail -3 gpurun_out/r02_gpu_tests_final.log
+date +%s > gpurun_out/bench_t0
+timeout 900 python bench.py --steps 3 --warmup 3 > gpurun_out/r02_bench_final_n1.json 2> gpurun_out/r02_bench_final_n1.err; echo "bench rc=$?"
+echo "bench seconds: $(( $(date +%s) - $(cat gpurun_out/bench_t0) ))"
+tail -c 600 gpurun_out/r02_bench_final_n1.err
