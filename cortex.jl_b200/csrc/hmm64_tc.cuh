@@ -18,6 +18,10 @@
 //     Traffic: 14 K bytes per (chain, step) instead of 12 K — the kernel is latency-bound, not bandwidth-bound;
 //   * scaling and exact normalisation are off the critical path as in k_hmm64_pass: the carried message is scaled by the
 //     power of two of the previous step's sum, the exactly normalised rows leave one step late.
+// Status: parity-green, measured SLOWER than k_hmm64_pass at config-3 size (1,430 cycles per step of both recursions against
+// 2 x 605; profiles/r02_hmm64_tc_ncu.txt), so it runs only with CXB_HMM64_TC=1. Compile-time switches used for that analysis
+// (make EXTRA=-D...): CXB_H64_TRACE (clock stamps inside a step, printed by CTA 3), H64_EXP=1|2|3 (ablations: 4 MMAs per
+// step instead of 24 / no deferred sums and write-out / both - wrong values, timing only).
 // Rules (HMM): m2f(z_t, tr_t) = normalise(em_t * pred_t), marginal = normalise(fwd_t * bwd_t),
 // m2f(z_t, tr_{t-1}) = normalise(em_t * bwd_t) — the values k_hmm_pass / k_hmm64_pass produce.
 #pragma once
