@@ -832,6 +832,14 @@ def run_workload(args, name, pkg, rank, world, local, main_record):
                                   "fp32_equivalent_tflops": r["tensor"]["fp32_equivalent_flops"] / (r["kernel_ms"] * 1e-3) / 1e12,
                                   "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained (cuBLAS bf16 8192^3, dense)",
                                   "note": r["tensor"]["note"]}
+    if name == "gauss_chains" and achieved:
+        # profiles/micro/stream_mix.cu (profiles/r02_stream_mix.log): a plain grid-stride kernel that reads 1 and writes 4 planes of
+        # 8-byte elements - the chain kernel's 12 B : 52 B mix - streams at 5.57 TB/s on a B200 (1 : 6: 5.72, 2 : 3: 5.92), the
+        # 1 : 1 copy that defines `peak` at 5.8 - 6.5: write-heavy streams do not reach the copy bandwidth.
+        rec["roofline"]["access_pattern_ceiling"] = {
+            "model": "streaming kernel with the same read : write mix (1 : 4 planes of 8-byte elements), measured",
+            "ceiling_gbs": 5574.7, "frac_of_ceiling": achieved / 5574.7,
+            "source": "profiles/r02_stream_mix.log (profiles/micro/stream_mix.cu)"}
     if name == "powerlaw" and r.get("scatters"):
         # What the memory system gives to THIS access pattern (profiles/micro/scatter_bw.cu on a B200, profiles/r02_scatter_bw.log):
         # random 32-byte sector scatters run at 35.1 G/s whatever else is going on (1.14 ms for the 40 M messages of a sweep),
