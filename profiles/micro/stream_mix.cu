@@ -21,6 +21,20 @@ __global__ void k(const float2* __restrict__ src, float2* __restrict__ dst, size
         for (int w = 0; w < W; ++w) __stcs(dst + (size_t)w * n + i, make_float2(acc.x + w, acc.y));
     }
 }
+// the same with 16-byte elements (two chains per thread would give the chain kernel these)
+template <int R, int W>
+__global__ void k16(const float4* __restrict__ src, float4* __restrict__ dst, size_t n) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        float4 acc = make_float4(1.0f, 2.0f, 3.0f, 4.0f);
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            float4 v = __ldcs(src + (size_t)r * n + i);
+            acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+        }
+#pragma unroll
+        for (int w = 0; w < W; ++w) __stcs(dst + (size_t)w * n + i, make_float4(acc.x + w, acc.y, acc.z, acc.w));
+    }
+}
 int main() {
     const size_t n = (size_t)64 << 20;  // 64 Mi elements of 8 bytes = 512 MiB per plane (the chain planes: 65,536 x 1,024 x 8 B)
     float2 *src, *dst;
@@ -46,6 +60,13 @@ int main() {
     run("read 2 : write 3 (backward recursion)", [&] { k<2, 3><<<grid, blk>>>(src, dst, n); }, n * 8.0 * 5);
     run("read 0 : write 4 (write only)", [&] { k<0, 4><<<grid, blk>>>(src, dst, n); }, n * 8.0 * 4);
     run("read 4 : write 1", [&] { k<4, 1><<<grid, blk>>>(src, dst, n); }, n * 8.0 * 5);
-    run("read 4 : write 0 (read only)", [&] { k<4, 0><<<grid, blk>>>(src, dst, n); }, n * 8.0 * 4);
+    const size_t n16 = n / 2;
+    const float4* s16 = reinterpret_cast<const float4*>(src);
+    float4* d16 = reinterpret_cast<float4*>(dst);
+    run("16-byte elements, read 1 : write 1 (copy)", [&] { k16<1, 1><<<grid, blk>>>(s16, d16, n16); }, n16 * 16.0 * 2);
+    run("16-byte elements, read 4 : write 4", [&] { k16<4, 4><<<grid, blk>>>(s16, d16, n16); }, n16 * 16.0 * 8);
+    run("16-byte elements, read 1 : write 4", [&] { k16<1, 4><<<grid, blk>>>(s16, d16, n16); }, n16 * 16.0 * 5);
+    run("16-byte elements, read 2 : write 3", [&] { k16<2, 3><<<grid, blk>>>(s16, d16, n16); }, n16 * 16.0 * 5);
+    run("16-byte elements, read 1 : write 6", [&] { k16<1, 6><<<grid, blk>>>(s16, d16, n16); }, n16 * 16.0 * 7);
     return 0;
 }
