@@ -460,7 +460,7 @@ def test_hmm64_kernel_lengths_and_long_chain_vs_numpy(T, M):
 
 
 @pytest.mark.parametrize("K,B,T,M", [(128, 5, 1, 4), (128, 5, 2, 4), (128, 130, 3, 7), (256, 7, 6, 32), (512, 131, 5, 32),
-                                      (512, 3, 40, 64), (320, 9, 12, 5)])
+                                      (512, 3, 40, 64), (320, 9, 12, 5), (512, 2, 1200, 16), (192, 3, 700, 9)])
 @pytest.mark.parametrize("schedule", ["paired", "pass_after_pass", "paired_nt64", "two_pieces", "cluster4", "cluster8"])
 def test_hmm_tensor_core_kernel_vs_numpy(K, B, T, M, schedule, monkeypatch):
     """K >= 128 fp32: tcgen05 path (bf16 split operands, fp32 TMEM accumulators, one launch per time step), ragged chain
