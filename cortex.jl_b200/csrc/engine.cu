@@ -15,6 +15,8 @@
 #include <map>
 #include <memory>
 
+#include <cub/device/device_scan.cuh>
+
 #include "common.cuh"
 #include "host_graph.hpp"
 
@@ -1262,9 +1264,34 @@ __global__ void __launch_bounds__(32) k_seq(View e, T* __restrict__ val, SeqArgs
 // components l, l+G, ... . rule < 0: element-wise product of the dependencies, normalised (App. C);
 // CAT_TABLE: out[a] = sum_b psi(a,b) in[b] with the table staged in shared memory; POTTS: closed form;
 // HMM_EMIT: column of the emission table.  Normalisation by warp-shuffle reduction.
+// Dependency lists of the members of a recorded level, flattened once when the memo is committed: member i of the memo's
+// lists reads the ids src[off[i] .. off[i + 1]) (and `low[i]`: its first dependency's variable has the lower id - the table
+// orientation of CAT_TABLE). A replay then streams its indices instead of chasing list -> dep_off -> dep_ids -> svar through
+// the CSR: ncu showed 456 B of DRAM reads per m2v signal on the power-law graph, 8 x what the rule needs (every 4-byte
+// index fetched a sector of its own). Null `off`: the engine's CSR (first run of a request). Same arithmetic either way.
+struct FlatDeps {
+    const uint32_t* off;
+    const uint32_t* src;
+    const uint8_t* low;
+};
+__global__ void k_flat_count(View e, const uint32_t* list, uint32_t n, uint32_t* cnt) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) {
+        const uint32_t s = list[i];
+        cnt[i] = e.dep_off[s + 1] - e.dep_off[s];
+    }
+    if (i == n) cnt[i] = 0;
+}
+__global__ void k_flat_fill(View e, const uint32_t* list, uint32_t n, const uint32_t* off, uint32_t* src, uint8_t* low) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint32_t s = list[i], d0 = e.dep_off[s], nd = e.dep_off[s + 1] - d0, o = off[i];
+    for (uint32_t j = 0; j < nd; ++j) src[o + j] = e.dep_ids[d0 + j];
+    low[i] = (nd > 0 && e.svar[e.dep_ids[d0]] < e.svar[s]) ? 1 : 0;
+}
 template <class T, int G, int MAXC>
 __global__ void k_rule_cat(View e, T* __restrict__ val, const uint32_t* list, uint32_t n, int rule,
-                           const T* __restrict__ table, const T* __restrict__ table_t, int n_sym, T potts_w) {
+                           const T* __restrict__ table, const T* __restrict__ table_t, int n_sym, T potts_w, const FlatDeps flat) {
     extern __shared__ unsigned char smem_raw[];
     T* sh = reinterpret_cast<T*>(smem_raw);
     if (*(volatile int*)e.err_flag) return;  // refused level: no value is written (uniform for the whole grid)
@@ -1287,13 +1314,23 @@ __global__ void k_rule_cat(View e, T* __restrict__ val, const uint32_t* list, ui
     const uint32_t i = i0 + g;
     const bool active = i < n;
     uint32_t s = active ? list[i] : 0;
-    uint32_t off = active ? e.dep_off[s] : 0, nd = active ? e.dep_off[s + 1] - off : 0;
+    const uint32_t* dep_ids = flat.off ? flat.src : e.dep_ids;
+    uint32_t off = 0, nd = 0;
+    if (active) {
+        if (flat.off) {
+            off = flat.off[i];
+            nd = flat.off[i + 1] - off;
+        } else {
+            off = e.dep_off[s];
+            nd = e.dep_off[s + 1] - off;
+        }
+    }
     T acc[MAXC];
 #pragma unroll
     for (int c = 0; c < MAXC; ++c) acc[c] = T(0);
     if (active && nd == 0) atomicOr(e.err_flag, ERR_RULE_ARG);
     if (active && nd > 0) {
-        const T* a = val + (size_t)e.dep_ids[off] * K;
+        const T* a = val + (size_t)dep_ids[off] * K;
 #pragma unroll
         for (int c = 0; c < MAXC; ++c) {
             int k = lane + c * G;
@@ -1302,7 +1339,7 @@ __global__ void k_rule_cat(View e, T* __restrict__ val, const uint32_t* list, ui
     }
     if (rule < 0) {
         for (uint32_t j = 1; j < nd; ++j) {
-            const T* b = val + (size_t)e.dep_ids[off + j] * K;
+            const T* b = val + (size_t)dep_ids[off + j] * K;
 #pragma unroll
             for (int c = 0; c < MAXC; ++c) {
                 int k = lane + c * G;
@@ -1326,7 +1363,7 @@ __global__ void k_rule_cat(View e, T* __restrict__ val, const uint32_t* list, ui
         }
         __syncwarp(gmask);
         bool u_is_low = false;
-        if (active && nd > 0) u_is_low = e.svar[e.dep_ids[off]] < e.svar[s];
+        if (active && nd > 0) u_is_low = flat.off ? flat.low[i] != 0 : e.svar[dep_ids[off]] < e.svar[s];
         // u low : out[a] = sum_b psi[b][a] in[b] -> table  [b*K + a];  u high: out[a] = sum_b psi[a][b] in[b] -> table_t[b*K + a]
         const T* tb = sh_table + (u_is_low ? 0 : (size_t)K * K);
 #pragma unroll
@@ -1341,7 +1378,7 @@ __global__ void k_rule_cat(View e, T* __restrict__ val, const uint32_t* list, ui
     } else if (rule == CXB_RULE_HMM_EMIT) {
         int o = 0;
         if (active && nd > 0) {
-            o = (int)val[(size_t)e.dep_ids[off] * K];
+            o = (int)val[(size_t)dep_ids[off] * K];
             if (o < 0 || o >= n_sym) {
                 atomicOr(e.err_flag, ERR_RULE_ARG);
                 o = 0;
@@ -1543,6 +1580,9 @@ struct Memo {
     DBuf<uint8_t> pre_props, post_props;
     DBuf<uint64_t> pre_nib, post_nib;
     DBuf<uint32_t> lists, desc;  // members level by level; descriptors (level, key, count, offset)
+    DBuf<uint32_t> flat_off, flat_src;  // flattened dependency lists of the members (FlatDeps), per-level replay of categorical graphs
+    DBuf<uint8_t> flat_low;
+    bool flat_ok = false;
     std::vector<uint32_t> h_desc;
     uint32_t n_desc = 0, n_list = 0;
     cxb_update_stats stats{};
@@ -1982,6 +2022,7 @@ struct DeviceEngine {
     int key_no_rule() const { return (int)key_ftype.size() + 1; }
 
     const uint32_t* rule_list_base = nullptr;  // where the members of the level being evaluated live (frontier buffer / a memo's lists)
+    FlatDeps rule_flat{nullptr, nullptr, nullptr};  // the memo's flattened dependency lists, indexed like its lists (replay only)
     template <class T>
     int32_t launch_rules_t(uint32_t total) {
         View v = view();
@@ -2038,11 +2079,13 @@ struct DeviceEngine {
                     return CXB_ERR_BAD_ARG;
                 }
                 unsigned grid = std::min(cdiv(cnt, gpb), 148u * 8u);  // persistent: 8 blocks of 256 threads per SM
+                FlatDeps fd{nullptr, nullptr, nullptr};
+                if (rule_flat.off) fd = FlatDeps{rule_flat.off + off, rule_flat.src, rule_flat.low + off};
 #define CAT_LAUNCH(GG, MC)                                                                                        \
     do {                                                                                                          \
         if (smem > 48 * 1024)                                                                                     \
             cudaFuncSetAttribute(k_rule_cat<T, GG, MC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);   \
-        CXB_LAUNCH((k_rule_cat<T, GG, MC>), grid, threads, smem, stream, v, val, list, cnt, rule, tb, tbt, n_sym, w); \
+        CXB_LAUNCH((k_rule_cat<T, GG, MC>), grid, threads, smem, stream, v, val, list, cnt, rule, tb, tbt, n_sym, w, fd); \
     } while (0)
                 if (G == 1) CAT_LAUNCH(1, 1);
                 else if (G == 2) CAT_LAUNCH(2, 1);
@@ -2173,8 +2216,9 @@ struct DeviceEngine {
         return flags_to_status(h_flags.p[0]);
     }
 
-    int32_t launch_rules(uint32_t total, const uint32_t* list_base = nullptr) {
+    int32_t launch_rules(uint32_t total, const uint32_t* list_base = nullptr, const Memo* flat_of = nullptr) {
         rule_list_base = list_base ? list_base : d_front.p;
+        rule_flat = (flat_of && flat_of->flat_ok) ? FlatDeps{flat_of->flat_off.p, flat_of->flat_src.p, flat_of->flat_low.p} : FlatDeps{nullptr, nullptr, nullptr};
         return dtype == CXB_F32 ? launch_rules_t<float>(total) : launch_rules_t<double>(total);
     }
 
@@ -2524,6 +2568,34 @@ struct DeviceEngine {
             rec.reset();  // no room for a recording: run without
         }
     }
+    // flattened dependency lists of every recorded member (FlatDeps): count, exclusive scan, fill
+    void build_flat_deps(Memo& m) {
+        const uint32_t n = m.n_list;
+        View v = view();
+        if (m.flat_off.reserve((size_t)n + 1) != cudaSuccess || m.flat_low.reserve(n) != cudaSuccess) {
+            cudaGetLastError();
+            return;
+        }
+        k_flat_count<<<cdiv((size_t)n + 1, 256), 256, 0, stream>>>(v, m.lists.p, n, m.flat_off.p);
+        size_t tmp_bytes = 0;
+        cub::DeviceScan::ExclusiveSum(nullptr, tmp_bytes, m.flat_off.p, m.flat_off.p, (int)(n + 1), stream);
+        DBuf<unsigned char> tmp;
+        if (tmp.reserve(std::max<size_t>(tmp_bytes, 1)) != cudaSuccess) {
+            cudaGetLastError();
+            return;
+        }
+        cub::DeviceScan::ExclusiveSum(tmp.p, tmp_bytes, m.flat_off.p, m.flat_off.p, (int)(n + 1), stream);
+        uint32_t total = 0;
+        if (cudaMemcpyAsync(&total, m.flat_off.p + n, sizeof(uint32_t), cudaMemcpyDeviceToHost, stream) != cudaSuccess ||
+            cudaStreamSynchronize(stream) != cudaSuccess || m.flat_src.reserve(std::max<size_t>(total, 1)) != cudaSuccess) {
+            cudaGetLastError();
+            return;
+        }
+        k_flat_fill<<<cdiv((size_t)n, 256), 256, 0, stream>>>(v, m.lists.p, n, m.flat_off.p, m.flat_src.p, m.flat_low.p);
+        if (cudaGetLastError() != cudaSuccess) return;
+        g_kernel_launches += 2;
+        m.flat_ok = true;
+    }
     int32_t commit_recording(int64_t n, const int64_t* ids) {
         Memo& m = *rec;
         if (last_ran != CXB_SCHEDULE_LEVEL) return CXB_OK;
@@ -2538,6 +2610,8 @@ struct DeviceEngine {
         }
         if (N) CXB_CUDA(cudaMemcpyAsync(m.post_props.p, d_props.p, N, cudaMemcpyDeviceToDevice, stream));
         if (!csr.nib.empty()) CXB_CUDA(cudaMemcpyAsync(m.post_nib.p, d_nib.p, csr.nib.size() * sizeof(uint64_t), cudaMemcpyDeviceToDevice, stream));
+        if (!resident_ok() && family == CXB_FAMILY_CATEGORICAL && m.n_list > 0 && !(getenv("CXB_MEMO_FLAT") && !atoi(getenv("CXB_MEMO_FLAT"))))
+            build_flat_deps(m);  // best effort: without them the replay walks the CSR
         CXB_CUDA(cudaStreamSynchronize(stream));
         // the rollback snapshot taken before the request IS the pre-state: hand its flag buffers over
         swap_buf(m.pre_props, d_snap_props);
@@ -2548,7 +2622,7 @@ struct DeviceEngine {
         m.stats = stats;
         for (int k = 0; k < 6; ++k) m.kind_count[k] = h_kind_count.p[k];
         m.last_use = ++memo_clock;
-        m.bytes = 2 * flag_bytes() + (m.lists.cap + m.desc.cap) * sizeof(uint32_t);
+        m.bytes = 2 * flag_bytes() + (m.lists.cap + m.desc.cap + m.flat_off.cap + m.flat_src.cap) * sizeof(uint32_t) + m.flat_low.cap;
         m.plan = recognise_plan(m);
         if (memos.size() >= MAX_MEMOS) {  // evict the least recently used
             size_t lru = 0;
@@ -2642,6 +2716,10 @@ struct DeviceEngine {
         m.seq_only = true;  // the sequential result stands (stats and last_ran are update_seq's)
         m.lists.release();
         m.desc.release();
+        m.flat_off.release();
+        m.flat_src.release();
+        m.flat_low.release();
+        m.flat_ok = false;
         m.post_props.release();
         m.post_nib.release();
         m.plan = 0;
@@ -2981,7 +3059,7 @@ struct DeviceEngine {
                 h_counts.p[nk + key] = m.h_desc[4 * d + 3];
                 total += m.h_desc[4 * d + 2];
             }
-            if ((st = launch_rules(total, m.lists.p))) return st;
+            if ((st = launch_rules(total, m.lists.p, &m))) return st;
         }
         return CXB_OK;
     }
